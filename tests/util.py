@@ -1,0 +1,48 @@
+"""Shared comparison helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def to_np(x):
+    if torch.is_tensor(x):
+        return x.detach().cpu().double().numpy()
+    return np.asarray(x, dtype=np.float64)
+
+
+def rel_err(a, b):
+    """max |a-b| relative to max |b| (the tolerance BASELINE.json states is
+    'relative'; images/losses/gradients are compared on their own scale)."""
+    a, b = to_np(a), to_np(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(float(np.max(np.abs(b))), 1e-30)
+    return float(np.max(np.abs(a - b))) / scale
+
+
+def mismatch_fraction(a, b, rtol):
+    a, b = to_np(a), to_np(b)
+    scale = max(float(np.max(np.abs(b))), 1e-30)
+    return float(np.mean(np.abs(a - b) > rtol * scale))
+
+
+def assert_close(a, b, rtol, what="", max_outlier_frac=0.0, outlier_rtol=None):
+    """All elements within rtol*max|b|, except at most `max_outlier_frac` of them
+    (coordinate-floor discontinuities), which must still be
+    within `outlier_rtol`."""
+    e = rel_err(a, b)
+    if e <= rtol:
+        return e
+    if max_outlier_frac > 0.0:
+        frac = mismatch_fraction(a, b, rtol)
+        assert frac <= max_outlier_frac, "%s: %.3g of elements beyond rtol=%g (max rel err %.3g)" % (what, frac, rtol, e)
+        if outlier_rtol is not None:
+            assert e <= outlier_rtol, "%s: outlier rel err %.3g > %g" % (what, e, outlier_rtol)
+        return e
+    raise AssertionError("%s: rel err %.3g > %g" % (what, e, rtol))
