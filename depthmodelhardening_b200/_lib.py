@@ -1,0 +1,115 @@
+"""ctypes binding of the C-ABI library (include/dmh_b200.h).
+
+There is NO fallback: if `libdmh_b200.so` is missing or a tensor is not on a
+CUDA device the call raises.  Build the library with
+`python -c "import __graft_entry__ as g; g.build()"` or `make -C
+depthmodelhardening_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmh_b200.so")
+
+_f = C.c_void_p          # device float*
+_i = C.c_int
+_ll = C.c_longlong
+_fl = C.c_float
+_st = C.c_void_p         # cudaStream_t
+
+# name -> (restype, argtypes); mirrors include/dmh_b200.h one to one
+SIGNATURES = {
+    "dmh_last_error": (C.c_char_p, []),
+    "dmh_version": (_i, []),
+    "dmh_build_arch": (_i, []),
+    "dmh_disp_to_depth": (_i, [_f, _ll, _fl, _fl, _f, _f, _st]),
+    "dmh_backproject_fwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),
+    "dmh_backproject_bwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),
+    "dmh_project3d_fwd": (_i, [_f, _f, _f, _i, _i, _i, _fl, _f, _st]),
+    "dmh_project3d_bwd_blocks": (_i, [_i, _i]),
+    "dmh_project3d_bwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _fl, _f, _f, _st]),
+    "dmh_grid_sample_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_grid_sample_bwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_ssim_fwd": (_i, [_f, _f, _i, _i, _i, _i, _f, _st]),
+    "dmh_ssim_bwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_reproj_loss_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_reproj_loss_bwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_smooth_workspace_floats": (_ll, [_i, _i, _i]),
+    "dmh_smooth_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_smooth_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _f, _fl, _f, _f, _f, _st]),
+    "dmh_warp_fwd": (_i, [_f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
+    "dmh_warp_bwd_blocks": (_i, [_i, _i]),
+    "dmh_warp_bwd": (_i, [_f, _f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
+    "dmh_photo_tiles": (_i, [_i, _i]),
+    "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _f, _f, _f, _f, _i, _i, _i,
+                             _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),
+    "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "depthmodelhardening_b200: %s not found -- the CUDA extension is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().dmh_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError("dmh_b200 %s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dmh_b200: tensor is on %s; the hot path is CUDA-only (no CPU fallback)" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("dmh_b200: tensor must be contiguous")
+    if t.dtype not in (torch.float32, torch.uint8, torch.int32, torch.int64):
+        raise RuntimeError("dmh_b200: unsupported dtype %s" % t.dtype)
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (for the `*_host` arguments)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else ptr(t).value
+    return arr
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view/copy of a CUDA tensor (the reference's tensors
+    on this path are all contiguous NCHW fp32; SURVEY.md 8(b) 'Ownership')."""
+    if not t.is_cuda:
+        raise RuntimeError("dmh_b200: tensor is on %s; the hot path is CUDA-only (no CPU fallback)" % t.device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,71 @@
+// Launch plumbing shared by the kernels: error channel, argument checks,
+// block reductions.  The library never allocates: every buffer is caller-owned.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "dmh_math.cuh"
+
+namespace dmh {
+
+void set_error(const char* fmt, ...);
+
+#define DMH_REQUIRE(cond, ...)                    \
+    do {                                          \
+        if (!(cond)) {                            \
+            dmh::set_error(__VA_ARGS__);          \
+            return DMH_ERR_INVALID;               \
+        }                                         \
+    } while (0)
+
+#define DMH_CHECK_LAUNCH(name)                                                           \
+    do {                                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            dmh::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__)); \
+            return DMH_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; result valid in thread 0.  `red` needs >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = (lane < (nthreads + 31) / 32) ? red[lane] : 0.0f;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+__device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
+
+// streaming 128-bit load that does not allocate in L1 (data read once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+}  // namespace dmh

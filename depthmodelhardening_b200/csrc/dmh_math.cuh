@@ -1,0 +1,251 @@
+// Per-pixel math of the hot path, shared by every kernel.
+//
+// Everything here is `DMH_HD` (__host__ __device__) and free of CUDA-only
+// constructs so that tests/host_emul.cpp can compile the SAME formulas with g++
+// and check them against the oracle on a machine without a GPU.  The host build
+// is test infrastructure; the product only ever runs the device instantiation.
+//
+// Reference lines restated (paths under /root/reference/DepthNetworks/monodepth2):
+//   disp_to_depth            layers.py:16-25
+//   BackprojectDepth.forward layers.py:163-168
+//   Project3D.forward        layers.py:182-198
+//   F.grid_sample(border, align_corners=True)  trainer.py:515-519 (ATen GridSampler.cuh)
+//   SSIM.forward             layers.py:239-253
+//   compute_reprojection_loss trainer.py:525-537
+#pragma once
+
+#if defined(__CUDACC__)
+#define DMH_HD __host__ __device__ __forceinline__
+#else
+#define DMH_HD inline
+#endif
+
+#include <math.h>
+
+namespace dmh {
+
+// Rounded-once primitives: the coordinate chain of the reference is a sequence
+// of separate elementwise torch ops, each rounded to fp32.  Forbid FMA
+// contraction there so floor() lands on the same side as ATen's.
+#if defined(__CUDA_ARCH__)
+DMH_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+DMH_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+DMH_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+DMH_HD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+#else
+DMH_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
+DMH_HD float add_rn(float a, float b) { volatile float r = a + b; return r; }
+DMH_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
+DMH_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
+#endif
+
+// ---------------------------------------------------------------------------
+// Camera model for one batch item: P = (K @ T)[:3,:] and inv_K[:3,:3].
+struct Camera {
+    float P[12];    // row-major 3x4
+    float iK[9];    // row-major 3x3
+};
+
+// (K @ T)[:3,:], fp32 accumulate in k order (layers.py:188).
+DMH_HD void compose_camera(const float* K, const float* T, const float* inv_K, Camera& cam) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float acc = K[i * 4 + 0] * T[0 * 4 + j];
+            acc = fmaf(K[i * 4 + 1], T[1 * 4 + j], acc);
+            acc = fmaf(K[i * 4 + 2], T[2 * 4 + j], acc);
+            acc = fmaf(K[i * 4 + 3], T[3 * 4 + j], acc);
+            cam.P[i * 4 + j] = acc;
+        }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) cam.iK[i * 3 + j] = inv_K[i * 4 + j];
+}
+
+struct DepthScale {      // disp_to_depth constants, computed in double on the host
+    float min_disp;      // 1/max_depth
+    float range;         // 1/min_depth - 1/max_depth
+};
+
+DMH_HD float disp_to_depth(float disp, const DepthScale& ds) {
+    const float scaled = add_rn(ds.min_disp, mul_rn(ds.range, disp));
+    return div_rn(1.0f, scaled);
+}
+// d depth / d disp = -range * depth^2
+DMH_HD float ddepth_ddisp(float depth, const DepthScale& ds) { return -ds.range * depth * depth; }
+
+// inv_K[:3,:3] @ (x, y, 1)
+DMH_HD void pixel_ray(const Camera& cam, float x, float y, float ray[3]) {
+    for (int i = 0; i < 3; ++i) {
+        float acc = cam.iK[i * 3 + 0] * x;
+        acc = fmaf(cam.iK[i * 3 + 1], y, acc);
+        acc = add_rn(acc, cam.iK[i * 3 + 2]);
+        ray[i] = acc;
+    }
+}
+
+// P @ (X, Y, Z, 1)
+DMH_HD void project_point(const Camera& cam, const float pt[3], float p[3]) {
+    for (int i = 0; i < 3; ++i) {
+        float acc = cam.P[i * 4 + 0] * pt[0];
+        acc = fmaf(cam.P[i * 4 + 1], pt[1], acc);
+        acc = fmaf(cam.P[i * 4 + 2], pt[2], acc);
+        acc = add_rn(acc, cam.P[i * 4 + 3]);
+        p[i] = acc;
+    }
+}
+
+// Normalised sampling coordinate as Project3D returns it (layers.py:192-197).
+DMH_HD float normalise_coord(float num, float den_eps, int size) {
+    const float raw = div_rn(num, den_eps);
+    const float n = div_rn(raw, (float)(size - 1));
+    return mul_rn(sub_rn(n, 0.5f), 2.0f);
+}
+
+// ATen grid_sampler_unnormalize (align_corners True / False)
+DMH_HD float unnormalise_coord(float g, int size, bool align_corners) {
+    if (align_corners) return mul_rn(div_rn(add_rn(g, 1.0f), 2.0f), (float)(size - 1));
+    return div_rn(sub_rn(mul_rn(add_rn(g, 1.0f), (float)size), 1.0f), 2.0f);
+}
+DMH_HD float unnormalise_mult(int size, bool align_corners) {
+    return align_corners ? (float)(size - 1) / 2.0f : (float)size / 2.0f;
+}
+
+// ATen clip_coordinates_set_grad: borders count as out of bounds for the gradient.
+DMH_HD float clip_coord(float in, int size, float& grad_mult) {
+    if (in <= 0.0f) { grad_mult = 0.0f; return 0.0f; }
+    const float mx = (float)(size - 1);
+    if (in >= mx) { grad_mult = 0.0f; return mx; }
+    grad_mult = 1.0f;
+    return in;
+}
+// forward-only clip: min(size-1, max(in, 0)) with fmin/fmax NaN semantics (NaN -> 0)
+DMH_HD float clip_coord_fwd(float in, int size) { return fminf((float)(size - 1), fmaxf(in, 0.0f)); }
+
+// ATen safe_downgrade_to_int_range
+DMH_HD float safe_coord(float x) {
+    if (x > 2147483646.0f || x < -2147483648.0f || !isfinite(x)) return -100.0f;
+    return x;
+}
+
+struct Bilinear {
+    int x0, y0;            // north-west tap (may be out of bounds)
+    float wnw, wne, wsw, wse;
+    float tx1, tx0, ty1, ty0;   // (ix_se-ix), (ix-ix_nw), (iy_se-iy), (iy-iy_nw)
+};
+
+DMH_HD Bilinear bilinear_setup(float ix, float iy) {
+    Bilinear b;
+    const float fx = floorf(ix), fy = floorf(iy);
+    b.x0 = (int)fx;
+    b.y0 = (int)fy;
+    b.tx1 = (fx + 1.0f) - ix;
+    b.tx0 = ix - fx;
+    b.ty1 = (fy + 1.0f) - iy;
+    b.ty0 = iy - fy;
+    b.wnw = b.tx1 * b.ty1;
+    b.wne = b.tx0 * b.ty1;
+    b.wsw = b.tx1 * b.ty0;
+    b.wse = b.tx0 * b.ty0;
+    return b;
+}
+
+// Full forward coordinate chain of A9-A12 for target pixel (x,y) with depth d.
+struct WarpCoord {
+    float ix, iy;          // clipped source coordinates
+    float mx, my;          // d(ix)/d(gx) incl. clip gate; d(iy)/d(gy)
+    float inv_z;           // 1/(p2+eps)
+    float u_raw, v_raw;    // p0/(p2+eps), p1/(p2+eps)
+    float ray[3];
+};
+
+DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, int W, int H, float eps) {
+    WarpCoord wc;
+    pixel_ray(cam, x, y, wc.ray);
+    float pt[3] = {mul_rn(depth, wc.ray[0]), mul_rn(depth, wc.ray[1]), mul_rn(depth, wc.ray[2])};
+    float p[3];
+    project_point(cam, pt, p);
+    const float z = add_rn(p[2], eps);
+    wc.inv_z = 1.0f / z;
+    wc.u_raw = div_rn(p[0], z);
+    wc.v_raw = div_rn(p[1], z);
+    const float gx = mul_rn(sub_rn(div_rn(wc.u_raw, (float)(W - 1)), 0.5f), 2.0f);
+    const float gy = mul_rn(sub_rn(div_rn(wc.v_raw, (float)(H - 1)), 0.5f), 2.0f);
+    float cgx = 0.0f, cgy = 0.0f;
+    const float ux = unnormalise_coord(gx, W, true);
+    const float uy = unnormalise_coord(gy, H, true);
+    // NaN: ATen's forward clip is fmin/fmax, which maps NaN to 0
+    wc.ix = (ux == ux) ? safe_coord(clip_coord(ux, W, cgx)) : 0.0f;
+    wc.iy = (uy == uy) ? safe_coord(clip_coord(uy, H, cgy)) : 0.0f;
+    wc.mx = cgx * unnormalise_mult(W, true);
+    wc.my = cgy * unnormalise_mult(H, true);
+    return wc;
+}
+
+// Back-propagate d(loss)/d(ix,iy) to d(loss)/d(depth) through A12..A10.
+//   gx = 2*(u_raw/(W-1) - .5): d gx/d u_raw = 2/(W-1);  u_raw = p0/z
+// Also returns d(loss)/d(p) (for the pose gradient) in dp[3].
+DMH_HD float warp_coord_bwd(const Camera& cam, const WarpCoord& wc, float g_ix, float g_iy, int W, int H,
+                            float dp[3]) {
+    const float g_u = g_ix * wc.mx * (2.0f / (float)(W - 1));
+    const float g_v = g_iy * wc.my * (2.0f / (float)(H - 1));
+    dp[0] = g_u * wc.inv_z;
+    dp[1] = g_v * wc.inv_z;
+    dp[2] = -(g_u * wc.u_raw + g_v * wc.v_raw) * wc.inv_z;
+    float g_depth = 0.0f;
+    for (int j = 0; j < 3; ++j) {
+        const float g_pt = cam.P[0 * 4 + j] * dp[0] + cam.P[1 * 4 + j] * dp[1] + cam.P[2 * 4 + j] * dp[2];
+        g_depth = fmaf(g_pt, wc.ray[j], g_depth);
+    }
+    return g_depth;
+}
+
+// ---------------------------------------------------------------------------
+// SSIM at one pixel from the five 3x3 SUMS (not means) of x, y, x^2, y^2, xy.
+struct SsimStats {
+    float mu_x, mu_y, A1, A2, B1, B2, n, d;
+};
+#define DMH_SSIM_C1 0.0001f
+#define DMH_SSIM_C2 0.0009f
+
+DMH_HD SsimStats ssim_stats(float sx, float sy, float sxx, float syy, float sxy) {
+    SsimStats s;
+    s.mu_x = div_rn(sx, 9.0f);
+    s.mu_y = div_rn(sy, 9.0f);
+    const float sig_x = sub_rn(div_rn(sxx, 9.0f), mul_rn(s.mu_x, s.mu_x));
+    const float sig_y = sub_rn(div_rn(syy, 9.0f), mul_rn(s.mu_y, s.mu_y));
+    const float sig_xy = sub_rn(div_rn(sxy, 9.0f), mul_rn(s.mu_x, s.mu_y));
+    s.A1 = add_rn(mul_rn(mul_rn(2.0f, s.mu_x), s.mu_y), DMH_SSIM_C1);
+    s.A2 = add_rn(mul_rn(2.0f, sig_xy), DMH_SSIM_C2);
+    s.B1 = add_rn(add_rn(mul_rn(s.mu_x, s.mu_x), mul_rn(s.mu_y, s.mu_y)), DMH_SSIM_C1);
+    s.B2 = add_rn(add_rn(sig_x, sig_y), DMH_SSIM_C2);
+    s.n = mul_rn(s.A1, s.A2);
+    s.d = mul_rn(s.B1, s.B2);
+    return s;
+}
+
+// clamp((1 - n/d)/2, 0, 1); `pass` = 1 where the clamp passes gradient (inclusive).
+DMH_HD float ssim_value(const SsimStats& s, float& pass) {
+    const float v = div_rn(sub_rn(1.0f, div_rn(s.n, s.d)), 2.0f);
+    pass = (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f;
+    return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+
+// dS/dx_k = ax + bx*x_k + cx*y_k   and   dS/dy_k = ay + bx*y_k + cx*x_k
+// for every tap k of the (reflect-padded) 3x3 window -- see DESIGN.md "SSIM backward".
+struct SsimCoef { float ax, ay, b, c; };
+
+DMH_HD SsimCoef ssim_coef(const SsimStats& s) {
+    const float r = 1.0f / s.d;
+    const float nr2 = s.n * r * r;
+    const float inv9 = 1.0f / 9.0f;
+    SsimCoef k;
+    k.ax = -inv9 * (s.mu_y * (s.A2 - s.A1) * r - nr2 * s.mu_x * (s.B2 - s.B1));
+    k.ay = -inv9 * (s.mu_x * (s.A2 - s.A1) * r - nr2 * s.mu_y * (s.B2 - s.B1));
+    k.b = inv9 * nr2 * s.B1;
+    k.c = -inv9 * s.A1 * r;
+    return k;
+}
+
+// reflect index for ReflectionPad2d(1): -1 -> 1, n -> n-2 (n >= 2)
+DMH_HD int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+}  // namespace dmh

@@ -1,0 +1,461 @@
+// A9-A15 fused: ONE kernel per scale does, for a 32x16 tile of target pixels,
+//   disp -> depth -> backproject -> project -> bilinear border warp of every
+//   source frame (with a 2-px reflect halo), 3x3 SSIM + L1 reprojection loss,
+//   per-pixel min over [identity+noise, reprojection] (automask), the partial
+//   sum of to_optimise, AND the backward pass down to d(loss)/d(disp)
+//   (+ optional pose-gradient partials), without ever materialising the warped
+//   images, the SSIM maps or any autograd intermediate in HBM.
+//
+// Restates M2/trainer.py:485-519 (generate_images_pred) and :589-660
+// (compute_losses) for one scale.  The backward is emitted speculatively in the
+// forward call (the loss is a mean with a static upstream weight); the autograd
+// wrapper multiplies by the incoming scalar gradient.
+//
+// Algorithmic bytes per target pixel and scale (fp32, F source frames):
+//   read  12 (target) + 12 F (sources, gathered via L2) + 4 (disp) + 4 Fi (ident)
+//         + 4 Fi (noise);  write 4 (grad_disp)  [+1 sel]
+// Shared memory per CTA: (3 + 1 + 3F) * 720 + 9 * 612 + 612 floats (~43 KB, F=1).
+#include "../../include/dmh_b200.h"
+#include "dmh_common.cuh"
+
+using namespace dmh;
+
+namespace {
+
+#define PH_TW 32
+#define PH_TH 16
+#define PH_R2W (PH_TW + 4)
+#define PH_R2H (PH_TH + 4)
+#define PH_R1W (PH_TW + 2)
+#define PH_R1H (PH_TH + 2)
+#define PH_R2 (PH_R2W * PH_R2H)
+#define PH_R1 (PH_R1W * PH_R1H)
+#define PH_THREADS 256
+#define PH_MAXF DMH_PHOTO_MAX_FRAMES
+
+struct PhotoParams {
+    const float* target;
+    const float* src[PH_MAXF];
+    const float* T[PH_MAXF];
+    const float* disp;
+    const float* K;
+    const float* inv_K;
+    const float* ident;
+    const float* noise;
+    float* loss_partial;
+    float* grad_disp;
+    float* grad_P_partial;
+    uint8_t* sel;
+    float* warped[PH_MAXF];
+    int B, H, W, F, flags;
+    DepthScale ds;
+    float grad_scale;
+};
+
+__device__ __forceinline__ int ext_to_img(int e, int n) {
+    e = e < -1 ? -1 : (e > n ? n : e);
+    return reflect1(e, n);
+}
+__device__ __forceinline__ float reflect_mult(int p, int q, int n) {
+    float m = 1.0f;
+    if (p == 1 && q == 0) m += 1.0f;
+    if (p == n - 2 && q == n - 1) m += 1.0f;
+    return m;
+}
+
+struct Taps {
+    long long o00;
+    bool nw, ne, sw, se;
+};
+__device__ __forceinline__ Taps make_taps(const Bilinear& bl, int H, int W) {
+    Taps t;
+    const bool x0in = bl.x0 >= 0 && bl.x0 < W, x1in = bl.x0 + 1 >= 0 && bl.x0 + 1 < W;
+    const bool y0in = bl.y0 >= 0 && bl.y0 < H, y1in = bl.y0 + 1 >= 0 && bl.y0 + 1 < H;
+    t.o00 = (long long)bl.y0 * W + bl.x0;
+    t.nw = y0in && x0in; t.ne = y0in && x1in; t.sw = y1in && x0in; t.se = y1in && x1in;
+    return t;
+}
+
+// 3x3 window sums for one channel plane in shared memory (row-major, then /9
+// inside ssim_stats) around R2 position (r+1, c+1)
+__device__ __forceinline__ SsimStats window_stats(const float* __restrict__ xs, const float* __restrict__ ys, int r,
+                                                  int c) {
+    float s1 = 0.f, s2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float a = xs[(r + dy) * PH_R2W + c + dx], d = ys[(r + dy) * PH_R2W + c + dx];
+            s1 = add_rn(s1, a);
+            s2 = add_rn(s2, d);
+            s11 = add_rn(s11, mul_rn(a, a));
+            s22 = add_rn(s22, mul_rn(d, d));
+            s12 = add_rn(s12, mul_rn(a, d));
+        }
+    return ssim_stats(s1, s2, s11, s22, s12);
+}
+
+template <int F>
+__global__ void __launch_bounds__(PH_THREADS)
+photo_scale_kernel(const PhotoParams p) {
+    extern __shared__ float smem[];
+    float* tgt = smem;                          // [3][R2]
+    float* dep = tgt + 3 * PH_R2;               // [R2]
+    float* pred = dep + PH_R2;                  // [F][3][R2]
+    float* ka = pred + F * 3 * PH_R2;           // [3][R1]  gated SSIM coefficient planes
+    float* kb = ka + 3 * PH_R1;
+    float* kc = kb + 3 * PH_R1;
+    float* gl1 = kc + 3 * PH_R1;                // [R1] gate of the winning frame for the L1 term / win index
+    float* cams = gl1 + PH_R1;                  // [F][24]
+    float* red = cams + F * 24;                 // [32]
+
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * PH_TW, y0 = blockIdx.y * PH_TH;
+    const size_t N = (size_t)H * W;
+    const bool no_ssim = (p.flags & DMH_PHOTO_NO_SSIM) != 0;
+    const bool avg = (p.flags & DMH_PHOTO_AVG_REPROJECTION) != 0;
+    const bool is_depth = (p.flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
+    const float w_ssim = no_ssim ? 0.0f : 0.85f / 3.0f;
+    const float w_l1 = no_ssim ? 1.0f / 3.0f : 0.15f / 3.0f;
+
+    // ---- cameras
+    if (tid < F * 21) {
+        const int f = tid / 21, t = tid % 21;
+        if (t < 12) {
+            const int i = t / 4, j = t % 4;
+            const float* k = p.K + b * 16 + i * 4;
+            const float* tt = p.T[f] + b * 16 + j;
+            float acc = __ldg(k) * __ldg(tt);
+            acc = fmaf(__ldg(k + 1), __ldg(tt + 4), acc);
+            acc = fmaf(__ldg(k + 2), __ldg(tt + 8), acc);
+            acc = fmaf(__ldg(k + 3), __ldg(tt + 12), acc);
+            cams[f * 24 + t] = acc;
+        } else {
+            const int i = (t - 12) / 3, j = (t - 12) % 3;
+            cams[f * 24 + t] = __ldg(p.inv_K + b * 16 + i * 4 + j);
+        }
+    }
+    // ---- target tile + depth, 2-px reflect halo
+    for (int i = tid; i < PH_R2; i += PH_THREADS) {
+        const int r = i / PH_R2W, c = i % PH_R2W;
+        const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
+        const size_t o = (size_t)iy * W + ix;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) tgt[ch * PH_R2 + i] = __ldg(p.target + ((size_t)b * 3 + ch) * N + o);
+        const float dv = __ldg(p.disp + (size_t)b * N + o);
+        dep[i] = is_depth ? dv : disp_to_depth(dv, p.ds);
+    }
+    __syncthreads();
+
+    // ---- warp every source frame into shared memory
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        Camera cam;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cam.P[i] = cams[f * 24 + i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cam.iK[i] = cams[f * 24 + 12 + i];
+        const float* sp = p.src[f] + (size_t)b * 3 * N;
+        for (int i = tid; i < PH_R2; i += PH_THREADS) {
+            const int r = i / PH_R2W, c = i % PH_R2W;
+            const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
+            const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, dep[i], W, H, 1e-7f);
+            const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+            const Taps t = make_taps(bl, H, W);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* s = sp + ch * N;
+                float acc = 0.0f;
+                if (t.nw) acc = fmaf(__ldg(s + t.o00), bl.wnw, acc);
+                if (t.ne) acc = fmaf(__ldg(s + t.o00 + 1), bl.wne, acc);
+                if (t.sw) acc = fmaf(__ldg(s + t.o00 + W), bl.wsw, acc);
+                if (t.se) acc = fmaf(__ldg(s + t.o00 + W + 1), bl.wse, acc);
+                pred[(f * 3 + ch) * PH_R2 + i] = acc;
+            }
+            if (p.warped[f]) {
+                const int ey = y0 - 2 + r, ex = x0 - 2 + c;
+                if (r >= 2 && r < PH_TH + 2 && c >= 2 && c < PH_TW + 2 && ey < H && ex < W) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        p.warped[f][((size_t)b * 3 + ch) * N + (size_t)ey * W + ex] = pred[(f * 3 + ch) * PH_R2 + i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- forward loss at every valid window centre q of the 1-px ring; argmin; loss sum
+    const int Fi = p.ident ? (avg ? 1 : F) : 0;      // identity candidates
+    float loss_local = 0.0f;
+    for (int i = tid; i < PH_R1; i += PH_THREADS) {
+        const int r = i / PH_R1W, c = i % PH_R1W;
+        const int qy = y0 - 1 + r, qx = x0 - 1 + c;
+        float win = -1.0f;                           // winning source frame (or -1: identity / invalid)
+        if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+            const size_t qo = (size_t)qy * W + qx;
+            const int ci = (r + 1) * PH_R2W + (c + 1);
+            float rp[F];
+            float rp_avg = 0.f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                float l1 = 0.f, ss = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float* xs = pred + (f * 3 + ch) * PH_R2;
+                    const float* ys = tgt + ch * PH_R2;
+                    l1 = add_rn(l1, fabsf(sub_rn(ys[ci], xs[ci])));
+                    if (!no_ssim) {
+                        float pass;
+                        ss = add_rn(ss, ssim_value(window_stats(xs, ys, r, c), pass));
+                    }
+                }
+                l1 = div_rn(l1, 3.0f);
+                rp[f] = no_ssim ? l1 : add_rn(mul_rn(0.85f, div_rn(ss, 3.0f)), mul_rn(0.15f, l1));
+                rp_avg = add_rn(rp_avg, rp[f]);
+            }
+            rp_avg = div_rn(rp_avg, (float)F);
+            // candidates in the reference's cat order: identity first, then reprojection
+            float best = 3.4e38f;
+            int best_idx = 0, idx = 0;
+            if (Fi > 0) {
+                if (avg) {
+                    float s = 0.f;
+                    for (int f = 0; f < F; ++f) s = add_rn(s, __ldg(p.ident + ((size_t)b * F + f) * N + qo));
+                    float v = div_rn(s, (float)F);
+                    if (p.noise) v = add_rn(v, __ldg(p.noise + (size_t)b * N + qo));
+                    best = v; best_idx = 0; idx = 1;
+                } else {
+                    for (int f = 0; f < F; ++f) {
+                        float v = __ldg(p.ident + ((size_t)b * F + f) * N + qo);
+                        if (p.noise) v = add_rn(v, __ldg(p.noise + ((size_t)b * F + f) * N + qo));
+                        if (idx == 0 || v < best) { best = v; best_idx = idx; }
+                        ++idx;
+                    }
+                }
+            }
+            if (avg) {
+                if (idx == 0 || rp_avg < best) { best = rp_avg; best_idx = idx; win = 0.0f; }
+            } else {
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    if (idx == 0 || rp[f] < best) { best = rp[f]; best_idx = idx; win = (float)f; }
+                    ++idx;
+                }
+            }
+            const bool interior = r >= 1 && r <= PH_TH && c >= 1 && c <= PH_TW;
+            if (interior) {
+                loss_local += best;
+                if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)best_idx;
+            }
+        }
+        gl1[i] = win;
+    }
+    __syncthreads();
+
+    // ---- backward, one source frame at a time
+    float g_depth_acc[2] = {0.f, 0.f};             // this thread owns interior pixels tid and tid+256
+    float gP[F][12];
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) gP[f][k] = 0.f;
+
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        // phase A: gated SSIM coefficients of frame f at every ring position
+        for (int i = tid; i < PH_R1; i += PH_THREADS) {
+            const int r = i / PH_R1W, c = i % PH_R1W;
+            const float win = gl1[i];
+            const float gate = avg ? (win >= 0.f ? 1.0f / (float)F : 0.f) : (win == (float)f ? 1.0f : 0.f);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float a = 0.f, bq = 0.f, cq = 0.f;
+                if (gate != 0.f && !no_ssim) {
+                    const SsimStats st = window_stats(pred + (f * 3 + ch) * PH_R2, tgt + ch * PH_R2, r, c);
+                    float pass;
+                    ssim_value(st, pass);
+                    const float g = gate * w_ssim * pass;
+                    if (g != 0.f) {
+                        const SsimCoef k = ssim_coef(st);
+                        a = g * k.ax; bq = g * k.b; cq = g * k.c;
+                    }
+                }
+                ka[ch * PH_R1 + i] = a; kb[ch * PH_R1 + i] = bq; kc[ch * PH_R1 + i] = cq;
+            }
+        }
+        __syncthreads();
+        // phase B: box-sum the coefficient planes -> d/d(pred), chain through the warp
+        Camera cam;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cam.P[i] = cams[f * 24 + i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cam.iK[i] = cams[f * 24 + 12 + i];
+        const float* sp = p.src[f] + (size_t)b * 3 * N;
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+            const int i = tid + slot * PH_THREADS;
+            const int r = i / PH_TW, c = i % PH_TW;
+            const int py = y0 + r, px = x0 + c;
+            if (py >= H || px >= W) continue;
+            const int ci2 = (r + 2) * PH_R2W + (c + 2);
+            const int ci1 = (r + 1) * PH_R1W + (c + 1);
+            const float win = gl1[ci1];
+            const float gate = avg ? (win >= 0.f ? 1.0f / (float)F : 0.f) : (win == (float)f ? 1.0f : 0.f);
+            float wy[3], wx[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                wy[d] = reflect_mult(py, py - 1 + d, H);
+                wx[d] = reflect_mult(px, px - 1 + d, W);
+            }
+            float g_pred[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float sa = 0.f, sb = 0.f, sc = 0.f;
+                if (!no_ssim) {
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float w = wy[dy] * wx[dx];
+                            const int o = ch * PH_R1 + (r + dy) * PH_R1W + c + dx;
+                            sa = fmaf(w, ka[o], sa);
+                            sb = fmaf(w, kb[o], sb);
+                            sc = fmaf(w, kc[o], sc);
+                        }
+                }
+                const float xv = pred[(f * 3 + ch) * PH_R2 + ci2], yv = tgt[ch * PH_R2 + ci2];
+                const float d = xv - yv;
+                const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                g_pred[ch] = sa + sb * xv + sc * yv + gate * w_l1 * sg;
+            }
+            // chain through the bilinear gather (recomputed: taps are L1/L2 hits)
+            const WarpCoord wc = warp_coord(cam, (float)px, (float)py, dep[ci2], W, H, 1e-7f);
+            const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+            const Taps t = make_taps(bl, H, W);
+            float gix = 0.f, giy = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* s = sp + ch * N;
+                const float go = g_pred[ch];
+                if (t.nw) { const float v = __ldg(s + t.o00);         gix -= v * bl.ty1 * go; giy -= v * bl.tx1 * go; }
+                if (t.ne) { const float v = __ldg(s + t.o00 + 1);     gix += v * bl.ty1 * go; giy -= v * bl.tx0 * go; }
+                if (t.sw) { const float v = __ldg(s + t.o00 + W);     gix -= v * bl.ty0 * go; giy += v * bl.tx1 * go; }
+                if (t.se) { const float v = __ldg(s + t.o00 + W + 1); gix += v * bl.ty0 * go; giy += v * bl.tx0 * go; }
+            }
+            float dp[3];
+            g_depth_acc[slot] += warp_coord_bwd(cam, wc, gix, giy, W, H, dp);
+            if (p.grad_P_partial) {
+                const float depth = dep[ci2];
+                const float pt[4] = {depth * wc.ray[0], depth * wc.ray[1], depth * wc.ray[2], 1.0f};
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) gP[f][a * 4 + k] = fmaf(dp[a], pt[k], gP[f][a * 4 + k]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+        const int i = tid + slot * PH_THREADS;
+        const int r = i / PH_TW, c = i % PH_TW;
+        const int py = y0 + r, px = x0 + c;
+        if (py >= H || px >= W) continue;
+        const float depth = dep[(r + 2) * PH_R2W + (c + 2)];
+        const float g = g_depth_acc[slot] * p.grad_scale;
+        p.grad_disp[(size_t)b * N + (size_t)py * W + px] = is_depth ? g : g * ddepth_ddisp(depth, p.ds);
+    }
+    const int blk = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    {
+        const float s = block_sum(loss_local, red);
+        if (tid == 0) p.loss_partial[blk] = s;
+    }
+    if (p.grad_P_partial) {
+        const int tiles = gridDim.x * gridDim.y;
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            float* out = p.grad_P_partial + (((size_t)f * p.B + b) * tiles + tile) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const float s = block_sum(gP[f][k] * p.grad_scale, red);
+                if (tid == 0) out[k] = s;
+            }
+        }
+    }
+}
+
+size_t photo_smem_bytes(int F) {
+    return sizeof(float) * ((size_t)(3 + 1 + 3 * F) * PH_R2 + 9 * PH_R1 + PH_R1 + (size_t)F * 24 + 32);
+}
+
+template <int F>
+int launch_photo(const PhotoParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = photo_smem_bytes(F);
+    static bool configured_dev[64] = {false};   // idempotent attribute; racing writers set the same value
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(photo_scale_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) {
+            set_error("dmh_photo_scale: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return DMH_ERR_CUDA;
+        }
+        configured = true;
+    }
+    photo_scale_kernel<F><<<grid, PH_THREADS, smem, st>>>(p);
+    return DMH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmh_photo_tiles(int H, int W) { return ceil_div(W, PH_TW) * ceil_div(H, PH_TH); }
+
+int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
+                    const float* disp, const float* K, const float* inv_K, const float* ident, const float* noise,
+                    int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
+                    float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
+                    float* const* warped_host, dmh_stream_t stream) {
+    DMH_REQUIRE(target && src_host && T_host && disp && K && inv_K && loss_partial && grad_disp,
+                "dmh_photo_scale: null pointer");
+    DMH_REQUIRE(F >= 1 && F <= PH_MAXF, "dmh_photo_scale: F=%d outside [1,%d]", F, PH_MAXF);
+    DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "dmh_photo_scale: bad shape B=%d H=%d W=%d", B, H, W);
+    const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
+    DMH_REQUIRE(is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_photo_scale: bad depth range");
+    PhotoParams p;
+    p.target = target;
+    for (int f = 0; f < PH_MAXF; ++f) {
+        p.src[f] = f < F ? src_host[f] : nullptr;
+        p.T[f] = f < F ? T_host[f] : nullptr;
+        p.warped[f] = (warped_host && f < F) ? warped_host[f] : nullptr;
+        DMH_REQUIRE(f >= F || (p.src[f] && p.T[f]), "dmh_photo_scale: null src/T for frame %d", f);
+    }
+    p.disp = disp; p.K = K; p.inv_K = inv_K; p.ident = ident; p.noise = noise;
+    p.loss_partial = loss_partial; p.grad_disp = grad_disp; p.grad_P_partial = grad_P_partial; p.sel = sel;
+    p.B = B; p.H = H; p.W = W; p.F = F; p.flags = flags;
+    p.ds.min_disp = is_depth ? 0.f : (float)(1.0 / (double)max_depth);
+    p.ds.range = is_depth ? 0.f : (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
+    p.grad_scale = grad_scale;
+    dim3 grid(ceil_div(W, PH_TW), ceil_div(H, PH_TH), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = DMH_OK;
+    switch (F) {
+        case 1: rc = launch_photo<1>(p, grid, st); break;
+        case 2: rc = launch_photo<2>(p, grid, st); break;
+        case 3: rc = launch_photo<3>(p, grid, st); break;
+        default: rc = launch_photo<4>(p, grid, st); break;
+    }
+    if (rc != DMH_OK) return rc;
+    DMH_CHECK_LAUNCH("dmh_photo_scale");
+    return DMH_OK;
+}
+
+}  // extern "C"

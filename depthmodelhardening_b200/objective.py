@@ -1,0 +1,180 @@
+"""Fused photometric objective: host-side mirror of `Trainer.generate_images_pred`
+(`M2/trainer.py:472-523`) and `Trainer.compute_losses` (`:539-674`).
+
+`fused_generate_images_pred` / `fused_compute_losses` are unbound methods with
+the reference's signatures; `install.install()` patches them onto the
+reference's `Trainer` so `train.py --adv_train` runs unchanged.  One
+`dmh_photo_scale` launch per scale replaces ~60 ATen kernels per (scale, frame)
+forward and their autograd backward.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _frame_T(self_opt, inputs, outputs, frame_id):
+    if frame_id == "s":
+        return inputs["stereo_T"]
+    return outputs[("cam_T_cam", 0, frame_id)]
+
+
+def tie_break_noise(shape, device, mode="reference"):
+    """`M2/trainer.py:644-645`: randn * 1e-5.  'reference' draws from the CPU
+    generator exactly as the reference does (same RNG stream, one H2D copy);
+    'device' draws on the GPU (different stream, no copy)."""
+    if mode == "reference":
+        return (torch.randn(shape) * 0.00001).to(device, non_blocking=True)
+    if mode == "device":
+        return torch.randn(shape, device=device) * 0.00001
+    if mode == "none":
+        return None
+    raise ValueError("noise mode %r" % mode)
+
+
+def photometric_losses(colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids, scales, height, width,
+                       min_depth=0.1, max_depth=100.0, no_ssim=False, avg_reprojection=False,
+                       disable_automasking=False, disparity_smoothness=1e-3, noise: Optional[Dict] = None,
+                       noise_mode="reference", want_selection=False):
+    """Per-scale loop of compute_losses on the fused kernels.
+
+    colors : {(frame_id, scale): (B,3,h,w)} -- sources at scale 0, frame 0 at every scale
+    disps  : {scale: (B,1,h_s,w_s)} network outputs (grad flows here)
+    Ts     : {frame_id: (B,4,4)} (grad flows here if required)
+    noise  : optional {scale: (B,Fi,H,W)} injected tie-break noise (already * 1e-5)
+    returns (losses dict like the reference's, aux dict)
+    """
+    srcs_ids = list(frame_ids[1:])
+    target = colors[(0, 0)]
+    B = target.shape[0]
+    srcs = [colors[(f, 0)] for f in srcs_ids]
+    T_list = [Ts[f] for f in srcs_ids]
+    n_src = len(srcs)
+    losses, aux = {}, {}
+    ident = None
+    if not disable_automasking:
+        # identity reprojection loss is scale independent: once, not once per scale
+        with torch.no_grad():
+            ident = torch.cat([ops.reprojection_loss(s, target, no_ssim) for s in srcs], 1)
+    n_ident = 0 if disable_automasking else (1 if avg_reprojection else n_src)
+    total = 0
+    for scale in scales:
+        disp = disps[scale]
+        if disp.shape[2] != height or disp.shape[3] != width:
+            disp_full = F.interpolate(disp, [height, width], mode="bilinear", align_corners=False)
+        else:
+            disp_full = disp
+        nz = None
+        if n_ident:
+            if noise is not None:
+                nz = noise[scale]
+                if nz is not None and nz.shape[1] != n_ident:
+                    nz = nz[:, :n_ident].contiguous()
+            else:
+                nz = tie_break_noise((B, n_ident, height, width), target.device, noise_mode)
+        ssum, sel = ops.photo_scale_sum(disp_full, target, srcs, T_list, K, inv_K, ident=ident, noise=nz,
+                                        min_depth=min_depth, max_depth=max_depth, no_ssim=no_ssim,
+                                        avg_reprojection=avg_reprojection, want_sel=want_selection)
+        loss = ssum / float(B * height * width)
+        if sel is not None:
+            aux[("argmin", scale)] = sel
+            if n_ident:
+                aux["identity_selection/{}".format(scale)] = (sel > n_ident - 1).float()
+        sm = ops.smooth_loss(disp, colors[(0, scale)], normalise=True)
+        loss = loss + disparity_smoothness * sm / (2 ** scale)
+        losses["loss/{}".format(scale)] = loss
+        total = total + loss
+    total = total / len(scales)
+    losses["loss"] = total
+    return losses, aux
+
+
+# ----------------------------------------------------------------------------- Trainer patches
+def fused_generate_images_pred(self, inputs, outputs):
+    """Replacement for `Trainer.generate_images_pred`.  The warped images are
+    not needed by the fused loss; they are only materialised (no-grad) when the
+    trainer is about to log them (`self._dmh_materialise` set by the caller) --
+    `outputs[("depth", 0, scale)]` is always provided because
+    `compute_depth_losses` (`M2/trainer.py:676-704`) reads it."""
+    opt = self.opt
+    if opt.v1_multiscale or getattr(opt, "pose_model_type", "") == "posecnn" or opt.predictive_mask:
+        return self._dmh_ref_generate_images_pred(inputs, outputs)
+    materialise = getattr(self, "_dmh_materialise", False)
+    for scale in opt.scales:
+        disp = outputs[("disp", scale)]
+        disp_full = F.interpolate(disp, [opt.height, opt.width], mode="bilinear", align_corners=False)
+        with torch.no_grad():
+            if not materialise:
+                _, depth = ops.disp_to_depth_cuda(disp_full, opt.min_depth, opt.max_depth)
+                outputs[("depth", 0, scale)] = depth
+                continue
+            for frame_id in opt.frame_ids[1:]:
+                T = _frame_T(opt, inputs, outputs, frame_id)
+                warped, grid, depth = ops.warp_with_aux(disp_full, inputs[("color", frame_id, 0)], inputs[("K", 0)],
+                                                        inputs[("inv_K", 0)], T, opt.min_depth, opt.max_depth)
+                outputs[("depth", 0, scale)] = depth
+                outputs[("sample", frame_id, scale)] = grid
+                outputs[("color", frame_id, scale)] = warped
+                if not opt.disable_automasking:
+                    outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
+
+
+def fused_compute_losses(self, inputs, outputs):
+    """Replacement for `Trainer.compute_losses` (`M2/trainer.py:539-674`)."""
+    opt = self.opt
+    if opt.v1_multiscale or getattr(opt, "pose_model_type", "") == "posecnn" or opt.predictive_mask:
+        return self._dmh_ref_compute_losses(inputs, outputs)
+    losses = {}
+    total_loss = 0
+    # supervised / contrastive terms: network-side, stock PyTorch (outside the graft); trainer.py:545-575
+    if opt.adv_train and opt.supervised_adv:
+        disp = outputs[("disp", 0)]
+        color_ben = inputs[("color_ben", 0, 0)]
+        with torch.no_grad():
+            disp_gt = self.gt_model(color_ben)
+        if opt.gt_depth:
+            from .layers import disp_to_depth
+            color_objmask = inputs[("color_objmask", 0, 0)][:, [0], :, :]
+            objdepth = inputs[("objdepth", 0, 0)].unsqueeze(3)
+            pred_depth = torch.clamp(disp_to_depth(disp, opt.min_depth, opt.max_depth)[1] * 5.4, 1e-3, 80)
+            pseudo_depth = torch.clamp(disp_to_depth(disp_gt, opt.min_depth, opt.max_depth)[1] * 5.4, 1e-3, 80)
+            gt_depth = color_objmask * objdepth + pseudo_depth * (1 - color_objmask)
+            loss_sup = self.sup_loss_creteria(gt_depth, pred_depth)
+        else:
+            loss_sup = self.sup_loss_creteria(disp_gt, disp)
+        losses["sup_loss"] = loss_sup
+        total_loss = total_loss + loss_sup
+    if opt.adv_train and opt.contrastive_learning:
+        contras_loss = self.models["contrastive_learning"](outputs["middle_features_aug"],
+                                                           outputs["middle_features_ben"])
+        losses["contras_loss"] = contras_loss
+        total_loss = total_loss + contras_loss
+    if opt.adv_train and opt.no_original_train:
+        losses["loss"] = total_loss
+        return losses
+
+    colors = {(0, s): inputs[("color", 0, s)] for s in opt.scales}
+    colors[(0, 0)] = inputs[("color", 0, 0)]
+    Ts = {}
+    for f in opt.frame_ids[1:]:
+        colors[(f, 0)] = inputs[("color", f, 0)]
+        Ts[f] = _frame_T(opt, inputs, outputs, f)
+    disps = {s: outputs[("disp", s)] for s in opt.scales}
+    pl, aux = photometric_losses(colors, disps, inputs[("K", 0)], inputs[("inv_K", 0)], Ts, opt.frame_ids, opt.scales,
+                                 opt.height, opt.width, opt.min_depth, opt.max_depth, bool(opt.no_ssim),
+                                 bool(opt.avg_reprojection), bool(opt.disable_automasking),
+                                 opt.disparity_smoothness, noise=getattr(self, "_dmh_noise", None),
+                                 noise_mode=getattr(self, "_dmh_noise_mode", "reference"),
+                                 want_selection=getattr(self, "_dmh_materialise", False))
+    for k, v in aux.items():
+        if isinstance(k, str):
+            outputs[k] = v
+    for s in opt.scales:
+        losses["loss/{}".format(s)] = pl["loss/{}".format(s)]
+    losses["loss"] = total_loss + pl["loss"]
+    return losses

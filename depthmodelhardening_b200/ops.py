@@ -1,0 +1,351 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (stage 2).
+
+PyTorch is plumbing here: it owns the buffers (caching allocator) and the
+stream; every numeric result comes from libdmh_b200.so.  Backward passes
+recompute from the saved *inputs* -- no intermediate is kept.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, ptr_array, stream
+
+PAD_MODES = {"zeros": 0, "border": 1}
+
+
+def _lib_():
+    return _lib.load()
+
+
+# ----------------------------------------------------------------------------- A9
+def disp_to_depth_cuda(disp: torch.Tensor, min_depth: float, max_depth: float):
+    d = f32c(disp)
+    scaled = torch.empty_like(d)
+    depth = torch.empty_like(d)
+    check(_lib_().dmh_disp_to_depth(ptr(d), d.numel(), min_depth, max_depth, ptr(scaled), ptr(depth), stream()),
+          "disp_to_depth")
+    return scaled, depth
+
+
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        scaled, depth = disp_to_depth_cuda(disp, min_depth, max_depth)
+        ctx.save_for_backward(depth)
+        ctx.range = 1.0 / min_depth - 1.0 / max_depth
+        return scaled, depth
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_depth):
+        (depth,) = ctx.saved_tensors
+        g = None
+        if g_scaled is not None:
+            g = g_scaled * ctx.range
+        if g_depth is not None:
+            gd = g_depth * (-ctx.range) * depth * depth
+            g = gd if g is None else g + gd
+        return g, None, None
+
+
+# ----------------------------------------------------------------------------- A10
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, B, H, W):
+        d, ik = f32c(depth), f32c(inv_K)
+        pts = torch.empty(B, 4, H * W, device=d.device, dtype=torch.float32)
+        check(_lib_().dmh_backproject_fwd(ptr(d), ptr(ik), B, H, W, ptr(pts), stream()), "backproject_fwd")
+        ctx.save_for_backward(ik)
+        ctx.dims = (B, H, W, depth.shape)
+        return pts
+
+    @staticmethod
+    def backward(ctx, g_pts):
+        (ik,) = ctx.saved_tensors
+        B, H, W, shape = ctx.dims
+        g = f32c(g_pts)
+        gd = torch.empty(B, 1, H, W, device=g.device, dtype=torch.float32)
+        check(_lib_().dmh_backproject_bwd(ptr(g), ptr(ik), B, H, W, ptr(gd), stream()), "backproject_bwd")
+        return gd.view(shape), None, None, None, None
+
+
+# ----------------------------------------------------------------------------- A11
+class _Project3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, B, H, W, eps):
+        p, k, t = f32c(points), f32c(K), f32c(T)
+        grid = torch.empty(B, H, W, 2, device=p.device, dtype=torch.float32)
+        check(_lib_().dmh_project3d_fwd(ptr(p), ptr(k), ptr(t), B, H, W, eps, ptr(grid), stream()), "project3d_fwd")
+        ctx.save_for_backward(p, k, t)
+        ctx.dims = (B, H, W, eps)
+        return grid
+
+    @staticmethod
+    def backward(ctx, g_grid):
+        p, k, t = ctx.saved_tensors
+        B, H, W, eps = ctx.dims
+        g = f32c(g_grid)
+        need_pts = ctx.needs_input_grad[0]
+        need_kt = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        g_pts = torch.empty_like(p) if need_pts else None
+        nblk = _lib_().dmh_project3d_bwd_blocks(H, W)
+        gP_part = torch.empty(B, nblk, 12, device=g.device, dtype=torch.float32) if need_kt else None
+        check(_lib_().dmh_project3d_bwd(ptr(g), ptr(p), ptr(k), ptr(t), B, H, W, eps, ptr(g_pts), ptr(gP_part),
+                                        stream()), "project3d_bwd")
+        gK = gT = None
+        if need_kt:
+            gK, gT = _grad_KT_from_P(gP_part.sum(1).view(B, 3, 4), k, t, ctx.needs_input_grad[1],
+                                     ctx.needs_input_grad[2])
+        return g_pts, gK, gT, None, None, None, None
+
+
+def _grad_KT_from_P(gP, K, T, need_K, need_T):
+    """P = (K @ T)[:3,:]  ->  dK[:3,:] = gP @ T^T,  dT = K[:3,:]^T @ gP   (tiny 4x4 algebra)."""
+    B = gP.shape[0]
+    gK = gT = None
+    if need_K:
+        gK = torch.zeros(B, 4, 4, device=gP.device, dtype=gP.dtype)
+        gK[:, :3, :] = torch.matmul(gP, T.transpose(1, 2))
+    if need_T:
+        gT = torch.matmul(K[:, :3, :].transpose(1, 2), gP)
+    return gK, gT
+
+
+# ----------------------------------------------------------------------------- A12
+class _GridSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, grid, padding_mode, align_corners):
+        s, g = f32c(src), f32c(grid)
+        B, Cc, Hs, Ws = s.shape
+        _, Ho, Wo, _ = g.shape
+        out = torch.empty(B, Cc, Ho, Wo, device=s.device, dtype=torch.float32)
+        check(_lib_().dmh_grid_sample_fwd(ptr(s), ptr(g), B, Cc, Hs, Ws, Ho, Wo, padding_mode, int(align_corners),
+                                          ptr(out), stream()), "grid_sample_fwd")
+        ctx.save_for_backward(s, g)
+        ctx.cfg = (padding_mode, int(align_corners))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        s, g = ctx.saved_tensors
+        pm, ac = ctx.cfg
+        B, Cc, Hs, Ws = s.shape
+        _, Ho, Wo, _ = g.shape
+        go = f32c(g_out)
+        g_src = torch.zeros_like(s) if ctx.needs_input_grad[0] else None
+        g_grid = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        check(_lib_().dmh_grid_sample_bwd(ptr(go), ptr(s), ptr(g), B, Cc, Hs, Ws, Ho, Wo, pm, ac, ptr(g_src),
+                                          ptr(g_grid), stream()), "grid_sample_bwd")
+        return g_src, g_grid, None, None
+
+
+def grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=False):
+    """Bilinear `F.grid_sample` on the CUDA kernels (zeros | border padding)."""
+    if mode != "bilinear":
+        raise NotImplementedError("dmh_b200.grid_sample: only bilinear is on the hot path")
+    if padding_mode not in PAD_MODES:
+        raise NotImplementedError("dmh_b200.grid_sample: padding_mode %r unsupported" % padding_mode)
+    return _GridSample.apply(src, grid, PAD_MODES[padding_mode], bool(align_corners))
+
+
+# ----------------------------------------------------------------------------- A13
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        a, b = f32c(x), f32c(y)
+        B, Cc, H, W = a.shape
+        out = torch.empty_like(a)
+        check(_lib_().dmh_ssim_fwd(ptr(a), ptr(b), B, Cc, H, W, ptr(out), stream()), "ssim_fwd")
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        a, b = ctx.saved_tensors
+        B, Cc, H, W = a.shape
+        g = f32c(g_out)
+        gx = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(a) if ctx.needs_input_grad[1] else None
+        check(_lib_().dmh_ssim_bwd(ptr(g), ptr(a), ptr(b), B, Cc, H, W, ptr(gx), ptr(gy), stream()), "ssim_bwd")
+        return gx, gy
+
+
+# ----------------------------------------------------------------------------- A14
+class _ReprojLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, no_ssim):
+        a, b = f32c(pred), f32c(target)
+        B, Cc, H, W = a.shape
+        out = torch.empty(B, 1, H, W, device=a.device, dtype=torch.float32)
+        check(_lib_().dmh_reproj_loss_fwd(ptr(a), ptr(b), B, Cc, H, W, int(no_ssim), ptr(out), stream()),
+              "reproj_loss_fwd")
+        ctx.save_for_backward(a, b)
+        ctx.no_ssim = int(no_ssim)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        a, b = ctx.saved_tensors
+        B, Cc, H, W = a.shape
+        g = f32c(g_out)
+        gp = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gt = torch.empty_like(a) if ctx.needs_input_grad[1] else None
+        check(_lib_().dmh_reproj_loss_bwd(ptr(g), ptr(a), ptr(b), B, Cc, H, W, ctx.no_ssim, ptr(gp), ptr(gt),
+                                          stream()), "reproj_loss_bwd")
+        return gp, gt, None
+
+
+def reprojection_loss(pred, target, no_ssim=False):
+    return _ReprojLoss.apply(pred, target, bool(no_ssim))
+
+
+# ----------------------------------------------------------------------------- A16
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img, normalise):
+        d, im = f32c(disp), f32c(img)
+        B, _, h, w = d.shape
+        Cc = im.shape[1]
+        ws = torch.empty(_lib_().dmh_smooth_workspace_floats(B, h, w), device=d.device, dtype=torch.float32)
+        loss = torch.empty((), device=d.device, dtype=torch.float32)
+        check(_lib_().dmh_smooth_fwd(ptr(d), ptr(im), B, Cc, h, w, int(normalise), ptr(ws), ptr(loss), stream()),
+              "smooth_fwd")
+        ctx.save_for_backward(d, im)
+        ctx.normalise = int(normalise)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        d, im = ctx.saved_tensors
+        B, _, h, w = d.shape
+        Cc = im.shape[1]
+        ws = torch.empty(_lib_().dmh_smooth_workspace_floats(B, h, w), device=d.device, dtype=torch.float32)
+        gl = f32c(g_loss).reshape(1)
+        gd = torch.empty_like(d)
+        gi = torch.empty_like(im) if ctx.needs_input_grad[1] else None
+        check(_lib_().dmh_smooth_bwd(ptr(d), ptr(im), B, Cc, h, w, ctx.normalise, ptr(gl), 1.0, ptr(ws), ptr(gd),
+                                     ptr(gi), stream()), "smooth_bwd")
+        return gd, gi, None
+
+
+def smooth_loss(disp, img, normalise=False):
+    return _Smooth.apply(disp, img, bool(normalise))
+
+
+# ----------------------------------------------------------------------------- A9-A12 fused
+class _WarpFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, src, K, inv_K, T, min_depth, max_depth, input_is_depth):
+        d, s, k, ik, t = f32c(disp), f32c(src), f32c(K), f32c(inv_K), f32c(T)
+        B, Cc, H, W = s.shape
+        out = torch.empty_like(s)
+        check(_lib_().dmh_warp_fwd(ptr(d), int(input_is_depth), min_depth, max_depth, ptr(s), ptr(k), ptr(ik), ptr(t),
+                                   B, Cc, H, W, ptr(out), None, None, stream()), "warp_fwd")
+        ctx.save_for_backward(d, s, k, ik, t)
+        ctx.cfg = (float(min_depth), float(max_depth), int(input_is_depth), disp.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        d, s, k, ik, t = ctx.saved_tensors
+        mn, mx, isd, dshape = ctx.cfg
+        B, Cc, H, W = s.shape
+        g = f32c(g_out)
+        need_d, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_kt = ctx.needs_input_grad[2] or ctx.needs_input_grad[4]
+        gd = torch.empty_like(d) if need_d else None
+        gs = torch.zeros_like(s) if need_s else None
+        nblk = _lib_().dmh_warp_bwd_blocks(H, W)
+        gP = torch.empty(B, nblk, 12, device=g.device, dtype=torch.float32) if need_kt else None
+        check(_lib_().dmh_warp_bwd(ptr(g), ptr(d), isd, mn, mx, ptr(s), ptr(k), ptr(ik), ptr(t), B, Cc, H, W, ptr(gd),
+                                   ptr(gs), ptr(gP), stream()), "warp_bwd")
+        gK = gT = None
+        if need_kt:
+            gK, gT = _grad_KT_from_P(gP.sum(1).view(B, 3, 4), k, t, ctx.needs_input_grad[2], ctx.needs_input_grad[4])
+        return (gd.view(dshape) if gd is not None else None), gs, gK, None, gT, None, None, None
+
+
+def warp_reproject(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_is_depth=False):
+    """disp (B,1,H,W) [or depth] + src (B,C,H,W) -> src warped into the target view.
+    One gather kernel for trainer.py:485-519 (disp_to_depth, BackprojectDepth,
+    Project3D, grid_sample(border, align_corners=True))."""
+    return _WarpFused.apply(disp, src, K, inv_K, T, float(min_depth), float(max_depth), bool(input_is_depth))
+
+
+def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_is_depth=False):
+    """No-grad variant also returning the sampling grid and the depth map
+    (the tensors the reference stores in `outputs` for logging)."""
+    d, s, k, ik, t = f32c(disp), f32c(src), f32c(K), f32c(inv_K), f32c(T)
+    B, Cc, H, W = s.shape
+    out = torch.empty_like(s)
+    grid = torch.empty(B, H, W, 2, device=s.device, dtype=torch.float32)
+    depth = torch.empty(B, 1, H, W, device=s.device, dtype=torch.float32)
+    check(_lib_().dmh_warp_fwd(ptr(d), int(input_is_depth), min_depth, max_depth, ptr(s), ptr(k), ptr(ik), ptr(t),
+                               B, Cc, H, W, ptr(out), ptr(grid), ptr(depth), stream()), "warp_fwd")
+    return out, grid, depth
+
+
+# ----------------------------------------------------------------------------- A9-A15 fused
+FLAG_NO_SSIM = 1
+FLAG_AVG_REPROJECTION = 2
+FLAG_INPUT_IS_DEPTH = 4
+
+
+class _PhotoScale(torch.autograd.Function):
+    """sum over (B,H,W) of the per-pixel min-reprojection loss for one scale, with
+    its gradient w.r.t. the full-resolution disparity (and poses) produced in the
+    same kernel launch."""
+
+    @staticmethod
+    def forward(ctx, disp, target, ident, noise, K, inv_K, min_depth, max_depth, flags, want_sel, n_src, *src_and_T):
+        srcs = [f32c(t) for t in src_and_T[:n_src]]
+        Ts = [f32c(t) for t in src_and_T[n_src:]]
+        d, tg, k, ik = f32c(disp), f32c(target), f32c(K), f32c(inv_K)
+        idn = f32c(ident) if ident is not None else None
+        nz = f32c(noise) if noise is not None else None
+        B, _, H, W = tg.shape
+        lib = _lib_()
+        tiles = lib.dmh_photo_tiles(H, W)
+        part = torch.empty(B * tiles, device=d.device, dtype=torch.float32)
+        gdisp = torch.empty_like(d)
+        need_T = any(ctx.needs_input_grad[11 + n_src + i] for i in range(n_src))
+        gP = torch.empty(n_src, B, tiles, 12, device=d.device, dtype=torch.float32) if need_T else None
+        sel = torch.empty(B, H, W, device=d.device, dtype=torch.uint8) if want_sel else None
+        check(lib.dmh_photo_scale(ptr(tg), ptr_array(srcs), ptr_array(Ts), n_src, ptr(d), ptr(k), ptr(ik), ptr(idn),
+                                  ptr(nz), B, H, W, min_depth, max_depth, flags, 1.0, ptr(part), ptr(gdisp), ptr(gP),
+                                  ptr(sel), None, stream()), "photo_scale")
+        total = torch.empty((), device=d.device, dtype=torch.float32)
+        check(lib.dmh_reduce_sum(ptr(part), part.numel(), 1.0, 0, ptr(total), stream()), "reduce_sum")
+        ctx.save_for_backward(gdisp, gP, k, *Ts)
+        ctx.n_src = n_src
+        ctx.dshape = disp.shape
+        if want_sel:
+            ctx.mark_non_differentiable(sel)
+            return total, sel
+        return total, None
+
+    @staticmethod
+    def backward(ctx, g_total, _g_sel):
+        saved = ctx.saved_tensors
+        gdisp, gP, k = saved[0], saved[1], saved[2]
+        Ts = saved[3:]
+        n_src = ctx.n_src
+        g_d = (gdisp * g_total).view(ctx.dshape) if ctx.needs_input_grad[0] else None
+        g_T: List[Optional[torch.Tensor]] = [None] * n_src
+        if gP is not None:
+            gPs = gP.sum(2) * g_total            # (F,B,12)
+            for i in range(n_src):
+                if ctx.needs_input_grad[11 + n_src + i]:
+                    _, g_T[i] = _grad_KT_from_P(gPs[i].view(-1, 3, 4), k, Ts[i], False, True)
+        return (g_d, None, None, None, None, None, None, None, None, None, None) + (None,) * n_src + tuple(g_T)
+
+
+def photo_scale_sum(disp_full, target, srcs: Sequence[torch.Tensor], Ts: Sequence[torch.Tensor], K, inv_K,
+                    ident=None, noise=None, min_depth=0.1, max_depth=100.0, no_ssim=False, avg_reprojection=False,
+                    input_is_depth=False, want_sel=False):
+    flags = (FLAG_NO_SSIM if no_ssim else 0) | (FLAG_AVG_REPROJECTION if avg_reprojection else 0) | \
+            (FLAG_INPUT_IS_DEPTH if input_is_depth else 0)
+    return _PhotoScale.apply(disp_full, target, ident, noise, K, inv_K, float(min_depth), float(max_depth), flags,
+                             bool(want_sel), len(srcs), *srcs, *Ts)

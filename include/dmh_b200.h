@@ -1,0 +1,157 @@
+/* dmh_b200 -- C ABI of the B200-native hot path of DepthModelHardening.
+ *
+ * The reference has no FFI / plugin layer (it is 100 % Python):
+ * the boundary it exposes for this path is a set of Python symbols.  Each entry
+ * point below names the reference symbol(s) it replaces (paths relative to
+ * /root/reference; M2 = DepthNetworks/monodepth2, TA = torchattacks).
+ * INTEGRATION.md shows the ctypes binding and the rebinding of those symbols.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned fp32 memory (NCHW,
+ *     contiguous) unless the name ends in `_host`; the library never allocates,
+ *     frees or synchronises -- work is enqueued on `stream` and returns;
+ *   - return value: DMH_OK (0) or an error code; `dmh_last_error()` returns a
+ *     thread-local message.  Wrappers raise RuntimeError on non-zero;
+ *   - "nullable" outputs may be NULL to skip that result;
+ *   - buffers marked "accumulated" must be zeroed by the caller (atomics add);
+ *   - re-entrant: no global state except the thread-local error string.
+ */
+#ifndef DMH_B200_H
+#define DMH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef struct CUstream_st* dmh_stream_t; /* == cudaStream_t */
+
+#define DMH_OK 0
+#define DMH_ERR_INVALID 1
+#define DMH_ERR_CUDA 2
+#define DMH_ERR_UNSUPPORTED 3
+
+#define DMH_PAD_ZEROS 0
+#define DMH_PAD_BORDER 1
+
+/* -- library ------------------------------------------------------------- */
+const char* dmh_last_error(void);
+int dmh_version(void);    /* 100*major + minor */
+int dmh_build_arch(void); /* 100 == compiled for sm_100a */
+
+/* -- A9  disp_to_depth (M2/layers.py:16-25) ------------------------------ */
+int dmh_disp_to_depth(const float* disp, long long n, float min_depth, float max_depth, float* scaled_disp,
+                      float* depth, dmh_stream_t stream);
+
+/* -- A10 BackprojectDepth.forward (M2/layers.py:163-168) ------------------
+ * depth (B,1,H,W), inv_K (B,4,4) -> points (B,4,H*W) [x,y,z,1 planes]        */
+int dmh_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points,
+                        dmh_stream_t stream);
+int dmh_backproject_bwd(const float* grad_points, const float* inv_K, int B, int H, int W, float* grad_depth,
+                        dmh_stream_t stream);
+
+/* -- A11 Project3D.forward (M2/layers.py:182-198) -------------------------
+ * points (B,4,N), K,T (B,4,4) -> grid (B,H,W,2) in [-1,1] (unclamped)
+ * bwd: grad_points (B,4,N); grad_P_partial (B, nblk, 12) per-block partial sums
+ * of d/d((K@T)[:3,:]) with nblk = dmh_project3d_bwd_blocks(H,W) (nullable).      */
+int dmh_project3d_fwd(const float* points, const float* K, const float* T, int B, int H, int W, float eps,
+                      float* grid, dmh_stream_t stream);
+int dmh_project3d_bwd_blocks(int H, int W);
+int dmh_project3d_bwd(const float* grad_grid, const float* points, const float* K, const float* T, int B, int H,
+                      int W, float eps, float* grad_points, float* grad_P_partial, dmh_stream_t stream);
+
+/* -- A12 F.grid_sample bilinear (M2/trainer.py:515-519; DH/trainer.py:523) --
+ * src (B,C,Hs,Ws), grid (B,Ho,Wo,2) -> out (B,C,Ho,Wo)
+ * bwd: grad_src (accumulated, nullable), grad_grid (nullable)                  */
+int dmh_grid_sample_fwd(const float* src, const float* grid, int B, int C, int Hs, int Ws, int Ho, int Wo,
+                        int padding_mode, int align_corners, float* out, dmh_stream_t stream);
+int dmh_grid_sample_bwd(const float* grad_out, const float* src, const float* grid, int B, int C, int Hs, int Ws,
+                        int Ho, int Wo, int padding_mode, int align_corners, float* grad_src, float* grad_grid,
+                        dmh_stream_t stream);
+
+/* -- A13 SSIM.forward (M2/layers.py:239-253) ------------------------------
+ * x,y (B,C,H,W) -> out (B,C,H,W); bwd gives grad_x / grad_y (each nullable)   */
+int dmh_ssim_fwd(const float* x, const float* y, int B, int C, int H, int W, float* out, dmh_stream_t stream);
+int dmh_ssim_bwd(const float* grad_out, const float* x, const float* y, int B, int C, int H, int W, float* grad_x,
+                 float* grad_y, dmh_stream_t stream);
+
+/* -- A14 Trainer.compute_reprojection_loss (M2/trainer.py:525-537) --------
+ * pred,target (B,C,H,W) -> out (B,1,H,W) = 0.85*mean_c SSIM + 0.15*mean_c|t-p|
+ * (L1 only when no_ssim)                                                      */
+int dmh_reproj_loss_fwd(const float* pred, const float* target, int B, int C, int H, int W, int no_ssim,
+                        float* out, dmh_stream_t stream);
+int dmh_reproj_loss_bwd(const float* grad_out, const float* pred, const float* target, int B, int C, int H, int W,
+                        int no_ssim, float* grad_pred, float* grad_target, dmh_stream_t stream);
+
+/* -- A16 get_smooth_loss (M2/layers.py:207-220) + mean-normalisation
+ *        (M2/trainer.py:662-664) -------------------------------------------
+ * disp (B,1,h,w), img (B,C,h,w).  normalise != 0 divides disp by its per-image
+ * mean + 1e-7 first.  Two-phase, deterministic:
+ *   fwd : loss_out[0] = loss (device scalar); ws = workspace of
+ *         dmh_smooth_workspace_floats(B,h,w) floats
+ *   bwd : grad_disp (B,1,h,w) and optional grad_img (B,C,h,w), both scaled by
+ *         the device scalar *grad_loss (nullable -> 1) times `weight`.          */
+long long dmh_smooth_workspace_floats(int B, int h, int w);
+int dmh_smooth_fwd(const float* disp, const float* img, int B, int C, int h, int w, int normalise, float* ws,
+                   float* loss_out, dmh_stream_t stream);
+int dmh_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int w, int normalise,
+                   const float* grad_loss, float weight, float* ws, float* grad_disp, float* grad_img,
+                   dmh_stream_t stream);
+
+/* -- A9-A12 fused gather: disp -> depth -> backproject -> project -> bilinear
+ *    border warp in ONE kernel (M2/trainer.py:485-519 for one (scale, frame)).
+ * disp (B,1,H,W) full resolution (or depth when input_is_depth), src (B,C,H,W),
+ * K,inv_K,T (B,4,4) -> warped (B,C,H,W); optional grid (B,H,W,2), depth (B,1,H,W)
+ * bwd: grad_disp (B,1,H,W) [d/d(disp) or d/d(depth)], grad_src (accumulated,
+ * nullable), grad_P_partial (B, nblk, 12) nullable, nblk = dmh_warp_bwd_blocks.  */
+int dmh_warp_fwd(const float* disp, int input_is_depth, float min_depth, float max_depth, const float* src,
+                 const float* K, const float* inv_K, const float* T, int B, int C, int H, int W, float* warped,
+                 float* grid_out, float* depth_out, dmh_stream_t stream);
+int dmh_warp_bwd_blocks(int H, int W);
+int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth, float min_depth, float max_depth,
+                 const float* src, const float* K, const float* inv_K, const float* T, int B, int C, int H, int W,
+                 float* grad_disp, float* grad_src, float* grad_P_partial, dmh_stream_t stream);
+
+/* -- A9-A15 fused objective for ONE scale, forward AND backward in one pass
+ *    (M2/trainer.py:472-523 + 589-660 for one value of `scale`).
+ *
+ * target (B,3,H,W); src_host[f] device pointers to (B,3,H,W), f < F <= 4;
+ * T_host[f] device pointers to (B,4,4); disp (B,1,H,W) full-res (post
+ * F.interpolate); ident (B,F,H,W) identity reprojection losses WITHOUT noise
+ * (dmh_reproj_loss_fwd of the un-warped sources; scale independent) or NULL when
+ * automasking is disabled; noise (B,Fi,H,W) tie-break noise already scaled
+ * (nullable == zeros), Fi = avg_reprojection ? 1 : F.
+ * flags: DMH_PHOTO_*.
+ * Outputs:
+ *   loss_partial : dmh_photo_blocks(B,H,W) floats, per-CTA sums of to_optimise
+ *   grad_disp    : (B,1,H,W) = grad_scale * d(sum to_optimise)/d(disp)
+ *   grad_P_partial (nullable): (F, B, tiles, 12) per-CTA partial sums of
+ *                  grad_scale * d(sum)/d((K@T_f)[:3,:])
+ *   sel (nullable): (B,H,W) uint8 argmin index over [ident..., reproj...]
+ *   warped_host (nullable): F device pointers (nullable each) to (B,3,H,W)      */
+#define DMH_PHOTO_NO_SSIM 1
+#define DMH_PHOTO_AVG_REPROJECTION 2
+#define DMH_PHOTO_INPUT_IS_DEPTH 4
+#define DMH_PHOTO_MAX_FRAMES 4
+int dmh_photo_tiles(int H, int W);           /* CTAs per batch item */
+int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
+                    const float* disp, const float* K, const float* inv_K, const float* ident, const float* noise,
+                    int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
+                    float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
+                    float* const* warped_host, dmh_stream_t stream);
+
+/* deterministic fixed-order sum of n floats into out[0] (double accumulate),
+ * out[0] = scale * sum (+ out[0] if accumulate)                                */
+int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMH_B200_H */

@@ -1,0 +1,248 @@
+"""GPU parity: stage-2 CUDA kernels (through the C ABI / ctypes) against the
+oracle on identical seeded inputs, and against the reference goldens.
+
+Tolerances (BASELINE.json north_star): <= 1e-5 relative (fp32) on warped
+images, losses and gradients; argmin / automask selections compared exactly
+(a handful of float near-ties tolerated and reported).  Gradient tensors may
+contain isolated pixels where the sampling coordinate sits within 1 ulp of an
+integer (floor() picks the other tap pair): those are
+bounded by `max_outlier_frac`.
+"""
+import numpy as np
+import pytest
+import torch
+
+from depthmodelhardening_b200 import synth
+from oracle import photometric as OP
+from oracle.make_golden import PHOTO_CASES
+from tests.util import assert_close, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+OUTL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from depthmodelhardening_b200 import _lib
+    _lib.load()     # fails loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def test_library_is_native(dev):
+    from depthmodelhardening_b200 import _lib
+    lib = _lib.load()
+    assert lib.dmh_build_arch() == 100
+    # error channel
+    rc = lib.dmh_backproject_fwd(None, None, 1, 1, 1, None, None)
+    assert rc != 0 and b"null" in lib.dmh_last_error()
+
+
+def test_no_cpu_fallback(dev):
+    from depthmodelhardening_b200 import layers
+    with pytest.raises(RuntimeError):
+        layers.SSIM()(torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8))
+
+
+def test_layers_dropins_vs_golden(dev):
+    from depthmodelhardening_b200 import layers as L
+    g = load_golden("layers")
+    pb = synth.photo_batch(batch=2, height=48, width=80, frame_ids=(0, -1), seed=21).to(dev)
+    B, H, W = pb.batch, pb.height, pb.width
+    depth = (1.0 / (0.01 + 9.99 * pb.disp[0])).clone().requires_grad_(True)
+    bp, pj, ss = L.BackprojectDepth(B, H, W), L.Project3D(B, H, W), L.SSIM()
+    pts = bp(depth, pb.inv_K)
+    T = pb.T[-1].clone().requires_grad_(True)
+    grid = pj(pts, pb.K, T)
+    (grid * synth.randn(grid.shape, 22).to(dev)).sum().backward()
+    assert_close(pts, g["points"], TOL, "points")
+    assert_close(grid, g["grid"], TOL, "grid")
+    assert_close(depth.grad, g["grad_depth"], TOL, "grad_depth")
+    assert_close(T.grad, g["grad_T"], 1e-4, "grad_T")
+    x = pb.color[(0, 0)].clone().requires_grad_(True)
+    y = pb.color[(-1, 0)].clone().requires_grad_(True)
+    s = ss(x, y)
+    (s * synth.randn(s.shape, 23).to(dev)).sum().backward()
+    assert_close(s, g["ssim"], TOL, "ssim")
+    assert_close(x.grad, g["grad_x"], TOL, "grad_x")
+    assert_close(y.grad, g["grad_y"], TOL, "grad_y")
+    d = pb.disp[0].clone().requires_grad_(True)
+    img = pb.color[(0, 0)].clone().requires_grad_(True)
+    sm = L.get_smooth_loss(d, img)
+    sm.backward()
+    assert_close(sm, g["smooth"], TOL, "smooth")
+    assert_close(d.grad, g["grad_disp"], TOL, "smooth grad_disp")
+    assert_close(img.grad, g["grad_img"], TOL, "smooth grad_img")
+    sd, dp = L.disp_to_depth(pb.disp[0], 0.1, 100.0)
+    assert_close(sd, g["scaled_disp"], 1e-6)
+    assert_close(dp, g["depth_from_disp"], 1e-6)
+
+
+def test_backproject_batch_mismatch_raises(dev):
+    from depthmodelhardening_b200 import layers as L
+    bp = L.BackprojectDepth(4, 8, 8)
+    with pytest.raises(RuntimeError):
+        bp(torch.rand(3, 1, 8, 8, device=dev), torch.eye(4, device=dev).repeat(3, 1, 1))
+
+
+@pytest.mark.parametrize("pad,ac", [("border", True), ("zeros", True), ("zeros", False), ("border", False)])
+def test_grid_sample_vs_torch(dev, pad, ac):
+    from depthmodelhardening_b200 import ops
+    src = synth.rand((2, 5, 20, 28), 1)
+    grid = (synth.rand((2, 17, 23, 2), 2) * 2.6 - 1.3)
+    up = synth.randn((2, 5, 17, 23), 3)
+    s0 = src.clone().requires_grad_(True)
+    g0 = grid.clone().requires_grad_(True)
+    ref = torch.nn.functional.grid_sample(s0, g0, mode="bilinear", padding_mode=pad, align_corners=ac)
+    (ref * up).sum().backward()
+    s1 = src.to(dev).requires_grad_(True)
+    g1 = grid.to(dev).requires_grad_(True)
+    out = ops.grid_sample(s1, g1, padding_mode=pad, align_corners=ac)
+    (out * up.to(dev)).sum().backward()
+    assert_close(out, ref, TOL, "grid_sample")
+    assert_close(g1.grad, g0.grad, TOL, "grad_grid")
+    assert_close(s1.grad, s0.grad, TOL, "grad_src")
+
+
+def test_warp_fused_vs_oracle(dev):
+    from depthmodelhardening_b200 import ops
+    pb = synth.photo_batch(batch=2, height=96, width=160, frame_ids=(0, -1, "s"), seed=5)
+    for f in (-1, "s"):
+        d0 = pb.disp[0].clone().requires_grad_(True)
+        T0 = pb.T[f].clone().requires_grad_(True)
+        s0 = pb.color[(f, 0)].clone().requires_grad_(True)
+        ref, _, _ = OP.warp_from_disp(d0, s0, pb.K, pb.inv_K, T0, 0.1, 100.0)
+        up = synth.randn(ref.shape, 6)
+        (ref * up).sum().backward()
+        d1 = pb.disp[0].to(dev).requires_grad_(True)
+        T1 = pb.T[f].to(dev).requires_grad_(True)
+        s1 = pb.color[(f, 0)].to(dev).requires_grad_(True)
+        out = ops.warp_reproject(d1, s1, pb.K.to(dev), pb.inv_K.to(dev), T1, 0.1, 100.0)
+        (out * up.to(dev)).sum().backward()
+        assert_close(out, ref, TOL, "warped %s" % f)
+        assert_close(d1.grad, d0.grad, TOL, "grad_disp %s" % f, max_outlier_frac=OUTL)
+        assert_close(T1.grad, T0.grad, 1e-4, "grad_T %s" % f)
+        assert_close(s1.grad, s0.grad, TOL, "grad_src %s" % f)
+
+
+def test_reproj_loss_vs_oracle(dev):
+    from depthmodelhardening_b200 import ops
+    pb = synth.photo_batch(batch=2, height=40, width=72, frame_ids=(0, -1), seed=7)
+    for no_ssim in (False, True):
+        p0 = pb.color[(-1, 0)].clone().requires_grad_(True)
+        t0 = pb.color[(0, 0)].clone().requires_grad_(True)
+        ref = OP.reprojection_loss(p0, t0, no_ssim)
+        up = synth.randn(ref.shape, 8)
+        (ref * up).sum().backward()
+        p1 = pb.color[(-1, 0)].to(dev).requires_grad_(True)
+        t1 = pb.color[(0, 0)].to(dev).requires_grad_(True)
+        out = ops.reprojection_loss(p1, t1, no_ssim)
+        (out * up.to(dev)).sum().backward()
+        assert_close(out, ref, TOL, "reproj")
+        assert_close(p1.grad, p0.grad, TOL, "grad_pred")
+        assert_close(t1.grad, t0.grad, TOL, "grad_target")
+
+
+def test_smooth_normalised_vs_oracle(dev):
+    from depthmodelhardening_b200 import ops
+    pb = synth.photo_batch(batch=3, height=40, width=72, frame_ids=(0, "s"), seed=9)
+    for s in (0, 2):
+        d0 = pb.disp[s].clone().requires_grad_(True)
+        ref = OP.normalised_smooth_loss(d0, pb.color[(0, s)])
+        (ref * 0.7).backward()
+        d1 = pb.disp[s].to(dev).requires_grad_(True)
+        out = ops.smooth_loss(d1, pb.color[(0, s)].to(dev), normalise=True)
+        (out * 0.7).backward()
+        assert_close(out, ref, TOL, "smooth")
+        assert_close(d1.grad, d0.grad, TOL, "smooth grad")
+
+
+def _run_fused(pb, dev, over):
+    from depthmodelhardening_b200 import objective
+    g = pb.to(dev)
+    disps = {s: g.disp[s].clone().requires_grad_(True) for s in g.scales}
+    Ts = {k: v.clone().requires_grad_(True) for k, v in g.T.items()}
+    losses, aux = objective.photometric_losses(
+        g.color, disps, g.K, g.inv_K, Ts, g.frame_ids, g.scales, g.height, g.width,
+        no_ssim=bool(over.get("no_ssim")), avg_reprojection=bool(over.get("avg_reprojection")),
+        disable_automasking=bool(over.get("disable_automasking")), noise=g.noise, want_selection=True)
+    losses["loss"].backward()
+    return losses, aux, disps, Ts
+
+
+@pytest.mark.parametrize("name", sorted(PHOTO_CASES))
+def test_fused_objective_vs_reference_golden(dev, name):
+    skw, over = PHOTO_CASES[name]
+    pb = synth.photo_batch(**skw)
+    g = load_golden("photo_" + name)
+    losses, aux, disps, _ = _run_fused(pb, dev, over)
+    assert_close(losses["loss"], g["loss"], TOL, "loss")
+    n_ident = 0 if over.get("disable_automasking") else (1 if over.get("avg_reprojection") else len(pb.frame_ids) - 1)
+    for s in pb.scales:
+        assert_close(losses["loss/%d" % s], g["loss_%d" % s], TOL, "loss/%d" % s)
+        assert_close(disps[s].grad, g["grad_disp_%d" % s], TOL, "grad_disp_%d" % s, max_outlier_frac=OUTL,
+                     outlier_rtol=0.5)
+        if n_ident:
+            sel = (aux[("argmin", s)].cpu().numpy() > n_ident - 1).astype(np.uint8)
+            assert np.mean(sel != g["ident_sel_%d" % s]) < 1e-4
+
+
+@pytest.mark.parametrize("frame_ids,shape", [((0, "s"), (4, 192, 640)), ((0, -1, 1), (2, 96, 320)),
+                                             ((0, -1, 1, "s"), (1, 72, 200)), ((0, "s"), (2, 50, 70))])
+def test_fused_objective_vs_oracle(dev, frame_ids, shape):
+    """Config 1 of BASELINE.json (B=4, 640x192 stereo) and ragged / multi-frame cases,
+    incl. a size that is not a multiple of the tile (and where the pyramid is ragged)."""
+    B, H, W = shape
+    scales = (0, 1, 2, 3) if H % 8 == 0 and W % 8 == 0 else (0, 1)
+    pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=frame_ids, scales=scales, seed=31)
+    cast = lambda t: t.clone()
+    colors = {k: cast(v) for k, v in pb.color.items()}
+    d0 = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+    T0 = {k: v.clone().requires_grad_(True) for k, v in pb.T.items()}
+    opts = OP.default_opts(scales=list(pb.scales))
+    total, ref_losses, aux0 = OP.photometric_objective(colors, d0, pb.K, pb.inv_K, T0, pb.frame_ids, pb.noise, opts,
+                                                       return_aux=True)
+    total.backward()
+    losses, aux, disps, Ts = _run_fused(pb, dev, {})
+    assert_close(losses["loss"], total, TOL, "loss")
+    for s in pb.scales:
+        assert_close(losses["loss/%d" % s], ref_losses["loss/%d" % s], TOL, "loss/%d" % s)
+        assert_close(disps[s].grad, d0[s].grad, TOL, "grad_disp_%d" % s, max_outlier_frac=OUTL, outlier_rtol=0.5)
+        sel_ref = aux0[("argmin", s)].numpy()
+        assert np.mean(aux[("argmin", s)].cpu().numpy() != sel_ref) < 1e-4
+    for f in pb.frame_ids[1:]:
+        if f == "s":
+            continue
+        assert_close(Ts[f].grad, T0[f].grad, 2e-4, "grad_T %s" % f)
+
+
+def test_fused_full_size_properties(dev):
+    """BASELINE config 2 sizes (B=32 is sharded per GPU; here B=8 of 1024x320):
+    size-independent properties instead of an oracle run --
+      * linearity: scaling the upstream gradient scales grad_disp,
+      * identical source and target with T=I -> reprojection loss ~ 0 wins everywhere
+        without automask and grad is ~0,
+      * determinism: two runs are bit-identical (no float atomics on the loss path)."""
+    from depthmodelhardening_b200 import objective
+    pb = synth.photo_batch(batch=8, height=320, width=1024, frame_ids=(0, "s"), seed=41).to(dev)
+    def run(mult):
+        disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+        losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, pb.T, pb.frame_ids, pb.scales,
+                                                 pb.height, pb.width, noise=pb.noise)
+        (losses["loss"] * mult).backward()
+        return losses["loss"].detach(), {s: d.grad for s, d in disps.items()}
+    l1, g1 = run(1.0)
+    l2, g2 = run(1.0)
+    l3, g3 = run(3.0)
+    assert torch.equal(l1, l2)
+    for s in pb.scales:
+        assert torch.equal(g1[s], g2[s])
+        assert rel_err(g3[s], 3.0 * g1[s]) < 1e-6
+    # identity: src == target, T = I  => warped == target, loss == smoothness only
+    colors = dict(pb.color)
+    colors[("s", 0)] = colors[(0, 0)]
+    Ti = {"s": torch.eye(4, device=dev).repeat(pb.batch, 1, 1)}
+    disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+    losses, _ = objective.photometric_losses(colors, disps, pb.K, pb.inv_K, Ti, pb.frame_ids, pb.scales, pb.height,
+                                             pb.width, disable_automasking=True, disparity_smoothness=0.0)
+    assert float(losses["loss"]) < 1e-4

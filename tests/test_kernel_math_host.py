@@ -1,0 +1,121 @@
+"""CPU: the per-pixel formulas of the CUDA kernels (csrc/dmh_math.cuh), compiled
+for the host by tests/host_emul.cpp, against the oracle and the reference
+goldens.  This validates the MATH of the kernels without a GPU (coordinate
+chain, bilinear gradient, coefficient form of the SSIM backward, reflection
+multiplicities, automask argmin); the real kernels' tiling is checked by the
+`-m gpu` tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from depthmodelhardening_b200 import synth
+from oracle import photometric as OP
+from oracle.make_golden import PHOTO_CASES
+from tests.util import assert_close, load_golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+SO = os.path.join(BUILD, "libdmh_hostemu.so")
+SRC = os.path.join(HERE, "host_emul.cpp")
+HDR = os.path.join(os.path.dirname(HERE), "depthmodelhardening_b200", "csrc", "dmh_math.cuh")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(BUILD, exist_ok=True)
+    if (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-o", SO, SRC])
+    return C.CDLL(SO)
+
+
+def fp(t):
+    return t.contiguous().data_ptr()
+
+
+def vp(t):
+    return C.c_void_p(t.contiguous().data_ptr())
+
+
+def test_warp_forward_backward_math(emu):
+    pb = synth.photo_batch(batch=2, height=48, width=80, frame_ids=(0, -1), seed=3)
+    B, H, W = pb.batch, pb.height, pb.width
+    disp = pb.disp[0].clone()
+    src = pb.color[(-1, 0)].contiguous()
+    T = pb.T[-1].contiguous()
+    warped = torch.empty(B, 3, H, W)
+    emu.emu_warp_fwd(vp(disp), vp(src), vp(pb.K), vp(pb.inv_K), vp(T), B, 3, H, W, C.c_float(0.1), C.c_float(100.0),
+                     vp(warped))
+    d = disp.clone().requires_grad_(True)
+    Tr = T.clone().requires_grad_(True)
+    ref, _, _ = OP.warp_from_disp(d, src, pb.K, pb.inv_K, Tr, 0.1, 100.0)
+    assert_close(warped, ref, 1e-5, "warped")
+    up = synth.randn(ref.shape, 4)
+    (ref * up).sum().backward()
+    gd = torch.empty(B, 1, H, W)
+    gP = torch.empty(B, 12)
+    emu.emu_warp_bwd(vp(up), vp(disp), vp(src), vp(pb.K), vp(pb.inv_K), vp(T), B, 3, H, W, C.c_float(0.1),
+                     C.c_float(100.0), vp(gd), vp(gP))
+    assert_close(gd, d.grad, 1e-5, "grad_disp", max_outlier_frac=2e-3)
+    gT = torch.matmul(pb.K[:, :3, :].transpose(1, 2), gP.view(B, 3, 4))
+    assert_close(gT, Tr.grad, 1e-4, "grad_T")
+
+
+def test_ssim_coefficient_backward_math(emu):
+    g = load_golden("layers")
+    pb = synth.photo_batch(batch=2, height=48, width=80, frame_ids=(0, -1), seed=21)
+    x, y = pb.color[(0, 0)].contiguous(), pb.color[(-1, 0)].contiguous()
+    up = synth.randn(x.shape, 23)
+    out, gx, gy = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    emu.emu_ssim(vp(x), vp(y), vp(up), x.shape[0] * x.shape[1], 48, 80, vp(out), vp(gx), vp(gy))
+    assert_close(out, g["ssim"], 1e-5, "ssim")
+    assert_close(gx, g["grad_x"], 1e-5, "grad_x")
+    assert_close(gy, g["grad_y"], 1e-5, "grad_y")
+
+
+@pytest.mark.parametrize("name", sorted(PHOTO_CASES))
+def test_fused_objective_math_vs_reference_golden(emu, name):
+    skw, over = PHOTO_CASES[name]
+    pb = synth.photo_batch(**skw)
+    g = load_golden("photo_" + name)
+    B, H, W = pb.batch, pb.height, pb.width
+    srcs_ids = pb.frame_ids[1:]
+    F_ = len(srcs_ids)
+    flags = (1 if over.get("no_ssim") else 0) | (2 if over.get("avg_reprojection") else 0)
+    automask = not over.get("disable_automasking", False)
+    target = pb.color[(0, 0)].contiguous()
+    srcs = [pb.color[(f, 0)].contiguous() for f in srcs_ids]
+    Ts = [pb.T[f].contiguous() for f in srcs_ids]
+    ident = None
+    if automask:
+        ident = torch.cat([OP.reprojection_loss(s, target, bool(over.get("no_ssim"))) for s in srcs], 1).contiguous()
+    src_arr = (C.c_void_p * F_)(*[fp(s) for s in srcs])
+    T_arr = (C.c_void_p * F_)(*[fp(t) for t in Ts])
+    n_ident = 0 if not automask else (1 if over.get("avg_reprojection") else F_)
+    total = 0.0
+    for s in pb.scales:
+        dlow = pb.disp[s].clone().requires_grad_(True)
+        dfull = torch.nn.functional.interpolate(dlow, [H, W], mode="bilinear", align_corners=False)
+        nz = pb.noise[s][:, :n_ident].contiguous() if automask else None
+        loss_sum = C.c_double(0.0)
+        gd = torch.empty(B, 1, H, W)
+        sel = torch.empty(B, H, W, dtype=torch.uint8)
+        emu.emu_photo_scale(vp(target), src_arr, T_arr, F_, vp(dfull.detach()), vp(pb.K), vp(pb.inv_K),
+                            vp(ident) if automask else None, vp(nz) if automask else None, B, H, W, C.c_float(0.1),
+                            C.c_float(100.0), flags, C.byref(loss_sum), vp(gd), vp(sel), None)
+        # compose with the parts outside the fused kernel (interpolate, smoothness) via the oracle
+        sm = OP.normalised_smooth_loss(dlow, pb.color[(0, s)])
+        smw = 1e-3 / (2 ** s)
+        loss_s = loss_sum.value / (B * H * W) + smw * float(sm)
+        assert_close(loss_s, g["loss_%d" % s], 1e-5, "loss/%d" % s)
+        total += loss_s
+        (dfull * gd / (B * H * W) / len(pb.scales)).sum().backward(retain_graph=True)
+        (sm * smw / len(pb.scales)).backward()
+        assert_close(dlow.grad, g["grad_disp_%d" % s], 1e-5, "grad_disp_%d" % s, max_outlier_frac=2e-3,
+                     outlier_rtol=0.5)
+        if automask:
+            assert np.array_equal((sel.numpy() > n_ident - 1).astype(np.uint8), g["ident_sel_%d" % s])
+    assert_close(total / len(pb.scales), g["loss"], 1e-5, "loss")
