@@ -41,6 +41,8 @@ SIGNATURES = {
     "dmh_smooth_workspace_floats": (_ll, [_i, _i, _i]),
     "dmh_smooth_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_smooth_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _f, _fl, _f, _f, _f, _st]),
+    "dmh_upsample_bilinear_fwd": (_i, [_f, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_upsample_bilinear_bwd": (_i, [_f, _i, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_warp_fwd": (_i, [_f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_warp_bwd_blocks": (_i, [_i, _i]),
     "dmh_warp_bwd": (_i, [_f, _f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),

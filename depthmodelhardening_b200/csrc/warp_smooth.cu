@@ -174,11 +174,12 @@ __global__ void smooth_mean_kernel(const float* __restrict__ disp, int hw, float
     if (threadIdx.x == 0) part[b * SM_NB1 + blockIdx.x] = s;
 }
 
-__device__ __forceinline__ float image_inv_mean(const float* part, int b, int hw, int normalise) {
+// per-image denominator of trainer.py:663: mean(disp) + 1e-7 (1 when not normalising)
+__device__ __forceinline__ float image_mean_eps(const float* part, int b, int hw, int normalise) {
     if (!normalise) return 1.0f;
     float s = 0.f;
     for (int i = 0; i < SM_NB1; ++i) s += part[b * SM_NB1 + i];
-    return 1.0f / (s / (float)hw + 1e-7f);
+    return s / (float)hw + 1e-7f;
 }
 
 __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int C, size_t plane, size_t a, size_t b2) {
@@ -194,16 +195,16 @@ smooth_fwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
     __shared__ float red[32];
     const int b = blockIdx.y;
     const int hw = h * w;
-    const float inv_m = image_inv_mean(mean_part, b, hw, normalise);
+    const float m = image_mean_eps(mean_part, b, hw, normalise);
     const float* d = disp + (size_t)b * hw;
     const float* im = img + (size_t)b * C * hw;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     float sx = 0.f, sy = 0.f;
     if (n < hw) {
         const int x = n % w, y = n / w;
-        const float dn = d[n] * inv_m;
-        if (x < w - 1) sx = fabsf(dn - d[n + 1] * inv_m) * edge_weight(im, C, hw, n, n + 1);
-        if (y < h - 1) sy = fabsf(dn - d[n + w] * inv_m) * edge_weight(im, C, hw, n, n + w);
+        const float dn = div_rn(d[n], m);
+        if (x < w - 1) sx = fabsf(dn - div_rn(d[n + 1], m)) * edge_weight(im, C, hw, n, n + 1);
+        if (y < h - 1) sy = fabsf(dn - div_rn(d[n + w], m)) * edge_weight(im, C, hw, n, n + w);
     }
     sx = block_sum(sx, red);
     sy = block_sum(sy, red);
@@ -243,7 +244,7 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
     __shared__ float red[32];
     const int b = blockIdx.y;
     const int hw = h * w;
-    const float inv_m = image_inv_mean(mean_part, b, hw, normalise);
+    const float m = image_mean_eps(mean_part, b, hw, normalise);
     const float up = weight * (grad_loss ? grad_loss[0] : 1.0f);
     const float* d = disp + (size_t)b * hw;
     const float* im = img + (size_t)b * C * hw;
@@ -252,13 +253,13 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
     if (n < hw) {
         const int x = n % w, y = n / w;
         dv = d[n];
-        const float dn = dv * inv_m;
+        const float dn = div_rn(dv, m);
         float gi[8];
         const bool want_img = grad_img != nullptr && C <= 8;
         if (want_img)
             for (int c = 0; c < C; ++c) gi[c] = 0.f;
         if (x < w - 1) {
-            const float diff = dn - d[n + 1] * inv_m;
+            const float diff = dn - div_rn(d[n + 1], m);
             const float e = edge_weight(im, C, hw, n, n + 1);
             g += sgn(diff) * e * inv_nx;
             if (want_img)
@@ -266,7 +267,7 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
                     gi[c] -= fabsf(diff) * e * inv_nx / (float)C * sgn(im[c * hw + n] - im[c * hw + n + 1]);
         }
         if (x > 0) {
-            const float diff = d[n - 1] * inv_m - dn;
+            const float diff = div_rn(d[n - 1], m) - dn;
             const float e = edge_weight(im, C, hw, n - 1, n);
             g -= sgn(diff) * e * inv_nx;
             if (want_img)
@@ -274,7 +275,7 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
                     gi[c] += fabsf(diff) * e * inv_nx / (float)C * sgn(im[c * hw + n - 1] - im[c * hw + n]);
         }
         if (y < h - 1) {
-            const float diff = dn - d[n + w] * inv_m;
+            const float diff = dn - div_rn(d[n + w], m);
             const float e = edge_weight(im, C, hw, n, n + w);
             g += sgn(diff) * e * inv_ny;
             if (want_img)
@@ -282,7 +283,7 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
                     gi[c] -= fabsf(diff) * e * inv_ny / (float)C * sgn(im[c * hw + n] - im[c * hw + n + w]);
         }
         if (y > 0) {
-            const float diff = d[n - w] * inv_m - dn;
+            const float diff = div_rn(d[n - w], m) - dn;
             const float e = edge_weight(im, C, hw, n - w, n);
             g -= sgn(diff) * e * inv_ny;
             if (want_img)
@@ -290,7 +291,7 @@ smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
                     gi[c] += fabsf(diff) * e * inv_ny / (float)C * sgn(im[c * hw + n - w] - im[c * hw + n]);
         }
         g *= up;
-        gn_out[(size_t)b * hw + n] = normalise ? g : g;
+        gn_out[(size_t)b * hw + n] = g;
         if (want_img)
             for (int c = 0; c < C; ++c) grad_img[((size_t)b * C + c) * hw + n] = gi[c] * up;
     }
@@ -307,7 +308,7 @@ smooth_bwd_finalize_kernel(int hw, int nblk, const float* __restrict__ mean_part
     __shared__ float s_corr, s_invm;
     const int b = blockIdx.y;
     if (threadIdx.x == 0) {
-        const float inv_m = image_inv_mean(mean_part, b, hw, 1);
+        const float inv_m = 1.0f / image_mean_eps(mean_part, b, hw, 1);
         double s = 0.0;
         for (int i = 0; i < nblk; ++i) s += (double)gd_part[(size_t)b * nblk + i];
         s_invm = inv_m;
@@ -319,6 +320,63 @@ smooth_bwd_finalize_kernel(int hw, int nblk, const float* __restrict__ mean_part
         float* g = grad_disp + (size_t)b * hw + n;
         *g = *g * s_invm - s_corr;
     }
+}
+
+
+// ---------------------------------------------------------------------------- bilinear up-sample
+// F.interpolate(disp, [H,W], mode="bilinear", align_corners=False) of trainer.py:481-482
+// (ATen upsample_bilinear2d: src = max(scale*(dst+0.5)-0.5, 0)), forward and a
+// DETERMINISTIC gather backward (ATen's CUDA backward scatters with atomics).
+struct UpTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ UpTap up_tap(int dst, float scale, int in_size) {
+    UpTap t;
+    const float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.0f);
+    t.i0 = min((int)src, in_size - 1);
+    t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
+    t.l1 = src - (float)t.i0;
+    t.l0 = 1.0f - t.l1;
+    return t;
+}
+
+__global__ void upsample_fwd_kernel(const float* __restrict__ in, int h, int w, int H, int W, float sh, float sw,
+                                    float* __restrict__ out) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= W || Y >= H) return;
+    const float* p = in + (size_t)blockIdx.z * h * w;
+    const UpTap ty = up_tap(Y, sh, h), tx = up_tap(X, sw, w);
+    const float v = ty.l0 * (tx.l0 * __ldg(p + ty.i0 * w + tx.i0) + tx.l1 * __ldg(p + ty.i0 * w + tx.i1)) +
+                    ty.l1 * (tx.l0 * __ldg(p + ty.i1 * w + tx.i0) + tx.l1 * __ldg(p + ty.i1 * w + tx.i1));
+    out[(size_t)blockIdx.z * H * W + (size_t)Y * W + X] = v;
+}
+
+// one thread per LOW-res pixel gathers every high-res pixel that read it
+__global__ void upsample_bwd_kernel(const float* __restrict__ gout, int h, int w, int H, int W, float sh, float sw,
+                                    const float* __restrict__ gscale, float* __restrict__ gin) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float* g = gout + (size_t)blockIdx.z * H * W;
+    const float rh = 1.0f / sh, rw = 1.0f / sw;
+    const int Y0 = max(0, (int)floorf(((float)y - 0.5f) * rh - 0.5f) - 1);
+    const int Y1 = min(H - 1, (int)ceilf(((float)y + 1.5f) * rh - 0.5f) + 1);
+    const int X0 = max(0, (int)floorf(((float)x - 0.5f) * rw - 0.5f) - 1);
+    const int X1 = min(W - 1, (int)ceilf(((float)x + 1.5f) * rw - 0.5f) + 1);
+    float acc = 0.0f;
+    for (int Y = Y0; Y <= Y1; ++Y) {
+        const UpTap ty = up_tap(Y, sh, h);
+        const float wy = (ty.i0 == y ? ty.l0 : 0.0f) + (ty.i1 == y ? ty.l1 : 0.0f);
+        if (wy == 0.0f) continue;
+        float row = 0.0f;
+        for (int X = X0; X <= X1; ++X) {
+            const UpTap tx = up_tap(X, sw, w);
+            const float wx = (tx.i0 == x ? tx.l0 : 0.0f) + (tx.i1 == x ? tx.l1 : 0.0f);
+            if (wx != 0.0f) row = fmaf(wx, __ldg(g + (size_t)Y * W + X), row);
+        }
+        acc = fmaf(wy, row, acc);
+    }
+    if (gscale) acc *= gscale[0];
+    gin[(size_t)blockIdx.z * h * w + (size_t)y * w + x] = acc;
 }
 
 // ---------------------------------------------------------------------------- reduce
@@ -427,6 +485,28 @@ int dmh_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int
     if (normalise)
         smooth_bwd_finalize_kernel<<<dim3(nb, B), SM_THREADS, 0, st>>>(h * w, nb, mean_part, gd_part, grad_disp);
     DMH_CHECK_LAUNCH("dmh_smooth_bwd");
+    return DMH_OK;
+}
+
+int dmh_upsample_bilinear_fwd(const float* in, int planes, int h, int w, int H, int W, float* out,
+                              dmh_stream_t stream) {
+    DMH_REQUIRE(in && out, "dmh_upsample_bilinear_fwd: null pointer");
+    DMH_REQUIRE(planes > 0 && planes <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "dmh_upsample_bilinear_fwd: bad shape");
+    dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), planes);
+    upsample_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, h, w, H, W, (float)h / (float)H,
+                                                                 (float)w / (float)W, out);
+    DMH_CHECK_LAUNCH("dmh_upsample_bilinear_fwd");
+    return DMH_OK;
+}
+
+int dmh_upsample_bilinear_bwd(const float* grad_out, int planes, int h, int w, int H, int W, const float* grad_scale,
+                              float* grad_in, dmh_stream_t stream) {
+    DMH_REQUIRE(grad_out && grad_in, "dmh_upsample_bilinear_bwd: null pointer");
+    DMH_REQUIRE(planes > 0 && planes <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "dmh_upsample_bilinear_bwd: bad shape");
+    dim3 block(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8), planes);
+    upsample_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(grad_out, h, w, H, W, (float)h / (float)H,
+                                                                 (float)w / (float)W, grad_scale, grad_in);
+    DMH_CHECK_LAUNCH("dmh_upsample_bilinear_bwd");
     return DMH_OK;
 }
 

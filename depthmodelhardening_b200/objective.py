@@ -66,7 +66,7 @@ def photometric_losses(colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids,
     for scale in scales:
         disp = disps[scale]
         if disp.shape[2] != height or disp.shape[3] != width:
-            disp_full = F.interpolate(disp, [height, width], mode="bilinear", align_corners=False)
+            disp_full = ops.upsample_bilinear(disp, (height, width))
         else:
             disp_full = disp
         nz = None

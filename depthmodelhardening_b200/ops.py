@@ -234,6 +234,32 @@ def smooth_loss(disp, img, normalise=False):
     return _Smooth.apply(disp, img, bool(normalise))
 
 
+
+# ----------------------------------------------------------------------------- F.interpolate (trainer.py:481-482)
+class _UpsampleBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        a = f32c(x)
+        B, Cc, h, w = a.shape
+        out = torch.empty(B, Cc, H, W, device=a.device, dtype=torch.float32)
+        check(_lib_().dmh_upsample_bilinear_fwd(ptr(a), B * Cc, h, w, H, W, ptr(out), stream()), "upsample_fwd")
+        ctx.dims = (B, Cc, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        B, Cc, h, w, H, W = ctx.dims
+        g = f32c(g_out)
+        gi = torch.empty(B, Cc, h, w, device=g.device, dtype=torch.float32)
+        check(_lib_().dmh_upsample_bilinear_bwd(ptr(g), B * Cc, h, w, H, W, None, ptr(gi), stream()), "upsample_bwd")
+        return gi, None, None
+
+
+def upsample_bilinear(x, size):
+    """`F.interpolate(x, size, mode="bilinear", align_corners=False)` with a
+    deterministic (gather) backward."""
+    return _UpsampleBilinear.apply(x, int(size[0]), int(size[1]))
+
 # ----------------------------------------------------------------------------- A9-A12 fused
 class _WarpFused(torch.autograd.Function):
     @staticmethod

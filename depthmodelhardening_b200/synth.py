@@ -131,7 +131,10 @@ def photo_batch(batch=4, height=192, width=640, frame_ids: Sequence = (0, "s"), 
     for s in scales:
         shape = (batch, 1, height // 2 ** s, width // 2 ** s)
         if disp_kind == "realistic":
-            disp[s] = (0.02 + 0.3 * smooth_field(shape, seed + 300 + s, down=8, noise=0.0)).contiguous()
+            # smooth field + fine texture: a bare bilinear up-sample is piecewise linear with exactly
+            # constant borders, which puts |d(x)-d(x+1)| at 0 +- 1 ulp where abs() is not differentiable
+            disp[s] = (0.02 + 0.3 * smooth_field(shape, seed + 300 + s, down=8, noise=0.0)
+                       + 0.004 * rand(shape, seed + 350 + s)).contiguous()
         else:
             disp[s] = rand(shape, seed + 400 + s)
     K, inv_K = intrinsics(height, width, batch)

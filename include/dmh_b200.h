@@ -102,6 +102,14 @@ int dmh_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int
                    const float* grad_loss, float weight, float* ws, float* grad_disp, float* grad_img,
                    dmh_stream_t stream);
 
+/* -- F.interpolate(disp, [H,W], "bilinear", align_corners=False) (M2/trainer.py:481-482)
+ * in (planes,h,w) -> out (planes,H,W).  bwd is a deterministic gather (ATen's CUDA
+ * backward uses atomics): grad_in = (*grad_scale, nullable -> 1) * dOut/dIn^T grad_out */
+int dmh_upsample_bilinear_fwd(const float* in, int planes, int h, int w, int H, int W, float* out,
+                              dmh_stream_t stream);
+int dmh_upsample_bilinear_bwd(const float* grad_out, int planes, int h, int w, int H, int W, const float* grad_scale,
+                              float* grad_in, dmh_stream_t stream);
+
 /* -- A9-A12 fused gather: disp -> depth -> backproject -> project -> bilinear
  *    border warp in ONE kernel (M2/trainer.py:485-519 for one (scale, frame)).
  * disp (B,1,H,W) full resolution (or depth when input_is_depth), src (B,C,H,W),

@@ -15,7 +15,7 @@ import torch
 from depthmodelhardening_b200 import synth
 from oracle import photometric as OP
 from oracle.make_golden import PHOTO_CASES
-from tests.util import assert_close, load_golden, rel_err
+from tests.util import assert_close, assert_close_arb, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -138,9 +138,13 @@ def test_reproj_loss_vs_oracle(dev):
         t1 = pb.color[(0, 0)].to(dev).requires_grad_(True)
         out = ops.reprojection_loss(p1, t1, no_ssim)
         (out * up.to(dev)).sum().backward()
-        assert_close(out, ref, TOL, "reproj")
-        assert_close(p1.grad, p0.grad, TOL, "grad_pred")
-        assert_close(t1.grad, t0.grad, TOL, "grad_target")
+        p2 = pb.color[(-1, 0)].double().requires_grad_(True)
+        t2 = pb.color[(0, 0)].double().requires_grad_(True)
+        ref64 = OP.reprojection_loss(p2, t2, no_ssim)
+        (ref64 * up.double()).sum().backward()
+        assert_close_arb(out, ref, ref64, TOL, "reproj")
+        assert_close_arb(p1.grad, p0.grad, p2.grad, TOL, "grad_pred")
+        assert_close_arb(t1.grad, t0.grad, t2.grad, TOL, "grad_target")
 
 
 def test_smooth_normalised_vs_oracle(dev):
@@ -246,3 +250,50 @@ def test_fused_full_size_properties(dev):
     losses, _ = objective.photometric_losses(colors, disps, pb.K, pb.inv_K, Ti, pb.frame_ids, pb.scales, pb.height,
                                              pb.width, disable_automasking=True, disparity_smoothness=0.0)
     assert float(losses["loss"]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 24, 40, 96, 160), (1, 1, 7, 9, 50, 70), (2, 1, 40, 128, 320, 1024)])
+def test_upsample_bilinear_vs_torch(dev, shape):
+    from depthmodelhardening_b200 import ops
+    B, Cc, h, w, H, W = shape
+    x = synth.rand((B, Cc, h, w), 51)
+    up = synth.randn((B, Cc, H, W), 52)
+    x0 = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.interpolate(x0, [H, W], mode="bilinear", align_corners=False)
+    (ref * up).sum().backward()
+    x1 = x.to(dev).requires_grad_(True)
+    out = ops.upsample_bilinear(x1, (H, W))
+    (out * up.to(dev)).sum().backward()
+    assert_close(out, ref, 1e-6, "upsample")
+    assert_close(x1.grad, x0.grad, TOL, "upsample grad")
+
+
+@pytest.mark.parametrize("frame_ids,hw", [((0, "s"), (64, 96)), ((0, -1, 1), (50, 70)), ((0, "s"), (33, 37))])
+def test_photo_scale_kernel_alone_vs_oracle(dev, frame_ids, hw):
+    """The fused per-scale kernel in isolation (no smoothness, no up-sampling):
+    sum of to_optimise, argmin, d/d(disp), d/d(T) against the oracle."""
+    from depthmodelhardening_b200 import ops
+    H, W = hw
+    pb = synth.photo_batch(batch=2, height=H, width=W, frame_ids=frame_ids, scales=(0,), seed=61)
+    srcs_ids = pb.frame_ids[1:]
+    target = pb.color[(0, 0)]
+    d0 = pb.disp[0].clone().requires_grad_(True)
+    T0 = {f: pb.T[f].clone().requires_grad_(True) for f in srcs_ids}
+    reproj = torch.cat([OP.reprojection_loss(OP.warp_from_disp(d0, pb.color[(f, 0)], pb.K, pb.inv_K, T0[f], 0.1, 100.0)[0],
+                                             target) for f in srcs_ids], 1)
+    ident = torch.cat([OP.reprojection_loss(pb.color[(f, 0)], target) for f in srcs_ids], 1)
+    comb = torch.cat((ident + pb.noise[0], reproj), 1)
+    to_opt, idx = torch.min(comb, dim=1)
+    to_opt.sum().backward()
+    g = pb.to(dev)
+    d1 = g.disp[0].clone().requires_grad_(True)
+    T1 = {f: g.T[f].clone().requires_grad_(True) for f in srcs_ids}
+    total, sel = ops.photo_scale_sum(d1, g.color[(0, 0)], [g.color[(f, 0)] for f in srcs_ids], [T1[f] for f in srcs_ids],
+                                     g.K, g.inv_K, ident=ident.to(dev), noise=g.noise[0], want_sel=True)
+    total.backward()
+    assert_close(total, to_opt.sum(), TOL, "sum to_optimise")
+    assert np.mean(sel.cpu().numpy() != idx.numpy()) < 1e-4
+    assert_close(d1.grad, d0.grad, TOL, "grad_disp", max_outlier_frac=OUTL, outlier_rtol=0.5)
+    for f in srcs_ids:
+        if f != "s":
+            assert_close(T1[f].grad, T0[f].grad, 2e-4, "grad_T")

@@ -46,3 +46,19 @@ def assert_close(a, b, rtol, what="", max_outlier_frac=0.0, outlier_rtol=None):
             assert e <= outlier_rtol, "%s: outlier rel err %.3g > %g" % (what, e, outlier_rtol)
         return e
     raise AssertionError("%s: rel err %.3g > %g" % (what, e, rtol))
+
+
+def assert_close_arb(a, ref32, ref64, rtol, what=""):
+    """Arbitrated comparison (fp64 re-run of the same code as
+    arbiter).  Pass if within rtol of the fp32 oracle; otherwise the CUDA result
+    must be within rtol of the fp64 truth, or at least as close to it as the fp32
+    oracle itself is (+20 %) -- i.e. the disagreement is fp32 rounding of the
+    reference, not an error of the kernel."""
+    e32 = rel_err(a, ref32)
+    if e32 <= rtol:
+        return e32
+    e64 = rel_err(a, ref64)
+    eref = rel_err(ref32, ref64)
+    assert e64 <= max(rtol, 1.2 * eref), "%s: rel err vs fp32 oracle %.3g, vs fp64 %.3g (oracle32 vs fp64 %.3g)" % (
+        what, e32, e64, eref)
+    return e32
