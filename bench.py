@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path benchmark (contract: see task statement / DESIGN.md).
+
+One "step" = one pass of the grafted hot path over one batch of synthetic input:
+  stage 1  physical-patch PGD step: patch-apply fwd (perspective warp + composite
+           + anti-aliased resize) -> patch-apply bwd from a supplied upstream
+           gradient -> [allreduce of the shared patch gradient when N>1] -> L-inf
+           sign/project update                          (Ba = per-GPU batch)
+  stage 2  monodepth2 photometric objective fwd+bwd: 4 scales, automask, SSIM+L1,
+           smoothness, gradients w.r.t. the 4 disparity maps   (B = per-GPU batch)
+Workload = BASELINE.json configs[1]: 1024x320, batch 32 per GPU, frame_ids [0,'s'].
+The depth network is outside the graft and is not part of the step.
+
+metric  reproj-loss fwd+bwd Mpix/s (target pixels N*B*H*W per step / step time);
+        PGD steps/s and the per-stage split are reported in extra keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W = 320, 1024
+SCALES = (0, 1, 2, 3)
+FRAME_IDS = (0, "s")
+METRIC = "reproj_loss_fwd_bwd_mpix_per_s"
+UNIT = "Mpix/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-patch", action="store_true", help="skip stage 1 (debug)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="dmh_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- workload
+def make_host_workload(batch, rank, with_patch):
+    from depthmodelhardening_b200 import synth
+    pb = synth.photo_batch(batch=batch, height=H, width=W, frame_ids=FRAME_IDS, scales=SCALES, seed=1000 * rank)
+    pt = synth.patch_batch(batch=batch, seed=1000 * rank) if with_patch else None
+    return pb, pt
+
+
+def algorithmic_bytes(batch, F=1, S=4):
+    """SURVEY.md 8(d) compulsory traffic (fp32)."""
+    sigma = sum(4.0 ** (-s) for s in range(S))
+    fwd = 12 + 12 * F + 4 * S + 4 * F * S + (4 * sigma + 12 * (sigma - 1))
+    bwd = fwd + 4 * S + 4 * sigma
+    per_px = fwd + bwd
+    return per_px * batch * H * W, per_px
+
+
+class Stage2:
+    def __init__(self, pb, device, noise_mode="injected"):
+        self.g = pb.to(device)
+        self.noise_mode = noise_mode
+        self.disps = {s: self.g.disp[s].clone().requires_grad_(True) for s in self.g.scales}
+
+    def step(self):
+        from depthmodelhardening_b200 import objective
+        g = self.g
+        for d in self.disps.values():
+            d.grad = None
+        losses, _ = objective.photometric_losses(
+            g.color, self.disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height, g.width,
+            noise=g.noise if self.noise_mode == "injected" else None,
+            noise_mode="device" if self.noise_mode != "injected" else "reference")
+        losses["loss"].backward()
+        return losses["loss"]
+
+
+class Stage1:
+    def __init__(self, pt, device, world):
+        import numpy as np
+        from depthmodelhardening_b200 import patch_ops, synth
+        self.ops = patch_ops
+        self.g = pt.to(device)
+        P34 = np.array(patch_ops.KITTI_P2_003086, dtype=np.float64).reshape(3, 4)
+        self.coeffs = patch_ops.homographies(pt.z0, pt.alpha, P34, obj_hw=(synth.PATCH_H, synth.PATCH_W)).to(device)
+        self.adv = self.g.obj.clone()
+        self.world = world
+
+    def step(self):
+        ops = self.ops
+        g = self.g
+        adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream)
+        if self.world > 1:
+            torch.distributed.all_reduce(grad_patch)
+        self.adv = ops.pgd_linf_step(self.adv, grad_patch, g.obj, alpha=0.02, eps=0.1)
+        return adv_scene
+
+
+def timed_loop(fn, steps, warmup, world):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        torch.distributed.barrier()
+    return ms / steps
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_reference_step(sample_batch, with_patch, threads=None):
+    """The reference algorithm on the host cores: oracle restatement (the
+    reference itself is Python and does not travel to the GPU box)."""
+    import numpy as np
+    from depthmodelhardening_b200 import synth
+    from oracle import patch as OQ
+    from oracle import photometric as OP
+    if threads:
+        torch.set_num_threads(threads)
+    pb = synth.photo_batch(batch=sample_batch, height=H, width=W, frame_ids=FRAME_IDS, scales=SCALES, seed=7)
+    pt = synth.patch_batch(batch=sample_batch, seed=7) if with_patch else None
+    P34 = np.array(OQ_P2(), dtype=np.float64).reshape(3, 4)
+
+    def step():
+        if pt is not None:
+            obj = pt.obj.clone().requires_grad_(True)
+            adv, _ = OQ.apply_patch(obj, pt.mask, pt.scenes, pt.z0, pt.alpha, P34)
+            (adv * pt.upstream).sum().backward()
+            OQ.pgd_linf_step(obj.detach(), obj.grad, pt.obj, 0.02, 0.1)
+        OP.objective_from_batch(pb)
+    return step
+
+
+def OQ_P2():
+    from oracle.refload import CALIB_P2
+    return CALIB_P2
+
+
+def run_cpu_baseline(sample_batch, with_patch, reps=2):
+    step = cpu_reference_step(sample_batch, with_patch)
+    step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_batch * H * W / dt / 1e6, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle (torch-CPU restatement of the reference) on a batch-%d slice of the 1024x320 workload, "
+                      "%d reps, %.2f s/step" % (sample_batch, reps, dt)}
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sb = args.cpu_sample_batch
+    with_patch = not args.no_patch
+    step = cpu_reference_step(sb, with_patch)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = sb * H * W / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: monodepth2 1024x320 stereo [0,'s'], 4 scales, automask; "
+                                   "patch PGD step + photometric loss fwd/bwd", "sample_batch": sb,
+                       "per_gpu_batch": args.batch},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "oracle port on a batch-%d slice, %d steps (the reference is pure Python and "
+                                       "cannot travel to the GPU box)" % (sb, steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    from depthmodelhardening_b200 import _lib
+    lib = _lib.load()
+    with_patch = not args.no_patch
+    if with_patch:
+        try:
+            from depthmodelhardening_b200 import patch_ops  # noqa: F401
+        except ImportError:
+            with_patch = False
+
+    B = args.batch
+    pb_host, pt_host = make_host_workload(B, rank, with_patch)
+    s2 = Stage2(pb_host, device)
+    s1 = Stage1(pt_host, device, world) if with_patch else None
+
+    def step():
+        if s1 is not None:
+            s1.step()
+        return s2.step()
+
+    # inputs > L2 (126 MB): colour frames alone are 2 x 126 MB at B=32, so no explicit flush is needed
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = lib.dmh_launch_count()
+    ms_step = timed_loop(step, args.steps, args.warmup, world)
+    n1 = lib.dmh_launch_count()
+    clocks = sampler.stop()
+    launches = int((n1 - n0) * args.steps / (args.steps + args.warmup))
+
+    # per-stage split (same loop, one stage at a time)
+    ms_s2 = timed_loop(s2.step, args.steps, 2, world)
+    ms_s1 = timed_loop(s1.step, args.steps, 2, world) if s1 is not None else None
+
+    # dominant kernel: the fused per-scale objective kernel, timed with events around its launches
+    from depthmodelhardening_b200 import ops
+    ops.KERNEL_EVENTS = []
+    for _ in range(3):
+        s2.step()
+    torch.cuda.synchronize()
+    kt = [a.elapsed_time(b) for (name, a, b) in ops.KERNEL_EVENTS if name == "photo_scale"]
+    ops.KERNEL_EVENTS = None
+    kms = sum(kt) / max(len(kt), 1)
+    F = len(FRAME_IDS) - 1
+    k_bytes = (12 + 12 * F + 4 + 4 * F + 4 * F + 4) * B * H * W
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = k_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    step_bytes, per_px = algorithmic_bytes(B, F, len(SCALES))
+    if s1 is not None:
+        step_bytes_total = step_bytes + 14.8e6 * B
+    else:
+        step_bytes_total = step_bytes
+
+    # end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.pin_memory()
+        host2 = {"color": {k: pin(v) for k, v in pb_host.color.items()},
+                 "disp": {k: pin(v) for k, v in pb_host.disp.items()},
+                 "K": pin(pb_host.K), "inv_K": pin(pb_host.inv_K), "T": {k: pin(v) for k, v in pb_host.T.items()}}
+        host_scenes = pin(pt_host.scenes) if s1 is not None else None
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * 4 for v in host2["color"].values()) + sum(v.numel() * 4 for v in host2["disp"].values()) \
+            + 2 * host2["K"].numel() * 4 + sum(v.numel() * 4 for v in host2["T"].values())
+        if s1 is not None:
+            h2d += host_scenes.numel() * 4
+        from depthmodelhardening_b200 import objective
+
+        def e2e_step():
+            nb = lambda t: t.to(device, non_blocking=True)
+            color = {k: nb(v) for k, v in host2["color"].items()}
+            disps = {k: nb(v).requires_grad_(True) for k, v in host2["disp"].items()}
+            K, iK = nb(host2["K"]), nb(host2["inv_K"])
+            T = {k: nb(v) for k, v in host2["T"].items()}
+            if s1 is not None:
+                s1.g.scenes = nb(host_scenes)
+                s1.step()
+            losses, _ = objective.photometric_losses(color, disps, K, iK, T, list(FRAME_IDS), list(SCALES), H, W,
+                                                     noise=None, noise_mode="device")
+            losses["loss"].backward()
+            loss_host.copy_(losses["loss"].detach(), non_blocking=True)
+
+        ms_e2e = timed_loop(e2e_step, max(3, args.steps // 2), 2, world)
+        e2e = {"value": world * B * H * W / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+               "note": "pinned host batch dict (frames, pyramid, disparities, K, T, scenes) copied every step; "
+                       "tie-break noise drawn on the device"}
+
+    line = {
+        "metric": METRIC, "value": world * B * H * W / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: monodepth2 1024x320 stereo [0,'s'], 4 scales, automask, SSIM+L1, "
+                               "smoothness; step = patch PGD step (stage 1) + photometric loss fwd/bwd (stage 2)"
+                               if s1 is not None else
+                               "configs[1] stage 2 only: photometric loss fwd/bwd (stage 1 not built yet)",
+                   "per_gpu_batch": B, "global_batch": B * world, "height": H, "width": W, "frame_ids": list(FRAME_IDS),
+                   "scales": list(SCALES), "l2_policy": "inputs (2x126 MB frames + 168 MB noise) exceed the 126 MB L2"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "stages": {"photometric_ms": ms_s2, "patch_pgd_ms": ms_s1,
+                   "pgd_steps_per_s": (1e3 / ms_s1) if ms_s1 else None,
+                   "photometric_mpix_per_s": world * B * H * W / (ms_s2 * 1e-3) / 1e6},
+        "roofline": {"bound": "hbm", "kernel": "photo_scale_kernel<1>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                     "kernel_ms": kms, "kernel_launches_timed": len(kt), "algorithmic_bytes_per_launch": k_bytes,
+                     "step_algorithmic_bytes": step_bytes_total,
+                     "step_hbm_frac": step_bytes_total / (ms_step * 1e-3) / 1e9 / peak},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,7 @@ SIGNATURES = {
     "dmh_last_error": (C.c_char_p, []),
     "dmh_version": (_i, []),
     "dmh_build_arch": (_i, []),
+    "dmh_launch_count": (_ll, []),
     "dmh_disp_to_depth": (_i, [_f, _ll, _fl, _fl, _f, _f, _st]),
     "dmh_backproject_fwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),
     "dmh_backproject_bwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),

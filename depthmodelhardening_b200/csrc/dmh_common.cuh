@@ -11,6 +11,7 @@
 namespace dmh {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // bookkeeping for dmh_launch_count()
 
 #define DMH_REQUIRE(cond, ...)                    \
     do {                                          \
@@ -28,6 +29,9 @@ void set_error(const char* fmt, ...);
             return DMH_ERR_CUDA;                                                         \
         }                                                                                \
     } while (0)
+
+// <<<>>> with launch accounting: DMH_LAUNCH(kernel, grid, block, smem, stream)(args...)
+#define DMH_LAUNCH(kernel, grid, block, smem, st) dmh::count_launches(1), kernel<<<grid, block, smem, st>>>
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -409,7 +409,7 @@ int launch_photo(const PhotoParams& p, dim3 grid, cudaStream_t st) {
         }
         configured = true;
     }
-    photo_scale_kernel<F><<<grid, PH_THREADS, smem, st>>>(p);
+    DMH_LAUNCH(photo_scale_kernel<F>, grid, PH_THREADS, smem, st)(p);
     return DMH_OK;
 }
 

@@ -440,7 +440,7 @@ int dmh_disp_to_depth(const float* disp, long long n, float min_depth, float max
     ds.min_disp = (float)(1.0 / (double)max_depth);
     ds.range = (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
     const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    disp_to_depth_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(disp, n, ds, scaled_disp, depth);
+    DMH_LAUNCH(disp_to_depth_kernel, blocks, 256, 0, (cudaStream_t)stream)(disp, n, ds, scaled_disp, depth);
     DMH_CHECK_LAUNCH("dmh_disp_to_depth");
     return DMH_OK;
 }
@@ -450,7 +450,7 @@ int dmh_backproject_fwd(const float* depth, const float* inv_K, int B, int H, in
     DMH_REQUIRE(depth && inv_K && points, "dmh_backproject_fwd: null pointer");
     DMH_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "dmh_backproject_fwd: bad shape B=%d H=%d W=%d", B, H, W);
     dim3 grid(ceil_div((long long)H * W, 256), B);
-    backproject_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth, inv_K, H, W, points);
+    DMH_LAUNCH(backproject_fwd_kernel, grid, 256, 0, (cudaStream_t)stream)(depth, inv_K, H, W, points);
     DMH_CHECK_LAUNCH("dmh_backproject_fwd");
     return DMH_OK;
 }
@@ -460,7 +460,7 @@ int dmh_backproject_bwd(const float* grad_points, const float* inv_K, int B, int
     DMH_REQUIRE(grad_points && inv_K && grad_depth, "dmh_backproject_bwd: null pointer");
     DMH_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "dmh_backproject_bwd: bad shape");
     dim3 grid(ceil_div((long long)H * W, 256), B);
-    backproject_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad_points, inv_K, H, W, grad_depth);
+    DMH_LAUNCH(backproject_bwd_kernel, grid, 256, 0, (cudaStream_t)stream)(grad_points, inv_K, H, W, grad_depth);
     DMH_CHECK_LAUNCH("dmh_backproject_bwd");
     return DMH_OK;
 }
@@ -470,7 +470,7 @@ int dmh_project3d_fwd(const float* points, const float* K, const float* T, int B
     DMH_REQUIRE(points && K && T && grid_out, "dmh_project3d_fwd: null pointer");
     DMH_REQUIRE(B > 0 && H > 1 && W > 1 && B <= 65535, "dmh_project3d_fwd: bad shape");
     dim3 grid(ceil_div((long long)H * W, 256), B);
-    project3d_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, K, T, H, W, eps, grid_out);
+    DMH_LAUNCH(project3d_fwd_kernel, grid, 256, 0, (cudaStream_t)stream)(points, K, T, H, W, eps, grid_out);
     DMH_CHECK_LAUNCH("dmh_project3d_fwd");
     return DMH_OK;
 }
@@ -482,7 +482,7 @@ int dmh_project3d_bwd(const float* grad_grid, const float* points, const float* 
     DMH_REQUIRE(grad_grid && points && K && T, "dmh_project3d_bwd: null pointer");
     DMH_REQUIRE(B > 0 && H > 1 && W > 1 && B <= 65535, "dmh_project3d_bwd: bad shape");
     dim3 grid(dmh_project3d_bwd_blocks(H, W), B);
-    project3d_bwd_kernel<<<grid, P3D_BWD_THREADS, 0, (cudaStream_t)stream>>>(grad_grid, points, K, T, H, W, eps,
+    DMH_LAUNCH(project3d_bwd_kernel, grid, P3D_BWD_THREADS, 0, (cudaStream_t)stream)(grad_grid, points, K, T, H, W, eps,
                                                                             grad_points, grad_P_partial);
     DMH_CHECK_LAUNCH("dmh_project3d_bwd");
     return DMH_OK;
@@ -497,7 +497,7 @@ int dmh_grid_sample_fwd(const float* src, const float* grid, int B, int C, int H
         return DMH_ERR_UNSUPPORTED;
     }
     dim3 g(ceil_div((long long)Ho * Wo, 256), B);
-    grid_sample_fwd_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, grid, C, Hs, Ws, Ho, Wo, padding_mode,
+    DMH_LAUNCH(grid_sample_fwd_kernel, g, 256, 0, (cudaStream_t)stream)(src, grid, C, Hs, Ws, Ho, Wo, padding_mode,
                                                                align_corners, out);
     DMH_CHECK_LAUNCH("dmh_grid_sample_fwd");
     return DMH_OK;
@@ -513,7 +513,7 @@ int dmh_grid_sample_bwd(const float* grad_out, const float* src, const float* gr
         return DMH_ERR_UNSUPPORTED;
     }
     dim3 g(ceil_div((long long)Ho * Wo, 256), B);
-    grid_sample_bwd_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(grad_out, src, grid, C, Hs, Ws, Ho, Wo, padding_mode,
+    DMH_LAUNCH(grid_sample_bwd_kernel, g, 256, 0, (cudaStream_t)stream)(grad_out, src, grid, C, Hs, Ws, Ho, Wo, padding_mode,
                                                                align_corners, grad_src, grad_grid);
     DMH_CHECK_LAUNCH("dmh_grid_sample_bwd");
     return DMH_OK;
@@ -523,7 +523,7 @@ int dmh_ssim_fwd(const float* x, const float* y, int B, int C, int H, int W, flo
     DMH_REQUIRE(x && y && out, "dmh_ssim_fwd: null pointer");
     DMH_REQUIRE(B > 0 && C > 0 && H >= 2 && W >= 2 && (long long)B * C <= 65535, "dmh_ssim_fwd: bad shape");
     dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B * C);
-    ssim_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, H, W, out);
+    DMH_LAUNCH(ssim_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(x, y, H, W, out);
     DMH_CHECK_LAUNCH("dmh_ssim_fwd");
     return DMH_OK;
 }
@@ -533,7 +533,7 @@ static int launch_ssim_bwd(const char* name, const float* grad_out, const float*
     DMH_REQUIRE(grad_out && x && y, "%s: null pointer", name);
     DMH_REQUIRE(B > 0 && C > 0 && H >= 2 && W >= 2 && (long long)B * C <= 65535, "%s: bad shape", name);
     dim3 grid(ceil_div(W, ST_TW), ceil_div(H, ST_TH), B * C);
-    ssim_bwd_kernel<<<grid, ST_THREADS, 0, (cudaStream_t)stream>>>(grad_out, x, y, C, H, W, mode, no_ssim, gx, gy);
+    DMH_LAUNCH(ssim_bwd_kernel, grid, ST_THREADS, 0, (cudaStream_t)stream)(grad_out, x, y, C, H, W, mode, no_ssim, gx, gy);
     DMH_CHECK_LAUNCH(name);
     return DMH_OK;
 }
@@ -548,7 +548,7 @@ int dmh_reproj_loss_fwd(const float* pred, const float* target, int B, int C, in
     DMH_REQUIRE(pred && target && out, "dmh_reproj_loss_fwd: null pointer");
     DMH_REQUIRE(B > 0 && C > 0 && H >= 2 && W >= 2 && B <= 65535, "dmh_reproj_loss_fwd: bad shape");
     dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B);
-    reproj_loss_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pred, target, C, H, W, no_ssim, out);
+    DMH_LAUNCH(reproj_loss_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(pred, target, C, H, W, no_ssim, out);
     DMH_CHECK_LAUNCH("dmh_reproj_loss_fwd");
     return DMH_OK;
 }

@@ -417,10 +417,10 @@ int dmh_warp_fwd(const float* disp, int input_is_depth, float min_depth, float m
     const DepthScale ds = input_is_depth ? DepthScale{0.f, 0.f} : make_depth_scale(min_depth, max_depth);
     dim3 grid(ceil_div((long long)H * W, WARP_THREADS), B);
     if (C == 3)
-        warp_fwd_kernel<3><<<grid, WARP_THREADS, 0, (cudaStream_t)stream>>>(disp, input_is_depth, ds, src, K, inv_K, T,
+        DMH_LAUNCH(warp_fwd_kernel<3>, grid, WARP_THREADS, 0, (cudaStream_t)stream)(disp, input_is_depth, ds, src, K, inv_K, T,
                                                                            C, H, W, warped, grid_out, depth_out);
     else
-        warp_fwd_kernel<0><<<grid, WARP_THREADS, 0, (cudaStream_t)stream>>>(disp, input_is_depth, ds, src, K, inv_K, T,
+        DMH_LAUNCH(warp_fwd_kernel<0>, grid, WARP_THREADS, 0, (cudaStream_t)stream)(disp, input_is_depth, ds, src, K, inv_K, T,
                                                                            C, H, W, warped, grid_out, depth_out);
     DMH_CHECK_LAUNCH("dmh_warp_fwd");
     return DMH_OK;
@@ -437,10 +437,10 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
     const DepthScale ds = input_is_depth ? DepthScale{0.f, 0.f} : make_depth_scale(min_depth, max_depth);
     dim3 grid(dmh_warp_bwd_blocks(H, W), B);
     if (C == 3)
-        warp_bwd_kernel<3><<<grid, WARP_THREADS, 0, (cudaStream_t)stream>>>(
+        DMH_LAUNCH(warp_bwd_kernel<3>, grid, WARP_THREADS, 0, (cudaStream_t)stream)(
             grad_warped, disp, input_is_depth, ds, src, K, inv_K, T, C, H, W, grad_disp, grad_src, grad_P_partial);
     else
-        warp_bwd_kernel<0><<<grid, WARP_THREADS, 0, (cudaStream_t)stream>>>(
+        DMH_LAUNCH(warp_bwd_kernel<0>, grid, WARP_THREADS, 0, (cudaStream_t)stream)(
             grad_warped, disp, input_is_depth, ds, src, K, inv_K, T, C, H, W, grad_disp, grad_src, grad_P_partial);
     DMH_CHECK_LAUNCH("dmh_warp_bwd");
     return DMH_OK;
@@ -460,10 +460,10 @@ int dmh_smooth_fwd(const float* disp, const float* img, int B, int C, int h, int
     float* mean_part = ws;
     float* loss_part = ws + (size_t)B * SM_NB1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (normalise) smooth_mean_kernel<<<dim3(SM_NB1, B), 256, 0, st>>>(disp, h * w, mean_part);
-    smooth_fwd_kernel<<<dim3(nb, B), SM_THREADS, 0, st>>>(disp, img, C, h, w, normalise, mean_part, loss_part);
+    if (normalise) DMH_LAUNCH(smooth_mean_kernel, dim3(SM_NB1, B), 256, 0, st)(disp, h * w, mean_part);
+    DMH_LAUNCH(smooth_fwd_kernel, dim3(nb, B), SM_THREADS, 0, st)(disp, img, C, h, w, normalise, mean_part, loss_part);
     const double inv_nx = 1.0 / ((double)B * h * (w - 1)), inv_ny = 1.0 / ((double)B * (h - 1) * w);
-    smooth_loss_reduce_kernel<<<1, 256, 0, st>>>(loss_part, B * nb, inv_nx, inv_ny, loss_out);
+    DMH_LAUNCH(smooth_loss_reduce_kernel, 1, 256, 0, st)(loss_part, B * nb, inv_nx, inv_ny, loss_out);
     DMH_CHECK_LAUNCH("dmh_smooth_fwd");
     return DMH_OK;
 }
@@ -478,12 +478,12 @@ int dmh_smooth_bwd(const float* disp, const float* img, int B, int C, int h, int
     float* mean_part = ws;
     float* gd_part = ws + (size_t)B * SM_NB1 + 2 * (size_t)B * nb;
     cudaStream_t st = (cudaStream_t)stream;
-    if (normalise) smooth_mean_kernel<<<dim3(SM_NB1, B), 256, 0, st>>>(disp, h * w, mean_part);
+    if (normalise) DMH_LAUNCH(smooth_mean_kernel, dim3(SM_NB1, B), 256, 0, st)(disp, h * w, mean_part);
     const float inv_nx = (float)(1.0 / ((double)B * h * (w - 1))), inv_ny = (float)(1.0 / ((double)B * (h - 1) * w));
-    smooth_bwd_kernel<<<dim3(nb, B), SM_THREADS, 0, st>>>(disp, img, C, h, w, normalise, mean_part, inv_nx, inv_ny,
+    DMH_LAUNCH(smooth_bwd_kernel, dim3(nb, B), SM_THREADS, 0, st)(disp, img, C, h, w, normalise, mean_part, inv_nx, inv_ny,
                                                           grad_loss, weight, grad_disp, gd_part, grad_img);
     if (normalise)
-        smooth_bwd_finalize_kernel<<<dim3(nb, B), SM_THREADS, 0, st>>>(h * w, nb, mean_part, gd_part, grad_disp);
+        DMH_LAUNCH(smooth_bwd_finalize_kernel, dim3(nb, B), SM_THREADS, 0, st)(h * w, nb, mean_part, gd_part, grad_disp);
     DMH_CHECK_LAUNCH("dmh_smooth_bwd");
     return DMH_OK;
 }
@@ -493,7 +493,7 @@ int dmh_upsample_bilinear_fwd(const float* in, int planes, int h, int w, int H, 
     DMH_REQUIRE(in && out, "dmh_upsample_bilinear_fwd: null pointer");
     DMH_REQUIRE(planes > 0 && planes <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "dmh_upsample_bilinear_fwd: bad shape");
     dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), planes);
-    upsample_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, h, w, H, W, (float)h / (float)H,
+    DMH_LAUNCH(upsample_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(in, h, w, H, W, (float)h / (float)H,
                                                                  (float)w / (float)W, out);
     DMH_CHECK_LAUNCH("dmh_upsample_bilinear_fwd");
     return DMH_OK;
@@ -504,7 +504,7 @@ int dmh_upsample_bilinear_bwd(const float* grad_out, int planes, int h, int w, i
     DMH_REQUIRE(grad_out && grad_in, "dmh_upsample_bilinear_bwd: null pointer");
     DMH_REQUIRE(planes > 0 && planes <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "dmh_upsample_bilinear_bwd: bad shape");
     dim3 block(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8), planes);
-    upsample_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(grad_out, h, w, H, W, (float)h / (float)H,
+    DMH_LAUNCH(upsample_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_out, h, w, H, W, (float)h / (float)H,
                                                                  (float)w / (float)W, grad_scale, grad_in);
     DMH_CHECK_LAUNCH("dmh_upsample_bilinear_bwd");
     return DMH_OK;
@@ -512,7 +512,7 @@ int dmh_upsample_bilinear_bwd(const float* grad_out, int planes, int h, int w, i
 
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream) {
     DMH_REQUIRE(in && out && n > 0, "dmh_reduce_sum: null pointer or n <= 0");
-    reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, scale, accumulate, out);
+    DMH_LAUNCH(reduce_sum_kernel, 1, 1024, 0, (cudaStream_t)stream)(in, n, scale, accumulate, out);
     DMH_CHECK_LAUNCH("dmh_reduce_sum");
     return DMH_OK;
 }

@@ -15,6 +15,27 @@ from ._lib import check, f32c, ptr, ptr_array, stream
 
 PAD_MODES = {"zeros": 0, "border": 1}
 
+# bench.py sets this to a list to collect (name, start_event, end_event) around
+# selected kernel launches on the launching stream; None = no instrumentation.
+KERNEL_EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            self.b.record()
+            KERNEL_EVENTS.append((self.name, self.a, self.b))
+        return False
+
 
 def _lib_():
     return _lib.load()
@@ -339,9 +360,10 @@ class _PhotoScale(torch.autograd.Function):
         need_T = any(ctx.needs_input_grad[11 + n_src + i] for i in range(n_src))
         gP = torch.empty(n_src, B, tiles, 12, device=d.device, dtype=torch.float32) if need_T else None
         sel = torch.empty(B, H, W, device=d.device, dtype=torch.uint8) if want_sel else None
-        check(lib.dmh_photo_scale(ptr(tg), ptr_array(srcs), ptr_array(Ts), n_src, ptr(d), ptr(k), ptr(ik), ptr(idn),
-                                  ptr(nz), B, H, W, min_depth, max_depth, flags, 1.0, ptr(part), ptr(gdisp), ptr(gP),
-                                  ptr(sel), None, stream()), "photo_scale")
+        with _timed("photo_scale"):
+            check(lib.dmh_photo_scale(ptr(tg), ptr_array(srcs), ptr_array(Ts), n_src, ptr(d), ptr(k), ptr(ik),
+                                      ptr(idn), ptr(nz), B, H, W, min_depth, max_depth, flags, 1.0, ptr(part),
+                                      ptr(gdisp), ptr(gP), ptr(sel), None, stream()), "photo_scale")
         total = torch.empty((), device=d.device, dtype=torch.float32)
         check(lib.dmh_reduce_sum(ptr(part), part.numel(), 1.0, 0, ptr(total), stream()), "reduce_sum")
         ctx.save_for_backward(gdisp, gP, k, *Ts)

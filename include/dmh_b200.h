@@ -42,6 +42,7 @@ typedef struct CUstream_st* dmh_stream_t; /* == cudaStream_t */
 const char* dmh_last_error(void);
 int dmh_version(void);    /* 100*major + minor */
 int dmh_build_arch(void); /* 100 == compiled for sm_100a */
+long long dmh_launch_count(void); /* kernels launched by this library in this process so far */
 
 /* -- A9  disp_to_depth (M2/layers.py:16-25) ------------------------------ */
 int dmh_disp_to_depth(const float* disp, long long n, float min_depth, float max_depth, float* scaled_disp,

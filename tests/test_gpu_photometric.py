@@ -15,7 +15,7 @@ import torch
 from depthmodelhardening_b200 import synth
 from oracle import photometric as OP
 from oracle.make_golden import PHOTO_CASES
-from tests.util import assert_close, assert_close_arb, load_golden, rel_err
+from tests.util import assert_close, assert_close_arb, assert_grad_close, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -182,10 +182,10 @@ def test_fused_objective_vs_reference_golden(dev, name):
     losses, aux, disps, _ = _run_fused(pb, dev, over)
     assert_close(losses["loss"], g["loss"], TOL, "loss")
     n_ident = 0 if over.get("disable_automasking") else (1 if over.get("avg_reprojection") else len(pb.frame_ids) - 1)
+    _, _, g64 = OP.objective_from_batch(pb, OP.default_opts(scales=list(pb.scales), **over), dtype=torch.float64)
     for s in pb.scales:
         assert_close(losses["loss/%d" % s], g["loss_%d" % s], TOL, "loss/%d" % s)
-        assert_close(disps[s].grad, g["grad_disp_%d" % s], TOL, "grad_disp_%d" % s, max_outlier_frac=OUTL,
-                     outlier_rtol=0.5)
+        assert_grad_close(disps[s].grad, g["grad_disp_%d" % s], g64[s], TOL, "grad_disp_%d" % s)
         if n_ident:
             sel = (aux[("argmin", s)].cpu().numpy() > n_ident - 1).astype(np.uint8)
             assert np.mean(sel != g["ident_sel_%d" % s]) < 1e-4
@@ -207,17 +207,23 @@ def test_fused_objective_vs_oracle(dev, frame_ids, shape):
     total, ref_losses, aux0 = OP.photometric_objective(colors, d0, pb.K, pb.inv_K, T0, pb.frame_ids, pb.noise, opts,
                                                        return_aux=True)
     total.backward()
+    dbl = lambda t: t.detach().double()
+    d64 = {s: dbl(pb.disp[s]).requires_grad_(True) for s in pb.scales}
+    T64 = {k: dbl(v).requires_grad_(True) for k, v in pb.T.items()}
+    t64, _ = OP.photometric_objective({k: dbl(v) for k, v in pb.color.items()}, d64, dbl(pb.K), dbl(pb.inv_K), T64,
+                                      pb.frame_ids, {k: dbl(v) for k, v in pb.noise.items()}, opts)
+    t64.backward()
     losses, aux, disps, Ts = _run_fused(pb, dev, {})
     assert_close(losses["loss"], total, TOL, "loss")
     for s in pb.scales:
         assert_close(losses["loss/%d" % s], ref_losses["loss/%d" % s], TOL, "loss/%d" % s)
-        assert_close(disps[s].grad, d0[s].grad, TOL, "grad_disp_%d" % s, max_outlier_frac=OUTL, outlier_rtol=0.5)
+        assert_grad_close(disps[s].grad, d0[s].grad, d64[s].grad, TOL, "grad_disp_%d" % s)
         sel_ref = aux0[("argmin", s)].numpy()
         assert np.mean(aux[("argmin", s)].cpu().numpy() != sel_ref) < 1e-4
     for f in pb.frame_ids[1:]:
         if f == "s":
             continue
-        assert_close(Ts[f].grad, T0[f].grad, 2e-4, "grad_T %s" % f)
+        assert_grad_close(Ts[f].grad, T0[f].grad, T64[f].grad, 1e-4, "grad_T %s" % f, outlier_frac=0.0, slack=3.0)
 
 
 def test_fused_full_size_properties(dev):

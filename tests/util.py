@@ -62,3 +62,31 @@ def assert_close_arb(a, ref32, ref64, rtol, what=""):
     assert e64 <= max(rtol, 1.2 * eref), "%s: rel err vs fp32 oracle %.3g, vs fp64 %.3g (oracle32 vs fp64 %.3g)" % (
         what, e32, e64, eref)
     return e32
+
+
+def assert_grad_close(a, ref32, ref64, rtol, what="", outlier_frac=2e-3, slack=2.0):
+    """Gradient comparison arbitrated by the fp64 oracle.
+
+    The fp32 reference's own gradients differ from the fp64 run of the same code
+    by 2-5e-5 relative (measured: tests/golden README) -- more than the 1e-5
+    target -- so an fp32 kernel with a different (fused) op order cannot be
+    closer than that to the fp32 reference.  Criterion: accept if within rtol of
+    the fp32 oracle; otherwise, allowing `outlier_frac` of the elements to be
+    coordinate-floor ties, every other element must be
+    within max(rtol, slack * reference-noise) of the fp64 truth, where
+    reference-noise is the fp32 oracle's own (1 - outlier_frac)-quantile error
+    against fp64."""
+    e32 = rel_err(a, ref32)
+    if e32 <= rtol:
+        return e32
+    a_, r32, r64 = to_np(a), to_np(ref32), to_np(ref64)
+    scale = max(float(np.max(np.abs(r64))), 1e-30)
+    ea = np.abs(a_ - r64).ravel() / scale
+    er = np.abs(r32 - r64).ravel() / scale
+    noise = float(np.quantile(er, 1.0 - outlier_frac)) if er.size > 1 else float(er.max())
+    thr = max(rtol, slack * noise)
+    frac = float(np.mean(ea > thr))
+    allowed = outlier_frac if er.size * outlier_frac >= 1.0 else 0.0
+    assert frac <= allowed, "%s: %.3g of elements beyond %.3g of fp64 (vs fp32 oracle %.3g; oracle noise %.3g)" % (
+        what, frac, thr, e32, noise)
+    return e32
