@@ -50,6 +50,16 @@ SIGNATURES = {
     "dmh_photo_tiles": (_i, [_i, _i]),
     "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _f, _f, _f, _f, _i, _i, _i,
                              _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),
+    "dmh_perspective_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_perspective_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_pgd_linf_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _st]),
+    "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),
+    "dmh_l0_adam_step": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _fl, _i,
+                              _st]),
+    "dmh_l0_finalize": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _f, _st]),
+    "dmh_topk_select": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
 }
 

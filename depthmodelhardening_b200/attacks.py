@@ -1,0 +1,236 @@
+"""Drop-in `Phy_obj_atk` (L-inf PGD) and `Phy_obj_atk_l0` (Adam + tanh mask,
+hard threshold) -- reference: /root/reference/torchattacks/attacks/
+phy_obj_atk.py and phy_obj_atk_l0.py.  Same constructor / call signatures and
+return 4-tuple; same consumption order of the Python / numpy RNGs, so seeding
+`random` and `numpy.random` reproduces the reference's placements and inits.
+
+Per iteration the reference runs 2*Ba perspective warps in a Python loop,
+composite, two Resizes, ~6 (L-inf) or ~25 (L0) elementwise launches and (L0) one
+host sync; here: one fused patch-apply launch each way, one update launch, and
+the L0 count stays on the device while `stp < steps`.
+
+Multi-GPU (one process per GPU, scenes sharded over ranks): when
+torch.distributed is initialised the patch gradient is all-reduced (mean over
+ranks) before the update, so every rank applies the identical update.
+"""
+from __future__ import annotations
+
+from random import sample
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import patch_ops
+from .physical import PhysicalTrans, ori_H, ori_W
+
+object_dataset_root = "/data3/share/kitti/object/"      # my_utils.py:11 (install() rebinds it)
+
+
+def _default_calib():
+    return f"{object_dataset_root}/training/calib/003086.txt"
+
+
+class Attack(object):
+    """Minimal mirror of torchattacks.attack.Attack (TA/attack.py:14-35, 296-320):
+    device discovery and eval/train toggling around forward()."""
+
+    def __init__(self, name, model):
+        self.attack = name
+        self.model = model
+        self.model_name = str(model).split("(")[0]
+        self.device = next(model.parameters()).device
+        self._attack_mode = "default"
+        self._targeted = False
+        self._return_type = "float"
+        self._supported_mode = ["default"]
+        self._model_training = False
+        self._batchnorm_training = False
+        self._dropout_training = False
+
+    def forward(self, *input):
+        raise NotImplementedError
+
+    def __call__(self, *input, **kwargs):
+        given_training = self.model.training
+        if self._model_training:
+            self.model.train()
+            for _, m in self.model.named_modules():
+                if not self._batchnorm_training and "BatchNorm" in m.__class__.__name__:
+                    m.eval()
+                if not self._dropout_training and "Dropout" in m.__class__.__name__:
+                    m.eval()
+        else:
+            self.model.eval()
+        images = self.forward(*input, **kwargs)
+        if given_training:
+            self.model.train()
+        return images
+
+
+def _sync_patch_grad(grad):
+    """Sum the shared patch's gradient over ranks (the ONE collective of stage 1);
+    mean so that the value equals the single-process gradient of the global-batch mean."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1:
+        torch.distributed.all_reduce(grad)
+        grad.div_(torch.distributed.get_world_size())
+    return grad
+
+
+def _tile_scenes(images, batch_size):
+    if images.size()[0] == 1:
+        return torch.cat(batch_size * [images.clone()], dim=0)
+    if images.size()[0] == batch_size:
+        return images
+    raise RuntimeError("Batch size doesn't match!")
+
+
+class Phy_obj_atk(Attack):
+    r"""Distance measure: Linf.  See reference phy_obj_atk.py:13-36."""
+
+    def __init__(self, model, obj_img, obj_mask, eps=0.3, alpha=2 / 255, steps=40, random_start=True,
+                 dist_range=list(range(5, 31, 2))):
+        super().__init__("PGD", model)
+        self.obj_img = obj_img
+        self.obj_mask = obj_mask
+        self.eps = eps
+        self.alpha = alpha
+        self.steps = steps
+        self.random_start = random_start
+        self._supported_mode = ["default", "targeted"]
+        self._targeted = True
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+
+    def _apply(self, trans, obj, scenes, z0, al):
+        co = trans._coeffs(z0, al)
+        return patch_ops.apply_patch(obj, self.obj_mask, scenes, co, self.scene_size)
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False):
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        loss = nn.MSELoss()
+        obj_img_adv = self.obj_img.clone().detach()
+        if self.random_start:
+            obj_img_adv = obj_img_adv + torch.empty_like(obj_img_adv).uniform_(-self.eps, self.eps)
+            obj_img_adv = torch.clamp(obj_img_adv, min=0, max=1).detach()
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        tr = self.phy_trans_adv
+        for _ in range(self.steps):
+            obj_img_adv.requires_grad_()
+            z0 = sample(tr.dist_range, batch_size)            # physicalTrans.py:146-155 order
+            al = sample(tr.angle_range, batch_size)
+            adv_scenes, obj_masks_out = self._apply(tr, obj_img_adv, scene_imgs, z0, al)
+            adv_depth = self.model(adv_scenes)
+            cost = -loss(adv_depth * obj_masks_out, self.depth_target)
+            grad = torch.autograd.grad(cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
+            grad = _sync_patch_grad(grad)
+            obj_img_adv = patch_ops.pgd_linf_step(obj_img_adv.detach(), grad, self.obj_img, self.alpha, self.eps)
+        tr.reset_img(obj_img_adv, self.obj_mask)
+        z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+        alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+        if eval:
+            z0_sample[0] = 7
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            adv_scenes, obj_masks_out = self._apply(tr, obj_img_adv, scene_imgs, z0_sample, alpha_sample)
+            ben_scenes, _ = self._apply(self.phy_trans_ben, self.obj_img, scene_imgs, z0_sample, alpha_sample)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
+
+
+class Phy_obj_atk_l0(Attack):
+    r"""Distance measure: L_0.  See reference phy_obj_atk_l0.py:16-41."""
+
+    def __init__(self, model, obj_img, obj_mask, adam_lr=0.5, steps=10, mask_wt=0.1, l0_thresh=1 / 10,
+                 dist_range=list(range(5, 31, 2))):
+        super().__init__("PGD", model)
+        self.obj_img = obj_img.clone().detach()
+        self.obj_mask = obj_mask.clone().detach()
+        self.steps = steps
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        self.clip_max = 1
+        self.learning_rate = adam_lr
+        self.mask_weight_init = mask_wt
+        self.mask_weight = self.mask_weight_init
+        self.l0_thresh = l0_thresh
+        self.l0_clip = self.clip_max / 255.
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.topk = None          # EXTENSION: set to an int to project onto the k largest pixels at the end
+        self._state = None
+
+    def cal_l0(self):
+        """phy_obj_atk_l0.py:43-52 -- 0-dim int64 tensor on the device."""
+        return patch_ops.l0_count(self.obj_img, self.pattern_pos_tensor.detach(), self.pattern_neg_tensor.detach(),
+                                  self.clip_max)
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False, color_jit=False):
+        img_B, img_C, img_H, img_W = images.size()
+        if img_H != ori_H or img_W != ori_W:
+            images = torch.nn.functional.interpolate(images, size=[ori_H, ori_W], mode="bilinear", align_corners=False,
+                                                     antialias=True)
+            print("image size inconsistent in l0 attack")
+        if color_jit:
+            # reference: self.color_aug is the tuple returned by ColorJitter.get_params (phy_obj_atk_l0.py:41,123)
+            raise TypeError("'tuple' object is not callable")
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        inits = []
+        for _ in range(2):                                  # phy_obj_atk_l0.py:73-83: numpy RNG, pos then neg
+            init_pattern = np.random.random(self.obj_img.size()) * self.clip_max
+            init_pattern = np.clip(init_pattern, 0.0, self.clip_max) / self.clip_max
+            inits.append(torch.Tensor(init_pattern).to(self.device))
+        st = patch_ops.L0State(self.obj_img, inits[0], inits[1], lr=self.learning_rate, betas=(0.5, 0.9),
+                               clip_max=float(self.clip_max))
+        self._state = st
+        self.pattern_pos_tensor, self.pattern_neg_tensor = st.ppos, st.pneg
+        loss = nn.MSELoss()
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        tr = self.phy_trans_adv
+        for stp in range(self.steps * 2):
+            obj_img_adv = st.compose_count(first=(stp == 0)).requires_grad_()
+            if stp >= self.steps:
+                # the early break needs the count on the host (one sync, second half only)
+                cnt = st.counts.cpu()
+                ratio = torch.tensor(float(cnt[0])) / torch.tensor(float(cnt[1]))
+                if ratio <= self.l0_thresh:
+                    self.mask_weight = 0
+                    break
+                self.mask_weight = self.mask_weight_init
+            z0 = sample(tr.dist_range, batch_size)
+            al = sample(tr.angle_range, batch_size)
+            co = tr._coeffs(z0, al)
+            adv_scenes, adv_obj_mask = patch_ops.apply_patch(obj_img_adv, self.obj_mask, scene_imgs, co,
+                                                             self.scene_size)
+            adv_depth = self.model(adv_scenes)
+            adv_cost = loss(adv_depth * adv_obj_mask, self.depth_target)
+            grad = torch.autograd.grad(adv_cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
+            grad = _sync_patch_grad(grad)
+            # mask cost gradient + clamp chain + Adam in one launch; mask_weight gated on the device
+            st.adam_step(grad, self.mask_weight_init, self.l0_thresh)
+        if self.topk is not None:
+            st.ppos, st.pneg, _ = patch_ops.topk_l0_project(st.ppos, st.pneg, int(self.topk))
+            self.pattern_pos_tensor, self.pattern_neg_tensor = st.ppos, st.pneg
+        obj_img_adv, self.pattern = st.finalize()
+        tr.reset_img(obj_img_adv, self.obj_mask)
+        z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+        alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+        if eval:
+            z0_sample[0] = 6.1
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            co = tr._coeffs(z0_sample, alpha_sample)
+            adv_scenes, obj_masks_out = patch_ops.apply_patch(obj_img_adv, self.obj_mask, scene_imgs, co,
+                                                              self.scene_size)
+            ben_scenes, _ = patch_ops.apply_patch(self.obj_img, self.obj_mask, scene_imgs, co, self.scene_size)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv

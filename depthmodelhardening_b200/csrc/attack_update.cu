@@ -1,0 +1,303 @@
+// Stage 1 -- patch update rules (A6-A8).  All of these touch < 4 MB and are
+// launch-latency bound: the point of the kernels is to replace
+// ~6 (L-inf) / ~25 (L0) ATen launches and one host sync per iteration by one
+// launch each, with the L0 count kept on the device.
+//
+//   dmh_pgd_linf_step     phy_obj_atk.py:98-100 (same 3 lines: pgd_depth.py:76-78, pgd.py:73-75)
+//   dmh_l0_compose_count  phy_obj_atk_l0.py:94-99 + cal_l0 :43-52
+//   dmh_l0_adam_step      phy_obj_atk_l0.py:130-138 (mask cost gradient + chain through the
+//                         compose clamps + torch.optim.Adam(betas=(0.5,0.9)) update)
+//   dmh_l0_finalize       phy_obj_atk_l0.py:143-150
+//   dmh_topk_select       EXTENSION: exact k-th largest by 4-pass radix
+//                         select with warp-aggregated shared-memory histograms
+#include "../../include/dmh_b200.h"
+#include "dmh_common.cuh"
+
+using namespace dmh;
+
+namespace {
+
+__device__ __forceinline__ float clamp01(float v, float hi) { return fminf(fmaxf(v, 0.0f), hi); }
+__device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+// ATen lerp: two branches so that lerp(a, b, 1) == b exactly
+__device__ __forceinline__ float lerp_aten(float a, float b, float w) {
+    return w < 0.5f ? a + w * (b - a) : b - (b - a) * (1.0f - w);
+}
+
+// --------------------------------------------------------------------------- A6
+__global__ void pgd_linf_kernel(const float* __restrict__ adv, const float* __restrict__ grad,
+                                const float* __restrict__ clean, long long n, float alpha, float eps,
+                                float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = add_rn(adv[i], mul_rn(alpha, sgnf(grad[i])));
+    const float c = clean[i];
+    const float delta = fminf(fmaxf(sub_rn(a, c), -eps), eps);
+    out[i] = fminf(fmaxf(add_rn(c, delta), 0.0f), 1.0f);
+}
+
+// --------------------------------------------------------------------------- A7
+// one thread per PIXEL (3 channels): compose the adversarial patch, count pixels
+// whose thresholded pattern is non-zero (warp ballot + one atomic per warp)
+__global__ void l0_compose_count_kernel(const float* __restrict__ obj, const float* __restrict__ ppos,
+                                        const float* __restrict__ pneg, int C, int npix, float clip_max, float thr,
+                                        float* __restrict__ adv, unsigned long long* __restrict__ count) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (p < npix) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const size_t o = (size_t)c * npix + p;
+            const float pos = clamp01(mul_rn(ppos[o], clip_max), clip_max);
+            const float neg = -clamp01(mul_rn(pneg[o], clip_max), clip_max);
+            if (adv) adv[o] = clamp01(add_rn(obj[o], add_rn(pos, neg)), clip_max);
+            const float pt = pos < thr ? 0.f : pos;
+            const float nt = neg > -thr ? 0.f : neg;
+            s = add_rn(s, fabsf(add_rn(pt, nt)));
+        }
+        alive = s != 0.f;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(count, (unsigned long long)__popc(ballot));
+}
+
+// --------------------------------------------------------------------------- A8
+// state: l0 bookkeeping kept on the device so that no host sync is needed to
+// pick mask_weight (phy_obj_atk_l0.py:102-111)
+//   counts[0] = current l0, counts[1] = l0 at step 0
+__global__ void l0_adam_kernel(const float* __restrict__ obj, const float* __restrict__ g_adv,
+                               float* __restrict__ ppos, float* __restrict__ pneg, float* __restrict__ m_pos,
+                               float* __restrict__ v_pos, float* __restrict__ m_neg, float* __restrict__ v_neg,
+                               int C, int npix, float clip_max, const unsigned long long* __restrict__ counts,
+                               float l0_thresh, float mask_weight_init, float step_size, float beta1, float beta2,
+                               float adam_eps, float bc2_sqrt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    // mask_weight = 0 once l0/l0_init <= thresh (fp32 division as torch does on the int64 tensors)
+    float mask_w = mask_weight_init;
+    if (counts) {
+        const float ratio = (float)counts[0] / (float)counts[1];
+        if (ratio <= l0_thresh) mask_w = 0.f;
+    }
+    // argmax over channels of tanh(P/10)/(2-1e-7)+0.5 (monotone in P: argmax of P, first max wins)
+    int am_p = 0, am_n = 0;
+    float best_p = ppos[p], best_n = pneg[p];
+    for (int c = 1; c < C; ++c) {
+        const float a = ppos[(size_t)c * npix + p], b = pneg[(size_t)c * npix + p];
+        if (a > best_p) { best_p = a; am_p = c; }
+        if (b > best_n) { best_n = b; am_n = c; }
+    }
+    const float mask_scale = mask_w / (float)npix;        // mean over the (1,H,W) max map
+    const float denom = 2.0f - 1e-7f;
+    for (int c = 0; c < C; ++c) {
+        const size_t o = (size_t)c * npix + p;
+        const float Pp = ppos[o], Pn = pneg[o];
+        const float pos_raw = mul_rn(Pp, clip_max), neg_raw = mul_rn(Pn, clip_max);
+        const float pos = clamp01(pos_raw, clip_max), neg = -clamp01(neg_raw, clip_max);
+        const float pre = add_rn(obj[o], add_rn(pos, neg));
+        // clamp passes gradient on the closed interval (torch.clamp backward)
+        const float pass_out = (pre >= 0.f && pre <= clip_max) ? 1.f : 0.f;
+        const float ga = g_adv ? g_adv[o] * pass_out : 0.f;
+        float gp = (pos_raw >= 0.f && pos_raw <= clip_max) ? ga * clip_max : 0.f;
+        float gn = (neg_raw >= 0.f && neg_raw <= clip_max) ? -ga * clip_max : 0.f;
+        if (mask_scale != 0.f) {
+            if (c == am_p) { const float t = tanhf(Pp / 10.0f); gp += mask_scale * (1.0f - t * t) / 10.0f / denom; }
+            if (c == am_n) { const float t = tanhf(Pn / 10.0f); gn += mask_scale * (1.0f - t * t) / 10.0f / denom; }
+        }
+        // torch.optim.Adam (single tensor): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;
+        // p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+        {
+            float m = m_pos[o], v = v_pos[o];
+            m = lerp_aten(m, gp, 1.0f - beta1);
+            v = v * beta2 + (1.0f - beta2) * gp * gp;
+            m_pos[o] = m; v_pos[o] = v;
+            ppos[o] = Pp - step_size * (m / (sqrtf(v) / bc2_sqrt + adam_eps));
+        }
+        {
+            float m = m_neg[o], v = v_neg[o];
+            m = lerp_aten(m, gn, 1.0f - beta1);
+            v = v * beta2 + (1.0f - beta2) * gn * gn;
+            m_neg[o] = m; v_neg[o] = v;
+            pneg[o] = Pn - step_size * (m / (sqrtf(v) / bc2_sqrt + adam_eps));
+        }
+    }
+}
+
+__global__ void l0_finalize_kernel(const float* __restrict__ obj, const float* __restrict__ ppos,
+                                   const float* __restrict__ pneg, long long n, float clip_max, float thr,
+                                   float* __restrict__ adv, float* __restrict__ pattern) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float pos = clamp01(mul_rn(ppos[i], clip_max), clip_max);
+    float neg = -clamp01(mul_rn(pneg[i], clip_max), clip_max);
+    if (pos < thr) pos = 0.f;
+    if (neg > -thr) neg = 0.f;
+    const float pat = add_rn(pos, neg);
+    if (pattern) pattern[i] = pat;
+    adv[i] = clamp01(add_rn(obj[i], pat), clip_max);
+}
+
+// --------------------------------------------------------------------------- top-k (extension)
+// magnitude per pixel = max_c max(clamp(P+), clamp(P-)); keep the k largest
+// (ties -> lower pixel index).  Single CTA, 4 radix passes over the fp32 bit
+// pattern (non-negative floats order like unsigned ints), 256-bin histograms in
+// shared memory filled with warp-aggregated atomics (__match_any_sync).
+#define TK_THREADS 1024
+
+__device__ __forceinline__ unsigned pixel_key(const float* __restrict__ ppos, const float* __restrict__ pneg, int C,
+                                              int npix, int p) {
+    float m = 0.f;
+    for (int c = 0; c < C; ++c) {
+        m = fmaxf(m, clamp01(ppos[(size_t)c * npix + p], 1.0f));
+        m = fmaxf(m, clamp01(pneg[(size_t)c * npix + p], 1.0f));
+    }
+    return __float_as_uint(m);
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_select_kernel(float* __restrict__ ppos, float* __restrict__ pneg, int C, int npix, int k,
+                   unsigned char* __restrict__ keep_out, unsigned* __restrict__ kth_key_out) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining, s_tie_budget;
+    const int tid = threadIdx.x;
+    unsigned prefix = 0, prefix_mask = 0;
+    unsigned remaining = (unsigned)k;                     // how many still to take among keys matching the prefix
+    if (k <= 0 || k >= npix) {
+        for (int p = tid; p < npix; p += TK_THREADS) {
+            const bool keep = k >= npix;
+            if (keep_out) keep_out[p] = keep;
+            if (!keep)
+                for (int c = 0; c < C; ++c) { ppos[(size_t)c * npix + p] = 0.f; pneg[(size_t)c * npix + p] = 0.f; }
+        }
+        if (tid == 0 && kth_key_out) *kth_key_out = 0u;
+        return;
+    }
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int base = 0; base < npix; base += TK_THREADS) {
+            const int p = base + tid;
+            const bool valid = p < npix;
+            unsigned key = valid ? pixel_key(ppos, pneg, C, npix, p) : 0u;
+            const bool match = valid && ((key & prefix_mask) == prefix);
+            const unsigned bin = match ? ((key >> shift) & 255u) : 0xffffffffu;
+            // warp-aggregated histogram update: one atomic per distinct bin per warp
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (match && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // walk bins from the largest digit down until `remaining` is covered
+            unsigned acc = 0;
+            int d = 255;
+            for (; d > 0; --d) {
+                if (acc + hist[d] >= remaining) break;
+                acc += hist[d];
+            }
+            s_prefix = prefix | ((unsigned)d << shift);
+            s_remaining = remaining - acc;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        prefix_mask |= 255u << shift;
+        __syncthreads();
+    }
+    // prefix == k-th largest key; `remaining` of the pixels equal to it are kept (lowest indices first)
+    if (tid == 0) { s_tie_budget = remaining; if (kth_key_out) *kth_key_out = prefix; }
+    __syncthreads();
+    // ordered tie resolution: chunks processed in index order, warp-prefix inside a chunk
+    __shared__ unsigned warp_ties[TK_THREADS / 32];
+    __shared__ unsigned chunk_base;
+    if (tid == 0) chunk_base = 0;
+    __syncthreads();
+    for (int base = 0; base < npix; base += TK_THREADS) {
+        const int p = base + tid;
+        const bool valid = p < npix;
+        const unsigned key = valid ? pixel_key(ppos, pneg, C, npix, p) : 0u;
+        const bool tie = valid && key == prefix;
+        const unsigned ballot = __ballot_sync(0xffffffffu, tie);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) warp_ties[wid] = __popc(ballot);
+        __syncthreads();
+        unsigned before = chunk_base;
+        for (int w = 0; w < wid; ++w) before += warp_ties[w];
+        before += __popc(ballot & ((1u << lane) - 1u));
+        const bool keep = valid && (key > prefix || (tie && before < s_tie_budget));
+        if (valid) {
+            if (keep_out) keep_out[p] = keep;
+            if (!keep)
+                for (int c = 0; c < C; ++c) { ppos[(size_t)c * npix + p] = 0.f; pneg[(size_t)c * npix + p] = 0.f; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < TK_THREADS / 32; ++w) t += warp_ties[w];
+            chunk_base += t;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
+                      float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(adv && grad && clean && out && n > 0, "dmh_pgd_linf_step: null pointer or n <= 0");
+    DMH_LAUNCH(pgd_linf_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(adv, grad, clean, n, alpha, eps, out);
+    DMH_CHECK_LAUNCH("dmh_pgd_linf_step");
+    return DMH_OK;
+}
+
+int dmh_l0_compose_count(const float* obj, const float* pattern_pos, const float* pattern_neg, int C, int H, int W,
+                         float clip_max, float threshold, float* adv, unsigned long long* count,
+                         dmh_stream_t stream) {
+    DMH_REQUIRE(obj && pattern_pos && pattern_neg && count, "dmh_l0_compose_count: null pointer");
+    DMH_REQUIRE(C > 0 && H > 0 && W > 0, "dmh_l0_compose_count: bad shape");
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dmh_l0_compose_count: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+    const int npix = H * W;
+    DMH_LAUNCH(l0_compose_count_kernel, ceil_div(npix, 256), 256, 0, (cudaStream_t)stream)(
+        obj, pattern_pos, pattern_neg, C, npix, clip_max, threshold, adv, count);
+    DMH_CHECK_LAUNCH("dmh_l0_compose_count");
+    return DMH_OK;
+}
+
+int dmh_l0_adam_step(const float* obj, const float* grad_adv, float* pattern_pos, float* pattern_neg, float* m_pos,
+                     float* v_pos, float* m_neg, float* v_neg, int C, int H, int W, float clip_max,
+                     const unsigned long long* counts, float l0_thresh, float mask_weight, float lr, float beta1,
+                     float beta2, float adam_eps, int step, dmh_stream_t stream) {
+    DMH_REQUIRE(obj && pattern_pos && pattern_neg && m_pos && v_pos && m_neg && v_neg, "dmh_l0_adam_step: null pointer");
+    DMH_REQUIRE(C > 0 && H > 0 && W > 0 && step >= 1, "dmh_l0_adam_step: bad shape or step < 1");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const int npix = H * W;
+    DMH_LAUNCH(l0_adam_kernel, ceil_div(npix, 256), 256, 0, (cudaStream_t)stream)(
+        obj, grad_adv, pattern_pos, pattern_neg, m_pos, v_pos, m_neg, v_neg, C, npix, clip_max, counts, l0_thresh,
+        mask_weight, (float)((double)lr / bc1), beta1, beta2, adam_eps, (float)sqrt(bc2));
+    DMH_CHECK_LAUNCH("dmh_l0_adam_step");
+    return DMH_OK;
+}
+
+int dmh_l0_finalize(const float* obj, const float* pattern_pos, const float* pattern_neg, long long n, float clip_max,
+                    float threshold, float* adv, float* pattern, dmh_stream_t stream) {
+    DMH_REQUIRE(obj && pattern_pos && pattern_neg && adv && n > 0, "dmh_l0_finalize: null pointer or n <= 0");
+    DMH_LAUNCH(l0_finalize_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(obj, pattern_pos, pattern_neg, n, clip_max,
+                                                                                threshold, adv, pattern);
+    DMH_CHECK_LAUNCH("dmh_l0_finalize");
+    return DMH_OK;
+}
+
+int dmh_topk_select(float* pattern_pos, float* pattern_neg, int C, int H, int W, int k, unsigned char* keep,
+                    unsigned* kth_key, dmh_stream_t stream) {
+    DMH_REQUIRE(pattern_pos && pattern_neg, "dmh_topk_select: null pointer");
+    DMH_REQUIRE(C > 0 && H > 0 && W > 0, "dmh_topk_select: bad shape");
+    DMH_LAUNCH(topk_select_kernel, 1, TK_THREADS, 0, (cudaStream_t)stream)(pattern_pos, pattern_neg, C, H * W, k, keep, kth_key);
+    DMH_CHECK_LAUNCH("dmh_topk_select");
+    return DMH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,407 @@
+// Stage 1 -- physical patch attack kernels.
+//
+//   dmh_perspective_fwd/bwd   PhysicalTrans.project / project_w_trans
+//                             (physicalTrans.py:130-196): Pad -> torchvision
+//                             perspective (bilinear, zeros, align_corners=False)
+//                             for the whole batch in one launch.
+//   dmh_patch_apply_fwd/bwd   the attack inner loop fused
+//                             (phy_obj_atk.py:86-90, phy_obj_atk_l0.py:115-119):
+//                             perspective warp of patch+mask, composite
+//                             scene*(1-m)+obj*m, anti-aliased bilinear Resize of
+//                             scene and mask to 320x1024 -- canvas-resolution
+//                             intermediates never touch HBM.
+//
+// Roofline: HBM.  Algorithmic bytes per attack-batch item (fp32):
+//   fwd  read scene 12*375*1242 + write adv 12*320*1024 + mask 4*320*1024 = 10.83 MB
+//   bwd  read upstream 12*320*1024 = 3.93 MB (+ patch/mask/grad 3.7 MB once)
+//
+// torchvision arithmetic restated (installed 0.26):
+//   grid  : _functional_tensor.py:672-698 (_perspective_grid, pixel centres +0.5)
+//   sample: grid_sample(bilinear, zeros, align_corners=False) (:545-561)
+//   resize: F.interpolate(bilinear, antialias=True, align_corners=False)
+//           (ATen UpSample.cuh upsample_antialias::_compute_weights*)
+#include "../../include/dmh_b200.h"
+#include "dmh_common.cuh"
+
+using namespace dmh;
+
+namespace {
+
+// ---------------------------------------------------------------------------
+struct Homography {           // per item, rescaled as torchvision does
+    float ax, bx, cx;         // theta1 row 0 / (0.5*ow)
+    float ay, by, cy;         // theta1 row 1 / (0.5*oh)
+    float g, h;               // theta2
+};
+
+__device__ __forceinline__ Homography load_homography(const float* __restrict__ coeffs, int b, int ow, int oh) {
+    const float* c = coeffs + b * 8;
+    Homography hm;
+    const float hx = 0.5f * (float)ow, hy = 0.5f * (float)oh;
+    hm.ax = div_rn(__ldg(c + 0), hx); hm.bx = div_rn(__ldg(c + 1), hx); hm.cx = div_rn(__ldg(c + 2), hx);
+    hm.ay = div_rn(__ldg(c + 3), hy); hm.by = div_rn(__ldg(c + 4), hy); hm.cy = div_rn(__ldg(c + 5), hy);
+    hm.g = __ldg(c + 6); hm.h = __ldg(c + 7);
+    return hm;
+}
+
+// source coordinates (in canvas pixels) sampled by output canvas pixel (px,py)
+__device__ __forceinline__ void perspective_src(const Homography& hm, int px, int py, int ow, int oh, float& ix,
+                                                float& iy) {
+    const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+    float n1 = x * hm.ax; n1 = fmaf(y, hm.bx, n1); n1 = add_rn(n1, hm.cx);
+    float n2 = x * hm.ay; n2 = fmaf(y, hm.by, n2); n2 = add_rn(n2, hm.cy);
+    float d = x * hm.g;   d = fmaf(y, hm.h, d);    d = add_rn(d, 1.0f);
+    const float gx = sub_rn(div_rn(n1, d), 1.0f);
+    const float gy = sub_rn(div_rn(n2, d), 1.0f);
+    ix = safe_coord(unnormalise_coord(gx, ow, false));
+    iy = safe_coord(unnormalise_coord(gy, oh, false));
+}
+
+// bilinear taps of the zero-PADDED patch canvas: a tap contributes iff it lies
+// inside the canvas (zeros padding) and inside the patch rectangle (pad value 0)
+struct PatchTaps {
+    int px0, py0;             // north-west tap in PATCH coordinates
+    float w[4];               // nw, ne, sw, se (0 where the tap is invalid)
+    bool any;
+};
+
+__device__ __forceinline__ PatchTaps patch_taps(float ix, float iy, int ow, int oh, int l_pad, int t_pad, int pw,
+                                                int ph) {
+    const Bilinear bl = bilinear_setup(ix, iy);
+    PatchTaps t;
+    t.px0 = bl.x0 - l_pad;
+    t.py0 = bl.y0 - t_pad;
+    const bool x0 = bl.x0 >= 0 && bl.x0 < ow && t.px0 >= 0 && t.px0 < pw;
+    const bool x1 = bl.x0 + 1 >= 0 && bl.x0 + 1 < ow && t.px0 + 1 >= 0 && t.px0 + 1 < pw;
+    const bool y0 = bl.y0 >= 0 && bl.y0 < oh && t.py0 >= 0 && t.py0 < ph;
+    const bool y1 = bl.y0 + 1 >= 0 && bl.y0 + 1 < oh && t.py0 + 1 >= 0 && t.py0 + 1 < ph;
+    t.w[0] = (x0 && y0) ? bl.wnw : 0.f;
+    t.w[1] = (x1 && y0) ? bl.wne : 0.f;
+    t.w[2] = (x0 && y1) ? bl.wsw : 0.f;
+    t.w[3] = (x1 && y1) ? bl.wse : 0.f;
+    t.any = (x0 || x1) && (y0 || y1);
+    return t;
+}
+
+__device__ __forceinline__ float sample_plane(const float* __restrict__ p, const PatchTaps& t, int pw) {
+    const long long o = (long long)t.py0 * pw + t.px0;
+    float acc = 0.f;
+    if (t.w[0] != 0.f) acc = fmaf(__ldg(p + o), t.w[0], acc);
+    if (t.w[1] != 0.f) acc = fmaf(__ldg(p + o + 1), t.w[1], acc);
+    if (t.w[2] != 0.f) acc = fmaf(__ldg(p + o + pw), t.w[2], acc);
+    if (t.w[3] != 0.f) acc = fmaf(__ldg(p + o + pw + 1), t.w[3], acc);
+    return acc;
+}
+
+// --------------------------------------------------------------------------- perspective (canvas resolution)
+__global__ void perspective_fwd_kernel(const float* __restrict__ img, const float* __restrict__ coeffs, int C, int ph,
+                                       int pw, int oh, int ow, int l_pad, int t_pad, float* __restrict__ out) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= ow || py >= oh) return;
+    const int b = blockIdx.z;
+    const Homography hm = load_homography(coeffs, b, ow, oh);
+    float ix, iy;
+    perspective_src(hm, px, py, ow, oh, ix, iy);
+    const PatchTaps t = patch_taps(ix, iy, ow, oh, l_pad, t_pad, pw, ph);
+    const size_t N = (size_t)oh * ow;
+    for (int c = 0; c < C; ++c)
+        out[((size_t)b * C + c) * N + (size_t)py * ow + px] = t.any ? sample_plane(img + (size_t)c * ph * pw, t, pw) : 0.f;
+}
+
+__global__ void perspective_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ coeffs, int C, int ph,
+                                       int pw, int oh, int ow, int l_pad, int t_pad, float* __restrict__ gimg) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= ow || py >= oh) return;
+    const int b = blockIdx.z;
+    const Homography hm = load_homography(coeffs, b, ow, oh);
+    float ix, iy;
+    perspective_src(hm, px, py, ow, oh, ix, iy);
+    const PatchTaps t = patch_taps(ix, iy, ow, oh, l_pad, t_pad, pw, ph);
+    if (!t.any) return;
+    const size_t N = (size_t)oh * ow;
+    const long long o = (long long)t.py0 * pw + t.px0;
+    for (int c = 0; c < C; ++c) {
+        const float g = gout[((size_t)b * C + c) * N + (size_t)py * ow + px];
+        if (g == 0.f) continue;
+        float* gp = gimg + (size_t)c * ph * pw;
+        if (t.w[0] != 0.f) atomicAdd(gp + o, t.w[0] * g);
+        if (t.w[1] != 0.f) atomicAdd(gp + o + 1, t.w[1] * g);
+        if (t.w[2] != 0.f) atomicAdd(gp + o + pw, t.w[2] * g);
+        if (t.w[3] != 0.f) atomicAdd(gp + o + pw + 1, t.w[3] * g);
+    }
+}
+
+// --------------------------------------------------------------------------- anti-aliased bilinear weights
+#define AA_MAXT 8
+struct AaSpan { int lo, n; float w[AA_MAXT]; };
+
+__device__ __forceinline__ float aa_filter(float x) { x = fabsf(x); return x < 1.0f ? 1.0f - x : 0.0f; }
+
+__device__ __forceinline__ AaSpan aa_span(int i, int in_size, float scale) {
+    AaSpan s;
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * ((float)i + 0.5f);
+    s.lo = max((int)(center - support + 0.5f), 0);
+    s.n = min((int)(center + support + 0.5f), in_size) - s.lo;
+    s.n = min(s.n, AA_MAXT);
+    float total = 0.f;
+#pragma unroll
+    for (int j = 0; j < AA_MAXT; ++j) {
+        float w = 0.f;
+        if (j < s.n) w = aa_filter(((float)j + ((float)s.lo - center) + 0.5f) * invscale);
+        s.w[j] = w;
+        total += w;
+    }
+    if (total != 0.f) {
+#pragma unroll
+        for (int j = 0; j < AA_MAXT; ++j) s.w[j] = s.w[j] / total;
+    }
+    return s;
+}
+
+// --------------------------------------------------------------------------- fused apply: forward
+#define PA_TW 64            // output tile width
+#define PA_TH 16            // output tile height
+#define PA_THREADS 256
+
+__global__ void __launch_bounds__(PA_THREADS)
+patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
+                       const float* __restrict__ scenes, const float* __restrict__ coeffs, int ph, int pw, int ih,
+                       int iw, int oh, int ow, int l_pad, int t_pad, float sy, float sx, int cw_max, int ch_max,
+                       float* __restrict__ adv, float* __restrict__ mask_out) {
+    extern __shared__ float smem[];
+    float* comp = smem;                                   // [4][ch_max][cw_max] : 3 colour planes + mask
+    __shared__ int x_lo[PA_TW], x_n[PA_TW], y_lo[PA_TH], y_n[PA_TH];
+    __shared__ float x_w[PA_TW][AA_MAXT], y_w[PA_TH][AA_MAXT];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * PA_TW, oy0 = blockIdx.y * PA_TH;
+    if (tid < PA_TW) {
+        const int ox = min(ox0 + tid, ow - 1);
+        const AaSpan s = aa_span(ox, iw, sx);
+        x_lo[tid] = s.lo; x_n[tid] = s.n;
+#pragma unroll
+        for (int j = 0; j < AA_MAXT; ++j) x_w[tid][j] = s.w[j];
+    } else if (tid < PA_TW + PA_TH) {
+        const int k = tid - PA_TW;
+        const int oy = min(oy0 + k, oh - 1);
+        const AaSpan s = aa_span(oy, ih, sy);
+        y_lo[k] = s.lo; y_n[k] = s.n;
+#pragma unroll
+        for (int j = 0; j < AA_MAXT; ++j) y_w[k][j] = s.w[j];
+    }
+    __syncthreads();
+    const int cx0 = x_lo[0], cy0 = y_lo[0];
+    const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
+    const int cw = min(x_lo[last_x] + x_n[last_x] - cx0, cw_max);
+    const int ch = min(y_lo[last_y] + y_n[last_y] - cy0, ch_max);
+    const Homography hm = load_homography(coeffs, b, iw, ih);
+    const size_t IN = (size_t)ih * iw;
+    const float* sc = scenes + (size_t)b * 3 * IN;
+    const size_t plane = (size_t)ch_max * cw_max;
+    const size_t PN = (size_t)ph * pw;
+    for (int i = tid; i < ch * cw; i += PA_THREADS) {
+        const int r = i / cw, c = i % cw;
+        const int cy = cy0 + r, cx = cx0 + c;            // always inside the canvas by construction of the spans
+        float ix, iy;
+        perspective_src(hm, cx, cy, iw, ih, ix, iy);
+        const PatchTaps t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+        const size_t so = (size_t)cy * iw + cx;
+        const float s0 = __ldg(sc + so), s1 = __ldg(sc + IN + so), s2 = __ldg(sc + 2 * IN + so);
+        float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        if (t.any) {
+            m = sample_plane(pmask, t, pw);
+            o0 = sample_plane(patch, t, pw);
+            o1 = sample_plane(patch + PN, t, pw);
+            o2 = sample_plane(patch + 2 * PN, t, pw);
+        }
+        const float om = sub_rn(1.0f, m);
+        const size_t o = (size_t)r * cw_max + c;
+        comp[o] = add_rn(mul_rn(s0, om), mul_rn(o0, m));
+        comp[plane + o] = add_rn(mul_rn(s1, om), mul_rn(o1, m));
+        comp[2 * plane + o] = add_rn(mul_rn(s2, om), mul_rn(o2, m));
+        comp[3 * plane + o] = m;
+    }
+    __syncthreads();
+    const int tx = tid % PA_TW;
+    const int ox = ox0 + tx;
+    if (ox >= ow) return;
+    const int xl = x_lo[tx] - cx0, xn = x_n[tx];
+    const size_t ON = (size_t)oh * ow;
+#pragma unroll
+    for (int k = 0; k < PA_TH / (PA_THREADS / PA_TW); ++k) {
+        const int ty = tid / PA_TW + k * (PA_THREADS / PA_TW);
+        const int oy = oy0 + ty;
+        if (oy >= oh) continue;
+        const int yl = y_lo[ty] - cy0, yn = y_n[ty];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < yn; ++j) {
+            const float wy = y_w[ty][j];
+            const float* row = comp + (size_t)(yl + j) * cw_max + xl;
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < xn; ++i) {
+                const float wx = x_w[tx][i];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) h[p] = fmaf(row[p * plane + i], wx, h[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p] = fmaf(h[p], wy, acc[p]);
+        }
+        const size_t oo = (size_t)oy * ow + ox;
+        adv[((size_t)b * 3 + 0) * ON + oo] = acc[0];
+        adv[((size_t)b * 3 + 1) * ON + oo] = acc[1];
+        adv[((size_t)b * 3 + 2) * ON + oo] = acc[2];
+        if (mask_out) mask_out[(size_t)b * ON + oo] = acc[3];
+    }
+}
+
+// --------------------------------------------------------------------------- fused apply: backward (to the patch)
+// One thread per canvas pixel: exits unless the pixel samples the patch; gathers
+// the transposed anti-aliased resize of the upstream gradient, multiplies by the
+// warped mask, scatters to the <=4 patch taps (RED.ADD; all batch items share
+// the one patch, which is why this is a scatter).
+__device__ __forceinline__ float aa_weight_of(int o, int in_size, float scale, int ci) {
+    // weight with which output index o reads input index ci (0 if outside its span)
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * ((float)o + 0.5f);
+    const int lo = max((int)(center - support + 0.5f), 0);
+    int n = min((int)(center + support + 0.5f), in_size) - lo;
+    n = min(n, AA_MAXT);
+    if (ci < lo || ci >= lo + n) return 0.f;
+    float total = 0.f, mine = 0.f;
+    for (int j = 0; j < n; ++j) {
+        const float w = aa_filter(((float)j + ((float)lo - center) + 0.5f) * invscale);
+        total += w;
+        if (lo + j == ci) mine = w;
+    }
+    return total != 0.f ? mine / total : mine;
+}
+
+__global__ void __launch_bounds__(256)
+patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__ pmask,
+                       const float* __restrict__ coeffs, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
+                       int t_pad, float sy, float sx, float* __restrict__ gpatch) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= iw || cy >= ih) return;
+    const int b = blockIdx.z;
+    const Homography hm = load_homography(coeffs, b, iw, ih);
+    float ix, iy;
+    perspective_src(hm, cx, cy, iw, ih, ix, iy);
+    const PatchTaps t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+    if (!t.any) return;
+    const float m = sample_plane(pmask, t, pw);
+    if (m == 0.f) return;
+    // outputs whose anti-aliasing window covers this canvas pixel
+    const float supx = sx >= 1.0f ? sx : 1.0f, supy = sy >= 1.0f ? sy : 1.0f;
+    const int ox_a = max(0, (int)floorf(((float)cx - supx - 0.5f) / sx) - 1);
+    const int ox_b = min(ow - 1, (int)ceilf(((float)cx + supx + 0.5f) / sx) + 1);
+    const int oy_a = max(0, (int)floorf(((float)cy - supy - 0.5f) / sy) - 1);
+    const int oy_b = min(oh - 1, (int)ceilf(((float)cy + supy + 0.5f) / sy) + 1);
+    const size_t ON = (size_t)oh * ow;
+    const float* g = gadv + (size_t)b * 3 * ON;
+    float gc[3] = {0.f, 0.f, 0.f};
+    for (int oy = oy_a; oy <= oy_b; ++oy) {
+        const float wy = aa_weight_of(oy, ih, sy, cy);
+        if (wy == 0.f) continue;
+        for (int ox = ox_a; ox <= ox_b; ++ox) {
+            const float w = wy * aa_weight_of(ox, iw, sx, cx);
+            if (w == 0.f) continue;
+            const size_t oo = (size_t)oy * ow + ox;
+            gc[0] = fmaf(w, __ldg(g + oo), gc[0]);
+            gc[1] = fmaf(w, __ldg(g + ON + oo), gc[1]);
+            gc[2] = fmaf(w, __ldg(g + 2 * ON + oo), gc[2]);
+        }
+    }
+    const size_t PN = (size_t)ph * pw;
+    const long long o = (long long)t.py0 * pw + t.px0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float gv = gc[c] * m;                       // d comp / d obj_warp = m
+        if (gv == 0.f) continue;
+        float* gp = gpatch + c * PN;
+        if (t.w[0] != 0.f) atomicAdd(gp + o, t.w[0] * gv);
+        if (t.w[1] != 0.f) atomicAdd(gp + o + 1, t.w[1] * gv);
+        if (t.w[2] != 0.f) atomicAdd(gp + o + pw, t.w[2] * gv);
+        if (t.w[3] != 0.f) atomicAdd(gp + o + pw + 1, t.w[3] * gv);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmh_perspective_fwd(const float* img, const float* coeffs, int B, int C, int ph, int pw, int oh, int ow,
+                        float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(img && coeffs && out, "dmh_perspective_fwd: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && ph > 0 && pw > 0 && oh >= ph && ow >= pw,
+                "dmh_perspective_fwd: bad shape (patch %dx%d, canvas %dx%d)", ph, pw, oh, ow);
+    const int l_pad = (ow - pw) / 2, t_pad = (oh - ph) / 2;
+    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8), B);
+    DMH_LAUNCH(perspective_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(img, coeffs, C, ph, pw, oh, ow, l_pad, t_pad, out);
+    DMH_CHECK_LAUNCH("dmh_perspective_fwd");
+    return DMH_OK;
+}
+
+int dmh_perspective_bwd(const float* grad_out, const float* coeffs, int B, int C, int ph, int pw, int oh, int ow,
+                        float* grad_img, dmh_stream_t stream) {
+    DMH_REQUIRE(grad_out && coeffs && grad_img, "dmh_perspective_bwd: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && ph > 0 && pw > 0 && oh >= ph && ow >= pw, "dmh_perspective_bwd: bad shape");
+    const int l_pad = (ow - pw) / 2, t_pad = (oh - ph) / 2;
+    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8), B);
+    DMH_LAUNCH(perspective_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_out, coeffs, C, ph, pw, oh, ow, l_pad, t_pad,
+                                                                          grad_img);
+    DMH_CHECK_LAUNCH("dmh_perspective_bwd");
+    return DMH_OK;
+}
+
+static int aa_tile_extent(int tile, float scale) {
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    return (int)(scale * tile + 2.0f * support + 3.0f);
+}
+
+int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs, int B,
+                        int ph, int pw, int ih, int iw, int oh, int ow, float* adv, float* mask_out,
+                        dmh_stream_t stream) {
+    DMH_REQUIRE(patch && patch_mask && scenes && coeffs && adv, "dmh_patch_apply_fwd: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && ih >= ph && iw >= pw && oh > 0 && ow > 0,
+                "dmh_patch_apply_fwd: bad shape");
+    const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
+    DMH_REQUIRE(sy < 3.0f && sx < 3.0f, "dmh_patch_apply_fwd: down-scale factor >= 3 unsupported (AA window > %d taps)", AA_MAXT);
+    const int l_pad = (iw - pw) / 2, t_pad = (ih - ph) / 2;
+    const int cw_max = aa_tile_extent(PA_TW, sx), ch_max = aa_tile_extent(PA_TH, sy);
+    const size_t smem = sizeof(float) * 4 * (size_t)cw_max * ch_max;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(patch_apply_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("dmh_patch_apply_fwd: %zu B shared memory unavailable: %s", smem, cudaGetErrorString(e));
+            return DMH_ERR_CUDA;
+        }
+    }
+    dim3 grid(ceil_div(ow, PA_TW), ceil_div(oh, PA_TH), B);
+    DMH_LAUNCH(patch_apply_fwd_kernel, grid, PA_THREADS, smem, (cudaStream_t)stream)(
+        patch, patch_mask, scenes, coeffs, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv, mask_out);
+    DMH_CHECK_LAUNCH("dmh_patch_apply_fwd");
+    return DMH_OK;
+}
+
+int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, int B, int ph, int pw,
+                        int ih, int iw, int oh, int ow, float* grad_patch, dmh_stream_t stream) {
+    DMH_REQUIRE(grad_adv && patch_mask && coeffs && grad_patch, "dmh_patch_apply_bwd: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && ih >= ph && iw >= pw && oh > 0 && ow > 0,
+                "dmh_patch_apply_bwd: bad shape");
+    const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
+    DMH_REQUIRE(sy < 3.0f && sx < 3.0f, "dmh_patch_apply_bwd: down-scale factor >= 3 unsupported");
+    const int l_pad = (iw - pw) / 2, t_pad = (ih - ph) / 2;
+    dim3 block(32, 8), grid(ceil_div(iw, 32), ceil_div(ih, 8), B);
+    DMH_LAUNCH(patch_apply_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_adv, patch_mask, coeffs, ph, pw, ih, iw, oh, ow,
+                                                                          l_pad, t_pad, sy, sx, grad_patch);
+    DMH_CHECK_LAUNCH("dmh_patch_apply_bwd");
+    return DMH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+"""Stage-1 host side: patch placement geometry (host, fp64), homography solve
+(one batched fp64 least-squares instead of 2*Ba sequential ones), and the
+autograd wrappers of the patch kernels.
+
+Reference lines mirrored (paths under /root/reference):
+  physicalTrans.py:62-105   fromZA2Coord / objPosOnImage (corner projection, int32 truncation)
+  physicalTrans.py:107-122  padding_img (centre pad -> start corners)
+  torchvision functional.py:674-704  _get_perspective_coeffs (fp64 gels, cast to fp32)
+"""
+from __future__ import annotations
+
+from math import cos, radians, sin
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, stream
+
+ORI_H, ORI_W = 375, 1242            # my_utils.py:12-13
+VEH_H, VEH_W, CAM_H = 1.6, 1.82, 1.65   # physicalTrans.py:40-42 (BMW)
+# KITTI object calib 003086 P2 as printed in physicalTrans.py:208-213 (used for synthetic runs)
+KITTI_P2_003086 = (7.215377e+02, 0.0, 6.095593e+02, 4.485728e+01,
+                   0.0, 7.215377e+02, 1.728540e+02, 2.163791e-01,
+                   0.0, 0.0, 1.0, 2.745884e-03)
+
+
+def _lib_():
+    return _lib.load()
+
+
+# ----------------------------------------------------------------------------- geometry (host)
+def plane_corners(z0: float, alpha: float) -> np.ndarray:
+    """World corners tl,tr,br,bl of the vehicle plane (physicalTrans.py:83-105)."""
+    off_x = cos(radians(alpha)) * VEH_W / 2
+    off_z = sin(radians(alpha)) * VEH_W / 2
+    yc = CAM_H - VEH_H / 2
+    y1, y2 = yc - VEH_H / 2, yc + VEH_H / 2
+    return np.array([[-off_x, y1, z0 - off_z], [off_x, y1, z0 + off_z], [off_x, y2, z0 + off_z],
+                     [-off_x, y2, z0 - off_z]], dtype=np.float64)
+
+
+def project_corners(z0: float, alpha: float, P34: np.ndarray, K: Optional[np.ndarray] = None,
+                    T: Optional[np.ndarray] = None) -> np.ndarray:
+    """(4,2) int32 image corners: objPosOnImage (physicalTrans.py:62-81) and the
+    project_w_trans variant (:175-189)."""
+    pts = plane_corners(z0, alpha)
+    hom = np.concatenate((pts.T, np.ones((1, 4))), axis=0)
+    if K is not None:
+        P = K[:3, :] if T is None else np.matmul(K, T)[:3, :]
+        cam = np.matmul(P, hom)
+        return (cam[:2, :] / (cam[[2], :] + 1e-7)).T.astype(np.int32)
+    if T is not None:
+        pts = np.matmul(T, hom).T[:, :3]
+        hom = np.concatenate((pts.T, np.ones((1, 4))), axis=0)
+    uvw = np.dot(hom.T, np.transpose(P34))
+    uvw[:, 0] /= uvw[:, 2]
+    uvw[:, 1] /= uvw[:, 2]
+    return uvw[:, 0:2].astype(np.int32)
+
+
+def start_corners(obj_hw, canvas_hw=(ORI_H, ORI_W)):
+    """Corners of the centred, zero-padded patch on the canvas (physicalTrans.py:107-122)."""
+    h, w = obj_hw
+    H, W = canvas_hw
+    l, t = (W - w) // 2, (H - h) // 2
+    return [[l, t], [l + w, t], [l + w, t + h], [l, t + h]]
+
+
+def solve_homographies(start: Sequence, ends: np.ndarray) -> torch.Tensor:
+    """(Ba,8) fp32 coefficients mapping output pixel -> input pixel; one batched
+    fp64 `gels` solve (torchvision solves them one by one, on the host, per call)."""
+    ends = np.asarray(ends, dtype=np.float64).reshape(-1, 4, 2)
+    n = ends.shape[0]
+    A = torch.zeros(n, 8, 8, dtype=torch.float64)
+    st = torch.tensor(start, dtype=torch.float64)          # (4,2)
+    en = torch.from_numpy(ends)                             # (n,4,2)
+    for i in range(4):
+        ex, ey = en[:, i, 0], en[:, i, 1]
+        sx, sy = st[i, 0], st[i, 1]
+        A[:, 2 * i, 0], A[:, 2 * i, 1], A[:, 2 * i, 2] = ex, ey, 1.0
+        A[:, 2 * i, 6], A[:, 2 * i, 7] = -sx * ex, -sx * ey
+        A[:, 2 * i + 1, 3], A[:, 2 * i + 1, 4], A[:, 2 * i + 1, 5] = ex, ey, 1.0
+        A[:, 2 * i + 1, 6], A[:, 2 * i + 1, 7] = -sy * ex, -sy * ey
+    rhs = st.reshape(8).unsqueeze(0).expand(n, 8).unsqueeze(-1)
+    sol = torch.linalg.lstsq(A, rhs, driver="gels").solution.squeeze(-1)
+    return sol.to(torch.float32).contiguous()
+
+
+def homographies(z0s, alphas, P34, K=None, T=None, obj_hw=(260, 300), canvas_hw=(ORI_H, ORI_W)) -> torch.Tensor:
+    ends = np.stack([project_corners(z, a, P34, K, T) for z, a in zip(z0s, alphas)])
+    return solve_homographies(start_corners(obj_hw, canvas_hw), ends)
+
+
+# ----------------------------------------------------------------------------- perspective (canvas resolution)
+class _Perspective(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, coeffs, oh, ow):
+        im, co = f32c(img), f32c(coeffs)
+        _, Cc, ph, pw = im.shape
+        B = co.shape[0]
+        out = torch.empty(B, Cc, oh, ow, device=im.device, dtype=torch.float32)
+        check(_lib_().dmh_perspective_fwd(ptr(im), ptr(co), B, Cc, ph, pw, oh, ow, ptr(out), stream()),
+              "perspective_fwd")
+        ctx.save_for_backward(co)
+        ctx.dims = (B, Cc, ph, pw, oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (co,) = ctx.saved_tensors
+        B, Cc, ph, pw, oh, ow = ctx.dims
+        g = f32c(g_out)
+        gi = torch.zeros(1, Cc, ph, pw, device=g.device, dtype=torch.float32)
+        check(_lib_().dmh_perspective_bwd(ptr(g), ptr(co), B, Cc, ph, pw, oh, ow, ptr(gi), stream()),
+              "perspective_bwd")
+        return gi, None, None, None
+
+
+def perspective_batch(img, coeffs, canvas_hw=(ORI_H, ORI_W)):
+    """img (1,C,h,w) -> (Ba,C,H,W): Pad + torchvision.perspective for every item."""
+    if img.shape[0] != 1:
+        raise RuntimeError("perspective_batch expects a single (1,C,h,w) image shared by the batch")
+    return _Perspective.apply(img, coeffs, int(canvas_hw[0]), int(canvas_hw[1]))
+
+
+# ----------------------------------------------------------------------------- fused apply
+class _PatchApply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, obj, mask, scenes, coeffs, oh, ow):
+        o, m, s, co = f32c(obj), f32c(mask), f32c(scenes), f32c(coeffs)
+        _, _, ph, pw = o.shape
+        B, _, ih, iw = s.shape
+        adv = torch.empty(B, 3, oh, ow, device=o.device, dtype=torch.float32)
+        mout = torch.empty(B, 1, oh, ow, device=o.device, dtype=torch.float32)
+        check(_lib_().dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(adv),
+                                          ptr(mout), stream()), "patch_apply_fwd")
+        ctx.save_for_backward(m, co)
+        ctx.dims = (B, ph, pw, ih, iw, oh, ow)
+        ctx.mark_non_differentiable(mout)
+        return adv, mout
+
+    @staticmethod
+    def backward(ctx, g_adv, _g_mask):
+        m, co = ctx.saved_tensors
+        B, ph, pw, ih, iw, oh, ow = ctx.dims
+        g = f32c(g_adv)
+        gp = torch.zeros(1, 3, ph, pw, device=g.device, dtype=torch.float32)
+        check(_lib_().dmh_patch_apply_bwd(ptr(g), ptr(m), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(gp), stream()),
+              "patch_apply_bwd")
+        return gp, None, None, None, None, None
+
+
+def apply_patch(obj, mask, scenes, coeffs, size=(320, 1024)):
+    """obj (1,3,h,w) [grad], mask (1,1,h,w), scenes (Ba,3,375,1242), coeffs (Ba,8)
+    -> adv scenes (Ba,3,320,1024), resized masks (Ba,1,320,1024)."""
+    if scenes.shape[0] != coeffs.shape[0]:
+        raise RuntimeError("Batch size doesn't match!")
+    return _PatchApply.apply(obj, mask, scenes, coeffs, int(size[0]), int(size[1]))
+
+
+def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024)):
+    """No-autograd fast path for a PGD iteration whose upstream gradient
+    d(cost)/d(adv_scene) is already known: returns (adv, mask_out, grad_patch)."""
+    o, m, s, co, up = f32c(obj), f32c(mask), f32c(scenes), f32c(coeffs), f32c(upstream)
+    _, _, ph, pw = o.shape
+    B, _, ih, iw = s.shape
+    oh, ow = int(size[0]), int(size[1])
+    adv = torch.empty(B, 3, oh, ow, device=o.device, dtype=torch.float32)
+    mout = torch.empty(B, 1, oh, ow, device=o.device, dtype=torch.float32)
+    gp = torch.zeros(1, 3, ph, pw, device=o.device, dtype=torch.float32)
+    lib = _lib_()
+    check(lib.dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(adv), ptr(mout),
+                                  stream()), "patch_apply_fwd")
+    check(lib.dmh_patch_apply_bwd(ptr(up), ptr(m), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(gp), stream()),
+          "patch_apply_bwd")
+    return adv, mout, gp
+
+
+# ----------------------------------------------------------------------------- update rules
+def pgd_linf_step(adv, grad, clean, alpha, eps):
+    """phy_obj_atk.py:98-100 in one launch."""
+    a, g, c = f32c(adv), f32c(grad), f32c(clean)
+    out = torch.empty_like(a)
+    check(_lib_().dmh_pgd_linf_step(ptr(a), ptr(g), ptr(c), a.numel(), float(alpha), float(eps), ptr(out), stream()),
+          "pgd_linf_step")
+    return out
+
+
+class L0State:
+    """Device-resident state of the L0 attack (patterns, Adam moments, counts)."""
+
+    def __init__(self, obj, pattern_pos, pattern_neg, lr=0.5, betas=(0.5, 0.9), eps=1e-8, clip_max=1.0):
+        self.obj = f32c(obj)
+        self.ppos = f32c(pattern_pos).clone()
+        self.pneg = f32c(pattern_neg).clone()
+        self.m_pos, self.v_pos = torch.zeros_like(self.ppos), torch.zeros_like(self.ppos)
+        self.m_neg, self.v_neg = torch.zeros_like(self.ppos), torch.zeros_like(self.ppos)
+        self.counts = torch.zeros(2, device=self.obj.device, dtype=torch.int64)   # [now, init]
+        self.lr, self.betas, self.eps, self.clip_max = float(lr), betas, float(eps), float(clip_max)
+        self.step = 0
+        self.thr = self.clip_max / 255.0
+        _, self.C, self.H, self.W = self.obj.shape
+
+    def compose_count(self, first=False):
+        """phy_obj_atk_l0.py:94-111: adv patch + l0 count (stays on the device)."""
+        adv = torch.empty_like(self.obj)
+        check(_lib_().dmh_l0_compose_count(ptr(self.obj), ptr(self.ppos), ptr(self.pneg), self.C, self.H, self.W,
+                                           self.clip_max, self.thr, ptr(adv), ptr(self.counts), stream()),
+              "l0_compose_count")
+        if first:
+            self.counts[1:2].copy_(self.counts[0:1])
+        return adv
+
+    def adam_step(self, grad_adv, mask_weight, l0_thresh):
+        self.step += 1
+        g = f32c(grad_adv) if grad_adv is not None else None
+        check(_lib_().dmh_l0_adam_step(ptr(self.obj), ptr(g), ptr(self.ppos), ptr(self.pneg), ptr(self.m_pos),
+                                       ptr(self.v_pos), ptr(self.m_neg), ptr(self.v_neg), self.C, self.H, self.W,
+                                       self.clip_max, ptr(self.counts), float(l0_thresh), float(mask_weight), self.lr,
+                                       self.betas[0], self.betas[1], self.eps, self.step, stream()), "l0_adam_step")
+
+    def finalize(self):
+        adv = torch.empty_like(self.obj)
+        pattern = torch.empty_like(self.obj)
+        check(_lib_().dmh_l0_finalize(ptr(self.obj), ptr(self.ppos), ptr(self.pneg), self.obj.numel(), self.clip_max,
+                                      self.thr, ptr(adv), ptr(pattern), stream()), "l0_finalize")
+        return adv, pattern
+
+    def l0(self) -> torch.Tensor:
+        return self.counts[0]
+
+
+def l0_count(obj, pattern_pos, pattern_neg, clip_max=1.0):
+    """cal_l0 (phy_obj_atk_l0.py:43-52) as a device int64 scalar."""
+    o, pp, pn = f32c(obj), f32c(pattern_pos), f32c(pattern_neg)
+    cnt = torch.zeros(1, device=o.device, dtype=torch.int64)
+    _, Cc, H, W = o.shape
+    check(_lib_().dmh_l0_compose_count(ptr(o), ptr(pp), ptr(pn), Cc, H, W, float(clip_max), float(clip_max) / 255.0,
+                                       None, ptr(cnt), stream()), "l0_compose_count")
+    return cnt[0]
+
+
+def topk_l0_project(pattern_pos, pattern_neg, k):
+    """EXTENSION: keep the k pixels with the largest channel-max magnitude (radix
+    select on the device); returns (P+, P-, keep mask) -- inputs are not modified."""
+    pp, pn = f32c(pattern_pos).clone(), f32c(pattern_neg).clone()
+    _, Cc, H, W = pp.shape
+    keep = torch.empty(H * W, device=pp.device, dtype=torch.uint8)
+    check(_lib_().dmh_topk_select(ptr(pp), ptr(pn), Cc, H, W, int(k), ptr(keep), None, stream()), "topk_select")
+    return pp, pn, keep.view(1, 1, H, W).bool()

@@ -153,6 +153,62 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
                     float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
                     float* const* warped_host, dmh_stream_t stream);
 
+/* ======================= stage 1: physical patch attack ======================= */
+
+/* -- A2+A3 PhysicalTrans.project / project_w_trans (physicalTrans.py:130-196):
+ * zero-pad the (C,ph,pw) image to the (oh,ow) canvas (centred, :107-122) and apply
+ * torchvision.perspective (bilinear, zeros, align_corners=False) with coeffs[b]
+ * (8 fp32 homography coefficients per item, output pixel -> input pixel, solved on
+ * the host in fp64 like torchvision functional.py:674-704) for all B items at once.
+ * img (C,ph,pw) shared by the batch -> out (B,C,oh,ow); bwd: grad_img accumulated. */
+int dmh_perspective_fwd(const float* img, const float* coeffs, int B, int C, int ph, int pw, int oh, int ow,
+                        float* out, dmh_stream_t stream);
+int dmh_perspective_bwd(const float* grad_out, const float* coeffs, int B, int C, int ph, int pw, int oh, int ow,
+                        float* grad_img, dmh_stream_t stream);
+
+/* -- A2-A5 fused attack forward (TA/attacks/phy_obj_atk.py:86-90, phy_obj_atk_l0.py:115-119):
+ * perspective(patch), perspective(mask), scene*(1-m)+obj*m, Resize([oh,ow]) (bilinear,
+ * antialias) of the composite and of the mask.
+ * patch (3,ph,pw), patch_mask (1,ph,pw), scenes (B,3,ih,iw), coeffs (B,8)
+ * -> adv (B,3,oh,ow), mask_out (B,1,oh,ow) (nullable)
+ * bwd: grad_adv (B,3,oh,ow) -> grad_patch (3,ph,pw) accumulated (sum over the batch). */
+int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs, int B,
+                        int ph, int pw, int ih, int iw, int oh, int ow, float* adv, float* mask_out,
+                        dmh_stream_t stream);
+int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, int B, int ph, int pw,
+                        int ih, int iw, int oh, int ow, float* grad_patch, dmh_stream_t stream);
+
+/* -- A6 L-inf PGD update (phy_obj_atk.py:98-100; pgd_depth.py:76-78; pgd.py:73-75):
+ * out = clamp(clean + clamp(adv + alpha*sign(grad) - clean, -eps, eps), 0, 1)          */
+int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
+                      float* out, dmh_stream_t stream);
+
+/* -- A7 L0 compose + cal_l0 (phy_obj_atk_l0.py:94-99, 43-52): adv (nullable) =
+ * clamp(obj + clamp(P+) - clamp(P-)); *count = #pixels whose thresholded pattern is
+ * non-zero in any channel (device uint64, overwritten).                              */
+int dmh_l0_compose_count(const float* obj, const float* pattern_pos, const float* pattern_neg, int C, int H, int W,
+                         float clip_max, float threshold, float* adv, unsigned long long* count,
+                         dmh_stream_t stream);
+
+/* -- A8 mask-cost gradient + Adam (phy_obj_atk_l0.py:130-138, torch.optim.Adam):
+ * grad_adv = d(adv_cost)/d(adv patch) (nullable); counts (nullable) = {l0 now, l0 at
+ * step 0} on the device: mask_weight becomes 0 when their ratio <= l0_thresh (:105-108)
+ * without a host sync.  P+/P-, m, v updated in place; `step` is 1-based.                */
+int dmh_l0_adam_step(const float* obj, const float* grad_adv, float* pattern_pos, float* pattern_neg, float* m_pos,
+                     float* v_pos, float* m_neg, float* v_neg, int C, int H, int W, float clip_max,
+                     const unsigned long long* counts, float l0_thresh, float mask_weight, float lr, float beta1,
+                     float beta2, float adam_eps, int step, dmh_stream_t stream);
+
+/* -- phy_obj_atk_l0.py:143-150: hard threshold at `threshold`, compose; pattern nullable */
+int dmh_l0_finalize(const float* obj, const float* pattern_pos, const float* pattern_neg, long long n, float clip_max,
+                    float threshold, float* adv, float* pattern, dmh_stream_t stream);
+
+/* -- EXTENSION (not reference behaviour): exact top-k L0 projection by
+ * radix select: keep the k pixels with the largest channel-max pattern magnitude (ties ->
+ * lower index), zero P+/P- elsewhere.  keep (H*W bytes) and kth_key nullable.          */
+int dmh_topk_select(float* pattern_pos, float* pattern_neg, int C, int H, int W, int k, unsigned char* keep,
+                    unsigned* kth_key, dmh_stream_t stream);
+
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);

@@ -1,0 +1,236 @@
+"""GPU parity: stage-1 CUDA kernels (through the C ABI / ctypes) against the
+oracle and the reference goldens.
+
+Integer / index work is compared bit-exactly: projected corners (host), the L0
+survivor set and count, the top-k selection, the L-inf update (pure clamp/sign
+arithmetic).  Floating point: <= 1e-5 relative on warped patches, composited
+scenes and patch gradients (atomics make the gradient's summation order
+run-dependent, still within tolerance).
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from depthmodelhardening_b200 import synth
+from oracle import patch as OQ
+from oracle.refload import CALIB_P2, write_calib
+from tests.util import assert_close, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+P34 = np.array(CALIB_P2, dtype=np.float64).reshape(3, 4)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from depthmodelhardening_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def calib(tmp_path_factory):
+    return write_calib(str(tmp_path_factory.mktemp("calib")))
+
+
+def crop(t):
+    return t[..., 100:228, 440:760]
+
+
+def test_physical_trans_project_vs_golden(dev, calib):
+    from depthmodelhardening_b200.physical import PhysicalTrans
+    g = load_golden("patch")
+    pbt = synth.patch_batch(batch=3, seed=0).to(dev)
+    pt = PhysicalTrans(pbt.obj.clone().requires_grad_(True), pbt.mask, {"path": calib}, (1, 3, 375, 1242))
+    z0, al = g["z0"].tolist(), g["alpha"].tolist()
+    imgs, masks, zs, als = pt.project(batch_size=3, z0_sample=z0, alpha_sample=al)
+    assert imgs.shape == (3, 3, 375, 1242) and masks.shape == (3, 1, 375, 1242) and zs == z0 and als == al
+    assert_close(crop(imgs), g["proj_img_crop"], TOL, "proj img")
+    assert_close(crop(masks), g["proj_mask_crop"], TOL, "proj mask")
+    assert_close(imgs.double().sum(), g["proj_img_sum"], 1e-6)
+    assert_close(masks.double().sum(), g["proj_mask_sum"], 1e-6)
+    for i, (z, a) in enumerate(zip(z0, al)):
+        assert np.array_equal(pt.objPosOnImage(z, a), g["corners"][i])
+    K = np.array([[0.58 * 1242, 0, 0.5 * 1242, 0], [0, 1.92 * 375, 0.5 * 375, 0], [0, 0, 1, 0], [0, 0, 0, 1]],
+                 dtype=np.float32)
+    T = np.eye(4, dtype=np.float32)
+    T[0, 3] = -0.1
+    imgs_k, masks_k = pt.project_w_trans(T, z0, al, K=K)
+    assert_close(crop(imgs_k), g["projk_img_crop"], TOL, "projk img")
+    assert_close(masks_k.double().sum(), g["projk_mask_sum"], 1e-6)
+    # reference composite + Resize on our warps, gradient to the patch through the perspective backward
+    adv = OQ.resize_aa(pbt.scenes * (1 - masks) + imgs * masks)
+    (adv * pbt.upstream).sum().backward()
+    assert_close(adv[:, :, 90:200, 380:640], g["adv_crop"], TOL, "adv crop")
+    assert_close(pt.obj_img.grad[:, :, ::3, ::3], g["grad_patch"], TOL, "grad patch (perspective bwd)")
+
+
+@pytest.mark.parametrize("batch", [3, 8])
+def test_fused_patch_apply_vs_oracle(dev, batch):
+    from depthmodelhardening_b200 import patch_ops
+    pbt = synth.patch_batch(batch=batch, seed=2)
+    obj = pbt.obj.clone().requires_grad_(True)
+    adv_ref, m_ref = OQ.apply_patch(obj, pbt.mask, pbt.scenes, pbt.z0, pbt.alpha, P34)
+    (adv_ref * pbt.upstream).sum().backward()
+    g = pbt.to(dev)
+    co = patch_ops.homographies(pbt.z0, pbt.alpha, P34).to(dev)
+    obj_d = g.obj.clone().requires_grad_(True)
+    adv, m = patch_ops.apply_patch(obj_d, g.mask, g.scenes, co)
+    (adv * g.upstream).sum().backward()
+    assert_close(adv, adv_ref, TOL, "adv scene")
+    assert_close(m, m_ref, TOL, "resized mask")
+    assert_close(obj_d.grad, obj.grad, TOL, "grad patch")
+    # the no-autograd fast path gives the same three results
+    adv2, m2, gp2 = patch_ops.apply_patch_fwd_bwd(g.obj, g.mask, g.scenes, co, g.upstream)
+    assert torch.equal(adv2, adv) and torch.equal(m2, m)
+    assert_close(gp2, obj.grad, TOL, "grad patch (fast path)")
+
+
+def test_fused_patch_apply_vs_golden(dev):
+    from depthmodelhardening_b200 import patch_ops
+    g = load_golden("patch")
+    pbt = synth.patch_batch(batch=3, seed=0).to(dev)
+    z0, al = g["z0"].tolist(), g["alpha"].tolist()
+    co = patch_ops.homographies(z0, al, P34).to(dev)
+    obj = pbt.obj.clone().requires_grad_(True)
+    adv, m = patch_ops.apply_patch(obj, pbt.mask, pbt.scenes, co)
+    (adv * pbt.upstream).sum().backward()
+    assert_close(adv.reshape(-1)[torch.from_numpy(g["adv_idx"]).to(dev)], g["adv_samples"], TOL, "adv samples")
+    assert_close(adv.double().sum(), g["adv_sum"], 1e-7)
+    assert_close(adv[:, :, 90:200, 380:640], g["adv_crop"], TOL, "adv crop")
+    assert_close(m[:, :, 90:200, 380:640], g["mask_rs_crop"], TOL, "mask crop")
+    assert_close(m.double().sum(), g["mask_rs_sum"], 1e-6)
+    assert_close(obj.grad[:, :, ::3, ::3], g["grad_patch"], TOL, "grad patch")
+    assert_close(obj.grad.double().sum(), g["grad_patch_sum"], 1e-5)
+
+
+def test_patch_apply_batch_mismatch_raises(dev):
+    from depthmodelhardening_b200 import patch_ops
+    pbt = synth.patch_batch(batch=2, seed=0).to(dev)
+    co = patch_ops.homographies([5, 6, 7], [0, 5, 10], P34).to(dev)
+    with pytest.raises(RuntimeError, match="Batch size"):
+        patch_ops.apply_patch(pbt.obj, pbt.mask, pbt.scenes, co)
+
+
+def test_pgd_linf_step_bit_exact(dev):
+    from depthmodelhardening_b200 import patch_ops
+    clean = synth.rand((1, 3, 260, 300), 1)
+    adv = (clean + (synth.rand(clean.shape, 2) - 0.5) * 0.2).clamp(0, 1)
+    grad = synth.randn(clean.shape, 3)
+    grad[0, 0, :5, :5] = 0.0                      # sign(0) == 0
+    ref = OQ.pgd_linf_step(adv, grad, clean, 0.02, 0.1)
+    out = patch_ops.pgd_linf_step(adv.to(dev), grad.to(dev), clean.to(dev), 0.02, 0.1)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_l0_compose_count_and_finalize_bit_exact(dev):
+    from depthmodelhardening_b200 import patch_ops
+    obj = synth.rand((1, 3, 260, 300), 11)
+    # patterns around the 1/255 threshold, some negative / above 1, exact cancellations included
+    pp = (synth.rand(obj.shape, 12) - 0.3) * 0.02
+    pn = (synth.rand(obj.shape, 13) - 0.3) * 0.02
+    pp[0, :, 10:20, 10:20] = 0.5
+    pn[0, :, 10:20, 10:20] = 0.5               # pos + neg cancels exactly -> not counted
+    pp[0, :, 30:40, :] = 1.7
+    adv_ref, pos, neg = OQ.l0_compose(obj, pp, pn)
+    cnt_ref, surv_ref = OQ.l0_count(pos, neg)
+    st = patch_ops.L0State(obj.to(dev), pp.to(dev), pn.to(dev))
+    adv = st.compose_count(first=True)
+    assert torch.equal(adv.cpu(), adv_ref)
+    assert int(st.counts[0]) == int(cnt_ref) and int(st.counts[1]) == int(cnt_ref)
+    assert int(patch_ops.l0_count(obj.to(dev), pp.to(dev), pn.to(dev))) == int(cnt_ref)
+    fin_ref, fpos, fneg = OQ.l0_finalize(obj, pp, pn)
+    fin, pattern = st.finalize()
+    assert torch.equal(fin.cpu(), fin_ref)
+    assert torch.equal(pattern.cpu(), fpos + fneg)
+    surv = (pattern.abs().sum(1) != 0).cpu()
+    assert torch.equal(surv, surv_ref)         # bit-exact L0 surviving-pixel set
+
+
+def test_l0_adam_step_vs_torch_autograd(dev):
+    """mask-cost gradient + clamp chain + Adam in one kernel vs autograd + torch.optim.Adam."""
+    from depthmodelhardening_b200 import patch_ops
+    obj = synth.rand((1, 3, 64, 80), 21)
+    pp0, pn0 = synth.rand(obj.shape, 22) * 1.2 - 0.1, synth.rand(obj.shape, 23) * 1.2 - 0.1
+    g_adv_steps = [synth.randn(obj.shape, 24 + i) * 1e-3 for i in range(3)]
+    pp = pp0.clone().requires_grad_(True)
+    pn = pn0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pp, pn], lr=0.5, betas=(0.5, 0.9))
+    st = patch_ops.L0State(obj.to(dev), pp0.to(dev), pn0.to(dev), lr=0.5)
+    for i, g_adv in enumerate(g_adv_steps):
+        mask_w = 0.06 if i != 1 else 0.0
+        adv, pos, neg = OQ.l0_compose(obj, pp, pn)
+        cost = (adv * g_adv).sum() + mask_w * OQ.l0_mask_cost(pp, pn)
+        opt.zero_grad()
+        cost.backward()
+        opt.step()
+        st.compose_count(first=(i == 0))
+        st.counts[1] = 1 if i != 1 else 10 ** 9          # force ratio > / <= thresh on the device
+        st.adam_step(g_adv.to(dev), 0.06, 0.1)
+        assert_close(st.ppos, pp, 2e-6, "P+ after step %d" % i)
+        assert_close(st.pneg, pn, 2e-6, "P- after step %d" % i)
+
+
+@pytest.mark.parametrize("k", [0, 1, 777, 40000, 78000, 90000])
+def test_topk_radix_select_bit_exact(dev, k):
+    from depthmodelhardening_b200 import patch_ops
+    pp = synth.rand((1, 3, 260, 300), 31) * 1.3 - 0.2
+    pn = synth.rand((1, 3, 260, 300), 32) * 1.3 - 0.2
+    # heavy ties: quantise a region, and a block of exact duplicates of the likely k-th value
+    pp[0, :, :100] = torch.round(pp[0, :, :100] * 8) / 8
+    pn[0, :, :100] = torch.round(pn[0, :, :100] * 8) / 8
+    rp, rn, keep_ref = OQ.topk_l0_project(pp, pn, k)
+    op, on, keep = patch_ops.topk_l0_project(pp.to(dev), pn.to(dev), k)
+    assert torch.equal(keep.cpu(), keep_ref)   # bit-exact top-k selection incl. tie order
+    assert torch.equal(op.cpu(), rp) and torch.equal(on.cpu(), rn)
+    assert int(keep.sum()) == min(max(k, 0), 78000)
+
+
+def _tiny(dev):
+    from oracle.make_golden import TinyDepth
+    return TinyDepth().to(dev)
+
+
+def test_linf_attack_class_vs_reference_golden(dev, calib):
+    import os
+    from depthmodelhardening_b200 import attacks
+    g = load_golden("attack_linf")
+    attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
+    pbt = synth.patch_batch(batch=3, seed=0).to(dev)
+    random.seed(5)
+    atk = attacks.Phy_obj_atk(_tiny(dev), pbt.obj.clone(), pbt.mask.clone(), eps=0.1, alpha=0.02, steps=2,
+                              random_start=False, dist_range=list(range(5, 10, 2)))
+    adv_s, ben_s, m_out, obj_adv = atk(pbt.scenes.clone(), 3)
+    assert adv_s.shape == (3, 3, 320, 1024) and m_out.shape == (3, 1, 320, 1024) and obj_adv.shape == (1, 3, 260, 300)
+    # same placements (RNG order) -> masks / benign scenes match to fp32 tolerance
+    assert_close(m_out.double().sum(), g["mask_out_sum"], 1e-6)
+    assert_close(ben_s.double().sum(), g["ben_scene_sum"], 1e-6)
+    # sign(grad) flips where |grad| ~ 0 (cuDNN vs CPU convolution rounding): bound the fraction
+    diff = (obj_adv.cpu()[:, :, ::2, ::2] - torch.from_numpy(g["obj_adv"])).abs()
+    assert float((diff > 1e-6).float().mean()) < 0.02
+    assert_close(adv_s.double().sum(), g["adv_scene_sum"], 1e-4)
+    with pytest.raises(RuntimeError, match="Batch size"):
+        atk(pbt.scenes[:2].clone(), 3)
+
+
+def test_l0_attack_class_vs_reference_golden(dev, calib):
+    import os
+    from depthmodelhardening_b200 import attacks
+    g = load_golden("attack_l0")
+    attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
+    pbt = synth.patch_batch(batch=3, seed=0).to(dev)
+    random.seed(6)
+    np.random.seed(7)
+    atk = attacks.Phy_obj_atk_l0(_tiny(dev), pbt.obj.clone(), pbt.mask.clone(), adam_lr=0.5, steps=2, mask_wt=0.06,
+                                 l0_thresh=0.1, dist_range=list(range(5, 10, 2)))
+    adv_s, ben_s, m_out, obj_adv = atk(pbt.scenes.clone(), 3)
+    l0 = int(atk.cal_l0())
+    assert abs(l0 - int(g["l0_count"])) <= 0.01 * int(g["l0_count"])
+    surv = (atk.pattern.abs().sum(1) != 0).cpu().numpy().astype(np.uint8)
+    surv_ref = np.unpackbits(g["survivors"])[:surv.size].reshape(surv.shape)
+    assert np.mean(surv != surv_ref) < 0.01
+    d = (atk.pattern_pos_tensor.cpu()[:, :, ::2, ::2] - torch.from_numpy(g["pattern_pos_tensor"])).abs()
+    assert float((d > 1e-3).float().mean()) < 0.02
+    assert_close(adv_s.double().sum(), g["adv_scene_sum"], 1e-3)
