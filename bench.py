@@ -158,7 +158,9 @@ class Stage1:
         g = self.g
         adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream)
         if self.world > 1:
-            torch.distributed.all_reduce(grad_patch)
+            from depthmodelhardening_b200 import dist as D
+            # the ONE collective of the step: patch gradient + scalar attack loss in a single all-reduce
+            grad_patch, _ = D.allreduce_patch_grad(grad_patch, [adv_scene.new_zeros(())], average=True)
         self.adv = ops.pgd_linf_step(self.adv, grad_patch, g.obj, alpha=0.02, eps=0.1)
         return adv_scene
 

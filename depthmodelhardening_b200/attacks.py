@@ -69,13 +69,11 @@ class Attack(object):
 
 
 def _sync_patch_grad(grad):
-    """Sum the shared patch's gradient over ranks (the ONE collective of stage 1);
-    mean so that the value equals the single-process gradient of the global-batch mean."""
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
-            torch.distributed.get_world_size() > 1:
-        torch.distributed.all_reduce(grad)
-        grad.div_(torch.distributed.get_world_size())
-    return grad
+    """The ONE collective of stage 1: mean of the shared patch's gradient over
+    ranks (equals the single-process gradient of the global-batch mean)."""
+    from . import dist as _dist
+    g, _ = _dist.allreduce_patch_grad(grad, (), average=True)
+    return g
 
 
 def _tile_scenes(images, batch_size):

@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), batch sharded over ranks,
+no data-path collective except the two the path really has:
+
+  1. all-reduce(sum) of the SHARED patch gradient, with the scalar attack loss
+     riding in the tail of the same buffer -- one collective per PGD step;
+  2. all-reduce(sum) of the per-scale loss numerators once per training step
+     (denominators are static: global B*H*W).
+
+Everything else is per-image and needs no communication.  Works with any
+torch.distributed backend (nccl on the GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(batch: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> Tuple[int, int]:
+    """Items [lo, hi) of a global batch owned by `rank` (equal shards; the batch
+    must divide evenly, as `BackprojectDepth(batch_size, ...)` bakes the shard
+    size in -- `M2/layers.py:154-161`)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    if batch % world_size != 0:
+        raise ValueError("global batch %d is not divisible by world size %d" % (batch, world_size))
+    per = batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(tensors: Dict, batch: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> Dict:
+    """Slice every tensor whose leading dim is the global batch; others are replicated."""
+    lo, hi = shard_range(batch, rank, world_size)
+    out = {}
+    for k, v in tensors.items():
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == batch:
+            out[k] = v[lo:hi].contiguous()
+        else:
+            out[k] = v
+    return out
+
+
+def allreduce_patch_grad(grad: torch.Tensor, scalars: Sequence[torch.Tensor] = (), average: bool = True):
+    """Sum `grad` (the shared patch's gradient) over ranks; `scalars` (0-dim
+    tensors, e.g. the attack loss) are appended to the same flat buffer so the
+    step costs ONE collective.  Returns (grad, [scalars...]) -- identical on
+    every rank, so the sign / Adam / threshold update that follows stays
+    bit-identical across ranks."""
+    r, w = world()
+    if w == 1:
+        return grad, list(scalars)
+    n = grad.numel()
+    buf = torch.empty(n + len(scalars), device=grad.device, dtype=grad.dtype)
+    buf[:n].copy_(grad.reshape(-1))
+    for i, s in enumerate(scalars):
+        buf[n + i] = s.to(grad.dtype)
+    dist.all_reduce(buf)
+    if average:
+        buf.div_(w)
+    return buf[:n].view_as(grad), [buf[n + i] for i in range(len(scalars))]
+
+
+def allreduce_loss_sums(sums: torch.Tensor) -> torch.Tensor:
+    """Sum the per-scale loss numerators (1-D tensor) over ranks, in place."""
+    _, w = world()
+    if w > 1:
+        dist.all_reduce(sums)
+    return sums

@@ -211,3 +211,60 @@ def topk_l0_project(p_pos, p_neg, k):
     keep[order[:k]] = True
     keep = keep.view(1, 1, *p_pos.shape[2:])
     return p_pos * keep, p_neg * keep, keep
+
+
+# ----------------------------------------------------------------------------- whole attack loops
+def linf_attack(model, obj, mask, scenes, placements, final_placement, P34, eps, alpha):
+    """phy_obj_atk.py:73-123 with the random placements injected:
+    placements = [(z0s, alphas)] per step.  Device agnostic (runs where the tensors live)."""
+    import torch.nn as nn
+    loss = nn.MSELoss()
+    adv = obj.clone().detach()
+    for z0s, als in placements:
+        adv.requires_grad_()
+        scene, m = apply_patch(adv, mask, scenes, z0s, als, P34)
+        depth = model(scene)
+        cost = -loss(depth * m, torch.zeros_like(depth))
+        grad = torch.autograd.grad(cost, adv)[0]
+        with torch.no_grad():
+            adv = pgd_linf_step(adv, grad, obj, alpha, eps)
+    z0s, als = final_placement
+    with torch.no_grad():
+        adv_s, m_out = apply_patch(adv, mask, scenes, z0s, als, P34)
+        ben_s, _ = apply_patch(obj, mask, scenes, z0s, als, P34)
+    return adv_s, ben_s, m_out, adv
+
+
+def l0_attack(model, obj, mask, scenes, init_pos, init_neg, placements, final_placement, P34, steps, lr, mask_wt,
+              l0_thresh):
+    """phy_obj_atk_l0.py:73-174 with the random inits / placements injected."""
+    import torch.nn as nn
+    loss = nn.MSELoss()
+    pp = init_pos.clone().requires_grad_(True)
+    pn = init_neg.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pp, pn], lr=lr, betas=(0.5, 0.9))
+    l0_init = None
+    it = iter(placements)
+    for stp in range(steps * 2):
+        adv, pos, neg = l0_compose(obj, pp, pn)
+        l0, _ = l0_count(pos, neg)
+        if stp == 0:
+            l0_init = l0
+        if (l0 / l0_init) <= l0_thresh:
+            w = 0
+            if stp >= steps:
+                break
+        else:
+            w = mask_wt
+        z0s, als = next(it)
+        scene, m = apply_patch(adv, mask, scenes, z0s, als, P34)
+        depth = model(scene)
+        cost = loss(depth * m, torch.zeros_like(depth)) + w * l0_mask_cost(pp, pn)
+        opt.zero_grad()
+        cost.backward()
+        opt.step()
+    adv, pos, neg = l0_finalize(obj, pp.detach(), pn.detach())
+    z0s, als = final_placement
+    with torch.no_grad():
+        adv_s, m_out = apply_patch(adv, mask, scenes, z0s, als, P34)
+    return adv_s, m_out, adv, pp.detach(), pn.detach(), pos + neg

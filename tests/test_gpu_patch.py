@@ -16,7 +16,7 @@ import torch
 from depthmodelhardening_b200 import synth
 from oracle import patch as OQ
 from oracle.refload import CALIB_P2, write_calib
-from tests.util import assert_close, load_golden, rel_err
+from tests.util import assert_close, assert_close_arb, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -58,7 +58,8 @@ def test_physical_trans_project_vs_golden(dev, calib):
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = -0.1
     imgs_k, masks_k = pt.project_w_trans(T, z0, al, K=K)
-    assert_close(crop(imgs_k), g["projk_img_crop"], TOL, "projk img")
+    i64, _, _ = OQ.project_patch(pbt.obj.cpu().double(), pbt.mask.cpu().double(), z0, al, P34, K=K, T=T)
+    assert_close_arb(crop(imgs_k), g["projk_img_crop"], crop(i64), TOL, "projk img")
     assert_close(masks_k.double().sum(), g["projk_mask_sum"], 1e-6)
     # reference composite + Resize on our warps, gradient to the patch through the perspective backward
     adv = OQ.resize_aa(pbt.scenes * (1 - masks) + imgs * masks)
@@ -79,13 +80,16 @@ def test_fused_patch_apply_vs_oracle(dev, batch):
     obj_d = g.obj.clone().requires_grad_(True)
     adv, m = patch_ops.apply_patch(obj_d, g.mask, g.scenes, co)
     (adv * g.upstream).sum().backward()
-    assert_close(adv, adv_ref, TOL, "adv scene")
-    assert_close(m, m_ref, TOL, "resized mask")
-    assert_close(obj_d.grad, obj.grad, TOL, "grad patch")
+    o64 = pbt.obj.double().requires_grad_(True)
+    adv64, m64 = OQ.apply_patch(o64, pbt.mask.double(), pbt.scenes.double(), pbt.z0, pbt.alpha, P34)
+    (adv64 * pbt.upstream.double()).sum().backward()
+    assert_close_arb(adv, adv_ref, adv64, TOL, "adv scene")
+    assert_close_arb(m, m_ref, m64, TOL, "resized mask")
+    assert_close_arb(obj_d.grad, obj.grad, o64.grad, TOL, "grad patch")
     # the no-autograd fast path gives the same three results
     adv2, m2, gp2 = patch_ops.apply_patch_fwd_bwd(g.obj, g.mask, g.scenes, co, g.upstream)
     assert torch.equal(adv2, adv) and torch.equal(m2, m)
-    assert_close(gp2, obj.grad, TOL, "grad patch (fast path)")
+    assert_close_arb(gp2, obj.grad, o64.grad, TOL, "grad patch (fast path)")
 
 
 def test_fused_patch_apply_vs_golden(dev):
@@ -231,6 +235,55 @@ def test_l0_attack_class_vs_reference_golden(dev, calib):
     surv = (atk.pattern.abs().sum(1) != 0).cpu().numpy().astype(np.uint8)
     surv_ref = np.unpackbits(g["survivors"])[:surv.size].reshape(surv.shape)
     assert np.mean(surv != surv_ref) < 0.01
+    # Adam's first steps are sign-like (+-lr): elements whose tiny gradient changes sign between the CPU
+    # reference run and this GPU run (cuDNN vs CPU convolution rounding) move by ~1; bound their fraction
     d = (atk.pattern_pos_tensor.cpu()[:, :, ::2, ::2] - torch.from_numpy(g["pattern_pos_tensor"])).abs()
-    assert float((d > 1e-3).float().mean()) < 0.02
+    assert float((d > 1e-3).float().mean()) < 0.10
     assert_close(adv_s.double().sum(), g["adv_scene_sum"], 1e-3)
+
+
+def _placements(seed, steps, ranges, batch):
+    """The (z0, alpha) draws the attack classes make, in their RNG order."""
+    random.seed(seed)
+    out = []
+    for _ in range(steps + 1):
+        z0 = random.sample(ranges[0], batch)
+        al = random.sample(ranges[1], batch)
+        out.append((z0, al))
+    return out[:-1], out[-1]
+
+
+def test_attack_classes_vs_oracle_loop_same_device(dev, calib):
+    """Our attack classes against the oracle's restatement of the reference loops, BOTH driven on the GPU with
+    the same network, so the only difference is kernels vs torch ops."""
+    import os
+    from depthmodelhardening_b200 import attacks
+    attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    dist, ang = list(range(5, 10, 2)), list(range(-30, 31, 5))
+    # ---- L-inf, 3 steps
+    pl, fin = _placements(9, 3, (dist, ang), 3)
+    ref = OQ.linf_attack(model, pbt.obj, pbt.mask, pbt.scenes, pl, fin, P34, eps=0.1, alpha=0.02)
+    random.seed(9)
+    atk = attacks.Phy_obj_atk(model, pbt.obj.clone(), pbt.mask.clone(), eps=0.1, alpha=0.02, steps=3,
+                              random_start=False, dist_range=dist)
+    out = atk(pbt.scenes.clone(), 3)
+    assert float(((out[3] - ref[3]).abs() > 1e-6).float().mean()) < 5e-3      # sign flips at |grad| ~ 0
+    assert_close(out[1], ref[1], TOL, "benign scenes")
+    assert_close(out[2], ref[2], TOL, "masks")
+    # ---- L0, steps=2 (4 iterations)
+    np.random.seed(3)
+    init = [torch.Tensor(np.clip(np.random.random(pbt.obj.size()), 0.0, 1.0)).to(dev) for _ in range(2)]
+    pl, fin = _placements(10, 4, (dist, ang), 3)
+    ref0 = OQ.l0_attack(model, pbt.obj, pbt.mask, pbt.scenes, init[0], init[1], pl, fin, P34, steps=2, lr=0.5,
+                        mask_wt=0.06, l0_thresh=0.1)
+    random.seed(10)
+    np.random.seed(3)
+    atk0 = attacks.Phy_obj_atk_l0(model, pbt.obj.clone(), pbt.mask.clone(), adam_lr=0.5, steps=2, mask_wt=0.06,
+                                  l0_thresh=0.1, dist_range=dist)
+    out0 = atk0(pbt.scenes.clone(), 3)
+    assert float(((atk0.pattern_pos_tensor - ref0[3]).abs() > 1e-4).float().mean()) < 5e-3
+    assert float(((atk0.pattern_neg_tensor - ref0[4]).abs() > 1e-4).float().mean()) < 5e-3
+    surv, surv_ref = (atk0.pattern.abs().sum(1) != 0), (ref0[5].abs().sum(1) != 0)
+    assert float((surv != surv_ref).float().mean()) < 5e-3
