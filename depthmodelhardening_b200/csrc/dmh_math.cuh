@@ -248,4 +248,66 @@ DMH_HD SsimCoef ssim_coef(const SsimStats& s) {
 // reflect index for ReflectionPad2d(1): -1 -> 1, n -> n-2 (n >= 2)
 DMH_HD int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
+
+// ---------------------------------------------------------------------------
+// Fast-path variants used by the fused F=1 kernel (photo_fast.cu): separable
+// 3x3 sums (row sums of 3, then 3 rows), FMA-contracted products, mean = sum*(1/9).
+// Same mathematics as ssim_stats(); rounding differs at the 1e-7 level.
+struct Row5 { float x, y, xx, yy, xy; };
+
+DMH_HD Row5 row5(float x0, float x1, float x2, float y0, float y1, float y2) {
+    Row5 r;
+    r.x = (x0 + x1) + x2;
+    r.y = (y0 + y1) + y2;
+    r.xx = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
+    r.yy = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
+    r.xy = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
+    return r;
+}
+
+DMH_HD SsimStats ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) {
+    const float inv9 = 1.0f / 9.0f;
+    SsimStats s;
+    s.mu_x = ((a.x + b.x) + c.x) * inv9;
+    s.mu_y = ((a.y + b.y) + c.y) * inv9;
+    const float exx = ((a.xx + b.xx) + c.xx) * inv9;
+    const float eyy = ((a.yy + b.yy) + c.yy) * inv9;
+    const float exy = ((a.xy + b.xy) + c.xy) * inv9;
+    const float mxx = s.mu_x * s.mu_x, myy = s.mu_y * s.mu_y, mxy = s.mu_x * s.mu_y;
+    const float sig_x = exx - mxx, sig_y = eyy - myy, sig_xy = exy - mxy;
+    s.A1 = fmaf(2.0f, mxy, DMH_SSIM_C1);
+    s.A2 = fmaf(2.0f, sig_xy, DMH_SSIM_C2);
+    s.B1 = (mxx + myy) + DMH_SSIM_C1;
+    s.B2 = (sig_x + sig_y) + DMH_SSIM_C2;
+    s.n = s.A1 * s.A2;
+    s.d = s.B1 * s.B2;
+    return s;
+}
+
+// value + coefficients sharing one reciprocal of d
+DMH_HD float ssim_value_coef(const SsimStats& s, float& pass, SsimCoef& k) {
+    const float r = 1.0f / s.d;
+    const float nr = s.n * r;
+    const float v = (1.0f - nr) * 0.5f;
+    pass = (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f;
+    const float nr2 = nr * r;
+    const float inv9 = 1.0f / 9.0f;
+    const float dA = (s.A2 - s.A1) * r, dB = nr2 * (s.B2 - s.B1);
+    k.ax = -inv9 * (s.mu_y * dA - s.mu_x * dB);
+    k.ay = -inv9 * (s.mu_x * dA - s.mu_y * dB);
+    k.b = inv9 * nr2 * s.B1;
+    k.c = -inv9 * s.A1 * r;
+    return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+
+// d(grad_disp)/d(g_ix, g_iy): warp_coord_bwd collapsed to two scalars
+//   g_depth = g_ix * ax + g_iy * ay
+DMH_HD void warp_chain_factors(const Camera& cam, const WarpCoord& wc, int W, int H, float& ax, float& ay) {
+    float pr[3];
+    for (int i = 0; i < 3; ++i)
+        pr[i] = cam.P[i * 4 + 0] * wc.ray[0] + cam.P[i * 4 + 1] * wc.ray[1] + cam.P[i * 4 + 2] * wc.ray[2];
+    ax = wc.mx * (2.0f / (float)(W - 1)) * wc.inv_z * (pr[0] - wc.u_raw * pr[2]);
+    ay = wc.my * (2.0f / (float)(H - 1)) * wc.inv_z * (pr[1] - wc.v_raw * pr[2]);
+}
+
 }  // namespace dmh

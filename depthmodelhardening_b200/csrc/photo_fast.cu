@@ -1,0 +1,355 @@
+// Fast path of dmh_photo_scale for ONE source frame (the headline stereo
+// configuration, frame_ids [0,'s']; also mono with a single source when no pose
+// gradient is requested).  Same contract and results as photo_scale_kernel<1>
+// in photo_objective.cu, ~3.4x fewer instructions:
+//
+//   * 32x32 tile, 256 threads; every thread OWNS 4 interior pixels of one
+//     column (rows 4s..4s+3) in the warp phase and in the gradient phase, so
+//     the whole backward chain of the gather (bilinear taps -> coordinates ->
+//     projection -> depth -> disparity) collapses into 3 scalars per pixel
+//     held in registers (no second gather, no coordinate recompute);
+//   * SSIM statistics by separable sliding windows: a thread walks down a
+//     column of the 34x34 ring and reuses the 3-wide row sums across the 3
+//     windows they belong to; value and backward coefficients share one
+//     reciprocal; the automask decision gates the coefficients in the same pass
+//     (single source frame -> the winner is known immediately);
+//   * the 3x3 box sums of the 9 coefficient planes are separable sliding
+//     windows too; reflection multiplicities are folded into the edge weights.
+//
+// Shared memory: tgt 3x36x36 + pred 3x36x36 + coef 9x34x34 floats + gate bytes
+// = 73.9 KB -> 3 CTAs / SM.   Roofline: HBM by traffic (40 B per target pixel),
+// but issue-bound in practice (see profiles/): ~900 instr / pixel.
+#include "../../include/dmh_b200.h"
+#include "dmh_common.cuh"
+
+using namespace dmh;
+
+namespace {
+
+#define FT_T 32
+#define FT_R2 36                 // tile + 2-px halo
+#define FT_R1 34                 // tile + 1-px ring
+#define FT_N2 (FT_R2 * FT_R2)
+#define FT_N1 (FT_R1 * FT_R1)
+#define FT_THREADS 256
+#define FT_STRIPS 7
+#define FT_ROWS 5                // 7 strips x 5 rows >= 34 ring rows
+
+struct FastParams {
+    const float* target;
+    const float* src;
+    const float* T;
+    const float* disp;
+    const float* K;
+    const float* inv_K;
+    const float* ident;
+    const float* noise;
+    float* loss_partial;
+    float* grad_disp;
+    uint8_t* sel;
+    float* warped;
+    int B, H, W, flags;
+    DepthScale ds;
+    float grad_scale;
+};
+
+__device__ __forceinline__ int ext_to_img(int e, int n) {
+    e = e < -1 ? -1 : (e > n ? n : e);
+    return reflect1(e, n);
+}
+
+struct Gathered { float v[3]; float dix[3], diy[3]; };
+
+// bilinear gather of 3 channels at (wc.ix, wc.iy) + d(value)/d(ix,iy)
+__device__ __forceinline__ Gathered gather3(const float* __restrict__ sp, size_t N, const WarpCoord& wc, int H, int W,
+                                            bool want_grad) {
+    const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+    const bool x0in = bl.x0 >= 0 && bl.x0 < W, x1in = bl.x0 + 1 >= 0 && bl.x0 + 1 < W;
+    const bool y0in = bl.y0 >= 0 && bl.y0 < H, y1in = bl.y0 + 1 >= 0 && bl.y0 + 1 < H;
+    const long long o = (long long)bl.y0 * W + bl.x0;
+    Gathered g;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* s = sp + ch * N;
+        const float nw = (y0in && x0in) ? __ldg(s + o) : 0.f;
+        const float ne = (y0in && x1in) ? __ldg(s + o + 1) : 0.f;
+        const float sw = (y1in && x0in) ? __ldg(s + o + W) : 0.f;
+        const float se = (y1in && x1in) ? __ldg(s + o + W + 1) : 0.f;
+        float acc = nw * bl.wnw;
+        acc = fmaf(ne, bl.wne, acc);
+        acc = fmaf(sw, bl.wsw, acc);
+        acc = fmaf(se, bl.wse, acc);
+        g.v[ch] = acc;
+        if (want_grad) {
+            g.dix[ch] = (ne - nw) * bl.ty1 + (se - sw) * bl.ty0;
+            g.diy[ch] = (sw - nw) * bl.tx1 + (se - ne) * bl.tx0;
+        }
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 3)
+photo_fast_kernel(const FastParams p) {
+    extern __shared__ float smem[];
+    float* tgt = smem;                       // [3][N2]
+    float* pred = tgt + 3 * FT_N2;           // [3][N2]
+    float* coef = pred + 3 * FT_N2;          // [9][N1]: (a,b,c) x 3 channels, gated
+    float* cams = coef + 9 * FT_N1;          // [24]
+    float* red = cams + 24;                  // [32]
+    uint8_t* gate = reinterpret_cast<uint8_t*>(red + 32);   // [N1]
+
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
+    const size_t N = (size_t)H * W;
+    const bool no_ssim = (p.flags & DMH_PHOTO_NO_SSIM) != 0;
+    const bool is_depth = (p.flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
+    const float w_ssim = no_ssim ? 0.0f : 0.85f / 3.0f;
+    const float w_l1 = no_ssim ? 1.0f / 3.0f : 0.15f / 3.0f;
+
+    if (tid < 12) {
+        const int i = tid / 4, j = tid % 4;
+        const float* k = p.K + b * 16 + i * 4;
+        const float* tt = p.T + b * 16 + j;
+        float acc = __ldg(k) * __ldg(tt);
+        acc = fmaf(__ldg(k + 1), __ldg(tt + 4), acc);
+        acc = fmaf(__ldg(k + 2), __ldg(tt + 8), acc);
+        acc = fmaf(__ldg(k + 3), __ldg(tt + 12), acc);
+        cams[tid] = acc;
+    } else if (tid < 21) {
+        const int i = (tid - 12) / 3, j = (tid - 12) % 3;
+        cams[tid] = __ldg(p.inv_K + b * 16 + i * 4 + j);
+    }
+    // ---- target tile, 2-px reflect halo
+    for (int i = tid; i < FT_N2; i += FT_THREADS) {
+        const int r = i / FT_R2, c = i - r * FT_R2;
+        const size_t o = (size_t)ext_to_img(y0 - 2 + r, H) * W + ext_to_img(x0 - 2 + c, W);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + i] = __ldg(p.target + ((size_t)b * 3 + ch) * N + o);
+    }
+    __syncthreads();
+    Camera cam;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cam.P[i] = cams[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cam.iK[i] = cams[12 + i];
+    const float* sp = p.src + (size_t)b * 3 * N;
+    const float* dp_ = p.disp + (size_t)b * N;
+
+    // ---- phase A: warp.  Owned interior pixels: column tid%32, rows 4*(tid/32)+k
+    const int oc = tid & 31, os = tid >> 5;
+    float D[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = 4 * os + k;
+        const int iy = ext_to_img(y0 + r, H), ix = ext_to_img(x0 + oc, W);
+        const float dv = __ldg(dp_ + (size_t)iy * W + ix);
+        const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
+        const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
+        const Gathered g = gather3(sp, N, wc, H, W, true);
+        float ax, ay;
+        warp_chain_factors(cam, wc, W, H, ax, ay);
+        const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
+        const int i2 = (r + 2) * FT_R2 + oc + 2;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            pred[ch * FT_N2 + i2] = g.v[ch];
+            D[k][ch] = (g.dix[ch] * ax + g.diy[ch] * ay) * dd;
+        }
+        if (p.warped && y0 + r < H && x0 + oc < W) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+        }
+    }
+    // halo ring of the pred tile: 2 top rows, 2 bottom rows, 2 left cols, 2 right cols = 272 pixels
+    for (int h = tid; h < 272; h += FT_THREADS) {
+        int r, c;
+        if (h < 72) { r = h / FT_R2; c = h - r * FT_R2; }
+        else if (h < 144) { const int t = h - 72; r = FT_R2 - 2 + t / FT_R2; c = t % FT_R2; }
+        else if (h < 208) { const int t = h - 144; r = 2 + (t >> 1); c = t & 1; }
+        else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
+        const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
+        const float dv = __ldg(dp_ + (size_t)iy * W + ix);
+        const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
+        const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
+        const Gathered g = gather3(sp, N, wc, H, W, false);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + r * FT_R2 + c] = g.v[ch];
+    }
+    __syncthreads();
+
+    // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients
+    float loss_local = 0.0f;
+    if (tid < FT_R1 * FT_STRIPS) {
+        const int c = tid % FT_R1, strip = tid / FT_R1;
+        const int r0 = strip * FT_ROWS;                 // first ring row of this strip == first R2 row of its window
+        const int qx = x0 - 1 + c;
+        const bool col_ok = qx >= 0 && qx < W;
+        Row5 hist[3][2];                                // [channel][older, newer] row sums
+        float cen_x[3], cen_y[3];                       // centre values of the previous row
+#pragma unroll
+        for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
+            const int r2 = r0 + rr;                     // R2 row being added
+            Row5 cur[3];
+            float mid_x[3], mid_y[3];
+            if (r2 < FT_R2) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float* xs = pred + ch * FT_N2 + r2 * FT_R2 + c;
+                    const float* ys = tgt + ch * FT_N2 + r2 * FT_R2 + c;
+                    const float xa = xs[0], xb = xs[1], xc = xs[2], ya = ys[0], yb = ys[1], yc = ys[2];
+                    cur[ch] = row5(xa, xb, xc, ya, yb, yc);
+                    mid_x[ch] = xb; mid_y[ch] = yb;
+                }
+            }
+            if (rr >= 2) {
+                const int qr = r0 + rr - 2;             // ring row of the window centre
+                const int qy = y0 - 1 + qr;
+                if (qr < FT_R1) {
+                    const int qi = qr * FT_R1 + c;
+                    float ka[3] = {0.f, 0.f, 0.f}, kb[3] = {0.f, 0.f, 0.f}, kc[3] = {0.f, 0.f, 0.f};
+                    uint8_t gt = 0;
+                    if (col_ok && qy >= 0 && qy < H) {
+                        float l1 = 0.f, ss = 0.f;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            l1 += fabsf(cen_y[ch] - cen_x[ch]);
+                            if (!no_ssim) {
+                                const SsimStats st = ssim_stats_rows(hist[ch][0], hist[ch][1], cur[ch]);
+                                float pass;
+                                SsimCoef k;
+                                ss += ssim_value_coef(st, pass, k);
+                                const float g = w_ssim * pass;
+                                ka[ch] = g * k.ax; kb[ch] = g * k.b; kc[ch] = g * k.c;
+                            }
+                        }
+                        l1 *= (1.0f / 3.0f);
+                        const float rp = no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                        const size_t qo = (size_t)qy * W + qx;
+                        float best = rp;
+                        int best_idx = 0;
+                        bool win = true;
+                        if (p.ident) {
+                            float idv = __ldg(p.ident + (size_t)b * N + qo);
+                            if (p.noise) idv = add_rn(idv, __ldg(p.noise + (size_t)b * N + qo));
+                            win = rp < idv;                     // torch.min: first minimum wins, identity is first
+                            best = win ? rp : idv;
+                            best_idx = win ? 1 : 0;
+                        }
+                        gt = win ? 1 : 0;
+                        if (!win) {
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) { ka[ch] = 0.f; kb[ch] = 0.f; kc[ch] = 0.f; }
+                        }
+                        if (qr >= 1 && qr <= FT_T && c >= 1 && c <= FT_T) {
+                            loss_local += best;
+                            if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)best_idx;
+                        }
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        coef[(ch * 3 + 0) * FT_N1 + qi] = ka[ch];
+                        coef[(ch * 3 + 1) * FT_N1 + qi] = kb[ch];
+                        coef[(ch * 3 + 2) * FT_N1 + qi] = kc[ch];
+                    }
+                    gate[qi] = gt;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                hist[ch][0] = hist[ch][1];
+                hist[ch][1] = cur[ch];
+                cen_x[ch] = mid_x[ch]; cen_y[ch] = mid_y[ch];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp)
+    {
+        const int px = x0 + oc;
+        const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
+        const float wr = (px == W - 2) ? 2.0f : 1.0f;
+        float hprev[2][9];
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r1 = 4 * os + rr;                      // ring row
+            float hc[9];
+            const float* base = coef + r1 * FT_R1 + oc;
+#pragma unroll
+            for (int pl = 0; pl < 9; ++pl) {
+                const float* q = base + pl * FT_N1;
+                hc[pl] = fmaf(wl, q[0], fmaf(wr, q[2], q[1]));
+            }
+            if (rr >= 2) {
+                const int k = rr - 2;
+                const int r = 4 * os + k;
+                const int py = y0 + r;
+                if (py < H && px < W) {
+                    const float wu = (py == 1) ? 2.0f : 1.0f;
+                    const float wd = (py == H - 2) ? 2.0f : 1.0f;
+                    const int i2 = (r + 2) * FT_R2 + oc + 2;
+                    const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
+                    float g = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float sa = fmaf(wu, hprev[0][ch * 3 + 0], fmaf(wd, hc[ch * 3 + 0], hprev[1][ch * 3 + 0]));
+                        const float sb = fmaf(wu, hprev[0][ch * 3 + 1], fmaf(wd, hc[ch * 3 + 1], hprev[1][ch * 3 + 1]));
+                        const float sc = fmaf(wu, hprev[0][ch * 3 + 2], fmaf(wd, hc[ch * 3 + 2], hprev[1][ch * 3 + 2]));
+                        const float xv = pred[ch * FT_N2 + i2], yv = tgt[ch * FT_N2 + i2];
+                        const float d = xv - yv;
+                        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                        const float g_pred = fmaf(sb, xv, fmaf(sc, yv, sa)) + gl1 * sg;
+                        g = fmaf(g_pred, D[k][ch], g);
+                    }
+                    p.grad_disp[(size_t)b * N + (size_t)py * W + px] = g;
+                }
+            }
+#pragma unroll
+            for (int pl = 0; pl < 9; ++pl) { hprev[0][pl] = hprev[1][pl]; hprev[1][pl] = hc[pl]; }
+        }
+    }
+    const float s = block_sum(loss_local, red);
+    if (tid == 0) p.loss_partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+}
+
+size_t fast_smem_bytes() { return sizeof(float) * (6 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
+
+}  // namespace
+
+namespace dmh {
+
+int photo_fast_tiles(int H, int W) { return ceil_div(W, FT_T) * ceil_div(H, FT_T); }
+
+// Called by dmh_photo_scale when F == 1 and no pose gradient is requested.
+int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, const float* K,
+                      const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
+                      float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
+                      uint8_t* sel, float* warped, cudaStream_t st) {
+    FastParams p;
+    p.target = target; p.src = src; p.T = T; p.disp = disp; p.K = K; p.inv_K = inv_K; p.ident = ident;
+    p.noise = noise; p.loss_partial = loss_partial; p.grad_disp = grad_disp; p.sel = sel; p.warped = warped;
+    p.B = B; p.H = H; p.W = W; p.flags = flags;
+    const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
+    p.ds.min_disp = is_depth ? 0.f : (float)(1.0 / (double)max_depth);
+    p.ds.range = is_depth ? 0.f : (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
+    p.grad_scale = grad_scale;
+    const size_t smem = fast_smem_bytes();
+    static bool configured_dev[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(photo_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("dmh_photo_scale(fast): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return DMH_ERR_CUDA;
+        }
+        configured_dev[dev & 63] = true;
+    }
+    dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B);
+    DMH_LAUNCH(photo_fast_kernel, grid, FT_THREADS, smem, st)(p);
+    return DMH_OK;
+}
+
+}  // namespace dmh

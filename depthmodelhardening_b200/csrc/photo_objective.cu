@@ -415,6 +415,14 @@ int launch_photo(const PhotoParams& p, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
+namespace dmh {
+int photo_fast_tiles(int H, int W);
+int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, const float* K,
+                      const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
+                      float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
+                      uint8_t* sel, float* warped, cudaStream_t st);
+}  // namespace dmh
+
 extern "C" {
 
 int dmh_photo_tiles(int H, int W) { return ceil_div(W, PH_TW) * ceil_div(H, PH_TH); }
@@ -430,6 +438,23 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
     DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "dmh_photo_scale: bad shape B=%d H=%d W=%d", B, H, W);
     const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
     DMH_REQUIRE(is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_photo_scale: bad depth range");
+    if (F == 1 && !grad_P_partial && !(flags & DMH_PHOTO_FORCE_GENERIC)) {
+        // single source frame, no pose gradient: the 32x32-tile fast kernel (photo_fast.cu).  It writes
+        // fewer partial sums than dmh_photo_tiles() promises; zero the tail so the caller's reduction is exact.
+        DMH_REQUIRE(src_host[0] && T_host[0], "dmh_photo_scale: null src/T for frame 0");
+        const int used = B * photo_fast_tiles(H, W), total = B * dmh_photo_tiles(H, W);
+        if (total > used) {
+            cudaError_t e = cudaMemsetAsync(loss_partial + used, 0, sizeof(float) * (size_t)(total - used),
+                                            (cudaStream_t)stream);
+            if (e != cudaSuccess) { set_error("dmh_photo_scale: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+        }
+        const int rc = launch_photo_fast(target, src_host[0], T_host[0], disp, K, inv_K, ident, noise, B, H, W, min_depth,
+                                         max_depth, flags, grad_scale, loss_partial, grad_disp, sel,
+                                         warped_host ? warped_host[0] : nullptr, (cudaStream_t)stream);
+        if (rc != DMH_OK) return rc;
+        DMH_CHECK_LAUNCH("dmh_photo_scale(fast)");
+        return DMH_OK;
+    }
     PhotoParams p;
     p.target = target;
     for (int f = 0; f < PH_MAXF; ++f) {

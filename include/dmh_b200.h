@@ -145,6 +145,7 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
 #define DMH_PHOTO_NO_SSIM 1
 #define DMH_PHOTO_AVG_REPROJECTION 2
 #define DMH_PHOTO_INPUT_IS_DEPTH 4
+#define DMH_PHOTO_FORCE_GENERIC 8 /* testing: never take the single-source fast kernel */
 #define DMH_PHOTO_MAX_FRAMES 4
 int dmh_photo_tiles(int H, int W);           /* CTAs per batch item */
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,

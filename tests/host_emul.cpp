@@ -307,4 +307,105 @@ void emu_photo_scale(const float* target, const float* const* src, const float* 
     *loss_sum = total;
 }
 
+
+// Single-source fast path arithmetic (photo_fast.cu): separable sliding sums,
+// sum*(1/9) means, shared reciprocal, chain collapsed into 3 scalars per pixel.
+void emu_photo_scale_fast(const float* target, const float* src, const float* T, const float* disp, const float* K,
+                          const float* inv_K, const float* ident, const float* noise, int B, int H, int W,
+                          float min_depth, float max_depth, int flags, double* loss_sum, float* gdisp, uint8_t* sel) {
+    const bool no_ssim = flags & 1;
+    const float w_ssim = no_ssim ? 0.f : 0.85f / 3.f, w_l1 = no_ssim ? 1.f / 3.f : 0.15f / 3.f;
+    DepthScale ds{(float)(1.0 / (double)max_depth), (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth)};
+    const long long N = (long long)H * W;
+    std::vector<float> pred(3 * N), D(3 * N), coef(9 * N), gate(N);
+    double total = 0.0;
+    auto PX = [&](const std::vector<float>& a, int ch, int y, int x) { return a[ch * N + (long long)reflect1(y, H) * W + reflect1(x, W)]; };
+    for (int b = 0; b < B; ++b) {
+        Camera cam;
+        compose_camera(K + b * 16, T + b * 16, inv_K + b * 16, cam);
+        const float* tg = target + (long long)b * 3 * N;
+        for (long long n = 0; n < N; ++n) {
+            const int x = (int)(n % W), y = (int)(n / W);
+            const float depth = disp_to_depth(disp[b * N + n], ds);
+            WarpCoord wc = warp_coord(cam, (float)x, (float)y, depth, W, H, 1e-7f);
+            Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+            TapSet t = taps(bl, H, W);
+            float ax, ay;
+            warp_chain_factors(cam, wc, W, H, ax, ay);
+            const float dd = ddepth_ddisp(depth, ds);
+            for (int c = 0; c < 3; ++c) {
+                const float* s = src + ((long long)b * 3 + c) * N;
+                const float nw = tap(s, t.o00, t.nw), ne = tap(s, t.o00 + 1, t.ne), sw = tap(s, t.o00 + W, t.sw),
+                            se = tap(s, t.o00 + W + 1, t.se);
+                float acc = nw * bl.wnw;
+                acc = fmaf(ne, bl.wne, acc); acc = fmaf(sw, bl.wsw, acc); acc = fmaf(se, bl.wse, acc);
+                pred[c * N + n] = acc;
+                const float dix = (ne - nw) * bl.ty1 + (se - sw) * bl.ty0, diy = (sw - nw) * bl.tx1 + (se - ne) * bl.tx0;
+                D[c * N + n] = (dix * ax + diy * ay) * dd;
+            }
+        }
+        for (int qy = 0; qy < H; ++qy)
+            for (int qx = 0; qx < W; ++qx) {
+                const long long q = (long long)qy * W + qx;
+                float l1 = 0.f, ss = 0.f, ka[3] = {0, 0, 0}, kb[3] = {0, 0, 0}, kc[3] = {0, 0, 0};
+                for (int c = 0; c < 3; ++c) {
+                    l1 += fabsf(tg[c * N + q] - pred[c * N + q]);
+                    if (!no_ssim) {
+                        Row5 rows[3];
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            auto TG = [&](int yy, int xx) { return tg[c * N + (long long)reflect1(yy, H) * W + reflect1(xx, W)]; };
+                            rows[dy + 1] = row5(PX(pred, c, qy + dy, qx - 1), PX(pred, c, qy + dy, qx), PX(pred, c, qy + dy, qx + 1),
+                                                TG(qy + dy, qx - 1), TG(qy + dy, qx), TG(qy + dy, qx + 1));
+                        }
+                        SsimStats st = ssim_stats_rows(rows[0], rows[1], rows[2]);
+                        float pass; SsimCoef k;
+                        ss += ssim_value_coef(st, pass, k);
+                        const float g = w_ssim * pass;
+                        ka[c] = g * k.ax; kb[c] = g * k.b; kc[c] = g * k.c;
+                    }
+                }
+                l1 *= (1.0f / 3.0f);
+                const float rp = no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                float best = rp; int best_idx = 0; bool win = true;
+                if (ident) {
+                    float idv = ident[b * N + q];
+                    if (noise) idv = add_rn(idv, noise[b * N + q]);
+                    win = rp < idv; best = win ? rp : idv; best_idx = win ? 1 : 0;
+                }
+                gate[q] = win ? 1.f : 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    coef[(c * 3 + 0) * N + q] = win ? ka[c] : 0.f;
+                    coef[(c * 3 + 1) * N + q] = win ? kb[c] : 0.f;
+                    coef[(c * 3 + 2) * N + q] = win ? kc[c] : 0.f;
+                }
+                total += best;
+                if (sel) sel[b * N + q] = (uint8_t)best_idx;
+            }
+        auto CF = [&](int pl, int y, int x) -> float { return (y < 0 || y >= H || x < 0 || x >= W) ? 0.f : coef[pl * N + (long long)y * W + x]; };
+        for (int py = 0; py < H; ++py)
+            for (int px = 0; px < W; ++px) {
+                const long long n = (long long)py * W + px;
+                const float wl = px == 1 ? 2.f : 1.f, wr = px == W - 2 ? 2.f : 1.f, wu = py == 1 ? 2.f : 1.f, wd = py == H - 2 ? 2.f : 1.f;
+                float g = 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    float s3[3];
+                    for (int j = 0; j < 3; ++j) {
+                        const int pl = c * 3 + j;
+                        float h[3];
+                        for (int dy = -1; dy <= 1; ++dy)
+                            h[dy + 1] = fmaf(wl, CF(pl, py + dy, px - 1), fmaf(wr, CF(pl, py + dy, px + 1), CF(pl, py + dy, px)));
+                        s3[j] = fmaf(wu, h[0], fmaf(wd, h[2], h[1]));
+                    }
+                    const float xv = pred[c * N + n], yv = tg[c * N + n];
+                    const float d = xv - yv;
+                    const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                    const float g_pred = fmaf(s3[1], xv, fmaf(s3[2], yv, s3[0])) + gate[n] * w_l1 * sg;
+                    g = fmaf(g_pred, D[c * N + n], g);
+                }
+                gdisp[b * N + n] = g;
+            }
+    }
+    *loss_sum = total;
+}
+
 }  // extern "C"

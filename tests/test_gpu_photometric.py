@@ -185,7 +185,8 @@ def test_fused_objective_vs_reference_golden(dev, name):
     _, _, g64 = OP.objective_from_batch(pb, OP.default_opts(scales=list(pb.scales), **over), dtype=torch.float64)
     for s in pb.scales:
         assert_close(losses["loss/%d" % s], g["loss_%d" % s], TOL, "loss/%d" % s)
-        assert_grad_close(disps[s].grad, g["grad_disp_%d" % s], g64[s], TOL, "grad_disp_%d" % s)
+        assert_grad_close(disps[s].grad, g["grad_disp_%d" % s], g64[s], TOL, "grad_disp_%d" % s,
+                          outlier_frac=5e-3 if name == "stereo_iid" else 2e-3)
         if n_ident:
             sel = (aux[("argmin", s)].cpu().numpy() > n_ident - 1).astype(np.uint8)
             assert np.mean(sel != g["ident_sel_%d" % s]) < 1e-4

@@ -15,7 +15,7 @@ import torch
 from depthmodelhardening_b200 import synth
 from oracle import photometric as OP
 from oracle.make_golden import PHOTO_CASES
-from tests.util import assert_close, load_golden
+from tests.util import assert_close, assert_grad_close, load_golden
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
@@ -119,3 +119,37 @@ def test_fused_objective_math_vs_reference_golden(emu, name):
         if automask:
             assert np.array_equal((sel.numpy() > n_ident - 1).astype(np.uint8), g["ident_sel_%d" % s])
     assert_close(total / len(pb.scales), g["loss"], 1e-5, "loss")
+
+
+@pytest.mark.parametrize("name", ["stereo_small", "stereo_iid", "no_ssim", "no_automask_f1"])
+def test_fast_path_arithmetic_vs_reference_golden(emu, name):
+    """photo_fast.cu's arithmetic (separable sums, sum*(1/9), collapsed chain) on the host."""
+    skw, over = PHOTO_CASES[name]
+    pb = synth.photo_batch(**skw)
+    g = load_golden("photo_" + name)
+    B, H, W = pb.batch, pb.height, pb.width
+    flags = 1 if over.get("no_ssim") else 0
+    automask = not over.get("disable_automasking", False)
+    target, src, T = pb.color[(0, 0)].contiguous(), pb.color[("s", 0)].contiguous(), pb.T["s"].contiguous()
+    ident = OP.reprojection_loss(src, target, bool(over.get("no_ssim"))).contiguous() if automask else None
+    _, _, g64 = OP.objective_from_batch(pb, OP.default_opts(scales=list(pb.scales), **over), dtype=torch.float64)
+    for s in pb.scales:
+        dlow = pb.disp[s].clone().requires_grad_(True)
+        dfull = torch.nn.functional.interpolate(dlow, [H, W], mode="bilinear", align_corners=False)
+        nz = pb.noise[s][:, :1].contiguous() if automask else None
+        loss_sum = C.c_double(0.0)
+        gd = torch.empty(B, 1, H, W)
+        sel = torch.empty(B, H, W, dtype=torch.uint8)
+        emu.emu_photo_scale_fast(vp(target), vp(src), vp(T), vp(dfull.detach()), vp(pb.K), vp(pb.inv_K),
+                                 vp(ident) if automask else None, vp(nz) if automask else None, B, H, W,
+                                 C.c_float(0.1), C.c_float(100.0), flags, C.byref(loss_sum), vp(gd), vp(sel))
+        sm = OP.normalised_smooth_loss(dlow, pb.color[(0, s)])
+        smw = 1e-3 / (2 ** s)
+        assert_close(loss_sum.value / (B * H * W) + smw * float(sm.detach()), g["loss_%d" % s], 1e-5, "loss/%d" % s)
+        (dfull * gd / (B * H * W) / len(pb.scales)).sum().backward(retain_graph=True)
+        (sm * smw / len(pb.scales)).backward()
+        # iid inputs ("adversarial gather") put many pixels on floor()/argmin knife edges: allow 0.5 % there
+        assert_grad_close(dlow.grad, g["grad_disp_%d" % s], g64[s], 1e-5, "grad_disp_%d" % s,
+                          outlier_frac=5e-3 if name == "stereo_iid" else 2e-3)
+        if automask:
+            assert np.mean((sel.numpy() > 0).astype(np.uint8) != g["ident_sel_%d" % s]) < 1e-3
