@@ -72,4 +72,32 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
     return v;
 }
 
+
+// ATen upsample_bilinear2d (align_corners=False) source taps: src = max(scale*(dst+0.5)-0.5, 0)
+struct UpTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ UpTap up_tap(int dst, float scale, int in_size) {
+    UpTap t;
+    const float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.0f);
+    t.i0 = min((int)src, in_size - 1);
+    t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
+    t.l1 = src - (float)t.i0;
+    t.l0 = 1.0f - t.l1;
+    return t;
+}
+
+// A (h,w) disparity map read as if F.interpolate'd to (H,W) (trainer.py:481-482);
+// direct read when the sizes match.
+struct DispSrc {
+    const float* ptr;
+    int h, w;
+    float sh, sw;      // h/H, w/W
+};
+__device__ __forceinline__ float load_disp(const DispSrc& d, int b, int iy, int ix, int H, int W) {
+    const float* p = d.ptr + (size_t)b * d.h * d.w;
+    if (d.h == H && d.w == W) return __ldg(p + (size_t)iy * W + ix);
+    const UpTap ty = up_tap(iy, d.sh, d.h), tx = up_tap(ix, d.sw, d.w);
+    return ty.l0 * (tx.l0 * __ldg(p + ty.i0 * d.w + tx.i0) + tx.l1 * __ldg(p + ty.i0 * d.w + tx.i1)) +
+           ty.l1 * (tx.l0 * __ldg(p + ty.i1 * d.w + tx.i0) + tx.l1 * __ldg(p + ty.i1 * d.w + tx.i1));
+}
+
 }  // namespace dmh

@@ -39,7 +39,7 @@ struct FastParams {
     const float* target;
     const float* src;
     const float* T;
-    const float* disp;
+    DispSrc disp;
     const float* K;
     const float* inv_K;
     const float* ident;
@@ -135,7 +135,6 @@ photo_fast_kernel(const FastParams p) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) cam.iK[i] = cams[12 + i];
     const float* sp = p.src + (size_t)b * 3 * N;
-    const float* dp_ = p.disp + (size_t)b * N;
 
     // ---- phase A: warp.  Owned interior pixels: column tid%32, rows 4*(tid/32)+k
     const int oc = tid & 31, os = tid >> 5;
@@ -144,7 +143,7 @@ photo_fast_kernel(const FastParams p) {
     for (int k = 0; k < 4; ++k) {
         const int r = 4 * os + k;
         const int iy = ext_to_img(y0 + r, H), ix = ext_to_img(x0 + oc, W);
-        const float dv = __ldg(dp_ + (size_t)iy * W + ix);
+        const float dv = load_disp(p.disp, b, iy, ix, H, W);
         const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
         const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
         const Gathered g = gather3(sp, N, wc, H, W, true);
@@ -170,7 +169,7 @@ photo_fast_kernel(const FastParams p) {
         else if (h < 208) { const int t = h - 144; r = 2 + (t >> 1); c = t & 1; }
         else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
         const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
-        const float dv = __ldg(dp_ + (size_t)iy * W + ix);
+        const float dv = load_disp(p.disp, b, iy, ix, H, W);
         const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
         const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
         const Gathered g = gather3(sp, N, wc, H, W, false);
@@ -323,12 +322,13 @@ namespace dmh {
 int photo_fast_tiles(int H, int W) { return ceil_div(W, FT_T) * ceil_div(H, FT_T); }
 
 // Called by dmh_photo_scale when F == 1 and no pose gradient is requested.
-int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, const float* K,
-                      const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
+int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, int disp_h,
+                      int disp_w, const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
                       uint8_t* sel, float* warped, cudaStream_t st) {
     FastParams p;
-    p.target = target; p.src = src; p.T = T; p.disp = disp; p.K = K; p.inv_K = inv_K; p.ident = ident;
+    p.target = target; p.src = src; p.T = T; p.K = K;
+    p.disp.ptr = disp; p.disp.h = disp_h; p.disp.w = disp_w; p.disp.sh = (float)disp_h / (float)H; p.disp.sw = (float)disp_w / (float)W; p.inv_K = inv_K; p.ident = ident;
     p.noise = noise; p.loss_partial = loss_partial; p.grad_disp = grad_disp; p.sel = sel; p.warped = warped;
     p.B = B; p.H = H; p.W = W; p.flags = flags;
     const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;

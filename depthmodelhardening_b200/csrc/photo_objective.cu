@@ -37,7 +37,7 @@ struct PhotoParams {
     const float* target;
     const float* src[PH_MAXF];
     const float* T[PH_MAXF];
-    const float* disp;
+    DispSrc disp;
     const float* K;
     const float* inv_K;
     const float* ident;
@@ -144,7 +144,7 @@ photo_scale_kernel(const PhotoParams p) {
         const size_t o = (size_t)iy * W + ix;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) tgt[ch * PH_R2 + i] = __ldg(p.target + ((size_t)b * 3 + ch) * N + o);
-        const float dv = __ldg(p.disp + (size_t)b * N + o);
+        const float dv = load_disp(p.disp, b, iy, ix, H, W);
         dep[i] = is_depth ? dv : disp_to_depth(dv, p.ds);
     }
     __syncthreads();
@@ -417,8 +417,8 @@ int launch_photo(const PhotoParams& p, dim3 grid, cudaStream_t st) {
 
 namespace dmh {
 int photo_fast_tiles(int H, int W);
-int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, const float* K,
-                      const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
+int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, int disp_h,
+                      int disp_w, const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
                       uint8_t* sel, float* warped, cudaStream_t st);
 }  // namespace dmh
@@ -428,14 +428,15 @@ extern "C" {
 int dmh_photo_tiles(int H, int W) { return ceil_div(W, PH_TW) * ceil_div(H, PH_TH); }
 
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
-                    const float* disp, const float* K, const float* inv_K, const float* ident, const float* noise,
-                    int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
+                    const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K, const float* ident,
+                    const float* noise, int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
                     float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
                     float* const* warped_host, dmh_stream_t stream) {
     DMH_REQUIRE(target && src_host && T_host && disp && K && inv_K && loss_partial && grad_disp,
                 "dmh_photo_scale: null pointer");
     DMH_REQUIRE(F >= 1 && F <= PH_MAXF, "dmh_photo_scale: F=%d outside [1,%d]", F, PH_MAXF);
     DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "dmh_photo_scale: bad shape B=%d H=%d W=%d", B, H, W);
+    DMH_REQUIRE(disp_h >= 1 && disp_w >= 1 && disp_h <= H && disp_w <= W, "dmh_photo_scale: bad disparity size %dx%d", disp_h, disp_w);
     const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
     DMH_REQUIRE(is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_photo_scale: bad depth range");
     if (F == 1 && !grad_P_partial && !(flags & DMH_PHOTO_FORCE_GENERIC)) {
@@ -448,7 +449,7 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
                                             (cudaStream_t)stream);
             if (e != cudaSuccess) { set_error("dmh_photo_scale: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
         }
-        const int rc = launch_photo_fast(target, src_host[0], T_host[0], disp, K, inv_K, ident, noise, B, H, W, min_depth,
+        const int rc = launch_photo_fast(target, src_host[0], T_host[0], disp, disp_h, disp_w, K, inv_K, ident, noise, B, H, W, min_depth,
                                          max_depth, flags, grad_scale, loss_partial, grad_disp, sel,
                                          warped_host ? warped_host[0] : nullptr, (cudaStream_t)stream);
         if (rc != DMH_OK) return rc;
@@ -463,7 +464,9 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
         p.warped[f] = (warped_host && f < F) ? warped_host[f] : nullptr;
         DMH_REQUIRE(f >= F || (p.src[f] && p.T[f]), "dmh_photo_scale: null src/T for frame %d", f);
     }
-    p.disp = disp; p.K = K; p.inv_K = inv_K; p.ident = ident; p.noise = noise;
+    p.disp.ptr = disp; p.disp.h = disp_h; p.disp.w = disp_w;
+    p.disp.sh = (float)disp_h / (float)H; p.disp.sw = (float)disp_w / (float)W;
+    p.K = K; p.inv_K = inv_K; p.ident = ident; p.noise = noise;
     p.loss_partial = loss_partial; p.grad_disp = grad_disp; p.grad_P_partial = grad_P_partial; p.sel = sel;
     p.B = B; p.H = H; p.W = W; p.F = F; p.flags = flags;
     p.ds.min_disp = is_depth ? 0.f : (float)(1.0 / (double)max_depth);

@@ -327,17 +327,6 @@ smooth_bwd_finalize_kernel(int hw, int nblk, const float* __restrict__ mean_part
 // F.interpolate(disp, [H,W], mode="bilinear", align_corners=False) of trainer.py:481-482
 // (ATen upsample_bilinear2d: src = max(scale*(dst+0.5)-0.5, 0)), forward and a
 // DETERMINISTIC gather backward (ATen's CUDA backward scatters with atomics).
-struct UpTap { int i0, i1; float l0, l1; };
-__device__ __forceinline__ UpTap up_tap(int dst, float scale, int in_size) {
-    UpTap t;
-    const float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.0f);
-    t.i0 = min((int)src, in_size - 1);
-    t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
-    t.l1 = src - (float)t.i0;
-    t.l0 = 1.0f - t.l1;
-    return t;
-}
-
 __global__ void upsample_fwd_kernel(const float* __restrict__ in, int h, int w, int H, int W, float sh, float sw,
                                     float* __restrict__ out) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x;

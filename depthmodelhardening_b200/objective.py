@@ -50,46 +50,43 @@ def photometric_losses(colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids,
     returns (losses dict like the reference's, aux dict)
     """
     srcs_ids = list(frame_ids[1:])
+    scales = list(scales)
     target = colors[(0, 0)]
     B = target.shape[0]
     srcs = [colors[(f, 0)] for f in srcs_ids]
     T_list = [Ts[f] for f in srcs_ids]
     n_src = len(srcs)
-    losses, aux = {}, {}
-    ident = None
-    if not disable_automasking:
-        # identity reprojection loss is scale independent: once, not once per scale
-        with torch.no_grad():
-            ident = torch.cat([ops.reprojection_loss(s, target, no_ssim) for s in srcs], 1)
     n_ident = 0 if disable_automasking else (1 if avg_reprojection else n_src)
-    total = 0
-    for scale in scales:
-        disp = disps[scale]
-        if disp.shape[2] != height or disp.shape[3] != width:
-            disp_full = ops.upsample_bilinear(disp, (height, width))
-        else:
-            disp_full = disp
-        nz = None
-        if n_ident:
+    nz = None
+    if n_ident:
+        nz = []
+        for scale in scales:
             if noise is not None:
-                nz = noise[scale]
-                if nz is not None and nz.shape[1] != n_ident:
-                    nz = nz[:, :n_ident].contiguous()
+                t = noise[scale]
+                if t is not None and t.shape[1] != n_ident:
+                    t = t[:, :n_ident].contiguous()
             else:
-                nz = tie_break_noise((B, n_ident, height, width), target.device, noise_mode)
-        ssum, sel = ops.photo_scale_sum(disp_full, target, srcs, T_list, K, inv_K, ident=ident, noise=nz,
-                                        min_depth=min_depth, max_depth=max_depth, no_ssim=no_ssim,
-                                        avg_reprojection=avg_reprojection, want_sel=want_selection)
-        loss = ssum / float(B * height * width)
-        if sel is not None:
+                t = tie_break_noise((B, n_ident, height, width), target.device, noise_mode)
+            nz.append(t)
+        if any(t is None for t in nz):
+            nz = None
+    if scales[0] != 0:
+        raise NotImplementedError("the fused objective needs scale 0 first in opt.scales (it is the photometric "
+                                  "target: source_scale == 0, trainer.py:483)")
+    colors0 = [target] + [colors[(0, s)] for s in scales[1:]]
+    out = ops.objective(colors0, srcs, T_list, [disps[s] for s in scales], K, inv_K, noises=nz, min_depth=min_depth,
+                        max_depth=max_depth, no_ssim=no_ssim, avg_reprojection=avg_reprojection,
+                        automask=not disable_automasking,
+                        smooth_weights=[disparity_smoothness / (2 ** s) for s in scales], want_sel=want_selection)
+    total, per_scale = out[0], out[1]
+    losses, aux = {}, {}
+    for i, scale in enumerate(scales):
+        losses["loss/{}".format(scale)] = per_scale[i]
+        if want_selection:
+            sel = out[2 + i]
             aux[("argmin", scale)] = sel
             if n_ident:
                 aux["identity_selection/{}".format(scale)] = (sel > n_ident - 1).float()
-        sm = ops.smooth_loss(disp, colors[(0, scale)], normalise=True)
-        loss = loss + disparity_smoothness * sm / (2 ** scale)
-        losses["loss/{}".format(scale)] = loss
-        total = total + loss
-    total = total / len(scales)
     losses["loss"] = total
     return losses, aux
 

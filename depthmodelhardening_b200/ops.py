@@ -361,7 +361,7 @@ class _PhotoScale(torch.autograd.Function):
         gP = torch.empty(n_src, B, tiles, 12, device=d.device, dtype=torch.float32) if need_T else None
         sel = torch.empty(B, H, W, device=d.device, dtype=torch.uint8) if want_sel else None
         with _timed("photo_scale"):
-            check(lib.dmh_photo_scale(ptr(tg), ptr_array(srcs), ptr_array(Ts), n_src, ptr(d), ptr(k), ptr(ik),
+            check(lib.dmh_photo_scale(ptr(tg), ptr_array(srcs), ptr_array(Ts), n_src, ptr(d), H, W, ptr(k), ptr(ik),
                                       ptr(idn), ptr(nz), B, H, W, min_depth, max_depth, flags, 1.0, ptr(part),
                                       ptr(gdisp), ptr(gP), ptr(sel), None, stream()), "photo_scale")
         total = torch.empty((), device=d.device, dtype=torch.float32)
@@ -397,3 +397,132 @@ def photo_scale_sum(disp_full, target, srcs: Sequence[torch.Tensor], Ts: Sequenc
             (FLAG_INPUT_IS_DEPTH if input_is_depth else 0)
     return _PhotoScale.apply(disp_full, target, ident, noise, K, inv_K, float(min_depth), float(max_depth), flags,
                              bool(want_sel), len(srcs), *srcs, *Ts)
+
+
+# ----------------------------------------------------------------------------- whole multi-scale objective
+import ctypes as _C
+
+
+class _Objective(torch.autograd.Function):
+    """generate_images_pred + compute_losses (photometric part) for ALL scales as one
+    autograd node: forward = ident + S x (photo kernel with fused up-sampling, smooth
+    fused) + one finish launch; backward = one dmh_disp_grad launch per scale that
+    applies the incoming scalar gradient(s) on the device."""
+
+    @staticmethod
+    def forward(ctx, K, inv_K, cfg, *tensors):
+        (min_depth, max_depth, flags, smooth_w, want_sel, n_src, S, automask, has_noise) = cfg
+        it = iter(tensors)
+        colors = [f32c(next(it)) for _ in range(S)]          # color(0, s)
+        srcs = [f32c(next(it)) for _ in range(n_src)]
+        Ts = [f32c(next(it)) for _ in range(n_src)]
+        disps = [f32c(next(it)) for _ in range(S)]
+        noises = [f32c(next(it)) for _ in range(S)] if has_noise else [None] * S
+        k, ik = f32c(K), f32c(inv_K)
+        target = colors[0]
+        B, _, H, W = target.shape
+        dev = target.device
+        lib = _lib_()
+        no_ssim = 1 if (flags & FLAG_NO_SSIM) else 0
+        ident = None
+        if automask:
+            ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32)
+            if n_src == 1:
+                check(lib.dmh_reproj_loss_fwd(ptr(srcs[0]), ptr(target), B, 3, H, W, no_ssim, ptr(ident), stream()),
+                      "ident")
+            else:
+                tmp = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
+                for f in range(n_src):
+                    check(lib.dmh_reproj_loss_fwd(ptr(srcs[f]), ptr(target), B, 3, H, W, no_ssim, ptr(tmp), stream()),
+                          "ident")
+                    ident[:, f:f + 1].copy_(tmp)
+        # disp grads are needed iff any disparity requires grad; pose grads iff any T does
+        base = 3 + S + n_src
+        need_T = any(ctx.needs_input_grad[base + i] for i in range(n_src))
+        tiles = lib.dmh_photo_tiles(H, W)
+        G, gN, wss, parts, gPs, sels = [], [], [], [], [], []
+        src_arr, T_arr = ptr_array(srcs), ptr_array(Ts)
+        inv_den = 1.0 / float(B * H * W)
+        for s in range(S):
+            d = disps[s]
+            h, w = d.shape[2], d.shape[3]
+            part = torch.empty(B * tiles, device=dev, dtype=torch.float32)
+            g_full = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
+            gP = torch.empty(n_src, B, tiles, 12, device=dev, dtype=torch.float32) if need_T else None
+            sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None
+            with _timed("photo_scale"):
+                check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik), ptr(ident),
+                                          ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den, ptr(part),
+                                          ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
+            ws = torch.empty(lib.dmh_smooth_fused_workspace_floats(B, h, w), device=dev, dtype=torch.float32)
+            gn = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
+            check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, h, w, ptr(ws), ptr(gn), stream()), "smooth_fused")
+            G.append(g_full); gN.append(gn); wss.append(ws); parts.append(part); gPs.append(gP); sels.append(sel)
+        img_scalars = torch.empty(S, B, 2, device=dev, dtype=torch.float32)
+        losses = torch.empty(S + 1, device=dev, dtype=torch.float32)
+        hs = (_C.c_int * S)(*[d.shape[2] for d in disps])
+        wsz = (_C.c_int * S)(*[d.shape[3] for d in disps])
+        pn = (_C.c_int * S)(*[p_.numel() for p_ in parts])
+        sw = (_C.c_float * S)(*[float(x) for x in smooth_w])
+        check(lib.dmh_objective_finish(S, B, ptr_array(wss), hs, wsz, ptr_array(parts), pn, sw, float(B * H * W),
+                                       ptr(img_scalars), ptr(losses), stream()), "objective_finish")
+        ctx.cfg = (S, n_src, B, H, W, tuple(float(x) for x in smooth_w), need_T, [tuple(d.shape) for d in disps],
+                   has_noise)
+        ctx.save_for_backward(img_scalars, k, *G, *gN, *[t for t in Ts], *[g for g in gPs if g is not None])
+        out_sels = tuple(sels) if want_sel else ()
+        for t in out_sels:
+            ctx.mark_non_differentiable(t)
+        return (losses[S], losses[:S]) + out_sels
+
+    @staticmethod
+    def backward(ctx, g_total, g_scales, *_unused):
+        S, n_src, B, H, W, smooth_w, need_T, dshapes, has_noise = ctx.cfg
+        saved = ctx.saved_tensors
+        img_scalars, k = saved[0], saved[1]
+        G = saved[2:2 + S]
+        gN = saved[2 + S:2 + 2 * S]
+        Ts = saved[2 + 2 * S:2 + 2 * S + n_src]
+        gPs = saved[2 + 2 * S + n_src:]
+        lib = _lib_()
+        gt = f32c(g_total).reshape(1) if g_total is not None else None
+        gs = f32c(g_scales) if g_scales is not None else None
+        if gt is None and gs is None:
+            gt = torch.zeros(1, device=G[0].device)
+        base = 3 + S + n_src
+        grads_disp = []
+        for s in range(S):
+            if not ctx.needs_input_grad[base + n_src + s]:
+                grads_disp.append(None)
+                continue
+            _, _, h, w = dshapes[s]
+            gd = torch.empty(B, 1, h, w, device=G[s].device, dtype=torch.float32)
+            check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
+                                    ptr(gs[s:s + 1]) if gs is not None else None, 1.0 / S, B, h, w, H, W, ptr(gd),
+                                    stream()), "disp_grad")
+            grads_disp.append(gd.view(dshapes[s]))
+        g_T = [None] * n_src
+        if need_T:
+            u = [(gt[0] / S if gt is not None else 0.0) + (gs[s] if gs is not None else 0.0) for s in range(S)]
+            for f in range(n_src):
+                if ctx.needs_input_grad[base + f]:
+                    acc = None
+                    for s in range(S):
+                        t = gPs[s][f].sum(1) * u[s]
+                        acc = t if acc is None else acc + t
+                    _, g_T[f] = _grad_KT_from_P(acc.view(-1, 3, 4), k, Ts[f], False, True)
+        return (None, None, None) + (None,) * S + (None,) * n_src + tuple(g_T) + tuple(grads_disp) + \
+            ((None,) * S if has_noise else ())
+
+
+def objective(colors0, srcs, Ts, disps, K, inv_K, noises=None, min_depth=0.1, max_depth=100.0, no_ssim=False,
+              avg_reprojection=False, automask=True, smooth_weights=None, want_sel=False):
+    """colors0[s] = colour(0, s) pyramid (scale 0 is the target); srcs/Ts per source frame;
+    disps[s] network disparities; noises[s] (B,Fi,H,W) or None.
+    Returns (total, per-scale losses (S,), *sel)."""
+    S, n_src = len(disps), len(srcs)
+    flags = (FLAG_NO_SSIM if no_ssim else 0) | (FLAG_AVG_REPROJECTION if avg_reprojection else 0)
+    has_noise = automask and noises is not None and all(n is not None for n in noises)
+    cfg = (float(min_depth), float(max_depth), flags, tuple(smooth_weights), bool(want_sel), n_src, S, bool(automask),
+           has_noise)
+    tensors = list(colors0) + list(srcs) + list(Ts) + list(disps) + (list(noises) if has_noise else [])
+    return _Objective.apply(K, inv_K, cfg, *tensors)

@@ -129,15 +129,17 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
  *    (M2/trainer.py:472-523 + 589-660 for one value of `scale`).
  *
  * target (B,3,H,W); src_host[f] device pointers to (B,3,H,W), f < F <= 4;
- * T_host[f] device pointers to (B,4,4); disp (B,1,H,W) full-res (post
- * F.interpolate); ident (B,F,H,W) identity reprojection losses WITHOUT noise
+ * T_host[f] device pointers to (B,4,4); disp (B,1,disp_h,disp_w): the network's
+ * disparity at its native scale -- the bilinear F.interpolate to (H,W) of
+ * trainer.py:481-482 is fused into the read (disp_h==H: direct); ident (B,F,H,W) identity reprojection losses WITHOUT noise
  * (dmh_reproj_loss_fwd of the un-warped sources; scale independent) or NULL when
  * automasking is disabled; noise (B,Fi,H,W) tie-break noise already scaled
  * (nullable == zeros), Fi = avg_reprojection ? 1 : F.
  * flags: DMH_PHOTO_*.
  * Outputs:
  *   loss_partial : dmh_photo_blocks(B,H,W) floats, per-CTA sums of to_optimise
- *   grad_disp    : (B,1,H,W) = grad_scale * d(sum to_optimise)/d(disp)
+ *   grad_disp    : (B,1,H,W) = grad_scale * d(sum to_optimise)/d(up-sampled disp); push it
+ *                  through dmh_upsample_bilinear_bwd / dmh_disp_grad to reach (disp_h,disp_w)
  *   grad_P_partial (nullable): (F, B, tiles, 12) per-CTA partial sums of
  *                  grad_scale * d(sum)/d((K@T_f)[:3,:])
  *   sel (nullable): (B,H,W) uint8 argmin index over [ident..., reproj...]
@@ -149,10 +151,34 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
 #define DMH_PHOTO_MAX_FRAMES 4
 int dmh_photo_tiles(int H, int W);           /* CTAs per batch item */
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
-                    const float* disp, const float* K, const float* inv_K, const float* ident, const float* noise,
-                    int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
+                    const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K, const float* ident,
+                    const float* noise, int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
                     float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
                     float* const* warped_host, dmh_stream_t stream);
+
+/* -- fused multi-scale objective glue (M2/trainer.py:589-674) -------------------
+ * dmh_smooth_fused: A16 forward + gradient w.r.t. the mean-normalised disparity in
+ *   one pass: gN (B,1,h,w) = d(smooth loss)/d(norm disp); ws (workspace of
+ *   dmh_smooth_fused_workspace_floats floats) receives the per-block partial sums.
+ * dmh_objective_finish: ONE launch for all S scales: img_scalars (S,B,2) = per image
+ *   {1/(mean+1e-7), correction term of the normalisation backward}; losses (S+1) =
+ *   per-scale losses [photo_sum/photo_den + smooth_weight*smooth] and their mean.
+ *   *_host arrays are host arrays of length S (device pointers / ints / floats).
+ * dmh_disp_grad: backward, one launch per scale:
+ *   grad_disp (B,1,h,w) = u * [ interpolate^T(G_full (B,1,H,W)) + smooth_weight *
+ *   (gN*inv_mean - corr) ],  u = *g_total * inv_S + *g_scale (device scalars, either
+ *   nullable); gN nullable (no smoothness term); img_scalars = the (B,2) slice of
+ *   this scale.                                                                   */
+long long dmh_smooth_fused_workspace_floats(int B, int h, int w);
+int dmh_smooth_fused(const float* disp, const float* img, int B, int C, int h, int w, float* ws, float* gN,
+                     dmh_stream_t stream);
+int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const int* h_host, const int* w_host,
+                         const float* const* photo_part_host, const int* photo_n_host,
+                         const float* smooth_weight_host, double photo_den, float* img_scalars, float* losses,
+                         dmh_stream_t stream);
+int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars, float smooth_weight,
+                  const float* g_total, const float* g_scale, float inv_S, int B, int h, int w, int H, int W,
+                  float* grad_disp, dmh_stream_t stream);
 
 /* ======================= stage 1: physical patch attack ======================= */
 
