@@ -47,6 +47,7 @@ SIGNATURES = {
     "dmh_warp_fwd": (_i, [_f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_warp_bwd_blocks": (_i, [_i, _i]),
     "dmh_warp_bwd": (_i, [_f, _f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
+    "dmh_identity_loss": (_i, [_f, C.POINTER(C.c_void_p), _i, _i, _i, _i, _i, _f, _st]),
     "dmh_photo_tiles": (_i, [_i, _i]),
     "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                              _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),
@@ -54,7 +55,8 @@ SIGNATURES = {
     "dmh_smooth_fused": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_objective_finish": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_double, _f, _f,
-                                  _st]),
+                                  _f, _st]),
+    "dmh_objective_finish_workspace_bytes": (_ll, [_i, _i]),
     "dmh_disp_grad": (_i, [_f, _f, _f, _fl, _f, _f, _fl, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_perspective_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_perspective_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),

@@ -24,6 +24,8 @@ namespace {
 
 #define SF_NB1 64
 #define SF_THREADS 256
+// blocks of sf_main_kernel per image (32 x 8 pixel CTAs)
+#define SF_BLOCKS(h, w) ((((w) + 31) / 32) * (((h) + 7) / 8))
 
 __global__ void sf_mean_kernel(const float* __restrict__ disp, int hw, float* __restrict__ part) {
     __shared__ float red[32];
@@ -51,55 +53,80 @@ __device__ __forceinline__ float edge_w(const float* __restrict__ im, int C, siz
 }
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
+// One thread per pixel.  Every edge weight exp(-mean_c|dI|) is evaluated once by the pixel on its left / top
+// ("owner") and handed to the right / bottom neighbour through shared memory (one row of CTA-width halo is
+// recomputed).  CTA = 32 x 8 pixels.
+#define SF_BW 32
+#define SF_BH 8
 __global__ void __launch_bounds__(SF_THREADS)
 sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, int C, int h, int w,
                const float* __restrict__ mean_part, float inv_nx, float inv_ny, float* __restrict__ gN,
                float* __restrict__ part) {
     __shared__ float red[32];
     __shared__ float s_m;
-    const int b = blockIdx.y;
+    __shared__ float s_gx[SF_BH][SF_BW + 1];      // signed, weighted x-edge term owned by (y, x): sgn(diff)*e
+    __shared__ float s_gy[SF_BH + 1][SF_BW];      // same for the y-edge owned by (y, x)
+    const int b = blockIdx.z;
     const int hw = h * w;
+    const int tx_ = threadIdx.x & (SF_BW - 1), ty_ = threadIdx.x / SF_BW;
     if (threadIdx.x < 32) {
         const float m0 = mean_eps_warp(mean_part, b, hw);
-        if (threadIdx.x == 0) s_m = m0;
+        if (threadIdx.x == 0) s_m = 1.0f / m0;
     }
     __syncthreads();
-    const float m = s_m;
+    const float inv_m = s_m;
     const float* d = disp + (size_t)b * hw;
     const float* im = img + (size_t)b * C * hw;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    float tx = 0.f, ty = 0.f, g = 0.f, dv = 0.f;
-    if (n < hw) {
-        const int x = n % w, y = n / w;
+    const int x = blockIdx.x * SF_BW + tx_, y = blockIdx.y * SF_BH + ty_;
+    const bool in = x < w && y < h;
+    const int n = y * w + x;
+    float tx = 0.f, ty = 0.f, gxo = 0.f, gyo = 0.f, dv = 0.f;
+    if (in) {
         dv = d[n];
-        const float dn = div_rn(dv, m);
+        const float dn = dv * inv_m;
         if (x < w - 1) {
-            const float diff = dn - div_rn(d[n + 1], m);
+            const float diff = dn - d[n + 1] * inv_m;
             const float e = edge_w(im, C, hw, n, n + 1);
             tx = fabsf(diff) * e;
-            g += sgn(diff) * e * inv_nx;
-        }
-        if (x > 0) {
-            const float diff = div_rn(d[n - 1], m) - dn;
-            g -= sgn(diff) * edge_w(im, C, hw, n - 1, n) * inv_nx;
+            gxo = sgn(diff) * e;
         }
         if (y < h - 1) {
-            const float diff = dn - div_rn(d[n + w], m);
+            const float diff = dn - d[n + w] * inv_m;
             const float e = edge_w(im, C, hw, n, n + w);
             ty = fabsf(diff) * e;
-            g += sgn(diff) * e * inv_ny;
+            gyo = sgn(diff) * e;
         }
-        if (y > 0) {
-            const float diff = div_rn(d[n - w], m) - dn;
-            g -= sgn(diff) * edge_w(im, C, hw, n - w, n) * inv_ny;
+    }
+    s_gx[ty_][tx_ + 1] = gxo;
+    s_gy[ty_ + 1][tx_] = gyo;
+    // halo: the x-edge owned by the pixel left of the tile, the y-edge owned by the pixel above it
+    if (tx_ == 0) {
+        float v = 0.f;
+        if (in && x > 0) {
+            const float diff = d[n - 1] * inv_m - dv * inv_m;
+            v = sgn(diff) * edge_w(im, C, hw, n - 1, n);
         }
+        s_gx[ty_][0] = v;
+    }
+    if (ty_ == 0) {
+        float v = 0.f;
+        if (in && y > 0) {
+            const float diff = d[n - w] * inv_m - dv * inv_m;
+            v = sgn(diff) * edge_w(im, C, hw, n - w, n);
+        }
+        s_gy[0][tx_] = v;
+    }
+    __syncthreads();
+    float g = 0.f;
+    if (in) {
+        g = (gxo - s_gx[ty_][tx_]) * inv_nx + (gyo - s_gy[ty_][tx_]) * inv_ny;
         gN[(size_t)b * hw + n] = g;
     }
     const float sx = block_sum(tx, red);
     const float sy = block_sum(ty, red);
     const float sg = block_sum(g * dv, red);
     if (threadIdx.x == 0) {
-        float* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 3;
+        float* o = part + ((size_t)b * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 3;
         o[0] = sx; o[1] = sy; o[2] = sg;
     }
 }
@@ -115,6 +142,8 @@ struct FinishParams {
     double inv_photo_den;
     float* img_scalars;                   // (S,B,2): 1/(mean+eps), corr
     float* losses;                        // (S+1): per-scale, total
+    double* img_sums;                     // workspace (S,B,3): photo, smooth-x, smooth-y numerators
+    unsigned* ticket;                     // workspace: arrival counter (zeroed by the launcher)
 };
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
@@ -129,55 +158,67 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return t;
 }
 
-__global__ void __launch_bounds__(1024)
+// One CTA per (scale, image): reduces that image's partial sums in a fixed order; the CTA that
+// arrives last (atomic ticket) adds the S*B results up, again in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
 finish_kernel(const FinishParams p) {
     __shared__ double red[32];
+    __shared__ bool s_last;
     const int blk = blockIdx.x;
-    if (blk < p.S * p.B) {
-        const int s = blk / p.B, b = blk % p.B;
-        const int hw = p.h[s] * p.w[s];
-        const int nb = (hw + SF_THREADS - 1) / SF_THREADS;
-        const float* mean_part = p.smooth_ws[s];
-        const float* part = p.smooth_ws[s] + (size_t)p.B * SF_NB1;
-        double sg = 0.0;
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) sg += (double)part[((size_t)b * nb + i) * 3 + 2];
-        sg = block_sum_d(sg, red);
-        float m = 0.f;
-        if (threadIdx.x < 32) m = mean_eps_warp(mean_part, b, hw);
-        if (threadIdx.x == 0) {
-            const float inv_m = 1.0f / m;
-            p.img_scalars[((size_t)s * p.B + b) * 2 + 0] = inv_m;
-            p.img_scalars[((size_t)s * p.B + b) * 2 + 1] = (float)(sg / (double)hw) * inv_m * inv_m;
-        }
-        return;
+    const int s = blk / p.B, b = blk % p.B;
+    const int hw = p.h[s] * p.w[s];
+    const int nb = SF_BLOCKS(p.h[s], p.w[s]);
+    const float* mean_part = p.smooth_ws[s];
+    const float* part = p.smooth_ws[s] + (size_t)p.B * SF_NB1 + (size_t)b * nb * 3;
+    double sx = 0.0, sy = 0.0, sg = 0.0, ph = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        sx += (double)part[(size_t)i * 3 + 0];
+        sy += (double)part[(size_t)i * 3 + 1];
+        sg += (double)part[(size_t)i * 3 + 2];
     }
-    // last block: the scalar losses
+    // this CTA's share of the photo partial sums (any fixed partition is fine)
+    const long long n = p.photo_n[s];
+    const long long lo = n * b / p.B, hi = n * (b + 1) / p.B;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) ph += (double)p.photo_part[s][i];
+    sx = block_sum_d(sx, red);
+    sy = block_sum_d(sy, red);
+    sg = block_sum_d(sg, red);
+    ph = block_sum_d(ph, red);
+    float m = 0.f;
+    if (threadIdx.x < 32) m = mean_eps_warp(mean_part, b, hw);
+    if (threadIdx.x == 0) {
+        const float inv_m = 1.0f / m;
+        p.img_scalars[((size_t)s * p.B + b) * 2 + 0] = inv_m;
+        p.img_scalars[((size_t)s * p.B + b) * 2 + 1] = (float)(sg / (double)hw) * inv_m * inv_m;
+        double* o = p.img_sums + ((size_t)s * p.B + b) * 3;
+        o[0] = ph; o[1] = sx; o[2] = sy;
+        __threadfence();
+        s_last = atomicAdd(p.ticket, 1u) == (unsigned)(p.S * p.B - 1);
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
     double total = 0.0;
-    for (int s = 0; s < p.S; ++s) {
-        const int hw = p.h[s] * p.w[s];
-        const int nb = (hw + SF_THREADS - 1) / SF_THREADS;
-        const float* part = p.smooth_ws[s] + (size_t)p.B * SF_NB1;
-        double ph = 0.0, sx = 0.0, sy = 0.0;
-        for (int i = threadIdx.x; i < p.photo_n[s]; i += blockDim.x) ph += (double)p.photo_part[s][i];
-        for (int i = threadIdx.x; i < p.B * nb; i += blockDim.x) {
-            sx += (double)part[(size_t)i * 3 + 0];
-            sy += (double)part[(size_t)i * 3 + 1];
+    for (int ss = 0; ss < p.S; ++ss) {
+        double a = 0.0, bx = 0.0, by = 0.0;
+        for (int bb = 0; bb < p.B; ++bb) {
+            const volatile double* o = p.img_sums + ((size_t)ss * p.B + bb) * 3;
+            a += o[0]; bx += o[1]; by += o[2];
         }
-        ph = block_sum_d(ph, red);
-        sx = block_sum_d(sx, red);
-        sy = block_sum_d(sy, red);
-        if (threadIdx.x == 0) {
-            const double inv_nx = 1.0 / ((double)p.B * p.h[s] * (p.w[s] - 1));
-            const double inv_ny = 1.0 / ((double)p.B * (p.h[s] - 1) * p.w[s]);
-            const double loss = ph * p.inv_photo_den + (double)p.smooth_weight[s] * (sx * inv_nx + sy * inv_ny);
-            p.losses[s] = (float)loss;
-            total += loss;
-        }
+        const double inv_nx = 1.0 / ((double)p.B * p.h[ss] * (p.w[ss] - 1));
+        const double inv_ny = 1.0 / ((double)p.B * (p.h[ss] - 1) * p.w[ss]);
+        const double loss = a * p.inv_photo_den + (double)p.smooth_weight[ss] * (bx * inv_nx + by * inv_ny);
+        p.losses[ss] = (float)loss;
+        total += loss;
     }
-    if (threadIdx.x == 0) p.losses[p.S] = (float)(total / (double)p.S);
+    p.losses[p.S] = (float)(total / (double)p.S);
+    *p.ticket = 0u;
 }
 
-// one thread per low-res pixel
+// one thread per low-res pixel.  For an integer up-scale factor r the full-res pixels that read low-res
+// pixel y are exactly Y in [r*y - r/2, r*y + 3r/2 - 1] (2r of them): their weights are tabulated once per
+// thread, the inner loop is one load + one FMA.  Other factors use the generic conservative window.
+template <int R>
 __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
                                  const float* __restrict__ img_scalars, float smooth_weight,
                                  const float* __restrict__ g_total, const float* __restrict__ g_scale, float inv_S,
@@ -189,8 +230,39 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
     const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
     const float* g = G_full + (size_t)b * H * W;
     float acc;
-    if (h == H && w == W) {
+    if (R == 1) {
         acc = __ldg(g + (size_t)y * W + x);
+    } else if (R > 1) {
+        constexpr int RW = R > 0 ? 2 * R : 1;
+        float wy[RW], wx[RW];
+        const int Y0 = R * y - R / 2, X0 = R * x - R / 2;
+#pragma unroll
+        for (int j = 0; j < 2 * R; ++j) {
+            const int Y = Y0 + j, X = X0 + j;
+            wy[j] = 0.f; wx[j] = 0.f;
+            if (Y >= 0 && Y < H) { const UpTap t = up_tap(Y, sh, h); wy[j] = (t.i0 == y ? t.l0 : 0.f) + (t.i1 == y ? t.l1 : 0.f); }
+            if (X >= 0 && X < W) { const UpTap t = up_tap(X, sw, w); wx[j] = (t.i0 == x ? t.l0 : 0.f) + (t.i1 == x ? t.l1 : 0.f); }
+        }
+        // image borders: rows/cols clamped by the source index (src < 0 -> 0) reach beyond the 2r window
+        acc = 0.0f;
+        const int Ya = (y == 0) ? 0 : Y0, Yb = (y == h - 1) ? H - 1 : Y0 + 2 * R - 1;
+        const int Xa = (x == 0) ? 0 : X0, Xb = (x == w - 1) ? W - 1 : X0 + 2 * R - 1;
+        for (int Y = max(Ya, 0); Y <= min(Yb, H - 1); ++Y) {
+            const int jy = Y - Y0;
+            float wyv;
+            if (jy >= 0 && jy < 2 * R) wyv = wy[jy];
+            else { const UpTap t = up_tap(Y, sh, h); wyv = (t.i0 == y ? t.l0 : 0.f) + (t.i1 == y ? t.l1 : 0.f); }
+            if (wyv == 0.f) continue;
+            float row = 0.0f;
+            for (int X = max(Xa, 0); X <= min(Xb, W - 1); ++X) {
+                const int jx = X - X0;
+                float wxv;
+                if (jx >= 0 && jx < 2 * R) wxv = wx[jx];
+                else { const UpTap t = up_tap(X, sw, w); wxv = (t.i0 == x ? t.l0 : 0.f) + (t.i1 == x ? t.l1 : 0.f); }
+                row = fmaf(wxv, __ldg(g + (size_t)Y * W + X), row);
+            }
+            acc = fmaf(wyv, row, acc);
+        }
     } else {
         const float rh = 1.0f / sh, rw = 1.0f / sw;
         const int Y0 = max(0, (int)floorf(((float)y - 0.5f) * rh - 0.5f) - 1);
@@ -223,31 +295,33 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
 extern "C" {
 
 long long dmh_smooth_fused_workspace_floats(int B, int h, int w) {
-    return (long long)B * SF_NB1 + 3LL * B * ceil_div((long long)h * w, SF_THREADS);
+    return (long long)B * SF_NB1 + 3LL * B * SF_BLOCKS(h, w);
 }
 
 int dmh_smooth_fused(const float* disp, const float* img, int B, int C, int h, int w, float* ws, float* gN,
                      dmh_stream_t stream) {
     DMH_REQUIRE(disp && img && ws && gN, "dmh_smooth_fused: null pointer");
     DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && h >= 2 && w >= 2, "dmh_smooth_fused: bad shape");
-    const int nb = ceil_div((long long)h * w, SF_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
     DMH_LAUNCH(sf_mean_kernel, dim3(SF_NB1, B), 256, 0, st)(disp, h * w, ws);
     const float inv_nx = (float)(1.0 / ((double)B * h * (w - 1))), inv_ny = (float)(1.0 / ((double)B * (h - 1) * w));
-    DMH_LAUNCH(sf_main_kernel, dim3(nb, B), SF_THREADS, 0, st)(disp, img, C, h, w, ws, inv_nx, inv_ny, gN,
-                                                             ws + (size_t)B * SF_NB1);
+    DMH_LAUNCH(sf_main_kernel, dim3(ceil_div(w, SF_BW), ceil_div(h, SF_BH), B), SF_THREADS, 0, st)(
+        disp, img, C, h, w, ws, inv_nx, inv_ny, gN, ws + (size_t)B * SF_NB1);
     DMH_CHECK_LAUNCH("dmh_smooth_fused");
     return DMH_OK;
 }
 
+long long dmh_objective_finish_workspace_bytes(int S, int B) { return 16 + 24LL * S * B; }
+
 int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const int* h_host, const int* w_host,
                          const float* const* photo_part_host, const int* photo_n_host,
-                         const float* smooth_weight_host, double photo_den, float* img_scalars, float* losses,
-                         dmh_stream_t stream) {
+                         const float* smooth_weight_host, double photo_den, void* workspace, float* img_scalars,
+                         float* losses, dmh_stream_t stream) {
     DMH_REQUIRE(S >= 1 && S <= FIN_MAXS && B > 0, "dmh_objective_finish: S=%d outside [1,%d] or B <= 0", S, FIN_MAXS);
     DMH_REQUIRE(smooth_ws_host && h_host && w_host && photo_part_host && photo_n_host && smooth_weight_host &&
-                    img_scalars && losses && photo_den > 0.0,
+                    workspace && img_scalars && losses && photo_den > 0.0,
                 "dmh_objective_finish: null pointer");
+    DMH_REQUIRE(((uintptr_t)workspace & 15) == 0, "dmh_objective_finish: workspace must be 16-byte aligned");
     FinishParams p;
     for (int s = 0; s < S; ++s) {
         DMH_REQUIRE(smooth_ws_host[s] && photo_part_host[s], "dmh_objective_finish: null buffer for scale %d", s);
@@ -259,7 +333,11 @@ int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const
         p.smooth_weight[s] = smooth_weight_host[s];
     }
     p.S = S; p.B = B; p.inv_photo_den = 1.0 / photo_den; p.img_scalars = img_scalars; p.losses = losses;
-    DMH_LAUNCH(finish_kernel, S * B + 1, 1024, 0, (cudaStream_t)stream)(p);
+    p.ticket = reinterpret_cast<unsigned*>(workspace);
+    p.img_sums = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 16, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dmh_objective_finish: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+    DMH_LAUNCH(finish_kernel, S * B, 256, 0, (cudaStream_t)stream)(p);
     DMH_CHECK_LAUNCH("dmh_objective_finish");
     return DMH_OK;
 }
@@ -271,9 +349,18 @@ int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars
     DMH_REQUIRE(!gN || img_scalars, "dmh_disp_grad: gN given without img_scalars");
     DMH_REQUIRE(B > 0 && B <= 65535 && h >= 1 && w >= 1 && H >= h && W >= w, "dmh_disp_grad: bad shape");
     dim3 block(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8), B);
-    DMH_LAUNCH(disp_grad_kernel, grid, block, 0, (cudaStream_t)stream)(G_full, gN, img_scalars, smooth_weight, g_total, g_scale,
-                                                                    inv_S, h, w, H, W, (float)h / (float)H,
-                                                                    (float)w / (float)W, grad_disp);
+    const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+    cudaStream_t st = (cudaStream_t)stream;
+    int R = 0;                                   // integer up-scale factor shared by both axes, else generic
+    if (H % h == 0 && W % w == 0 && H / h == W / w) R = H / h;
+#define DMH_DG(RR) DMH_LAUNCH(disp_grad_kernel<RR>, grid, block, 0, st)(G_full, gN, img_scalars, smooth_weight, g_total, \
+                                                                       g_scale, inv_S, h, w, H, W, sh, sw, grad_disp)
+    if (R == 1) DMH_DG(1);
+    else if (R == 2) DMH_DG(2);
+    else if (R == 4) DMH_DG(4);
+    else if (R == 8) DMH_DG(8);
+    else DMH_DG(0);
+#undef DMH_DG
     DMH_CHECK_LAUNCH("dmh_disp_grad");
     return DMH_OK;
 }

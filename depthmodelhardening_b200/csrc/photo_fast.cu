@@ -313,6 +313,85 @@ photo_fast_kernel(const FastParams p) {
     if (tid == 0) p.loss_partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
 }
 
+
+// ---------------------------------------------------------------------------
+// Identity reprojection loss (M2/trainer.py:608-615): compute_reprojection_loss of the UN-warped
+// source against the target.  Scale independent -> computed once per batch (the reference recomputes it
+// for every scale).  32x32 tile, 1-px reflect halo, sliding-window SSIM down each column.
+#define ID_R 34
+#define ID_N (ID_R * ID_R)
+struct IdentParams {
+    const float* target;
+    const float* src[DMH_PHOTO_MAX_FRAMES];
+    float* out;                 // (B,F,H,W)
+    int B, F, H, W, no_ssim;
+};
+
+__global__ void __launch_bounds__(256)
+ident_fast_kernel(const IdentParams p) {
+    __shared__ float xs[3][ID_N];
+    __shared__ float ys[3][ID_N];
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W;
+    const int b = blockIdx.z / p.F, f = blockIdx.z % p.F;
+    const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
+    const size_t N = (size_t)H * W;
+    const float* sp = p.src[f] + (size_t)b * 3 * N;
+    const float* tp = p.target + (size_t)b * 3 * N;
+    for (int i = tid; i < ID_N; i += 256) {
+        const int r = i / ID_R, c = i - r * ID_R;
+        const size_t o = (size_t)ext_to_img(y0 - 1 + r, H) * W + ext_to_img(x0 - 1 + c, W);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            xs[ch][i] = __ldg(sp + ch * N + o);
+            ys[ch][i] = __ldg(tp + ch * N + o);
+        }
+    }
+    __syncthreads();
+    const int c = tid & 31, strip = tid >> 5;           // 8 strips of 4 rows
+    const int px = x0 + c;
+    Row5 hist[3][2];
+    float cen_x[3], cen_y[3];
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+        const int r2 = 4 * strip + rr;                   // halo-tile row
+        Row5 cur[3];
+        float mid_x[3], mid_y[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* xr = &xs[ch][r2 * ID_R + c];
+            const float* yr = &ys[ch][r2 * ID_R + c];
+            cur[ch] = row5(xr[0], xr[1], xr[2], yr[0], yr[1], yr[2]);
+            mid_x[ch] = xr[1]; mid_y[ch] = yr[1];
+        }
+        if (rr >= 2) {
+            const int py = y0 + 4 * strip + rr - 2;
+            if (py < H && px < W) {
+                float l1 = 0.f, ss = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    l1 += fabsf(cen_y[ch] - cen_x[ch]);
+                    if (!p.no_ssim) {
+                        const SsimStats st = ssim_stats_rows(hist[ch][0], hist[ch][1], cur[ch]);
+                        float pass;
+                        SsimCoef k;
+                        ss += ssim_value_coef(st, pass, k);
+                    }
+                }
+                l1 *= (1.0f / 3.0f);
+                const float rp = p.no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                p.out[((size_t)b * p.F + f) * N + (size_t)py * W + px] = rp;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            hist[ch][0] = hist[ch][1];
+            hist[ch][1] = cur[ch];
+            cen_x[ch] = mid_x[ch]; cen_y[ch] = mid_y[ch];
+        }
+    }
+}
+
 size_t fast_smem_bytes() { return sizeof(float) * (6 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
 
 }  // namespace
@@ -349,6 +428,18 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     }
     dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B);
     DMH_LAUNCH(photo_fast_kernel, grid, FT_THREADS, smem, st)(p);
+    return DMH_OK;
+}
+
+
+int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
+                      float* out, cudaStream_t st) {
+    IdentParams p;
+    p.target = target;
+    for (int f = 0; f < DMH_PHOTO_MAX_FRAMES; ++f) p.src[f] = f < F ? src_host[f] : nullptr;
+    p.out = out; p.B = B; p.F = F; p.H = H; p.W = W; p.no_ssim = no_ssim;
+    dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B * F);
+    DMH_LAUNCH(ident_fast_kernel, grid, 256, 0, st)(p);
     return DMH_OK;
 }
 

@@ -421,9 +421,23 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
                       int disp_w, const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
                       uint8_t* sel, float* warped, cudaStream_t st);
+int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
+                      float* out, cudaStream_t st);
 }  // namespace dmh
 
 extern "C" {
+
+int dmh_identity_loss(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
+                      float* ident, dmh_stream_t stream) {
+    DMH_REQUIRE(target && src_host && ident, "dmh_identity_loss: null pointer");
+    DMH_REQUIRE(F >= 1 && F <= PH_MAXF, "dmh_identity_loss: F=%d outside [1,%d]", F, PH_MAXF);
+    DMH_REQUIRE(B > 0 && (long long)B * F <= 65535 && H >= 2 && W >= 2, "dmh_identity_loss: bad shape");
+    for (int f = 0; f < F; ++f) DMH_REQUIRE(src_host[f], "dmh_identity_loss: null src for frame %d", f);
+    const int rc = launch_ident_fast(target, src_host, F, B, H, W, no_ssim, ident, (cudaStream_t)stream);
+    if (rc != DMH_OK) return rc;
+    DMH_CHECK_LAUNCH("dmh_identity_loss");
+    return DMH_OK;
+}
 
 int dmh_photo_tiles(int H, int W) { return ceil_div(W, PH_TW) * ceil_div(H, PH_TH); }
 

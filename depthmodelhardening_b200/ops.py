@@ -427,15 +427,8 @@ class _Objective(torch.autograd.Function):
         ident = None
         if automask:
             ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32)
-            if n_src == 1:
-                check(lib.dmh_reproj_loss_fwd(ptr(srcs[0]), ptr(target), B, 3, H, W, no_ssim, ptr(ident), stream()),
-                      "ident")
-            else:
-                tmp = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
-                for f in range(n_src):
-                    check(lib.dmh_reproj_loss_fwd(ptr(srcs[f]), ptr(target), B, 3, H, W, no_ssim, ptr(tmp), stream()),
-                          "ident")
-                    ident[:, f:f + 1].copy_(tmp)
+            check(lib.dmh_identity_loss(ptr(target), ptr_array(srcs), n_src, B, H, W, no_ssim, ptr(ident), stream()),
+                  "identity_loss")
         # disp grads are needed iff any disparity requires grad; pose grads iff any T does
         base = 3 + S + n_src
         need_T = any(ctx.needs_input_grad[base + i] for i in range(n_src))
@@ -464,8 +457,9 @@ class _Objective(torch.autograd.Function):
         wsz = (_C.c_int * S)(*[d.shape[3] for d in disps])
         pn = (_C.c_int * S)(*[p_.numel() for p_ in parts])
         sw = (_C.c_float * S)(*[float(x) for x in smooth_w])
+        fin_ws = torch.empty(lib.dmh_objective_finish_workspace_bytes(S, B), device=dev, dtype=torch.uint8)
         check(lib.dmh_objective_finish(S, B, ptr_array(wss), hs, wsz, ptr_array(parts), pn, sw, float(B * H * W),
-                                       ptr(img_scalars), ptr(losses), stream()), "objective_finish")
+                                       ptr(fin_ws), ptr(img_scalars), ptr(losses), stream()), "objective_finish")
         ctx.cfg = (S, n_src, B, H, W, tuple(float(x) for x in smooth_w), need_T, [tuple(d.shape) for d in disps],
                    has_noise)
         ctx.save_for_backward(img_scalars, k, *G, *gN, *[t for t in Ts], *[g for g in gPs if g is not None])

@@ -144,6 +144,10 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
  *                  grad_scale * d(sum)/d((K@T_f)[:3,:])
  *   sel (nullable): (B,H,W) uint8 argmin index over [ident..., reproj...]
  *   warped_host (nullable): F device pointers (nullable each) to (B,3,H,W)      */
+/* identity reprojection losses of the automask (M2/trainer.py:608-615): ident (B,F,H,W),
+ * ident[:,f] = compute_reprojection_loss(src_f, target); scale independent, computed once. */
+int dmh_identity_loss(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
+                      float* ident, dmh_stream_t stream);
 #define DMH_PHOTO_NO_SSIM 1
 #define DMH_PHOTO_AVG_REPROJECTION 2
 #define DMH_PHOTO_INPUT_IS_DEPTH 4
@@ -163,7 +167,8 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
  * dmh_objective_finish: ONE launch for all S scales: img_scalars (S,B,2) = per image
  *   {1/(mean+1e-7), correction term of the normalisation backward}; losses (S+1) =
  *   per-scale losses [photo_sum/photo_den + smooth_weight*smooth] and their mean.
- *   *_host arrays are host arrays of length S (device pointers / ints / floats).
+ *   *_host arrays are host arrays of length S (device pointers / ints / floats);
+ *   workspace: dmh_objective_finish_workspace_bytes(S,B) bytes, 16-byte aligned.
  * dmh_disp_grad: backward, one launch per scale:
  *   grad_disp (B,1,h,w) = u * [ interpolate^T(G_full (B,1,H,W)) + smooth_weight *
  *   (gN*inv_mean - corr) ],  u = *g_total * inv_S + *g_scale (device scalars, either
@@ -172,10 +177,11 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
 long long dmh_smooth_fused_workspace_floats(int B, int h, int w);
 int dmh_smooth_fused(const float* disp, const float* img, int B, int C, int h, int w, float* ws, float* gN,
                      dmh_stream_t stream);
+long long dmh_objective_finish_workspace_bytes(int S, int B);
 int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const int* h_host, const int* w_host,
                          const float* const* photo_part_host, const int* photo_n_host,
-                         const float* smooth_weight_host, double photo_den, float* img_scalars, float* losses,
-                         dmh_stream_t stream);
+                         const float* smooth_weight_host, double photo_den, void* workspace, float* img_scalars,
+                         float* losses, dmh_stream_t stream);
 int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars, float smooth_weight,
                   const float* g_total, const float* g_scale, float inv_S, int B, int h, int w, int H, int W,
                   float* grad_disp, dmh_stream_t stream);
