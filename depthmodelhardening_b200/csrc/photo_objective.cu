@@ -76,23 +76,19 @@ __device__ __forceinline__ Taps make_taps(const Bilinear& bl, int H, int W) {
     return t;
 }
 
-// 3x3 window sums for one channel plane in shared memory (row-major, then /9
-// inside ssim_stats) around R2 position (r+1, c+1)
+// 3x3 window statistics for one channel plane in shared memory around R2 position (r+1, c+1).
+// Same arithmetic as the single-source fast kernel and the identity-loss kernel (row sums of 3, then 3 rows,
+// mean = sum * (1/9)) so that the automask compares like with like.
 __device__ __forceinline__ SsimStats window_stats(const float* __restrict__ xs, const float* __restrict__ ys, int r,
                                                   int c) {
-    float s1 = 0.f, s2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    Row5 rows[3];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const float a = xs[(r + dy) * PH_R2W + c + dx], d = ys[(r + dy) * PH_R2W + c + dx];
-            s1 = add_rn(s1, a);
-            s2 = add_rn(s2, d);
-            s11 = add_rn(s11, mul_rn(a, a));
-            s22 = add_rn(s22, mul_rn(d, d));
-            s12 = add_rn(s12, mul_rn(a, d));
-        }
-    return ssim_stats(s1, s2, s11, s22, s12);
+    for (int dy = 0; dy < 3; ++dy) {
+        const float* x = xs + (r + dy) * PH_R2W + c;
+        const float* y = ys + (r + dy) * PH_R2W + c;
+        rows[dy] = row5(x[0], x[1], x[2], y[0], y[1], y[2]);
+    }
+    return ssim_stats_rows(rows[0], rows[1], rows[2]);
 }
 
 template <int F>
@@ -205,14 +201,15 @@ photo_scale_kernel(const PhotoParams p) {
                 for (int ch = 0; ch < 3; ++ch) {
                     const float* xs = pred + (f * 3 + ch) * PH_R2;
                     const float* ys = tgt + ch * PH_R2;
-                    l1 = add_rn(l1, fabsf(sub_rn(ys[ci], xs[ci])));
+                    l1 += fabsf(ys[ci] - xs[ci]);
                     if (!no_ssim) {
                         float pass;
-                        ss = add_rn(ss, ssim_value(window_stats(xs, ys, r, c), pass));
+                        SsimCoef kk;
+                        ss += ssim_value_coef(window_stats(xs, ys, r, c), pass, kk);
                     }
                 }
-                l1 = div_rn(l1, 3.0f);
-                rp[f] = no_ssim ? l1 : add_rn(mul_rn(0.85f, div_rn(ss, 3.0f)), mul_rn(0.15f, l1));
+                l1 *= (1.0f / 3.0f);
+                rp[f] = no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
                 rp_avg = add_rn(rp_avg, rp[f]);
             }
             rp_avg = div_rn(rp_avg, (float)F);
@@ -275,12 +272,10 @@ photo_scale_kernel(const PhotoParams p) {
                 if (gate != 0.f && !no_ssim) {
                     const SsimStats st = window_stats(pred + (f * 3 + ch) * PH_R2, tgt + ch * PH_R2, r, c);
                     float pass;
-                    ssim_value(st, pass);
+                    SsimCoef k;
+                    ssim_value_coef(st, pass, k);
                     const float g = gate * w_ssim * pass;
-                    if (g != 0.f) {
-                        const SsimCoef k = ssim_coef(st);
-                        a = g * k.ax; bq = g * k.b; cq = g * k.c;
-                    }
+                    a = g * k.ax; bq = g * k.b; cq = g * k.c;
                 }
                 ka[ch * PH_R1 + i] = a; kb[ch * PH_R1 + i] = bq; kc[ch * PH_R1 + i] = cq;
             }
