@@ -41,7 +41,7 @@ UNIT = "Mpix/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
@@ -325,40 +325,83 @@ def main():
     else:
         step_bytes_total = step_bytes
 
-    # end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
+    # end to end: pinned host inputs -> H2D -> step -> D2H loss, EVERY step, through the public Python API.
+    # Double-buffered: a copy stream uploads batch i+1 while the compute stream works on batch i (every byte is
+    # still copied inside the timed region; the pipeline only overlaps the copy with the previous step).
     e2e = None
     if not args.no_e2e:
-        pin = lambda t: t.pin_memory()
-        host2 = {"color": {k: pin(v) for k, v in pb_host.color.items()},
-                 "disp": {k: pin(v) for k, v in pb_host.disp.items()},
-                 "K": pin(pb_host.K), "inv_K": pin(pb_host.inv_K), "T": {k: pin(v) for k, v in pb_host.T.items()}}
-        host_scenes = pin(pt_host.scenes) if s1 is not None else None
-        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-        h2d = sum(v.numel() * 4 for v in host2["color"].values()) + sum(v.numel() * 4 for v in host2["disp"].values()) \
-            + 2 * host2["K"].numel() * 4 + sum(v.numel() * 4 for v in host2["T"].values())
-        if s1 is not None:
-            h2d += host_scenes.numel() * 4
         from depthmodelhardening_b200 import objective
+        pin = lambda t: t.pin_memory()
+        host = {("color",) + k: pin(v) for k, v in pb_host.color.items()}
+        host.update({("disp", k): pin(v) for k, v in pb_host.disp.items()})
+        host[("K",)] = pin(pb_host.K)
+        host[("inv_K",)] = pin(pb_host.inv_K)
+        host.update({("T", k): pin(v) for k, v in pb_host.T.items()})
+        if s1 is not None:
+            host[("scenes",)] = pin(pt_host.scenes)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        slots = [{k: torch.empty_like(v, device=device) for k, v in host.items()} for _ in range(2)]
+        for sl in slots:
+            for k in sl:
+                if k[0] == "disp":
+                    sl[k].requires_grad_(True)
+        copy_stream = torch.cuda.Stream(device=device)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
-            nb = lambda t: t.to(device, non_blocking=True)
-            color = {k: nb(v) for k, v in host2["color"].items()}
-            disps = {k: nb(v).requires_grad_(True) for k, v in host2["disp"].items()}
-            K, iK = nb(host2["K"]), nb(host2["inv_K"])
-            T = {k: nb(v) for k, v in host2["T"].items()}
+        def upload(slot):
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(done[slot])          # the previous user of this slot has finished
+                for k, v in host.items():
+                    slots[slot][k].copy_(v, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def compute(slot):
+            sl = slots[slot]
+            torch.cuda.current_stream().wait_event(ready[slot])
+            color = {k[1:]: v for k, v in sl.items() if k[0] == "color"}
+            disps = {k[1]: v for k, v in sl.items() if k[0] == "disp"}
+            T = {k[1]: v for k, v in sl.items() if k[0] == "T"}
+            for d in disps.values():
+                d.grad = None
             if s1 is not None:
-                s1.g.scenes = nb(host_scenes)
+                s1.g.scenes = sl[("scenes",)]
                 s1.step()
-            losses, _ = objective.photometric_losses(color, disps, K, iK, T, list(FRAME_IDS), list(SCALES), H, W,
-                                                     noise=None, noise_mode="device")
+            losses, _ = objective.photometric_losses(color, disps, sl[("K",)], sl[("inv_K",)], T, list(FRAME_IDS),
+                                                     list(SCALES), H, W, noise=None, noise_mode="device")
             losses["loss"].backward()
             loss_host.copy_(losses["loss"].detach(), non_blocking=True)
+            done[slot].record()
 
-        ms_e2e = timed_loop(e2e_step, max(3, args.steps // 2), 2, world)
+        def run_pipeline(n):
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload((i + 1) % 2)
+                compute(i % 2)
+
+        run_pipeline(3)                                       # warm-up
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        n_e2e = max(4, args.steps // 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        copy_stream.wait_event(e0)
+        run_pipeline(n_e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / n_e2e
+        if world > 1:
+            t = torch.tensor([ms_e2e], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms_e2e = float(t.item())
         e2e = {"value": world * B * H * W / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
-               "note": "pinned host batch dict (frames, pyramid, disparities, K, T, scenes) copied every step; "
-                       "tie-break noise drawn on the device"}
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": n_e2e,
+               "note": "public Python API; the batch dict (frames, pyramid, disparities, K, inv_K, T, scenes) is copied "
+                       "from pinned host memory every step on a copy stream, double-buffered against the previous "
+                       "step's compute; tie-break noise drawn on the device; loss read back every step"}
 
     line = {
         "metric": METRIC, "value": world * B * H * W / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,

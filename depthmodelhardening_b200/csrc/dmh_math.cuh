@@ -102,8 +102,9 @@ DMH_HD float normalise_coord(float num, float den_eps, int size) {
 
 // ATen grid_sampler_unnormalize (align_corners True / False)
 DMH_HD float unnormalise_coord(float g, int size, bool align_corners) {
-    if (align_corners) return mul_rn(div_rn(add_rn(g, 1.0f), 2.0f), (float)(size - 1));
-    return div_rn(sub_rn(mul_rn(add_rn(g, 1.0f), (float)size), 1.0f), 2.0f);
+    // "/ 2" is exact in binary floating point: x * 0.5f rounds identically and is one instruction
+    if (align_corners) return mul_rn(mul_rn(add_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    return mul_rn(sub_rn(mul_rn(add_rn(g, 1.0f), (float)size), 1.0f), 0.5f);
 }
 DMH_HD float unnormalise_mult(int size, bool align_corners) {
     return align_corners ? (float)(size - 1) / 2.0f : (float)size / 2.0f;
@@ -285,8 +286,16 @@ DMH_HD SsimStats ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) {
 }
 
 // value + coefficients sharing one reciprocal of d
+// reciprocal of the SSIM denominator d = B1*B2 >= C1*C2 > 0: MUFU.RCP (2 ulp) on the device -- the error it
+// adds to the SSIM value is ~1e-7, far below the 1e-5 tolerance; IEEE division on the host emulation
+#if defined(__CUDA_ARCH__)
+DMH_HD float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+DMH_HD float fast_rcp(float x) { return 1.0f / x; }
+#endif
+
 DMH_HD float ssim_value_coef(const SsimStats& s, float& pass, SsimCoef& k) {
-    const float r = 1.0f / s.d;
+    const float r = fast_rcp(s.d);
     const float nr = s.n * r;
     const float v = (1.0f - nr) * 0.5f;
     pass = (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f;
