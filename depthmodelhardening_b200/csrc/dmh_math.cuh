@@ -174,8 +174,10 @@ DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, in
     const float ux = unnormalise_coord(gx, W, true);
     const float uy = unnormalise_coord(gy, H, true);
     // NaN: ATen's forward clip is fmin/fmax, which maps NaN to 0
-    wc.ix = (ux == ux) ? safe_coord(clip_coord(ux, W, cgx)) : 0.0f;
-    wc.iy = (uy == uy) ? safe_coord(clip_coord(uy, H, cgy)) : 0.0f;
+    // (after the border clip the coordinate is in [0, size-1] -- +-inf included -- so ATen's
+    //  safe_downgrade_to_int_range is the identity here)
+    wc.ix = (ux == ux) ? clip_coord(ux, W, cgx) : 0.0f;
+    wc.iy = (uy == uy) ? clip_coord(uy, H, cgy) : 0.0f;
     wc.mx = cgx * unnormalise_mult(W, true);
     wc.my = cgy * unnormalise_mult(H, true);
     return wc;

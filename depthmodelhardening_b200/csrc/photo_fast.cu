@@ -121,12 +121,16 @@ photo_fast_kernel(const FastParams p) {
         const int i = (tid - 12) / 3, j = (tid - 12) % 3;
         cams[tid] = __ldg(p.inv_K + b * 16 + i * 4 + j);
     }
-    // ---- target tile, 2-px reflect halo
-    for (int i = tid; i < FT_N2; i += FT_THREADS) {
-        const int r = i / FT_R2, c = i - r * FT_R2;
-        const size_t o = (size_t)ext_to_img(y0 - 2 + r, H) * W + ext_to_img(x0 - 2 + c, W);
+    // ---- target tile, 2-px reflect halo: 36 columns x 7 row groups = 252 threads, column index maths once
+    if (tid < FT_R2 * 7) {
+        const int c = tid % FT_R2, rg = tid / FT_R2;
+        const int ix = ext_to_img(x0 - 2 + c, W);
+        const float* tp = p.target + (size_t)b * 3 * N + ix;
+        for (int r = rg; r < FT_R2; r += 7) {
+            const int o = ext_to_img(y0 - 2 + r, H) * W;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + i] = __ldg(p.target + ((size_t)b * 3 + ch) * N + o);
+            for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + r * FT_R2 + c] = __ldg(tp + ch * N + o);
+        }
     }
     __syncthreads();
     Camera cam;
