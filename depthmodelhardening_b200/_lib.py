@@ -60,8 +60,8 @@ SIGNATURES = {
     "dmh_disp_grad": (_i, [_f, _f, _f, _fl, _f, _f, _fl, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_perspective_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_perspective_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
-    "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
-    "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_pgd_linf_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _st]),
     "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),
     "dmh_l0_adam_step": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _fl, _i,

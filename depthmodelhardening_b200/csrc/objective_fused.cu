@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(SF_THREADS)
 sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, int C, int h, int w,
                const float* __restrict__ mean_part, float inv_nx, float inv_ny, float* __restrict__ gN,
                float* __restrict__ part) {
-    __shared__ float red[32];
     __shared__ float s_m;
     __shared__ float s_gx[SF_BH][SF_BW + 1];      // signed, weighted x-edge term owned by (y, x): sgn(diff)*e
     __shared__ float s_gy[SF_BH + 1][SF_BW];      // same for the y-edge owned by (y, x)
@@ -122,12 +121,18 @@ sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, in
         g = (gxo - s_gx[ty_][tx_]) * inv_nx + (gyo - s_gy[ty_][tx_]) * inv_ny;
         gN[(size_t)b * hw + n] = g;
     }
-    const float sx = block_sum(tx, red);
-    const float sy = block_sum(ty, red);
-    const float sg = block_sum(g * dv, red);
-    if (threadIdx.x == 0) {
-        float* o = part + ((size_t)b * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 3;
-        o[0] = sx; o[1] = sy; o[2] = sg;
+    // one combined reduction of the three partial sums (warp shuffles, then 3 x 8 values in shared memory)
+    __shared__ float s_red[3][SF_THREADS / 32];
+    const float r0 = warp_sum(tx), r1 = warp_sum(ty), r2 = warp_sum(g * dv);
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5] = r0; s_red[1][threadIdx.x >> 5] = r1; s_red[2][threadIdx.x >> 5] = r2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < SF_THREADS / 32; ++i) t += s_red[threadIdx.x][i];
+        part[((size_t)b * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
     }
 }
 
@@ -225,7 +230,8 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
                                  int h, int w, int H, int W, float sh, float sw, float* __restrict__ grad) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
+    const bool in = x < w && y < h;
+    if (R <= 1 && !in) return;                            // (R > 1: every thread helps to fill the weight tables)
     const int b = blockIdx.z;
     const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
     const float* g = G_full + (size_t)b * H * W;
@@ -233,33 +239,42 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
     if (R == 1) {
         acc = __ldg(g + (size_t)y * W + x);
     } else if (R > 1) {
+        // weights depend only on (y, offset) / (x, offset): tabulated once per CTA (32 x 8 low-res pixels)
         constexpr int RW = R > 0 ? 2 * R : 1;
-        float wy[RW], wx[RW];
-        const int Y0 = R * y - R / 2, X0 = R * x - R / 2;
-#pragma unroll
-        for (int j = 0; j < 2 * R; ++j) {
-            const int Y = Y0 + j, X = X0 + j;
-            wy[j] = 0.f; wx[j] = 0.f;
-            if (Y >= 0 && Y < H) { const UpTap t = up_tap(Y, sh, h); wy[j] = (t.i0 == y ? t.l0 : 0.f) + (t.i1 == y ? t.l1 : 0.f); }
-            if (X >= 0 && X < W) { const UpTap t = up_tap(X, sw, w); wx[j] = (t.i0 == x ? t.l0 : 0.f) + (t.i1 == x ? t.l1 : 0.f); }
+        __shared__ float s_wy[8][RW], s_wx[32][RW];
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        for (int i = t; i < 8 * RW + 32 * RW; i += 256) {
+            if (i < 8 * RW) {
+                const int ly = i / RW, j = i % RW;
+                const int yy = blockIdx.y * 8 + ly, Y = R * yy - R / 2 + j;
+                float wv = 0.f;
+                if (yy < h && Y >= 0 && Y < H) { const UpTap tp = up_tap(Y, sh, h); wv = (tp.i0 == yy ? tp.l0 : 0.f) + (tp.i1 == yy ? tp.l1 : 0.f); }
+                s_wy[ly][j] = wv;
+            } else {
+                const int k = i - 8 * RW;
+                const int lx = k / RW, j = k % RW;
+                const int xx = blockIdx.x * 32 + lx, X = R * xx - R / 2 + j;
+                float wv = 0.f;
+                if (xx < w && X >= 0 && X < W) { const UpTap tp = up_tap(X, sw, w); wv = (tp.i0 == xx ? tp.l0 : 0.f) + (tp.i1 == xx ? tp.l1 : 0.f); }
+                s_wx[lx][j] = wv;
+            }
         }
-        // image borders: rows/cols clamped by the source index (src < 0 -> 0) reach beyond the 2r window
+        __syncthreads();
+        if (!in) return;
+        const int Y0 = R * y - R / 2, X0 = R * x - R / 2;
         acc = 0.0f;
-        const int Ya = (y == 0) ? 0 : Y0, Yb = (y == h - 1) ? H - 1 : Y0 + 2 * R - 1;
-        const int Xa = (x == 0) ? 0 : X0, Xb = (x == w - 1) ? W - 1 : X0 + 2 * R - 1;
-        for (int Y = max(Ya, 0); Y <= min(Yb, H - 1); ++Y) {
-            const int jy = Y - Y0;
-            float wyv;
-            if (jy >= 0 && jy < 2 * R) wyv = wy[jy];
-            else { const UpTap t = up_tap(Y, sh, h); wyv = (t.i0 == y ? t.l0 : 0.f) + (t.i1 == y ? t.l1 : 0.f); }
-            if (wyv == 0.f) continue;
+#pragma unroll
+        for (int jy = 0; jy < RW; ++jy) {
+            const int Y = Y0 + jy;
+            const float wyv = s_wy[threadIdx.y][jy];
+            if (wyv == 0.f) continue;                      // also covers Y outside the image
+            const float* grow = g + (size_t)Y * W;
             float row = 0.0f;
-            for (int X = max(Xa, 0); X <= min(Xb, W - 1); ++X) {
-                const int jx = X - X0;
-                float wxv;
-                if (jx >= 0 && jx < 2 * R) wxv = wx[jx];
-                else { const UpTap t = up_tap(X, sw, w); wxv = (t.i0 == x ? t.l0 : 0.f) + (t.i1 == x ? t.l1 : 0.f); }
-                row = fmaf(wxv, __ldg(g + (size_t)Y * W + X), row);
+#pragma unroll
+            for (int jx = 0; jx < RW; ++jx) {
+                const int X = X0 + jx;
+                const float wxv = s_wx[threadIdx.x][jx];
+                if (wxv != 0.f) row = fmaf(wxv, __ldg(grow + X), row);
             }
             acc = fmaf(wyv, row, acc);
         }

@@ -169,9 +169,10 @@ __device__ __forceinline__ AaSpan aa_span(int i, int in_size, float scale) {
 
 __global__ void __launch_bounds__(PA_THREADS)
 patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
-                       const float* __restrict__ scenes, const float* __restrict__ coeffs, int ph, int pw, int ih,
-                       int iw, int oh, int ow, int l_pad, int t_pad, float sy, float sx, int cw_max, int ch_max,
-                       float* __restrict__ adv, float* __restrict__ mask_out) {
+                       const float* __restrict__ scenes, const float* __restrict__ coeffs,
+                       const int* __restrict__ bbox, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
+                       int t_pad, float sy, float sx, int cw_max, int ch_max, float* __restrict__ adv,
+                       float* __restrict__ mask_out) {
     extern __shared__ float smem[];
     float* comp = smem;                                   // [4][ch_max][cw_max] : 3 colour planes + mask
     __shared__ int x_lo[PA_TW], x_n[PA_TW], y_lo[PA_TH], y_n[PA_TH];
@@ -203,15 +204,26 @@ patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict_
     const float* sc = scenes + (size_t)b * 3 * IN;
     const size_t plane = (size_t)ch_max * cw_max;
     const size_t PN = (size_t)ph * pw;
+    // canvas pixels outside the item's bounding box cannot sample the patch: skip the perspective maths there
+    bool tile_hits = true;
+    int bx0 = 0, by0 = 0, bx1 = iw - 1, by1 = ih - 1;
+    if (bbox) {
+        bx0 = __ldg(bbox + b * 4); by0 = __ldg(bbox + b * 4 + 1); bx1 = __ldg(bbox + b * 4 + 2); by1 = __ldg(bbox + b * 4 + 3);
+        tile_hits = !(cx0 > bx1 || cx0 + cw - 1 < bx0 || cy0 > by1 || cy0 + ch - 1 < by0);
+    }
     for (int i = tid; i < ch * cw; i += PA_THREADS) {
         const int r = i / cw, c = i % cw;
         const int cy = cy0 + r, cx = cx0 + c;            // always inside the canvas by construction of the spans
-        float ix, iy;
-        perspective_src(hm, cx, cy, iw, ih, ix, iy);
-        const PatchTaps t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
         const size_t so = (size_t)cy * iw + cx;
         const float s0 = __ldg(sc + so), s1 = __ldg(sc + IN + so), s2 = __ldg(sc + 2 * IN + so);
         float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        PatchTaps t;
+        t.any = false;
+        if (tile_hits && cx >= bx0 && cx <= bx1 && cy >= by0 && cy <= by1) {
+            float ix, iy;
+            perspective_src(hm, cx, cy, iw, ih, ix, iy);
+            t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+        }
         if (t.any) {
             m = sample_plane(pmask, t, pw);
             o0 = sample_plane(patch, t, pw);
@@ -283,12 +295,17 @@ __device__ __forceinline__ float aa_weight_of(int o, int in_size, float scale, i
 
 __global__ void __launch_bounds__(256)
 patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__ pmask,
-                       const float* __restrict__ coeffs, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
-                       int t_pad, float sy, float sx, float* __restrict__ gpatch) {
-    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (cx >= iw || cy >= ih) return;
+                       const float* __restrict__ coeffs, const int* __restrict__ bbox, int ph, int pw, int ih, int iw,
+                       int oh, int ow, int l_pad, int t_pad, float sy, float sx, float* __restrict__ gpatch) {
     const int b = blockIdx.z;
+    int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    int cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (bbox) {                                           // grid covers the largest bounding box of the batch
+        cx += __ldg(bbox + b * 4);
+        cy += __ldg(bbox + b * 4 + 1);
+        if (cx > __ldg(bbox + b * 4 + 2) || cy > __ldg(bbox + b * 4 + 3)) return;
+    }
+    if (cx >= iw || cy >= ih) return;
     const Homography hm = load_homography(coeffs, b, iw, ih);
     float ix, iy;
     perspective_src(hm, cx, cy, iw, ih, ix, iy);
@@ -364,9 +381,9 @@ static int aa_tile_extent(int tile, float scale) {
     return (int)(scale * tile + 2.0f * support + 3.0f);
 }
 
-int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs, int B,
-                        int ph, int pw, int ih, int iw, int oh, int ow, float* adv, float* mask_out,
-                        dmh_stream_t stream) {
+int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs,
+                        const int* bbox, int B, int ph, int pw, int ih, int iw, int oh, int ow, float* adv,
+                        float* mask_out, dmh_stream_t stream) {
     DMH_REQUIRE(patch && patch_mask && scenes && coeffs && adv, "dmh_patch_apply_fwd: null pointer");
     DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && ih >= ph && iw >= pw && oh > 0 && ow > 0,
                 "dmh_patch_apply_fwd: bad shape");
@@ -384,22 +401,26 @@ int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float
     }
     dim3 grid(ceil_div(ow, PA_TW), ceil_div(oh, PA_TH), B);
     DMH_LAUNCH(patch_apply_fwd_kernel, grid, PA_THREADS, smem, (cudaStream_t)stream)(
-        patch, patch_mask, scenes, coeffs, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv, mask_out);
+        patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
+        mask_out);
     DMH_CHECK_LAUNCH("dmh_patch_apply_fwd");
     return DMH_OK;
 }
 
-int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, int B, int ph, int pw,
-                        int ih, int iw, int oh, int ow, float* grad_patch, dmh_stream_t stream) {
+int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, const int* bbox,
+                        int bbox_max_w, int bbox_max_h, int B, int ph, int pw, int ih, int iw, int oh, int ow,
+                        float* grad_patch, dmh_stream_t stream) {
     DMH_REQUIRE(grad_adv && patch_mask && coeffs && grad_patch, "dmh_patch_apply_bwd: null pointer");
     DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && ih >= ph && iw >= pw && oh > 0 && ow > 0,
                 "dmh_patch_apply_bwd: bad shape");
     const float sy = (float)ih / (float)oh, sx = (float)iw / (float)ow;
     DMH_REQUIRE(sy < 3.0f && sx < 3.0f, "dmh_patch_apply_bwd: down-scale factor >= 3 unsupported");
     const int l_pad = (iw - pw) / 2, t_pad = (ih - ph) / 2;
-    dim3 block(32, 8), grid(ceil_div(iw, 32), ceil_div(ih, 8), B);
-    DMH_LAUNCH(patch_apply_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_adv, patch_mask, coeffs, ph, pw, ih, iw, oh, ow,
-                                                                          l_pad, t_pad, sy, sx, grad_patch);
+    DMH_REQUIRE(!bbox || (bbox_max_w > 0 && bbox_max_h > 0), "dmh_patch_apply_bwd: bbox given without its max extent");
+    const int gw = bbox ? (bbox_max_w < iw ? bbox_max_w : iw) : iw, gh = bbox ? (bbox_max_h < ih ? bbox_max_h : ih) : ih;
+    dim3 block(32, 8), grid(ceil_div(gw, 32), ceil_div(gh, 8), B);
+    DMH_LAUNCH(patch_apply_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_adv, patch_mask, coeffs, bbox, ph, pw, ih, iw,
+                                                                          oh, ow, l_pad, t_pad, sy, sx, grad_patch);
     DMH_CHECK_LAUNCH("dmh_patch_apply_bwd");
     return DMH_OK;
 }

@@ -88,9 +88,74 @@ def solve_homographies(start: Sequence, ends: np.ndarray) -> torch.Tensor:
     return sol.to(torch.float32).contiguous()
 
 
-def homographies(z0s, alphas, P34, K=None, T=None, obj_hw=(260, 300), canvas_hw=(ORI_H, ORI_W)) -> torch.Tensor:
+class Placement:
+    """Per-item placement of the patch on the canvas: the (Ba,8) perspective
+    coefficients plus a conservative (Ba,4) int32 bounding box {x0,y0,x1,y1}
+    (inclusive canvas pixels) outside of which item b cannot sample the patch.
+    The box is only an optimisation hint for the fused apply kernels (they skip
+    the perspective maths / launch smaller grids); results do not depend on it."""
+
+    def __init__(self, coeffs: torch.Tensor, bbox: Optional[torch.Tensor] = None, bbox_wh=(0, 0)):
+        self.coeffs, self.bbox, self.bbox_wh = coeffs, bbox, (int(bbox_wh[0]), int(bbox_wh[1]))
+
+    @property
+    def shape(self):
+        return self.coeffs.shape
+
+    @property
+    def device(self):
+        return self.coeffs.device
+
+    def to(self, device):
+        return Placement(self.coeffs.to(device), None if self.bbox is None else self.bbox.to(device), self.bbox_wh)
+
+
+def placement_bbox(coeffs: torch.Tensor, ends: np.ndarray, obj_hw, canvas_hw=(ORI_H, ORI_W)):
+    """Bounding box of the canvas pixels that can sample the patch.  The patch
+    rectangle is convex and the homography's denominator g*x+h*y+1 is positive at
+    the four projected corners, hence on the whole quadrilateral: the pre-image
+    of the rectangle is exactly the convex hull of those corners.  A margin covers
+    the half-pixel reach of the bilinear taps (magnified when the patch is
+    enlarged) and the fp32 rounding of the coefficients.  Items whose denominator
+    changes sign get the full canvas."""
+    H, W = canvas_hw
+    ends = np.asarray(ends, dtype=np.float64).reshape(-1, 4, 2)
+    co = coeffs.detach().cpu().double().numpy()
+    den = co[:, [6]] * ends[:, :, 0] + co[:, [7]] * ends[:, :, 1] + 1.0        # (n,4)
+    ok = (den > 1e-3).all(axis=1)
+    ext_w = ends[:, :, 0].max(1) - ends[:, :, 0].min(1)
+    ext_h = ends[:, :, 1].max(1) - ends[:, :, 1].min(1)
+    margin = 3.0 + np.ceil(np.maximum(ext_w / obj_hw[1], ext_h / obj_hw[0]))
+    x0 = np.clip(np.floor(ends[:, :, 0].min(1) - margin), 0, W - 1)
+    x1 = np.clip(np.ceil(ends[:, :, 0].max(1) + margin), 0, W - 1)
+    y0 = np.clip(np.floor(ends[:, :, 1].min(1) - margin), 0, H - 1)
+    y1 = np.clip(np.ceil(ends[:, :, 1].max(1) + margin), 0, H - 1)
+    box = np.stack([x0, y0, x1, y1], axis=1)
+    box[~ok] = (0, 0, W - 1, H - 1)
+    box = box.astype(np.int32)
+    wh = (int((box[:, 2] - box[:, 0] + 1).max()), int((box[:, 3] - box[:, 1] + 1).max()))
+    return torch.from_numpy(box).contiguous(), wh
+
+
+def make_placement(start, ends, obj_hw, canvas_hw=(ORI_H, ORI_W)) -> Placement:
+    co = solve_homographies(start, ends)
+    box, wh = placement_bbox(co, ends, obj_hw, canvas_hw)
+    return Placement(co, box, wh)
+
+
+def homographies(z0s, alphas, P34, K=None, T=None, obj_hw=(260, 300), canvas_hw=(ORI_H, ORI_W)) -> Placement:
     ends = np.stack([project_corners(z, a, P34, K, T) for z, a in zip(z0s, alphas)])
-    return solve_homographies(start_corners(obj_hw, canvas_hw), ends)
+    return make_placement(start_corners(obj_hw, canvas_hw), ends, obj_hw, canvas_hw)
+
+
+def _unpack(place):
+    """(coeffs, bbox or None, max bbox width, max bbox height) of a Placement or a bare (Ba,8) tensor."""
+    if isinstance(place, Placement):
+        bb = place.bbox
+        if bb is not None:
+            bb = bb.to(device=place.coeffs.device, dtype=torch.int32).contiguous()
+        return f32c(place.coeffs), bb, place.bbox_wh[0], place.bbox_wh[1]
+    return f32c(place), None, 0, 0
 
 
 # ----------------------------------------------------------------------------- perspective (canvas resolution)
@@ -122,39 +187,43 @@ def perspective_batch(img, coeffs, canvas_hw=(ORI_H, ORI_W)):
     """img (1,C,h,w) -> (Ba,C,H,W): Pad + torchvision.perspective for every item."""
     if img.shape[0] != 1:
         raise RuntimeError("perspective_batch expects a single (1,C,h,w) image shared by the batch")
+    if isinstance(coeffs, Placement):
+        coeffs = coeffs.coeffs
     return _Perspective.apply(img, coeffs, int(canvas_hw[0]), int(canvas_hw[1]))
 
 
 # ----------------------------------------------------------------------------- fused apply
 class _PatchApply(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, obj, mask, scenes, coeffs, oh, ow):
-        o, m, s, co = f32c(obj), f32c(mask), f32c(scenes), f32c(coeffs)
+    def forward(ctx, obj, mask, scenes, place, oh, ow):
+        o, m, s = f32c(obj), f32c(mask), f32c(scenes)
+        co, bb, bw, bh = _unpack(place)
         _, _, ph, pw = o.shape
         B, _, ih, iw = s.shape
         adv = torch.empty(B, 3, oh, ow, device=o.device, dtype=torch.float32)
         mout = torch.empty(B, 1, oh, ow, device=o.device, dtype=torch.float32)
-        check(_lib_().dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(adv),
-                                          ptr(mout), stream()), "patch_apply_fwd")
-        ctx.save_for_backward(m, co)
-        ctx.dims = (B, ph, pw, ih, iw, oh, ow)
+        check(_lib_().dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), ptr(bb), B, ph, pw, ih, iw, oh, ow,
+                                          ptr(adv), ptr(mout), stream()), "patch_apply_fwd")
+        ctx.save_for_backward(m, co, *([bb] if bb is not None else []))
+        ctx.dims = (B, ph, pw, ih, iw, oh, ow, bw, bh)
         ctx.mark_non_differentiable(mout)
         return adv, mout
 
     @staticmethod
     def backward(ctx, g_adv, _g_mask):
-        m, co = ctx.saved_tensors
-        B, ph, pw, ih, iw, oh, ow = ctx.dims
+        m, co, *rest = ctx.saved_tensors
+        bb = rest[0] if rest else None
+        B, ph, pw, ih, iw, oh, ow, bw, bh = ctx.dims
         g = f32c(g_adv)
         gp = torch.zeros(1, 3, ph, pw, device=g.device, dtype=torch.float32)
-        check(_lib_().dmh_patch_apply_bwd(ptr(g), ptr(m), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(gp), stream()),
-              "patch_apply_bwd")
+        check(_lib_().dmh_patch_apply_bwd(ptr(g), ptr(m), ptr(co), ptr(bb), bw, bh, B, ph, pw, ih, iw, oh, ow,
+                                          ptr(gp), stream()), "patch_apply_bwd")
         return gp, None, None, None, None, None
 
 
 def apply_patch(obj, mask, scenes, coeffs, size=(320, 1024)):
-    """obj (1,3,h,w) [grad], mask (1,1,h,w), scenes (Ba,3,375,1242), coeffs (Ba,8)
-    -> adv scenes (Ba,3,320,1024), resized masks (Ba,1,320,1024)."""
+    """obj (1,3,h,w) [grad], mask (1,1,h,w), scenes (Ba,3,375,1242), coeffs (Ba,8) tensor
+    or Placement -> adv scenes (Ba,3,320,1024), resized masks (Ba,1,320,1024)."""
     if scenes.shape[0] != coeffs.shape[0]:
         raise RuntimeError("Batch size doesn't match!")
     return _PatchApply.apply(obj, mask, scenes, coeffs, int(size[0]), int(size[1]))
@@ -163,7 +232,8 @@ def apply_patch(obj, mask, scenes, coeffs, size=(320, 1024)):
 def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024)):
     """No-autograd fast path for a PGD iteration whose upstream gradient
     d(cost)/d(adv_scene) is already known: returns (adv, mask_out, grad_patch)."""
-    o, m, s, co, up = f32c(obj), f32c(mask), f32c(scenes), f32c(coeffs), f32c(upstream)
+    o, m, s, up = f32c(obj), f32c(mask), f32c(scenes), f32c(upstream)
+    co, bb, bw, bh = _unpack(coeffs)
     _, _, ph, pw = o.shape
     B, _, ih, iw = s.shape
     oh, ow = int(size[0]), int(size[1])
@@ -171,10 +241,10 @@ def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024)):
     mout = torch.empty(B, 1, oh, ow, device=o.device, dtype=torch.float32)
     gp = torch.zeros(1, 3, ph, pw, device=o.device, dtype=torch.float32)
     lib = _lib_()
-    check(lib.dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(adv), ptr(mout),
-                                  stream()), "patch_apply_fwd")
-    check(lib.dmh_patch_apply_bwd(ptr(up), ptr(m), ptr(co), B, ph, pw, ih, iw, oh, ow, ptr(gp), stream()),
-          "patch_apply_bwd")
+    check(lib.dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), ptr(bb), B, ph, pw, ih, iw, oh, ow, ptr(adv),
+                                  ptr(mout), stream()), "patch_apply_fwd")
+    check(lib.dmh_patch_apply_bwd(ptr(up), ptr(m), ptr(co), ptr(bb), bw, bh, B, ph, pw, ih, iw, oh, ow, ptr(gp),
+                                  stream()), "patch_apply_bwd")
     return adv, mout, gp
 
 

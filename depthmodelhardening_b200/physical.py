@@ -81,7 +81,9 @@ class PhysicalTrans(object):
         co = self._coeff_cache.get(key)
         if co is None:
             ends = np.stack([patch_ops.project_corners(z, a, self.P, K, T) for z, a in zip(z0_sample, alpha_sample)])
-            co = patch_ops.solve_homographies(self.pos_obj_img_start, ends).to(self.obj_img.device)
+            _, _, h, w = self.obj_img.size()
+            co = patch_ops.make_placement(self.pos_obj_img_start, ends, (h, w),
+                                          (self.output_size[2], self.output_size[3])).to(self.obj_img.device)
             if len(self._coeff_cache) > 256:
                 self._coeff_cache.clear()
             self._coeff_cache[key] = co

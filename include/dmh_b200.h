@@ -204,12 +204,16 @@ int dmh_perspective_bwd(const float* grad_out, const float* coeffs, int B, int C
  * antialias) of the composite and of the mask.
  * patch (3,ph,pw), patch_mask (1,ph,pw), scenes (B,3,ih,iw), coeffs (B,8)
  * -> adv (B,3,oh,ow), mask_out (B,1,oh,ow) (nullable)
- * bwd: grad_adv (B,3,oh,ow) -> grad_patch (3,ph,pw) accumulated (sum over the batch). */
-int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs, int B,
-                        int ph, int pw, int ih, int iw, int oh, int ow, float* adv, float* mask_out,
-                        dmh_stream_t stream);
-int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, int B, int ph, int pw,
-                        int ih, int iw, int oh, int ow, float* grad_patch, dmh_stream_t stream);
+ * bwd: grad_adv (B,3,oh,ow) -> grad_patch (3,ph,pw) accumulated (sum over the batch).
+ * bbox (nullable): (B,4) int32 device array {x0,y0,x1,y1} (inclusive canvas pixels) outside of which item b
+ * cannot sample the patch (host-computed from the projected corners; an optimisation hint that must be
+ * conservative); bwd launches only max-bbox-sized grids (bbox_max_w/h = largest extent over the batch).  */
+int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs,
+                        const int* bbox, int B, int ph, int pw, int ih, int iw, int oh, int ow, float* adv,
+                        float* mask_out, dmh_stream_t stream);
+int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const float* coeffs, const int* bbox,
+                        int bbox_max_w, int bbox_max_h, int B, int ph, int pw, int ih, int iw, int oh, int ow,
+                        float* grad_patch, dmh_stream_t stream);
 
 /* -- A6 L-inf PGD update (phy_obj_atk.py:98-100; pgd_depth.py:76-78; pgd.py:73-75):
  * out = clamp(clean + clamp(adv + alpha*sign(grad) - clean, -eps, eps), 0, 1)          */
