@@ -24,8 +24,11 @@ namespace {
 
 #define SF_NB1 64
 #define SF_THREADS 256
-// blocks of sf_main_kernel per image (32 x 8 pixel CTAs)
-#define SF_BLOCKS(h, w) ((((w) + 31) / 32) * (((h) + 7) / 8))
+// CTA tile of sf_main_kernel: 128 x 32 pixels (8 warps x 4 rows, 4 pixels per lane)
+#define SF_TW 128
+#define SF_TH 32
+#define SF_RPW 4
+#define SF_BLOCKS(h, w) ((((w) + SF_TW - 1) / SF_TW) * (((h) + SF_TH - 1) / SF_TH))
 
 __global__ void sf_mean_kernel(const float* __restrict__ disp, int hw, float* __restrict__ part) {
     __shared__ float red[32];
@@ -46,87 +49,151 @@ __device__ __forceinline__ float mean_eps_warp(const float* __restrict__ mean_pa
     return s / (float)hw + 1e-7f;
 }
 
-__device__ __forceinline__ float edge_w(const float* __restrict__ im, int C, size_t plane, size_t a, size_t b2) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += fabsf(__ldg(im + c * plane + a) - __ldg(im + c * plane + b2));
-    return expf(-(s / (float)C));
-}
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
-// One thread per pixel.  Every edge weight exp(-mean_c|dI|) is evaluated once by the pixel on its left / top
-// ("owner") and handed to the right / bottom neighbour through shared memory (one row of CTA-width halo is
-// recomputed).  CTA = 32 x 8 pixels.
-#define SF_BW 32
-#define SF_BH 8
+// four consecutive pixels of one row (x .. x+3); zeros beyond the row end
+__device__ __forceinline__ void load_px4(const float* __restrict__ row, int x, int w, bool vec, float v[4]) {
+    if (vec && x + 3 < w) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + x));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (x + j < w) ? __ldg(row + x + j) : 0.f;
+    }
+}
+
+// A16 forward + gradient w.r.t. the normalised disparity.  A lane owns 4 consecutive pixels of a row and
+// walks down SF_RPW rows keeping the previous row in registers, so every disparity / colour value is loaded
+// once per warp (128-bit loads) plus one row of overlap above and below; the edge weight exp(-mean_c|dI|)
+// of every edge is evaluated once by the pixel on its left / top ("owner") and reaches the right / bottom
+// neighbour through a register or a warp shuffle.
+template <int C>
 __global__ void __launch_bounds__(SF_THREADS)
-sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, int C, int h, int w,
-               const float* __restrict__ mean_part, float inv_nx, float inv_ny, float* __restrict__ gN,
+sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, int h, int w,
+               const float* __restrict__ mean_part, float inv_nx, float inv_ny, int vec, float* __restrict__ gN,
                float* __restrict__ part) {
     __shared__ float s_m;
-    __shared__ float s_gx[SF_BH][SF_BW + 1];      // signed, weighted x-edge term owned by (y, x): sgn(diff)*e
-    __shared__ float s_gy[SF_BH + 1][SF_BW];      // same for the y-edge owned by (y, x)
+    __shared__ float s_red[3][SF_THREADS / 32];
     const int b = blockIdx.z;
     const int hw = h * w;
-    const int tx_ = threadIdx.x & (SF_BW - 1), ty_ = threadIdx.x / SF_BW;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x < 32) {
         const float m0 = mean_eps_warp(mean_part, b, hw);
         if (threadIdx.x == 0) s_m = 1.0f / m0;
     }
     __syncthreads();
     const float inv_m = s_m;
+    const float inv_c = 1.0f / (float)C;
     const float* d = disp + (size_t)b * hw;
     const float* im = img + (size_t)b * C * hw;
-    const int x = blockIdx.x * SF_BW + tx_, y = blockIdx.y * SF_BH + ty_;
-    const bool in = x < w && y < h;
-    const int n = y * w + x;
-    float tx = 0.f, ty = 0.f, gxo = 0.f, gyo = 0.f, dv = 0.f;
-    if (in) {
-        dv = d[n];
-        const float dn = dv * inv_m;
-        if (x < w - 1) {
-            const float diff = dn - d[n + 1] * inv_m;
-            const float e = edge_w(im, C, hw, n, n + 1);
-            tx = fabsf(diff) * e;
-            gxo = sgn(diff) * e;
-        }
-        if (y < h - 1) {
-            const float diff = dn - d[n + w] * inv_m;
-            const float e = edge_w(im, C, hw, n, n + w);
-            ty = fabsf(diff) * e;
-            gyo = sgn(diff) * e;
-        }
+    const int x = blockIdx.x * SF_TW + 4 * lane;
+    const int xr = blockIdx.x * SF_TW + SF_TW;              // first pixel right of the tile
+    const int xl = blockIdx.x * SF_TW - 1;                  // last pixel left of the tile
+    const int yb = blockIdx.y * SF_TH + SF_RPW * wid;       // first output row of this warp
+    const bool vok = vec != 0;
+
+    float dc[4], ic[C][4];                                  // owner row y: normalised disparity, colour
+    float dn_[4], in_[C][4];                                // row y + 1
+    float gy_up[4] = {0.f, 0.f, 0.f, 0.f};                  // y-edge terms owned by row y - 1
+    float sum_x = 0.f, sum_y = 0.f, sum_g = 0.f;
+
+    int y = yb - 1;
+    if (y >= 0 && y < h) {
+        load_px4(d + (size_t)y * w, x, w, vok, dc);
+#pragma unroll
+        for (int c = 0; c < C; ++c) load_px4(im + (size_t)c * hw + (size_t)y * w, x, w, vok, ic[c]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dc[j] = 0.f; for (int c = 0; c < C; ++c) ic[c][j] = 0.f; }
     }
-    s_gx[ty_][tx_ + 1] = gxo;
-    s_gy[ty_ + 1][tx_] = gyo;
-    // halo: the x-edge owned by the pixel left of the tile, the y-edge owned by the pixel above it
-    if (tx_ == 0) {
-        float v = 0.f;
-        if (in && x > 0) {
-            const float diff = d[n - 1] * inv_m - dv * inv_m;
-            v = sgn(diff) * edge_w(im, C, hw, n - 1, n);
+#pragma unroll
+    for (int r = -1; r < SF_RPW; ++r, ++y) {
+        const bool row_ok = y >= 0 && y < h;
+        const bool below_ok = y + 1 < h && y + 1 >= 0;
+        if (below_ok) {
+            load_px4(d + (size_t)(y + 1) * w, x, w, vok, dn_);
+#pragma unroll
+            for (int c = 0; c < C; ++c) load_px4(im + (size_t)c * hw + (size_t)(y + 1) * w, x, w, vok, in_[c]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dn_[j] = 0.f; for (int c = 0; c < C; ++c) in_[c][j] = 0.f; }
         }
-        s_gx[ty_][0] = v;
-    }
-    if (ty_ == 0) {
-        float v = 0.f;
-        if (in && y > 0) {
-            const float diff = d[n - w] * inv_m - dv * inv_m;
-            v = sgn(diff) * edge_w(im, C, hw, n - w, n);
+        // y-edge owned by (y, x+j): valid iff y and y+1 are rows of the image
+        float gy[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float sabs = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - in_[c][j]);
+            const float e = expf(-(sabs * inv_c));
+            const float diff = dc[j] * inv_m - dn_[j] * inv_m;
+            const bool ok = row_ok && below_ok && x + j < w;
+            gy[j] = ok ? sgn(diff) * e : 0.f;
+            if (r >= 0 && ok) sum_y += fabsf(diff) * e;
         }
-        s_gy[0][tx_] = v;
-    }
-    __syncthreads();
-    float g = 0.f;
-    if (in) {
-        g = (gxo - s_gx[ty_][tx_]) * inv_nx + (gyo - s_gy[ty_][tx_]) * inv_ny;
-        gN[(size_t)b * hw + n] = g;
+        if (r >= 0) {
+            // right neighbour of pixel 3: lane+1's pixel 0, or (lane 31) the first pixel of the next tile
+            float dr = __shfl_down_sync(0xffffffffu, dc[0], 1);
+            float ir[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) ir[c] = __shfl_down_sync(0xffffffffu, ic[c][0], 1);
+            if (lane == 31 && row_ok && xr < w) {
+                dr = __ldg(d + (size_t)y * w + xr);
+#pragma unroll
+                for (int c = 0; c < C; ++c) ir[c] = __ldg(im + (size_t)c * hw + (size_t)y * w + xr);
+            }
+            float gx[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float sabs = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - (j < 3 ? ic[c][j + 1] : ir[c]));
+                const float e = expf(-(sabs * inv_c));
+                const float diff = dc[j] * inv_m - (j < 3 ? dc[j + 1] : dr) * inv_m;
+                const bool ok = row_ok && x + j < w - 1;
+                gx[j] = ok ? sgn(diff) * e : 0.f;
+                if (ok) sum_x += fabsf(diff) * e;
+            }
+            // x-edge owned by the pixel left of pixel 0: lane-1's gx[3], or (lane 0) recomputed across the tile border
+            float gl = __shfl_up_sync(0xffffffffu, gx[3], 1);
+            if (lane == 0) {
+                gl = 0.f;
+                if (row_ok && xl >= 0 && x < w) {
+                    float sabs = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) sabs += fabsf(__ldg(im + (size_t)c * hw + (size_t)y * w + xl) - ic[c][0]);
+                    const float diff = __ldg(d + (size_t)y * w + xl) * inv_m - dc[0] * inv_m;
+                    gl = sgn(diff) * expf(-(sabs * inv_c));
+                }
+            }
+            if (row_ok) {
+                float g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = (gx[j] - (j > 0 ? gx[j - 1] : gl)) * inv_nx + (gy[j] - gy_up[j]) * inv_ny;
+                    if (x + j < w) sum_g += g[j] * dc[j];
+                }
+                float* go = gN + (size_t)b * hw + (size_t)y * w + x;
+                if (vok && x + 3 < w) {
+                    *reinterpret_cast<float4*>(go) = make_float4(g[0], g[1], g[2], g[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < w) go[j] = g[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gy_up[j] = gy[j];
+            dc[j] = dn_[j];
+#pragma unroll
+            for (int c = 0; c < C; ++c) ic[c][j] = in_[c][j];
+        }
     }
     // one combined reduction of the three partial sums (warp shuffles, then 3 x 8 values in shared memory)
-    __shared__ float s_red[3][SF_THREADS / 32];
-    const float r0 = warp_sum(tx), r1 = warp_sum(ty), r2 = warp_sum(g * dv);
-    if ((threadIdx.x & 31) == 0) {
-        s_red[0][threadIdx.x >> 5] = r0; s_red[1][threadIdx.x >> 5] = r1; s_red[2][threadIdx.x >> 5] = r2;
-    }
+    const float r0 = warp_sum(sum_x), r1 = warp_sum(sum_y), r2 = warp_sum(sum_g);
+    if (lane == 0) { s_red[0][wid] = r0; s_red[1][wid] = r1; s_red[2][wid] = r2; }
     __syncthreads();
     if (threadIdx.x < 3) {
         float t = 0.f;
@@ -220,18 +287,46 @@ finish_kernel(const FinishParams p) {
     *p.ticket = 0u;
 }
 
-// one thread per low-res pixel.  For an integer up-scale factor r the full-res pixels that read low-res
-// pixel y are exactly Y in [r*y - r/2, r*y + 3r/2 - 1] (2r of them): their weights are tabulated once per
-// thread, the inner loop is one load + one FMA.  Other factors use the generic conservative window.
+// Transposed bilinear up-sampling (F.interpolate backward) + normalisation backward + upstream scaling.
+// Integer up-scale factor R (2, 4, 8): full-res pixel X = R*c - R/2 + j (chunk c, j < R) reads low-res
+// pixels c-1 (weight 1-l_j) and c (weight l_j), so low-res pixel x gathers chunk x and chunk x+1.
+// CTA = 32 x 8 low-res pixels.  Stage 1: a warp takes one full-res row, lane c loads chunk c with one or
+// two 128/64-bit loads (coalesced; every full-res value is read once) and reduces it against both weight
+// sets; the contribution to the left neighbour travels by shuffle; row results go to shared memory.
+// Stage 2: one thread per low-res pixel sums its 2R rows.  Deterministic (no atomics; ATen's CUDA
+// backward of upsample_bilinear2d scatters with atomicAdd).  R == 1: plain copy; other factors: generic
+// conservative window (one thread per low-res pixel).
 template <int R>
-__global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
-                                 const float* __restrict__ img_scalars, float smooth_weight,
-                                 const float* __restrict__ g_total, const float* __restrict__ g_scale, float inv_S,
-                                 int h, int w, int H, int W, float sh, float sw, float* __restrict__ grad) {
+__device__ __forceinline__ void load_chunk(const float* __restrict__ grow, int X, int W, float v[R]) {
+    if (X >= 0 && X + R <= W) {
+        if (R == 8) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(grow + X));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(grow + X + 4));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4 % R] = b.x; v[5 % R] = b.y; v[6 % R] = b.z; v[7 % R] = b.w;
+        } else if (R == 4) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(grow + X));
+            const float2 b = __ldg(reinterpret_cast<const float2*>(grow + X + 2));
+            v[0] = a.x; v[1] = a.y; v[2 % R] = b.x; v[3 % R] = b.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = __ldg(grow + X + j);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = (X + j >= 0 && X + j < W) ? __ldg(grow + X + j) : 0.f;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
+                 const float* __restrict__ img_scalars, float smooth_weight, const float* __restrict__ g_total,
+                 const float* __restrict__ g_scale, float inv_S, int h, int w, int H, int W, float sh, float sw,
+                 float* __restrict__ grad) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const bool in = x < w && y < h;
-    if (R <= 1 && !in) return;                            // (R > 1: every thread helps to fill the weight tables)
+    if (R <= 1 && !in) return;                            // (R > 1: every thread works on the tile)
     const int b = blockIdx.z;
     const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
     const float* g = G_full + (size_t)b * H * W;
@@ -239,10 +334,12 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
     if (R == 1) {
         acc = __ldg(g + (size_t)y * W + x);
     } else if (R > 1) {
-        // weights depend only on (y, offset) / (x, offset): tabulated once per CTA (32 x 8 low-res pixels)
-        constexpr int RW = R > 0 ? 2 * R : 1;
+        constexpr int RW = R > 0 ? 2 * R : 1, RR = R > 0 ? R : 1, NR = 9 * RR;
         __shared__ float s_wy[8][RW], s_wx[32][RW];
-        const int t = threadIdx.y * 32 + threadIdx.x;
+        __shared__ float s_h[NR][32];
+        const int lane = threadIdx.x, wid = threadIdx.y;
+        const int t = wid * 32 + lane;
+        // weights depend only on (y, offset) / (x, offset): tabulated once per CTA with the forward's up_tap
         for (int i = t; i < 8 * RW + 32 * RW; i += 256) {
             if (i < 8 * RW) {
                 const int ly = i / RW, j = i % RW;
@@ -260,24 +357,41 @@ __global__ void disp_grad_kernel(const float* __restrict__ G_full, const float* 
             }
         }
         __syncthreads();
+        float wA[RR], wB[RR], wE[RR];                       // chunk c -> low-res c, chunk c -> low-res c-1, chunk 32 -> 31
+#pragma unroll
+        for (int j = 0; j < RR; ++j) {
+            wA[j] = s_wx[lane][j];
+            wB[j] = lane > 0 ? s_wx[lane - 1][RR + j] : 0.f;
+            wE[j] = s_wx[31][RR + j];
+        }
+        const int Xc = R * x - R / 2;                        // first full-res column of this lane's chunk
+        const int Xe = R * (blockIdx.x * 32 + 32) - R / 2;  // chunk 32 (lane 0 takes it)
+        const int Yt = R * (blockIdx.y * 8) - R / 2;        // first full-res row of the tile's window
+        for (int ry = wid; ry < NR; ry += 8) {
+            const int Y = Yt + ry;
+            float a = 0.f, bm = 0.f, e = 0.f;
+            if (Y >= 0 && Y < H) {                           // warp-uniform
+                const float* grow = g + (size_t)Y * W;
+                float v[RR];
+                load_chunk<RR>(grow, Xc, W, v);
+#pragma unroll
+                for (int j = 0; j < RR; ++j) { a = fmaf(wA[j], v[j], a); bm = fmaf(wB[j], v[j], bm); }
+                if (lane == 0) {
+                    load_chunk<RR>(grow, Xe, W, v);
+#pragma unroll
+                    for (int j = 0; j < RR; ++j) e = fmaf(wE[j], v[j], e);
+                }
+            }
+            float nb = __shfl_down_sync(0xffffffffu, bm, 1);
+            const float ee = __shfl_sync(0xffffffffu, e, 0);
+            if (lane == 31) nb = ee;
+            s_h[ry][lane] = a + nb;
+        }
+        __syncthreads();
         if (!in) return;
-        const int Y0 = R * y - R / 2, X0 = R * x - R / 2;
         acc = 0.0f;
 #pragma unroll
-        for (int jy = 0; jy < RW; ++jy) {
-            const int Y = Y0 + jy;
-            const float wyv = s_wy[threadIdx.y][jy];
-            if (wyv == 0.f) continue;                      // also covers Y outside the image
-            const float* grow = g + (size_t)Y * W;
-            float row = 0.0f;
-#pragma unroll
-            for (int jx = 0; jx < RW; ++jx) {
-                const int X = X0 + jx;
-                const float wxv = s_wx[threadIdx.x][jx];
-                if (wxv != 0.f) row = fmaf(wxv, __ldg(grow + X), row);
-            }
-            acc = fmaf(wyv, row, acc);
-        }
+        for (int j = 0; j < RW; ++j) acc = fmaf(s_wy[wid][j], s_h[R * wid + j][lane], acc);
     } else {
         const float rh = 1.0f / sh, rw = 1.0f / sw;
         const int Y0 = max(0, (int)floorf(((float)y - 0.5f) * rh - 0.5f) - 1);
@@ -316,12 +430,18 @@ long long dmh_smooth_fused_workspace_floats(int B, int h, int w) {
 int dmh_smooth_fused(const float* disp, const float* img, int B, int C, int h, int w, float* ws, float* gN,
                      dmh_stream_t stream) {
     DMH_REQUIRE(disp && img && ws && gN, "dmh_smooth_fused: null pointer");
-    DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && h >= 2 && w >= 2, "dmh_smooth_fused: bad shape");
+    DMH_REQUIRE(B > 0 && B <= 65535 && (C == 3 || C == 1) && h >= 2 && w >= 2,
+                "dmh_smooth_fused: bad shape (the image must have 3 channels or 1)");
     cudaStream_t st = (cudaStream_t)stream;
     DMH_LAUNCH(sf_mean_kernel, dim3(SF_NB1, B), 256, 0, st)(disp, h * w, ws);
     const float inv_nx = (float)(1.0 / ((double)B * h * (w - 1))), inv_ny = (float)(1.0 / ((double)B * (h - 1) * w));
-    DMH_LAUNCH(sf_main_kernel, dim3(ceil_div(w, SF_BW), ceil_div(h, SF_BH), B), SF_THREADS, 0, st)(
-        disp, img, C, h, w, ws, inv_nx, inv_ny, gN, ws + (size_t)B * SF_NB1);
+    const int vec = (w % 4 == 0) && (((uintptr_t)disp | (uintptr_t)img | (uintptr_t)gN) % 16 == 0);
+    const dim3 grid(ceil_div(w, SF_TW), ceil_div(h, SF_TH), B);
+    float* part = ws + (size_t)B * SF_NB1;
+    if (C == 3)
+        DMH_LAUNCH(sf_main_kernel<3>, grid, SF_THREADS, 0, st)(disp, img, h, w, ws, inv_nx, inv_ny, vec, gN, part);
+    else
+        DMH_LAUNCH(sf_main_kernel<1>, grid, SF_THREADS, 0, st)(disp, img, h, w, ws, inv_nx, inv_ny, vec, gN, part);
     DMH_CHECK_LAUNCH("dmh_smooth_fused");
     return DMH_OK;
 }
@@ -368,6 +488,7 @@ int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars
     cudaStream_t st = (cudaStream_t)stream;
     int R = 0;                                   // integer up-scale factor shared by both axes, else generic
     if (H % h == 0 && W % w == 0 && H / h == W / w) R = H / h;
+    if (R > 1 && ((uintptr_t)G_full % 16 != 0 || W % 4 != 0)) R = 0;   // vector loads need aligned rows
 #define DMH_DG(RR) DMH_LAUNCH(disp_grad_kernel<RR>, grid, block, 0, st)(G_full, gN, img_scalars, smooth_weight, g_total, \
                                                                        g_scale, inv_S, h, w, H, W, sh, sw, grad_disp)
     if (R == 1) DMH_DG(1);

@@ -19,12 +19,53 @@
 // Shared memory: tgt 3x36x36 + pred 3x36x36 + coef 9x34x34 floats + gate bytes
 // = 73.9 KB -> 3 CTAs / SM.   Roofline: HBM by traffic (40 B per target pixel),
 // but issue-bound in practice (see profiles/): ~900 instr / pixel.
+//
+// Target tile staging: ONE elected thread issues a 4-D TMA load
+// (cp.async.bulk.tensor, box 36 x 36 x 3 x 1 at (x0-2, y0-2, 0, b), out-of-image
+// elements zero-filled) that lands on an mbarrier while all warps run the gather
+// phase; the 1-px reflection (ReflectionPad2d) of border tiles is patched in
+// shared memory afterwards.  Rows that are not 16-byte aligned (W % 4 != 0 or a
+// misaligned base) take the plain-load instantiation of the same kernel.
+#include <cuda.h>
+#include <string.h>
+
 #include "../../include/dmh_b200.h"
 #include "dmh_common.cuh"
 
 using namespace dmh;
 
 namespace {
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; sm_100a here)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 #define FT_T 32
 #define FT_R2 36                 // tile + 2-px halo
@@ -88,10 +129,12 @@ __device__ __forceinline__ Gathered gather3(const float* __restrict__ sp, size_t
     return g;
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(FT_THREADS, 3)
-photo_fast_kernel(const FastParams p) {
-    extern __shared__ float smem[];
-    float* tgt = smem;                       // [3][N2]
+photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t tgt_bar;
+    float* tgt = smem;                       // [3][N2] (TMA destination: 128-byte aligned)
     float* pred = tgt + 3 * FT_N2;           // [3][N2]
     float* coef = pred + 3 * FT_N2;          // [9][N1]: (a,b,c) x 3 channels, gated
     float* cams = coef + 9 * FT_N1;          // [24]
@@ -121,8 +164,15 @@ photo_fast_kernel(const FastParams p) {
         const int i = (tid - 12) / 3, j = (tid - 12) % 3;
         cams[tid] = __ldg(p.inv_K + b * 16 + i * 4 + j);
     }
-    // ---- target tile, 2-px reflect halo: 36 columns x 7 row groups = 252 threads, column index maths once
-    if (tid < FT_R2 * 7) {
+    if (TMA) {
+        // ---- target tile by TMA: in flight during the whole gather phase
+        if (tid == 0) {
+            mbar_init(&tgt_bar, 1);
+            mbar_expect_tx(&tgt_bar, 3 * FT_N2 * sizeof(float));
+            tma_load_4d(tgt, &tgt_map, &tgt_bar, x0 - 2, y0 - 2, 0, b);
+        }
+    } else if (tid < FT_R2 * 7) {
+        // ---- target tile, 2-px reflect halo: 36 columns x 7 row groups = 252 threads, column index maths once
         const int c = tid % FT_R2, rg = tid / FT_R2;
         const int ix = ext_to_img(x0 - 2 + c, W);
         const float* tp = p.target + (size_t)b * 3 * N + ix;
@@ -180,7 +230,42 @@ photo_fast_kernel(const FastParams p) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + r * FT_R2 + c] = g.v[ch];
     }
+    // identity losses (+ tie-break noise) of this thread's phase-B pixels: requested before the barrier so
+    // that their latency overlaps the other warps' gather
+    float idv_pre[FT_ROWS];
+    {
+        const int c = tid % FT_R1, strip = tid / FT_R1;
+        const int qx = x0 - 1 + c;
+#pragma unroll
+        for (int k = 0; k < FT_ROWS; ++k) {
+            const int qr = strip * FT_ROWS + k, qy = y0 - 1 + qr;
+            float v = 0.f;
+            if (p.ident && tid < FT_R1 * FT_STRIPS && qr < FT_R1 && qx >= 0 && qx < W && qy >= 0 && qy < H) {
+                const size_t qo = (size_t)b * N + (size_t)qy * W + qx;
+                v = __ldg(p.ident + qo);
+                if (p.noise) v = add_rn(v, __ldg(p.noise + qo));
+            }
+            idv_pre[k] = v;
+        }
+    }
     __syncthreads();
+    if (TMA) {
+        mbar_wait(&tgt_bar, 0);
+        // ReflectionPad2d(1) at the image border: TMA zero-fills out-of-image elements; patch them from the
+        // in-image rows / columns of the same tile (sources are never patched themselves)
+        if (x0 < 2 || y0 < 2 || x0 + FT_T + 2 > W || y0 + FT_T + 2 > H) {
+            for (int i = tid; i < FT_N2; i += FT_THREADS) {
+                const int r = i / FT_R2, c = i - r * FT_R2;
+                const int ey = y0 - 2 + r, ex = x0 - 2 + c;
+                if (ey < 0 || ey >= H || ex < 0 || ex >= W) {
+                    const int sr = ext_to_img(ey, H) - (y0 - 2), sc = ext_to_img(ex, W) - (x0 - 2);
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + i] = tgt[ch * FT_N2 + sr * FT_R2 + sc];
+                }
+            }
+            __syncthreads();
+        }
+    }
 
     // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients
     float loss_local = 0.0f;
@@ -234,8 +319,7 @@ photo_fast_kernel(const FastParams p) {
                         int best_idx = 0;
                         bool win = true;
                         if (p.ident) {
-                            float idv = __ldg(p.ident + (size_t)b * N + qo);
-                            if (p.noise) idv = add_rn(idv, __ldg(p.noise + (size_t)b * N + qo));
+                            const float idv = idv_pre[rr - 2];
                             win = rp < idv;                     // torch.min: first minimum wins, identity is first
                             best = win ? rp : idv;
                             best_idx = win ? 1 : 0;
@@ -396,6 +480,22 @@ ident_fast_kernel(const IdentParams p) {
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmaEncodeFn tma_encoder() {
+    static TmaEncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<TmaEncodeFn>(f);
+    }();
+    return fn;
+}
+
 size_t fast_smem_bytes() { return sizeof(float) * (6 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
 
 }  // namespace
@@ -423,7 +523,9 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured_dev[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(photo_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(photo_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photo_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("dmh_photo_scale(fast): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return DMH_ERR_CUDA;
@@ -431,7 +533,22 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
         configured_dev[dev & 63] = true;
     }
     dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B);
-    DMH_LAUNCH(photo_fast_kernel, grid, FT_THREADS, smem, st)(p);
+    // TMA descriptor of the target frames viewed as a (W, H, 3, B) fp32 tensor; needs 16-byte aligned rows
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    bool use_tma = (W % 4 == 0) && ((uintptr_t)target % 16 == 0) && tma_encoder() != nullptr;
+    if (use_tma) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
+        const cuuint32_t box[4] = {FT_R2, FT_R2, 3, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = tma_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(target), gdim, gstr,
+                                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        use_tma = (r == CUDA_SUCCESS);
+    }
+    if (use_tma) DMH_LAUNCH(photo_fast_kernel<true>, grid, FT_THREADS, smem, st)(p, map);
+    else DMH_LAUNCH(photo_fast_kernel<false>, grid, FT_THREADS, smem, st)(p, map);
     return DMH_OK;
 }
 
