@@ -21,8 +21,9 @@
 // but issue-bound in practice (see profiles/): ~900 instr / pixel.
 //
 // Target tile staging: ONE elected thread issues a 4-D TMA load
-// (cp.async.bulk.tensor, box 36 x 36 x 3 x 1 at (x0-2, y0-2, 0, b), out-of-image
-// elements zero-filled) that lands on an mbarrier while all warps run the gather
+// (cp.async.bulk.tensor, box 40 x 36 x 3 x 1 at (x0-4, y0-2, 0, b) -- the innermost
+// start coordinate must be 16-byte aligned, measured: x0-2 raises an illegal
+// instruction -- out-of-image elements zero-filled) that lands on an mbarrier while all warps run the gather
 // phase; the 1-px reflection (ReflectionPad2d) of border tiles is patched in
 // shared memory afterwards.  Rows that are not 16-byte aligned (W % 4 != 0 or a
 // misaligned base) take the plain-load instantiation of the same kernel.
@@ -71,6 +72,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 #define FT_R2 36                 // tile + 2-px halo
 #define FT_R1 34                 // tile + 1-px ring
 #define FT_N2 (FT_R2 * FT_R2)
+#define FT_TP 40                 // row pitch of the target tile: TMA needs a 16-byte aligned start column (x0-4)
+#define FT_TO 2                  // column of the target tile that holds halo column 0 (image column x0-2)
+#define FT_NT (FT_R2 * FT_TP)
 #define FT_N1 (FT_R1 * FT_R1)
 #define FT_THREADS 256
 #define FT_STRIPS 7
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3)
 photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t tgt_bar;
-    float* tgt = smem;                       // [3][N2] (TMA destination: 128-byte aligned)
-    float* pred = tgt + 3 * FT_N2;           // [3][N2]
+    float* tgt = smem;                       // [3][36][40] (TMA destination: 128-byte aligned)
+    float* pred = tgt + 3 * FT_NT;           // [3][N2]
     float* coef = pred + 3 * FT_N2;          // [9][N1]: (a,b,c) x 3 channels, gated
     float* cams = coef + 9 * FT_N1;          // [24]
     float* red = cams + 24;                  // [32]
@@ -168,8 +172,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         // ---- target tile by TMA: in flight during the whole gather phase
         if (tid == 0) {
             mbar_init(&tgt_bar, 1);
-            mbar_expect_tx(&tgt_bar, 3 * FT_N2 * sizeof(float));
-            tma_load_4d(tgt, &tgt_map, &tgt_bar, x0 - 2, y0 - 2, 0, b);
+            mbar_expect_tx(&tgt_bar, 3 * FT_NT * sizeof(float));
+            tma_load_4d(tgt, &tgt_map, &tgt_bar, x0 - 2 - FT_TO, y0 - 2, 0, b);
         }
     } else if (tid < FT_R2 * 7) {
         // ---- target tile, 2-px reflect halo: 36 columns x 7 row groups = 252 threads, column index maths once
@@ -179,7 +183,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         for (int r = rg; r < FT_R2; r += 7) {
             const int o = ext_to_img(y0 - 2 + r, H) * W;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + r * FT_R2 + c] = __ldg(tp + ch * N + o);
+            for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_NT + r * FT_TP + c + FT_TO] = __ldg(tp + ch * N + o);
         }
     }
     __syncthreads();
@@ -260,7 +264,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 if (ey < 0 || ey >= H || ex < 0 || ex >= W) {
                     const int sr = ext_to_img(ey, H) - (y0 - 2), sc = ext_to_img(ex, W) - (x0 - 2);
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) tgt[ch * FT_N2 + i] = tgt[ch * FT_N2 + sr * FT_R2 + sc];
+                    for (int ch = 0; ch < 3; ++ch)
+                        tgt[ch * FT_NT + r * FT_TP + c + FT_TO] = tgt[ch * FT_NT + sr * FT_TP + sc + FT_TO];
                 }
             }
             __syncthreads();
@@ -285,7 +290,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const float* xs = pred + ch * FT_N2 + r2 * FT_R2 + c;
-                    const float* ys = tgt + ch * FT_N2 + r2 * FT_R2 + c;
+                    const float* ys = tgt + ch * FT_NT + r2 * FT_TP + c + FT_TO;
                     const float xa = xs[0], xb = xs[1], xc = xs[2], ya = ys[0], yb = ys[1], yc = ys[2];
                     cur[ch] = row5(xa, xb, xc, ya, yb, yc);
                     mid_x[ch] = xb; mid_y[ch] = yb;
@@ -384,7 +389,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                         const float sa = fmaf(wu, hprev[0][ch * 3 + 0], fmaf(wd, hc[ch * 3 + 0], hprev[1][ch * 3 + 0]));
                         const float sb = fmaf(wu, hprev[0][ch * 3 + 1], fmaf(wd, hc[ch * 3 + 1], hprev[1][ch * 3 + 1]));
                         const float sc = fmaf(wu, hprev[0][ch * 3 + 2], fmaf(wd, hc[ch * 3 + 2], hprev[1][ch * 3 + 2]));
-                        const float xv = pred[ch * FT_N2 + i2], yv = tgt[ch * FT_N2 + i2];
+                        const float xv = pred[ch * FT_N2 + i2], yv = tgt[ch * FT_NT + (r + 2) * FT_TP + oc + 2 + FT_TO];
                         const float d = xv - yv;
                         const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
                         const float g_pred = fmaf(sb, xv, fmaf(sc, yv, sa)) + gl1 * sg;
@@ -496,7 +501,7 @@ TmaEncodeFn tma_encoder() {
     return fn;
 }
 
-size_t fast_smem_bytes() { return sizeof(float) * (6 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
+size_t fast_smem_bytes() { return sizeof(float) * (3 * FT_NT + 3 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
 
 }  // namespace
 
@@ -540,7 +545,7 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     if (use_tma) {
         const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
-        const cuuint32_t box[4] = {FT_R2, FT_R2, 3, 1};
+        const cuuint32_t box[4] = {FT_TP, FT_R2, 3, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUresult r = tma_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(target), gdim, gstr,
                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
