@@ -68,6 +68,9 @@ SIGNATURES = {
                               _st]),
     "dmh_l0_finalize": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _f, _st]),
     "dmh_topk_select": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_hint_select_blocks": (_i, [_i, _i, _i]),
+    "dmh_hint_select": (_i, [C.POINTER(C.c_void_p), _i, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f,
+                             C.POINTER(C.c_void_p), _f, _f, _st]),
     "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
 }
 

@@ -1,0 +1,224 @@
+"""Depth-hints objective: host-side mirror of
+`DepthNetworks/depth-hints/trainer.py` -- `generate_images_pred` (:476-525, the
+extra depth-hint warp), `compute_loss_masks` (:541-590),
+`compute_proxy_supervised_loss` (:525-539) and the per-scale loop of
+`compute_losses` (:629-727).
+
+Differences of the depth-hints objective from monodepth2's (`objective.py`):
+  * the minimum over the source frames is taken first ("compute mins as we go",
+    :670-672, 683-685), ONE tie-break noise plane is added to the identity minimum;
+  * the per-pixel argmin runs over [reprojection, identity, depth-hint reprojection];
+    the reprojection loss is a MASKED mean  sum(l * m) / (sum(m) + 1e-7), m = argmin != identity;
+  * where the hint wins, log(|hint - depth| + 1) is added (masked mean again).
+
+Built from the op-level kernels (fused warp, SSIM+L1 reprojection loss, smoothness,
+bilinear up-sampling: `ops.py`) plus `dmh_hint_select`, which does the min / argmin /
+masks / both masked-sum numerators / proxy loss and their derivatives in one pass.
+CUDA tensors only -- no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import check, f32c, ptr, ptr_array, stream
+from .objective import _frame_T, tie_break_noise
+
+
+def _lib_():
+    return _lib.load()
+
+
+class _HintSelect(torch.autograd.Function):
+    """(reprojection loss, proxy loss, argmin) of one scale from the per-frame
+    reprojection losses [grad], the predicted depth [grad] and the constant maps."""
+
+    @staticmethod
+    def forward(ctx, ident, noise, hint_reproj, depth, hint_depth, hint_valid, avg, want_sel, *reproj):
+        rl = [f32c(t) for t in reproj]
+        F_ = len(rl)
+        B, _, H, W = rl[0].shape
+        dev = rl[0].device
+        idn = f32c(ident) if ident is not None else None
+        nz = f32c(noise) if noise is not None else None
+        hr = f32c(hint_reproj) if hint_reproj is not None else None
+        dp = f32c(depth) if hr is not None else None
+        hd = f32c(hint_depth) if hr is not None else None
+        hv = f32c(hint_valid) if hr is not None else None
+        lib = _lib_()
+        nblk = lib.dmh_hint_select_blocks(B, H, W)
+        part = torch.empty(4, nblk, device=dev, dtype=torch.float32)
+        g_rl = [torch.empty_like(t) for t in rl]
+        g_dp = torch.empty_like(dp) if hr is not None else None
+        sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None
+        check(lib.dmh_hint_select(ptr_array(rl), F_, ptr(idn), ptr(nz), ptr(hr), ptr(dp), ptr(hd), ptr(hv), int(avg),
+                                  B, H, W, ptr(part), ptr_array(g_rl), ptr(g_dp), ptr(sel), stream()), "hint_select")
+        sums = torch.empty(4, device=dev, dtype=torch.float32)
+        for k in range(4 if hr is not None else 2):
+            check(lib.dmh_reduce_sum(ptr(part[k]), nblk, 1.0, 0, ptr(sums[k:k + 1]), stream()), "reduce_sum")
+        inv_r = 1.0 / (sums[1] + 1e-7)
+        loss_r = sums[0] * inv_r
+        if hr is not None:
+            inv_h = 1.0 / (sums[3] + 1e-7)
+            loss_h = sums[2] * inv_h
+        else:
+            inv_h = torch.zeros((), device=dev)
+            loss_h = torch.zeros((), device=dev)
+        ctx.save_for_backward(inv_r, inv_h, g_dp, *g_rl)
+        ctx.n = F_
+        if sel is not None:
+            ctx.mark_non_differentiable(sel)
+        return loss_r, loss_h, sel
+
+    @staticmethod
+    def backward(ctx, g_r, g_h, _g_sel):
+        inv_r, inv_h, g_dp, *g_rl = ctx.saved_tensors
+        grads = [None] * 8
+        if ctx.needs_input_grad[3] and g_dp is not None and g_h is not None:
+            grads[3] = g_dp * (g_h * inv_h)
+        out = []
+        for i in range(ctx.n):
+            out.append(g_rl[i] * (g_r * inv_r) if (g_r is not None and ctx.needs_input_grad[8 + i]) else None)
+        return tuple(grads) + tuple(out)
+
+
+def hint_reprojection_loss(target, src, depth_hint, depth_hint_mask, K, inv_K, T, no_ssim=False):
+    """`DH/trainer.py:510-525` + `:629-634`: warp the stereo source with the depth
+    hint -- NOTE `F.grid_sample(..., padding_mode="border")` with the DEFAULT
+    align_corners (False), unlike the main warp -- then compute_reprojection_loss and
+    `+ 1000 * (1 - depth_hint_mask)`.  No gradient (inputs only)."""
+    with torch.no_grad():
+        B, _, H, W = target.shape
+        pts = ops._Backproject.apply(f32c(depth_hint), inv_K, B, H, W)
+        grid = ops._Project3D.apply(pts, K, T, B, H, W, 1e-7)
+        pred = ops.grid_sample(src, grid, padding_mode="border", align_corners=False)
+        loss = ops.reprojection_loss(pred, target, no_ssim)
+        loss = loss + 1000 * (1 - depth_hint_mask)
+    return loss, pred
+
+
+def depth_hint_losses(colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids, scales, height, width,
+                      depth_hint=None, depth_hint_mask=None, use_depth_hints=True, min_depth=0.1, max_depth=100.0,
+                      no_ssim=False, avg_reprojection=False, disable_automasking=False, disparity_smoothness=1e-3,
+                      noise: Optional[Dict] = None, noise_mode="reference", want_selection=False):
+    """Per-scale loop of the depth-hints `compute_losses` (`DH/trainer.py:636-727`).
+
+    colors / disps / Ts as in `objective.photometric_losses`; noise: optional
+    {scale: (B,1,H,W)} tie-break noise already * 1e-5; depth_hint, depth_hint_mask (B,1,H,W).
+    Returns (losses, aux) with the reference's keys: 'loss', 'loss/s', 'reproj_loss/s',
+    'depth_hint_loss/s'; aux: 'identity_selection/s', 'depth_hint_pixels/s' when requested."""
+    srcs_ids = list(frame_ids[1:])
+    target = colors[(0, 0)]
+    B = target.shape[0]
+    srcs = [colors[(f, 0)] for f in srcs_ids]
+    if use_depth_hints:
+        if "s" not in srcs_ids:
+            raise KeyError(("color_depth_hint", "s", 0))     # the reference only builds the hint warp for 's'
+        if disable_automasking:
+            # DH/trainer.py:554-555 evaluates `if depth_hint_reprojection_loss:` on a (B,1,H,W) tensor
+            raise RuntimeError("Boolean value of Tensor with more than one element is ambiguous")
+        hint_rl, hint_pred = hint_reprojection_loss(target, colors[("s", 0)], depth_hint, depth_hint_mask, K, inv_K,
+                                                    Ts["s"], no_ssim)
+    else:
+        hint_rl = hint_pred = None
+    ident = None
+    if not disable_automasking:
+        with torch.no_grad():
+            ident = torch.empty(B, len(srcs), height, width, device=target.device, dtype=torch.float32)
+            check(_lib_().dmh_identity_loss(ptr(f32c(target)), ptr_array([f32c(s) for s in srcs]), len(srcs), B, height,
+                                            width, int(no_ssim), ptr(ident), stream()), "identity_loss")
+    losses, aux = {}, {}
+    total = 0
+    for scale in scales:
+        disp = disps[scale]
+        disp_full = ops.upsample_bilinear(disp, (height, width)) if disp.shape[2] != height else disp
+        rl = []
+        for f, src in zip(srcs_ids, srcs):
+            pred = ops.warp_reproject(disp_full, src, K, inv_K, Ts[f], min_depth, max_depth)
+            rl.append(ops.reprojection_loss(pred, target, no_ssim))
+        _, depth = ops._DispToDepth.apply(disp_full, float(min_depth), float(max_depth))
+        nz = None
+        if ident is not None:
+            nz = noise[scale] if noise is not None else tie_break_noise((B, 1, height, width), target.device, noise_mode)
+        loss_r, loss_h, sel = _HintSelect.apply(ident, nz, hint_rl, depth, depth_hint, depth_hint_mask,
+                                                bool(avg_reprojection), bool(want_selection), *rl)
+        losses["reproj_loss/{}".format(scale)] = loss_r
+        loss = loss_r
+        if use_depth_hints:
+            losses["depth_hint_loss/{}".format(scale)] = loss_h
+            loss = loss + loss_h
+        if want_selection:
+            aux[("argmin", scale)] = sel
+            aux["identity_selection/{}".format(scale)] = (sel == 1).float().unsqueeze(1)
+            if use_depth_hints:
+                aux["depth_hint_pixels/{}".format(scale)] = (sel == 2).float().unsqueeze(1)
+        smooth = ops.smooth_loss(disp, colors[(0, scale)], normalise=True)
+        loss = loss + disparity_smoothness * smooth / (2 ** scale)
+        losses["loss/{}".format(scale)] = loss
+        total = total + loss
+    total = total / len(scales)
+    losses["loss"] = total
+    if hint_pred is not None:
+        aux[("color_depth_hint", "s", 0)] = hint_pred
+    return losses, aux
+
+
+# ----------------------------------------------------------------------------- Trainer patches (depth-hints trainer)
+def dh_generate_images_pred(self, inputs, outputs):
+    """Replacement for the depth-hints `Trainer.generate_images_pred`: only the depth
+    maps (read by `compute_depth_losses`) are produced; warps happen inside the loss."""
+    opt = self.opt
+    if opt.v1_multiscale or getattr(opt, "pose_model_type", "") == "posecnn" or opt.predictive_mask:
+        return self._dmh_ref_generate_images_pred(inputs, outputs)
+    import torch.nn.functional as F
+    for scale in opt.scales:
+        with torch.no_grad():
+            disp_full = F.interpolate(outputs[("disp", scale)], [opt.height, opt.width], mode="bilinear",
+                                      align_corners=False)
+            _, depth = ops.disp_to_depth_cuda(disp_full, opt.min_depth, opt.max_depth)
+        outputs[("depth", 0, scale)] = depth
+
+
+def dh_compute_losses(self, inputs, outputs):
+    """Replacement for the depth-hints `Trainer.compute_losses` (`DH/trainer.py:592-729`)."""
+    opt = self.opt
+    if opt.v1_multiscale or getattr(opt, "pose_model_type", "") == "posecnn" or opt.predictive_mask:
+        return self._dmh_ref_compute_losses(inputs, outputs)
+    losses = {}
+    total_loss = 0
+    if opt.adv_train and opt.supervised_adv:               # network-side terms: stock PyTorch (:597-611)
+        with torch.no_grad():
+            disp_gt = self.gt_model(inputs[("color_ben", 0, 0)])
+        loss_sup = self.sup_loss_creteria(disp_gt, outputs[("disp", 0)])
+        losses["sup_loss"] = loss_sup
+        total_loss = total_loss + loss_sup
+    if opt.adv_train and opt.contrastive_learning:         # (:613-624)
+        contras_loss = self.models["contrastive_learning"](outputs["middle_features_aug"],
+                                                           outputs["middle_features_ben"]) * 0.1
+        losses["contras_loss"] = contras_loss
+        total_loss = total_loss + contras_loss
+    if opt.adv_train and opt.no_original_train:
+        losses["loss"] = total_loss
+        return losses
+    colors = {(0, s): inputs[("color", 0, s)] for s in opt.scales}
+    Ts = {}
+    for f in opt.frame_ids[1:]:
+        colors[(f, 0)] = inputs[("color", f, 0)]
+        Ts[f] = _frame_T(opt, inputs, outputs, f)
+    disps = {s: outputs[("disp", s)] for s in opt.scales}
+    pl, aux = depth_hint_losses(colors, disps, inputs[("K", 0)], inputs[("inv_K", 0)], Ts, opt.frame_ids, opt.scales,
+                                opt.height, opt.width, inputs.get("depth_hint"), inputs.get("depth_hint_mask"),
+                                bool(opt.use_depth_hints), opt.min_depth, opt.max_depth, bool(opt.no_ssim),
+                                bool(opt.avg_reprojection), bool(opt.disable_automasking), opt.disparity_smoothness,
+                                noise=getattr(self, "_dmh_noise", None),
+                                noise_mode=getattr(self, "_dmh_noise_mode", "reference"), want_selection=True)
+    for k, v in aux.items():
+        if isinstance(k, str):
+            outputs[k] = v
+    for k, v in pl.items():
+        if k != "loss":
+            losses[k] = v
+    losses["loss"] = total_loss + pl["loss"]
+    return losses

@@ -15,6 +15,7 @@ from __future__ import annotations
 import sys
 
 from . import attacks as _attacks
+from . import depth_hints as _depth_hints
 from . import layers as _layers
 from . import objective as _objective
 from . import physical as _physical
@@ -96,8 +97,14 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
         T.compute_reprojection_loss = _layers.compute_reprojection_loss
         done[mod_name + ".Trainer.compute_reprojection_loss"] = True
         if mode == "fused":
-            T.generate_images_pred = _objective.fused_generate_images_pred
-            T.compute_losses = _objective.fused_compute_losses
+            if hasattr(T, "compute_loss_masks"):
+                # the depth-hints trainer (DH/trainer.py:541): masked-mean objective + depth-hint terms
+                T.generate_images_pred = _depth_hints.dh_generate_images_pred
+                T.compute_losses = _depth_hints.dh_compute_losses
+                done[mod_name + ".Trainer.compute_losses(depth-hints)"] = True
+            else:
+                T.generate_images_pred = _objective.fused_generate_images_pred
+                T.compute_losses = _objective.fused_compute_losses
             done[mod_name + ".Trainer.compute_losses"] = True
     return done
 

@@ -111,7 +111,7 @@ class PhotoBatch:
 
 
 def photo_batch(batch=4, height=192, width=640, frame_ids: Sequence = (0, "s"), scales=(0, 1, 2, 3),
-                disp_kind="realistic", image_kind="smooth", seed=0) -> PhotoBatch:
+                disp_kind="realistic", image_kind="smooth", seed=0, depth_hints=False) -> PhotoBatch:
     frame_ids = list(frame_ids)
     scales = list(scales)
     color = {}
@@ -146,7 +146,16 @@ def photo_batch(batch=4, height=192, width=640, frame_ids: Sequence = (0, "s"), 
             T[f] = temporal_T(batch, seed + 500 + 7 * int(f))
     nf = len(frame_ids) - 1
     noise = {s: (randn((batch, nf, height, width), seed + 600 + s) * 0.00001).contiguous() for s in scales}
-    return PhotoBatch(batch, height, width, frame_ids, scales, color, disp, K, inv_K, T, noise)
+    pb = PhotoBatch(batch, height, width, frame_ids, scales, color, disp, K, inv_K, T, noise)
+    if depth_hints:
+        # depth_hint = depth(disp_0) * (1 + 0.1 N(0,1)), valid mask ~ Bernoulli(0.8)
+        # (DH/datasets/mono_dataset.py:367-388 loads both as (1,H,W) float maps)
+        d0 = F.interpolate(disp[scales[0]], size=(height, width), mode="bilinear", align_corners=False)
+        depth = 1.0 / (1.0 / pb.max_depth + (1.0 / pb.min_depth - 1.0 / pb.max_depth) * d0)
+        hint = (depth * (1.0 + 0.1 * randn(depth.shape, seed + 950))).clamp_(min=1e-3)
+        pb.extras["depth_hint"] = hint.contiguous()
+        pb.extras["depth_hint_mask"] = (rand(depth.shape, seed + 951) < 0.8).float().contiguous()
+    return pb
 
 
 def ellipse_mask(h=PATCH_H, w=PATCH_W) -> torch.Tensor:

@@ -246,6 +246,22 @@ int dmh_l0_finalize(const float* obj, const float* pattern_pos, const float* pat
 int dmh_topk_select(float* pattern_pos, float* pattern_neg, int C, int H, int W, int k, unsigned char* keep,
                     unsigned* kth_key, dmh_stream_t stream);
 
+/* -- A18 depth-hints objective, per scale (DepthNetworks/depth-hints/trainer.py:541-590
+ * compute_loss_masks, :525-539 compute_proxy_supervised_loss, :666-713):
+ * reproj_host[f] (B,1,H,W) per-frame reprojection losses, f < F <= 4; ident (B,F,H,W)
+ * identity losses WITHOUT noise (NULL: automasking disabled); noise (B,1,H,W) nullable;
+ * hint_reproj (B,1,H,W) = reprojection loss of the depth-hint warp + 1000*(1-hint_valid)
+ * (NULL: no depth hints); depth = predicted depth, hint_depth, hint_valid (B,1,H,W).
+ * Outputs: part = 4 x dmh_hint_select_blocks floats: per-CTA partial sums of
+ *   [reproj*mask_r, mask_r, proxy*mask_h, mask_h]  (mask_r = argmin != identity,
+ *   mask_h = argmin == hint); g_reproj_host[f] (B,1,H,W) = d(sum reproj*mask_r)/d reproj_f;
+ *   g_depth (B,1,H,W) = d(sum proxy*mask_h)/d depth; sel (B,H,W) argmin index (nullable). */
+int dmh_hint_select_blocks(int B, int H, int W);
+int dmh_hint_select(const float* const* reproj_host, int F, const float* ident, const float* noise,
+                    const float* hint_reproj, const float* depth, const float* hint_depth, const float* hint_valid,
+                    int avg_reprojection, int B, int H, int W, float* part, float* const* g_reproj_host,
+                    float* g_depth, unsigned char* sel, dmh_stream_t stream);
+
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);
