@@ -403,6 +403,25 @@ def main():
                        "from pinned host memory every step on a copy stream, double-buffered against the previous "
                        "step's compute; tie-break noise drawn on the device; loss read back every step"}
 
+    # DRAM traffic and instruction count of the dominant kernel per launch: from the committed `ncu --set full`
+    # capture of this same command (profiles/r01_ncu_full_j.txt; mean of the 4 per-scale launches at B=32)
+    ncu_traffic = 380.1e6 if (B == 32 and F == 1) else None
+    ncu_warp_inst = 366.9e6 if (B == 32 and F == 1) else None
+    sm_clock_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA> (dmh_photo_scale, one launch per scale)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "traffic": ncu_traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                "kernel_ms": kms, "kernel_launches_timed": len(kt), "algorithmic_bytes_per_launch": k_bytes,
+                "step_algorithmic_bytes": step_bytes_total,
+                "step_hbm_frac": step_bytes_total / (ms_step * 1e-3) / 1e9 / peak,
+                "note": "traffic == algorithmic bytes (no re-reads) but the kernel is fp32 instruction-issue bound, "
+                        "not HBM bound: see issue_frac"}
+    if ncu_warp_inst and kms > 0:
+        # fraction of the SM issue slots (148 SMs x 4 schedulers x 1 warp-instruction / clock) the kernel uses
+        roofline["issue_frac"] = ncu_warp_inst / (kms * 1e-3) / (148 * 4 * sm_clock_hz)
+        roofline["warp_instructions_per_launch"] = ncu_warp_inst
+
     line = {
         "metric": METRIC, "value": world * B * H * W / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -418,12 +437,7 @@ def main():
         "stages": {"photometric_ms": ms_s2, "patch_pgd_ms": ms_s1,
                    "pgd_steps_per_s": (1e3 / ms_s1) if ms_s1 else None,
                    "photometric_mpix_per_s": world * B * H * W / (ms_s2 * 1e-3) / 1e6},
-        "roofline": {"bound": "hbm", "kernel": "photo_scale_kernel<1>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                     "kernel_ms": kms, "kernel_launches_timed": len(kt), "algorithmic_bytes_per_launch": k_bytes,
-                     "step_algorithmic_bytes": step_bytes_total,
-                     "step_hbm_frac": step_bytes_total / (ms_step * 1e-3) / 1e9 / peak},
+        "roofline": roofline,
     }
     if e2e is not None:
         line["e2e"] = e2e
