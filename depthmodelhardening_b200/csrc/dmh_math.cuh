@@ -253,41 +253,19 @@ DMH_HD int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i 
 
 
 // ---------------------------------------------------------------------------
-// Fast-path variants used by the fused F=1 kernel (photo_fast.cu): separable
-// 3x3 sums (row sums of 3, then 3 rows), FMA-contracted products, mean = sum*(1/9).
-// Same mathematics as ssim_stats(); rounding differs at the 1e-7 level.
-struct Row5 { float x, y, xx, yy, xy; };
-
-DMH_HD Row5 row5(float x0, float x1, float x2, float y0, float y1, float y2) {
-    Row5 r;
-    r.x = (x0 + x1) + x2;
-    r.y = (y0 + y1) + y2;
-    r.xx = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
-    r.yy = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
-    r.xy = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
-    return r;
-}
-
-DMH_HD SsimStats ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) {
-    const float inv9 = 1.0f / 9.0f;
-    SsimStats s;
-    s.mu_x = ((a.x + b.x) + c.x) * inv9;
-    s.mu_y = ((a.y + b.y) + c.y) * inv9;
-    const float exx = ((a.xx + b.xx) + c.xx) * inv9;
-    const float eyy = ((a.yy + b.yy) + c.yy) * inv9;
-    const float exy = ((a.xy + b.xy) + c.xy) * inv9;
-    const float mxx = s.mu_x * s.mu_x, myy = s.mu_y * s.mu_y, mxy = s.mu_x * s.mu_y;
-    const float sig_x = exx - mxx, sig_y = eyy - myy, sig_xy = exy - mxy;
-    s.A1 = fmaf(2.0f, mxy, DMH_SSIM_C1);
-    s.A2 = fmaf(2.0f, sig_xy, DMH_SSIM_C2);
-    s.B1 = (mxx + myy) + DMH_SSIM_C1;
-    s.B2 = (sig_x + sig_y) + DMH_SSIM_C2;
-    s.n = s.A1 * s.A2;
-    s.d = s.B1 * s.B2;
-    return s;
-}
-
-// value + coefficients sharing one reciprocal of d
+// Fast-path SSIM used by the fused kernels (photo_fast.cu, photo_objective.cu, identity loss): separable
+// 3x3 sums (row sums of 3, then 3 rows), mean = sum*(1/9).  Same mathematics as ssim_stats(); rounding differs
+// at the 1e-7 level.  Written once over a lane type T with an EXPLICIT op sequence (no compiler contraction):
+//   T = float   one pixel / channel per lane (host emulation and every kernel)
+//   T = float2  two channels per lane on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one issue slot
+//               for two results -- these kernels are issue-bound, not FMA-pipe bound); each half is
+//               rounded exactly like the scalar instantiation, so both give bit-identical values.
+DMH_HD float vadd(float a, float b) { return add_rn(a, b); }
+DMH_HD float vsub(float a, float b) { return sub_rn(a, b); }
+DMH_HD float vmul(float a, float b) { return mul_rn(a, b); }
+DMH_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+DMH_HD float vclamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+DMH_HD float vpass01(float v) { return (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f; }
 // reciprocal of the SSIM denominator d = B1*B2 >= C1*C2 > 0: MUFU.RCP (2 ulp) on the device -- the error it
 // adds to the SSIM value is ~1e-7, far below the 1e-5 tolerance; IEEE division on the host emulation
 #if defined(__CUDA_ARCH__)
@@ -295,20 +273,110 @@ DMH_HD float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f
 #else
 DMH_HD float fast_rcp(float x) { return 1.0f / x; }
 #endif
+DMH_HD float vrcp(float x) { return fast_rcp(x); }
+template <class T> struct Lane;
+template <> struct Lane<float> { static DMH_HD float splat(float v) { return v; } };
+#if defined(__CUDACC__)
+DMH_HD float2 vadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+DMH_HD float2 vsub(float2 a, float2 b) { return vadd(a, make_float2(-b.x, -b.y)); }
+DMH_HD float2 vmul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+DMH_HD float2 vfma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+DMH_HD float2 vclamp01(float2 v) { return make_float2(vclamp01(v.x), vclamp01(v.y)); }
+DMH_HD float2 vpass01(float2 v) { return make_float2(vpass01(v.x), vpass01(v.y)); }
+DMH_HD float2 vrcp(float2 x) { return make_float2(fast_rcp(x.x), fast_rcp(x.y)); }
+template <> struct Lane<float2> { static DMH_HD float2 splat(float v) { return make_float2(v, v); } };
+#endif
 
+template <class T> struct Row5T { T x, y, xx, yy, xy; };
+typedef Row5T<float> Row5;
+
+template <class T>
+DMH_HD Row5T<T> row5(T x0, T x1, T x2, T y0, T y1, T y2) {
+    Row5T<T> r;
+    r.x = vadd(vadd(x0, x1), x2);
+    r.y = vadd(vadd(y0, y1), y2);
+    r.xx = vfma(x2, x2, vfma(x1, x1, vmul(x0, x0)));
+    r.yy = vfma(y2, y2, vfma(y1, y1, vmul(y0, y0)));
+    r.xy = vfma(x2, y2, vfma(x1, y1, vmul(x0, y0)));
+    return r;
+}
+
+template <class T> struct SsimStatsT { T mu_x, mu_y, A1, A2, B1, B2, n, d; };
+
+template <class T>
+DMH_HD SsimStatsT<T> ssim_stats_rows_t(const Row5T<T>& a, const Row5T<T>& b, const Row5T<T>& c) {
+    const T inv9 = Lane<T>::splat(1.0f / 9.0f), two = Lane<T>::splat(2.0f);
+    const T c1 = Lane<T>::splat(DMH_SSIM_C1), c2 = Lane<T>::splat(DMH_SSIM_C2);
+    SsimStatsT<T> s;
+    s.mu_x = vmul(vadd(vadd(a.x, b.x), c.x), inv9);
+    s.mu_y = vmul(vadd(vadd(a.y, b.y), c.y), inv9);
+    const T exx = vmul(vadd(vadd(a.xx, b.xx), c.xx), inv9);
+    const T eyy = vmul(vadd(vadd(a.yy, b.yy), c.yy), inv9);
+    const T exy = vmul(vadd(vadd(a.xy, b.xy), c.xy), inv9);
+    const T mxx = vmul(s.mu_x, s.mu_x), myy = vmul(s.mu_y, s.mu_y), mxy = vmul(s.mu_x, s.mu_y);
+    const T sig_x = vsub(exx, mxx), sig_y = vsub(eyy, myy), sig_xy = vsub(exy, mxy);
+    s.A1 = vfma(two, mxy, c1);
+    s.A2 = vfma(two, sig_xy, c2);
+    s.B1 = vadd(vadd(mxx, myy), c1);
+    s.B2 = vadd(vadd(sig_x, sig_y), c2);
+    s.n = vmul(s.A1, s.A2);
+    s.d = vmul(s.B1, s.B2);
+    return s;
+}
+
+// dS/dx_k = ax + b*x_k + c*y_k   and   dS/dy_k = ay + b*y_k + c*x_k  (see ssim_coef above)
+template <class T> struct SsimCoefT { T ax, ay, b, c; };
+
+// value + coefficients sharing one reciprocal of d; `pass` = 1 where the clamp passes gradient
+template <class T>
+DMH_HD T ssim_value_coef_t(const SsimStatsT<T>& s, T& pass, SsimCoefT<T>& k) {
+    const T one = Lane<T>::splat(1.0f), half = Lane<T>::splat(0.5f);
+    const T inv9 = Lane<T>::splat(1.0f / 9.0f), ninv9 = Lane<T>::splat(-1.0f / 9.0f);
+    const T r = vrcp(s.d);
+    const T nr = vmul(s.n, r);
+    const T v = vmul(vsub(one, nr), half);
+    pass = vpass01(v);
+    const T nr2 = vmul(nr, r);
+    const T dA = vmul(vsub(s.A2, s.A1), r), dB = vmul(nr2, vsub(s.B2, s.B1));
+    k.ax = vmul(ninv9, vsub(vmul(s.mu_y, dA), vmul(s.mu_x, dB)));
+    k.ay = vmul(ninv9, vsub(vmul(s.mu_x, dA), vmul(s.mu_y, dB)));
+    k.b = vmul(vmul(inv9, nr2), s.B1);
+    k.c = vmul(vmul(ninv9, s.A1), r);
+    return vclamp01(v);
+}
+
+// scalar entry points (names used by the kernels and by tests/host_emul.cpp)
+DMH_HD SsimStats ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) {
+    const SsimStatsT<float> t = ssim_stats_rows_t<float>(a, b, c);
+    SsimStats s;
+    s.mu_x = t.mu_x; s.mu_y = t.mu_y; s.A1 = t.A1; s.A2 = t.A2; s.B1 = t.B1; s.B2 = t.B2; s.n = t.n; s.d = t.d;
+    return s;
+}
 DMH_HD float ssim_value_coef(const SsimStats& s, float& pass, SsimCoef& k) {
-    const float r = fast_rcp(s.d);
-    const float nr = s.n * r;
-    const float v = (1.0f - nr) * 0.5f;
-    pass = (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f;
-    const float nr2 = nr * r;
-    const float inv9 = 1.0f / 9.0f;
-    const float dA = (s.A2 - s.A1) * r, dB = nr2 * (s.B2 - s.B1);
-    k.ax = -inv9 * (s.mu_y * dA - s.mu_x * dB);
-    k.ay = -inv9 * (s.mu_x * dA - s.mu_y * dB);
-    k.b = inv9 * nr2 * s.B1;
-    k.c = -inv9 * s.A1 * r;
-    return fminf(fmaxf(v, 0.0f), 1.0f);
+    SsimStatsT<float> t;
+    t.mu_x = s.mu_x; t.mu_y = s.mu_y; t.A1 = s.A1; t.A2 = s.A2; t.B1 = s.B1; t.B2 = s.B2; t.n = s.n; t.d = s.d;
+    SsimCoefT<float> kt;
+    const float v = ssim_value_coef_t<float>(t, pass, kt);
+    k.ax = kt.ax; k.ay = kt.ay; k.b = kt.b; k.c = kt.c;
+    return v;
 }
 
 // d(grad_disp)/d(g_ix, g_iy): warp_coord_bwd collapsed to two scalars

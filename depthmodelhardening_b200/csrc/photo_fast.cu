@@ -105,32 +105,53 @@ __device__ __forceinline__ int ext_to_img(int e, int n) {
 
 struct Gathered { float v[3]; float dix[3], diy[3]; };
 
-// bilinear gather of 3 channels at (wc.ix, wc.iy) + d(value)/d(ix,iy)
-__device__ __forceinline__ Gathered gather3(const float* __restrict__ sp, size_t N, const WarpCoord& wc, int H, int W,
-                                            bool want_grad) {
+// The four bilinear taps of one sampling position.  With border padding the clipped coordinate lies in
+// [0, W-1] x [0, H-1], so the north-west tap is always inside the image; the east / south taps fall outside
+// only when the coordinate sits exactly on the last column / row, where their weight (tx0 / ty0) is 0 and
+// ATen's gradient gate (clip_coordinates_set_grad) is 0 as well.  Those taps are therefore CLAMPED onto the
+// last column / row (dx = 0 / dy = 0): every load is unconditional and in bounds, no predicates.
+struct Tap {
+    int o, dx, dy;               // offset of the north-west tap; +dx -> east, +dy -> south
+    float tx0, tx1, ty0, ty1;    // (ix - ix_nw), (ix_se - ix), (iy - iy_nw), (iy_se - iy)
+};
+
+__device__ __forceinline__ Tap make_tap(const WarpCoord& wc, int H, int W) {
     const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
-    const bool x0in = bl.x0 >= 0 && bl.x0 < W, x1in = bl.x0 + 1 >= 0 && bl.x0 + 1 < W;
-    const bool y0in = bl.y0 >= 0 && bl.y0 < H, y1in = bl.y0 + 1 >= 0 && bl.y0 + 1 < H;
-    const long long o = (long long)bl.y0 * W + bl.x0;
+    Tap t;
+    t.o = bl.y0 * W + bl.x0;
+    t.dx = (bl.x0 + 1 < W) ? 1 : 0;
+    t.dy = (bl.y0 + 1 < H) ? W : 0;
+    t.tx0 = bl.tx0; t.tx1 = bl.tx1; t.ty0 = bl.ty0; t.ty1 = bl.ty1;
+    return t;
+}
+
+// bilinear gather of 3 channels + d(value)/d(ix,iy)
+__device__ __forceinline__ Gathered gather_taps(const float* __restrict__ sp, size_t N, const Tap& t, bool want_grad) {
+    const float wnw = t.tx1 * t.ty1, wne = t.tx0 * t.ty1, wsw = t.tx1 * t.ty0, wse = t.tx0 * t.ty0;
     Gathered g;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float* s = sp + ch * N;
-        const float nw = (y0in && x0in) ? __ldg(s + o) : 0.f;
-        const float ne = (y0in && x1in) ? __ldg(s + o + 1) : 0.f;
-        const float sw = (y1in && x0in) ? __ldg(s + o + W) : 0.f;
-        const float se = (y1in && x1in) ? __ldg(s + o + W + 1) : 0.f;
-        float acc = nw * bl.wnw;
-        acc = fmaf(ne, bl.wne, acc);
-        acc = fmaf(sw, bl.wsw, acc);
-        acc = fmaf(se, bl.wse, acc);
+        const float* s = sp + ch * N + t.o;
+        const float nw = __ldg(s), ne = __ldg(s + t.dx), sw = __ldg(s + t.dy), se = __ldg(s + t.dy + t.dx);
+        float acc = nw * wnw;
+        acc = fmaf(ne, wne, acc);
+        acc = fmaf(sw, wsw, acc);
+        acc = fmaf(se, wse, acc);
         g.v[ch] = acc;
         if (want_grad) {
-            g.dix[ch] = (ne - nw) * bl.ty1 + (se - sw) * bl.ty0;
-            g.diy[ch] = (sw - nw) * bl.tx1 + (se - ne) * bl.tx0;
+            g.dix[ch] = (ne - nw) * t.ty1 + (se - sw) * t.ty0;
+            g.diy[ch] = (sw - nw) * t.tx1 + (se - ne) * t.tx0;
         }
     }
     return g;
+}
+
+// position (r, c) in the 36 x 36 frame of halo-ring pixel h < 272: 2 top rows, 2 bottom rows, 2 left / right columns
+__device__ __forceinline__ void halo_rc(int h, int& r, int& c) {
+    if (h < 72) { r = h / FT_R2; c = h - r * FT_R2; }
+    else if (h < 144) { const int t = h - 72; r = FT_R2 - 2 + t / FT_R2; c = t % FT_R2; }
+    else if (h < 208) { const int t = h - 144; r = 2 + (t >> 1); c = t & 1; }
+    else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
 }
 
 template <bool TMA>
@@ -140,8 +161,9 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     __shared__ __align__(8) uint64_t tgt_bar;
     float* tgt = smem;                       // [3][36][40] (TMA destination: 128-byte aligned)
     float* pred = tgt + 3 * FT_NT;           // [3][N2]
-    float* coef = pred + 3 * FT_N2;          // [9][N1]: (a,b,c) x 3 channels, gated
-    float* cams = coef + 9 * FT_N1;          // [24]
+    float2* coefP = reinterpret_cast<float2*>(pred + 3 * FT_N2);   // [3][N1] float2: (a,b,c) of channels (0,1), gated
+    float* coefS = reinterpret_cast<float*>(coefP + 3 * FT_N1);    // [3][N1]: (a,b,c) of channel 2
+    float* cams = coefS + 3 * FT_N1;         // [24]
     float* red = cams + 24;                  // [32]
     uint8_t* gate = reinterpret_cast<uint8_t*>(red + 32);   // [N1]
 
@@ -194,43 +216,64 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     for (int i = 0; i < 9; ++i) cam.iK[i] = cams[12 + i];
     const float* sp = p.src + (size_t)b * 3 * N;
 
-    // ---- phase A: warp.  Owned interior pixels: column tid%32, rows 4*(tid/32)+k
+    // ---- phase A: warp.  A thread owns the interior pixels of column tid%32, rows 4*(tid/32)+k, plus one pixel
+    // of the halo ring.  Software-pipelined over those 5 pixels: all disparity loads, then the coordinate chains,
+    // then the gathers -- the memory latency is paid once per stage instead of once per pixel.
     const int oc = tid & 31, os = tid >> 5;
     float D[4][3];
+    {
+        int hr, hc;
+        halo_rc(tid, hr, hc);
+        int py[5], pxx[5];
+        const int ixo = ext_to_img(x0 + oc, W);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = 4 * os + k;
-        const int iy = ext_to_img(y0 + r, H), ix = ext_to_img(x0 + oc, W);
-        const float dv = load_disp(p.disp, b, iy, ix, H, W);
-        const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
-        const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
-        const Gathered g = gather3(sp, N, wc, H, W, true);
-        float ax, ay;
-        warp_chain_factors(cam, wc, W, H, ax, ay);
-        const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
-        const int i2 = (r + 2) * FT_R2 + oc + 2;
+        for (int k = 0; k < 4; ++k) { py[k] = ext_to_img(y0 + 4 * os + k, H); pxx[k] = ixo; }
+        py[4] = ext_to_img(y0 - 2 + hr, H);
+        pxx[4] = ext_to_img(x0 - 2 + hc, W);
+        float dv[5];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            pred[ch * FT_N2 + i2] = g.v[ch];
-            D[k][ch] = (g.dix[ch] * ax + g.diy[ch] * ay) * dd;
+        for (int k = 0; k < 5; ++k) dv[k] = load_disp(p.disp, b, py[k], pxx[k], H, W);
+        Tap tp[5];
+        float gax[4], gay[4];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float depth = is_depth ? dv[k] : disp_to_depth(dv[k], p.ds);
+            const WarpCoord wc = warp_coord(cam, (float)pxx[k], (float)py[k], depth, W, H, 1e-7f);
+            tp[k] = make_tap(wc, H, W);
+            if (k < 4) {
+                float ax, ay;
+                warp_chain_factors(cam, wc, W, H, ax, ay);
+                const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
+                gax[k] = ax * dd; gay[k] = ay * dd;
+            }
         }
-        if (p.warped && y0 + r < H && x0 + oc < W) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+        for (int k = 0; k < 5; ++k) {
+            const Gathered g = gather_taps(sp, N, tp[k], k < 4);
+            const int r = 4 * os + k;
+            const int i2 = (k < 4) ? (r + 2) * FT_R2 + oc + 2 : hr * FT_R2 + hc;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + i2] = g.v[ch];
+            if (k < 4) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) D[k][ch] = g.dix[ch] * gax[k] + g.diy[ch] * gay[k];
+                if (p.warped && y0 + r < H && x0 + oc < W) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+                }
+            }
         }
     }
-    // halo ring of the pred tile: 2 top rows, 2 bottom rows, 2 left cols, 2 right cols = 272 pixels
-    for (int h = tid; h < 272; h += FT_THREADS) {
+    // the remaining 16 pixels of the halo ring
+    if (tid < 272 - FT_THREADS) {
         int r, c;
-        if (h < 72) { r = h / FT_R2; c = h - r * FT_R2; }
-        else if (h < 144) { const int t = h - 72; r = FT_R2 - 2 + t / FT_R2; c = t % FT_R2; }
-        else if (h < 208) { const int t = h - 144; r = 2 + (t >> 1); c = t & 1; }
-        else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
+        halo_rc(tid + FT_THREADS, r, c);
         const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
-        const float dv = load_disp(p.disp, b, iy, ix, H, W);
-        const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
+        const float dvh = load_disp(p.disp, b, iy, ix, H, W);
+        const float depth = is_depth ? dvh : disp_to_depth(dvh, p.ds);
         const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
-        const Gathered g = gather3(sp, N, wc, H, W, false);
+        const Gathered g = gather_taps(sp, N, make_tap(wc, H, W), false);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + r * FT_R2 + c] = g.v[ch];
     }
@@ -272,54 +315,68 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         }
     }
 
-    // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients
+    // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients.
+    // Channels 0 and 1 ride in the two halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2), channel 2 is scalar.
     float loss_local = 0.0f;
     if (tid < FT_R1 * FT_STRIPS) {
         const int c = tid % FT_R1, strip = tid / FT_R1;
         const int r0 = strip * FT_ROWS;                 // first ring row of this strip == first R2 row of its window
         const int qx = x0 - 1 + c;
         const bool col_ok = qx >= 0 && qx < W;
-        Row5 hist[3][2];                                // [channel][older, newer] row sums
-        float cen_x[3], cen_y[3];                       // centre values of the previous row
+        Row5T<float2> histP[2];                         // channels (0,1): [older, newer] row sums
+        Row5T<float> histS[2];                          // channel 2
+        float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;   // centre values of the previous row
+        float cenxS = 0.f, cenyS = 0.f;
+        const float2 w_ssim2 = make_float2(w_ssim, w_ssim);
 #pragma unroll
         for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
             const int r2 = r0 + rr;                     // R2 row being added
-            Row5 cur[3];
-            float mid_x[3], mid_y[3];
+            Row5T<float2> curP;
+            Row5T<float> curS;
+            float2 midxP = make_float2(0.f, 0.f), midyP = midxP;
+            float midxS = 0.f, midyS = 0.f;
             if (r2 < FT_R2) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float* xs = pred + ch * FT_N2 + r2 * FT_R2 + c;
-                    const float* ys = tgt + ch * FT_NT + r2 * FT_TP + c + FT_TO;
-                    const float xa = xs[0], xb = xs[1], xc = xs[2], ya = ys[0], yb = ys[1], yc = ys[2];
-                    cur[ch] = row5(xa, xb, xc, ya, yb, yc);
-                    mid_x[ch] = xb; mid_y[ch] = yb;
-                }
+                const float* xs = pred + r2 * FT_R2 + c;
+                const float* ys = tgt + r2 * FT_TP + c + FT_TO;
+                const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
+                             xc = make_float2(xs[2], xs[FT_N2 + 2]);
+                const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
+                             yc = make_float2(ys[2], ys[FT_NT + 2]);
+                curP = row5(xa, xb, xc, ya, yb, yc);
+                midxP = xb; midyP = yb;
+                const float* x2 = xs + 2 * FT_N2;
+                const float* y2 = ys + 2 * FT_NT;
+                curS = row5(x2[0], x2[1], x2[2], y2[0], y2[1], y2[2]);
+                midxS = x2[1]; midyS = y2[1];
             }
             if (rr >= 2) {
                 const int qr = r0 + rr - 2;             // ring row of the window centre
                 const int qy = y0 - 1 + qr;
                 if (qr < FT_R1) {
                     const int qi = qr * FT_R1 + c;
-                    float ka[3] = {0.f, 0.f, 0.f}, kb[3] = {0.f, 0.f, 0.f}, kc[3] = {0.f, 0.f, 0.f};
+                    float2 kaP = make_float2(0.f, 0.f), kbP = kaP, kcP = kaP;
+                    float kaS = 0.f, kbS = 0.f, kcS = 0.f;
                     uint8_t gt = 0;
                     if (col_ok && qy >= 0 && qy < H) {
-                        float l1 = 0.f, ss = 0.f;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            l1 += fabsf(cen_y[ch] - cen_x[ch]);
-                            if (!no_ssim) {
-                                const SsimStats st = ssim_stats_rows(hist[ch][0], hist[ch][1], cur[ch]);
-                                float pass;
-                                SsimCoef k;
-                                ss += ssim_value_coef(st, pass, k);
-                                const float g = w_ssim * pass;
-                                ka[ch] = g * k.ax; kb[ch] = g * k.b; kc[ch] = g * k.c;
-                            }
+                        float l1 = fabsf(cenyP.x - cenxP.x);
+                        l1 += fabsf(cenyP.y - cenxP.y);
+                        l1 += fabsf(cenyS - cenxS);
+                        float ss = 0.f;
+                        if (!no_ssim) {
+                            float2 passP;
+                            SsimCoefT<float2> kP;
+                            const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
+                            float passS;
+                            SsimCoefT<float> kS;
+                            const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
+                            ss = (vP.x + vP.y) + vS;
+                            const float2 gP = vmul(w_ssim2, passP);
+                            kaP = vmul(gP, kP.ax); kbP = vmul(gP, kP.b); kcP = vmul(gP, kP.c);
+                            const float gS = w_ssim * passS;
+                            kaS = gS * kS.ax; kbS = gS * kS.b; kcS = gS * kS.c;
                         }
                         l1 *= (1.0f / 3.0f);
                         const float rp = no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
-                        const size_t qo = (size_t)qy * W + qx;
                         float best = rp;
                         int best_idx = 0;
                         bool win = true;
@@ -331,29 +388,22 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                         }
                         gt = win ? 1 : 0;
                         if (!win) {
-#pragma unroll
-                            for (int ch = 0; ch < 3; ++ch) { ka[ch] = 0.f; kb[ch] = 0.f; kc[ch] = 0.f; }
+                            kaP = make_float2(0.f, 0.f); kbP = kaP; kcP = kaP;
+                            kaS = 0.f; kbS = 0.f; kcS = 0.f;
                         }
                         if (qr >= 1 && qr <= FT_T && c >= 1 && c <= FT_T) {
                             loss_local += best;
-                            if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)best_idx;
+                            if (p.sel) p.sel[(size_t)b * N + (size_t)qy * W + qx] = (uint8_t)best_idx;
                         }
                     }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        coef[(ch * 3 + 0) * FT_N1 + qi] = ka[ch];
-                        coef[(ch * 3 + 1) * FT_N1 + qi] = kb[ch];
-                        coef[(ch * 3 + 2) * FT_N1 + qi] = kc[ch];
-                    }
+                    coefP[0 * FT_N1 + qi] = kaP; coefP[1 * FT_N1 + qi] = kbP; coefP[2 * FT_N1 + qi] = kcP;
+                    coefS[0 * FT_N1 + qi] = kaS; coefS[1 * FT_N1 + qi] = kbS; coefS[2 * FT_N1 + qi] = kcS;
                     gate[qi] = gt;
                 }
             }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                hist[ch][0] = hist[ch][1];
-                hist[ch][1] = cur[ch];
-                cen_x[ch] = mid_x[ch]; cen_y[ch] = mid_y[ch];
-            }
+            histP[0] = histP[1]; histP[1] = curP;
+            histS[0] = histS[1]; histS[1] = curS;
+            cenxP = midxP; cenyP = midyP; cenxS = midxS; cenyS = midyS;
         }
     }
     __syncthreads();
@@ -363,16 +413,22 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         const int px = x0 + oc;
         const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
         const float wr = (px == W - 2) ? 2.0f : 1.0f;
-        float hprev[2][9];
+        const float2 wl2 = make_float2(wl, wl), wr2 = make_float2(wr, wr);
+        float2 hprevP[2][3];
+        float hprevS[2][3];
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r1 = 4 * os + rr;                      // ring row
-            float hc[9];
-            const float* base = coef + r1 * FT_R1 + oc;
+            float2 hcP[3];
+            float hcS[3];
+            const float2* baseP = coefP + r1 * FT_R1 + oc;
+            const float* baseS = coefS + r1 * FT_R1 + oc;
 #pragma unroll
-            for (int pl = 0; pl < 9; ++pl) {
-                const float* q = base + pl * FT_N1;
-                hc[pl] = fmaf(wl, q[0], fmaf(wr, q[2], q[1]));
+            for (int j = 0; j < 3; ++j) {
+                const float2* q = baseP + j * FT_N1;
+                hcP[j] = vfma(wl2, q[0], vfma(wr2, q[2], q[1]));
+                const float* qs = baseS + j * FT_N1;
+                hcS[j] = fmaf(wl, qs[0], fmaf(wr, qs[2], qs[1]));
             }
             if (rr >= 2) {
                 const int k = rr - 2;
@@ -381,25 +437,36 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 if (py < H && px < W) {
                     const float wu = (py == 1) ? 2.0f : 1.0f;
                     const float wd = (py == H - 2) ? 2.0f : 1.0f;
+                    const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
                     const int i2 = (r + 2) * FT_R2 + oc + 2;
+                    const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
                     const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
-                    float g = 0.0f;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float sa = fmaf(wu, hprev[0][ch * 3 + 0], fmaf(wd, hc[ch * 3 + 0], hprev[1][ch * 3 + 0]));
-                        const float sb = fmaf(wu, hprev[0][ch * 3 + 1], fmaf(wd, hc[ch * 3 + 1], hprev[1][ch * 3 + 1]));
-                        const float sc = fmaf(wu, hprev[0][ch * 3 + 2], fmaf(wd, hc[ch * 3 + 2], hprev[1][ch * 3 + 2]));
-                        const float xv = pred[ch * FT_N2 + i2], yv = tgt[ch * FT_NT + (r + 2) * FT_TP + oc + 2 + FT_TO];
-                        const float d = xv - yv;
-                        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-                        const float g_pred = fmaf(sb, xv, fmaf(sc, yv, sa)) + gl1 * sg;
-                        g = fmaf(g_pred, D[k][ch], g);
-                    }
+                    const float2 saP = vfma(wu2, hprevP[0][0], vfma(wd2, hcP[0], hprevP[1][0]));
+                    const float2 sbP = vfma(wu2, hprevP[0][1], vfma(wd2, hcP[1], hprevP[1][1]));
+                    const float2 scP = vfma(wu2, hprevP[0][2], vfma(wd2, hcP[2], hprevP[1][2]));
+                    const float saS = fmaf(wu, hprevS[0][0], fmaf(wd, hcS[0], hprevS[1][0]));
+                    const float sbS = fmaf(wu, hprevS[0][1], fmaf(wd, hcS[1], hprevS[1][1]));
+                    const float scS = fmaf(wu, hprevS[0][2], fmaf(wd, hcS[2], hprevS[1][2]));
+                    const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
+                    const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
+                    const float2 dP = vsub(xvP, yvP);
+                    const float dS = xvS - yvS;
+                    const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
+                                                   dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
+                    const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
+                    const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
+                    const float gpS = fmaf(sbS, xvS, fmaf(scS, yvS, saS)) + sgS;
+                    float g = gpP.x * D[k][0];
+                    g = fmaf(gpP.y, D[k][1], g);
+                    g = fmaf(gpS, D[k][2], g);
                     p.grad_disp[(size_t)b * N + (size_t)py * W + px] = g;
                 }
             }
 #pragma unroll
-            for (int pl = 0; pl < 9; ++pl) { hprev[0][pl] = hprev[1][pl]; hprev[1][pl] = hc[pl]; }
+            for (int j = 0; j < 3; ++j) {
+                hprevP[0][j] = hprevP[1][j]; hprevP[1][j] = hcP[j];
+                hprevS[0][j] = hprevS[1][j]; hprevS[1][j] = hcS[j];
+            }
         }
     }
     const float s = block_sum(loss_local, red);
