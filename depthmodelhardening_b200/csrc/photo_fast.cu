@@ -125,14 +125,21 @@ __device__ __forceinline__ Tap make_tap(const WarpCoord& wc, int H, int W) {
     return t;
 }
 
-// bilinear gather of 3 channels + d(value)/d(ix,iy)
-__device__ __forceinline__ Gathered gather_taps(const float* __restrict__ sp, size_t N, const Tap& t, bool want_grad) {
+// bilinear gather of 3 channels + d(value)/d(ix,iy), split into the 12 loads and their combination so that
+// the loads of several pixels can be in flight together
+__device__ __forceinline__ void load_taps(const float* __restrict__ sp, size_t N, const Tap& t, float v[3][4]) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* s = sp + ch * N + t.o;
+        v[ch][0] = __ldg(s); v[ch][1] = __ldg(s + t.dx); v[ch][2] = __ldg(s + t.dy); v[ch][3] = __ldg(s + t.dy + t.dx);
+    }
+}
+__device__ __forceinline__ Gathered combine_taps(const float v[3][4], const Tap& t, bool want_grad) {
     const float wnw = t.tx1 * t.ty1, wne = t.tx0 * t.ty1, wsw = t.tx1 * t.ty0, wse = t.tx0 * t.ty0;
     Gathered g;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float* s = sp + ch * N + t.o;
-        const float nw = __ldg(s), ne = __ldg(s + t.dx), sw = __ldg(s + t.dy), se = __ldg(s + t.dy + t.dx);
+        const float nw = v[ch][0], ne = v[ch][1], sw = v[ch][2], se = v[ch][3];
         float acc = nw * wnw;
         acc = fmaf(ne, wne, acc);
         acc = fmaf(sw, wsw, acc);
@@ -144,6 +151,11 @@ __device__ __forceinline__ Gathered gather_taps(const float* __restrict__ sp, si
         }
     }
     return g;
+}
+__device__ __forceinline__ Gathered gather_taps(const float* __restrict__ sp, size_t N, const Tap& t, bool want_grad) {
+    float v[3][4];
+    load_taps(sp, N, t, v);
+    return combine_taps(v, t, want_grad);
 }
 
 // position (r, c) in the 36 x 36 frame of halo-ring pixel h < 272: 2 top rows, 2 bottom rows, 2 left / right columns
@@ -247,20 +259,31 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 gax[k] = ax * dd; gay[k] = ay * dd;
             }
         }
+        // gathers: the 12 taps of TWO pixels are requested before either is consumed
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const Gathered g = gather_taps(sp, N, tp[k], k < 4);
-            const int r = 4 * os + k;
-            const int i2 = (k < 4) ? (r + 2) * FT_R2 + oc + 2 : hr * FT_R2 + hc;
+        for (int k0 = 0; k0 < 5; k0 += 2) {
+            float tv[2][3][4];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + i2] = g.v[ch];
-            if (k < 4) {
+            for (int j = 0; j < 2; ++j) {
+                if (k0 + j < 5) load_taps(sp, N, tp[k0 + j], tv[j]);
+            }
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) D[k][ch] = g.dix[ch] * gax[k] + g.diy[ch] * gay[k];
-                if (p.warped && y0 + r < H && x0 + oc < W) {
+            for (int j = 0; j < 2; ++j) {
+                const int k = k0 + j;
+                if (k >= 5) continue;
+                const Gathered g = combine_taps(tv[j], tp[k], k < 4);
+                const int r = 4 * os + k;
+                const int i2 = (k < 4) ? (r + 2) * FT_R2 + oc + 2 : hr * FT_R2 + hc;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+                for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + i2] = g.v[ch];
+                if (k < 4) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) D[k][ch] = g.dix[ch] * gax[k] + g.diy[ch] * gay[k];
+                    if (p.warped && y0 + r < H && x0 + oc < W) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+                    }
                 }
             }
         }
