@@ -312,3 +312,64 @@ def test_photo_scale_kernel_alone_vs_oracle(dev, frame_ids, hw):
     for f in srcs_ids:
         if f != "s":
             assert_grad_close(T1[f].grad, T0[f].grad, T64[f].grad, 1e-4, "grad_T", outlier_frac=0.0, slack=3.0)
+
+
+def test_bf16_frames(dev):
+    """BASELINE north_star: 'within 1e-5 relative (fp32) or 2e-3 (bf16 inputs)'.  Colour frames handed over in
+    bf16 (half the H2D bytes) are up-cast on the device and the fp32 kernels run unchanged: the result must equal
+    the oracle on the SAME bf16-rounded frames to 1e-5 and stay within 2e-3 of the fp32-input reference loss."""
+    from depthmodelhardening_b200 import objective
+    pb = synth.photo_batch(batch=2, height=64, width=96, frame_ids=(0, "s"), seed=51)
+    total32, _, _ = OP.objective_from_batch(pb)
+    rounded = synth.photo_batch(batch=2, height=64, width=96, frame_ids=(0, "s"), seed=51)
+    rounded.color = {k: v.to(torch.bfloat16).float() for k, v in pb.color.items()}
+    total_r, losses_r, grads_r = OP.objective_from_batch(rounded)
+    _, _, grads64 = OP.objective_from_batch(rounded, dtype=torch.float64)
+    g = pb.to(dev)
+    colors = {k: v.to(torch.bfloat16) for k, v in g.color.items()}
+    disps = {s: g.disp[s].clone().requires_grad_(True) for s in g.scales}
+    losses, _ = objective.photometric_losses(colors, disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height,
+                                             g.width, noise=g.noise)
+    losses["loss"].backward()
+    assert_close(losses["loss"], total_r, TOL, "loss vs oracle on bf16-rounded frames")
+    for s in pb.scales:
+        assert_grad_close(disps[s].grad, grads_r[s], grads64[s], TOL, "grad_disp_%d" % s)
+    assert rel_err(losses["loss"], total32) < 2e-3
+
+
+@pytest.mark.parametrize("hw", [(320, 1024), (640, 2048)])
+def test_general_kernel_full_size_properties(dev, hw):
+    """BASELINE config 5 shapes (frame_ids [0,-1,1], two temporal sources, resolution sweep up to 2048x640;
+    B=2 here): the multi-source kernel (photo_scale_kernel<2>, pose gradients on) must be run-to-run
+    bit-identical, linear in the upstream gradient, and give ~0 photometric loss for identical frames
+    under the identity pose."""
+    from depthmodelhardening_b200 import objective
+    H, W = hw
+    pb = synth.photo_batch(batch=2, height=H, width=W, frame_ids=(0, -1, 1), seed=43).to(dev)
+
+    def run(mult):
+        disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+        Ts = {k: v.clone().requires_grad_(True) for k, v in pb.T.items()}
+        losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, Ts, pb.frame_ids, pb.scales,
+                                                 pb.height, pb.width, noise=pb.noise)
+        (losses["loss"] * mult).backward()
+        return losses["loss"].detach(), {s: d.grad for s, d in disps.items()}, {k: t.grad for k, t in Ts.items()}
+
+    l1, g1, t1 = run(1.0)
+    l2, g2, t2 = run(1.0)
+    l3, g3, t3 = run(3.0)
+    assert torch.equal(l1, l2)
+    for s in pb.scales:
+        assert torch.equal(g1[s], g2[s])
+        assert rel_err(g3[s], 3.0 * g1[s]) < 1e-6
+        assert torch.isfinite(g1[s]).all()
+    for k in t1:
+        assert rel_err(t3[k], 3.0 * t1[k]) < 1e-5
+    colors = dict(pb.color)
+    colors[(-1, 0)] = colors[(0, 0)]
+    colors[(1, 0)] = colors[(0, 0)]
+    Ti = {k: torch.eye(4, device=dev).repeat(pb.batch, 1, 1) for k in (-1, 1)}
+    disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+    losses, _ = objective.photometric_losses(colors, disps, pb.K, pb.inv_K, Ti, pb.frame_ids, pb.scales, pb.height,
+                                             pb.width, disable_automasking=True, disparity_smoothness=0.0)
+    assert float(losses["loss"]) < 1e-4
