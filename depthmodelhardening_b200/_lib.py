@@ -71,6 +71,8 @@ SIGNATURES = {
     "dmh_hint_select_blocks": (_i, [_i, _i, _i]),
     "dmh_hint_select": (_i, [C.POINTER(C.c_void_p), _i, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f,
                              C.POINTER(C.c_void_p), _f, _f, _st]),
+    "dmh_cost_volume_workspace_floats": (_ll, [_i, _i, _i, _i, _i]),
+    "dmh_cost_volume": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
 }
 

@@ -15,6 +15,7 @@ from __future__ import annotations
 import sys
 
 from . import attacks as _attacks
+from . import cost_volume as _cost_volume
 from . import depth_hints as _depth_hints
 from . import layers as _layers
 from . import objective as _objective
@@ -106,10 +107,23 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
                 T.generate_images_pred = _objective.fused_generate_images_pred
                 T.compute_losses = _objective.fused_compute_losses
             done[mod_name + ".Trainer.compute_losses"] = True
+    # --- ManyDepth cost volume (MD/networks/resnet_encoder.py:157): ResnetEncoderMatching.match_features
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is not None and mod_name.endswith("resnet_encoder") and hasattr(mod, "ResnetEncoderMatching"):
+            cls = mod.ResnetEncoderMatching
+            if not hasattr(cls, "_dmh_ref_match_features"):
+                cls._dmh_ref_match_features = cls.match_features
+            cls.match_features = _cost_volume.match_features
+            done[mod_name + ".ResnetEncoderMatching.match_features"] = True
     return done
 
 
 def uninstall() -> None:
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is not None and mod_name.endswith("resnet_encoder") and hasattr(mod, "ResnetEncoderMatching"):
+            cls = mod.ResnetEncoderMatching
+            if hasattr(cls, "_dmh_ref_match_features"):
+                cls.match_features = cls._dmh_ref_match_features
     layers_mod = sys.modules.get("layers")
     if layers_mod is not None:
         for name in _LAYER_SYMBOLS:

@@ -262,6 +262,20 @@ int dmh_hint_select(const float* const* reproj_host, int F, const float* ident, 
                     int avg_reprojection, int B, int H, int W, float* part, float* const* g_reproj_host,
                     float* g_depth, unsigned char* sel, dmh_stream_t stream);
 
+/* -- next-3: ManyDepth cost volume (DepthNetworks/manydepth2/networks/resnet_encoder.py:157-236,
+ * ResnetEncoderMatching.match_features), no gradient (the reference builds it under no_grad):
+ * current_feats (B,C,h,w), lookup_feats (B,L,C,h,w), poses (B,L,4,4) (an all-zero pose marks a missing
+ * lookup frame), K, inv_K (B,4,4) at the matching resolution, depth_bins (D) on the device.
+ * -> cost_volume (B,D,h,w) = mean over contributing lookups of mean_c |warp(lookup) - current| with the
+ * 2-px edge masks, empty cells filled with the per-pixel max over the bins when set_missing_to_max;
+ * missing_mask (B,D,h,w) = 1 where the cell was empty.  C must be 16, L <= 4.
+ * workspace: dmh_cost_volume_workspace_floats floats, 16-byte aligned (channel-last copy of the lookups). */
+long long dmh_cost_volume_workspace_floats(int B, int L, int C, int h, int w);
+int dmh_cost_volume(const float* current_feats, const float* lookup_feats, const float* poses, const float* K,
+                    const float* inv_K, const float* depth_bins, int B, int L, int C, int D, int h, int w,
+                    int set_missing_to_max, float* workspace, float* cost_volume, float* missing_mask,
+                    dmh_stream_t stream);
+
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);
