@@ -100,7 +100,7 @@ def main():
 
     if "costvol" in want:
         from depthmodelhardening_b200 import cost_volume as CV
-        from oracle.make_golden_md import cost_volume_inputs     # seeded input factory only (no oracle compute)
+        cost_volume_inputs = synth.cost_volume_inputs
         B, L, h, w, D = 16, 2, 80, 256, 96
         cur, look, poses, K, inv_K, bins = [t.to(dev) for t in cost_volume_inputs(B=B, L=L, h=h, w=w, D=D, seed=9)]
         ms = timed(lambda: CV.cost_volume(cur, look, poses, K, inv_K, bins), args.steps, args.warmup)

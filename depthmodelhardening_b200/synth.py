@@ -197,3 +197,17 @@ def patch_batch(batch=4, seed=0, scene_kind="smooth") -> PatchBatch:
     ppos = rand((1, 3, PATCH_H, PATCH_W), seed + 901)
     pneg = rand((1, 3, PATCH_H, PATCH_W), seed + 902)
     return PatchBatch(batch, obj, mask, scenes, z0, alpha, upstream, ppos, pneg)
+
+
+def cost_volume_inputs(B=2, L=2, C=16, h=24, w=40, D=12, seed=80):
+    """Seeded matching-resolution inputs: smooth non-negative features (post-ReLU), small temporal poses,
+    item 1's second lookup frame missing (all-zero pose), KITTI intrinsics at (h, w), linear depth bins."""
+    cur = smooth_field((B, C, h, w), seed, down=4, noise=0.02)
+    look = torch.stack([smooth_field((B, C, h, w), seed + 1 + l, down=4, noise=0.02) for l in range(L)], 1)
+    poses = torch.stack([temporal_T(B, seed + 10 + 7 * l) for l in range(L)], 1).contiguous()
+    poses[:, :, 0, 3] += 0.3                      # a visible baseline so that the bins sweep along the epipolar line
+    if B > 1 and L > 1:
+        poses[1, 1] = 0.0
+    K, inv_K = intrinsics(h, w, B)
+    bins = torch.linspace(0.5, 20.0, D)
+    return cur.contiguous(), look.contiguous(), poses, K, inv_K, bins

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import cost_volume as OC
-from oracle.make_golden_md import cost_volume_inputs
+from depthmodelhardening_b200.synth import cost_volume_inputs
 from tests.util import assert_close, load_golden
 
 TOL = 1e-5
