@@ -1,0 +1,49 @@
+"""Host -> device staging of a training batch as ONE transfer.
+
+The reference moves its batch dictionary tensor by tensor (`inputs[key] = ipt.to(self.device)`,
+`M2/trainer.py:262-263`): ~20 separate copies per step, each paying its own launch and PCIe ramp.
+`BatchArena` lays the dictionary out in one pinned host buffer and one device buffer of the same layout
+(256-byte aligned slots); `upload()` is a single `cudaMemcpyAsync`, the tensors handed to the kernels are views.
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable
+
+import torch
+
+_ALIGN = 256
+
+
+class BatchArena:
+    def __init__(self, example: Dict[Hashable, torch.Tensor], device, slots: int = 2):
+        """example: key -> host tensor giving shape/dtype of every entry; `slots` device copies (double buffering)."""
+        self.layout = {}
+        off = 0
+        for k, v in example.items():
+            n = v.numel() * v.element_size()
+            self.layout[k] = (off, tuple(v.shape), v.dtype, n)
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.nbytes = off
+        self.host = torch.empty(off, dtype=torch.uint8).pin_memory()
+        self.dev = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(slots)]
+
+    def _views(self, buf):
+        out = {}
+        for k, (off, shape, dtype, n) in self.layout.items():
+            out[k] = buf[off:off + n].view(dtype).view(shape)
+        return out
+
+    def host_views(self) -> Dict[Hashable, torch.Tensor]:
+        """Pinned host tensors to fill (e.g. as DataLoader collate targets)."""
+        return self._views(self.host)
+
+    def device_views(self, slot: int) -> Dict[Hashable, torch.Tensor]:
+        return self._views(self.dev[slot])
+
+    def upload(self, slot: int, stream=None) -> None:
+        """One async H2D copy of the whole batch into device slot `slot` (on `stream` or the current stream)."""
+        if stream is None:
+            self.dev[slot].copy_(self.host, non_blocking=True)
+        else:
+            with torch.cuda.stream(stream):
+                self.dev[slot].copy_(self.host, non_blocking=True)

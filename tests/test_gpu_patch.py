@@ -287,3 +287,19 @@ def test_attack_classes_vs_oracle_loop_same_device(dev, calib):
     assert float(((atk0.pattern_neg_tensor - ref0[4]).abs() > 1e-4).float().mean()) < 5e-3
     surv, surv_ref = (atk0.pattern.abs().sum(1) != 0), (ref0[5].abs().sum(1) != 0)
     assert float((surv != surv_ref).float().mean()) < 5e-3
+
+
+def test_batch_arena_roundtrip(dev):
+    """staging.BatchArena: one pinned arena, one H2D copy; device views carry exactly the host values."""
+    from depthmodelhardening_b200.staging import BatchArena
+    ex = {("color", 0, 0): torch.rand(2, 3, 8, 12), ("K",): torch.rand(2, 4, 4), ("idx",): torch.arange(7, dtype=torch.int32),
+          ("disp", 1): torch.rand(2, 1, 4, 6)}
+    arena = BatchArena(ex, dev, slots=2)
+    for k, v in arena.host_views().items():
+        assert v.is_pinned() and v.shape == ex[k].shape and v.dtype == ex[k].dtype
+        v.copy_(ex[k])
+    arena.upload(1)
+    torch.cuda.synchronize()
+    for k, v in arena.device_views(1).items():
+        assert v.is_cuda and torch.equal(v.cpu(), ex[k])
+        assert v.data_ptr() % 256 == 0
