@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-patch", action="store_true", help="skip stage 1 (debug)")
+    ap.add_argument("--attack", default="l0", choices=["l0", "linf"],
+                    help="stage-1 update rule: l0 = README config (--norm_type l_0), linf = sign/project step")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     return ap.parse_args()
 
@@ -143,7 +145,11 @@ class Stage2:
 
 
 class Stage1:
-    def __init__(self, pt, device, world):
+    """One PGD iteration of the physical patch attack with the depth network's gradient supplied
+    (the network is outside the graft): [L0: compose patterns + count] -> patch apply fwd -> bwd to the
+    patch -> [all-reduce] -> update (L0: mask-cost gradient + Adam, README `--norm_type l_0`; or L-inf)."""
+
+    def __init__(self, pt, device, world, attack="l0"):
         import numpy as np
         from depthmodelhardening_b200 import patch_ops, synth
         self.ops = patch_ops
@@ -152,16 +158,26 @@ class Stage1:
         self.coeffs = patch_ops.homographies(pt.z0, pt.alpha, P34, obj_hw=(synth.PATCH_H, synth.PATCH_W)).to(device)
         self.adv = self.g.obj.clone()
         self.world = world
+        self.attack = attack
+        if attack == "l0":      # M2/trainer.py:216-218: adam_lr 0.5, mask_wt 0.06, l0_thresh 0.1
+            self.l0 = patch_ops.L0State(self.g.obj, self.g.pattern_pos, self.g.pattern_neg, lr=0.5, betas=(0.5, 0.9))
+            self.first = True
 
     def step(self):
         ops = self.ops
         g = self.g
+        if self.attack == "l0":
+            self.adv = self.l0.compose_count(first=self.first)
+            self.first = False
         adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream)
         if self.world > 1:
             from depthmodelhardening_b200 import dist as D
             # the ONE collective of the step: patch gradient + scalar attack loss in a single all-reduce
             grad_patch, _ = D.allreduce_patch_grad(grad_patch, [adv_scene.new_zeros(())], average=True)
-        self.adv = ops.pgd_linf_step(self.adv, grad_patch, g.obj, alpha=0.02, eps=0.1)
+        if self.attack == "l0":
+            self.l0.adam_step(grad_patch, 0.06, 0.1)
+        else:
+            self.adv = ops.pgd_linf_step(self.adv, grad_patch, g.obj, alpha=0.02, eps=0.1)
         return adv_scene
 
 
@@ -187,7 +203,7 @@ def timed_loop(fn, steps, warmup, world):
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_reference_step(sample_batch, with_patch, threads=None):
+def cpu_reference_step(sample_batch, with_patch, threads=None, attack="l0"):
     """The reference algorithm on the host cores: oracle restatement (the
     reference itself is Python and does not travel to the GPU box)."""
     import numpy as np
@@ -199,9 +215,23 @@ def cpu_reference_step(sample_batch, with_patch, threads=None):
     pb = synth.photo_batch(batch=sample_batch, height=H, width=W, frame_ids=FRAME_IDS, scales=SCALES, seed=7)
     pt = synth.patch_batch(batch=sample_batch, seed=7) if with_patch else None
     P34 = np.array(OQ_P2(), dtype=np.float64).reshape(3, 4)
+    state = {}
+    if pt is not None and attack == "l0":
+        state["pp"] = pt.pattern_pos.clone().requires_grad_(True)
+        state["pn"] = pt.pattern_neg.clone().requires_grad_(True)
+        state["opt"] = torch.optim.Adam([state["pp"], state["pn"]], lr=0.5, betas=(0.5, 0.9))
 
     def step():
-        if pt is not None:
+        if pt is not None and attack == "l0":
+            # one iteration of phy_obj_atk_l0.py:94-138 with the network gradient supplied
+            adv, pos, neg = OQ.l0_compose(pt.obj, state["pp"], state["pn"])
+            OQ.l0_count(pos, neg)
+            scene, _ = OQ.apply_patch(adv, pt.mask, pt.scenes, pt.z0, pt.alpha, P34)
+            cost = (scene * pt.upstream).sum() + 0.06 * OQ.l0_mask_cost(state["pp"], state["pn"])
+            state["opt"].zero_grad()
+            cost.backward()
+            state["opt"].step()
+        elif pt is not None:
             obj = pt.obj.clone().requires_grad_(True)
             adv, _ = OQ.apply_patch(obj, pt.mask, pt.scenes, pt.z0, pt.alpha, P34)
             (adv * pt.upstream).sum().backward()
@@ -215,8 +245,8 @@ def OQ_P2():
     return CALIB_P2
 
 
-def run_cpu_baseline(sample_batch, with_patch, reps=2):
-    step = cpu_reference_step(sample_batch, with_patch)
+def run_cpu_baseline(sample_batch, with_patch, reps=2, attack="l0"):
+    step = cpu_reference_step(sample_batch, with_patch, attack=attack)
     step()
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -233,7 +263,7 @@ def reference_arm(args, rank, world):
     torch.set_num_threads(os.cpu_count() or 1)
     sb = args.cpu_sample_batch
     with_patch = not args.no_patch
-    step = cpu_reference_step(sb, with_patch)
+    step = cpu_reference_step(sb, with_patch, attack=args.attack)
     for _ in range(min(args.warmup, 1)):
         step()
     steps = max(1, min(args.steps, 3))
@@ -281,7 +311,7 @@ def main():
     B = args.batch
     pb_host, pt_host = make_host_workload(B, rank, with_patch)
     s2 = Stage2(pb_host, device)
-    s1 = Stage1(pt_host, device, world) if with_patch else None
+    s1 = Stage1(pt_host, device, world, args.attack) if with_patch else None
 
     def step():
         if s1 is not None:
@@ -431,7 +461,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: monodepth2 1024x320 stereo [0,'s'], 4 scales, automask, SSIM+L1, "
-                               "smoothness; step = patch PGD step (stage 1) + photometric loss fwd/bwd (stage 2)"
+                               "smoothness; step = patch PGD step (stage 1, %s update) + photometric loss fwd/bwd (stage 2)" % args.attack
                                if s1 is not None else
                                "configs[1] stage 2 only: photometric loss fwd/bwd (stage 1 not built yet)",
                    "per_gpu_batch": B, "global_batch": B * world, "height": H, "width": W, "frame_ids": list(FRAME_IDS),
@@ -446,7 +476,7 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None)
+        line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None, attack=args.attack)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
