@@ -27,6 +27,7 @@ SIGNATURES = {
     "dmh_version": (_i, []),
     "dmh_build_arch": (_i, []),
     "dmh_launch_count": (_ll, []),
+    "dmh_const_div_exact": (_i, [_i]),
     "dmh_disp_to_depth": (_i, [_f, _ll, _fl, _fl, _f, _f, _st]),
     "dmh_backproject_fwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),
     "dmh_backproject_bwd": (_i, [_f, _f, _i, _i, _i, _f, _st]),

@@ -32,7 +32,10 @@ DMH_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 DMH_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
 DMH_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 DMH_HD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+// 1/x correctly rounded == div_rn(1.0f, x) bit for bit, without the generic division's slow-path call site
+DMH_HD float rcp_rn(float x) { return __frcp_rn(x); }
 #else
+DMH_HD float rcp_rn(float x) { volatile float r = 1.0f / x; return r; }
 DMH_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
 DMH_HD float add_rn(float a, float b) { volatile float r = a + b; return r; }
 DMH_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
@@ -67,7 +70,7 @@ struct DepthScale {      // disp_to_depth constants, computed in double on the h
 
 DMH_HD float disp_to_depth(float disp, const DepthScale& ds) {
     const float scaled = add_rn(ds.min_disp, mul_rn(ds.range, disp));
-    return div_rn(1.0f, scaled);
+    return rcp_rn(scaled);
 }
 // d depth / d disp = -range * depth^2
 DMH_HD float ddepth_ddisp(float depth, const DepthScale& ds) { return -ds.range * depth * depth; }
@@ -149,6 +152,17 @@ DMH_HD Bilinear bilinear_setup(float ix, float iy) {
     return b;
 }
 
+// a / c for a launch constant c (W-1, H-1) in three instructions: q0 = a*rc, r = a - q0*c (exact, FMA),
+// q = q0 + r*rc.  Correctly rounded -- i.e. bit-identical to IEEE division -- for the constants the library has
+// verified EXHAUSTIVELY on the device (all 2^24 significands of two binades; the result depends only on the
+// significand of a), see dmh::const_div_exact() in core.cu; other constants take div_rn.  +-inf / NaN pass through.
+DMH_HD float div_const(float a, float c, float rc) {
+    const float q0 = mul_rn(a, rc);
+    const float r = fmaf(-q0, c, a);
+    const float q = fmaf(r, rc, q0);
+    return (fabsf(a) <= 3.402823466e+38f) ? q : a;
+}
+
 // Full forward coordinate chain of A9-A12 for target pixel (x,y) with depth d.
 struct WarpCoord {
     float ix, iy;          // clipped source coordinates
@@ -158,7 +172,9 @@ struct WarpCoord {
     float ray[3];
 };
 
-DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, int W, int H, float eps) {
+template <bool FASTDIV = false>
+DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, int W, int H, float eps,
+                            float rcw = 0.0f, float rch = 0.0f) {
     WarpCoord wc;
     pixel_ray(cam, x, y, wc.ray);
     float pt[3] = {mul_rn(depth, wc.ray[0]), mul_rn(depth, wc.ray[1]), mul_rn(depth, wc.ray[2])};
@@ -168,8 +184,10 @@ DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, in
     wc.inv_z = 1.0f / z;
     wc.u_raw = div_rn(p[0], z);
     wc.v_raw = div_rn(p[1], z);
-    const float gx = mul_rn(sub_rn(div_rn(wc.u_raw, (float)(W - 1)), 0.5f), 2.0f);
-    const float gy = mul_rn(sub_rn(div_rn(wc.v_raw, (float)(H - 1)), 0.5f), 2.0f);
+    const float nu = FASTDIV ? div_const(wc.u_raw, (float)(W - 1), rcw) : div_rn(wc.u_raw, (float)(W - 1));
+    const float nv = FASTDIV ? div_const(wc.v_raw, (float)(H - 1), rch) : div_rn(wc.v_raw, (float)(H - 1));
+    const float gx = mul_rn(sub_rn(nu, 0.5f), 2.0f);
+    const float gy = mul_rn(sub_rn(nv, 0.5f), 2.0f);
     float cgx = 0.0f, cgy = 0.0f;
     const float ux = unnormalise_coord(gx, W, true);
     const float uy = unnormalise_coord(gy, H, true);

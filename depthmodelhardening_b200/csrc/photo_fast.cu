@@ -96,6 +96,7 @@ struct FastParams {
     int B, H, W, flags;
     DepthScale ds;
     float grad_scale;
+    float rcw, rch;              // 1/(W-1), 1/(H-1) for the verified 3-instruction division
 };
 
 __device__ __forceinline__ int ext_to_img(int e, int n) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void halo_rc(int h, int& r, int& c) {
     else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
 }
 
-template <bool TMA>
+template <bool TMA, bool FASTDIV>
 __global__ void __launch_bounds__(FT_THREADS, 3)
 photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map) {
     extern __shared__ __align__(128) float smem[];
@@ -250,7 +251,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             const float depth = is_depth ? dv[k] : disp_to_depth(dv[k], p.ds);
-            const WarpCoord wc = warp_coord(cam, (float)pxx[k], (float)py[k], depth, W, H, 1e-7f);
+            const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)pxx[k], (float)py[k], depth, W, H, 1e-7f, p.rcw, p.rch);
             tp[k] = make_tap(wc, H, W);
             if (k < 4) {
                 float ax, ay;
@@ -295,7 +296,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
         const float dvh = load_disp(p.disp, b, iy, ix, H, W);
         const float depth = is_depth ? dvh : disp_to_depth(dvh, p.ds);
-        const WarpCoord wc = warp_coord(cam, (float)ix, (float)iy, depth, W, H, 1e-7f);
+        const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)ix, (float)iy, depth, W, H, 1e-7f, p.rcw, p.rch);
         const Gathered g = gather_taps(sp, N, make_tap(wc, H, W), false);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + r * FT_R2 + c] = g.v[ch];
@@ -618,9 +619,11 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured_dev[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(photo_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photo_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaSuccess;
+        const void* fns[4] = {(const void*)photo_fast_kernel<false, false>, (const void*)photo_fast_kernel<false, true>,
+                              (const void*)photo_fast_kernel<true, false>, (const void*)photo_fast_kernel<true, true>};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("dmh_photo_scale(fast): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return DMH_ERR_CUDA;
@@ -642,8 +645,12 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         use_tma = (r == CUDA_SUCCESS);
     }
-    if (use_tma) DMH_LAUNCH(photo_fast_kernel<true>, grid, FT_THREADS, smem, st)(p, map);
-    else DMH_LAUNCH(photo_fast_kernel<false>, grid, FT_THREADS, smem, st)(p, map);
+    // division by W-1 / H-1 in the coordinate chain: the 3-instruction form where it is proven bit-exact
+    const bool fastdiv = W > 1 && H > 1 && const_div_exact(W - 1, &p.rcw) && const_div_exact(H - 1, &p.rch);
+    if (use_tma && fastdiv) DMH_LAUNCH((photo_fast_kernel<true, true>), grid, FT_THREADS, smem, st)(p, map);
+    else if (use_tma) DMH_LAUNCH((photo_fast_kernel<true, false>), grid, FT_THREADS, smem, st)(p, map);
+    else if (fastdiv) DMH_LAUNCH((photo_fast_kernel<false, true>), grid, FT_THREADS, smem, st)(p, map);
+    else DMH_LAUNCH((photo_fast_kernel<false, false>), grid, FT_THREADS, smem, st)(p, map);
     return DMH_OK;
 }
 

@@ -276,6 +276,12 @@ int dmh_cost_volume(const float* current_feats, const float* lookup_feats, const
                     int set_missing_to_max, float* workspace, float* cost_volume, float* missing_mask,
                     dmh_stream_t stream);
 
+/* Diagnostics: 1 iff the library's 3-instruction division by the constant c (used for the /(W-1), /(H-1) of
+ * Project3D, layers.py:195-196, in the fused kernel) has been verified bit-identical to IEEE division for
+ * every float numerator on the current device (exhaustive over all significands; first call per constant
+ * launches a small kernel and synchronises, then cached).  0: the kernels use IEEE division for that size. */
+int dmh_const_div_exact(int c);
+
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);
