@@ -438,9 +438,9 @@ def main():
                        "stream, double-buffered against the previous step's compute; tie-break noise drawn on the device; loss read back every step"}
 
     # DRAM traffic and instruction count of the dominant kernel per launch: from the committed `ncu --set full`
-    # capture of this same command (profiles/r01_ncu_full_j.txt; mean of the 4 per-scale launches at B=32)
-    ncu_traffic = 380.1e6 if (B == 32 and F == 1) else None
-    ncu_warp_inst = 366.9e6 if (B == 32 and F == 1) else None
+    # capture of this same command (profiles/r01_ncu_full_q.txt; mean of the 4 per-scale launches at B=32)
+    ncu_traffic = 380.3e6 if (B == 32 and F == 1) else None
+    ncu_warp_inst = 313.3e6 if (B == 32 and F == 1) else None
     sm_clock_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA> (dmh_photo_scale, one launch per scale)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
