@@ -52,13 +52,16 @@ SIGNATURES = {
     "dmh_photo_tiles": (_i, [_i, _i]),
     "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                              _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),
+    "dmh_photo_scale_dh": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _f, _f,
+                                _f, _i, _i, _i, _fl, _fl, _i, _f, _f, _f, _f, _f, _st]),
     "dmh_smooth_fused_workspace_floats": (_ll, [_i, _i, _i]),
     "dmh_smooth_fused": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_objective_finish": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_double, _f, _f,
                                   _f, _st]),
     "dmh_objective_finish_workspace_bytes": (_ll, [_i, _i]),
-    "dmh_disp_grad": (_i, [_f, _f, _f, _fl, _f, _f, _fl, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_disp_grad": (_i, [_f, _f, _f, _fl, _f, _f, _f, _fl, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_axpby_dev": (_i, [_f, _f, _f, _f, _ll, _f, _st]),
     "dmh_perspective_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_perspective_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),

@@ -110,9 +110,25 @@ hint_select_kernel(const HintParams p) {
     if (threadIdx.x == 0) p.part[3 * nblk + blockIdx.x] = t;
 }
 
+__global__ void axpby_dev_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ b,
+                                 const float* __restrict__ y, long long n, float* __restrict__ out) {
+    const float av = a[0], bv = b[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fmaf(av, x[i], bv * y[i]);
+}
+
 }  // namespace
 
 extern "C" {
+
+int dmh_axpby_dev(const float* a, const float* x, const float* b, const float* y, long long n, float* out,
+                  dmh_stream_t stream) {
+    DMH_REQUIRE(a && x && b && y && out && n > 0, "dmh_axpby_dev: null pointer or empty");
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    DMH_LAUNCH(axpby_dev_kernel, blocks, 256, 0, (cudaStream_t)stream)(a, x, b, y, n, out);
+    DMH_CHECK_LAUNCH("dmh_axpby_dev");
+    return DMH_OK;
+}
 
 int dmh_hint_select_blocks(int B, int H, int W) {
     return ceil_div((long long)B * H * W, (long long)HS_THREADS * HS_PER_THREAD);

@@ -321,8 +321,8 @@ template <int R>
 __global__ void __launch_bounds__(256)
 disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
                  const float* __restrict__ img_scalars, float smooth_weight, const float* __restrict__ g_total,
-                 const float* __restrict__ g_scale, float inv_S, int h, int w, int H, int W, float sh, float sw,
-                 float* __restrict__ grad) {
+                 const float* __restrict__ g_scale, const float* __restrict__ g_smooth, float inv_S, int h, int w,
+                 int H, int W, float sh, float sw, float* __restrict__ grad) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const bool in = x < w && y < h;
@@ -412,11 +412,14 @@ disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
             acc = fmaf(wy, row, acc);
         }
     }
+    float sm = 0.0f;
     if (gN) {
         const float inv_m = img_scalars[b * 2], corr = img_scalars[b * 2 + 1];
-        acc += smooth_weight * (gN[(size_t)b * h * w + (size_t)y * w + x] * inv_m - corr);
+        sm = smooth_weight * (gN[(size_t)b * h * w + (size_t)y * w + x] * inv_m - corr);
     }
-    grad[(size_t)b * h * w + (size_t)y * w + x] = up * acc;
+    // g_smooth: separate upstream weight of the smoothness term (depth-hints objective: the photometric
+    // gradients arrive already weighted by their masked-mean denominators)
+    grad[(size_t)b * h * w + (size_t)y * w + x] = g_smooth ? fmaf(g_smooth[0], sm, up * acc) : up * (acc + sm);
 }
 
 }  // namespace
@@ -478,8 +481,8 @@ int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const
 }
 
 int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars, float smooth_weight,
-                  const float* g_total, const float* g_scale, float inv_S, int B, int h, int w, int H, int W,
-                  float* grad_disp, dmh_stream_t stream) {
+                  const float* g_total, const float* g_scale, const float* g_smooth, float inv_S, int B, int h, int w,
+                  int H, int W, float* grad_disp, dmh_stream_t stream) {
     DMH_REQUIRE(G_full && grad_disp && (g_total || g_scale), "dmh_disp_grad: null pointer");
     DMH_REQUIRE(!gN || img_scalars, "dmh_disp_grad: gN given without img_scalars");
     DMH_REQUIRE(B > 0 && B <= 65535 && h >= 1 && w >= 1 && H >= h && W >= w, "dmh_disp_grad: bad shape");
@@ -490,7 +493,7 @@ int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars
     if (H % h == 0 && W % w == 0 && H / h == W / w) R = H / h;
     if (R > 1 && ((uintptr_t)G_full % 16 != 0 || W % 4 != 0)) R = 0;   // vector loads need aligned rows
 #define DMH_DG(RR) DMH_LAUNCH(disp_grad_kernel<RR>, grid, block, 0, st)(G_full, gN, img_scalars, smooth_weight, g_total, \
-                                                                       g_scale, inv_S, h, w, H, W, sh, sw, grad_disp)
+                                                                       g_scale, g_smooth, inv_S, h, w, H, W, sh, sw, grad_disp)
     if (R == 1) DMH_DG(1);
     else if (R == 2) DMH_DG(2);
     else if (R == 4) DMH_DG(4);

@@ -50,6 +50,12 @@ struct PhotoParams {
     int B, H, W, F, flags;
     DepthScale ds;
     float grad_scale;
+    // depth-hints mode (DMH_PHOTO_DEPTH_HINTS; DH/trainer.py:541-590, 666-713)
+    int dh;                        // 1: min over frames first, argmin [reprojection, identity, hint], masked sums
+    const float* hint_reproj;      // (B,1,H,W) hint reprojection loss + 1000*(1-valid); NULL: no hints
+    const float* hint_depth;       // (B,1,H,W)
+    const float* hint_valid;       // (B,1,H,W)
+    float* grad_hint;              // (B,1,H,W) d(sum proxy*mask_h)/d(up-sampled disp)
 };
 
 __device__ __forceinline__ int ext_to_img(int e, int n) {
@@ -185,6 +191,7 @@ photo_scale_kernel(const PhotoParams p) {
     // ---- forward loss at every valid window centre q of the 1-px ring; argmin; loss sum
     const int Fi = p.ident ? (avg ? 1 : F) : 0;      // identity candidates
     float loss_local = 0.0f;
+    float dh_r = 0.f, dh_rm = 0.f, dh_h = 0.f, dh_hm = 0.f;      // depth-hints mode: the four masked sums
     for (int i = tid; i < PH_R1; i += PH_THREADS) {
         const int r = i / PH_R1W, c = i % PH_R1W;
         const int qy = y0 - 1 + r, qx = x0 - 1 + c;
@@ -213,6 +220,53 @@ photo_scale_kernel(const PhotoParams p) {
                 rp_avg = add_rn(rp_avg, rp[f]);
             }
             rp_avg = div_rn(rp_avg, (float)F);
+            const bool interior = r >= 1 && r <= PH_TH && c >= 1 && c <= PH_TW;
+            if (p.dh) {
+                // depth-hints objective: reduce over the frames FIRST (DH/trainer.py:670-672, 683-685), one
+                // tie-break noise plane, argmin over [reprojection, identity, hint] (:541-590)
+                float rpm = avg ? rp_avg : rp[0];
+                int fb = 0;
+                if (!avg) {
+#pragma unroll
+                    for (int f = 1; f < F; ++f)
+                        if (rp[f] < rpm) { rpm = rp[f]; fb = f; }
+                }
+                int idx = 0;
+                float best = rpm;
+                if (Fi > 0) {
+                    float idv = __ldg(p.ident + ((size_t)b * F) * N + qo);
+                    if (avg) {
+                        for (int f = 1; f < F; ++f) idv = add_rn(idv, __ldg(p.ident + ((size_t)b * F + f) * N + qo));
+                        idv = div_rn(idv, (float)F);
+                    } else {
+                        for (int f = 1; f < F; ++f) idv = fminf(idv, __ldg(p.ident + ((size_t)b * F + f) * N + qo));
+                    }
+                    if (p.noise) idv = add_rn(idv, __ldg(p.noise + (size_t)b * N + qo));
+                    if (idv < best) { best = idv; idx = 1; }
+                }
+                if (p.hint_reproj) {
+                    const float hv = __ldg(p.hint_reproj + (size_t)b * N + qo);
+                    if (hv < best) { best = hv; idx = 2; }
+                }
+                win = (idx != 1) ? (float)fb : -1.0f;       // reprojection mask = argmin != identity
+                if (interior) {
+                    if (idx != 1) { dh_r += rpm; dh_rm += 1.0f; }
+                    if (p.hint_reproj) {
+                        const float m_h = (idx == 2) ? 1.0f : 0.0f;
+                        const float depth = dep[ci];
+                        const float hd = __ldg(p.hint_depth + (size_t)b * N + qo);
+                        const float va = __ldg(p.hint_valid + (size_t)b * N + qo);
+                        const float diff = sub_rn(hd, depth);
+                        const float a1 = add_rn(fabsf(diff), 1.0f);
+                        dh_h += mul_rn(mul_rn(logf(a1), va), m_h);
+                        dh_hm += m_h;
+                        const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
+                        const float gd = m_h * va * sg / a1;
+                        p.grad_hint[(size_t)b * N + qo] = is_depth ? gd : gd * ddepth_ddisp(depth, p.ds);
+                    }
+                    if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)idx;
+                }
+            } else {
             // candidates in the reference's cat order: identity first, then reprojection
             float best = 3.4e38f;
             int best_idx = 0, idx = 0;
@@ -241,10 +295,10 @@ photo_scale_kernel(const PhotoParams p) {
                     ++idx;
                 }
             }
-            const bool interior = r >= 1 && r <= PH_TH && c >= 1 && c <= PH_TW;
             if (interior) {
                 loss_local += best;
                 if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)best_idx;
+            }
             }
         }
         gl1[i] = win;
@@ -365,7 +419,18 @@ photo_scale_kernel(const PhotoParams p) {
         p.grad_disp[(size_t)b * N + (size_t)py * W + px] = is_depth ? g : g * ddepth_ddisp(depth, p.ds);
     }
     const int blk = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    {
+    if (p.dh) {
+        // [4][B * tiles]: sum reproj*mask_r, sum mask_r, sum proxy*mask_h, sum mask_h
+        const int nblk = p.B * gridDim.x * gridDim.y;
+        float s = block_sum(dh_r, red);
+        if (tid == 0) p.loss_partial[blk] = s;
+        s = block_sum(dh_rm, red);
+        if (tid == 0) p.loss_partial[nblk + blk] = s;
+        s = block_sum(dh_h, red);
+        if (tid == 0) p.loss_partial[2 * nblk + blk] = s;
+        s = block_sum(dh_hm, red);
+        if (tid == 0) p.loss_partial[3 * nblk + blk] = s;
+    } else {
         const float s = block_sum(loss_local, red);
         if (tid == 0) p.loss_partial[blk] = s;
     }
@@ -436,6 +501,35 @@ int dmh_identity_loss(const float* target, const float* const* src_host, int F, 
 
 int dmh_photo_tiles(int H, int W) { return ceil_div(W, PH_TW) * ceil_div(H, PH_TH); }
 
+// depth-hints arguments handed from dmh_photo_scale_dh to the shared launcher below (same thread, same call)
+struct DhNext { bool armed; const float *hint_reproj, *hint_depth, *hint_valid; float* grad_hint; };
+static thread_local DhNext g_dh_next = {false, nullptr, nullptr, nullptr, nullptr};
+
+int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
+                    const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K, const float* ident,
+                    const float* noise, int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
+                    float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
+                    float* const* warped_host, dmh_stream_t stream);
+
+int dmh_photo_scale_dh(const float* target, const float* const* src_host, const float* const* T_host, int F,
+                       const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K,
+                       const float* ident, const float* noise, const float* hint_reproj, const float* hint_depth,
+                       const float* hint_valid, int B, int H, int W, float min_depth, float max_depth, int flags,
+                       float* sums_partial, float* grad_disp, float* grad_disp_hint, float* grad_P_partial,
+                       uint8_t* sel, dmh_stream_t stream) {
+    DMH_REQUIRE(!hint_reproj || (hint_depth && hint_valid && grad_disp_hint),
+                "dmh_photo_scale_dh: depth hints need hint_depth, hint_valid and grad_disp_hint");
+    DMH_REQUIRE(!noise || ident, "dmh_photo_scale_dh: noise without identity losses");
+    g_dh_next.armed = true;
+    g_dh_next.hint_reproj = hint_reproj; g_dh_next.hint_depth = hint_depth; g_dh_next.hint_valid = hint_valid;
+    g_dh_next.grad_hint = grad_disp_hint;
+    const int rc = dmh_photo_scale(target, src_host, T_host, F, disp, disp_h, disp_w, K, inv_K, ident, noise, B, H, W,
+                                   min_depth, max_depth, flags | DMH_PHOTO_FORCE_GENERIC, 1.0f, sums_partial, grad_disp,
+                                   grad_P_partial, sel, nullptr, stream);
+    g_dh_next.armed = false;
+    return rc;
+}
+
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
                     const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K, const float* ident,
                     const float* noise, int B, int H, int W, float min_depth, float max_depth, int flags, float grad_scale,
@@ -481,6 +575,12 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
     p.ds.min_disp = is_depth ? 0.f : (float)(1.0 / (double)max_depth);
     p.ds.range = is_depth ? 0.f : (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
     p.grad_scale = grad_scale;
+    p.dh = 0; p.hint_reproj = nullptr; p.hint_depth = nullptr; p.hint_valid = nullptr; p.grad_hint = nullptr;
+    if (g_dh_next.armed) {       // set by dmh_photo_scale_dh on this thread for the call it forwards
+        p.dh = 1; p.hint_reproj = g_dh_next.hint_reproj; p.hint_depth = g_dh_next.hint_depth;
+        p.hint_valid = g_dh_next.hint_valid; p.grad_hint = g_dh_next.grad_hint;
+        g_dh_next.armed = false;
+    }
     dim3 grid(ceil_div(W, PH_TW), ceil_div(H, PH_TH), B);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = DMH_OK;

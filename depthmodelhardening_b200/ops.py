@@ -491,8 +491,8 @@ class _Objective(torch.autograd.Function):
             _, _, h, w = dshapes[s]
             gd = torch.empty(B, 1, h, w, device=G[s].device, dtype=torch.float32)
             check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
-                                    ptr(gs[s:s + 1]) if gs is not None else None, 1.0 / S, B, h, w, H, W, ptr(gd),
-                                    stream()), "disp_grad")
+                                    ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
+                                    ptr(gd), stream()), "disp_grad")
             grads_disp.append(gd.view(dshapes[s]))
         g_T = [None] * n_src
         if need_T:

@@ -160,6 +160,23 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
                     float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
                     float* const* warped_host, dmh_stream_t stream);
 
+/* Depth-hints variant of dmh_photo_scale (A18; DepthNetworks/depth-hints/trainer.py:476-525, 541-590, 629-727),
+ * one scale: same fused warp + SSIM/L1 + backward, but the per-pixel decision is the depth-hints one -- min (or
+ * mean) over the source frames first, ONE tie-break noise plane noise (B,1,H,W) added to the identity minimum,
+ * argmin over [reprojection, identity, hint_reproj]; reprojection mask = argmin != identity, hint mask =
+ * argmin == hint.  hint_reproj (B,1,H,W) = reprojection loss of the depth-hint warp + 1000*(1-hint_valid)
+ * (NULL: use_depth_hints off), hint_depth / hint_valid (B,1,H,W).
+ * Outputs: sums_partial = 4 x B*dmh_photo_tiles floats, per-CTA partial sums of [reproj*mask_r, mask_r,
+ * log(|hint-depth|+1)*valid*mask_h, mask_h]; grad_disp = d(sum reproj*mask_r)/d(up-sampled disp) and
+ * grad_disp_hint = d(sum proxy*mask_h)/d(up-sampled disp), both UN-normalised (the masked-mean denominators are
+ * known only after the pass: the caller divides); grad_P_partial as in dmh_photo_scale; sel = argmin index.   */
+int dmh_photo_scale_dh(const float* target, const float* const* src_host, const float* const* T_host, int F,
+                       const float* disp, int disp_h, int disp_w, const float* K, const float* inv_K,
+                       const float* ident, const float* noise, const float* hint_reproj, const float* hint_depth,
+                       const float* hint_valid, int B, int H, int W, float min_depth, float max_depth, int flags,
+                       float* sums_partial, float* grad_disp, float* grad_disp_hint, float* grad_P_partial,
+                       uint8_t* sel, dmh_stream_t stream);
+
 /* -- fused multi-scale objective glue (M2/trainer.py:589-674) -------------------
  * dmh_smooth_fused: A16 forward + gradient w.r.t. the mean-normalised disparity in
  *   one pass: gN (B,1,h,w) = d(smooth loss)/d(norm disp); ws (workspace of
@@ -173,7 +190,9 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
  *   grad_disp (B,1,h,w) = u * [ interpolate^T(G_full (B,1,H,W)) + smooth_weight *
  *   (gN*inv_mean - corr) ],  u = *g_total * inv_S + *g_scale (device scalars, either
  *   nullable); gN nullable (no smoothness term); img_scalars = the (B,2) slice of
- *   this scale.                                                                   */
+ *   this scale.  g_smooth (nullable device scalar): separate upstream weight of the
+ *   smoothness term: grad = u * interpolate^T(G_full) + *g_smooth * smooth_weight * (...)
+ *   (depth-hints objective, whose photometric gradients carry their own weights).  */
 long long dmh_smooth_fused_workspace_floats(int B, int h, int w);
 int dmh_smooth_fused(const float* disp, const float* img, int B, int C, int h, int w, float* ws, float* gN,
                      dmh_stream_t stream);
@@ -183,8 +202,8 @@ int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const
                          const float* smooth_weight_host, double photo_den, void* workspace, float* img_scalars,
                          float* losses, dmh_stream_t stream);
 int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars, float smooth_weight,
-                  const float* g_total, const float* g_scale, float inv_S, int B, int h, int w, int H, int W,
-                  float* grad_disp, dmh_stream_t stream);
+                  const float* g_total, const float* g_scale, const float* g_smooth, float inv_S, int B, int h, int w,
+                  int H, int W, float* grad_disp, dmh_stream_t stream);
 
 /* ======================= stage 1: physical patch attack ======================= */
 
@@ -281,6 +300,10 @@ int dmh_cost_volume(const float* current_feats, const float* lookup_feats, const
  * every float numerator on the current device (exhaustive over all significands; first call per constant
  * launches a small kernel and synchronises, then cached).  0: the kernels use IEEE division for that size. */
 int dmh_const_div_exact(int c);
+
+/* out[i] = a[0] * x[i] + b[0] * y[i] with DEVICE scalars a, b (no host sync); out may alias x or y. */
+int dmh_axpby_dev(const float* a, const float* x, const float* b, const float* y, long long n, float* out,
+                  dmh_stream_t stream);
 
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
