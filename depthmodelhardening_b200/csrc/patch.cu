@@ -167,6 +167,10 @@ __device__ __forceinline__ AaSpan aa_span(int i, int in_size, float scale) {
 #define PA_TH 16            // output tile height
 #define PA_THREADS 256
 
+// NT: compile-time bound on the anti-aliasing taps per axis: a span holds at most ceil(2 * support) pixels, i.e. 3
+// when both scale factors are < 1.5 (the 1242x375 -> 1024x320 case), else AA_MAXT.  Fixed trip counts, fully
+// unrolled; taps beyond a span carry weight 0 and are clamped onto the tile.
+template <int NT>
 __global__ void __launch_bounds__(PA_THREADS)
 patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
                        const float* __restrict__ scenes, const float* __restrict__ coeffs,
@@ -211,51 +215,75 @@ patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict_
         bx0 = __ldg(bbox + b * 4); by0 = __ldg(bbox + b * 4 + 1); bx1 = __ldg(bbox + b * 4 + 2); by1 = __ldg(bbox + b * 4 + 3);
         tile_hits = !(cx0 > bx1 || cx0 + cw - 1 < bx0 || cy0 > by1 || cy0 + ch - 1 < by0);
     }
-    for (int i = tid; i < ch * cw; i += PA_THREADS) {
-        const int r = i / cw, c = i % cw;
-        const int cy = cy0 + r, cx = cx0 + c;            // always inside the canvas by construction of the spans
-        const size_t so = (size_t)cy * iw + cx;
-        const float s0 = __ldg(sc + so), s1 = __ldg(sc + IN + so), s2 = __ldg(sc + 2 * IN + so);
-        float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
-        PatchTaps t;
-        t.any = false;
-        if (tile_hits && cx >= bx0 && cx <= bx1 && cy >= by0 && cy <= by1) {
-            float ix, iy;
-            perspective_src(hm, cx, cy, iw, ih, ix, iy);
-            t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+    // a warp takes a tile row, its lanes the columns (no index division); a tile narrower than NT columns is
+    // zero-filled up to NT so that the fixed-count loops below never read uninitialised shared memory
+    const int lane = tid & 31, wid = tid >> 5;
+    const int cwz = max(cw, NT);
+    for (int r = wid; r < ch; r += PA_THREADS / 32) {
+        const int cy = cy0 + r;
+        const bool row_in = true;
+        for (int c0 = 0; c0 < cwz; c0 += 96) {
+            float sv[3][3];
+            bool in[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {                 // up to 9 scene loads in flight per lane
+                const int c = c0 + 32 * u + lane;
+                in[u] = row_in && c < cw;
+                const size_t so = (size_t)cy * iw + cx0 + c;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sv[u][k] = in[u] ? __ldg(sc + k * IN + so) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int c = c0 + 32 * u + lane;
+                if (c >= cwz) continue;
+                const int cx = cx0 + c;
+                float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                if (in[u] && tile_hits && cx >= bx0 && cx <= bx1 && cy >= by0 && cy <= by1) {
+                    float ix, iy;
+                    perspective_src(hm, cx, cy, iw, ih, ix, iy);
+                    const PatchTaps t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+                    if (t.any) {
+                        m = sample_plane(pmask, t, pw);
+                        o0 = sample_plane(patch, t, pw);
+                        o1 = sample_plane(patch + PN, t, pw);
+                        o2 = sample_plane(patch + 2 * PN, t, pw);
+                    }
+                }
+                const float om = sub_rn(1.0f, m);
+                const size_t o = (size_t)r * cw_max + c;
+                comp[o] = add_rn(mul_rn(sv[u][0], om), mul_rn(o0, m));
+                comp[plane + o] = add_rn(mul_rn(sv[u][1], om), mul_rn(o1, m));
+                comp[2 * plane + o] = add_rn(mul_rn(sv[u][2], om), mul_rn(o2, m));
+                comp[3 * plane + o] = m;
+            }
         }
-        if (t.any) {
-            m = sample_plane(pmask, t, pw);
-            o0 = sample_plane(patch, t, pw);
-            o1 = sample_plane(patch + PN, t, pw);
-            o2 = sample_plane(patch + 2 * PN, t, pw);
-        }
-        const float om = sub_rn(1.0f, m);
-        const size_t o = (size_t)r * cw_max + c;
-        comp[o] = add_rn(mul_rn(s0, om), mul_rn(o0, m));
-        comp[plane + o] = add_rn(mul_rn(s1, om), mul_rn(o1, m));
-        comp[2 * plane + o] = add_rn(mul_rn(s2, om), mul_rn(o2, m));
-        comp[3 * plane + o] = m;
     }
     __syncthreads();
     const int tx = tid % PA_TW;
     const int ox = ox0 + tx;
     if (ox >= ow) return;
-    const int xl = x_lo[tx] - cx0, xn = x_n[tx];
+    const int xl = max(min(x_lo[tx] - cx0, cw - NT), 0);  // (the span itself never exceeds the tile)
+    const int xshift = (x_lo[tx] - cx0) - xl;             // > 0 only if the clamp moved the window: shift the weights
+    float wxr[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) wxr[i] = (i - xshift >= 0 && i - xshift < AA_MAXT) ? x_w[tx][i - xshift] : 0.f;
     const size_t ON = (size_t)oh * ow;
 #pragma unroll
     for (int k = 0; k < PA_TH / (PA_THREADS / PA_TW); ++k) {
         const int ty = tid / PA_TW + k * (PA_THREADS / PA_TW);
         const int oy = oy0 + ty;
         if (oy >= oh) continue;
-        const int yl = y_lo[ty] - cy0, yn = y_n[ty];
+        const int yl = y_lo[ty] - cy0;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < yn; ++j) {
-            const float wy = y_w[ty][j];
-            const float* row = comp + (size_t)(yl + j) * cw_max + xl;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float wy = y_w[ty][j];                  // 0 beyond the span
+            const float* row = comp + (size_t)min(yl + j, ch - 1) * cw_max + xl;
             float h[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int i = 0; i < xn; ++i) {
-                const float wx = x_w[tx][i];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const float wx = wxr[i];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) h[p] = fmaf(row[p * plane + i], wx, h[p]);
             }
@@ -393,16 +421,23 @@ int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float
     const int cw_max = aa_tile_extent(PA_TW, sx), ch_max = aa_tile_extent(PA_TH, sy);
     const size_t smem = sizeof(float) * 4 * (size_t)cw_max * ch_max;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(patch_apply_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(patch_apply_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(patch_apply_fwd_kernel<AA_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("dmh_patch_apply_fwd: %zu B shared memory unavailable: %s", smem, cudaGetErrorString(e));
             return DMH_ERR_CUDA;
         }
     }
     dim3 grid(ceil_div(ow, PA_TW), ceil_div(oh, PA_TH), B);
-    DMH_LAUNCH(patch_apply_fwd_kernel, grid, PA_THREADS, smem, (cudaStream_t)stream)(
-        patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
-        mask_out);
+    if (sy < 1.5f && sx < 1.5f)
+        DMH_LAUNCH(patch_apply_fwd_kernel<3>, grid, PA_THREADS, smem, (cudaStream_t)stream)(
+            patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
+            mask_out);
+    else
+        DMH_LAUNCH(patch_apply_fwd_kernel<AA_MAXT>, grid, PA_THREADS, smem, (cudaStream_t)stream)(
+            patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
+            mask_out);
     DMH_CHECK_LAUNCH("dmh_patch_apply_fwd");
     return DMH_OK;
 }

@@ -92,6 +92,31 @@ def test_fused_patch_apply_vs_oracle(dev, batch):
     assert_close_arb(gp2, obj.grad, o64.grad, TOL, "grad patch (fast path)")
 
 
+@pytest.mark.parametrize("size", [(321, 1030), (200, 650), (375, 1242), (160, 512)])
+def test_fused_patch_apply_ragged_output_sizes(dev, size):
+    """Output sizes that are not multiples of the 64 x 16 tile, both tap-count instantiations of the resize
+    (scale < 1.5: 3 taps per axis; larger down-scales: generic 8) and the identity resize: forward and the
+    gradient to the patch against the oracle."""
+    from depthmodelhardening_b200 import patch_ops
+    pbt = synth.patch_batch(batch=2, seed=3)
+    up = synth.randn((2, 3) + size, 904) * 1e-3
+    obj = pbt.obj.clone().requires_grad_(True)
+    adv_ref, m_ref = OQ.apply_patch(obj, pbt.mask, pbt.scenes, pbt.z0, pbt.alpha, P34, size=size)
+    (adv_ref * up).sum().backward()
+    o64 = pbt.obj.double().requires_grad_(True)
+    adv64, m64 = OQ.apply_patch(o64, pbt.mask.double(), pbt.scenes.double(), pbt.z0, pbt.alpha, P34, size=size)
+    (adv64 * up.double()).sum().backward()
+    g = pbt.to(dev)
+    co = patch_ops.homographies(pbt.z0, pbt.alpha, P34).to(dev)
+    obj_d = g.obj.clone().requires_grad_(True)
+    adv, m = patch_ops.apply_patch(obj_d, g.mask, g.scenes, co, size=size)
+    (adv * up.to(dev)).sum().backward()
+    assert torch.isfinite(adv).all() and torch.isfinite(m).all()
+    assert_close_arb(adv, adv_ref, adv64, TOL, "adv scene %s" % (size,))
+    assert_close_arb(m, m_ref, m64, TOL, "resized mask")
+    assert_close_arb(obj_d.grad, obj.grad, o64.grad, TOL, "grad patch")
+
+
 def test_fused_patch_apply_vs_golden(dev):
     from depthmodelhardening_b200 import patch_ops
     g = load_golden("patch")
