@@ -5,6 +5,9 @@ SURVEY.md section 8 timed on one GPU with CUDA events, inputs resident in HBM, o
   dh        depth-hints objective (A18, BASELINE config 4): B=32, 1024x320, [0,'s'], 4 scales, fwd+bwd
   md_f2     multi-source photometric objective (BASELINE config 5): B=16, [0,-1,1], 1024x320 and 2048x640
   costvol   ManyDepth cost volume (next-3): B=16, 2 lookups, 96 bins, 16 ch at 80x256 (1024x320 / 4)
+  attack    CONTEXT: the whole L0 / L-inf attack loop of the drop-in classes with a stock
+            PyTorch random-init ResNet-18 monodepth2-style depth network in the loop (the network is outside
+            the graft), Ba=32 scenes of 375x1242: PGD iterations per second end to end on the device
 
 usage: python bench_extra.py [--steps K] [--warmup W] [--only dh,md_f2,costvol]
 """
@@ -43,7 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="dh,md_f2,costvol")
+    ap.add_argument("--only", default="dh,md_f2,costvol,attack")
     args = ap.parse_args()
     from depthmodelhardening_b200 import _lib, synth
     lib = _lib.load()
@@ -110,6 +113,82 @@ def main():
                           "algorithmic_bytes": alg, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
                           "taps_gbs": B * D * L * h * w * 4 * 64 / (ms * 1e-3) / 1e9,
                           "note": "gather-bound: taps_gbs = bytes requested from L1/L2 by the bilinear taps"}))
+
+
+    if "attack" in want:
+        attack_context(dev, args)
+
+
+class _DepthNetR18(torch.nn.Module):
+    """Stock PyTorch stand-in for monodepth2's ResNet-18 encoder + DepthDecoder (random init, outside the
+    graft): torchvision resnet18 trunk, 5 up-convolution stages with skip connections, sigmoid disparity."""
+
+    def __init__(self):
+        super().__init__()
+        import torchvision
+        r = torchvision.models.resnet18(weights=None)
+        self.stem = torch.nn.Sequential(r.conv1, r.bn1, r.relu)
+        self.pool, self.l1, self.l2, self.l3, self.l4 = r.maxpool, r.layer1, r.layer2, r.layer3, r.layer4
+        enc, dec = [64, 64, 128, 256, 512], [16, 32, 64, 128, 256]
+        conv = lambda i, o: torch.nn.Sequential(torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(i, o, 3), torch.nn.ELU())
+        self.up0 = torch.nn.ModuleList([conv(enc[4] if i == 4 else dec[i + 1], dec[i]) for i in range(5)])
+        self.up1 = torch.nn.ModuleList([conv(dec[i] + (enc[i - 1] if i > 0 else 0), dec[i]) for i in range(5)])
+        self.head = torch.nn.Sequential(torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(dec[0], 1, 3))
+
+    def forward(self, x):
+        import torch.nn.functional as F
+        f0 = self.stem((x - 0.45) / 0.225)
+        f1 = self.l1(self.pool(f0)); f2 = self.l2(f1); f3 = self.l3(f2); f4 = self.l4(f3)
+        feats, y = [f0, f1, f2, f3, f4], f4
+        for i in range(4, -1, -1):
+            y = F.interpolate(self.up0[i](y), scale_factor=2, mode="nearest")
+            if i > 0:
+                y = torch.cat([y, feats[i - 1]], 1)
+            y = self.up1[i](y)
+        return torch.sigmoid(self.head(y))
+
+
+def attack_context(dev, args):
+    import random
+    import tempfile
+    import time
+    import numpy as np
+    from depthmodelhardening_b200 import attacks, synth
+    torch.manual_seed(0)
+    net = _DepthNetR18().to(dev).eval()
+    tmp = tempfile.mkdtemp(prefix="dmh_calib_")
+    os.makedirs(os.path.join(tmp, "training", "calib"))
+    with open(os.path.join(tmp, "training", "calib", "003086.txt"), "w") as f:
+        p2 = " ".join(repr(v) for v in __import__("depthmodelhardening_b200.patch_ops", fromlist=["x"]).KITTI_P2_003086)
+        for k in ("P0", "P1", "P2", "P3"):
+            f.write("%s: %s\n" % (k, p2))
+        f.write("R0_rect: 1 0 0 0 1 0 0 0 1\nTr_velo_to_cam: 1 0 0 0 0 1 0 0 0 0 1 0\nTr_imu_to_velo: 1 0 0 0 0 1 0 0 0 0 1 0\n")
+    attacks.object_dataset_root = tmp
+    Ba = 32
+    pt = synth.patch_batch(batch=Ba, seed=3).to(dev)
+    # 32 placements per iteration without replacement need >= 32 distances / angles (physicalTrans.py:146-155)
+    dist = [5 + 0.2 * i for i in range(40)]
+    for name, make in (("l0", lambda: attacks.Phy_obj_atk_l0(net, pt.obj, pt.mask, adam_lr=0.5, steps=5, mask_wt=0.06,
+                                                            l0_thresh=0.1, dist_range=dist)),
+                       ("linf", lambda: attacks.Phy_obj_atk(net, pt.obj, pt.mask, eps=0.1, alpha=0.02, steps=10,
+                                                            random_start=False, dist_range=dist))):
+        atk = make()
+        for tr in (atk.phy_trans_adv, atk.phy_trans_ben):
+            tr.angle_range = [-30 + 1.5 * i for i in range(41)]
+        random.seed(0); np.random.seed(0)
+        atk(pt.scenes, Ba)                                   # warm-up (cuDNN autotune, homography cache)
+        torch.cuda.synchronize()
+        random.seed(1); np.random.seed(1)
+        t0 = time.perf_counter()
+        atk(pt.scenes, Ba)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        iters = 10 if name == "l0" else 10
+        print(json.dumps({"workload": "CONTEXT: whole %s attack call incl. a stock ResNet-18 depth net fwd+bwd per "
+                                      "iteration (network outside the graft)" % name, "attack_batch": Ba,
+                          "iterations": iters, "s_per_call": dt, "pgd_iterations_per_s": iters / dt,
+                          "note": "wall clock around one forward() of the drop-in class, device-synchronised; "
+                                  "the graft's own share per iteration is bench.py stages.patch_pgd_ms"}))
 
 
 if __name__ == "__main__":
