@@ -2,6 +2,7 @@
 """Secondary measurements (NOT the driver's bench contract -- that is bench.py): the widened rows of
 SURVEY.md section 8 timed on one GPU with CUDA events, inputs resident in HBM, one JSON line per workload:
 
+  cfg1      BASELINE configs[0] (B=4, 640x192, [0,'s']): eager vs CUDA-graph replay (objective.GraphedObjective)
   dh        depth-hints objective (A18, BASELINE config 4): B=32, 1024x320, [0,'s'], 4 scales, fwd+bwd
   md_f2     multi-source photometric objective (BASELINE config 5): B=16, [0,-1,1], 1024x320 and 2048x640
   costvol   ManyDepth cost volume (next-3): B=16, 2 lookups, 96 bins, 16 ch at 80x256 (1024x320 / 4)
@@ -46,13 +47,36 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="dh,md_f2,costvol,attack")
+    ap.add_argument("--only", default="cfg1,dh,md_f2,costvol,attack")
     args = ap.parse_args()
     from depthmodelhardening_b200 import _lib, synth
     lib = _lib.load()
     dev = torch.device("cuda:0")
     peak = peak_gbs()
     want = args.only.split(",")
+
+    if "cfg1" in want:
+        from depthmodelhardening_b200 import objective
+        B, H, W = 4, 192, 640
+        pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, "s"), seed=4).to(dev)
+        disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+
+        def eager():
+            for d in disps.values():
+                d.grad = None
+            losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, pb.T, pb.frame_ids, pb.scales, H, W,
+                                                     noise=pb.noise)
+            losses["loss"].backward()
+        ms_e = timed(eager, 10 * args.steps, args.warmup)
+        g = objective.GraphedObjective(pb.color, pb.disp, pb.K, pb.inv_K, pb.T, pb.frame_ids, pb.scales, H, W,
+                                       noise=pb.noise)
+        ms_g = timed(lambda: g.graph.replay(), 10 * args.steps, args.warmup)
+        ms_c = timed(lambda: g(pb.color, pb.disp, None, None, None, None), 10 * args.steps, args.warmup)
+        print(json.dumps({"workload": "configs[0]: photometric objective fwd+bwd, B=4 640x192 stereo", "B": B, "H": H,
+                          "W": W, "eager_ms": ms_e, "graph_replay_ms": ms_g, "graph_with_input_copies_ms": ms_c,
+                          "mpix_per_s_eager": B * H * W / ms_e / 1e3, "mpix_per_s_graph": B * H * W / ms_g / 1e3,
+                          "note": "eager is launch-bound at this size (~25 launches per step); "
+                                  "objective.GraphedObjective replays one captured CUDA graph"}))
 
     if "dh" in want:
         from depthmodelhardening_b200 import depth_hints as DH

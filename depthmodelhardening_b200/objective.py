@@ -175,3 +175,62 @@ def fused_compute_losses(self, inputs, outputs):
         losses["loss/{}".format(s)] = pl["loss/{}".format(s)]
     losses["loss"] = total_loss + pl["loss"]
     return losses
+
+
+# ----------------------------------------------------------------------------- CUDA-graph replay (small batches)
+class GraphedObjective:
+    """Forward + backward of `photometric_losses` captured once into a CUDA graph and replayed.
+
+    At the reference's CPU-runnable configuration (B=4, 640x192) one step is ~25 short launches and eager
+    PyTorch is launch-bound (0.55 ms per step against 0.22 ms of GPU work, measured on B200); replaying a graph
+    removes the Python / launch overhead.  Shapes, options and the set of tensors are frozen at construction;
+    `__call__` copies new values into the static buffers (device-to-device), replays, and returns the static
+    loss / per-scale losses / disparity gradients (valid until the next call).  Tie-break noise: a static
+    buffer per scale that the caller may refresh through `noise=`; it is NOT redrawn by the replay."""
+
+    def __init__(self, colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids, scales, height, width,
+                 noise: Optional[Dict] = None, warmup: int = 3, **opts):
+        dev = colors[(0, 0)].device
+        self.frame_ids, self.scales, self.hw, self.opts = list(frame_ids), list(scales), (height, width), dict(opts)
+        self.colors = {k: v.detach().clone() for k, v in colors.items()}
+        self.disps = {s: disps[s].detach().clone().requires_grad_(True) for s in self.scales}
+        self.K, self.inv_K = K.detach().clone(), inv_K.detach().clone()
+        self.Ts = {k: v.detach().clone() for k, v in Ts.items()}
+        n_src = len(self.frame_ids) - 1
+        automask = not self.opts.get("disable_automasking", False)
+        n_ident = 0 if not automask else (1 if self.opts.get("avg_reprojection", False) else n_src)
+        self.noise = None
+        if n_ident:
+            B = self.colors[(0, 0)].shape[0]
+            self.noise = {s: (noise[s][:, :n_ident].detach().clone() if noise is not None else
+                              tie_break_noise((B, n_ident, height, width), dev, "device")) for s in self.scales}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside the capture (lazy one-time set-up)
+            for _ in range(max(1, warmup)):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses, self.grads = self._run()
+
+    def _run(self):
+        losses, _ = photometric_losses(self.colors, self.disps, self.K, self.inv_K, self.Ts, self.frame_ids,
+                                       self.scales, self.hw[0], self.hw[1], noise=self.noise, **self.opts)
+        grads = torch.autograd.grad(losses["loss"], [self.disps[s] for s in self.scales])
+        return losses, dict(zip(self.scales, grads))
+
+    @torch.no_grad()
+    def __call__(self, colors: Optional[Dict] = None, disps: Optional[Dict] = None, K=None, inv_K=None,
+                 Ts: Optional[Dict] = None, noise: Optional[Dict] = None):
+        for dst, src in ((self.colors, colors), (self.disps, disps), (self.Ts, Ts), (self.noise, noise)):
+            if src is not None and dst is not None:
+                for k, v in src.items():
+                    if k in dst:
+                        dst[k].copy_(v if dst is not self.noise else v[:, :dst[k].shape[1]], non_blocking=True)
+        if K is not None:
+            self.K.copy_(K, non_blocking=True)
+        if inv_K is not None:
+            self.inv_K.copy_(inv_K, non_blocking=True)
+        self.graph.replay()
+        return self.losses, self.grads

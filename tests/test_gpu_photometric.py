@@ -387,3 +387,28 @@ def test_constant_division_is_verified_exact(dev):
     # and the check is not vacuous: some constants do fail it (they take IEEE division)
     fails = [c for c in range(3, 400, 2) if lib.dmh_const_div_exact(c) == 0]
     print("constants failing the 3-instruction division:", fails[:10], len(fails))
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    """objective.GraphedObjective: the captured fwd+bwd replays bit-identically to the eager path, also after
+    new inputs are copied into its static buffers (BASELINE configs[0] shape family: B=4, stereo)."""
+    from depthmodelhardening_b200 import objective
+    a = synth.photo_batch(batch=4, height=96, width=160, frame_ids=(0, "s"), seed=61).to(dev)
+    b = synth.photo_batch(batch=4, height=96, width=160, frame_ids=(0, "s"), seed=62).to(dev)
+
+    def eager(pb):
+        disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
+        losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, pb.T, pb.frame_ids, pb.scales,
+                                                 pb.height, pb.width, noise=pb.noise)
+        losses["loss"].backward()
+        return losses["loss"].detach().clone(), {s: d.grad.clone() for s, d in disps.items()}
+
+    g = objective.GraphedObjective(a.color, a.disp, a.K, a.inv_K, a.T, a.frame_ids, a.scales, a.height, a.width,
+                                   noise=a.noise)
+    for pb in (a, b, a):
+        losses, grads = g(pb.color, pb.disp, pb.K, pb.inv_K, pb.T, pb.noise)
+        torch.cuda.synchronize()
+        l_ref, g_ref = eager(pb)
+        assert torch.equal(losses["loss"], l_ref)
+        for s in pb.scales:
+            assert torch.equal(grads[s], g_ref[s])
