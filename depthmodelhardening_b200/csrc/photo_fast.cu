@@ -522,57 +522,72 @@ ident_fast_kernel(const IdentParams p) {
     const size_t N = (size_t)H * W;
     const float* sp = p.src[f] + (size_t)b * 3 * N;
     const float* tp = p.target + (size_t)b * 3 * N;
-    for (int i = tid; i < ID_N; i += 256) {
-        const int r = i / ID_R, c = i - r * ID_R;
-        const size_t o = (size_t)ext_to_img(y0 - 1 + r, H) * W + ext_to_img(x0 - 1 + c, W);
+    {   // tile + 1-px reflect halo: a warp takes a row (index maths once per row / per lane), 6 loads in flight
+        const int lane = tid & 31, wid = tid >> 5;
+        const int ixa = ext_to_img(x0 - 1 + lane, W);
+        const int ixb = ext_to_img(x0 - 1 + 32 + (lane & 1), W);          // columns 32, 33 (lanes 0, 1)
+        for (int r = wid; r < ID_R; r += 8) {
+            const size_t ro = (size_t)ext_to_img(y0 - 1 + r, H) * W;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            xs[ch][i] = __ldg(sp + ch * N + o);
-            ys[ch][i] = __ldg(tp + ch * N + o);
+            for (int ch = 0; ch < 3; ++ch) {
+                xs[ch][r * ID_R + lane] = __ldg(sp + ch * N + ro + ixa);
+                ys[ch][r * ID_R + lane] = __ldg(tp + ch * N + ro + ixa);
+            }
+            if (lane < 2) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    xs[ch][r * ID_R + 32 + lane] = __ldg(sp + ch * N + ro + ixb);
+                    ys[ch][r * ID_R + 32 + lane] = __ldg(tp + ch * N + ro + ixb);
+                }
+            }
         }
     }
     __syncthreads();
+    // same lane-typed SSIM arithmetic as the fused kernels (channels 0,1 packed, channel 2 scalar): the
+    // identity loss and the reprojection loss must come out of identical arithmetic (automask ties)
     const int c = tid & 31, strip = tid >> 5;           // 8 strips of 4 rows
     const int px = x0 + c;
-    Row5 hist[3][2];
-    float cen_x[3], cen_y[3];
+    Row5T<float2> histP[2];
+    Row5T<float> histS[2];
+    float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;
+    float cenxS = 0.f, cenyS = 0.f;
 #pragma unroll
     for (int rr = 0; rr < 6; ++rr) {
         const int r2 = 4 * strip + rr;                   // halo-tile row
-        Row5 cur[3];
-        float mid_x[3], mid_y[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float* xr = &xs[ch][r2 * ID_R + c];
-            const float* yr = &ys[ch][r2 * ID_R + c];
-            cur[ch] = row5(xr[0], xr[1], xr[2], yr[0], yr[1], yr[2]);
-            mid_x[ch] = xr[1]; mid_y[ch] = yr[1];
-        }
+        const float* x0p = &xs[0][r2 * ID_R + c];
+        const float* y0p = &ys[0][r2 * ID_R + c];
+        const float2 xa = make_float2(x0p[0], x0p[ID_N]), xb = make_float2(x0p[1], x0p[ID_N + 1]),
+                     xc = make_float2(x0p[2], x0p[ID_N + 2]);
+        const float2 ya = make_float2(y0p[0], y0p[ID_N]), yb = make_float2(y0p[1], y0p[ID_N + 1]),
+                     yc = make_float2(y0p[2], y0p[ID_N + 2]);
+        const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
+        const float* x2p = x0p + 2 * ID_N;
+        const float* y2p = y0p + 2 * ID_N;
+        const Row5T<float> curS = row5(x2p[0], x2p[1], x2p[2], y2p[0], y2p[1], y2p[2]);
         if (rr >= 2) {
             const int py = y0 + 4 * strip + rr - 2;
             if (py < H && px < W) {
-                float l1 = 0.f, ss = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    l1 += fabsf(cen_y[ch] - cen_x[ch]);
-                    if (!p.no_ssim) {
-                        const SsimStats st = ssim_stats_rows(hist[ch][0], hist[ch][1], cur[ch]);
-                        float pass;
-                        SsimCoef k;
-                        ss += ssim_value_coef(st, pass, k);
-                    }
+                float l1 = fabsf(cenyP.x - cenxP.x);
+                l1 += fabsf(cenyP.y - cenxP.y);
+                l1 += fabsf(cenyS - cenxS);
+                float ss = 0.f;
+                if (!p.no_ssim) {
+                    float2 passP;
+                    SsimCoefT<float2> kP;
+                    const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
+                    float passS;
+                    SsimCoefT<float> kS;
+                    const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
+                    ss = (vP.x + vP.y) + vS;
                 }
                 l1 *= (1.0f / 3.0f);
                 const float rp = p.no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
                 p.out[((size_t)b * p.F + f) * N + (size_t)py * W + px] = rp;
             }
         }
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            hist[ch][0] = hist[ch][1];
-            hist[ch][1] = cur[ch];
-            cen_x[ch] = mid_x[ch]; cen_y[ch] = mid_y[ch];
-        }
+        histP[0] = histP[1]; histP[1] = curP;
+        histS[0] = histS[1]; histS[1] = curS;
+        cenxP = xb; cenyP = yb; cenxS = x2p[1]; cenyS = y2p[1];
     }
 }
 
