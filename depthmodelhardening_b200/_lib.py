@@ -49,6 +49,7 @@ SIGNATURES = {
     "dmh_warp_bwd_blocks": (_i, [_i, _i]),
     "dmh_warp_bwd": (_i, [_f, _f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_identity_loss": (_i, [_f, C.POINTER(C.c_void_p), _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_identity_loss_pack": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_photo_tiles": (_i, [_i, _i]),
     "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                              _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),

@@ -42,6 +42,15 @@ DMH_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
 DMH_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
 #endif
 
+// MUFU.RCP (1 ulp) on the device, IEEE division on the host emulation.  Used only where ~1e-7 relative error is
+// irrelevant: the SSIM denominator d = B1*B2 >= C1*C2 > 0 (value tolerance 1e-5) and the 1/z of the BACKWARD
+// chain (gradient tolerance 1e-5); never in the forward coordinate chain, whose floor() picks the taps.
+#if defined(__CUDA_ARCH__)
+DMH_HD float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+DMH_HD float fast_rcp(float x) { return 1.0f / x; }
+#endif
+
 // ---------------------------------------------------------------------------
 // Camera model for one batch item: P = (K @ T)[:3,:] and inv_K[:3,:3].
 struct Camera {
@@ -181,7 +190,7 @@ DMH_HD WarpCoord warp_coord(const Camera& cam, float x, float y, float depth, in
     float p[3];
     project_point(cam, pt, p);
     const float z = add_rn(p[2], eps);
-    wc.inv_z = 1.0f / z;
+    wc.inv_z = fast_rcp(z);          // backward chain only
     wc.u_raw = div_rn(p[0], z);
     wc.v_raw = div_rn(p[1], z);
     const float nu = FASTDIV ? div_const(wc.u_raw, (float)(W - 1), rcw) : div_rn(wc.u_raw, (float)(W - 1));
@@ -284,13 +293,6 @@ DMH_HD float vmul(float a, float b) { return mul_rn(a, b); }
 DMH_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
 DMH_HD float vclamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 DMH_HD float vpass01(float v) { return (v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f; }
-// reciprocal of the SSIM denominator d = B1*B2 >= C1*C2 > 0: MUFU.RCP (2 ulp) on the device -- the error it
-// adds to the SSIM value is ~1e-7, far below the 1e-5 tolerance; IEEE division on the host emulation
-#if defined(__CUDA_ARCH__)
-DMH_HD float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-#else
-DMH_HD float fast_rcp(float x) { return 1.0f / x; }
-#endif
 DMH_HD float vrcp(float x) { return fast_rcp(x); }
 template <class T> struct Lane;
 template <> struct Lane<float> { static DMH_HD float splat(float v) { return v; } };
@@ -414,8 +416,11 @@ DMH_HD void warp_chain_factors(const Camera& cam, const WarpCoord& wc, int W, in
     float pr[3];
     for (int i = 0; i < 3; ++i)
         pr[i] = cam.P[i * 4 + 0] * wc.ray[0] + cam.P[i * 4 + 1] * wc.ray[1] + cam.P[i * 4 + 2] * wc.ray[2];
-    ax = wc.mx * (2.0f / (float)(W - 1)) * wc.inv_z * (pr[0] - wc.u_raw * pr[2]);
-    ay = wc.my * (2.0f / (float)(H - 1)) * wc.inv_z * (pr[1] - wc.v_raw * pr[2]);
+    // d(ix)/d(u_raw) = mx * 2/(W-1) with mx = gate * (W-1)/2: the two constants cancel, only the clip gate is left
+    (void)W; (void)H;
+    const float gx = wc.mx != 0.0f ? wc.inv_z : 0.0f, gy = wc.my != 0.0f ? wc.inv_z : 0.0f;
+    ax = gx * (pr[0] - wc.u_raw * pr[2]);
+    ay = gy * (pr[1] - wc.v_raw * pr[2]);
 }
 
 }  // namespace dmh

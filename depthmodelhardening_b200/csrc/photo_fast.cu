@@ -107,32 +107,43 @@ __device__ __forceinline__ int ext_to_img(int e, int n) {
 struct Gathered { float v[3]; float dix[3], diy[3]; };
 
 // The four bilinear taps of one sampling position.  With border padding the clipped coordinate lies in
-// [0, W-1] x [0, H-1], so the north-west tap is always inside the image; the east / south taps fall outside
-// only when the coordinate sits exactly on the last column / row, where their weight (tx0 / ty0) is 0 and
-// ATen's gradient gate (clip_coordinates_set_grad) is 0 as well.  Those taps are therefore CLAMPED onto the
-// last column / row (dx = 0 / dy = 0): every load is unconditional and in bounds, no predicates.
+// [0, W-1] x [0, H-1].  The north-west tap is CLAMPED to (W-2, H-2), so the east / south taps are always
+// +1 / +W: every load is unconditional, in bounds, and at a fixed offset from one base address.  The clamp
+// only acts when the coordinate sits exactly on the last column / row (ix == W-1): the weights become
+// (tx1, tx0) = (0, 1) instead of (1, 0) on the duplicated tap -- the same interpolated value bit for bit --
+// and ATen's gradient gate (clip_coordinates_set_grad: borders count as out of bounds) zeroes d/d(ix) there.
 struct Tap {
-    int o, dx, dy;               // offset of the north-west tap; +dx -> east, +dy -> south
+    int o;                       // pixel index of the north-west tap
     float tx0, tx1, ty0, ty1;    // (ix - ix_nw), (ix_se - ix), (iy - iy_nw), (iy_se - iy)
 };
 
 __device__ __forceinline__ Tap make_tap(const WarpCoord& wc, int H, int W) {
-    const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+    const float fx = fminf(floorf(wc.ix), (float)(W - 2)), fy = fminf(floorf(wc.iy), (float)(H - 2));
     Tap t;
-    t.o = bl.y0 * W + bl.x0;
-    t.dx = (bl.x0 + 1 < W) ? 1 : 0;
-    t.dy = (bl.y0 + 1 < H) ? W : 0;
-    t.tx0 = bl.tx0; t.tx1 = bl.tx1; t.ty0 = bl.ty0; t.ty1 = bl.ty1;
+    t.o = (int)fy * W + (int)fx;
+    t.tx1 = (fx + 1.0f) - wc.ix; t.tx0 = wc.ix - fx;
+    t.ty1 = (fy + 1.0f) - wc.iy; t.ty0 = wc.iy - fy;
     return t;
 }
 
-// bilinear gather of 3 channels + d(value)/d(ix,iy), split into the 12 loads and their combination so that
-// the loads of several pixels can be in flight together
-__device__ __forceinline__ void load_taps(const float* __restrict__ sp, size_t N, const Tap& t, float v[3][4]) {
+// bilinear gather of 3 channels + d(value)/d(ix,iy), split into the loads and their combination so that the
+// loads of several pixels can be in flight together.  PK: the source is pixel-packed (B,H,W,4) -- one 128-bit
+// load per tap (dmh_identity_loss_pack writes that layout); otherwise planar (B,3,H,W), 12 scalar loads.
+template <bool PK>
+__device__ __forceinline__ void load_taps(const float* __restrict__ sp, size_t N, int W, const Tap& t, float v[3][4]) {
+    if (PK) {
+        const float4* s = reinterpret_cast<const float4*>(sp) + t.o;
+        const float4 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + W), d = __ldg(s + W + 1);
+        v[0][0] = a.x; v[1][0] = a.y; v[2][0] = a.z;
+        v[0][1] = b.x; v[1][1] = b.y; v[2][1] = b.z;
+        v[0][2] = c.x; v[1][2] = c.y; v[2][2] = c.z;
+        v[0][3] = d.x; v[1][3] = d.y; v[2][3] = d.z;
+    } else {
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float* s = sp + ch * N + t.o;
-        v[ch][0] = __ldg(s); v[ch][1] = __ldg(s + t.dx); v[ch][2] = __ldg(s + t.dy); v[ch][3] = __ldg(s + t.dy + t.dx);
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* s = sp + ch * N + t.o;
+            v[ch][0] = __ldg(s); v[ch][1] = __ldg(s + 1); v[ch][2] = __ldg(s + W); v[ch][3] = __ldg(s + W + 1);
+        }
     }
 }
 __device__ __forceinline__ Gathered combine_taps(const float v[3][4], const Tap& t, bool want_grad) {
@@ -153,11 +164,6 @@ __device__ __forceinline__ Gathered combine_taps(const float v[3][4], const Tap&
     }
     return g;
 }
-__device__ __forceinline__ Gathered gather_taps(const float* __restrict__ sp, size_t N, const Tap& t, bool want_grad) {
-    float v[3][4];
-    load_taps(sp, N, t, v);
-    return combine_taps(v, t, want_grad);
-}
 
 // position (r, c) in the 36 x 36 frame of halo-ring pixel h < 272: 2 top rows, 2 bottom rows, 2 left / right columns
 __device__ __forceinline__ void halo_rc(int h, int& r, int& c) {
@@ -167,7 +173,40 @@ __device__ __forceinline__ void halo_rc(int h, int& r, int& c) {
     else { const int t = h - 208; r = 2 + (t >> 1); c = FT_R2 - 2 + (t & 1); }
 }
 
-template <bool TMA, bool FASTDIV>
+// image index of tile coordinate e >= 0 (a pixel of the tile proper): in-image, or the ReflectionPad2d(1) mirror
+// of the first row / column past the border (n -> n-2); anything further out is clamped onto that (unused values)
+__device__ __forceinline__ int tile_to_img(int e, int n) {
+    e = min(e, n);
+    return e == n ? n - 2 : e;
+}
+
+// F.interpolate(disp, [H, W], bilinear, align_corners=False) at one pixel from its row / column taps
+__device__ __forceinline__ float up_sample(const float* __restrict__ dp, int dw, const UpTap& ty, const UpTap& tx) {
+    const float* r0 = dp + ty.i0 * dw;
+    const float* r1 = dp + ty.i1 * dw;
+    return ty.l0 * (tx.l0 * __ldg(r0 + tx.i0) + tx.l1 * __ldg(r0 + tx.i1)) +
+           ty.l1 * (tx.l0 * __ldg(r1 + tx.i0) + tx.l1 * __ldg(r1 + tx.i1));
+}
+
+// One pixel of the warp: depth -> exact coordinate chain -> taps (+ the two backward factors when wanted)
+template <bool FASTDIV>
+__device__ __forceinline__ Tap pixel_tap(const Camera& cam, const FastParams& p, bool is_depth, int ix, int iy, float dv,
+                                         bool want_grad, float& gax, float& gay) {
+    const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
+    const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)ix, (float)iy, depth, p.W, p.H, 1e-7f, p.rcw, p.rch);
+    if (want_grad) {
+        float ax, ay;
+        warp_chain_factors(cam, wc, p.W, p.H, ax, ay);
+        const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
+        gax = ax * dd; gay = ay * dd;
+    }
+    return make_tap(wc, p.H, p.W);
+}
+
+// TMA: target tile by cp.async.bulk.tensor; FASTDIV: verified 3-instruction division by W-1 / H-1;
+// PK: pixel-packed source (128-bit taps); UP: the disparity map is smaller than the frame (scales 1..3).
+// SSIM is always on here (no_ssim takes the general kernel).
+template <bool TMA, bool FASTDIV, bool PK, bool UP>
 __global__ void __launch_bounds__(FT_THREADS, 3)
 photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map) {
     extern __shared__ __align__(128) float smem[];
@@ -184,11 +223,9 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     const int H = p.H, W = p.W;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
-    const size_t N = (size_t)H * W;
-    const bool no_ssim = (p.flags & DMH_PHOTO_NO_SSIM) != 0;
+    const int N = H * W;                      // per-item offsets fit 32 bits (checked by the launcher)
     const bool is_depth = (p.flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
-    const float w_ssim = no_ssim ? 0.0f : 0.85f / 3.0f;
-    const float w_l1 = no_ssim ? 1.0f / 3.0f : 0.15f / 3.0f;
+    const float w_ssim = 0.85f / 3.0f, w_l1 = 0.15f / 3.0f;
 
     if (tid < 12) {
         const int i = tid / 4, j = tid % 4;
@@ -213,8 +250,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     } else if (tid < FT_R2 * 7) {
         // ---- target tile, 2-px reflect halo: 36 columns x 7 row groups = 252 threads, column index maths once
         const int c = tid % FT_R2, rg = tid / FT_R2;
-        const int ix = ext_to_img(x0 - 2 + c, W);
-        const float* tp = p.target + (size_t)b * 3 * N + ix;
+        const float* tp = p.target + (size_t)b * 3 * N + ext_to_img(x0 - 2 + c, W);
         for (int r = rg; r < FT_R2; r += 7) {
             const int o = ext_to_img(y0 - 2 + r, H) * W;
 #pragma unroll
@@ -227,7 +263,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     for (int i = 0; i < 12; ++i) cam.P[i] = cams[i];
 #pragma unroll
     for (int i = 0; i < 9; ++i) cam.iK[i] = cams[12 + i];
-    const float* sp = p.src + (size_t)b * 3 * N;
+    const float* sp = p.src + (size_t)b * (PK ? 4 : 3) * N;
+    const float* dp = p.disp.ptr + (size_t)b * (p.disp.h * p.disp.w);
 
     // ---- phase A: warp.  A thread owns the interior pixels of column tid%32, rows 4*(tid/32)+k, plus one pixel
     // of the halo ring.  Software-pipelined over those 5 pixels: all disparity loads, then the coordinate chains,
@@ -238,35 +275,32 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         int hr, hc;
         halo_rc(tid, hr, hc);
         int py[5], pxx[5];
-        const int ixo = ext_to_img(x0 + oc, W);
+        const int ixo = tile_to_img(x0 + oc, W);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { py[k] = ext_to_img(y0 + 4 * os + k, H); pxx[k] = ixo; }
+        for (int k = 0; k < 4; ++k) { py[k] = tile_to_img(y0 + 4 * os + k, H); pxx[k] = ixo; }
         py[4] = ext_to_img(y0 - 2 + hr, H);
         pxx[4] = ext_to_img(x0 - 2 + hc, W);
         float dv[5];
+        if (!UP) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) dv[k] = load_disp(p.disp, b, py[k], pxx[k], H, W);
-        Tap tp[5];
-        float gax[4], gay[4];
+            for (int k = 0; k < 5; ++k) dv[k] = __ldg(dp + py[k] * W + pxx[k]);
+        } else {
+            const UpTap txo = up_tap(ixo, p.disp.sw, p.disp.w);        // shared by the 4 owned pixels
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float depth = is_depth ? dv[k] : disp_to_depth(dv[k], p.ds);
-            const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)pxx[k], (float)py[k], depth, W, H, 1e-7f, p.rcw, p.rch);
-            tp[k] = make_tap(wc, H, W);
-            if (k < 4) {
-                float ax, ay;
-                warp_chain_factors(cam, wc, W, H, ax, ay);
-                const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
-                gax[k] = ax * dd; gay[k] = ay * dd;
-            }
+            for (int k = 0; k < 4; ++k) dv[k] = up_sample(dp, p.disp.w, up_tap(py[k], p.disp.sh, p.disp.h), txo);
+            dv[4] = up_sample(dp, p.disp.w, up_tap(py[4], p.disp.sh, p.disp.h), up_tap(pxx[4], p.disp.sw, p.disp.w));
         }
-        // gathers: the 12 taps of TWO pixels are requested before either is consumed
+        Tap tp[5];
+        float gax[5], gay[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tp[k] = pixel_tap<FASTDIV>(cam, p, is_depth, pxx[k], py[k], dv[k], k < 4, gax[k], gay[k]);
+        // gathers: the taps of TWO pixels are requested before either is consumed
 #pragma unroll
         for (int k0 = 0; k0 < 5; k0 += 2) {
             float tv[2][3][4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                if (k0 + j < 5) load_taps(sp, N, tp[k0 + j], tv[j]);
+                if (k0 + j < 5) load_taps<PK>(sp, N, W, tp[k0 + j], tv[j]);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -283,7 +317,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                     if (p.warped && y0 + r < H && x0 + oc < W) {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch)
-                            p.warped[((size_t)b * 3 + ch) * N + (size_t)(y0 + r) * W + x0 + oc] = g.v[ch];
+                            p.warped[((size_t)b * 3 + ch) * N + (y0 + r) * W + x0 + oc] = g.v[ch];
                     }
                 }
             }
@@ -294,27 +328,35 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         int r, c;
         halo_rc(tid + FT_THREADS, r, c);
         const int iy = ext_to_img(y0 - 2 + r, H), ix = ext_to_img(x0 - 2 + c, W);
-        const float dvh = load_disp(p.disp, b, iy, ix, H, W);
-        const float depth = is_depth ? dvh : disp_to_depth(dvh, p.ds);
-        const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)ix, (float)iy, depth, W, H, 1e-7f, p.rcw, p.rch);
-        const Gathered g = gather_taps(sp, N, make_tap(wc, H, W), false);
+        const float dvh = UP ? up_sample(dp, p.disp.w, up_tap(iy, p.disp.sh, p.disp.h), up_tap(ix, p.disp.sw, p.disp.w))
+                             : __ldg(dp + iy * W + ix);
+        float u0, u1;
+        const Tap th = pixel_tap<FASTDIV>(cam, p, is_depth, ix, iy, dvh, false, u0, u1);
+        float tvh[3][4];
+        load_taps<PK>(sp, N, W, th, tvh);
+        const Gathered g = combine_taps(tvh, th, false);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + r * FT_R2 + c] = g.v[ch];
     }
     // identity losses (+ tie-break noise) of this thread's phase-B pixels: requested before the barrier so
-    // that their latency overlaps the other warps' gather
+    // that their latency overlaps the other warps' gather.  Ring pixels outside the image are marked by a NaN
+    // (rp < NaN is false: they never win, their coefficients are gated to 0 and they add nothing to the loss).
+    const int bc = tid % FT_R1, bstrip = tid / FT_R1;
+    const bool has_ident = p.ident != nullptr;
     float idv_pre[FT_ROWS];
     {
-        const int c = tid % FT_R1, strip = tid / FT_R1;
-        const int qx = x0 - 1 + c;
+        const int qx = x0 - 1 + bc;
+        const bool col_ok = qx >= 0 && qx < W && tid < FT_R1 * FT_STRIPS;
+        const float* idp = p.ident + (size_t)b * N + qx;
+        const float* nzp = p.noise + (size_t)b * N + qx;
 #pragma unroll
         for (int k = 0; k < FT_ROWS; ++k) {
-            const int qr = strip * FT_ROWS + k, qy = y0 - 1 + qr;
-            float v = 0.f;
-            if (p.ident && tid < FT_R1 * FT_STRIPS && qr < FT_R1 && qx >= 0 && qx < W && qy >= 0 && qy < H) {
-                const size_t qo = (size_t)b * N + (size_t)qy * W + qx;
-                v = __ldg(p.ident + qo);
-                if (p.noise) v = add_rn(v, __ldg(p.noise + qo));
+            const int qr = bstrip * FT_ROWS + k, qy = y0 - 1 + qr;
+            const bool ok = col_ok && qr < FT_R1 && qy >= 0 && qy < H;
+            float v = ok ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);     // +inf: always loses to rp
+            if (ok && has_ident) {
+                v = __ldg(idp + qy * W);
+                if (p.noise) v = add_rn(v, __ldg(nzp + qy * W));
             }
             idv_pre[k] = v;
         }
@@ -340,94 +382,66 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     }
 
     // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients.
-    // Channels 0 and 1 ride in the two halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2), channel 2 is scalar.
+    // Channels 0 and 1 ride in the two halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2), channel 2 is
+    // scalar.  Straight-line: rows past the tile are clamped (their results are discarded by the predicated
+    // stores), out-of-image ring pixels are gated through the NaN identity marker.
     float loss_local = 0.0f;
     if (tid < FT_R1 * FT_STRIPS) {
-        const int c = tid % FT_R1, strip = tid / FT_R1;
-        const int r0 = strip * FT_ROWS;                 // first ring row of this strip == first R2 row of its window
-        const int qx = x0 - 1 + c;
-        const bool col_ok = qx >= 0 && qx < W;
+        const int r0 = bstrip * FT_ROWS;                // first ring row of this strip == first R2 row of its window
+        const bool col_in = bc >= 1 && bc <= FT_T;
         Row5T<float2> histP[2];                         // channels (0,1): [older, newer] row sums
         Row5T<float> histS[2];                          // channel 2
-        float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;   // centre values of the previous row
-        float cenxS = 0.f, cenyS = 0.f;
+        float2 cenxP, cenyP;                            // centre values of the previous row
+        float cenxS, cenyS;
         const float2 w_ssim2 = make_float2(w_ssim, w_ssim);
 #pragma unroll
         for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
-            const int r2 = r0 + rr;                     // R2 row being added
-            Row5T<float2> curP;
-            Row5T<float> curS;
-            float2 midxP = make_float2(0.f, 0.f), midyP = midxP;
-            float midxS = 0.f, midyS = 0.f;
-            if (r2 < FT_R2) {
-                const float* xs = pred + r2 * FT_R2 + c;
-                const float* ys = tgt + r2 * FT_TP + c + FT_TO;
-                const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
-                             xc = make_float2(xs[2], xs[FT_N2 + 2]);
-                const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
-                             yc = make_float2(ys[2], ys[FT_NT + 2]);
-                curP = row5(xa, xb, xc, ya, yb, yc);
-                midxP = xb; midyP = yb;
-                const float* x2 = xs + 2 * FT_N2;
-                const float* y2 = ys + 2 * FT_NT;
-                curS = row5(x2[0], x2[1], x2[2], y2[0], y2[1], y2[2]);
-                midxS = x2[1]; midyS = y2[1];
-            }
+            const int r2 = min(r0 + rr, FT_R2 - 1);     // R2 row being added
+            const float* xs = pred + r2 * FT_R2 + bc;
+            const float* ys = tgt + r2 * FT_TP + bc + FT_TO;
+            const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
+                         xc = make_float2(xs[2], xs[FT_N2 + 2]);
+            const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
+                         yc = make_float2(ys[2], ys[FT_NT + 2]);
+            const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
+            const float* x2 = xs + 2 * FT_N2;
+            const float* y2 = ys + 2 * FT_NT;
+            const float x2m = x2[1], y2m = y2[1];
+            const Row5T<float> curS = row5(x2[0], x2m, x2[2], y2[0], y2m, y2[2]);
             if (rr >= 2) {
                 const int qr = r0 + rr - 2;             // ring row of the window centre
-                const int qy = y0 - 1 + qr;
+                float l1 = fabsf(cenyP.x - cenxP.x);
+                l1 += fabsf(cenyP.y - cenxP.y);
+                l1 += fabsf(cenyS - cenxS);
+                float2 passP;
+                SsimCoefT<float2> kP;
+                const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
+                float passS;
+                SsimCoefT<float> kS;
+                const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
+                const float ss = (vP.x + vP.y) + vS;
+                l1 *= (1.0f / 3.0f);
+                const float rp = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                const float idv = idv_pre[rr - 2];
+                const bool win = rp < idv;              // torch.min: first minimum wins, identity is first
+                const float gw = win ? w_ssim : 0.0f;
+                const float2 gP = vmul(make_float2(gw, gw), passP);
+                const float gS = gw * passS;
                 if (qr < FT_R1) {
-                    const int qi = qr * FT_R1 + c;
-                    float2 kaP = make_float2(0.f, 0.f), kbP = kaP, kcP = kaP;
-                    float kaS = 0.f, kbS = 0.f, kcS = 0.f;
-                    uint8_t gt = 0;
-                    if (col_ok && qy >= 0 && qy < H) {
-                        float l1 = fabsf(cenyP.x - cenxP.x);
-                        l1 += fabsf(cenyP.y - cenxP.y);
-                        l1 += fabsf(cenyS - cenxS);
-                        float ss = 0.f;
-                        if (!no_ssim) {
-                            float2 passP;
-                            SsimCoefT<float2> kP;
-                            const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
-                            float passS;
-                            SsimCoefT<float> kS;
-                            const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
-                            ss = (vP.x + vP.y) + vS;
-                            const float2 gP = vmul(w_ssim2, passP);
-                            kaP = vmul(gP, kP.ax); kbP = vmul(gP, kP.b); kcP = vmul(gP, kP.c);
-                            const float gS = w_ssim * passS;
-                            kaS = gS * kS.ax; kbS = gS * kS.b; kcS = gS * kS.c;
-                        }
-                        l1 *= (1.0f / 3.0f);
-                        const float rp = no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
-                        float best = rp;
-                        int best_idx = 0;
-                        bool win = true;
-                        if (p.ident) {
-                            const float idv = idv_pre[rr - 2];
-                            win = rp < idv;                     // torch.min: first minimum wins, identity is first
-                            best = win ? rp : idv;
-                            best_idx = win ? 1 : 0;
-                        }
-                        gt = win ? 1 : 0;
-                        if (!win) {
-                            kaP = make_float2(0.f, 0.f); kbP = kaP; kcP = kaP;
-                            kaS = 0.f; kbS = 0.f; kcS = 0.f;
-                        }
-                        if (qr >= 1 && qr <= FT_T && c >= 1 && c <= FT_T) {
-                            loss_local += best;
-                            if (p.sel) p.sel[(size_t)b * N + (size_t)qy * W + qx] = (uint8_t)best_idx;
-                        }
-                    }
-                    coefP[0 * FT_N1 + qi] = kaP; coefP[1 * FT_N1 + qi] = kbP; coefP[2 * FT_N1 + qi] = kcP;
-                    coefS[0 * FT_N1 + qi] = kaS; coefS[1 * FT_N1 + qi] = kbS; coefS[2 * FT_N1 + qi] = kcS;
-                    gate[qi] = gt;
+                    const int qi = qr * FT_R1 + bc;
+                    coefP[0 * FT_N1 + qi] = vmul(gP, kP.ax); coefP[1 * FT_N1 + qi] = vmul(gP, kP.b);
+                    coefP[2 * FT_N1 + qi] = vmul(gP, kP.c);
+                    coefS[0 * FT_N1 + qi] = gS * kS.ax; coefS[1 * FT_N1 + qi] = gS * kS.b; coefS[2 * FT_N1 + qi] = gS * kS.c;
+                    gate[qi] = win ? 1 : 0;
+                }
+                if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
+                    loss_local += win ? rp : idv;
+                    if (p.sel) p.sel[(size_t)b * N + (y0 - 1 + qr) * W + x0 - 1 + bc] = (uint8_t)((win && has_ident) ? 1 : 0);
                 }
             }
             histP[0] = histP[1]; histP[1] = curP;
             histS[0] = histS[1]; histS[1] = curS;
-            cenxP = midxP; cenyP = midyP; cenxS = midxS; cenyS = midyS;
+            cenxP = xb; cenyP = yb; cenxS = x2m; cenyS = y2m;
         }
     }
     __syncthreads();
@@ -440,6 +454,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         const float2 wl2 = make_float2(wl, wl), wr2 = make_float2(wr, wr);
         float2 hprevP[2][3];
         float hprevS[2][3];
+        float* gout = p.grad_disp + (size_t)b * N + px;
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r1 = 4 * os + rr;                      // ring row
@@ -458,33 +473,31 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 const int k = rr - 2;
                 const int r = 4 * os + k;
                 const int py = y0 + r;
-                if (py < H && px < W) {
-                    const float wu = (py == 1) ? 2.0f : 1.0f;
-                    const float wd = (py == H - 2) ? 2.0f : 1.0f;
-                    const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
-                    const int i2 = (r + 2) * FT_R2 + oc + 2;
-                    const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
-                    const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
-                    const float2 saP = vfma(wu2, hprevP[0][0], vfma(wd2, hcP[0], hprevP[1][0]));
-                    const float2 sbP = vfma(wu2, hprevP[0][1], vfma(wd2, hcP[1], hprevP[1][1]));
-                    const float2 scP = vfma(wu2, hprevP[0][2], vfma(wd2, hcP[2], hprevP[1][2]));
-                    const float saS = fmaf(wu, hprevS[0][0], fmaf(wd, hcS[0], hprevS[1][0]));
-                    const float sbS = fmaf(wu, hprevS[0][1], fmaf(wd, hcS[1], hprevS[1][1]));
-                    const float scS = fmaf(wu, hprevS[0][2], fmaf(wd, hcS[2], hprevS[1][2]));
-                    const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
-                    const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
-                    const float2 dP = vsub(xvP, yvP);
-                    const float dS = xvS - yvS;
-                    const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
-                                                   dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
-                    const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
-                    const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
-                    const float gpS = fmaf(sbS, xvS, fmaf(scS, yvS, saS)) + sgS;
-                    float g = gpP.x * D[k][0];
-                    g = fmaf(gpP.y, D[k][1], g);
-                    g = fmaf(gpS, D[k][2], g);
-                    p.grad_disp[(size_t)b * N + (size_t)py * W + px] = g;
-                }
+                const float wu = (py == 1) ? 2.0f : 1.0f;
+                const float wd = (py == H - 2) ? 2.0f : 1.0f;
+                const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
+                const int i2 = (r + 2) * FT_R2 + oc + 2;
+                const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
+                const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
+                const float2 saP = vfma(wu2, hprevP[0][0], vfma(wd2, hcP[0], hprevP[1][0]));
+                const float2 sbP = vfma(wu2, hprevP[0][1], vfma(wd2, hcP[1], hprevP[1][1]));
+                const float2 scP = vfma(wu2, hprevP[0][2], vfma(wd2, hcP[2], hprevP[1][2]));
+                const float saS = fmaf(wu, hprevS[0][0], fmaf(wd, hcS[0], hprevS[1][0]));
+                const float sbS = fmaf(wu, hprevS[0][1], fmaf(wd, hcS[1], hprevS[1][1]));
+                const float scS = fmaf(wu, hprevS[0][2], fmaf(wd, hcS[2], hprevS[1][2]));
+                const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
+                const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
+                const float2 dP = vsub(xvP, yvP);
+                const float dS = xvS - yvS;
+                const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
+                                               dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
+                const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
+                const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
+                const float gpS = fmaf(sbS, xvS, fmaf(scS, yvS, saS)) + sgS;
+                float g = gpP.x * D[k][0];
+                g = fmaf(gpP.y, D[k][1], g);
+                g = fmaf(gpS, D[k][2], g);
+                if (py < H && px < W) gout[py * W] = g;
             }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -507,7 +520,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
 struct IdentParams {
     const float* target;
     const float* src[DMH_PHOTO_MAX_FRAMES];
-    float* out;                 // (B,F,H,W)
+    float* out;                 // (B,F,H,W); nullable when only the packed copy is wanted
+    float4* packed;             // nullable (F == 1): source frame 0 re-laid out as (B,H,W,4) for the 128-bit tap gather
     int B, F, H, W, no_ssim;
 };
 
@@ -543,10 +557,21 @@ ident_fast_kernel(const IdentParams p) {
         }
     }
     __syncthreads();
-    // same lane-typed SSIM arithmetic as the fused kernels (channels 0,1 packed, channel 2 scalar): the
-    // identity loss and the reprojection loss must come out of identical arithmetic (automask ties)
     const int c = tid & 31, strip = tid >> 5;           // 8 strips of 4 rows
     const int px = x0 + c;
+    if (p.packed && px < W) {     // pixel-packed copy of the source tile: a warp writes 512 contiguous bytes per row
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = 4 * strip + k, py = y0 + r;
+            if (py < H) {
+                const int i = (r + 1) * ID_R + c + 1;
+                p.packed[(size_t)b * N + (size_t)py * W + px] = make_float4(xs[0][i], xs[1][i], xs[2][i], 0.0f);
+            }
+        }
+    }
+    if (!p.out) return;
+    // same lane-typed SSIM arithmetic as the fused kernels (channels 0,1 packed, channel 2 scalar): the
+    // identity loss and the reprojection loss must come out of identical arithmetic (automask ties)
     Row5T<float2> histP[2];
     Row5T<float> histS[2];
     float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;
@@ -635,9 +660,14 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     cudaGetDevice(&dev);
     if (!configured_dev[dev & 63]) {
         cudaError_t e = cudaSuccess;
-        const void* fns[4] = {(const void*)photo_fast_kernel<false, false>, (const void*)photo_fast_kernel<false, true>,
-                              (const void*)photo_fast_kernel<true, false>, (const void*)photo_fast_kernel<true, true>};
-        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+#define DMH_FAST_FN(T_, D_, P_, U_) (const void*)photo_fast_kernel<T_, D_, P_, U_>
+#define DMH_FAST_FN4(P_, U_) DMH_FAST_FN(false, false, P_, U_), DMH_FAST_FN(false, true, P_, U_), \
+                             DMH_FAST_FN(true, false, P_, U_), DMH_FAST_FN(true, true, P_, U_)
+        const void* fns[16] = {DMH_FAST_FN4(false, false), DMH_FAST_FN4(false, true), DMH_FAST_FN4(true, false),
+                               DMH_FAST_FN4(true, true)};
+#undef DMH_FAST_FN4
+#undef DMH_FAST_FN
+        for (int i = 0; i < 16 && e == cudaSuccess; ++i)
             e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("dmh_photo_scale(fast): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -662,18 +692,31 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     }
     // division by W-1 / H-1 in the coordinate chain: the 3-instruction form where it is proven bit-exact
     const bool fastdiv = W > 1 && H > 1 && const_div_exact(W - 1, &p.rcw) && const_div_exact(H - 1, &p.rch);
-    if (use_tma && fastdiv) DMH_LAUNCH((photo_fast_kernel<true, true>), grid, FT_THREADS, smem, st)(p, map);
-    else if (use_tma) DMH_LAUNCH((photo_fast_kernel<true, false>), grid, FT_THREADS, smem, st)(p, map);
-    else if (fastdiv) DMH_LAUNCH((photo_fast_kernel<false, true>), grid, FT_THREADS, smem, st)(p, map);
-    else DMH_LAUNCH((photo_fast_kernel<false, false>), grid, FT_THREADS, smem, st)(p, map);
+    const bool packed = (flags & DMH_PHOTO_SRC_PACKED) != 0;
+    const bool up = !(disp_h == H && disp_w == W);
+#define DMH_FAST_GO(T_, D_, P_, U_) DMH_LAUNCH((photo_fast_kernel<T_, D_, P_, U_>), grid, FT_THREADS, smem, st)(p, map)
+#define DMH_FAST_GO2(P_, U_)                                           \
+    do {                                                               \
+        if (use_tma && fastdiv) DMH_FAST_GO(true, true, P_, U_);       \
+        else if (use_tma) DMH_FAST_GO(true, false, P_, U_);            \
+        else if (fastdiv) DMH_FAST_GO(false, true, P_, U_);            \
+        else DMH_FAST_GO(false, false, P_, U_);                        \
+    } while (0)
+    if (packed && up) DMH_FAST_GO2(true, true);
+    else if (packed) DMH_FAST_GO2(true, false);
+    else if (up) DMH_FAST_GO2(false, true);
+    else DMH_FAST_GO2(false, false);
+#undef DMH_FAST_GO2
+#undef DMH_FAST_GO
     return DMH_OK;
 }
 
 
 int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
-                      float* out, cudaStream_t st) {
+                      float* out, float* packed, cudaStream_t st) {
     IdentParams p;
     p.target = target;
+    p.packed = reinterpret_cast<float4*>(packed);
     for (int f = 0; f < DMH_PHOTO_MAX_FRAMES; ++f) p.src[f] = f < F ? src_host[f] : nullptr;
     p.out = out; p.B = B; p.F = F; p.H = H; p.W = W; p.no_ssim = no_ssim;
     dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B * F);

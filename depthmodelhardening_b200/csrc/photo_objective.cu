@@ -482,7 +482,7 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
                       uint8_t* sel, float* warped, cudaStream_t st);
 int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
-                      float* out, cudaStream_t st);
+                      float* out, float* packed, cudaStream_t st);
 }  // namespace dmh
 
 extern "C" {
@@ -493,9 +493,21 @@ int dmh_identity_loss(const float* target, const float* const* src_host, int F, 
     DMH_REQUIRE(F >= 1 && F <= PH_MAXF, "dmh_identity_loss: F=%d outside [1,%d]", F, PH_MAXF);
     DMH_REQUIRE(B > 0 && (long long)B * F <= 65535 && H >= 2 && W >= 2, "dmh_identity_loss: bad shape");
     for (int f = 0; f < F; ++f) DMH_REQUIRE(src_host[f], "dmh_identity_loss: null src for frame %d", f);
-    const int rc = launch_ident_fast(target, src_host, F, B, H, W, no_ssim, ident, (cudaStream_t)stream);
+    const int rc = launch_ident_fast(target, src_host, F, B, H, W, no_ssim, ident, nullptr, (cudaStream_t)stream);
     if (rc != DMH_OK) return rc;
     DMH_CHECK_LAUNCH("dmh_identity_loss");
+    return DMH_OK;
+}
+
+int dmh_identity_loss_pack(const float* target, const float* src, int B, int H, int W, int no_ssim, float* ident,
+                           float* src_packed, dmh_stream_t stream) {
+    DMH_REQUIRE(target && src && src_packed, "dmh_identity_loss_pack: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "dmh_identity_loss_pack: bad shape");
+    DMH_REQUIRE((uintptr_t)src_packed % 16 == 0, "dmh_identity_loss_pack: src_packed must be 16-byte aligned");
+    const float* srcs[1] = {src};
+    const int rc = launch_ident_fast(target, srcs, 1, B, H, W, no_ssim, ident, src_packed, (cudaStream_t)stream);
+    if (rc != DMH_OK) return rc;
+    DMH_CHECK_LAUNCH("dmh_identity_loss_pack");
     return DMH_OK;
 }
 
@@ -542,7 +554,11 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
     DMH_REQUIRE(disp_h >= 1 && disp_w >= 1 && disp_h <= H && disp_w <= W, "dmh_photo_scale: bad disparity size %dx%d", disp_h, disp_w);
     const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
     DMH_REQUIRE(is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_photo_scale: bad depth range");
-    if (F == 1 && !grad_P_partial && !(flags & DMH_PHOTO_FORCE_GENERIC)) {
+    DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED) || (F == 1 && !grad_P_partial && H * (long long)W < (1ll << 28) &&
+                                                    !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM)) &&
+                                                    (uintptr_t)src_host[0] % 16 == 0),
+                "dmh_photo_scale: DMH_PHOTO_SRC_PACKED needs F == 1, SSIM on, no pose gradient and a 16-byte aligned source");
+    if (F == 1 && !grad_P_partial && !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM)) && H * (long long)W < (1ll << 28)) {
         // single source frame, no pose gradient: the 32x32-tile fast kernel (photo_fast.cu).  It writes
         // fewer partial sums than dmh_photo_tiles() promises; zero the tail so the caller's reduction is exact.
         DMH_REQUIRE(src_host[0] && T_host[0], "dmh_photo_scale: null src/T for frame 0");

@@ -338,6 +338,7 @@ def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_
 FLAG_NO_SSIM = 1
 FLAG_AVG_REPROJECTION = 2
 FLAG_INPUT_IS_DEPTH = 4
+FLAG_SRC_PACKED = 16
 
 
 class _PhotoScale(torch.autograd.Function):
@@ -424,17 +425,26 @@ class _Objective(torch.autograd.Function):
         dev = target.device
         lib = _lib_()
         no_ssim = 1 if (flags & FLAG_NO_SSIM) else 0
-        ident = None
-        if automask:
-            ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32)
-            check(lib.dmh_identity_loss(ptr(target), ptr_array(srcs), n_src, B, H, W, no_ssim, ptr(ident), stream()),
-                  "identity_loss")
         # disp grads are needed iff any disparity requires grad; pose grads iff any T does
         base = 3 + S + n_src
         need_T = any(ctx.needs_input_grad[base + i] for i in range(n_src))
+        # single source, no pose gradient: the per-scale kernel gathers from a pixel-packed (B,H,W,4) copy of the
+        # source (one 128-bit load per bilinear tap), written once by the identity-loss kernel
+        packed = n_src == 1 and not need_T and not no_ssim and H * W < (1 << 28)
+        ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32) if automask else None
+        src_arr = ptr_array(srcs)
+        if packed:
+            src_pk = torch.empty(B, H, W, 4, device=dev, dtype=torch.float32)
+            check(lib.dmh_identity_loss_pack(ptr(target), ptr(srcs[0]), B, H, W, no_ssim, ptr(ident), ptr(src_pk),
+                                             stream()), "identity_loss_pack")
+            src_arr = ptr_array([src_pk])
+            flags |= FLAG_SRC_PACKED
+        elif automask:
+            check(lib.dmh_identity_loss(ptr(target), src_arr, n_src, B, H, W, no_ssim, ptr(ident), stream()),
+                  "identity_loss")
         tiles = lib.dmh_photo_tiles(H, W)
         G, gN, wss, parts, gPs, sels = [], [], [], [], [], []
-        src_arr, T_arr = ptr_array(srcs), ptr_array(Ts)
+        T_arr = ptr_array(Ts)
         inv_den = 1.0 / float(B * H * W)
         for s in range(S):
             d = disps[s]

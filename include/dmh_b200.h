@@ -148,10 +148,17 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
  * ident[:,f] = compute_reprojection_loss(src_f, target); scale independent, computed once. */
 int dmh_identity_loss(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
                       float* ident, dmh_stream_t stream);
+/* Single-source variant that ALSO writes the source frame pixel-packed, src_packed (B,H,W,4) fp32 (RGB + one pad
+ * float, 16-byte aligned): with DMH_PHOTO_SRC_PACKED the per-scale kernel gathers each bilinear tap with one
+ * 128-bit load instead of three scalar ones (the gather of F.grid_sample, M2/trainer.py:515-519, is repeated for
+ * every scale, the re-layout is done once).  ident nullable: re-layout only (automasking disabled).            */
+int dmh_identity_loss_pack(const float* target, const float* src, int B, int H, int W, int no_ssim, float* ident,
+                           float* src_packed, dmh_stream_t stream);
 #define DMH_PHOTO_NO_SSIM 1
 #define DMH_PHOTO_AVG_REPROJECTION 2
 #define DMH_PHOTO_INPUT_IS_DEPTH 4
 #define DMH_PHOTO_FORCE_GENERIC 8 /* testing: never take the single-source fast kernel */
+#define DMH_PHOTO_SRC_PACKED 16 /* src_host[0] is the (B,H,W,4) layout of dmh_identity_loss_pack; F == 1, no pose grad */
 #define DMH_PHOTO_MAX_FRAMES 4
 int dmh_photo_tiles(int H, int W);           /* CTAs per batch item */
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,

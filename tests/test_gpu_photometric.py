@@ -412,3 +412,45 @@ def test_cuda_graph_replay_matches_eager(dev):
         assert torch.equal(losses["loss"], l_ref)
         for s in pb.scales:
             assert torch.equal(grads[s], g_ref[s])
+
+
+@pytest.mark.parametrize("hw,dhw", [((64, 96), (64, 96)), ((50, 70), (50, 70)), ((96, 160), (24, 40)), ((33, 37), (17, 19))])
+def test_packed_source_gather_is_bit_identical(dev, hw, dhw):
+    """dmh_identity_loss_pack writes the same identity loss as dmh_identity_loss plus a (B,H,W,4) copy of the
+    source; dmh_photo_scale with DMH_PHOTO_SRC_PACKED (128-bit tap loads) must reproduce the planar gather bit
+    for bit -- loss partial sums, disparity gradient and argmin -- incl. ragged tiles and up-sampled disparities."""
+    from depthmodelhardening_b200 import _lib, ops
+    from depthmodelhardening_b200._lib import check, ptr, ptr_array, stream
+    H, W = hw
+    h, w = dhw
+    B = 2
+    pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, "s"), scales=(0,), seed=71).to(dev)
+    lib = _lib.load()
+    target, src = pb.color[(0, 0)].contiguous(), pb.color[("s", 0)].contiguous()
+    gen = torch.Generator().manual_seed(5)
+    disp = (0.05 + 0.4 * torch.rand(B, 1, h, w, generator=gen)).to(dev)
+    ident_a = torch.empty(B, 1, H, W, device=dev)
+    ident_b = torch.empty_like(ident_a)
+    pk = torch.full((B, H, W, 4), 7.0, device=dev)
+    check(lib.dmh_identity_loss(ptr(target), ptr_array([src]), 1, B, H, W, 0, ptr(ident_a), stream()))
+    check(lib.dmh_identity_loss_pack(ptr(target), ptr(src), B, H, W, 0, ptr(ident_b), ptr(pk), stream()))
+    assert torch.equal(ident_a, ident_b)
+    assert torch.equal(pk[..., :3], src.permute(0, 2, 3, 1))
+    pk2 = torch.empty_like(pk)
+    check(lib.dmh_identity_loss_pack(ptr(target), ptr(src), B, H, W, 0, None, ptr(pk2), stream()))   # re-layout only
+    assert torch.equal(pk2[..., :3], pk[..., :3])
+    tiles = lib.dmh_photo_tiles(H, W)
+    outs = []
+    for flags, s in ((0, src), (ops.FLAG_SRC_PACKED, pk)):
+        part = torch.empty(B * tiles, device=dev)
+        g = torch.empty(B, 1, H, W, device=dev)
+        sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+        check(lib.dmh_photo_scale(ptr(target), ptr_array([s]), ptr_array([pb.T["s"].contiguous()]), 1, ptr(disp), h, w,
+                                  ptr(pb.K.contiguous()), ptr(pb.inv_K.contiguous()), ptr(ident_a),
+                                  ptr(pb.noise[0][:, :1].contiguous()), B, H, W, 0.1, 100.0, flags, 1.0, ptr(part), ptr(g),
+                                  None, ptr(sel), None, stream()), "photo_scale")
+        outs.append((part, g, sel))
+    torch.cuda.synchronize()
+    for a, b_ in zip(outs[0], outs[1]):
+        assert torch.equal(a, b_)
+    assert float(outs[0][1].abs().max()) > 0
