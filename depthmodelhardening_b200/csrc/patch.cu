@@ -298,6 +298,206 @@ patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict_
     }
 }
 
+// --------------------------------------------------------------------------- fused apply: forward, 3-tap windows
+// The hot instantiation (both scale factors < 1.5, e.g. 1242x375 -> 1024x320): an anti-aliasing span holds at
+// most 3 pixels per axis.  Same arithmetic as the general kernel above, re-organised for the issue slots:
+//   * compile-time tile pitch / plane stride: every shared-memory access is base + immediate;
+//   * tiles that cannot see the patch (the placement bounding box misses them: ~85 % of the tiles) copy the
+//     scene straight into the tile -- scene*(1-0) + 0*0 is the scene bit for bit -- skip the mask plane and
+//     write mask 0;
+//   * only the 3 live weights per axis are computed (ATen's normalisation included).
+struct AaSpan3 { int lo; float w[3]; };
+__device__ __forceinline__ AaSpan3 aa_span3(int i, int in_size, float scale) {
+    AaSpan3 s;
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * ((float)i + 0.5f);
+    s.lo = max((int)(center - support + 0.5f), 0);
+    const int n = min(min((int)(center + support + 0.5f), in_size) - s.lo, 3);
+    float total = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float w = 0.f;
+        if (j < n) w = aa_filter(((float)j + ((float)s.lo - center) + 0.5f) * invscale);
+        s.w[j] = w;
+        total += w;
+    }
+    if (total != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s.w[j] = s.w[j] / total;
+    }
+    return s;
+}
+
+template <int PITCH, int ROWS>
+__global__ void __launch_bounds__(PA_THREADS)
+patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
+                        const float* __restrict__ scenes, const float* __restrict__ coeffs,
+                        const int* __restrict__ bbox, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
+                        int t_pad, float sy, float sx, float* __restrict__ adv, float* __restrict__ mask_out) {
+    extern __shared__ float smem[];
+    constexpr int PLANE = PITCH * ROWS;
+    float* comp = smem;                                   // [4][ROWS][PITCH] : 3 colour planes + mask
+    __shared__ int x_lo[PA_TW], y_lo[PA_TH];
+    __shared__ float x_w[PA_TW][3], y_w[PA_TH][3];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * PA_TW, oy0 = blockIdx.y * PA_TH;
+    if (tid < PA_TW) {
+        const AaSpan3 s = aa_span3(min(ox0 + tid, ow - 1), iw, sx);
+        x_lo[tid] = s.lo;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x_w[tid][j] = s.w[j];
+    } else if (tid < PA_TW + PA_TH) {
+        const int k = tid - PA_TW;
+        const AaSpan3 s = aa_span3(min(oy0 + k, oh - 1), ih, sy);
+        y_lo[k] = s.lo;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) y_w[k][j] = s.w[j];
+    }
+    __syncthreads();
+    const int cx0 = x_lo[0], cy0 = y_lo[0];
+    const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
+    const int cw = min(min(x_lo[last_x] + 3, iw) - cx0, PITCH);
+    const int ch = min(min(y_lo[last_y] + 3, ih) - cy0, ROWS);
+    const int IN = ih * iw;
+    const float* sc = scenes + (size_t)b * 3 * IN + cx0;
+    bool tile_hits = true;
+    int bx0 = 0, by0 = 0, bx1 = iw - 1, by1 = ih - 1;
+    if (bbox) {
+        bx0 = __ldg(bbox + b * 4); by0 = __ldg(bbox + b * 4 + 1); bx1 = __ldg(bbox + b * 4 + 2); by1 = __ldg(bbox + b * 4 + 3);
+        tile_hits = !(cx0 > bx1 || cx0 + cw - 1 < bx0 || cy0 > by1 || cy0 + ch - 1 < by0);
+    }
+    // a warp takes a tile row, its lanes the columns; a tile narrower than 3 columns is zero-filled up to 3 so
+    // that the fixed-count loops below never read uninitialised shared memory
+    const int lane = tid & 31, wid = tid >> 5;
+    const int cwz = max(cw, 3);
+    if (!tile_hits) {
+        for (int r = wid; r < ch; r += PA_THREADS / 32) {
+            const float* srow = sc + (cy0 + r) * iw;
+            float* crow = comp + r * PITCH;
+            float sv[(PITCH + 31) / 32][3];
+#pragma unroll
+            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+                const int c = 32 * u + lane;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sv[u][k] = c < cw ? __ldg(srow + k * IN + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+                const int c = 32 * u + lane;
+                if (c < cwz) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) crow[k * PLANE + c] = sv[u][k];
+                }
+            }
+        }
+    } else {
+        const Homography hm = load_homography(coeffs, b, iw, ih);
+        const int PN = ph * pw;
+        for (int r = wid; r < ch; r += PA_THREADS / 32) {
+            const int cy = cy0 + r;
+            const float* srow = sc + cy * iw;
+            float* crow = comp + r * PITCH;
+            float sv[(PITCH + 31) / 32][3];
+#pragma unroll
+            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+                const int c = 32 * u + lane;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sv[u][k] = c < cw ? __ldg(srow + k * IN + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+                const int c = 32 * u + lane;
+                if (c >= cwz) continue;
+                const int cx = cx0 + c;
+                float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                if (c < cw && cx >= bx0 && cx <= bx1 && cy >= by0 && cy <= by1) {
+                    float ix, iy;
+                    perspective_src(hm, cx, cy, iw, ih, ix, iy);
+                    const PatchTaps t = patch_taps(ix, iy, iw, ih, l_pad, t_pad, pw, ph);
+                    if (t.any) {
+                        m = sample_plane(pmask, t, pw);
+                        o0 = sample_plane(patch, t, pw);
+                        o1 = sample_plane(patch + PN, t, pw);
+                        o2 = sample_plane(patch + 2 * PN, t, pw);
+                    }
+                }
+                const float om = sub_rn(1.0f, m);
+                crow[c] = add_rn(mul_rn(sv[u][0], om), mul_rn(o0, m));
+                crow[PLANE + c] = add_rn(mul_rn(sv[u][1], om), mul_rn(o1, m));
+                crow[2 * PLANE + c] = add_rn(mul_rn(sv[u][2], om), mul_rn(o2, m));
+                crow[3 * PLANE + c] = m;
+            }
+        }
+    }
+    __syncthreads();
+    const int tx = tid % PA_TW;
+    const int ox = ox0 + tx;
+    if (ox >= ow) return;
+    const int xl = max(min(x_lo[tx] - cx0, cw - 3), 0);   // (the span itself never exceeds the tile)
+    const int xshift = (x_lo[tx] - cx0) - xl;             // > 0 only if the clamp moved the window: shift the weights
+    const float xw0 = x_w[tx][0], xw1 = x_w[tx][1], xw2 = x_w[tx][2];
+    const float wx0 = xshift == 0 ? xw0 : 0.f;
+    const float wx1 = xshift == 0 ? xw1 : (xshift == 1 ? xw0 : 0.f);
+    const float wx2 = xshift == 0 ? xw2 : (xshift == 1 ? xw1 : (xshift == 2 ? xw0 : 0.f));
+    const int ON = oh * ow;
+    const int ty0 = tid / PA_TW;
+    float* aout = adv + (size_t)b * 3 * ON + (oy0 + ty0) * ow + ox;
+    float* mout = mask_out ? mask_out + (size_t)b * ON + (oy0 + ty0) * ow + ox : nullptr;
+    const float* cbase = comp + xl;
+    constexpr int KSTEP = PA_THREADS / PA_TW;
+    if (tile_hits) {
+#pragma unroll
+        for (int k = 0; k < PA_TH / KSTEP; ++k) {
+            const int ty = ty0 + k * KSTEP;
+            if (oy0 + ty >= oh) break;
+            const int yl = y_lo[ty] - cy0;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float wy = y_w[ty][j];              // 0 beyond the span
+                const float* row = cbase + min(yl + j, ch - 1) * PITCH;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    float h = row[p * PLANE] * wx0;
+                    h = fmaf(row[p * PLANE + 1], wx1, h);
+                    h = fmaf(row[p * PLANE + 2], wx2, h);
+                    acc[p] = fmaf(h, wy, acc[p]);
+                }
+            }
+            aout[k * KSTEP * ow] = acc[0];
+            aout[ON + k * KSTEP * ow] = acc[1];
+            aout[2 * ON + k * KSTEP * ow] = acc[2];
+            if (mout) mout[k * KSTEP * ow] = acc[3];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PA_TH / KSTEP; ++k) {
+            const int ty = ty0 + k * KSTEP;
+            if (oy0 + ty >= oh) break;
+            const int yl = y_lo[ty] - cy0;
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float wy = y_w[ty][j];
+                const float* row = cbase + min(yl + j, ch - 1) * PITCH;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    float h = row[p * PLANE] * wx0;
+                    h = fmaf(row[p * PLANE + 1], wx1, h);
+                    h = fmaf(row[p * PLANE + 2], wx2, h);
+                    acc[p] = fmaf(h, wy, acc[p]);
+                }
+            }
+            aout[k * KSTEP * ow] = acc[0];
+            aout[ON + k * KSTEP * ow] = acc[1];
+            aout[2 * ON + k * KSTEP * ow] = acc[2];
+            if (mout) mout[k * KSTEP * ow] = 0.f;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------- fused apply: backward (to the patch)
 // One thread per canvas pixel: exits unless the pixel samples the patch; gathers
 // the transposed anti-aliased resize of the upstream gradient, multiplies by the
@@ -430,7 +630,29 @@ int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float
         }
     }
     dim3 grid(ceil_div(ow, PA_TW), ceil_div(oh, PA_TH), B);
-    if (sy < 1.5f && sx < 1.5f)
+    if (sy < 1.5f && sx < 1.5f && (long long)ih * iw * 3 < (1ll << 31) && (long long)oh * ow * 3 < (1ll << 31)) {
+        // 3-tap windows: tile extents are compile-time (84 x 24 covers scale factors up to ~1.23, else 104 x 30)
+        const bool small = cw_max <= 84 && ch_max <= 24;
+        const size_t smem3 = sizeof(float) * 4 * (small ? 84 * 24 : 104 * 30);
+        static bool configured[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(patch_apply_fwd3_kernel<104, 30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(sizeof(float) * 4 * 104 * 30));
+            if (e != cudaSuccess) {
+                set_error("dmh_patch_apply_fwd: shared memory unavailable: %s", cudaGetErrorString(e));
+                return DMH_ERR_CUDA;
+            }
+            configured[dev & 63] = true;
+        }
+        if (small)
+            DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out);
+        else
+            DMH_LAUNCH((patch_apply_fwd3_kernel<104, 30>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out);
+    } else if (sy < 1.5f && sx < 1.5f)
         DMH_LAUNCH(patch_apply_fwd_kernel<3>, grid, PA_THREADS, smem, (cudaStream_t)stream)(
             patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
             mask_out);
