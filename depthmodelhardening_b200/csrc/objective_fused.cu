@@ -30,12 +30,32 @@ namespace {
 #define SF_RPW 4
 #define SF_BLOCKS(h, w) ((((w) + SF_TW - 1) / SF_TW) * (((h) + SF_TH - 1) / SF_TH))
 
-__global__ void sf_mean_kernel(const float* __restrict__ disp, int hw, float* __restrict__ part) {
+__global__ void __launch_bounds__(SF_THREADS)
+sf_mean_kernel(const float* __restrict__ disp, int hw, float* __restrict__ part) {
     __shared__ float red[32];
     const int b = blockIdx.y;
     const float* d = disp + (size_t)b * hw;
     float s = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) s += d[i];
+    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (((uintptr_t)d & 15) == 0) {
+        // 128-bit loads, four of them in flight per thread (the kernel is pure latency otherwise)
+        const float4* d4 = reinterpret_cast<const float4*>(d);
+        const int n4 = hw >> 2;
+        int i = t;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            const float4 a = __ldg(d4 + i), b4 = __ldg(d4 + i + stride), c = __ldg(d4 + i + 2 * stride),
+                         e = __ldg(d4 + i + 3 * stride);
+            s += ((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c.x + c.y) + (c.z + c.w)) +
+                 ((e.x + e.y) + (e.z + e.w));
+        }
+        for (; i < n4; i += stride) {
+            const float4 a = __ldg(d4 + i);
+            s += (a.x + a.y) + (a.z + a.w);
+        }
+        for (int j = (n4 << 2) + t; j < hw; j += stride) s += d[j];
+    } else {
+        for (int i = t; i < hw; i += stride) s += d[i];
+    }
     s = block_sum(s, red);
     if (threadIdx.x == 0) part[b * SF_NB1 + blockIdx.x] = s;
 }
@@ -234,7 +254,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
 // arrives last (atomic ticket) adds the S*B results up, again in a fixed order -> deterministic.
 __global__ void __launch_bounds__(256)
 finish_kernel(const FinishParams p) {
-    __shared__ double red[32];
+    __shared__ double red4[4][8];
     __shared__ bool s_last;
     const int blk = blockIdx.x;
     const int s = blk / p.B, b = blk % p.B;
@@ -252,10 +272,17 @@ finish_kernel(const FinishParams p) {
     const long long n = p.photo_n[s];
     const long long lo = n * b / p.B, hi = n * (b + 1) / p.B;
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) ph += (double)p.photo_part[s][i];
-    sx = block_sum_d(sx, red);
-    sy = block_sum_d(sy, red);
-    sg = block_sum_d(sg, red);
-    ph = block_sum_d(ph, red);
+    // the four block sums share one pair of barriers (fixed order: lanes by shuffle tree, then warps 0..7)
+    sx = warp_sum_d(sx); sy = warp_sum_d(sy); sg = warp_sum_d(sg); ph = warp_sum_d(ph);
+    if ((threadIdx.x & 31) == 0) {
+        const int wid = threadIdx.x >> 5;
+        red4[0][wid] = sx; red4[1][wid] = sy; red4[2][wid] = sg; red4[3][wid] = ph;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sx = sy = sg = ph = 0.0;
+        for (int i = 0; i < 8; ++i) { sx += red4[0][i]; sy += red4[1][i]; sg += red4[2][i]; ph += red4[3][i]; }
+    }
     float m = 0.f;
     if (threadIdx.x < 32) m = mean_eps_warp(mean_part, b, hw);
     if (threadIdx.x == 0) {
@@ -268,23 +295,33 @@ finish_kernel(const FinishParams p) {
         s_last = atomicAdd(p.ticket, 1u) == (unsigned)(p.S * p.B - 1);
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last) return;
     __threadfence();
-    double total = 0.0;
-    for (int ss = 0; ss < p.S; ++ss) {
+    // last CTA: warp ss adds up scale ss (lane bb takes images bb, bb+32, ... in order; fixed shuffle tree)
+    const int lane = threadIdx.x & 31, ss = threadIdx.x >> 5;
+    __shared__ double s_loss[8];
+    if (ss < p.S) {
         double a = 0.0, bx = 0.0, by = 0.0;
-        for (int bb = 0; bb < p.B; ++bb) {
+        for (int bb = lane; bb < p.B; bb += 32) {
             const volatile double* o = p.img_sums + ((size_t)ss * p.B + bb) * 3;
             a += o[0]; bx += o[1]; by += o[2];
         }
-        const double inv_nx = 1.0 / ((double)p.B * p.h[ss] * (p.w[ss] - 1));
-        const double inv_ny = 1.0 / ((double)p.B * (p.h[ss] - 1) * p.w[ss]);
-        const double loss = a * p.inv_photo_den + (double)p.smooth_weight[ss] * (bx * inv_nx + by * inv_ny);
-        p.losses[ss] = (float)loss;
-        total += loss;
+        a = warp_sum_d(a); bx = warp_sum_d(bx); by = warp_sum_d(by);
+        if (lane == 0) {
+            const double inv_nx = 1.0 / ((double)p.B * p.h[ss] * (p.w[ss] - 1));
+            const double inv_ny = 1.0 / ((double)p.B * (p.h[ss] - 1) * p.w[ss]);
+            const double loss = a * p.inv_photo_den + (double)p.smooth_weight[ss] * (bx * inv_nx + by * inv_ny);
+            p.losses[ss] = (float)loss;
+            s_loss[ss] = loss;
+        }
     }
-    p.losses[p.S] = (float)(total / (double)p.S);
-    *p.ticket = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int i = 0; i < p.S; ++i) total += s_loss[i];
+        p.losses[p.S] = (float)(total / (double)p.S);
+        *p.ticket = 0u;
+    }
 }
 
 // Transposed bilinear up-sampling (F.interpolate backward) + normalisation backward + upstream scaling.
@@ -315,6 +352,31 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ grow, int X
 #pragma unroll
         for (int j = 0; j < R; ++j) v[j] = (X + j >= 0 && X + j < W) ? __ldg(grow + X + j) : 0.f;
     }
+}
+
+// Same-size case (scale 0) of dmh_disp_grad: pure elementwise, 4 pixels per thread (128-bit loads / stores).
+__global__ void __launch_bounds__(256)
+disp_grad_same_kernel(const float4* __restrict__ G4, const float4* __restrict__ gN4, const float* __restrict__ img_scalars,
+                      float smooth_weight, const float* __restrict__ g_total, const float* __restrict__ g_scale,
+                      const float* __restrict__ g_smooth, float inv_S, int n4, float4* __restrict__ grad4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int b = blockIdx.y;
+    const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
+    const size_t o = (size_t)b * n4 + i;
+    const float4 a = __ldg(G4 + o);
+    float acc[4] = {a.x, a.y, a.z, a.w}, sm[4] = {0.f, 0.f, 0.f, 0.f}, out[4];
+    if (gN4) {
+        const float inv_m = img_scalars[b * 2], corr = img_scalars[b * 2 + 1];
+        const float4 n = __ldg(gN4 + o);
+        const float nv[4] = {n.x, n.y, n.z, n.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm[j] = smooth_weight * (nv[j] * inv_m - corr);
+    }
+    const float gsm = g_smooth ? g_smooth[0] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = g_smooth ? fmaf(gsm, sm[j], up * acc[j]) : up * (acc[j] + sm[j]);
+    grad4[o] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 template <int R>
@@ -367,25 +429,40 @@ disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
         const int Xc = R * x - R / 2;                        // first full-res column of this lane's chunk
         const int Xe = R * (blockIdx.x * 32 + 32) - R / 2;  // chunk 32 (lane 0 takes it)
         const int Yt = R * (blockIdx.y * 8) - R / 2;        // first full-res row of the tile's window
-        for (int ry = wid; ry < NR; ry += 8) {
-            const int Y = Yt + ry;
-            float a = 0.f, bm = 0.f, e = 0.f;
-            if (Y >= 0 && Y < H) {                           // warp-uniform
-                const float* grow = g + (size_t)Y * W;
-                float v[RR];
-                load_chunk<RR>(grow, Xc, W, v);
+        // rows of this warp: wid, wid + 8, ...; the loads of a batch of rows are issued before any is consumed
+        constexpr int NPW = (NR + 7) / 8, BS = RR >= 8 ? 3 : NPW;
 #pragma unroll
-                for (int j = 0; j < RR; ++j) { a = fmaf(wA[j], v[j], a); bm = fmaf(wB[j], v[j], bm); }
-                if (lane == 0) {
-                    load_chunk<RR>(grow, Xe, W, v);
+        for (int i0 = 0; i0 < NPW; i0 += BS) {
+            float v[BS][RR], ve[BS][RR];
 #pragma unroll
-                    for (int j = 0; j < RR; ++j) e = fmaf(wE[j], v[j], e);
+            for (int i = 0; i < BS; ++i) {
+                const int ry = wid + 8 * (i0 + i), Y = Yt + ry;
+                const bool ok = i0 + i < NPW && ry < NR && Y >= 0 && Y < H;      // warp-uniform
+                const float* grow = g + (size_t)(ok ? Y : 0) * W;
+                if (ok) load_chunk<RR>(grow, Xc, W, v[i]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < RR; ++j) v[i][j] = 0.f;
+                }
+                if (ok && lane == 0) load_chunk<RR>(grow, Xe, W, ve[i]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < RR; ++j) ve[i][j] = 0.f;
                 }
             }
-            float nb = __shfl_down_sync(0xffffffffu, bm, 1);
-            const float ee = __shfl_sync(0xffffffffu, e, 0);
-            if (lane == 31) nb = ee;
-            s_h[ry][lane] = a + nb;
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                const int ry = wid + 8 * (i0 + i);
+                float a = 0.f, bm = 0.f, e = 0.f;
+#pragma unroll
+                for (int j = 0; j < RR; ++j) {
+                    a = fmaf(wA[j], v[i][j], a); bm = fmaf(wB[j], v[i][j], bm); e = fmaf(wE[j], ve[i][j], e);
+                }
+                float nb = __shfl_down_sync(0xffffffffu, bm, 1);
+                const float ee = __shfl_sync(0xffffffffu, e, 0);
+                if (lane == 31) nb = ee;
+                if (i0 + i < NPW && ry < NR) s_h[ry][lane] = a + nb;
+            }
         }
         __syncthreads();
         if (!in) return;
@@ -494,7 +571,13 @@ int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars
     if (R > 1 && ((uintptr_t)G_full % 16 != 0 || W % 4 != 0)) R = 0;   // vector loads need aligned rows
 #define DMH_DG(RR) DMH_LAUNCH(disp_grad_kernel<RR>, grid, block, 0, st)(G_full, gN, img_scalars, smooth_weight, g_total, \
                                                                        g_scale, g_smooth, inv_S, h, w, H, W, sh, sw, grad_disp)
-    if (R == 1) DMH_DG(1);
+    if (R == 1 && ((size_t)h * w) % 4 == 0 && (uintptr_t)G_full % 16 == 0 && (uintptr_t)grad_disp % 16 == 0 &&
+        (!gN || (uintptr_t)gN % 16 == 0)) {
+        const int n4 = (int)(((size_t)h * w) / 4);
+        DMH_LAUNCH(disp_grad_same_kernel, dim3(ceil_div(n4, 256), B), 256, 0, st)(
+            reinterpret_cast<const float4*>(G_full), reinterpret_cast<const float4*>(gN), img_scalars, smooth_weight,
+            g_total, g_scale, g_smooth, inv_S, n4, reinterpret_cast<float4*>(grad_disp));
+    } else if (R == 1) DMH_DG(1);
     else if (R == 2) DMH_DG(2);
     else if (R == 4) DMH_DG(4);
     else if (R == 8) DMH_DG(8);
