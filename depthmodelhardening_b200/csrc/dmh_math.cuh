@@ -350,62 +350,77 @@ DMH_HD Row5T<T> row5(T x0, T x1, T x2, T y0, T y1, T y2) {
     return r;
 }
 
-template <class T> struct SsimStatsT { T mu_x, mu_y, A1, A2, B1, B2, n, d; };
+// Window statistics in SUM form: with X = sum x, XY = sum x*y, ... over the 3x3 window (mu_x = X/9,
+// sigma_xy = XY/9 - X*Y/81) every factor of SSIM is carried multiplied by 81,
+//   A1 = 2*X*Y + 81*C1            B1 = X^2 + Y^2 + 81*C1
+//   A2 = 18*XY - 2*X*Y + 81*C2    B2 = 9*(XX + YY) - (X^2 + Y^2) + 81*C2
+// n/d = (A1*A2)/(B1*B2) is unchanged (the 81^2 cancel) and the five divisions by 9 disappear; the cancellation
+// in the variances is the same as in the mean form (same relative rounding, ~1e-7).
+template <class T> struct SsimStatsT { T X, Y, A1, A2, B1, B2, n, d; };
 
 template <class T>
 DMH_HD SsimStatsT<T> ssim_stats_rows_t(const Row5T<T>& a, const Row5T<T>& b, const Row5T<T>& c) {
-    const T inv9 = Lane<T>::splat(1.0f / 9.0f), two = Lane<T>::splat(2.0f);
-    const T c1 = Lane<T>::splat(DMH_SSIM_C1), c2 = Lane<T>::splat(DMH_SSIM_C2);
+    const T c1 = Lane<T>::splat(81.0f * DMH_SSIM_C1), c2 = Lane<T>::splat(81.0f * DMH_SSIM_C2);
+    const T two = Lane<T>::splat(2.0f), mtwo = Lane<T>::splat(-2.0f), nine = Lane<T>::splat(9.0f),
+            eighteen = Lane<T>::splat(18.0f);
     SsimStatsT<T> s;
-    s.mu_x = vmul(vadd(vadd(a.x, b.x), c.x), inv9);
-    s.mu_y = vmul(vadd(vadd(a.y, b.y), c.y), inv9);
-    const T exx = vmul(vadd(vadd(a.xx, b.xx), c.xx), inv9);
-    const T eyy = vmul(vadd(vadd(a.yy, b.yy), c.yy), inv9);
-    const T exy = vmul(vadd(vadd(a.xy, b.xy), c.xy), inv9);
-    const T mxx = vmul(s.mu_x, s.mu_x), myy = vmul(s.mu_y, s.mu_y), mxy = vmul(s.mu_x, s.mu_y);
-    const T sig_x = vsub(exx, mxx), sig_y = vsub(eyy, myy), sig_xy = vsub(exy, mxy);
-    s.A1 = vfma(two, mxy, c1);
-    s.A2 = vfma(two, sig_xy, c2);
-    s.B1 = vadd(vadd(mxx, myy), c1);
-    s.B2 = vadd(vadd(sig_x, sig_y), c2);
+    s.X = vadd(vadd(a.x, b.x), c.x);
+    s.Y = vadd(vadd(a.y, b.y), c.y);
+    const T sxx = vadd(vadd(a.xx, b.xx), c.xx), syy = vadd(vadd(a.yy, b.yy), c.yy), sxy = vadd(vadd(a.xy, b.xy), c.xy);
+    const T pxy = vmul(s.X, s.Y), pxx = vmul(s.X, s.X), pyy = vmul(s.Y, s.Y);
+    const T p2 = vadd(pxx, pyy);
+    s.A1 = vfma(two, pxy, c1);
+    s.A2 = vfma(eighteen, sxy, vfma(mtwo, pxy, c2));
+    s.B1 = vadd(p2, c1);
+    s.B2 = vfma(nine, vadd(sxx, syy), vsub(c2, p2));
     s.n = vmul(s.A1, s.A2);
     s.d = vmul(s.B1, s.B2);
     return s;
 }
 
-// dS/dx_k = ax + b*x_k + c*y_k   and   dS/dy_k = ay + b*y_k + c*x_k  (see ssim_coef above)
-template <class T> struct SsimCoefT { T ax, ay, b, c; };
-
-// value + coefficients sharing one reciprocal of d; `pass` = 1 where the clamp passes gradient
+// clamp((1 - n/d)/2, 0, 1); also returns r = 1/d and nr = n/d for the coefficients, `pass` = 1 where the
+// clamp passes gradient (inclusive)
 template <class T>
-DMH_HD T ssim_value_coef_t(const SsimStatsT<T>& s, T& pass, SsimCoefT<T>& k) {
-    const T one = Lane<T>::splat(1.0f), half = Lane<T>::splat(0.5f);
-    const T inv9 = Lane<T>::splat(1.0f / 9.0f), ninv9 = Lane<T>::splat(-1.0f / 9.0f);
-    const T r = vrcp(s.d);
-    const T nr = vmul(s.n, r);
-    const T v = vmul(vsub(one, nr), half);
+DMH_HD T ssim_value_t(const SsimStatsT<T>& s, T& pass, T& r, T& nr) {
+    r = vrcp(s.d);
+    nr = vmul(s.n, r);
+    const T v = vfma(nr, Lane<T>::splat(-0.5f), Lane<T>::splat(0.5f));
     pass = vpass01(v);
-    const T nr2 = vmul(nr, r);
-    const T dA = vmul(vsub(s.A2, s.A1), r), dB = vmul(nr2, vsub(s.B2, s.B1));
-    k.ax = vmul(ninv9, vsub(vmul(s.mu_y, dA), vmul(s.mu_x, dB)));
-    k.ay = vmul(ninv9, vsub(vmul(s.mu_x, dA), vmul(s.mu_y, dB)));
-    k.b = vmul(vmul(inv9, nr2), s.B1);
-    k.c = vmul(vmul(ninv9, s.A1), r);
     return vclamp01(v);
 }
 
-// scalar entry points (names used by the kernels and by tests/host_emul.cpp)
-DMH_HD SsimStats ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) {
-    const SsimStatsT<float> t = ssim_stats_rows_t<float>(a, b, c);
-    SsimStats s;
-    s.mu_x = t.mu_x; s.mu_y = t.mu_y; s.A1 = t.A1; s.A2 = t.A2; s.B1 = t.B1; s.B2 = t.B2; s.n = t.n; s.d = t.d;
-    return s;
+// g * dS/dx_k = ka + kb*x_k + kc*y_k for every tap k of the (reflect-padded) 3x3 window (see ssim_coef above;
+// in sum form  ka = g*[X*(B2-B1)*n/d^2 - Y*(A2-A1)/d],  kb = 9*g*n*B1/d^2,  kc = -9*g*A1/d)
+template <class T>
+DMH_HD void ssim_coef_gated_t(const SsimStatsT<T>& s, T r, T nr, T g, T& ka, T& kb, T& kc) {
+    const T gr = vmul(g, r);
+    const T gnr2 = vmul(gr, nr);
+    kc = vmul(vmul(gr, Lane<T>::splat(-9.0f)), s.A1);
+    kb = vmul(vmul(gnr2, Lane<T>::splat(9.0f)), s.B1);
+    const T e1 = vmul(gnr2, vsub(s.B2, s.B1)), e2 = vmul(gr, vsub(s.A2, s.A1));
+    ka = vsub(vmul(s.X, e1), vmul(s.Y, e2));
 }
-DMH_HD float ssim_value_coef(const SsimStats& s, float& pass, SsimCoef& k) {
-    SsimStatsT<float> t;
-    t.mu_x = s.mu_x; t.mu_y = s.mu_y; t.A1 = s.A1; t.A2 = s.A2; t.B1 = s.B1; t.B2 = s.B2; t.n = s.n; t.d = s.d;
+
+// dS/dx_k = ax + b*x_k + c*y_k   and   dS/dy_k = ay + b*y_k + c*x_k  (see ssim_coef above)
+template <class T> struct SsimCoefT { T ax, ay, b, c; };
+
+// value + un-gated coefficients sharing one reciprocal of d; `pass` = 1 where the clamp passes gradient
+template <class T>
+DMH_HD T ssim_value_coef_t(const SsimStatsT<T>& s, T& pass, SsimCoefT<T>& k) {
+    T r, nr;
+    const T v = ssim_value_t(s, pass, r, nr);
+    ssim_coef_gated_t(s, r, nr, Lane<T>::splat(1.0f), k.ax, k.b, k.c);
+    const T nr2 = vmul(nr, r);
+    k.ay = vsub(vmul(s.Y, vmul(nr2, vsub(s.B2, s.B1))), vmul(s.X, vmul(r, vsub(s.A2, s.A1))));
+    return v;
+}
+
+// scalar entry points (names used by the kernels and by tests/host_emul.cpp)
+typedef SsimStatsT<float> SsimStatsRows;
+DMH_HD SsimStatsRows ssim_stats_rows(const Row5& a, const Row5& b, const Row5& c) { return ssim_stats_rows_t<float>(a, b, c); }
+DMH_HD float ssim_value_coef(const SsimStatsRows& s, float& pass, SsimCoef& k) {
     SsimCoefT<float> kt;
-    const float v = ssim_value_coef_t<float>(t, pass, kt);
+    const float v = ssim_value_coef_t<float>(s, pass, kt);
     k.ax = kt.ax; k.ay = kt.ay; k.b = kt.b; k.c = kt.c;
     return v;
 }

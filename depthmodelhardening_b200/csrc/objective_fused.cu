@@ -70,6 +70,13 @@ __device__ __forceinline__ float mean_eps_warp(const float* __restrict__ mean_pa
 }
 
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+// exp(-s / C) for s >= 0 as one multiply + MUFU.EX2 (relative error 2^-22, far inside the 1e-5 tolerance of the
+// smoothness term; expf's range reduction costs ~8 more issue slots per edge)
+__device__ __forceinline__ float edge_weight(float sabs, float neg_inv_c_log2e) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sabs * neg_inv_c_log2e));
+    return r;
+}
 
 // four consecutive pixels of one row (x .. x+3); zeros beyond the row end
 __device__ __forceinline__ void load_px4(const float* __restrict__ row, int x, int w, bool vec, float v[4]) {
@@ -88,7 +95,7 @@ __device__ __forceinline__ void load_px4(const float* __restrict__ row, int x, i
 // of every edge is evaluated once by the pixel on its left / top ("owner") and reaches the right / bottom
 // neighbour through a register or a warp shuffle.
 template <int C>
-__global__ void __launch_bounds__(SF_THREADS)
+__global__ void __launch_bounds__(SF_THREADS, 4)
 sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, int h, int w,
                const float* __restrict__ mean_part, float inv_nx, float inv_ny, int vec, float* __restrict__ gN,
                float* __restrict__ part) {
@@ -103,7 +110,7 @@ sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, in
     }
     __syncthreads();
     const float inv_m = s_m;
-    const float inv_c = 1.0f / (float)C;
+    const float nicl = -1.4426950408889634f / (float)C;
     const float* d = disp + (size_t)b * hw;
     const float* im = img + (size_t)b * C * hw;
     const int x = blockIdx.x * SF_TW + 4 * lane;
@@ -145,7 +152,7 @@ sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, in
             float sabs = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - in_[c][j]);
-            const float e = expf(-(sabs * inv_c));
+            const float e = edge_weight(sabs, nicl);
             const float diff = dc[j] * inv_m - dn_[j] * inv_m;
             const bool ok = row_ok && below_ok && x + j < w;
             gy[j] = ok ? sgn(diff) * e : 0.f;
@@ -168,7 +175,7 @@ sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, in
                 float sabs = 0.f;
 #pragma unroll
                 for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - (j < 3 ? ic[c][j + 1] : ir[c]));
-                const float e = expf(-(sabs * inv_c));
+                const float e = edge_weight(sabs, nicl);
                 const float diff = dc[j] * inv_m - (j < 3 ? dc[j + 1] : dr) * inv_m;
                 const bool ok = row_ok && x + j < w - 1;
                 gx[j] = ok ? sgn(diff) * e : 0.f;
@@ -183,7 +190,7 @@ sf_main_kernel(const float* __restrict__ disp, const float* __restrict__ img, in
 #pragma unroll
                     for (int c = 0; c < C; ++c) sabs += fabsf(__ldg(im + (size_t)c * hw + (size_t)y * w + xl) - ic[c][0]);
                     const float diff = __ldg(d + (size_t)y * w + xl) * inv_m - dc[0] * inv_m;
-                    gl = sgn(diff) * expf(-(sabs * inv_c));
+                    gl = sgn(diff) * edge_weight(sabs, nicl);
                 }
             }
             if (row_ok) {

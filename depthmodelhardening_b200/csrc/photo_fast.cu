@@ -393,7 +393,6 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         Row5T<float> histS[2];                          // channel 2
         float2 cenxP, cenyP;                            // centre values of the previous row
         float cenxS, cenyS;
-        const float2 w_ssim2 = make_float2(w_ssim, w_ssim);
 #pragma unroll
         for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
             const int r2 = min(r0 + rr, FT_R2 - 1);     // R2 row being added
@@ -413,25 +412,26 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 float l1 = fabsf(cenyP.x - cenxP.x);
                 l1 += fabsf(cenyP.y - cenxP.y);
                 l1 += fabsf(cenyS - cenxS);
-                float2 passP;
-                SsimCoefT<float2> kP;
-                const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
-                float passS;
-                SsimCoefT<float> kS;
-                const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
+                const SsimStatsT<float2> stP = ssim_stats_rows_t(histP[0], histP[1], curP);
+                const SsimStatsT<float> stS = ssim_stats_rows_t(histS[0], histS[1], curS);
+                float2 passP, rP, nrP;
+                const float2 vP = ssim_value_t(stP, passP, rP, nrP);
+                float passS, rS, nrS;
+                const float vS = ssim_value_t(stS, passS, rS, nrS);
                 const float ss = (vP.x + vP.y) + vS;
                 l1 *= (1.0f / 3.0f);
                 const float rp = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
                 const float idv = idv_pre[rr - 2];
                 const bool win = rp < idv;              // torch.min: first minimum wins, identity is first
                 const float gw = win ? w_ssim : 0.0f;
-                const float2 gP = vmul(make_float2(gw, gw), passP);
-                const float gS = gw * passS;
+                float2 kaP, kbP, kcP;
+                ssim_coef_gated_t(stP, rP, nrP, vmul(make_float2(gw, gw), passP), kaP, kbP, kcP);
+                float kaS, kbS, kcS;
+                ssim_coef_gated_t(stS, rS, nrS, gw * passS, kaS, kbS, kcS);
                 if (qr < FT_R1) {
                     const int qi = qr * FT_R1 + bc;
-                    coefP[0 * FT_N1 + qi] = vmul(gP, kP.ax); coefP[1 * FT_N1 + qi] = vmul(gP, kP.b);
-                    coefP[2 * FT_N1 + qi] = vmul(gP, kP.c);
-                    coefS[0 * FT_N1 + qi] = gS * kS.ax; coefS[1 * FT_N1 + qi] = gS * kS.b; coefS[2 * FT_N1 + qi] = gS * kS.c;
+                    coefP[0 * FT_N1 + qi] = kaP; coefP[1 * FT_N1 + qi] = kbP; coefP[2 * FT_N1 + qi] = kcP;
+                    coefS[0 * FT_N1 + qi] = kaS; coefS[1 * FT_N1 + qi] = kbS; coefS[2 * FT_N1 + qi] = kcS;
                     gate[qi] = win ? 1 : 0;
                 }
                 if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
@@ -525,18 +525,55 @@ struct IdentParams {
     int B, F, H, W, no_ssim;
 };
 
-__global__ void __launch_bounds__(256)
-ident_fast_kernel(const IdentParams p) {
-    __shared__ float xs[3][ID_N];
-    __shared__ float ys[3][ID_N];
+// TMA: both tiles arrive by cp.async.bulk.tensor (box 40 x 34 x 3 at (x0-4, y0-1): 16-byte aligned start column,
+// zero fill outside the image, reflection patched in shared memory on border tiles) -- no per-thread load / index
+// instructions at all; otherwise plain loads with the same shared-memory layout.
+#define ID_P 40                  // row pitch of the tiles
+#define ID_O 3                   // column of the tile that holds halo column 0 (image column x0-1)
+#define ID_PL (ID_R * ID_P)      // plane stride
+struct IdentMaps { CUtensorMap tgt; CUtensorMap src[DMH_PHOTO_MAX_FRAMES]; };
+
+template <bool TMA>
+__global__ void __launch_bounds__(256, 4)
+ident_fast_kernel(const IdentParams p, const __grid_constant__ IdentMaps maps) {
+    __shared__ __align__(128) float xs[3 * ID_PL];
+    __shared__ __align__(128) float ys[3 * ID_PL];
+    __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int H = p.H, W = p.W;
     const int b = blockIdx.z / p.F, f = blockIdx.z % p.F;
     const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
     const size_t N = (size_t)H * W;
-    const float* sp = p.src[f] + (size_t)b * 3 * N;
-    const float* tp = p.target + (size_t)b * 3 * N;
-    {   // tile + 1-px reflect halo: a warp takes a row (index maths once per row / per lane), 6 loads in flight
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, 2 * 3 * ID_PL * sizeof(float));
+            tma_load_4d(xs, &maps.src[f], &bar, x0 - 1 - ID_O, y0 - 1, 0, b);
+            tma_load_4d(ys, &maps.tgt, &bar, x0 - 1 - ID_O, y0 - 1, 0, b);
+        }
+        __syncthreads();                                  // barrier initialised before anyone polls it
+        mbar_wait(&bar, 0);
+        if (x0 < 1 || y0 < 1 || x0 + FT_T + 1 > W || y0 + FT_T + 1 > H) {
+            for (int i = tid; i < ID_N; i += 256) {
+                const int r = i / ID_R, c = i - r * ID_R;
+                const int ey = y0 - 1 + r, ex = x0 - 1 + c;
+                if (ey < 0 || ey >= H || ex < 0 || ex >= W) {
+                    const int sr = ext_to_img(ey, H) - (y0 - 1), sc = ext_to_img(ex, W) - (x0 - 1);
+                    // a reflected source may itself lie outside the tile when the image is narrower than the halo
+                    if (sr >= 0 && sr < ID_R && sc >= 0 && sc < ID_R) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            xs[ch * ID_PL + r * ID_P + c + ID_O] = xs[ch * ID_PL + sr * ID_P + sc + ID_O];
+                            ys[ch * ID_PL + r * ID_P + c + ID_O] = ys[ch * ID_PL + sr * ID_P + sc + ID_O];
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // tile + 1-px reflect halo: a warp takes a row (index maths once per row / per lane), 6 loads in flight
+        const float* sp = p.src[f] + (size_t)b * 3 * N;
+        const float* tp = p.target + (size_t)b * 3 * N;
         const int lane = tid & 31, wid = tid >> 5;
         const int ixa = ext_to_img(x0 - 1 + lane, W);
         const int ixb = ext_to_img(x0 - 1 + 32 + (lane & 1), W);          // columns 32, 33 (lanes 0, 1)
@@ -544,14 +581,14 @@ ident_fast_kernel(const IdentParams p) {
             const size_t ro = (size_t)ext_to_img(y0 - 1 + r, H) * W;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                xs[ch][r * ID_R + lane] = __ldg(sp + ch * N + ro + ixa);
-                ys[ch][r * ID_R + lane] = __ldg(tp + ch * N + ro + ixa);
+                xs[ch * ID_PL + r * ID_P + lane + ID_O] = __ldg(sp + ch * N + ro + ixa);
+                ys[ch * ID_PL + r * ID_P + lane + ID_O] = __ldg(tp + ch * N + ro + ixa);
             }
             if (lane < 2) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    xs[ch][r * ID_R + 32 + lane] = __ldg(sp + ch * N + ro + ixb);
-                    ys[ch][r * ID_R + 32 + lane] = __ldg(tp + ch * N + ro + ixb);
+                    xs[ch * ID_PL + r * ID_P + 32 + lane + ID_O] = __ldg(sp + ch * N + ro + ixb);
+                    ys[ch * ID_PL + r * ID_P + 32 + lane + ID_O] = __ldg(tp + ch * N + ro + ixb);
                 }
             }
         }
@@ -564,8 +601,8 @@ ident_fast_kernel(const IdentParams p) {
         for (int k = 0; k < 4; ++k) {
             const int r = 4 * strip + k, py = y0 + r;
             if (py < H) {
-                const int i = (r + 1) * ID_R + c + 1;
-                p.packed[(size_t)b * N + (size_t)py * W + px] = make_float4(xs[0][i], xs[1][i], xs[2][i], 0.0f);
+                const int i = (r + 1) * ID_P + c + 1 + ID_O;
+                p.packed[(size_t)b * N + (size_t)py * W + px] = make_float4(xs[i], xs[ID_PL + i], xs[2 * ID_PL + i], 0.0f);
             }
         }
     }
@@ -579,15 +616,15 @@ ident_fast_kernel(const IdentParams p) {
 #pragma unroll
     for (int rr = 0; rr < 6; ++rr) {
         const int r2 = 4 * strip + rr;                   // halo-tile row
-        const float* x0p = &xs[0][r2 * ID_R + c];
-        const float* y0p = &ys[0][r2 * ID_R + c];
-        const float2 xa = make_float2(x0p[0], x0p[ID_N]), xb = make_float2(x0p[1], x0p[ID_N + 1]),
-                     xc = make_float2(x0p[2], x0p[ID_N + 2]);
-        const float2 ya = make_float2(y0p[0], y0p[ID_N]), yb = make_float2(y0p[1], y0p[ID_N + 1]),
-                     yc = make_float2(y0p[2], y0p[ID_N + 2]);
+        const float* x0p = xs + r2 * ID_P + c + ID_O;
+        const float* y0p = ys + r2 * ID_P + c + ID_O;
+        const float2 xa = make_float2(x0p[0], x0p[ID_PL]), xb = make_float2(x0p[1], x0p[ID_PL + 1]),
+                     xc = make_float2(x0p[2], x0p[ID_PL + 2]);
+        const float2 ya = make_float2(y0p[0], y0p[ID_PL]), yb = make_float2(y0p[1], y0p[ID_PL + 1]),
+                     yc = make_float2(y0p[2], y0p[ID_PL + 2]);
         const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
-        const float* x2p = x0p + 2 * ID_N;
-        const float* y2p = y0p + 2 * ID_N;
+        const float* x2p = x0p + 2 * ID_PL;
+        const float* y2p = y0p + 2 * ID_PL;
         const Row5T<float> curS = row5(x2p[0], x2p[1], x2p[2], y2p[0], y2p[1], y2p[2]);
         if (rr >= 2) {
             const int py = y0 + 4 * strip + rr - 2;
@@ -597,12 +634,10 @@ ident_fast_kernel(const IdentParams p) {
                 l1 += fabsf(cenyS - cenxS);
                 float ss = 0.f;
                 if (!p.no_ssim) {
-                    float2 passP;
-                    SsimCoefT<float2> kP;
-                    const float2 vP = ssim_value_coef_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, kP);
-                    float passS;
-                    SsimCoefT<float> kS;
-                    const float vS = ssim_value_coef_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, kS);
+                    float2 passP, rP, nrP;
+                    const float2 vP = ssim_value_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, rP, nrP);
+                    float passS, rS, nrS;
+                    const float vS = ssim_value_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, rS, nrS);
                     ss = (vP.x + vP.y) + vS;
                 }
                 l1 *= (1.0f / 3.0f);
@@ -720,7 +755,26 @@ int launch_ident_fast(const float* target, const float* const* src_host, int F, 
     for (int f = 0; f < DMH_PHOTO_MAX_FRAMES; ++f) p.src[f] = f < F ? src_host[f] : nullptr;
     p.out = out; p.B = B; p.F = F; p.H = H; p.W = W; p.no_ssim = no_ssim;
     dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B * F);
-    DMH_LAUNCH(ident_fast_kernel, grid, 256, 0, st)(p);
+    // TMA descriptors of the frames viewed as (W, H, 3, B) fp32 tensors; rows must be 16-byte aligned
+    IdentMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool use_tma = (W % 4 == 0) && ((uintptr_t)target % 16 == 0) && tma_encoder() != nullptr;
+    for (int f = 0; f < F && use_tma; ++f) use_tma = (uintptr_t)src_host[f] % 16 == 0;
+    if (use_tma) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
+        const cuuint32_t box[4] = {ID_P, ID_R, 3, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        for (int f = -1; f < F && use_tma; ++f) {
+            const float* base = f < 0 ? target : src_host[f];
+            use_tma = tma_encoder()(f < 0 ? &maps.tgt : &maps.src[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                    const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+    }
+    if (use_tma) DMH_LAUNCH(ident_fast_kernel<true>, grid, 256, 0, st)(p, maps);
+    else DMH_LAUNCH(ident_fast_kernel<false>, grid, 256, 0, st)(p, maps);
     return DMH_OK;
 }
 

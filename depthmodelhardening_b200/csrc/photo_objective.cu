@@ -85,7 +85,7 @@ __device__ __forceinline__ Taps make_taps(const Bilinear& bl, int H, int W) {
 // 3x3 window statistics for one channel plane in shared memory around R2 position (r+1, c+1).
 // Same arithmetic as the single-source fast kernel and the identity-loss kernel (row sums of 3, then 3 rows,
 // mean = sum * (1/9)) so that the automask compares like with like.
-__device__ __forceinline__ SsimStats window_stats(const float* __restrict__ xs, const float* __restrict__ ys, int r,
+__device__ __forceinline__ SsimStatsRows window_stats(const float* __restrict__ xs, const float* __restrict__ ys, int r,
                                                   int c) {
     Row5 rows[3];
 #pragma unroll
@@ -324,7 +324,7 @@ photo_scale_kernel(const PhotoParams p) {
             for (int ch = 0; ch < 3; ++ch) {
                 float a = 0.f, bq = 0.f, cq = 0.f;
                 if (gate != 0.f && !no_ssim) {
-                    const SsimStats st = window_stats(pred + (f * 3 + ch) * PH_R2, tgt + ch * PH_R2, r, c);
+                    const SsimStatsRows st = window_stats(pred + (f * 3 + ch) * PH_R2, tgt + ch * PH_R2, r, c);
                     float pass;
                     SsimCoef k;
                     ssim_value_coef(st, pass, k);

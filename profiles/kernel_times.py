@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Per-kernel average durations of the bench step measured in place (torch.profiler / CUPTI activity records:
+warm caches, real launch order), unlike the serialised cold-cache ncu launch list.
+usage: python profiles/kernel_times.py [--steps 10] [--batch 32]"""
+import argparse
+import collections
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=32)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    pb, pt = bench.make_host_workload(a.batch, 0, True)
+    s2, s1 = bench.Stage2(pb, dev), bench.Stage1(pt, dev, 1)
+
+    def step():
+        s1.step()
+        s2.step()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(a.steps):
+            step()
+        torch.cuda.synchronize()
+    tot = collections.Counter()
+    cnt = collections.Counter()
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            tot[e.name] += e.device_time
+            cnt[e.name] += 1
+    s = 0.0
+    for k, v in tot.most_common():
+        print("%9.1f us/step  %3d launches/step  avg %8.1f us  %s" % (v / a.steps, cnt[k] // a.steps, v / cnt[k], k[:90]))
+        s += v / a.steps
+    print("%9.1f us/step  sum of kernel time" % s)
+
+
+if __name__ == "__main__":
+    main()

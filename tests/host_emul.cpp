@@ -357,7 +357,7 @@ void emu_photo_scale_fast(const float* target, const float* src, const float* T,
                             rows[dy + 1] = row5(PX(pred, c, qy + dy, qx - 1), PX(pred, c, qy + dy, qx), PX(pred, c, qy + dy, qx + 1),
                                                 TG(qy + dy, qx - 1), TG(qy + dy, qx), TG(qy + dy, qx + 1));
                         }
-                        SsimStats st = ssim_stats_rows(rows[0], rows[1], rows[2]);
+                        SsimStatsRows st = ssim_stats_rows(rows[0], rows[1], rows[2]);
                         float pass; SsimCoef k;
                         ss += ssim_value_coef(st, pass, k);
                         const float g = w_ssim * pass;
