@@ -307,12 +307,19 @@ patch_apply_fwd_kernel(const float* __restrict__ patch, const float* __restrict_
 //     write mask 0;
 //   * only the 3 live weights per axis are computed (ATen's normalisation included).
 struct AaSpan3 { int lo; float w[3]; };
+// first input index of the anti-aliasing span of output index i; explicitly rounded op by op so that every caller
+// (the per-thread tile geometry and the weight table) gets the same integer
+__device__ __forceinline__ int aa_span_lo(int i, float scale) {
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float center = mul_rn(scale, add_rn((float)i, 0.5f));
+    return max((int)add_rn(sub_rn(center, support), 0.5f), 0);
+}
 __device__ __forceinline__ AaSpan3 aa_span3(int i, int in_size, float scale) {
     AaSpan3 s;
     const float support = scale >= 1.0f ? scale : 1.0f;
     const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
-    const float center = scale * ((float)i + 0.5f);
-    s.lo = max((int)(center - support + 0.5f), 0);
+    const float center = mul_rn(scale, add_rn((float)i, 0.5f));
+    s.lo = aa_span_lo(i, scale);
     const int n = min(min((int)(center + support + 0.5f), in_size) - s.lo, 3);
     float total = 0.f;
 #pragma unroll
@@ -337,12 +344,35 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
                         int t_pad, float sy, float sx, float* __restrict__ adv, float* __restrict__ mask_out) {
     extern __shared__ float smem[];
     constexpr int PLANE = PITCH * ROWS;
+    constexpr int NCU = (PITCH + 31) / 32, NRU = (ROWS + 7) / 8;
     float* comp = smem;                                   // [4][ROWS][PITCH] : 3 colour planes + mask
     __shared__ int x_lo[PA_TW], y_lo[PA_TH];
     __shared__ float x_w[PA_TW][3], y_w[PA_TH][3];
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
     const int ox0 = blockIdx.x * PA_TW, oy0 = blockIdx.y * PA_TH;
+    // tile geometry from the span starts alone (every thread, no shared memory): the scene loads are issued
+    // BEFORE the weights are tabulated, so their latency overlaps that phase
+    const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
+    const int cx0 = aa_span_lo(ox0, sx), cy0 = aa_span_lo(oy0, sy);
+    const int cw = min(min(aa_span_lo(ox0 + last_x, sx) + 3, iw) - cx0, PITCH);
+    const int ch = min(min(aa_span_lo(oy0 + last_y, sy) + 3, ih) - cy0, ROWS);
+    const int IN = ih * iw;
+    const float* sc = scenes + (size_t)b * 3 * IN + cx0;
+    // a warp takes tile rows wid, wid+8, ..., its lanes the columns lane, lane+32, ...: all loads in flight at once
+    const int lane = tid & 31, wid = tid >> 5;
+    float sv[NRU][NCU][3];
+#pragma unroll
+    for (int ru = 0; ru < NRU; ++ru) {
+        const int r = wid + 8 * ru;
+        const float* srow = sc + (cy0 + min(r, ch - 1)) * iw;
+#pragma unroll
+        for (int u = 0; u < NCU; ++u) {
+            const int c = 32 * u + lane;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sv[ru][u][k] = (r < ch && c < cw) ? __ldg(srow + k * IN + c) : 0.f;
+        }
+    }
     if (tid < PA_TW) {
         const AaSpan3 s = aa_span3(min(ox0 + tid, ow - 1), iw, sx);
         x_lo[tid] = s.lo;
@@ -355,59 +385,41 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
 #pragma unroll
         for (int j = 0; j < 3; ++j) y_w[k][j] = s.w[j];
     }
-    __syncthreads();
-    const int cx0 = x_lo[0], cy0 = y_lo[0];
-    const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
-    const int cw = min(min(x_lo[last_x] + 3, iw) - cx0, PITCH);
-    const int ch = min(min(y_lo[last_y] + 3, ih) - cy0, ROWS);
-    const int IN = ih * iw;
-    const float* sc = scenes + (size_t)b * 3 * IN + cx0;
     bool tile_hits = true;
     int bx0 = 0, by0 = 0, bx1 = iw - 1, by1 = ih - 1;
     if (bbox) {
         bx0 = __ldg(bbox + b * 4); by0 = __ldg(bbox + b * 4 + 1); bx1 = __ldg(bbox + b * 4 + 2); by1 = __ldg(bbox + b * 4 + 3);
         tile_hits = !(cx0 > bx1 || cx0 + cw - 1 < bx0 || cy0 > by1 || cy0 + ch - 1 < by0);
     }
-    // a warp takes a tile row, its lanes the columns; a tile narrower than 3 columns is zero-filled up to 3 so
-    // that the fixed-count loops below never read uninitialised shared memory
-    const int lane = tid & 31, wid = tid >> 5;
+    // a tile narrower than 3 columns is zero-filled up to 3 so that the fixed-count loops below never read
+    // uninitialised shared memory
     const int cwz = max(cw, 3);
     if (!tile_hits) {
-        for (int r = wid; r < ch; r += PA_THREADS / 32) {
-            const float* srow = sc + (cy0 + r) * iw;
+#pragma unroll
+        for (int ru = 0; ru < NRU; ++ru) {
+            const int r = wid + 8 * ru;
+            if (r >= ch) continue;
             float* crow = comp + r * PITCH;
-            float sv[(PITCH + 31) / 32][3];
 #pragma unroll
-            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
-                const int c = 32 * u + lane;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sv[u][k] = c < cw ? __ldg(srow + k * IN + c) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+            for (int u = 0; u < NCU; ++u) {
                 const int c = 32 * u + lane;
                 if (c < cwz) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) crow[k * PLANE + c] = sv[u][k];
+                    for (int k = 0; k < 3; ++k) crow[k * PLANE + c] = sv[ru][u][k];
                 }
             }
         }
     } else {
         const Homography hm = load_homography(coeffs, b, iw, ih);
         const int PN = ph * pw;
-        for (int r = wid; r < ch; r += PA_THREADS / 32) {
+#pragma unroll
+        for (int ru = 0; ru < NRU; ++ru) {
+            const int r = wid + 8 * ru;
+            if (r >= ch) continue;
             const int cy = cy0 + r;
-            const float* srow = sc + cy * iw;
             float* crow = comp + r * PITCH;
-            float sv[(PITCH + 31) / 32][3];
 #pragma unroll
-            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
-                const int c = 32 * u + lane;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sv[u][k] = c < cw ? __ldg(srow + k * IN + c) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < (PITCH + 31) / 32; ++u) {
+            for (int u = 0; u < NCU; ++u) {
                 const int c = 32 * u + lane;
                 if (c >= cwz) continue;
                 const int cx = cx0 + c;
@@ -424,9 +436,9 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
                     }
                 }
                 const float om = sub_rn(1.0f, m);
-                crow[c] = add_rn(mul_rn(sv[u][0], om), mul_rn(o0, m));
-                crow[PLANE + c] = add_rn(mul_rn(sv[u][1], om), mul_rn(o1, m));
-                crow[2 * PLANE + c] = add_rn(mul_rn(sv[u][2], om), mul_rn(o2, m));
+                crow[c] = add_rn(mul_rn(sv[ru][u][0], om), mul_rn(o0, m));
+                crow[PLANE + c] = add_rn(mul_rn(sv[ru][u][1], om), mul_rn(o1, m));
+                crow[2 * PLANE + c] = add_rn(mul_rn(sv[ru][u][2], om), mul_rn(o2, m));
                 crow[3 * PLANE + c] = m;
             }
         }
@@ -550,11 +562,31 @@ patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__
     const size_t ON = (size_t)oh * ow;
     const float* g = gadv + (size_t)b * 3 * ON;
     float gc[3] = {0.f, 0.f, 0.f};
+    // the column weights do not depend on the row: evaluate them once (the candidate window holds at most
+    // 2*support/scale + 4 <= 8 outputs for scale factors in [1, 3))
+    constexpr int MAXO = 8;
+    float wxv[MAXO];
+#pragma unroll
+    for (int i = 0; i < MAXO; ++i) wxv[i] = (ox_a + i <= ox_b) ? aa_weight_of(ox_a + i, iw, sx, cx) : 0.f;
     for (int oy = oy_a; oy <= oy_b; ++oy) {
         const float wy = aa_weight_of(oy, ih, sy, cy);
         if (wy == 0.f) continue;
-        for (int ox = ox_a; ox <= ox_b; ++ox) {
-            const float w = wy * aa_weight_of(ox, iw, sx, cx);
+        const float* grow = g + (size_t)oy * ow + ox_a;
+#pragma unroll
+        for (int i = 0; i < MAXO; ++i) {
+            const float w = wy * wxv[i];
+            if (w == 0.f) continue;
+            gc[0] = fmaf(w, __ldg(grow + i), gc[0]);
+            gc[1] = fmaf(w, __ldg(grow + ON + i), gc[1]);
+            gc[2] = fmaf(w, __ldg(grow + 2 * ON + i), gc[2]);
+        }
+    }
+    // windows wider than MAXO (up-scaling by more than ~1.3x): the remaining columns, weight by weight
+    for (int ox = ox_a + MAXO; ox <= ox_b; ++ox) {
+        const float wx = aa_weight_of(ox, iw, sx, cx);
+        if (wx == 0.f) continue;
+        for (int oy = oy_a; oy <= oy_b; ++oy) {
+            const float w = aa_weight_of(oy, ih, sy, cy) * wx;
             if (w == 0.f) continue;
             const size_t oo = (size_t)oy * ow + ox;
             gc[0] = fmaf(w, __ldg(g + oo), gc[0]);
