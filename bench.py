@@ -452,11 +452,11 @@ def main():
             s1.g.scenes = scenes_f32
 
     # DRAM traffic and instruction count of the dominant kernel per launch: from the committed `ncu --set full`
-    # capture of this same command (profiles/r01_ncu_full_q.txt; mean of the 4 per-scale launches at B=32)
-    ncu_traffic = 380.3e6 if (B == 32 and F == 1) else None
-    ncu_warp_inst = 313.3e6 if (B == 32 and F == 1) else None
+    # capture of this same command (profiles/r01_ncu_full_u.txt; mean of the 4 per-scale launches at B=32)
+    ncu_traffic = 418.2e6 if (B == 32 and F == 1) else None
+    ncu_warp_inst = 257.5e6 if (B == 32 and F == 1) else None
     sm_clock_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-    roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA> (dmh_photo_scale, one launch per scale)",
+    roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA,FASTDIV,PACKED,UP> (dmh_photo_scale, one launch per scale)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "traffic": ncu_traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
