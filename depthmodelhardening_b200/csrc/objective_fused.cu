@@ -361,6 +361,105 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ grow, int X
     }
 }
 
+// Integer factors 2 / 4 / 8 with a TALL tile: 32 x (64/R) low-res pixels per CTA, i.e. ~66-72 full-res rows of
+// 32*R columns (16-64 KB of gradient per CTA, 9 row loads per thread in flight in batches) -- the 32 x 8 tile of
+// the general kernel below spends its time in per-CTA latency (weights, two barriers) for 2-3 loads per thread.
+template <int R>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ grow, int X, int W, float v[R]);
+
+template <int R>
+__global__ void __launch_bounds__(256)
+disp_grad_up_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
+                    const float* __restrict__ img_scalars, float smooth_weight, const float* __restrict__ g_total,
+                    const float* __restrict__ g_scale, const float* __restrict__ g_smooth, float inv_S, int h, int w,
+                    int H, int W, float sh, float sw, float* __restrict__ grad) {
+    constexpr int RW = 2 * R, LR = 64 / R, NR = R * LR + R, NPW = (NR + 7) / 8, BS = R >= 8 ? 3 : (R >= 4 ? 5 : NPW);
+    __shared__ float s_wy[LR][RW], s_wx[32][RW];
+    __shared__ float s_h[NR][32];
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    const int x = blockIdx.x * 32 + lane;
+    const int b = blockIdx.z;
+    const float* g = G_full + (size_t)b * H * W;
+    const int t = wid * 32 + lane;
+    // weights depend only on (y, offset) / (x, offset): tabulated once per CTA with the forward's up_tap
+    for (int i = t; i < LR * RW + 32 * RW; i += 256) {
+        if (i < LR * RW) {
+            const int ly = i / RW, j = i % RW;
+            const int yy = blockIdx.y * LR + ly, Y = R * yy - R / 2 + j;
+            float wv = 0.f;
+            if (yy < h && Y >= 0 && Y < H) { const UpTap tp = up_tap(Y, sh, h); wv = (tp.i0 == yy ? tp.l0 : 0.f) + (tp.i1 == yy ? tp.l1 : 0.f); }
+            s_wy[ly][j] = wv;
+        } else {
+            const int k = i - LR * RW;
+            const int lx = k / RW, j = k % RW;
+            const int xx = blockIdx.x * 32 + lx, X = R * xx - R / 2 + j;
+            float wv = 0.f;
+            if (xx < w && X >= 0 && X < W) { const UpTap tp = up_tap(X, sw, w); wv = (tp.i0 == xx ? tp.l0 : 0.f) + (tp.i1 == xx ? tp.l1 : 0.f); }
+            s_wx[lx][j] = wv;
+        }
+    }
+    __syncthreads();
+    float wA[R], wB[R], wE[R];                              // chunk c -> low-res c, chunk c -> low-res c-1, chunk 32 -> 31
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        wA[j] = s_wx[lane][j];
+        wB[j] = lane > 0 ? s_wx[lane - 1][R + j] : 0.f;
+        wE[j] = s_wx[31][R + j];
+    }
+    const int Xc = R * x - R / 2;                            // first full-res column of this lane's chunk
+    const int Xe = R * (blockIdx.x * 32 + 32) - R / 2;      // chunk 32 (lane 0 takes it)
+    const int Yt = R * (blockIdx.y * LR) - R / 2;           // first full-res row of the tile's window
+#pragma unroll
+    for (int i0 = 0; i0 < NPW; i0 += BS) {
+        float v[BS][R], ve[BS][R];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            const int ry = wid + 8 * (i0 + i), Y = Yt + ry;
+            const bool ok = i0 + i < NPW && ry < NR && Y >= 0 && Y < H;          // warp-uniform
+            const float* grow = g + (size_t)(ok ? Y : 0) * W;
+            if (ok) load_chunk<R>(grow, Xc, W, v[i]);
+            else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[i][j] = 0.f;
+            }
+            if (ok && lane == 0) load_chunk<R>(grow, Xe, W, ve[i]);
+            else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) ve[i][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            const int ry = wid + 8 * (i0 + i);
+            float a = 0.f, bm = 0.f, e = 0.f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                a = fmaf(wA[j], v[i][j], a); bm = fmaf(wB[j], v[i][j], bm); e = fmaf(wE[j], ve[i][j], e);
+            }
+            float nb = __shfl_down_sync(0xffffffffu, bm, 1);
+            const float ee = __shfl_sync(0xffffffffu, e, 0);
+            if (lane == 31) nb = ee;
+            if (i0 + i < NPW && ry < NR) s_h[ry][lane] = a + nb;
+        }
+    }
+    __syncthreads();
+    if (x >= w) return;
+    const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
+    float inv_m = 0.f, corr = 0.f;
+    if (gN) { inv_m = img_scalars[b * 2]; corr = img_scalars[b * 2 + 1]; }
+#pragma unroll
+    for (int m = 0; m < LR / 8; ++m) {
+        const int ly = wid + 8 * m, y = blockIdx.y * LR + ly;
+        if (y >= h) continue;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < RW; ++j) acc = fmaf(s_wy[ly][j], s_h[R * ly + j][lane], acc);
+        const size_t o = (size_t)b * h * w + (size_t)y * w + x;
+        const float sm = gN ? smooth_weight * (gN[o] * inv_m - corr) : 0.0f;
+        grad[o] = g_smooth ? fmaf(g_smooth[0], sm, up * acc) : up * (acc + sm);
+    }
+}
+
 // Same-size case (scale 0) of dmh_disp_grad: pure elementwise, 4 pixels per thread (128-bit loads / stores).
 __global__ void __launch_bounds__(256)
 disp_grad_same_kernel(const float4* __restrict__ G4, const float4* __restrict__ gN4, const float* __restrict__ img_scalars,
@@ -585,9 +684,15 @@ int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars
             reinterpret_cast<const float4*>(G_full), reinterpret_cast<const float4*>(gN), img_scalars, smooth_weight,
             g_total, g_scale, g_smooth, inv_S, n4, reinterpret_cast<float4*>(grad_disp));
     } else if (R == 1) DMH_DG(1);
-    else if (R == 2) DMH_DG(2);
-    else if (R == 4) DMH_DG(4);
-    else if (R == 8) DMH_DG(8);
+    else if (R == 2 || R == 4 || R == 8) {
+        const dim3 gtall(ceil_div(w, 32), ceil_div(h, 64 / R), B);
+#define DMH_DGU(RR) DMH_LAUNCH(disp_grad_up_kernel<RR>, gtall, block, 0, st)(G_full, gN, img_scalars, smooth_weight, g_total, \
+                                                                           g_scale, g_smooth, inv_S, h, w, H, W, sh, sw, grad_disp)
+        if (R == 2) DMH_DGU(2);
+        else if (R == 4) DMH_DGU(4);
+        else DMH_DGU(8);
+#undef DMH_DGU
+    }
     else DMH_DG(0);
 #undef DMH_DG
     DMH_CHECK_LAUNCH("dmh_disp_grad");
