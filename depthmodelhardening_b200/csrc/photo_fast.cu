@@ -213,9 +213,12 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     __shared__ __align__(8) uint64_t tgt_bar;
     float* tgt = smem;                       // [3][36][40] (TMA destination: 128-byte aligned)
     float* pred = tgt + 3 * FT_NT;           // [3][N2]
-    float2* coefP = reinterpret_cast<float2*>(pred + 3 * FT_N2);   // [3][N1] float2: (a,b,c) of channels (0,1), gated
-    float* coefS = reinterpret_cast<float*>(coefP + 3 * FT_N1);    // [3][N1]: (a,b,c) of channel 2
-    float* cams = coefS + 3 * FT_N1;         // [24]
+    // gated SSIM coefficients of a ring pixel, laid out for 128-bit accesses: Q1 = (a0, a1, b0, b1),
+    // Q2 = (c0, c1, a2, b2), Q3 = c2  (a, b, c of channels 0, 1, 2)
+    float4* coefQ1 = reinterpret_cast<float4*>(pred + 3 * FT_N2);  // [N1]
+    float4* coefQ2 = coefQ1 + FT_N1;                                // [N1]
+    float* coefQ3 = reinterpret_cast<float*>(coefQ2 + FT_N1);       // [N1]
+    float* cams = coefQ3 + FT_N1;            // [24]
     float* red = cams + 24;                  // [32]
     uint8_t* gate = reinterpret_cast<uint8_t*>(red + 32);   // [N1]
 
@@ -430,8 +433,9 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 ssim_coef_gated_t(stS, rS, nrS, gw * passS, kaS, kbS, kcS);
                 if (qr < FT_R1) {
                     const int qi = qr * FT_R1 + bc;
-                    coefP[0 * FT_N1 + qi] = kaP; coefP[1 * FT_N1 + qi] = kbP; coefP[2 * FT_N1 + qi] = kcP;
-                    coefS[0 * FT_N1 + qi] = kaS; coefS[1 * FT_N1 + qi] = kbS; coefS[2 * FT_N1 + qi] = kcS;
+                    coefQ1[qi] = make_float4(kaP.x, kaP.y, kbP.x, kbP.y);
+                    coefQ2[qi] = make_float4(kcP.x, kcP.y, kaS, kbS);
+                    coefQ3[qi] = kcS;
                     gate[qi] = win ? 1 : 0;
                 }
                 if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
@@ -452,22 +456,26 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
         const float wr = (px == W - 2) ? 2.0f : 1.0f;
         const float2 wl2 = make_float2(wl, wl), wr2 = make_float2(wr, wr);
-        float2 hprevP[2][3];
-        float hprevS[2][3];
+        // packed quantities: 0 = (a0,a1), 1 = (b0,b1), 2 = (c0,c1), 3 = (a2,b2); scalar: c2
+        float2 hprev[2][4];
+        float hprevC[2];
         float* gout = p.grad_disp + (size_t)b * N + px;
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r1 = 4 * os + rr;                      // ring row
-            float2 hcP[3];
-            float hcS[3];
-            const float2* baseP = coefP + r1 * FT_R1 + oc;
-            const float* baseS = coefS + r1 * FT_R1 + oc;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float2* q = baseP + j * FT_N1;
-                hcP[j] = vfma(wl2, q[0], vfma(wr2, q[2], q[1]));
-                const float* qs = baseS + j * FT_N1;
-                hcS[j] = fmaf(wl, qs[0], fmaf(wr, qs[2], qs[1]));
+            float2 hc[4];
+            float hcC;
+            {
+                const float4* q1 = coefQ1 + r1 * FT_R1 + oc;
+                const float4* q2 = coefQ2 + r1 * FT_R1 + oc;
+                const float* q3 = coefQ3 + r1 * FT_R1 + oc;
+                const float4 l1 = q1[0], m1 = q1[1], e1 = q1[2];
+                const float4 l2 = q2[0], m2 = q2[1], e2 = q2[2];
+                hc[0] = vfma(wl2, make_float2(l1.x, l1.y), vfma(wr2, make_float2(e1.x, e1.y), make_float2(m1.x, m1.y)));
+                hc[1] = vfma(wl2, make_float2(l1.z, l1.w), vfma(wr2, make_float2(e1.z, e1.w), make_float2(m1.z, m1.w)));
+                hc[2] = vfma(wl2, make_float2(l2.x, l2.y), vfma(wr2, make_float2(e2.x, e2.y), make_float2(m2.x, m2.y)));
+                hc[3] = vfma(wl2, make_float2(l2.z, l2.w), vfma(wr2, make_float2(e2.z, e2.w), make_float2(m2.z, m2.w)));
+                hcC = fmaf(wl, q3[0], fmaf(wr, q3[2], q3[1]));
             }
             if (rr >= 2) {
                 const int k = rr - 2;
@@ -479,12 +487,11 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 const int i2 = (r + 2) * FT_R2 + oc + 2;
                 const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
                 const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
-                const float2 saP = vfma(wu2, hprevP[0][0], vfma(wd2, hcP[0], hprevP[1][0]));
-                const float2 sbP = vfma(wu2, hprevP[0][1], vfma(wd2, hcP[1], hprevP[1][1]));
-                const float2 scP = vfma(wu2, hprevP[0][2], vfma(wd2, hcP[2], hprevP[1][2]));
-                const float saS = fmaf(wu, hprevS[0][0], fmaf(wd, hcS[0], hprevS[1][0]));
-                const float sbS = fmaf(wu, hprevS[0][1], fmaf(wd, hcS[1], hprevS[1][1]));
-                const float scS = fmaf(wu, hprevS[0][2], fmaf(wd, hcS[2], hprevS[1][2]));
+                const float2 saP = vfma(wu2, hprev[0][0], vfma(wd2, hc[0], hprev[1][0]));
+                const float2 sbP = vfma(wu2, hprev[0][1], vfma(wd2, hc[1], hprev[1][1]));
+                const float2 scP = vfma(wu2, hprev[0][2], vfma(wd2, hc[2], hprev[1][2]));
+                const float2 sab2 = vfma(wu2, hprev[0][3], vfma(wd2, hc[3], hprev[1][3]));
+                const float scS = fmaf(wu, hprevC[0], fmaf(wd, hcC, hprevC[1]));
                 const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
                 const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
                 const float2 dP = vsub(xvP, yvP);
@@ -493,17 +500,15 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                                                dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
                 const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
                 const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
-                const float gpS = fmaf(sbS, xvS, fmaf(scS, yvS, saS)) + sgS;
+                const float gpS = fmaf(sab2.y, xvS, fmaf(scS, yvS, sab2.x)) + sgS;
                 float g = gpP.x * D[k][0];
                 g = fmaf(gpP.y, D[k][1], g);
                 g = fmaf(gpS, D[k][2], g);
                 if (py < H && px < W) gout[py * W] = g;
             }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                hprevP[0][j] = hprevP[1][j]; hprevP[1][j] = hcP[j];
-                hprevS[0][j] = hprevS[1][j]; hprevS[1][j] = hcS[j];
-            }
+            for (int j = 0; j < 4; ++j) { hprev[0][j] = hprev[1][j]; hprev[1][j] = hc[j]; }
+            hprevC[0] = hprevC[1]; hprevC[1] = hcC;
         }
     }
     const float s = block_sum(loss_local, red);
