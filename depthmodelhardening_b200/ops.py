@@ -403,6 +403,17 @@ def photo_scale_sum(disp_full, target, srcs: Sequence[torch.Tensor], Ts: Sequenc
 # ----------------------------------------------------------------------------- whole multi-scale objective
 import ctypes as _C
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One high-priority side stream per device (created once)."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
+    return st
+
 
 class _Objective(torch.autograd.Function):
     """generate_images_pred + compute_losses (photometric part) for ALL scales as one
@@ -446,6 +457,21 @@ class _Objective(torch.autograd.Function):
         G, gN, wss, parts, gPs, sels = [], [], [], [], [], []
         T_arr = ptr_array(Ts)
         inv_den = 1.0 / float(B * H * W)
+        # the smoothness term (memory-bound, 8 small launches) is independent of the photometric kernels
+        # (issue-bound): it runs on a side stream and fills their idle issue / memory slots; joined before `finish`
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        for s in range(S):
+            d = disps[s]
+            h, w = d.shape[2], d.shape[3]
+            wss.append(torch.empty(lib.dmh_smooth_fused_workspace_floats(B, h, w), device=dev, dtype=torch.float32))
+            gN.append(torch.empty(B, 1, h, w, device=dev, dtype=torch.float32))
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for s in range(S):
+                d = disps[s]
+                check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]), ptr(gN[s]),
+                                           stream()), "smooth_fused")
         for s in range(S):
             d = disps[s]
             h, w = d.shape[2], d.shape[3]
@@ -457,10 +483,8 @@ class _Objective(torch.autograd.Function):
                 check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik), ptr(ident),
                                           ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den, ptr(part),
                                           ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
-            ws = torch.empty(lib.dmh_smooth_fused_workspace_floats(B, h, w), device=dev, dtype=torch.float32)
-            gn = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
-            check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, h, w, ptr(ws), ptr(gn), stream()), "smooth_fused")
-            G.append(g_full); gN.append(gn); wss.append(ws); parts.append(part); gPs.append(gP); sels.append(sel)
+            G.append(g_full); parts.append(part); gPs.append(gP); sels.append(sel)
+        cur.wait_stream(side)
         img_scalars = torch.empty(S, B, 2, device=dev, dtype=torch.float32)
         losses = torch.empty(S + 1, device=dev, dtype=torch.float32)
         hs = (_C.c_int * S)(*[d.shape[2] for d in disps])
