@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--no-patch", action="store_true", help="skip stage 1 (debug)")
     ap.add_argument("--attack", default="l0", choices=["l0", "linf"],
                     help="stage-1 update rule: l0 = README config (--norm_type l_0), linf = sign/project step")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
     return ap.parse_args()
 
 
@@ -247,7 +247,7 @@ def OQ_P2():
     return CALIB_P2
 
 
-def run_cpu_baseline(sample_batch, with_patch, reps=2, attack="l0"):
+def run_cpu_baseline(sample_batch, with_patch, reps=8, attack="l0"):
     step = cpu_reference_step(sample_batch, with_patch, attack=attack)
     step()
     t0 = time.perf_counter()
@@ -268,7 +268,7 @@ def reference_arm(args, rank, world):
     step = cpu_reference_step(sb, with_patch, attack=args.attack)
     for _ in range(min(args.warmup, 1)):
         step()
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 12))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -452,9 +452,9 @@ def main():
             s1.g.scenes = scenes_f32
 
     # DRAM traffic and instruction count of the dominant kernel per launch: from the committed `ncu --set full`
-    # capture of this same command (profiles/r01_ncu_full_u.txt; mean of the 4 per-scale launches at B=32)
-    ncu_traffic = 418.2e6 if (B == 32 and F == 1) else None
-    ncu_warp_inst = 257.5e6 if (B == 32 and F == 1) else None
+    # capture of this same command (profiles/r01_ncu_full_x.txt; mean of the 4 per-scale launches at B=32)
+    ncu_traffic = 419.1e6 if (B == 32 and F == 1) else None
+    ncu_warp_inst = 244.4e6 if (B == 32 and F == 1) else None
     sm_clock_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA,FASTDIV,PACKED,UP> (dmh_photo_scale, one launch per scale)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
