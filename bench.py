@@ -300,6 +300,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     from depthmodelhardening_b200 import _lib
     lib = _lib.load()
@@ -339,8 +341,16 @@ def main():
     for _ in range(3):
         s2.step()
     torch.cuda.synchronize()
-    kt = [a.elapsed_time(b) for (name, a, b) in ops.KERNEL_EVENTS if name == "photo_scale"]
+    ev = [(a, b) for (name, a, b) in ops.KERNEL_EVENTS if name == "photo_scale"]
     ops.KERNEL_EVENTS = None
+    # the per-scale launches of a step alternate between two streams and overlap at their tails: the time of one
+    # launch is the span of the step's group (first start -> last end) divided by the launches in it
+    S_ = len(SCALES)
+    kt = []
+    for i in range(0, len(ev) - S_ + 1, S_):
+        grp = ev[i:i + S_]
+        span = max(grp[0][0].elapsed_time(b) for (_, b) in grp) - min(grp[0][0].elapsed_time(a) for (a, _) in grp)
+        kt += [span / S_] * S_
     kms = sum(kt) / max(len(kt), 1)
     F = len(FRAME_IDS) - 1
     k_bytes = (12 + 12 * F + 4 + 4 * F + 4 * F + 4) * B * H * W

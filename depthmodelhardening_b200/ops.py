@@ -406,12 +406,13 @@ import ctypes as _C
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    """One high-priority side stream per device (created once)."""
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+def _side_stream(dev, which=0):
+    """Side streams of a device, created once: 0 = high priority (smoothness launches), 1 = normal priority."""
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, which)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx, priority=-1 if which == 0 else 0)
     return st
 
 
@@ -472,6 +473,10 @@ class _Objective(torch.autograd.Function):
                 d = disps[s]
                 check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]), ptr(gN[s]),
                                            stream()), "smooth_fused")
+        # the per-scale launches are independent of each other: odd scales go to a second stream so that the
+        # tail of one launch (10240 CTAs = 23.06 waves of 444) overlaps the head of the next
+        alt = _side_stream(dev, 1)
+        alt.wait_stream(cur)
         for s in range(S):
             d = disps[s]
             h, w = d.shape[2], d.shape[3]
@@ -479,11 +484,13 @@ class _Objective(torch.autograd.Function):
             g_full = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
             gP = torch.empty(n_src, B, tiles, 12, device=dev, dtype=torch.float32) if need_T else None
             sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None
-            with _timed("photo_scale"):
-                check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik), ptr(ident),
-                                          ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den, ptr(part),
-                                          ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
+            with torch.cuda.stream(alt if (s & 1) else cur):
+                with _timed("photo_scale"):
+                    check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik),
+                                              ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den,
+                                              ptr(part), ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
             G.append(g_full); parts.append(part); gPs.append(gP); sels.append(sel)
+        cur.wait_stream(alt)
         cur.wait_stream(side)
         img_scalars = torch.empty(S, B, 2, device=dev, dtype=torch.float32)
         losses = torch.empty(S + 1, device=dev, dtype=torch.float32)
@@ -518,16 +525,22 @@ class _Objective(torch.autograd.Function):
             gt = torch.zeros(1, device=G[0].device)
         base = 3 + S + n_src
         grads_disp = []
+        # four independent, short launches: alternate two streams so that their tails overlap
+        dev = G[0].device
+        cur, alt = torch.cuda.current_stream(dev), _side_stream(dev, 1)
+        alt.wait_stream(cur)
         for s in range(S):
             if not ctx.needs_input_grad[base + n_src + s]:
                 grads_disp.append(None)
                 continue
             _, _, h, w = dshapes[s]
-            gd = torch.empty(B, 1, h, w, device=G[s].device, dtype=torch.float32)
-            check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
-                                    ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
-                                    ptr(gd), stream()), "disp_grad")
+            gd = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
+            with torch.cuda.stream(alt if (s & 1) else cur):
+                check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
+                                        ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
+                                        ptr(gd), stream()), "disp_grad")
             grads_disp.append(gd.view(dshapes[s]))
+        cur.wait_stream(alt)
         g_T = [None] * n_src
         if need_T:
             u = [(gt[0] / S if gt is not None else 0.0) + (gs[s] if gs is not None else 0.0) for s in range(S)]
