@@ -92,7 +92,7 @@ def test_fused_patch_apply_vs_oracle(dev, batch):
     assert_close_arb(gp2, obj.grad, o64.grad, TOL, "grad patch (fast path)")
 
 
-@pytest.mark.parametrize("size", [(321, 1030), (200, 650), (375, 1242), (160, 512)])
+@pytest.mark.parametrize("size", [(321, 1030), (200, 650), (375, 1242), (160, 512), (270, 900)])
 def test_fused_patch_apply_ragged_output_sizes(dev, size):
     """Output sizes that are not multiples of the 64 x 16 tile, both tap-count instantiations of the resize
     (scale < 1.5: 3 taps per axis; larger down-scales: generic 8) and the identity resize: forward and the
