@@ -299,9 +299,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner at
+    # communicator creation, ...) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     from depthmodelhardening_b200 import _lib
     lib = _lib.load()
@@ -503,10 +506,12 @@ def main():
         line["e2e_bf16_frames"] = e2e_bf16
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None, attack=args.attack)
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
 
 
 if __name__ == "__main__":
