@@ -190,14 +190,14 @@ __device__ __forceinline__ float up_sample(const float* __restrict__ dp, int dw,
 
 // One pixel of the warp: depth -> exact coordinate chain -> taps (+ the two backward factors when wanted)
 template <bool FASTDIV>
-__device__ __forceinline__ Tap pixel_tap(const Camera& cam, const FastParams& p, bool is_depth, int ix, int iy, float dv,
+__device__ __forceinline__ Tap pixel_tap(const Camera& cam, const FastParams& p, int ix, int iy, float dv,
                                          bool want_grad, float& gax, float& gay) {
-    const float depth = is_depth ? dv : disp_to_depth(dv, p.ds);
+    const float depth = disp_to_depth(dv, p.ds);
     const WarpCoord wc = warp_coord<FASTDIV>(cam, (float)ix, (float)iy, depth, p.W, p.H, 1e-7f, p.rcw, p.rch);
     if (want_grad) {
         float ax, ay;
         warp_chain_factors(cam, wc, p.W, p.H, ax, ay);
-        const float dd = (is_depth ? 1.0f : ddepth_ddisp(depth, p.ds)) * p.grad_scale;
+        const float dd = ddepth_ddisp(depth, p.ds) * p.grad_scale;
         gax = ax * dd; gay = ay * dd;
     }
     return make_tap(wc, p.H, p.W);
@@ -205,7 +205,8 @@ __device__ __forceinline__ Tap pixel_tap(const Camera& cam, const FastParams& p,
 
 // TMA: target tile by cp.async.bulk.tensor; FASTDIV: verified 3-instruction division by W-1 / H-1;
 // PK: pixel-packed source (128-bit taps); UP: the disparity map is smaller than the frame (scales 1..3).
-// SSIM is always on here (no_ssim takes the general kernel).
+// SSIM is always on and the input is a disparity here (no_ssim, depth inputs and the materialised warped images
+// take the general kernel).
 template <bool TMA, bool FASTDIV, bool PK, bool UP>
 __global__ void __launch_bounds__(FT_THREADS, 3)
 photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map) {
@@ -227,7 +228,6 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
     const int N = H * W;                      // per-item offsets fit 32 bits (checked by the launcher)
-    const bool is_depth = (p.flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
     const float w_ssim = 0.85f / 3.0f, w_l1 = 0.15f / 3.0f;
 
     if (tid < 12) {
@@ -296,7 +296,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         Tap tp[5];
         float gax[5], gay[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) tp[k] = pixel_tap<FASTDIV>(cam, p, is_depth, pxx[k], py[k], dv[k], k < 4, gax[k], gay[k]);
+        for (int k = 0; k < 5; ++k) tp[k] = pixel_tap<FASTDIV>(cam, p, pxx[k], py[k], dv[k], k < 4, gax[k], gay[k]);
         // gathers: the taps of TWO pixels are requested before either is consumed
 #pragma unroll
         for (int k0 = 0; k0 < 5; k0 += 2) {
@@ -317,11 +317,6 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
                 if (k < 4) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) D[k][ch] = g.dix[ch] * gax[k] + g.diy[ch] * gay[k];
-                    if (p.warped && y0 + r < H && x0 + oc < W) {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch)
-                            p.warped[((size_t)b * 3 + ch) * N + (y0 + r) * W + x0 + oc] = g.v[ch];
-                    }
                 }
             }
         }
@@ -334,7 +329,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         const float dvh = UP ? up_sample(dp, p.disp.w, up_tap(iy, p.disp.sh, p.disp.h), up_tap(ix, p.disp.sw, p.disp.w))
                              : __ldg(dp + iy * W + ix);
         float u0, u1;
-        const Tap th = pixel_tap<FASTDIV>(cam, p, is_depth, ix, iy, dvh, false, u0, u1);
+        const Tap th = pixel_tap<FASTDIV>(cam, p, ix, iy, dvh, false, u0, u1);
         float tvh[3][4];
         load_taps<PK>(sp, N, W, th, tvh);
         const Gathered g = combine_taps(tvh, th, false);

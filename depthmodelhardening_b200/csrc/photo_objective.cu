@@ -554,11 +554,15 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
     DMH_REQUIRE(disp_h >= 1 && disp_w >= 1 && disp_h <= H && disp_w <= W, "dmh_photo_scale: bad disparity size %dx%d", disp_h, disp_w);
     const bool is_depth = (flags & DMH_PHOTO_INPUT_IS_DEPTH) != 0;
     DMH_REQUIRE(is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_photo_scale: bad depth range");
-    DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED) || (F == 1 && !grad_P_partial && H * (long long)W < (1ll << 28) &&
-                                                    !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM)) &&
-                                                    (uintptr_t)src_host[0] % 16 == 0),
-                "dmh_photo_scale: DMH_PHOTO_SRC_PACKED needs F == 1, SSIM on, no pose gradient and a 16-byte aligned source");
-    if (F == 1 && !grad_P_partial && !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM)) && H * (long long)W < (1ll << 28)) {
+    DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED) || (uintptr_t)src_host[0] % 16 == 0,
+                "dmh_photo_scale: DMH_PHOTO_SRC_PACKED needs a 16-byte aligned source");
+    const bool fast_ok = F == 1 && !grad_P_partial && !(warped_host && warped_host[0]) &&
+                         !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM | DMH_PHOTO_INPUT_IS_DEPTH)) &&
+                         H * (long long)W < (1ll << 28);
+    DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED) || fast_ok,
+                "dmh_photo_scale: DMH_PHOTO_SRC_PACKED needs the single-source fast path (F == 1, SSIM on, disparity "
+                "input, no pose gradient, no warped output)");
+    if (fast_ok) {
         // single source frame, no pose gradient: the 32x32-tile fast kernel (photo_fast.cu).  It writes
         // fewer partial sums than dmh_photo_tiles() promises; zero the tail so the caller's reduction is exact.
         DMH_REQUIRE(src_host[0] && T_host[0], "dmh_photo_scale: null src/T for frame 0");

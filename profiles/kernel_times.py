@@ -28,6 +28,8 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    for name, fn in (("stage 1 (patch step)", s1.step), ("stage 2 (objective fwd+bwd)", s2.step), ("step", step)):
+        print("%9.1f us  %s, CUDA events over 20 iterations" % (1e3 * bench.timed_loop(fn, 20, 3, 1), name))
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         for _ in range(a.steps):
             step()
