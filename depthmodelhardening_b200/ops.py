@@ -402,8 +402,14 @@ def photo_scale_sum(disp_full, target, srcs: Sequence[torch.Tensor], Ts: Sequenc
 
 # ----------------------------------------------------------------------------- whole multi-scale objective
 import ctypes as _C
+import os as _os
 
 _SIDE_STREAMS = {}
+# single-source objective: the one fused kernel per scale (default) or the two-kernel form -- warp kernel without
+# halo + TMA-fed loss kernel, bit-identical results.  Measured on B200 at config 2 (profiles/r01_ncu_split.txt):
+# 142 + 261 us per scale against 369-393 us fused (the halo recomputation the split saves is paid back in
+# stores / loads of the warped frame and a loss kernel that starts on a cold TMA wait), so the default stays fused.
+SPLIT_PATH = _os.environ.get("DMH_SPLIT", "0") == "1"
 
 
 def _side_stream(dev, which=0):
@@ -454,6 +460,7 @@ class _Objective(torch.autograd.Function):
         elif automask:
             check(lib.dmh_identity_loss(ptr(target), src_arr, n_src, B, H, W, no_ssim, ptr(ident), stream()),
                   "identity_loss")
+        split = packed and SPLIT_PATH and W % 4 == 0 and W >= 8 and H >= 8 and target.data_ptr() % 16 == 0
         tiles = lib.dmh_photo_tiles(H, W)
         G, gN, wss, parts, gPs, sels = [], [], [], [], [], []
         T_arr = ptr_array(Ts)
@@ -486,9 +493,20 @@ class _Objective(torch.autograd.Function):
             sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None
             with torch.cuda.stream(alt if (s & 1) else cur):
                 with _timed("photo_scale"):
-                    check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik),
-                                              ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den,
-                                              ptr(part), ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
+                    if split:
+                        # warp kernel (every pixel gathered once) + TMA-fed loss kernel; same bits as the fused kernel
+                        ws_split = torch.empty(lib.dmh_photo_split_workspace_floats(B, H, W), device=dev,
+                                               dtype=torch.float32)
+                        check(lib.dmh_photo_scale_split(ptr(target), ptr(src_pk), ptr(Ts[0]), ptr(d), h, w, ptr(k), ptr(ik),
+                                                        ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth, flags,
+                                                        inv_den, ptr(ws_split), ptr(part), ptr(g_full), ptr(sel), stream()),
+                                  "photo_scale_split")
+                        if s & 1:
+                            ws_split.record_stream(alt)
+                    else:
+                        check(lib.dmh_photo_scale(ptr(target), src_arr, T_arr, n_src, ptr(d), h, w, ptr(k), ptr(ik),
+                                                  ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth, flags, inv_den,
+                                                  ptr(part), ptr(g_full), ptr(gP), ptr(sel), None, stream()), "photo_scale")
             G.append(g_full); parts.append(part); gPs.append(gP); sels.append(sel)
         cur.wait_stream(alt)
         cur.wait_stream(side)

@@ -167,6 +167,18 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
                     float* loss_partial, float* grad_disp, float* grad_P_partial, uint8_t* sel,
                     float* const* warped_host, dmh_stream_t stream);
 
+/* Split form of the single-source fast path of dmh_photo_scale (F == 1, SSIM on, disparity input, no pose gradient):
+ * kernel 1 warps the source frame once per pixel (no halo recomputation) into `workspace` -- the warped frame with a
+ * 2-pixel reflect border plus the collapsed backward factors d(pred)/d(disp) -- kernel 2 stages the target and the
+ * warped tile through shared memory by TMA and does SSIM + L1, the automask decision and the backward.  Results are
+ * bit-identical to dmh_photo_scale.  workspace: dmh_photo_split_workspace_floats(B,H,W) floats, 16-byte aligned.
+ * Needs W % 4 == 0, 16-byte aligned frames, W, H >= 8.  flags: DMH_PHOTO_SRC_PACKED allowed (src = packed copy).  */
+long long dmh_photo_split_workspace_floats(int B, int H, int W);
+int dmh_photo_scale_split(const float* target, const float* src, const float* T, const float* disp, int disp_h, int disp_w,
+                          const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W,
+                          float min_depth, float max_depth, int flags, float grad_scale, float* workspace,
+                          float* loss_partial, float* grad_disp, uint8_t* sel, dmh_stream_t stream);
+
 /* Depth-hints variant of dmh_photo_scale (A18; DepthNetworks/depth-hints/trainer.py:476-525, 541-590, 629-727),
  * one scale: same fused warp + SSIM/L1 + backward, but the per-pixel decision is the depth-hints one -- min (or
  * mean) over the source frames first, ONE tie-break noise plane noise (B,1,H,W) added to the identity minimum,

@@ -454,3 +454,45 @@ def test_packed_source_gather_is_bit_identical(dev, hw, dhw):
     for a, b_ in zip(outs[0], outs[1]):
         assert torch.equal(a, b_)
     assert float(outs[0][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("hw,dhw", [((64, 96), (64, 96)), ((40, 72), (40, 72)), ((96, 160), (24, 40)), ((72, 200), (36, 100))])
+def test_split_path_is_bit_identical_to_fused(dev, hw, dhw):
+    """dmh_photo_scale_split (warp kernel without halo + TMA-fed loss kernel) against the fused single-source kernel:
+    loss partial sums, disparity gradient and argmin must agree bit for bit, incl. ragged tiles and up-sampled
+    disparities (W % 4 == 0: the split path needs TMA)."""
+    from depthmodelhardening_b200 import _lib, ops
+    from depthmodelhardening_b200._lib import check, ptr, ptr_array, stream
+    H, W = hw
+    h, w = dhw
+    B = 2
+    pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, "s"), scales=(0,), seed=73).to(dev)
+    lib = _lib.load()
+    target, src = pb.color[(0, 0)].contiguous(), pb.color[("s", 0)].contiguous()
+    gen = torch.Generator().manual_seed(6)
+    disp = (0.05 + 0.4 * torch.rand(B, 1, h, w, generator=gen)).to(dev)
+    ident = torch.empty(B, 1, H, W, device=dev)
+    pk = torch.empty(B, H, W, 4, device=dev)
+    check(lib.dmh_identity_loss_pack(ptr(target), ptr(src), B, H, W, 0, ptr(ident), ptr(pk), stream()))
+    tiles = lib.dmh_photo_tiles(H, W)
+    K, iK, T = pb.K.contiguous(), pb.inv_K.contiguous(), pb.T["s"].contiguous()
+    nz = pb.noise[0][:, :1].contiguous()
+    outs = []
+    for split in (False, True):
+        part = torch.zeros(B * tiles, device=dev)
+        g = torch.empty(B, 1, H, W, device=dev)
+        sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+        if split:
+            ws = torch.full((lib.dmh_photo_split_workspace_floats(B, H, W),), float("nan"), device=dev)
+            check(lib.dmh_photo_scale_split(ptr(target), ptr(pk), ptr(T), ptr(disp), h, w, ptr(K), ptr(iK), ptr(ident),
+                                            ptr(nz), B, H, W, 0.1, 100.0, ops.FLAG_SRC_PACKED, 1.0, ptr(ws), ptr(part),
+                                            ptr(g), ptr(sel), stream()), "photo_scale_split")
+        else:
+            check(lib.dmh_photo_scale(ptr(target), ptr_array([pk]), ptr_array([T]), 1, ptr(disp), h, w, ptr(K), ptr(iK),
+                                      ptr(ident), ptr(nz), B, H, W, 0.1, 100.0, ops.FLAG_SRC_PACKED, 1.0, ptr(part), ptr(g),
+                                      None, ptr(sel), None, stream()), "photo_scale")
+        outs.append((part, g, sel))
+    torch.cuda.synchronize()
+    for a, b_ in zip(outs[0], outs[1]):
+        assert torch.isfinite(b_.float()).all()
+        assert torch.equal(a, b_)
