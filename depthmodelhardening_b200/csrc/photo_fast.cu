@@ -16,9 +16,19 @@
 //   * the 3x3 box sums of the 9 coefficient planes are separable sliding
 //     windows too; reflection multiplicities are folded into the edge weights.
 //
-// Shared memory: tgt 3x36x36 + pred 3x36x36 + coef 9x34x34 floats + gate bytes
-// = 73.9 KB -> 3 CTAs / SM.   Roofline: HBM by traffic (40 B per target pixel),
-// but issue-bound in practice (see profiles/): ~900 instr / pixel.
+//   * the source is gathered from a pixel-packed (B,H,W,4) copy written once per step by the identity-loss
+//     kernel below: one 128-bit load per bilinear tap, the north-west tap clamped so that the other three sit
+//     at fixed offsets (bit-identical to the planar gather);
+//   * SSIM in sum form (no divisions by 9), branch-free, channels (0,1) in packed fp32 (explicitly rounded
+//     add/mul/fma.rn.f32x2), coefficient planes laid out for 128-bit shared-memory accesses.
+//
+// Shared memory: tgt 3x36x40 + pred 3x36x36 + coef 9x34x34 floats + gate bytes = 75.8 KB -> 3 CTAs / SM.
+// Roofline: HBM by traffic (40 B per target pixel, 419 MB per launch at B=32 -- ncu measures exactly that), but
+// instruction-issue bound in practice: ~745 lane-instructions / pixel at ~57 % issue utilisation (profiles/).
+//
+// Also here: ident_fast_kernel (identity reprojection loss + the packed copy, both tiles by TMA) and the
+// two-kernel alternative warp_pred_kernel + photo_fast_kernel<SPLIT> (dmh_photo_scale_split: bit-identical,
+// measured slower, opt-in).
 //
 // Target tile staging: ONE elected thread issues a 4-D TMA load
 // (cp.async.bulk.tensor, box 40 x 36 x 3 x 1 at (x0-4, y0-2, 0, b) -- the innermost
