@@ -142,6 +142,46 @@ class Phy_obj_atk(Attack):
         return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
 
 
+class Phy_obj_atk_vanila(Attack):
+    r"""Drop-in of the reference's `Phy_obj_atk_vanila` (torchattacks/attacks/phy_obj_atk_vanila.py:18-96): no
+    optimisation -- a given object image is placed on the scenes at random (or, with `eval`, fixed first) distance /
+    yaw, next to the benign object, with the resized placement masks.  Same signature, return 4-tuple and
+    `random.sample` order as the reference; one fused patch-apply launch per branch instead of 2*Ba perspective
+    warps, a composite and two Resizes each."""
+
+    def __init__(self, model, obj_img, obj_mask, dist_range=list(range(5, 31, 2))):
+        super().__init__("PGD", model)
+        self.obj_img = obj_img
+        self.obj_mask = obj_mask
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        self.eps_for_division = 1e-10
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+
+    def forward(self, images, obj_img, batch_size, cfg_path=None, eval=False):
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        self.obj_img = obj_img                      # (phy_trans_ben keeps the object it was constructed with)
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        obj_img_adv = self.obj_img.clone().detach()
+        self.phy_trans_adv.reset_img(obj_img_adv, self.obj_mask)
+        z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+        alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+        if eval:
+            z0_sample[0] = 7
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            co = self.phy_trans_adv._coeffs(z0_sample, alpha_sample)
+            adv_scenes, obj_masks_out = patch_ops.apply_patch(obj_img_adv, self.obj_mask, scene_imgs, co, self.scene_size)
+            ben_scenes, _ = patch_ops.apply_patch(self.phy_trans_ben.obj_img, self.obj_mask, scene_imgs, co,
+                                                  self.scene_size)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
+
+
 class Phy_obj_atk_l0(Attack):
     r"""Distance measure: L_0.  See reference phy_obj_atk_l0.py:16-41."""
 

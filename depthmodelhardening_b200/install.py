@@ -79,8 +79,9 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
     if dataset_root is not None:
         _attacks.object_dataset_root = dataset_root
     for mod_name, cls in (("torchattacks.attacks.phy_obj_atk", "Phy_obj_atk"),
-                          ("torchattacks.attacks.phy_obj_atk_l0", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk"),
-                          ("torchattacks", "Phy_obj_atk_l0")):
+                          ("torchattacks.attacks.phy_obj_atk_l0", "Phy_obj_atk_l0"),
+                          ("torchattacks.attacks.phy_obj_atk_vanila", "Phy_obj_atk_vanila"), ("torchattacks", "Phy_obj_atk"),
+                          ("torchattacks", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk_vanila")):
         mod = sys.modules.get(mod_name)
         if mod is not None and hasattr(mod, cls):
             setattr(mod, cls, getattr(_attacks, cls))

@@ -328,3 +328,30 @@ def test_batch_arena_roundtrip(dev):
     for k, v in arena.device_views(1).items():
         assert v.is_cuda and torch.equal(v.cpu(), ex[k])
         assert v.data_ptr() % 256 == 0
+
+
+@pytest.mark.parametrize("ev", [False, True])
+def test_vanila_attack_class_vs_reference_golden(dev, calib, ev):
+    """Drop-in `Phy_obj_atk_vanila` (next-4: the placement-only attack of the evaluation harness) against the
+    unmodified reference class run on the CPU (oracle/make_golden_vanila.py): same `random.sample` order -> same
+    placements; adversarial / benign scenes and resized masks to fp32 tolerance."""
+    import os
+    from depthmodelhardening_b200 import attacks
+    g = load_golden("attack_vanila")
+    tag = "eval" if ev else "rand"
+    attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
+    pbt = synth.patch_batch(batch=3, seed=0).to(dev)
+    other = synth.rand((1, 3, synth.PATCH_H, synth.PATCH_W), 77).to(dev)
+    random.seed(11)
+    atk = attacks.Phy_obj_atk_vanila(_tiny(dev), pbt.obj.clone(), pbt.mask.clone(), dist_range=list(range(5, 10, 2)))
+    adv_s, ben_s, m_out, obj_adv = atk(pbt.scenes.clone(), other.clone(), 3, eval=ev)
+    assert adv_s.shape == (3, 3, 320, 1024) and ben_s.shape == adv_s.shape and m_out.shape == (3, 1, 320, 1024)
+    assert torch.equal(obj_adv, other)
+    assert_close(m_out.double().sum(), g[tag + "_mask_sum"], 1e-6)
+    assert_close(adv_s.double().sum(), g[tag + "_adv_sum"], 1e-6)
+    assert_close(ben_s.double().sum(), g[tag + "_ben_sum"], 1e-6)
+    assert_close(adv_s[:, :, 90:200:2, 380:640:2], g[tag + "_adv_crop"], TOL, "adv crop")
+    assert_close(ben_s[:, :, 90:200:2, 380:640:2], g[tag + "_ben_crop"], TOL, "ben crop")
+    assert_close(m_out[:, :, 90:200:2, 380:640:2], g[tag + "_mask_crop"], TOL, "mask crop")
+    with pytest.raises(RuntimeError, match="Batch size"):
+        atk(pbt.scenes[:2].clone(), other.clone(), 3)
