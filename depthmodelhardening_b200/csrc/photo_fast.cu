@@ -219,6 +219,192 @@ __device__ __forceinline__ Tap pixel_tap(const Camera& cam, const FastParams& p,
     return make_tap(wc, p.H, p.W);
 }
 
+// ---- phase B of the tile kernels: SSIM statistics by sliding windows down a ring column; decision; gated
+// coefficients.  Channels 0 and 1 ride in the two halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2), channel 2
+// is scalar.  Straight-line: rows past the tile are clamped (their results are discarded by the predicated stores),
+// out-of-image ring pixels are gated through the NaN identity marker.  `tid` < 256: index among the 256 threads that
+// run the phase (threads >= 238 idle); returns this thread's share of the tile's loss sum.
+struct TileSmem {
+    float* tgt;      // [3][36][40]
+    float* pred;     // [3][36][36]
+    float4* q1;      // [N1] (a0, a1, b0, b1)
+    float4* q2;      // [N1] (c0, c1, a2, b2)
+    float* q3;       // [N1] c2
+    uint8_t* gate;   // [N1]
+};
+
+__device__ __forceinline__ void prefetch_ident(const FastParams& p, int tid, int b, int x0, int y0,
+                                               float (&idv_pre)[FT_ROWS]) {
+    const int H = p.H, W = p.W, N = H * W;
+    const int bc = tid % FT_R1, bstrip = tid / FT_R1;
+    const bool has_ident = p.ident != nullptr;
+    const int qx = x0 - 1 + bc;
+    const bool col_ok = qx >= 0 && qx < W && tid < FT_R1 * FT_STRIPS;
+    const float* idp = p.ident + (size_t)b * N + qx;
+    const float* nzp = p.noise + (size_t)b * N + qx;
+#pragma unroll
+    for (int k = 0; k < FT_ROWS; ++k) {
+        const int qr = bstrip * FT_ROWS + k, qy = y0 - 1 + qr;
+        const bool ok = col_ok && qr < FT_R1 && qy >= 0 && qy < H;
+        float v = ok ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);     // +inf: always loses to rp
+        if (ok && has_ident) {
+            v = __ldg(idp + qy * W);
+            if (p.noise) v = add_rn(v, __ldg(nzp + qy * W));
+        }
+        idv_pre[k] = v;
+    }
+}
+
+__device__ __forceinline__ float phase_b(const FastParams& p, const TileSmem& sm, int tid, int b, int x0, int y0,
+                                         const float (&idv_pre)[FT_ROWS]) {
+    const int W = p.W, N = p.H * p.W;
+    const float w_ssim = 0.85f / 3.0f;
+    const int bc = tid % FT_R1, bstrip = tid / FT_R1;
+    const bool has_ident = p.ident != nullptr;
+    const float* tgt = sm.tgt;
+    const float* pred = sm.pred;
+    float4* coefQ1 = sm.q1;
+    float4* coefQ2 = sm.q2;
+    float* coefQ3 = sm.q3;
+    uint8_t* gate = sm.gate;
+    float loss_local = 0.0f;
+    if (tid < FT_R1 * FT_STRIPS) {
+        const int r0 = bstrip * FT_ROWS;                // first ring row of this strip == first R2 row of its window
+        const bool col_in = bc >= 1 && bc <= FT_T;
+        Row5T<float2> histP[2];                         // channels (0,1): [older, newer] row sums
+        Row5T<float> histS[2];                          // channel 2
+        float2 cenxP, cenyP;                            // centre values of the previous row
+        float cenxS, cenyS;
+#pragma unroll
+        for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
+            const int r2 = min(r0 + rr, FT_R2 - 1);     // R2 row being added
+            const float* xs = pred + r2 * FT_R2 + bc;
+            const float* ys = tgt + r2 * FT_TP + bc + FT_TO;
+            const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
+                         xc = make_float2(xs[2], xs[FT_N2 + 2]);
+            const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
+                         yc = make_float2(ys[2], ys[FT_NT + 2]);
+            const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
+            const float* x2 = xs + 2 * FT_N2;
+            const float* y2 = ys + 2 * FT_NT;
+            const float x2m = x2[1], y2m = y2[1];
+            const Row5T<float> curS = row5(x2[0], x2m, x2[2], y2[0], y2m, y2[2]);
+            if (rr >= 2) {
+                const int qr = r0 + rr - 2;             // ring row of the window centre
+                float l1 = fabsf(cenyP.x - cenxP.x);
+                l1 += fabsf(cenyP.y - cenxP.y);
+                l1 += fabsf(cenyS - cenxS);
+                const SsimStatsT<float2> stP = ssim_stats_rows_t(histP[0], histP[1], curP);
+                const SsimStatsT<float> stS = ssim_stats_rows_t(histS[0], histS[1], curS);
+                float2 passP, rP, nrP;
+                const float2 vP = ssim_value_t(stP, passP, rP, nrP);
+                float passS, rS, nrS;
+                const float vS = ssim_value_t(stS, passS, rS, nrS);
+                const float ss = (vP.x + vP.y) + vS;
+                l1 *= (1.0f / 3.0f);
+                const float rp = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                const float idv = idv_pre[rr - 2];
+                const bool win = rp < idv;              // torch.min: first minimum wins, identity is first
+                const float gw = win ? w_ssim : 0.0f;
+                float2 kaP, kbP, kcP;
+                ssim_coef_gated_t(stP, rP, nrP, vmul(make_float2(gw, gw), passP), kaP, kbP, kcP);
+                float kaS, kbS, kcS;
+                ssim_coef_gated_t(stS, rS, nrS, gw * passS, kaS, kbS, kcS);
+                if (qr < FT_R1) {
+                    const int qi = qr * FT_R1 + bc;
+                    coefQ1[qi] = make_float4(kaP.x, kaP.y, kbP.x, kbP.y);
+                    coefQ2[qi] = make_float4(kcP.x, kcP.y, kaS, kbS);
+                    coefQ3[qi] = kcS;
+                    gate[qi] = win ? 1 : 0;
+                }
+                if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
+                    loss_local += win ? rp : idv;
+                    if (p.sel) p.sel[(size_t)b * N + (y0 - 1 + qr) * W + x0 - 1 + bc] = (uint8_t)((win && has_ident) ? 1 : 0);
+                }
+            }
+            histP[0] = histP[1]; histP[1] = curP;
+            histS[0] = histS[1]; histS[1] = curS;
+            cenxP = xb; cenyP = yb; cenxS = x2m; cenyS = y2m;
+        }
+    }
+    return loss_local;
+}
+
+// ---- phase C of the tile kernels: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp).
+// `tid` < 256 owns column tid%32, rows 4*(tid/32)+k of the tile; D = d(pred_ch)/d(disp) of those 4 pixels.
+__device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm, int tid, int b, int x0, int y0,
+                                        const float (&D)[4][3]) {
+    const int H = p.H, W = p.W, N = H * W;
+    const float w_l1 = 0.15f / 3.0f;
+    const int oc = tid & 31, os = tid >> 5;
+    const float* tgt = sm.tgt;
+    const float* pred = sm.pred;
+    const float4* coefQ1 = sm.q1;
+    const float4* coefQ2 = sm.q2;
+    const float* coefQ3 = sm.q3;
+    const uint8_t* gate = sm.gate;
+    {
+        const int px = x0 + oc;
+        const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
+        const float wr = (px == W - 2) ? 2.0f : 1.0f;
+        const float2 wl2 = make_float2(wl, wl), wr2 = make_float2(wr, wr);
+        // packed quantities: 0 = (a0,a1), 1 = (b0,b1), 2 = (c0,c1), 3 = (a2,b2); scalar: c2
+        float2 hprev[2][4];
+        float hprevC[2];
+        float* gout = p.grad_disp + (size_t)b * N + px;
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r1 = 4 * os + rr;                      // ring row
+            float2 hc[4];
+            float hcC;
+            {
+                const float4* q1 = coefQ1 + r1 * FT_R1 + oc;
+                const float4* q2 = coefQ2 + r1 * FT_R1 + oc;
+                const float* q3 = coefQ3 + r1 * FT_R1 + oc;
+                const float4 l1 = q1[0], m1 = q1[1], e1 = q1[2];
+                const float4 l2 = q2[0], m2 = q2[1], e2 = q2[2];
+                hc[0] = vfma(wl2, make_float2(l1.x, l1.y), vfma(wr2, make_float2(e1.x, e1.y), make_float2(m1.x, m1.y)));
+                hc[1] = vfma(wl2, make_float2(l1.z, l1.w), vfma(wr2, make_float2(e1.z, e1.w), make_float2(m1.z, m1.w)));
+                hc[2] = vfma(wl2, make_float2(l2.x, l2.y), vfma(wr2, make_float2(e2.x, e2.y), make_float2(m2.x, m2.y)));
+                hc[3] = vfma(wl2, make_float2(l2.z, l2.w), vfma(wr2, make_float2(e2.z, e2.w), make_float2(m2.z, m2.w)));
+                hcC = fmaf(wl, q3[0], fmaf(wr, q3[2], q3[1]));
+            }
+            if (rr >= 2) {
+                const int k = rr - 2;
+                const int r = 4 * os + k;
+                const int py = y0 + r;
+                const float wu = (py == 1) ? 2.0f : 1.0f;
+                const float wd = (py == H - 2) ? 2.0f : 1.0f;
+                const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
+                const int i2 = (r + 2) * FT_R2 + oc + 2;
+                const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
+                const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
+                const float2 saP = vfma(wu2, hprev[0][0], vfma(wd2, hc[0], hprev[1][0]));
+                const float2 sbP = vfma(wu2, hprev[0][1], vfma(wd2, hc[1], hprev[1][1]));
+                const float2 scP = vfma(wu2, hprev[0][2], vfma(wd2, hc[2], hprev[1][2]));
+                const float2 sab2 = vfma(wu2, hprev[0][3], vfma(wd2, hc[3], hprev[1][3]));
+                const float scS = fmaf(wu, hprevC[0], fmaf(wd, hcC, hprevC[1]));
+                const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
+                const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
+                const float2 dP = vsub(xvP, yvP);
+                const float dS = xvS - yvS;
+                const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
+                                               dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
+                const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
+                const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
+                const float gpS = fmaf(sab2.y, xvS, fmaf(scS, yvS, sab2.x)) + sgS;
+                float g = gpP.x * D[k][0];
+                g = fmaf(gpP.y, D[k][1], g);
+                g = fmaf(gpS, D[k][2], g);
+                if (py < H && px < W) gout[py * W] = g;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hprev[0][j] = hprev[1][j]; hprev[1][j] = hc[j]; }
+            hprevC[0] = hprevC[1]; hprevC[1] = hcC;
+        }
+    }
+}
+
 // TMA: target tile by cp.async.bulk.tensor; FASTDIV: verified 3-instruction division by W-1 / H-1;
 // PK: pixel-packed source (128-bit taps); UP: the disparity map is smaller than the frame (scales 1..3).
 // SSIM is always on and the input is a disparity here (no_ssim, depth inputs and the materialised warped images
@@ -363,26 +549,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     // identity losses (+ tie-break noise) of this thread's phase-B pixels: requested before the barrier so
     // that their latency overlaps the other warps' gather.  Ring pixels outside the image are marked by a NaN
     // (rp < NaN is false: they never win, their coefficients are gated to 0 and they add nothing to the loss).
-    const int bc = tid % FT_R1, bstrip = tid / FT_R1;
-    const bool has_ident = p.ident != nullptr;
     float idv_pre[FT_ROWS];
-    {
-        const int qx = x0 - 1 + bc;
-        const bool col_ok = qx >= 0 && qx < W && tid < FT_R1 * FT_STRIPS;
-        const float* idp = p.ident + (size_t)b * N + qx;
-        const float* nzp = p.noise + (size_t)b * N + qx;
-#pragma unroll
-        for (int k = 0; k < FT_ROWS; ++k) {
-            const int qr = bstrip * FT_ROWS + k, qy = y0 - 1 + qr;
-            const bool ok = col_ok && qr < FT_R1 && qy >= 0 && qy < H;
-            float v = ok ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);     // +inf: always loses to rp
-            if (ok && has_ident) {
-                v = __ldg(idp + qy * W);
-                if (p.noise) v = add_rn(v, __ldg(nzp + qy * W));
-            }
-            idv_pre[k] = v;
-        }
-    }
+    prefetch_ident(p, tid, b, x0, y0, idv_pre);
     __syncthreads();
     if (TMA) {
         mbar_wait(&tgt_bar, 0);
@@ -403,73 +571,10 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
         }
     }
 
-    // ---- phase B: SSIM statistics by sliding windows down a ring column; decision; gated coefficients.
-    // Channels 0 and 1 ride in the two halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2), channel 2 is
-    // scalar.  Straight-line: rows past the tile are clamped (their results are discarded by the predicated
-    // stores), out-of-image ring pixels are gated through the NaN identity marker.
-    float loss_local = 0.0f;
-    if (tid < FT_R1 * FT_STRIPS) {
-        const int r0 = bstrip * FT_ROWS;                // first ring row of this strip == first R2 row of its window
-        const bool col_in = bc >= 1 && bc <= FT_T;
-        Row5T<float2> histP[2];                         // channels (0,1): [older, newer] row sums
-        Row5T<float> histS[2];                          // channel 2
-        float2 cenxP, cenyP;                            // centre values of the previous row
-        float cenxS, cenyS;
-#pragma unroll
-        for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
-            const int r2 = min(r0 + rr, FT_R2 - 1);     // R2 row being added
-            const float* xs = pred + r2 * FT_R2 + bc;
-            const float* ys = tgt + r2 * FT_TP + bc + FT_TO;
-            const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
-                         xc = make_float2(xs[2], xs[FT_N2 + 2]);
-            const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
-                         yc = make_float2(ys[2], ys[FT_NT + 2]);
-            const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
-            const float* x2 = xs + 2 * FT_N2;
-            const float* y2 = ys + 2 * FT_NT;
-            const float x2m = x2[1], y2m = y2[1];
-            const Row5T<float> curS = row5(x2[0], x2m, x2[2], y2[0], y2m, y2[2]);
-            if (rr >= 2) {
-                const int qr = r0 + rr - 2;             // ring row of the window centre
-                float l1 = fabsf(cenyP.x - cenxP.x);
-                l1 += fabsf(cenyP.y - cenxP.y);
-                l1 += fabsf(cenyS - cenxS);
-                const SsimStatsT<float2> stP = ssim_stats_rows_t(histP[0], histP[1], curP);
-                const SsimStatsT<float> stS = ssim_stats_rows_t(histS[0], histS[1], curS);
-                float2 passP, rP, nrP;
-                const float2 vP = ssim_value_t(stP, passP, rP, nrP);
-                float passS, rS, nrS;
-                const float vS = ssim_value_t(stS, passS, rS, nrS);
-                const float ss = (vP.x + vP.y) + vS;
-                l1 *= (1.0f / 3.0f);
-                const float rp = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
-                const float idv = idv_pre[rr - 2];
-                const bool win = rp < idv;              // torch.min: first minimum wins, identity is first
-                const float gw = win ? w_ssim : 0.0f;
-                float2 kaP, kbP, kcP;
-                ssim_coef_gated_t(stP, rP, nrP, vmul(make_float2(gw, gw), passP), kaP, kbP, kcP);
-                float kaS, kbS, kcS;
-                ssim_coef_gated_t(stS, rS, nrS, gw * passS, kaS, kbS, kcS);
-                if (qr < FT_R1) {
-                    const int qi = qr * FT_R1 + bc;
-                    coefQ1[qi] = make_float4(kaP.x, kaP.y, kbP.x, kbP.y);
-                    coefQ2[qi] = make_float4(kcP.x, kcP.y, kaS, kbS);
-                    coefQ3[qi] = kcS;
-                    gate[qi] = win ? 1 : 0;
-                }
-                if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
-                    loss_local += win ? rp : idv;
-                    if (p.sel) p.sel[(size_t)b * N + (y0 - 1 + qr) * W + x0 - 1 + bc] = (uint8_t)((win && has_ident) ? 1 : 0);
-                }
-            }
-            histP[0] = histP[1]; histP[1] = curP;
-            histS[0] = histS[1]; histS[1] = curS;
-            cenxP = xb; cenyP = yb; cenxS = x2m; cenyS = y2m;
-        }
-    }
+    TileSmem sm;
+    sm.tgt = tgt; sm.pred = pred; sm.q1 = coefQ1; sm.q2 = coefQ2; sm.q3 = coefQ3; sm.gate = gate;
+    const float loss_local = phase_b(p, sm, tid, b, x0, y0, idv_pre);
     __syncthreads();
-
-    // ---- phase C: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp)
     if (SPLIT) {
         // d(pred)/d(disp) factors of this thread's 4 pixels, written by warp_pred_kernel (loaded here, not before
         // phase B: 12 registers less across the SSIM phase)
@@ -482,66 +587,7 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
             for (int ch = 0; ch < 3; ++ch) D[k][ch] = in ? __ldg(dg + ch * N + y * W) : 0.0f;
         }
     }
-    {
-        const int px = x0 + oc;
-        const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
-        const float wr = (px == W - 2) ? 2.0f : 1.0f;
-        const float2 wl2 = make_float2(wl, wl), wr2 = make_float2(wr, wr);
-        // packed quantities: 0 = (a0,a1), 1 = (b0,b1), 2 = (c0,c1), 3 = (a2,b2); scalar: c2
-        float2 hprev[2][4];
-        float hprevC[2];
-        float* gout = p.grad_disp + (size_t)b * N + px;
-#pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-            const int r1 = 4 * os + rr;                      // ring row
-            float2 hc[4];
-            float hcC;
-            {
-                const float4* q1 = coefQ1 + r1 * FT_R1 + oc;
-                const float4* q2 = coefQ2 + r1 * FT_R1 + oc;
-                const float* q3 = coefQ3 + r1 * FT_R1 + oc;
-                const float4 l1 = q1[0], m1 = q1[1], e1 = q1[2];
-                const float4 l2 = q2[0], m2 = q2[1], e2 = q2[2];
-                hc[0] = vfma(wl2, make_float2(l1.x, l1.y), vfma(wr2, make_float2(e1.x, e1.y), make_float2(m1.x, m1.y)));
-                hc[1] = vfma(wl2, make_float2(l1.z, l1.w), vfma(wr2, make_float2(e1.z, e1.w), make_float2(m1.z, m1.w)));
-                hc[2] = vfma(wl2, make_float2(l2.x, l2.y), vfma(wr2, make_float2(e2.x, e2.y), make_float2(m2.x, m2.y)));
-                hc[3] = vfma(wl2, make_float2(l2.z, l2.w), vfma(wr2, make_float2(e2.z, e2.w), make_float2(m2.z, m2.w)));
-                hcC = fmaf(wl, q3[0], fmaf(wr, q3[2], q3[1]));
-            }
-            if (rr >= 2) {
-                const int k = rr - 2;
-                const int r = 4 * os + k;
-                const int py = y0 + r;
-                const float wu = (py == 1) ? 2.0f : 1.0f;
-                const float wd = (py == H - 2) ? 2.0f : 1.0f;
-                const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
-                const int i2 = (r + 2) * FT_R2 + oc + 2;
-                const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
-                const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
-                const float2 saP = vfma(wu2, hprev[0][0], vfma(wd2, hc[0], hprev[1][0]));
-                const float2 sbP = vfma(wu2, hprev[0][1], vfma(wd2, hc[1], hprev[1][1]));
-                const float2 scP = vfma(wu2, hprev[0][2], vfma(wd2, hc[2], hprev[1][2]));
-                const float2 sab2 = vfma(wu2, hprev[0][3], vfma(wd2, hc[3], hprev[1][3]));
-                const float scS = fmaf(wu, hprevC[0], fmaf(wd, hcC, hprevC[1]));
-                const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
-                const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
-                const float2 dP = vsub(xvP, yvP);
-                const float dS = xvS - yvS;
-                const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
-                                               dP.y > 0.f ? gl1 : (dP.y < 0.f ? -gl1 : 0.f));
-                const float sgS = dS > 0.f ? gl1 : (dS < 0.f ? -gl1 : 0.f);
-                const float2 gpP = vadd(vfma(sbP, xvP, vfma(scP, yvP, saP)), sgP);
-                const float gpS = fmaf(sab2.y, xvS, fmaf(scS, yvS, sab2.x)) + sgS;
-                float g = gpP.x * D[k][0];
-                g = fmaf(gpP.y, D[k][1], g);
-                g = fmaf(gpS, D[k][2], g);
-                if (py < H && px < W) gout[py * W] = g;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { hprev[0][j] = hprev[1][j]; hprev[1][j] = hc[j]; }
-            hprevC[0] = hprevC[1]; hprevC[1] = hcC;
-        }
-    }
+    phase_c(p, sm, tid, b, x0, y0, D);
     const float s = block_sum(loss_local, red);
     if (tid == 0) p.loss_partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
 }
