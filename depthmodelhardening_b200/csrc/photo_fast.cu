@@ -594,6 +594,220 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
 
 
 // ---------------------------------------------------------------------------
+// Producer / consumer form: a persistent CTA of 12 warps walks over the tiles.  Warps 8-11 (producers) gather the
+// warped tile of tile i+1 into the second shared-memory buffer and start its target TMA while warps 0-7 (consumers)
+// run phases B and C of tile i: neither the gather latency nor the phase barriers of one tile leave the SM's issue
+// slots idle.  Hand-off through mbarriers (full[s]: 128 producer arrivals + the TMA bytes; empty[s]: 256 consumer
+// arrivals); consumers synchronise among themselves with named barrier 1, producers with named barrier 2.  The
+// backward factors D travel through global memory (written by the producer, read back through L2 by the consumer
+// that owns the pixel in phase C).  2 CTAs per SM (108.6 KB each).  Same arithmetic, same bits as the fused kernel.
+#define PC_CONS 256
+#ifndef PC_PROD
+#define PC_PROD 256
+#endif
+#define PC_THREADS (PC_CONS + PC_PROD)
+#define PC_CTAS (PC_PROD == 128 ? 2 : 1)
+#define PC_HALVES (1024 / (PC_PROD * 4))          // groups of 4 rows per producer thread
+#define PC_NH ((272 + PC_PROD - 1) / PC_PROD)      // halo pixels per producer thread (the last one partial)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <bool FASTDIV, bool PK, bool UP>
+__global__ void __launch_bounds__(PC_THREADS, PC_CTAS)
+photo_pc_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map, int tiles_x, int tiles_y, int ntiles) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
+    // buffers s = 0, 1: target tiles at smem + s * 3*FT_NT (TMA destinations, 128-byte aligned), warped tiles after
+    float4* q1 = reinterpret_cast<float4*>(smem + 6 * FT_NT + 6 * FT_N2);
+    float4* q2 = q1 + FT_N1;
+    float* q3 = reinterpret_cast<float*>(q2 + FT_N1);
+    float* cams = q3 + FT_N1;                 // [2][24]
+    float* red = cams + 48;                   // [32]
+    uint8_t* gate = reinterpret_cast<uint8_t*>(red + 32);
+
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W, N = H * W;
+    if (tid == 0) {
+        mbar_init(&full_bar[0], PC_PROD + 1); mbar_init(&full_bar[1], PC_PROD + 1);
+        mbar_init(&empty_bar[0], PC_CONS); mbar_init(&empty_bar[1], PC_CONS);
+    }
+    __syncthreads();
+    const int per_img = tiles_x * tiles_y;
+
+    if (tid >= PC_CONS) {
+        // ================================================================ producers
+        const int pt = tid - PC_CONS;
+        const int pc_ = pt & 31, pw = pt >> 5;                       // column, row group of the interior
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            const int b = t / per_img, rem = t - b * per_img;
+            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int x0 = tx * FT_T, y0 = ty * FT_T;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (pt == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full_bar[s], 3 * FT_NT * sizeof(float));
+                tma_load_4d(smem + s * 3 * FT_NT, &tgt_map, &full_bar[s], x0 - 2 - FT_TO, y0 - 2, 0, b);
+            }
+            float* cm = cams + 24 * s;
+            if (pt < 12) {
+                const int i = pt / 4, j = pt % 4;
+                const float* k = p.K + b * 16 + i * 4;
+                const float* tt = p.T + b * 16 + j;
+                float acc = __ldg(k) * __ldg(tt);
+                acc = fmaf(__ldg(k + 1), __ldg(tt + 4), acc);
+                acc = fmaf(__ldg(k + 2), __ldg(tt + 8), acc);
+                acc = fmaf(__ldg(k + 3), __ldg(tt + 12), acc);
+                cm[pt] = acc;
+            } else if (pt < 21) {
+                const int i = (pt - 12) / 3, j = (pt - 12) % 3;
+                cm[pt] = __ldg(p.inv_K + b * 16 + i * 4 + j);
+            }
+            named_bar(2, PC_PROD);
+            Camera cam;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) cam.P[i] = cm[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) cam.iK[i] = cm[12 + i];
+            const float* sp = p.src + (size_t)b * (PK ? 4 : 3) * N;
+            const float* dp = p.disp.ptr + (size_t)b * (p.disp.h * p.disp.w);
+            float* pred = smem + 6 * FT_NT + s * 3 * FT_N2;
+            float* dout = p.dfac_out + (size_t)b * 3 * N;
+            // ---- interior: column pc_, rows 8*pw .. 8*pw+7, four at a time (column taps shared)
+            const int ixo = tile_to_img(x0 + pc_, W);
+#pragma unroll 1
+            for (int half = 0; half < PC_HALVES; ++half) {
+                const int rb = 4 * PC_HALVES * pw + 4 * half;
+                int py[4];
+                float dv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) py[k] = tile_to_img(y0 + rb + k, H);
+                if (!UP) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dv[k] = __ldg(dp + py[k] * W + ixo);
+                } else {
+                    const UpTap txo = up_tap(ixo, p.disp.sw, p.disp.w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dv[k] = up_sample(dp, p.disp.w, up_tap(py[k], p.disp.sh, p.disp.h), txo);
+                }
+                Tap tp[4];
+                float gax[4], gay[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tp[k] = pixel_tap<FASTDIV>(cam, p, ixo, py[k], dv[k], true, gax[k], gay[k]);
+#pragma unroll
+                for (int k0 = 0; k0 < 4; k0 += 2) {
+                    float tv[2][3][4];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) load_taps<PK>(sp, N, W, tp[k0 + j], tv[j]);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int k = k0 + j, r = rb + k;
+                        const Gathered g = combine_taps(tv[j], tp[k], true);
+                        const int i2 = (r + 2) * FT_R2 + pc_ + 2;
+                        const bool in = y0 + r < H && x0 + pc_ < W;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            pred[ch * FT_N2 + i2] = g.v[ch];
+                            if (in) dout[ch * N + (y0 + r) * W + x0 + pc_] = g.dix[ch] * gax[k] + g.diy[ch] * gay[k];
+                        }
+                    }
+                }
+            }
+            // ---- halo ring: 272 pixels, up to 3 per thread (the third only for the first 16 threads)
+            {
+                int hr[PC_NH], hc[PC_NH];
+                Tap th[PC_NH];
+                const int nh = pt < 272 - (PC_NH - 1) * PC_PROD ? PC_NH : PC_NH - 1;
+#pragma unroll
+                for (int j = 0; j < PC_NH; ++j) {
+                    if (j < nh) {
+                        halo_rc(pt + PC_PROD * j, hr[j], hc[j]);
+                        const int iy = ext_to_img(y0 - 2 + hr[j], H), ix = ext_to_img(x0 - 2 + hc[j], W);
+                        const float dvh = UP ? up_sample(dp, p.disp.w, up_tap(iy, p.disp.sh, p.disp.h),
+                                                         up_tap(ix, p.disp.sw, p.disp.w))
+                                             : __ldg(dp + iy * W + ix);
+                        float u0, u1;
+                        th[j] = pixel_tap<FASTDIV>(cam, p, ix, iy, dvh, false, u0, u1);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PC_NH; ++j) {
+                    if (j < nh) {
+                        float tvh[3][4];
+                        load_taps<PK>(sp, N, W, th[j], tvh);
+                        const Gathered g = combine_taps(tvh, th[j], false);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) pred[ch * FT_N2 + hr[j] * FT_R2 + hc[j]] = g.v[ch];
+                    }
+                }
+            }
+            __threadfence_block();
+            mbar_arrive(&full_bar[s]);
+        }
+    } else {
+        // ================================================================ consumers
+        const int oc = tid & 31, os = tid >> 5;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            const int b = t / per_img, rem = t - b * per_img;
+            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int x0 = tx * FT_T, y0 = ty * FT_T;
+            float idv_pre[FT_ROWS];
+            prefetch_ident(p, tid, b, x0, y0, idv_pre);
+            mbar_wait(&full_bar[s], ph);
+            float* tgt = smem + s * 3 * FT_NT;
+            if (x0 < 2 || y0 < 2 || x0 + FT_T + 2 > W || y0 + FT_T + 2 > H) {      // ReflectionPad2d(1) of the target
+                for (int i = tid; i < FT_N2; i += PC_CONS) {
+                    const int r = i / FT_R2, c = i - r * FT_R2;
+                    const int ey = y0 - 2 + r, ex = x0 - 2 + c;
+                    if (ey < 0 || ey >= H || ex < 0 || ex >= W) {
+                        const int sr = ext_to_img(ey, H) - (y0 - 2), sc = ext_to_img(ex, W) - (x0 - 2);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            tgt[ch * FT_NT + r * FT_TP + c + FT_TO] = tgt[ch * FT_NT + sr * FT_TP + sc + FT_TO];
+                    }
+                }
+                named_bar(1, PC_CONS);
+            }
+            TileSmem sm;
+            sm.tgt = tgt; sm.pred = smem + 6 * FT_NT + s * 3 * FT_N2; sm.q1 = q1; sm.q2 = q2; sm.q3 = q3; sm.gate = gate;
+            const float loss_local = phase_b(p, sm, tid, b, x0, y0, idv_pre);
+            // backward factors of this thread's 4 pixels (written by the producer of this CTA: read through L2)
+            float D[4][3];
+            {
+                const float* dg = p.dfac_out + (size_t)b * 3 * N + x0 + oc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int y = y0 + 4 * os + k;
+                    const bool in = y < H && x0 + oc < W;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) D[k][ch] = in ? __ldcg(dg + ch * N + y * W) : 0.0f;
+                }
+            }
+            const float wsum = warp_sum(loss_local);
+            if ((tid & 31) == 0) red[tid >> 5] = wsum;
+            named_bar(1, PC_CONS);                                   // coefficient planes + red[] complete
+            phase_c(p, sm, tid, b, x0, y0, D);
+            if (tid == 0) {
+                float tot = 0.f;
+#pragma unroll
+                for (int i = 0; i < PC_CONS / 32; ++i) tot += red[i];
+                p.loss_partial[t] = tot;
+            }
+            mbar_arrive(&empty_bar[s]);                              // this thread is done with buffer s
+            named_bar(1, PC_CONS);                                   // nobody still reads the coefficient planes / red[]
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Split design, kernel 1: the warp alone.  One thread per 4 pixels of a column (no halo: every pixel of the frame is
 // gathered exactly once, against 1.27x in the fused kernel), low register / no shared-memory footprint, i.e. enough
 // resident warps to hide the gather latency.  Writes
@@ -911,6 +1125,49 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     const bool fastdiv = W > 1 && H > 1 && const_div_exact(W - 1, &p.rcw) && const_div_exact(H - 1, &p.rch);
     const bool packed = (flags & DMH_PHOTO_SRC_PACKED) != 0;
     const bool up = !(disp_h == H && disp_w == W);
+    if (split_ws && (flags & DMH_PHOTO_PIPELINED)) {
+        // ---- persistent producer / consumer kernel; the workspace holds the backward factors (B,3,H,W)
+        if (!use_tma) {
+            set_error("dmh_photo_scale_split(pipelined): needs TMA (W %% 4 == 0, 16-byte aligned frames)");
+            return DMH_ERR_INVALID;
+        }
+        p.dfac_out = split_ws;
+        p.dfac = split_ws;
+        const size_t smem_pc = sizeof(float) * (6 * FT_NT + 6 * FT_N2 + 9 * FT_N1 + 48 + 32) + FT_N1;
+        static bool pc_cfg[64] = {false};
+        static int pc_sms[64] = {0};
+        if (!pc_cfg[dev & 63]) {
+            cudaError_t e = cudaSuccess;
+            const void* fns[8] = {(const void*)photo_pc_kernel<false, false, false>, (const void*)photo_pc_kernel<false, false, true>,
+                                  (const void*)photo_pc_kernel<false, true, false>, (const void*)photo_pc_kernel<false, true, true>,
+                                  (const void*)photo_pc_kernel<true, false, false>, (const void*)photo_pc_kernel<true, false, true>,
+                                  (const void*)photo_pc_kernel<true, true, false>, (const void*)photo_pc_kernel<true, true, true>};
+            for (int i = 0; i < 8 && e == cudaSuccess; ++i)
+                e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pc);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pc_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) {
+                set_error("dmh_photo_scale_split(pipelined): configuration failed: %s", cudaGetErrorString(e));
+                return DMH_ERR_CUDA;
+            }
+            pc_cfg[dev & 63] = true;
+        }
+        const int tiles_x = ceil_div(W, FT_T), tiles_y = ceil_div(H, FT_T), ntiles = tiles_x * tiles_y * B;
+        const int nblk = ntiles < PC_CTAS * pc_sms[dev & 63] ? ntiles : PC_CTAS * pc_sms[dev & 63];
+#define DMH_PC_GO(D_, P_, U_) DMH_LAUNCH((photo_pc_kernel<D_, P_, U_>), nblk, PC_THREADS, smem_pc, st)(p, map, tiles_x, tiles_y, ntiles)
+        if (fastdiv) {
+            if (packed && up) DMH_PC_GO(true, true, true);
+            else if (packed) DMH_PC_GO(true, true, false);
+            else if (up) DMH_PC_GO(true, false, true);
+            else DMH_PC_GO(true, false, false);
+        } else {
+            if (packed && up) DMH_PC_GO(false, true, true);
+            else if (packed) DMH_PC_GO(false, true, false);
+            else if (up) DMH_PC_GO(false, false, true);
+            else DMH_PC_GO(false, false, false);
+        }
+#undef DMH_PC_GO
+        return DMH_OK;
+    }
     if (split_ws) {
         // ---- split design: warp_pred_kernel (warp only, no halo) + the loss kernel fed by two TMA loads
         if (!use_tma || W < 8 || H < 8) {

@@ -339,6 +339,7 @@ FLAG_NO_SSIM = 1
 FLAG_AVG_REPROJECTION = 2
 FLAG_INPUT_IS_DEPTH = 4
 FLAG_SRC_PACKED = 16
+FLAG_PIPELINED = 32
 
 
 class _PhotoScale(torch.autograd.Function):
@@ -409,7 +410,10 @@ _SIDE_STREAMS = {}
 # halo + TMA-fed loss kernel, bit-identical results.  Measured on B200 at config 2 (profiles/r01_ncu_split.txt):
 # 142 + 261 us per scale against 369-393 us fused (the halo recomputation the split saves is paid back in
 # stores / loads of the warped frame and a loss kernel that starts on a cold TMA wait), so the default stays fused.
-SPLIT_PATH = _os.environ.get("DMH_SPLIT", "0") == "1"
+SPLIT_PATH = _os.environ.get("DMH_SPLIT", "0") in ("1", "2")
+# DMH_SPLIT=2: the persistent producer / consumer kernel (one launch per scale, warp of tile i+1 beside SSIM of tile i;
+# bit-identical, measured 520-550 us per scale -- 16 warps per SM issue less than the fused kernel's 24)
+PIPELINED = _os.environ.get("DMH_SPLIT", "0") == "2"
 
 
 def _side_stream(dev, which=0):
@@ -498,7 +502,8 @@ class _Objective(torch.autograd.Function):
                         ws_split = torch.empty(lib.dmh_photo_split_workspace_floats(B, H, W), device=dev,
                                                dtype=torch.float32)
                         check(lib.dmh_photo_scale_split(ptr(target), ptr(src_pk), ptr(Ts[0]), ptr(d), h, w, ptr(k), ptr(ik),
-                                                        ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth, flags,
+                                                        ptr(ident), ptr(noises[s]), B, H, W, min_depth, max_depth,
+                                                        flags | (FLAG_PIPELINED if PIPELINED else 0),
                                                         inv_den, ptr(ws_split), ptr(part), ptr(g_full), ptr(sel), stream()),
                                   "photo_scale_split")
                         if s & 1:

@@ -159,6 +159,7 @@ int dmh_identity_loss_pack(const float* target, const float* src, int B, int H, 
 #define DMH_PHOTO_INPUT_IS_DEPTH 4
 #define DMH_PHOTO_FORCE_GENERIC 8 /* testing: never take the single-source fast kernel */
 #define DMH_PHOTO_SRC_PACKED 16 /* src_host[0] is the (B,H,W,4) layout of dmh_identity_loss_pack; F == 1, no pose grad */
+#define DMH_PHOTO_PIPELINED 32 /* dmh_photo_scale_split: one persistent producer / consumer kernel instead of two kernels */
 #define DMH_PHOTO_MAX_FRAMES 4
 int dmh_photo_tiles(int H, int W);           /* CTAs per batch item */
 int dmh_photo_scale(const float* target, const float* const* src_host, const float* const* T_host, int F,
