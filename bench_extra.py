@@ -99,7 +99,7 @@ def main():
         print(json.dumps({"workload": "depth-hints objective fwd+bwd (config 4)", "B": B, "H": H, "W": W,
                           "ms_per_step": ms, "mpix_per_s": B * H * W / ms / 1e3, "gpu_launches": int(launches),
                           "algorithmic_bytes_per_px": bpp, "hbm_frac": bpp * B * H * W / (ms * 1e-3) / 1e9 / peak,
-                          "note": "fused: one dmh_photo_scale_dh launch per scale (multi-source kernel in depth-hints mode)"}))
+                          "note": "fused: one dmh_photo_scale_dh launch per scale (single-source fast kernel with the depth-hints decision, packed source)"}))
 
     if "md_f2" in want:
         from depthmodelhardening_b200 import objective

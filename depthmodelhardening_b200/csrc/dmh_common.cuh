@@ -103,4 +103,13 @@ __device__ __forceinline__ float load_disp(const DispSrc& d, int b, int iy, int 
            ty.l1 * (tx.l0 * __ldg(p + ty.i1 * d.w + tx.i0) + tx.l1 * __ldg(p + ty.i1 * d.w + tx.i1));
 }
 
+// depth-hints arguments of the single-source fast kernel (photo_fast.cu), handed over by dmh_photo_scale_dh
+struct FastDhArgs {
+    const float* hint_reproj;
+    const float* hint_depth;
+    const float* hint_valid;
+    float* grad_hint;
+    int nblk;              // stride between the four partial-sum arrays
+};
+
 }  // namespace dmh

@@ -107,6 +107,12 @@ struct FastParams {
     float* predp;                // warp_pred_kernel output: (B,3,H+4,WP) warped frame, image pixel (x,y) at (x+2,y+2)
     float* dfac_out;             // warp_pred_kernel output
     int WP;                      // row pitch of predp (multiple of 4 floats)
+    // depth-hints objective (DH/trainer.py:541-590, 666-713), DH instantiation only
+    const float* hint_reproj;    // (B,1,H,W) hint reprojection loss + 1000*(1-valid); NULL: no hints
+    const float* hint_depth;     // (B,1,H,W)
+    const float* hint_valid;     // (B,1,H,W)
+    float* grad_hint;            // (B,1,H,W) d(sum proxy*mask_h)/d(up-sampled disp)
+    int dh_nblk;                 // stride between the four partial-sum arrays
     int B, H, W, flags;
     DepthScale ds;
     float grad_scale;
@@ -233,8 +239,12 @@ struct TileSmem {
     uint8_t* gate;   // [N1]
 };
 
+// DH: the value kept is min(identity + noise, hint loss) -- the hint wins only when strictly smaller -- and bit k of
+// `hflags` says that it was the hint (argmin order of the depth-hints objective: reprojection, identity, hint).
+template <bool DH = false>
 __device__ __forceinline__ void prefetch_ident(const FastParams& p, int tid, int b, int x0, int y0,
-                                               float (&idv_pre)[FT_ROWS]) {
+                                               float (&idv_pre)[FT_ROWS], unsigned& hflags) {
+    hflags = 0u;
     const int H = p.H, W = p.W, N = H * W;
     const int bc = tid % FT_R1, bstrip = tid / FT_R1;
     const bool has_ident = p.ident != nullptr;
@@ -251,12 +261,20 @@ __device__ __forceinline__ void prefetch_ident(const FastParams& p, int tid, int
             v = __ldg(idp + qy * W);
             if (p.noise) v = add_rn(v, __ldg(nzp + qy * W));
         }
+        if (DH && ok && p.hint_reproj) {
+            const float hv = __ldg(p.hint_reproj + (size_t)b * N + qy * W + qx);
+            if (hv < v) { v = hv; hflags |= 1u << k; }
+        }
         idv_pre[k] = v;
     }
 }
 
+// DH: the depth-hints decision -- argmin over [reprojection, identity + noise, hint] with the reprojection first
+// (ties go to it), reprojection mask = argmin != identity, hint mask = argmin == hint; four masked sums in acc
+// (reproj*mask_r, mask_r, log(|hint - depth| + 1)*valid*mask_h, mask_h) and the proxy-loss gradient map.
+template <bool DH, bool UP>
 __device__ __forceinline__ float phase_b(const FastParams& p, const TileSmem& sm, int tid, int b, int x0, int y0,
-                                         const float (&idv_pre)[FT_ROWS]) {
+                                         const float (&idv_pre)[FT_ROWS], unsigned hflags, float (&acc)[4]) {
     const int W = p.W, N = p.H * p.W;
     const float w_ssim = 0.85f / 3.0f;
     const int bc = tid % FT_R1, bstrip = tid / FT_R1;
@@ -304,7 +322,14 @@ __device__ __forceinline__ float phase_b(const FastParams& p, const TileSmem& sm
                 l1 *= (1.0f / 3.0f);
                 const float rp = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
                 const float idv = idv_pre[rr - 2];
-                const bool win = rp < idv;              // torch.min: first minimum wins, identity is first
+                bool win = rp < idv;                    // torch.min: first minimum wins, identity is first
+                int dh_idx = 0;
+                const bool in_img = idv == idv;         // (NaN marks ring pixels outside the image)
+                if (DH) {
+                    // idv = min(identity, hint) with the hint flagged: argmin over [reprojection, identity, hint]
+                    if (idv < rp) dh_idx = ((hflags >> (rr - 2)) & 1u) ? 2 : 1;
+                    win = in_img && dh_idx != 1;        // the reprojection term is optimised unless the identity wins
+                }
                 const float gw = win ? w_ssim : 0.0f;
                 float2 kaP, kbP, kcP;
                 ssim_coef_gated_t(stP, rP, nrP, vmul(make_float2(gw, gw), passP), kaP, kbP, kcP);
@@ -315,11 +340,17 @@ __device__ __forceinline__ float phase_b(const FastParams& p, const TileSmem& sm
                     coefQ1[qi] = make_float4(kaP.x, kaP.y, kbP.x, kbP.y);
                     coefQ2[qi] = make_float4(kcP.x, kcP.y, kaS, kbS);
                     coefQ3[qi] = kcS;
-                    gate[qi] = win ? 1 : 0;
+                    gate[qi] = (uint8_t)((win ? 1 : 0) | ((DH && dh_idx == 2) ? 2 : 0));
                 }
-                if (col_in && qr >= 1 && qr <= FT_T && idv == idv) {     // a pixel of the tile proper, inside the image
-                    loss_local += win ? rp : idv;
-                    if (p.sel) p.sel[(size_t)b * N + (y0 - 1 + qr) * W + x0 - 1 + bc] = (uint8_t)((win && has_ident) ? 1 : 0);
+                if (col_in && qr >= 1 && qr <= FT_T && in_img) {         // a pixel of the tile proper, inside the image
+                    const int qo = (y0 - 1 + qr) * W + x0 - 1 + bc;
+                    if (!DH) {
+                        loss_local += win ? rp : idv;
+                        if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)((win && has_ident) ? 1 : 0);
+                    } else {
+                        if (dh_idx != 1) { acc[0] += rp; acc[1] += 1.0f; }
+                        if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)dh_idx;
+                    }
                 }
             }
             histP[0] = histP[1]; histP[1] = curP;
@@ -332,8 +363,11 @@ __device__ __forceinline__ float phase_b(const FastParams& p, const TileSmem& sm
 
 // ---- phase C of the tile kernels: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp).
 // `tid` < 256 owns column tid%32, rows 4*(tid/32)+k of the tile; D = d(pred_ch)/d(disp) of those 4 pixels.
+// DH: the proxy loss of the depth hints, log(|hint - depth| + 1) * valid where the hint won (bit 1 of the gate byte),
+// its masked sums (acc[2], acc[3]) and its gradient map, for the same 4 pixels.
+template <bool DH, bool UP>
 __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm, int tid, int b, int x0, int y0,
-                                        const float (&D)[4][3]) {
+                                        const float (&D)[4][3], float (&acc)[4]) {
     const int H = p.H, W = p.W, N = H * W;
     const float w_l1 = 0.15f / 3.0f;
     const int oc = tid & 31, os = tid >> 5;
@@ -343,6 +377,20 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
     const float4* coefQ2 = sm.q2;
     const float* coefQ3 = sm.q3;
     const uint8_t* gate = sm.gate;
+    float h_dv[4], h_hd[4], h_va[4];
+    if (DH && p.hint_reproj) {
+        // requested up front: their latency hides behind the box sums
+        const float* dp = p.disp.ptr + (size_t)b * (p.disp.h * p.disp.w);
+        const int hx = min(x0 + oc, W - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int hy = min(y0 + 4 * os + k, H - 1);
+            h_dv[k] = UP ? up_sample(dp, p.disp.w, up_tap(hy, p.disp.sh, p.disp.h), up_tap(hx, p.disp.sw, p.disp.w))
+                         : __ldg(dp + hy * W + hx);
+            h_hd[k] = __ldg(p.hint_depth + (size_t)b * N + hy * W + hx);
+            h_va[k] = __ldg(p.hint_valid + (size_t)b * N + hy * W + hx);
+        }
+    }
     {
         const int px = x0 + oc;
         const float wl = (px == 1) ? 2.0f : 1.0f;           // ring column 0 reaches pixel 1 twice (reflection)
@@ -378,7 +426,7 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
                 const float2 wu2 = make_float2(wu, wu), wd2 = make_float2(wd, wd);
                 const int i2 = (r + 2) * FT_R2 + oc + 2;
                 const int it = (r + 2) * FT_TP + oc + 2 + FT_TO;
-                const float gl1 = gate[(r + 1) * FT_R1 + oc + 1] ? w_l1 : 0.0f;
+                const float gl1 = (gate[(r + 1) * FT_R1 + oc + 1] & 1) ? w_l1 : 0.0f;
                 const float2 saP = vfma(wu2, hprev[0][0], vfma(wd2, hc[0], hprev[1][0]));
                 const float2 sbP = vfma(wu2, hprev[0][1], vfma(wd2, hc[1], hprev[1][1]));
                 const float2 scP = vfma(wu2, hprev[0][2], vfma(wd2, hc[2], hprev[1][2]));
@@ -397,6 +445,16 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
                 g = fmaf(gpP.y, D[k][1], g);
                 g = fmaf(gpS, D[k][2], g);
                 if (py < H && px < W) gout[py * W] = g;
+                if (DH && p.hint_reproj && py < H && px < W) {
+                    const float m_h = (gate[(r + 1) * FT_R1 + oc + 1] & 2) ? 1.0f : 0.0f;
+                    const float depth = disp_to_depth(h_dv[k], p.ds);
+                    const float diff = sub_rn(h_hd[k], depth);
+                    const float a1 = add_rn(fabsf(diff), 1.0f);
+                    acc[2] += mul_rn(mul_rn(logf(a1), h_va[k]), m_h);
+                    acc[3] += m_h;
+                    const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
+                    p.grad_hint[(size_t)b * N + py * W + px] = m_h * h_va[k] * sg / a1 * ddepth_ddisp(depth, p.ds);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) { hprev[0][j] = hprev[1][j]; hprev[1][j] = hc[j]; }
@@ -411,7 +469,7 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
 // take the general kernel).
 // SPLIT: the warp was done by warp_pred_kernel (below): the warped tile arrives by a second TMA load from its padded,
 // reflect-bordered output and the backward factors D from global memory -- this kernel is then phases B and C only.
-template <bool TMA, bool FASTDIV, bool PK, bool UP, bool SPLIT>
+template <bool TMA, bool FASTDIV, bool PK, bool UP, bool SPLIT, bool DH = false>
 __global__ void __launch_bounds__(FT_THREADS, 3)
 photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map,
                   const __grid_constant__ CUtensorMap pred_map) {
@@ -550,7 +608,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
     // that their latency overlaps the other warps' gather.  Ring pixels outside the image are marked by a NaN
     // (rp < NaN is false: they never win, their coefficients are gated to 0 and they add nothing to the loss).
     float idv_pre[FT_ROWS];
-    prefetch_ident(p, tid, b, x0, y0, idv_pre);
+    unsigned hflags;
+    prefetch_ident<DH>(p, tid, b, x0, y0, idv_pre, hflags);
     __syncthreads();
     if (TMA) {
         mbar_wait(&tgt_bar, 0);
@@ -573,7 +632,8 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
 
     TileSmem sm;
     sm.tgt = tgt; sm.pred = pred; sm.q1 = coefQ1; sm.q2 = coefQ2; sm.q3 = coefQ3; sm.gate = gate;
-    const float loss_local = phase_b(p, sm, tid, b, x0, y0, idv_pre);
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float loss_local = phase_b<DH, UP>(p, sm, tid, b, x0, y0, idv_pre, hflags, acc4);
     __syncthreads();
     if (SPLIT) {
         // d(pred)/d(disp) factors of this thread's 4 pixels, written by warp_pred_kernel (loaded here, not before
@@ -587,9 +647,19 @@ photo_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_ma
             for (int ch = 0; ch < 3; ++ch) D[k][ch] = in ? __ldg(dg + ch * N + y * W) : 0.0f;
         }
     }
-    phase_c(p, sm, tid, b, x0, y0, D);
-    const float s = block_sum(loss_local, red);
-    if (tid == 0) p.loss_partial[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    phase_c<DH, UP>(p, sm, tid, b, x0, y0, D, acc4);
+    const int blk = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (DH) {
+        // [4][dh_nblk]: sum reproj*mask_r, sum mask_r, sum proxy*mask_h, sum mask_h
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float s = block_sum(acc4[q], red);
+            if (tid == 0) p.loss_partial[q * p.dh_nblk + blk] = s;
+        }
+    } else {
+        const float s = block_sum(loss_local, red);
+        if (tid == 0) p.loss_partial[blk] = s;
+    }
 }
 
 
@@ -760,7 +830,8 @@ photo_pc_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map,
             const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * FT_T, y0 = ty * FT_T;
             float idv_pre[FT_ROWS];
-            prefetch_ident(p, tid, b, x0, y0, idv_pre);
+            unsigned hflags;
+            prefetch_ident<false>(p, tid, b, x0, y0, idv_pre, hflags);
             mbar_wait(&full_bar[s], ph);
             float* tgt = smem + s * 3 * FT_NT;
             if (x0 < 2 || y0 < 2 || x0 + FT_T + 2 > W || y0 + FT_T + 2 > H) {      // ReflectionPad2d(1) of the target
@@ -778,7 +849,8 @@ photo_pc_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map,
             }
             TileSmem sm;
             sm.tgt = tgt; sm.pred = smem + 6 * FT_NT + s * 3 * FT_N2; sm.q1 = q1; sm.q2 = q2; sm.q3 = q3; sm.gate = gate;
-            const float loss_local = phase_b(p, sm, tid, b, x0, y0, idv_pre);
+            float acc4[4];
+            const float loss_local = phase_b<false, UP>(p, sm, tid, b, x0, y0, idv_pre, hflags, acc4);
             // backward factors of this thread's 4 pixels (written by the producer of this CTA: read through L2)
             float D[4][3];
             {
@@ -794,7 +866,7 @@ photo_pc_kernel(const FastParams p, const __grid_constant__ CUtensorMap tgt_map,
             const float wsum = warp_sum(loss_local);
             if ((tid & 31) == 0) red[tid >> 5] = wsum;
             named_bar(1, PC_CONS);                                   // coefficient planes + red[] complete
-            phase_c(p, sm, tid, b, x0, y0, D);
+            phase_c<false, UP>(p, sm, tid, b, x0, y0, D, acc4);
             if (tid == 0) {
                 float tot = 0.f;
 #pragma unroll
@@ -1071,7 +1143,7 @@ long long photo_split_workspace_floats(int B, int H, int W) {
 int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, int disp_h,
                       int disp_w, const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
-                      uint8_t* sel, float* warped, float* split_ws, cudaStream_t st) {
+                      uint8_t* sel, float* warped, float* split_ws, const FastDhArgs* dh, cudaStream_t st) {
     FastParams p;
     p.target = target; p.src = src; p.T = T; p.K = K;
     p.disp.ptr = disp; p.disp.h = disp_h; p.disp.w = disp_w; p.disp.sh = (float)disp_h / (float)H; p.disp.sw = (float)disp_w / (float)W; p.inv_K = inv_K; p.ident = ident;
@@ -1082,6 +1154,9 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
     p.ds.range = is_depth ? 0.f : (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
     p.grad_scale = grad_scale;
     p.dfac = nullptr; p.predp = nullptr; p.dfac_out = nullptr; p.WP = 0;
+    p.hint_reproj = dh ? dh->hint_reproj : nullptr; p.hint_depth = dh ? dh->hint_depth : nullptr;
+    p.hint_valid = dh ? dh->hint_valid : nullptr; p.grad_hint = dh ? dh->grad_hint : nullptr;
+    p.dh_nblk = dh ? dh->nblk : 0;
     const size_t smem = fast_smem_bytes();
     static bool configured_dev[64] = {false};
     int dev = 0;
@@ -1100,6 +1175,15 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute((const void*)photo_fast_kernel<true, false, false, false, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define DMH_DH_FN(T_, D_, P_, U_) (const void*)photo_fast_kernel<T_, D_, P_, U_, false, true>
+#define DMH_DH_FN4(P_, U_) DMH_DH_FN(false, false, P_, U_), DMH_DH_FN(false, true, P_, U_), \
+                           DMH_DH_FN(true, false, P_, U_), DMH_DH_FN(true, true, P_, U_)
+        const void* dfns[16] = {DMH_DH_FN4(false, false), DMH_DH_FN4(false, true), DMH_DH_FN4(true, false),
+                                DMH_DH_FN4(true, true)};
+#undef DMH_DH_FN4
+#undef DMH_DH_FN
+        for (int i = 0; i < 16 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(dfns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("dmh_photo_scale(fast): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return DMH_ERR_CUDA;
@@ -1214,7 +1298,11 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
         DMH_LAUNCH((photo_fast_kernel<true, false, false, false, true>), grid, FT_THREADS, smem, st)(p, map, pmap);
         return DMH_OK;
     }
-#define DMH_FAST_GO(T_, D_, P_, U_) DMH_LAUNCH((photo_fast_kernel<T_, D_, P_, U_, false>), grid, FT_THREADS, smem, st)(p, map, map)
+#define DMH_FAST_GO(T_, D_, P_, U_)                                                                           \
+    do {                                                                                                      \
+        if (dh) DMH_LAUNCH((photo_fast_kernel<T_, D_, P_, U_, false, true>), grid, FT_THREADS, smem, st)(p, map, map); \
+        else DMH_LAUNCH((photo_fast_kernel<T_, D_, P_, U_, false>), grid, FT_THREADS, smem, st)(p, map, map);   \
+    } while (0)
 #define DMH_FAST_GO2(P_, U_)                                           \
     do {                                                               \
         if (use_tma && fastdiv) DMH_FAST_GO(true, true, P_, U_);       \

@@ -480,7 +480,7 @@ int photo_fast_tiles(int H, int W);
 int launch_photo_fast(const float* target, const float* src, const float* T, const float* disp, int disp_h,
                       int disp_w, const float* K, const float* inv_K, const float* ident, const float* noise, int B, int H, int W, float min_depth,
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
-                      uint8_t* sel, float* warped, float* split_ws, cudaStream_t st);
+                      uint8_t* sel, float* warped, float* split_ws, const FastDhArgs* dh, cudaStream_t st);
 long long photo_split_workspace_floats(int B, int H, int W);
 int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
                       float* out, float* packed, cudaStream_t st);
@@ -533,6 +533,32 @@ int dmh_photo_scale_dh(const float* target, const float* const* src_host, const 
     DMH_REQUIRE(!hint_reproj || (hint_depth && hint_valid && grad_disp_hint),
                 "dmh_photo_scale_dh: depth hints need hint_depth, hint_valid and grad_disp_hint");
     DMH_REQUIRE(!noise || ident, "dmh_photo_scale_dh: noise without identity losses");
+    // single source, no pose gradient (the stereo-only depth-hints configuration): the 32x32-tile fast kernel
+    // with the depth-hints decision; same contract (its fewer per-CTA partials sit at the head of each array)
+    if (F == 1 && !grad_P_partial && !(flags & (DMH_PHOTO_FORCE_GENERIC | DMH_PHOTO_NO_SSIM | DMH_PHOTO_INPUT_IS_DEPTH |
+                                                DMH_PHOTO_AVG_REPROJECTION)) &&
+        H * (long long)W < (1ll << 28)) {
+        DMH_REQUIRE(target && src_host && src_host[0] && T_host && T_host[0] && disp && K && inv_K && sums_partial && grad_disp,
+                    "dmh_photo_scale_dh: null pointer");
+        DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2 && disp_h >= 1 && disp_w >= 1 && disp_h <= H && disp_w <= W,
+                    "dmh_photo_scale_dh: bad shape");
+        DMH_REQUIRE(min_depth > 0.f && max_depth > min_depth, "dmh_photo_scale_dh: bad depth range");
+        DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED) || (uintptr_t)src_host[0] % 16 == 0,
+                    "dmh_photo_scale_dh: DMH_PHOTO_SRC_PACKED needs a 16-byte aligned source");
+        const int nblk = B * dmh_photo_tiles(H, W);
+        cudaError_t e = cudaMemsetAsync(sums_partial, 0, sizeof(float) * 4 * (size_t)nblk, (cudaStream_t)stream);
+        if (e != cudaSuccess) { set_error("dmh_photo_scale_dh: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+        FastDhArgs a;
+        a.hint_reproj = hint_reproj; a.hint_depth = hint_depth; a.hint_valid = hint_valid; a.grad_hint = grad_disp_hint;
+        a.nblk = nblk;
+        const int rc = launch_photo_fast(target, src_host[0], T_host[0], disp, disp_h, disp_w, K, inv_K, ident, noise, B, H, W,
+                                         min_depth, max_depth, flags, 1.0f, sums_partial, grad_disp, sel, nullptr, nullptr, &a,
+                                         (cudaStream_t)stream);
+        if (rc != DMH_OK) return rc;
+        DMH_CHECK_LAUNCH("dmh_photo_scale_dh(fast)");
+        return DMH_OK;
+    }
+    DMH_REQUIRE(!(flags & DMH_PHOTO_SRC_PACKED), "dmh_photo_scale_dh: DMH_PHOTO_SRC_PACKED needs the single-source fast path");
     g_dh_next.armed = true;
     g_dh_next.hint_reproj = hint_reproj; g_dh_next.hint_depth = hint_depth; g_dh_next.hint_valid = hint_valid;
     g_dh_next.grad_hint = grad_disp_hint;
@@ -595,7 +621,7 @@ int dmh_photo_scale(const float* target, const float* const* src_host, const flo
         }
         const int rc = launch_photo_fast(target, src_host[0], T_host[0], disp, disp_h, disp_w, K, inv_K, ident, noise, B, H, W, min_depth,
                                          max_depth, flags, grad_scale, loss_partial, grad_disp, sel,
-                                         warped_host ? warped_host[0] : nullptr, g_split_ws, (cudaStream_t)stream);
+                                         warped_host ? warped_host[0] : nullptr, g_split_ws, nullptr, (cudaStream_t)stream);
         if (rc != DMH_OK) return rc;
         DMH_CHECK_LAUNCH("dmh_photo_scale(fast)");
         return DMH_OK;

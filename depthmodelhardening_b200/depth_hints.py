@@ -128,7 +128,7 @@ def depth_hint_losses(colors: Dict, disps: Dict, K, inv_K, Ts: Dict, frame_ids, 
 
 
 def _prologue(colors, Ts, frame_ids, height, width, depth_hint, depth_hint_mask, use_depth_hints, no_ssim,
-              disable_automasking, K, inv_K, fast_math=True):
+              disable_automasking, K, inv_K, fast_math=True, pack_out=None):
     """Scale-independent, gradient-free parts: the hint reprojection loss and the identity losses."""
     srcs_ids = list(frame_ids[1:])
     target = colors[(0, 0)]
@@ -145,9 +145,16 @@ def _prologue(colors, Ts, frame_ids, height, width, depth_hint, depth_hint_mask,
     else:
         hint_rl = hint_pred = None
     ident = None
-    if not disable_automasking:
-        with torch.no_grad():
+    with torch.no_grad():
+        if not disable_automasking:
             ident = torch.empty(B, len(srcs), height, width, device=target.device, dtype=torch.float32)
+        if pack_out is not None and len(srcs) == 1 and not no_ssim:
+            # single source: the identity-loss kernel also writes the pixel-packed copy the fast kernel gathers from
+            pk = torch.empty(B, height, width, 4, device=target.device, dtype=torch.float32)
+            check(_lib_().dmh_identity_loss_pack(ptr(f32c(target)), ptr(f32c(srcs[0])), B, height, width, 0, ptr(ident),
+                                                 ptr(pk), stream()), "identity_loss_pack")
+            pack_out.append(pk)
+        elif ident is not None:
             check(_lib_().dmh_identity_loss(ptr(f32c(target)), ptr_array([f32c(s) for s in srcs]), len(srcs), B, height,
                                             width, int(no_ssim), ptr(ident), stream()), "identity_loss")
     return srcs_ids, srcs, target, B, hint_rl, hint_pred, ident
@@ -158,7 +165,7 @@ class _ObjectiveDH(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, K, inv_K, cfg, ident, hint_rl, hint_depth, hint_valid, *tensors):
-        (min_depth, max_depth, flags, smooth_w, want_sel, n_src, S, has_noise) = cfg
+        (min_depth, max_depth, flags, smooth_w, want_sel, n_src, S, has_noise, src_pk) = cfg
         it = iter(tensors)
         colors = [f32c(next(it)) for _ in range(S)]
         srcs = [f32c(next(it)) for _ in range(n_src)]
@@ -179,6 +186,9 @@ class _ObjectiveDH(torch.autograd.Function):
         tiles = lib.dmh_photo_tiles(H, W)
         nblk = B * tiles
         src_arr, T_arr = ptr_array(srcs), ptr_array(Ts)
+        if src_pk is not None and not need_T:             # single source, no pose gradient: packed 128-bit gather
+            src_arr = ptr_array([src_pk])
+            flags |= ops.FLAG_SRC_PACKED
         G_r, G_h, gN, wss, gPs, sels, sums = [], [], [], [], [], [], []
         for s in range(S):
             d = disps[s]
@@ -289,9 +299,10 @@ def _depth_hint_losses_fused(colors, disps, K, inv_K, Ts, frame_ids, scales, hei
     scales = list(scales)
     if scales[0] != 0:
         raise NotImplementedError("the fused objective needs scale 0 first in opt.scales")
+    packs = []
     srcs_ids, srcs, target, B, hint_rl, hint_pred, ident = _prologue(
         colors, Ts, frame_ids, height, width, depth_hint, depth_hint_mask, use_depth_hints, no_ssim,
-        disable_automasking, K, inv_K)
+        disable_automasking, K, inv_K, pack_out=None if avg_reprojection else packs)
     nz = None
     if ident is not None:
         nz = [noise[s] if noise is not None else tie_break_noise((B, 1, height, width), target.device, noise_mode)
@@ -301,7 +312,7 @@ def _depth_hint_losses_fused(colors, disps, K, inv_K, Ts, frame_ids, scales, hei
     S, n_src = len(scales), len(srcs)
     flags = (ops.FLAG_NO_SSIM if no_ssim else 0) | (ops.FLAG_AVG_REPROJECTION if avg_reprojection else 0)
     cfg = (float(min_depth), float(max_depth), flags, tuple(disparity_smoothness / (2 ** s) for s in scales),
-           bool(want_selection), n_src, S, nz is not None)
+           bool(want_selection), n_src, S, nz is not None, packs[0] if packs else None)
     colors0 = [target] + [colors[(0, s)] for s in scales[1:]]
     tensors = colors0 + srcs + [Ts[f] for f in srcs_ids] + [disps[s] for s in scales] + (nz if nz is not None else [])
     out = _ObjectiveDH.apply(K, inv_K, cfg, ident, hint_rl, depth_hint if use_depth_hints else None,
