@@ -53,16 +53,20 @@ warp_fwd_kernel(const float* __restrict__ disp, int input_is_depth, DepthScale d
     if (n >= N) return;
     const int px = n % W, py = n / W;
     const float dv = disp[(size_t)b * N + n];
-    const float depth = input_is_depth ? dv : disp_to_depth(dv, ds);
+    const bool is_depth = (input_is_depth & 1) != 0;
+    const bool half_pixel = (input_is_depth & 2) != 0;      // grid_sample(align_corners=False): the depth-hints warp
+    const float depth = is_depth ? dv : disp_to_depth(dv, ds);
     if (depth_out) depth_out[(size_t)b * N + n] = depth;
     const WarpCoord wc = warp_coord(cam, (float)px, (float)py, depth, W, H, 1e-7f);
-    if (grid_out) {
-        float2 g;
-        g.x = normalise_coord(wc.u_raw, 1.0f, W);   // u_raw already divided by z
-        g.y = normalise_coord(wc.v_raw, 1.0f, H);
-        reinterpret_cast<float2*>(grid_out)[(size_t)b * N + n] = g;
+    const float gxn = normalise_coord(wc.u_raw, 1.0f, W);   // u_raw already divided by z
+    const float gyn = normalise_coord(wc.v_raw, 1.0f, H);
+    if (grid_out) reinterpret_cast<float2*>(grid_out)[(size_t)b * N + n] = make_float2(gxn, gyn);
+    float six = wc.ix, siy = wc.iy;
+    if (half_pixel) {       // same op sequence as Project3D -> grid_sample(border, align_corners=False)
+        six = clip_coord_fwd(unnormalise_coord(gxn, W, false), W);
+        siy = clip_coord_fwd(unnormalise_coord(gyn, H, false), H);
     }
-    const Bilinear bl = bilinear_setup(wc.ix, wc.iy);
+    const Bilinear bl = bilinear_setup(six, siy);
     const bool x0in = bl.x0 >= 0 && bl.x0 < W, x1in = bl.x0 + 1 >= 0 && bl.x0 + 1 < W;
     const bool y0in = bl.y0 >= 0 && bl.y0 < H, y1in = bl.y0 + 1 >= 0 && bl.y0 + 1 < H;
     const long long o00 = (long long)bl.y0 * W + bl.x0;
@@ -402,8 +406,8 @@ int dmh_warp_fwd(const float* disp, int input_is_depth, float min_depth, float m
                  float* grid_out, float* depth_out, dmh_stream_t stream) {
     DMH_REQUIRE(disp && src && K && inv_K && T && warped, "dmh_warp_fwd: null pointer");
     DMH_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && B <= 65535, "dmh_warp_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
-    DMH_REQUIRE(input_is_depth || (min_depth > 0.f && max_depth > min_depth), "dmh_warp_fwd: bad depth range");
-    const DepthScale ds = input_is_depth ? DepthScale{0.f, 0.f} : make_depth_scale(min_depth, max_depth);
+    DMH_REQUIRE((input_is_depth & 1) || (min_depth > 0.f && max_depth > min_depth), "dmh_warp_fwd: bad depth range");
+    const DepthScale ds = (input_is_depth & 1) ? DepthScale{0.f, 0.f} : make_depth_scale(min_depth, max_depth);
     dim3 grid(ceil_div((long long)H * W, WARP_THREADS), B);
     if (C == 3)
         DMH_LAUNCH(warp_fwd_kernel<3>, grid, WARP_THREADS, 0, (cudaStream_t)stream)(disp, input_is_depth, ds, src, K, inv_K, T,

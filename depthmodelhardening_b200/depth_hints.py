@@ -96,9 +96,9 @@ def hint_reprojection_loss(target, src, depth_hint, depth_hint_mask, K, inv_K, T
     tie, as in the reference, where both losses come out of the same code."""
     with torch.no_grad():
         B, _, H, W = target.shape
-        pts = ops._Backproject.apply(f32c(depth_hint), inv_K, B, H, W)
-        grid = ops._Project3D.apply(pts, K, T, B, H, W, 1e-7)
-        pred = ops.grid_sample(src, grid, padding_mode="border", align_corners=False)
+        # one fused gather (same op sequence as BackprojectDepth -> Project3D -> grid_sample(border, align_corners=False))
+        pred, _, _ = ops.warp_with_aux(depth_hint, src, K, inv_K, T, input_is_depth=True, align_corners=False,
+                                       want_aux=False)
         if fast_math:
             loss = torch.empty(B, 1, H, W, device=pred.device, dtype=torch.float32)
             check(_lib_().dmh_identity_loss(ptr(f32c(target)), ptr_array([pred]), 1, B, H, W, int(no_ssim), ptr(loss),

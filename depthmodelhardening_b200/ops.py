@@ -321,15 +321,18 @@ def warp_reproject(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input
     return _WarpFused.apply(disp, src, K, inv_K, T, float(min_depth), float(max_depth), bool(input_is_depth))
 
 
-def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_is_depth=False):
+def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_is_depth=False, align_corners=True,
+                  want_aux=True):
     """No-grad variant also returning the sampling grid and the depth map
-    (the tensors the reference stores in `outputs` for logging)."""
+    (the tensors the reference stores in `outputs` for logging).  align_corners=False: the sampling convention of
+    the depth-hints warp (`F.grid_sample` default, DH/trainer.py:523-525)."""
     d, s, k, ik, t = f32c(disp), f32c(src), f32c(K), f32c(inv_K), f32c(T)
     B, Cc, H, W = s.shape
     out = torch.empty_like(s)
-    grid = torch.empty(B, H, W, 2, device=s.device, dtype=torch.float32)
-    depth = torch.empty(B, 1, H, W, device=s.device, dtype=torch.float32)
-    check(_lib_().dmh_warp_fwd(ptr(d), int(input_is_depth), min_depth, max_depth, ptr(s), ptr(k), ptr(ik), ptr(t),
+    grid = torch.empty(B, H, W, 2, device=s.device, dtype=torch.float32) if want_aux else None
+    depth = torch.empty(B, 1, H, W, device=s.device, dtype=torch.float32) if want_aux else None
+    mode = (1 if input_is_depth else 0) | (0 if align_corners else 2)       # dmh_warp_fwd: bit 0 depth input, bit 1 half-pixel
+    check(_lib_().dmh_warp_fwd(ptr(d), mode, min_depth, max_depth, ptr(s), ptr(k), ptr(ik), ptr(t),
                                B, Cc, H, W, ptr(out), ptr(grid), ptr(depth), stream()), "warp_fwd")
     return out, grid, depth
 

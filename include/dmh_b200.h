@@ -115,6 +115,8 @@ int dmh_upsample_bilinear_bwd(const float* grad_out, int planes, int h, int w, i
  *    border warp in ONE kernel (M2/trainer.py:485-519 for one (scale, frame)).
  * disp (B,1,H,W) full resolution (or depth when input_is_depth), src (B,C,H,W),
  * K,inv_K,T (B,4,4) -> warped (B,C,H,W); optional grid (B,H,W,2), depth (B,1,H,W)
+ * fwd: input_is_depth bit 0 = the input is a depth map, bit 1 = sample with align_corners=False (the depth-hints
+ *      warp, DH/trainer.py:523-525; forward only).
  * bwd: grad_disp (B,1,H,W) [d/d(disp) or d/d(depth)], grad_src (accumulated,
  * nullable), grad_P_partial (B, nblk, 12) nullable, nblk = dmh_warp_bwd_blocks.  */
 int dmh_warp_fwd(const float* disp, int input_is_depth, float min_depth, float max_depth, const float* src,
