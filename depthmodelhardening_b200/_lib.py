@@ -82,6 +82,7 @@ SIGNATURES = {
     "dmh_cost_volume_workspace_floats": (_ll, [_i, _i, _i, _i, _i]),
     "dmh_cost_volume": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
+    "dmh_reduce_rows": (_i, [_f, _i, _ll, _fl, _f, _st]),
 }
 
 _lib = None

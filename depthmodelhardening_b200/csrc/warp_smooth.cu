@@ -373,10 +373,13 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ gout, int h, int w
 }
 
 // ---------------------------------------------------------------------------- reduce
+// (one block per row: blockIdx.x selects the row of a (rows, n) array; rows == 1 for dmh_reduce_sum)
 __global__ void reduce_sum_kernel(const float* __restrict__ in, long long n, float scale, int accumulate,
                                   float* __restrict__ out) {
     __shared__ double red[32];
     double s = 0.0;
+    in += (size_t)blockIdx.x * n;
+    out += blockIdx.x;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)in[i];
     s = warp_sum_d(s);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -507,6 +510,13 @@ int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, fl
     DMH_REQUIRE(in && out && n > 0, "dmh_reduce_sum: null pointer or n <= 0");
     DMH_LAUNCH(reduce_sum_kernel, 1, 1024, 0, (cudaStream_t)stream)(in, n, scale, accumulate, out);
     DMH_CHECK_LAUNCH("dmh_reduce_sum");
+    return DMH_OK;
+}
+
+int dmh_reduce_rows(const float* in, int rows, long long n, float scale, float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(in && out && n > 0 && rows > 0 && rows <= 65535, "dmh_reduce_rows: null pointer or bad shape");
+    DMH_LAUNCH(reduce_sum_kernel, rows, 1024, 0, (cudaStream_t)stream)(in, n, scale, 0, out);
+    DMH_CHECK_LAUNCH("dmh_reduce_rows");
     return DMH_OK;
 }
 

@@ -202,8 +202,7 @@ class _ObjectiveDH(torch.autograd.Function):
                                          ptr(noises[s]), ptr(hr), ptr(hd), ptr(hv), B, H, W, min_depth, max_depth, flags,
                                          ptr(part), ptr(g_r), ptr(g_h), ptr(gP), ptr(sel), stream()), "photo_scale_dh")
             sm = torch.empty(4, device=dev, dtype=torch.float32)
-            for q in range(4 if hr is not None else 2):
-                check(lib.dmh_reduce_sum(ptr(part[q]), nblk, 1.0, 0, ptr(sm[q:q + 1]), stream()), "reduce_sum")
+            check(lib.dmh_reduce_rows(ptr(part), 4 if hr is not None else 2, nblk, 1.0, ptr(sm), stream()), "reduce_rows")
             ws = torch.empty(lib.dmh_smooth_fused_workspace_floats(B, h, w), device=dev, dtype=torch.float32)
             gn = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
             check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, h, w, ptr(ws), ptr(gn), stream()), "smooth_fused")

@@ -330,6 +330,9 @@ int dmh_axpby_dev(const float* a, const float* x, const float* b, const float* y
 /* deterministic fixed-order sum of n floats into out[0] (double accumulate),
  * out[0] = scale * sum (+ out[0] if accumulate)                                */
 int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, float* out, dmh_stream_t stream);
+/* the same for every row of a (rows, n) array in one launch: out[r] = scale * sum(in[r, :])  (the four masked sums
+ * of the depth-hints objective, DH/trainer.py:699-713) */
+int dmh_reduce_rows(const float* in, int rows, long long n, float scale, float* out, dmh_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
