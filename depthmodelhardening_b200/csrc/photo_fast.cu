@@ -379,16 +379,19 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
     const uint8_t* gate = sm.gate;
     float h_dv[4], h_hd[4], h_va[4];
     if (DH && p.hint_reproj) {
-        // requested up front: their latency hides behind the box sums
+        // only where the hint won (bit 1 of the gate byte); requested up front: the latency hides behind the box sums
         const float* dp = p.disp.ptr + (size_t)b * (p.disp.h * p.disp.w);
         const int hx = min(x0 + oc, W - 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int hy = min(y0 + 4 * os + k, H - 1);
-            h_dv[k] = UP ? up_sample(dp, p.disp.w, up_tap(hy, p.disp.sh, p.disp.h), up_tap(hx, p.disp.sw, p.disp.w))
-                         : __ldg(dp + hy * W + hx);
-            h_hd[k] = __ldg(p.hint_depth + (size_t)b * N + hy * W + hx);
-            h_va[k] = __ldg(p.hint_valid + (size_t)b * N + hy * W + hx);
+            h_dv[k] = 0.f; h_hd[k] = 0.f; h_va[k] = 0.f;
+            if (gate[(4 * os + k + 1) * FT_R1 + oc + 1] & 2) {
+                h_dv[k] = UP ? up_sample(dp, p.disp.w, up_tap(hy, p.disp.sh, p.disp.h), up_tap(hx, p.disp.sw, p.disp.w))
+                             : __ldg(dp + hy * W + hx);
+                h_hd[k] = __ldg(p.hint_depth + (size_t)b * N + hy * W + hx);
+                h_va[k] = __ldg(p.hint_valid + (size_t)b * N + hy * W + hx);
+            }
         }
     }
     {
@@ -446,14 +449,17 @@ __device__ __forceinline__ void phase_c(const FastParams& p, const TileSmem& sm,
                 g = fmaf(gpS, D[k][2], g);
                 if (py < H && px < W) gout[py * W] = g;
                 if (DH && p.hint_reproj && py < H && px < W) {
-                    const float m_h = (gate[(r + 1) * FT_R1 + oc + 1] & 2) ? 1.0f : 0.0f;
-                    const float depth = disp_to_depth(h_dv[k], p.ds);
-                    const float diff = sub_rn(h_hd[k], depth);
-                    const float a1 = add_rn(fabsf(diff), 1.0f);
-                    acc[2] += mul_rn(mul_rn(logf(a1), h_va[k]), m_h);
-                    acc[3] += m_h;
-                    const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
-                    p.grad_hint[(size_t)b * N + py * W + px] = m_h * h_va[k] * sg / a1 * ddepth_ddisp(depth, p.ds);
+                    float gh = 0.0f;
+                    if (gate[(r + 1) * FT_R1 + oc + 1] & 2) {            // the hint won here
+                        const float depth = disp_to_depth(h_dv[k], p.ds);
+                        const float diff = sub_rn(h_hd[k], depth);
+                        const float a1 = add_rn(fabsf(diff), 1.0f);
+                        acc[2] += mul_rn(logf(a1), h_va[k]);
+                        acc[3] += 1.0f;
+                        const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
+                        gh = h_va[k] * sg / a1 * ddepth_ddisp(depth, p.ds);
+                    }
+                    p.grad_hint[(size_t)b * N + py * W + px] = gh;
                 }
             }
 #pragma unroll
