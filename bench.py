@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-u8", action="store_true",
+                    help="skip the additional (informational) end-to-end measurement with 8-bit frame transport")
     ap.add_argument("--no-e2e-bf16", action="store_true",
                     help="skip the additional (informational) end-to-end measurement with bf16 frame transport")
     ap.add_argument("--no-patch", action="store_true", help="skip stage 1 (debug)")
@@ -376,7 +378,10 @@ def main():
     def measure_e2e(frame_dtype):
         from depthmodelhardening_b200 import objective
         pin = lambda t: t.pin_memory()
-        cast = (lambda t: t.to(frame_dtype)) if frame_dtype != torch.float32 else (lambda t: t)
+        if frame_dtype == torch.uint8:
+            cast = lambda t: (t * 255.0).round().clamp_(0, 255).to(torch.uint8)
+        else:
+            cast = (lambda t: t.to(frame_dtype)) if frame_dtype != torch.float32 else (lambda t: t)
         host = {("color",) + k: pin(cast(v)) for k, v in pb_host.color.items()}
         host.update({("disp", k): pin(v) for k, v in pb_host.disp.items()})
         host[("K",)] = pin(pb_host.K)
@@ -396,6 +401,11 @@ def main():
             for k in sl:
                 if k[0] == "disp":
                     sl[k].requires_grad_(True)
+        f32buf = {}
+        if frame_dtype == torch.uint8:
+            from depthmodelhardening_b200.staging import unpack_u8
+            f32buf = {k: torch.empty(v.shape, dtype=torch.float32, device=device) for k, v in host.items()
+                      if v.dtype == torch.uint8}
         copy_stream = torch.cuda.Stream(device=device)
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
@@ -409,6 +419,11 @@ def main():
         def compute(slot):
             sl = slots[slot]
             torch.cuda.current_stream().wait_event(ready[slot])
+            if frame_dtype == torch.uint8:
+                # bytes -> k/255 fp32 on the device (dmh_unpack_u8: the loaders' to_tensor arithmetic, bit for bit)
+                sl = dict(sl)
+                for k, buf in f32buf.items():
+                    sl[k] = unpack_u8(sl[k], out=buf)
             color = {k[1:]: v for k, v in sl.items() if k[0] == "color"}
             disps = {k[1]: v for k, v in sl.items() if k[0] == "disp"}
             T = {k[1]: v for k, v in sl.items() if k[0] == "T"}
@@ -453,10 +468,16 @@ def main():
                        "stream, double-buffered against the previous step's compute; tie-break noise drawn on the device; loss read back every step"}
 
 
-    e2e = e2e_bf16 = None
+    e2e = e2e_bf16 = e2e_u8 = None
     if not args.no_e2e:
         scenes_f32 = s1.g.scenes if s1 is not None else None
         e2e = measure_e2e(torch.float32)
+        if not args.no_e2e_u8:
+            e2e_u8 = measure_e2e(torch.uint8)
+            e2e_u8["note"] = ("OPTION, not the headline: colour frames, pyramid and scenes travel as the 8-bit images the "
+                              "reference's loaders decode (a quarter of the bytes) and become k/255 fp32 on the device "
+                              "(dmh_unpack_u8, IEEE division == torchvision to_tensor bit for bit): lossless for 8-bit "
+                              "sources; the synthetic frames are quantised to k/255 for this measurement")
         if not args.no_e2e_bf16:
             e2e_bf16 = measure_e2e(torch.bfloat16)
             e2e_bf16["note"] = ("OPTION, not the headline: colour frames, pyramid and scenes travel as bf16 (half the "
@@ -504,6 +525,8 @@ def main():
         line["e2e"] = e2e
     if e2e_bf16 is not None:
         line["e2e_bf16_frames"] = e2e_bf16
+    if e2e_u8 is not None:
+        line["e2e_u8_frames"] = e2e_u8
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None, attack=args.attack)
     if world > 1:

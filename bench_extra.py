@@ -10,7 +10,11 @@ SURVEY.md section 8 timed on one GPU with CUDA events, inputs resident in HBM, o
             PyTorch random-init ResNet-18 monodepth2-style depth network in the loop (the network is outside
             the graft), Ba=32 scenes of 375x1242: PGD iterations per second end to end on the device
 
-usage: python bench_extra.py [--steps K] [--warmup W] [--only dh,md_f2,costvol]
+  compose   training-batch compositing on the device (next-2): B=32 raw 8-bit 1242x375 stereo pairs -> composited
+            adversarial / benign frames -> Pillow-exact Lanczos pyramids -> fp32 (loader.AdvBatchComposer); the
+            installed Pillow resizing the same pyramids on one host core is timed beside it
+
+usage: python bench_extra.py [--steps K] [--warmup W] [--only dh,md_f2,costvol,compose]
 """
 import argparse
 import json
@@ -47,7 +51,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="cfg1,dh,md_f2,costvol,attack")
+    ap.add_argument("--only", default="cfg1,dh,md_f2,costvol,compose,attack")
     args = ap.parse_args()
     from depthmodelhardening_b200 import _lib, synth
     lib = _lib.load()
@@ -139,6 +143,9 @@ def main():
                           "note": "gather-bound: taps_gbs = bytes requested from L1/L2 by the bilinear taps"}))
 
 
+    if "compose" in want:
+        compose_bench(dev, args, lib)
+
     if "attack" in want:
         attack_context(dev, args)
 
@@ -170,6 +177,65 @@ class _DepthNetR18(torch.nn.Module):
                 y = torch.cat([y, feats[i - 1]], 1)
             y = self.up1[i](y)
         return torch.sigmoid(self.head(y))
+
+
+def _write_calib():
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="dmh_calib_")
+    os.makedirs(os.path.join(tmp, "training", "calib"))
+    path = os.path.join(tmp, "training", "calib", "003086.txt")
+    with open(path, "w") as f:
+        p2 = " ".join(repr(v) for v in __import__("depthmodelhardening_b200.patch_ops", fromlist=["x"]).KITTI_P2_003086)
+        for k in ("P0", "P1", "P2", "P3"):
+            f.write("%s: %s\n" % (k, p2))
+        f.write("R0_rect: 1 0 0 0 1 0 0 0 1\nTr_velo_to_cam: 1 0 0 0 0 1 0 0 0 0 1 0\nTr_imu_to_velo: 1 0 0 0 0 1 0 0 0 0 1 0\n")
+    return tmp, path
+
+
+def compose_bench(dev, args, lib):
+    """next-2: MonoDataset.prep_adv_data + preprocess for a collated batch on the device."""
+    import time
+    import numpy as np
+    from depthmodelhardening_b200 import loader, synth
+    B, H, W, S = 32, 320, 1024, 4
+    _, calib = _write_calib()
+    pt = synth.patch_batch(batch=1, seed=3).to(dev)
+    comp = loader.AdvBatchComposer(pt.obj, pt.mask, {"path": calib}, H, W, S)
+    comp.update_adv_obj(synth.rand(tuple(pt.obj.shape), 78).to(dev))
+    c0 = synth.frames_u8(41, batch=B).to(dev)
+    cs = synth.frames_u8(42, batch=B).to(dev)
+    sides = ["l" if i % 2 == 0 else "r" for i in range(B)]
+    flips = [(i // 2) % 2 == 1 for i in range(B)]
+    z0 = [5.0 + 0.125 * i for i in range(B)]
+    al = [-30.0 + 1.875 * i for i in range(B)]
+    fn = lambda: comp(c0, cs, sides, flips, z0, al)
+    n0 = lib.dmh_launch_count()
+    fn()
+    launches = lib.dmh_launch_count() - n0
+    ms = timed(fn, args.steps, args.warmup)
+    pyr = lambda: [loader.pyramid_u8(x, H, W, S) for x in (c0, cs, c0)]
+    ms_pyr = timed(pyr, args.steps, args.warmup)
+    # the same three pyramids per item with the installed Pillow on one host core (what a DataLoader worker does)
+    from PIL import Image
+    host = np.ascontiguousarray(np.transpose(c0[0].cpu().numpy(), (1, 2, 0)))
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps * 3):
+        im = Image.fromarray(host)
+        for i in range(S):
+            im = im.resize((W >> i, H >> i), Image.LANCZOS)
+    cpu_ms_item = (time.perf_counter() - t0) / reps * 1e3
+    # bytes: 2 raw frames in, 3 composites out/in, 3 pyramids (u8 + fp32) out, 5 warped canvases (fp32) out + in
+    px, pyr_px = 375 * 1242, sum((H >> i) * (W >> i) for i in range(S))
+    bytes_item = 3 * px * (2 + 3 * 2) + 3 * 3 * pyr_px * (1 + 4) + 2 * 4 * px * (3 * 3 + 2)
+    print(json.dumps({"workload": "training-batch compositing on the device (next-2: prep_adv_data + preprocess)",
+                      "B": B, "native": [375, 1242], "H": H, "W": W, "scales": S, "ms_per_batch": ms,
+                      "items_per_s": B / (ms * 1e-3), "pyramids_only_ms": ms_pyr, "gpu_launches_per_batch": int(launches),
+                      "approx_bytes_per_batch": bytes_item * B, "approx_gbs": bytes_item * B / (ms * 1e-3) / 1e9,
+                      "cpu_pillow_pyramids_ms_per_item": cpu_ms_item, "cpu_cores": 1,
+                      "note": "GPU: 5 batched perspective launches, 4 composites, 13 Lanczos resizes (2 passes each), "
+                              "13 unpacks; CPU figure: only the three 4-level Pillow pyramids of one item on one core "
+                              "(the reference additionally warps and composites on the CPU, ~1 s per item)"}))
 
 
 def attack_context(dev, args):

@@ -55,6 +55,26 @@ bool const_div_exact(int c, float* rc_out) {
     return ok;
 }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- 8-bit frame transport: torchvision's to_tensor (`img.to(float32).div(255)`) on the device.  IEEE division:
+// the k/255 the reference's loaders produce, bit for bit (a multiplication by 1/255 differs in the last place for
+// about a third of the 256 values).  16 bytes in, 4 x 128-bit stores out per thread; HBM-bound (5 B per element).
+__global__ void __launch_bounds__(256) unpack_u8_kernel(const uint8_t* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long nv = n >> 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(in) + i);
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o[j] = make_float4(div_rn((float)(w[j] & 0xffu), 255.0f), div_rn((float)((w[j] >> 8) & 0xffu), 255.0f),
+                               div_rn((float)((w[j] >> 16) & 0xffu), 255.0f), div_rn((float)(w[j] >> 24), 255.0f));
+    }
+    // tail (n % 16 elements) by the first threads of the grid
+    const long long t = (nv << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = div_rn((float)in[t], 255.0f);
+}
 }  // namespace dmh
 
 extern "C" {
@@ -65,5 +85,18 @@ int dmh_build_arch(void) { return 100; }
 int dmh_const_div_exact(int c) {
     float rc;
     return dmh::const_div_exact(c, &rc) ? 1 : 0;
+}
+int dmh_unpack_u8(const uint8_t* in, long long n, float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(in && out, "dmh_unpack_u8: null pointer");
+    DMH_REQUIRE(n >= 0, "dmh_unpack_u8: negative size");
+    DMH_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "dmh_unpack_u8: buffers must be 16-byte aligned");
+    if (n == 0) return DMH_OK;
+    const long long nv = n >> 4;
+    long long blocks = (nv + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;          // grid-stride over 16 CTAs per SM
+    if (blocks < 1) blocks = 1;
+    DMH_LAUNCH(dmh::unpack_u8_kernel, (int)blocks, 256, 0, (cudaStream_t)stream)(in, n, out);
+    DMH_CHECK_LAUNCH("dmh_unpack_u8");
+    return DMH_OK;
 }
 }

@@ -1,0 +1,236 @@
+"""Training-batch compositing on the GPU.
+
+The reference builds every adversarial training item inside its DataLoader workers, on the CPU
+(`DepthNetworks/monodepth2/datasets/mono_dataset.py`):
+
+  prep_adv_data (:186-265)  to_tensor(frame) -> PhysicalTrans.project / project_w_trans of the adversarial and the
+                            benign patch -> optional flip -> scene*(1-m) + obj*m -> to_pilimage (8-bit again)
+  preprocess    (:119-144)  4-level pyramid, level i resized from level i-1 with PIL ANTIALIAS (Lanczos), to_tensor
+
+`AdvBatchComposer` does the same for a whole collated batch of raw 8-bit frames that is already on the device:
+one batched perspective launch per warped tensor (`physical.PhysicalTrans`), `dmh_compose_u8`, `dmh_lanczos_u8`
+(Pillow's fixed-point resampling, bit-exact) and `dmh_unpack_u8` (to_tensor).  It is a *host-code change* for a
+maintainer (a post-collate hook instead of `prep_adv_data`), which is why it sits outside
+`install()`.  There is no CPU path: tensors must be CUDA tensors.
+
+Not mirrored: the colour jitter (`color_aug`; off in the reference's adversarial configuration,
+`mono_dataset.py:301`, `adv_args['color_aug']`) and `half_no_synthesis`.
+"""
+from __future__ import annotations
+
+import math
+from random import sample
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, patch_ops
+from .physical import PhysicalTrans
+from .staging import unpack_u8
+
+_PRECISION_BITS = 32 - 8 - 2          # Resample.c: PRECISION_BITS
+_coeff_cache: Dict = {}
+
+
+def _lanczos(x: float) -> float:
+    def sinc(v):
+        if v == 0.0:
+            return 1.0
+        v *= math.pi
+        return math.sin(v) / v
+    return sinc(x) * sinc(x / 3) if -3.0 <= x < 3.0 else 0.0
+
+
+def lanczos_coefficients(in_size: int, out_size: int):
+    """Pillow's `precompute_coeffs` + `normalize_coeffs_8bpc` for the Lanczos filter (support 3) over the whole axis:
+    (bounds int32 [out, 2] = (first input index, tap count), weights int32 [out, ksize]).  Double precision with the
+    C library's sin (math.sin) and Pillow's summation order, so the integers are Pillow's."""
+    scale = in_size / out_size
+    fscale = scale if scale > 1.0 else 1.0
+    support = 3.0 * fscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    inv = 1.0 / fscale
+    one = float(1 << _PRECISION_BITS)
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = max(int(center - support + 0.5), 0)
+        n = min(int(center + support + 0.5), in_size) - lo
+        ws = [_lanczos((j + lo - center + 0.5) * inv) for j in range(n)]
+        total = 0.0
+        for w in ws:
+            total += w
+        for j, w in enumerate(ws):
+            if total != 0.0:
+                w = w / total
+            kk[o, j] = int(w * one - 0.5) if w < 0 else int(w * one + 0.5)
+        bounds[o, 0], bounds[o, 1] = lo, n
+    return bounds, kk
+
+
+def _device_coefficients(in_size: int, out_size: int, device):
+    key = (in_size, out_size, str(device))
+    hit = _coeff_cache.get(key)
+    if hit is None:
+        b, k = lanczos_coefficients(in_size, out_size)
+        hit = (torch.from_numpy(b).to(device), torch.from_numpy(k).to(device), k.shape[1])
+        _coeff_cache[key] = hit
+    return hit
+
+
+def _need_u8_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("dmh_b200: %s is on %s; the compositing path is CUDA-only (no CPU fallback)" % (what, t.device))
+    if t.dtype != torch.uint8:
+        raise RuntimeError("%s: expected uint8, got %s" % (what, t.dtype))
+    return t.contiguous()
+
+
+def resize_lanczos_u8(img: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """uint8 CUDA tensor [..., H, W] -> [..., out_h, out_w]; == `PIL.Image.resize((out_w, out_h), LANCZOS)` plane by
+    plane, bit for bit (`transforms.Resize(..., interpolation=Image.ANTIALIAS)`, mono_dataset.py:100-104)."""
+    img = _need_u8_cuda(img, "resize_lanczos_u8 input")
+    H, W = img.shape[-2:]
+    planes = img.numel() // max(H * W, 1)
+    if planes == 0 or H == 0 or W == 0 or out_h <= 0 or out_w <= 0:
+        raise RuntimeError("resize_lanczos_u8: empty image (%s -> %dx%d)" % (tuple(img.shape), out_h, out_w))
+    lib = _lib.load()
+    out = torch.empty(img.shape[:-2] + (out_h, out_w), dtype=torch.uint8, device=img.device)
+    bx = kx = by = ky = None
+    nx = ny = 0
+    if out_w != W:
+        bx, kx, nx = _device_coefficients(W, out_w, img.device)
+    if out_h != H:
+        by, ky, ny = _device_coefficients(H, out_h, img.device)
+    tmp = torch.empty((planes, H, out_w), dtype=torch.uint8, device=img.device) if (nx and ny) else None
+    _lib.check(lib.dmh_lanczos_u8(_lib.ptr(img), planes, H, W, out_h, out_w, _lib.ptr(bx), _lib.ptr(kx), nx,
+                                  _lib.ptr(by), _lib.ptr(ky), ny, _lib.ptr(tmp), _lib.ptr(out), _lib.stream()),
+               "lanczos_u8")
+    return out
+
+
+def pyramid_u8(img: torch.Tensor, height: int, width: int, num_scales: int = 4):
+    """MonoDataset.preprocess (mono_dataset.py:126-131): level i = Resize(height // 2^i, width // 2^i) of level i-1
+    (level -1 = the native-resolution image); 8-bit levels."""
+    out, cur = [], img
+    for i in range(num_scales):
+        cur = resize_lanczos_u8(cur, height // (2 ** i), width // (2 ** i))
+        out.append(cur)
+    return out
+
+
+def compose_u8(scene: Optional[torch.Tensor], obj: torch.Tensor, mask: Optional[torch.Tensor],
+               flip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """to_pilimage(to_tensor(scene) * (1 - mask) + obj * mask) as 8-bit planes (mono_dataset.py:229-236); `flip`
+    (B,) int32: items whose warped patch and mask are mirrored first (:226-228).  scene None: to_pilimage(obj)."""
+    lib = _lib.load()
+    obj = _lib.f32c(obj)
+    B, C, H, W = obj.shape
+    if scene is not None:
+        scene = _need_u8_cuda(scene, "compose_u8 scene")
+        if tuple(scene.shape) != (B, C, H, W):
+            raise RuntimeError("compose_u8: scene %s does not match the warped patch %s" % (tuple(scene.shape), (B, C, H, W)))
+        if mask is None:
+            raise RuntimeError("compose_u8: a scene needs a mask")
+    if mask is not None:
+        mask = _lib.f32c(mask)
+        if tuple(mask.shape) != (B, 1, H, W):
+            raise RuntimeError("compose_u8: mask must be (B,1,H,W)")
+    if flip is not None:
+        flip = flip.to(device=obj.device, dtype=torch.int32).contiguous()
+        if flip.numel() != B:
+            raise RuntimeError("compose_u8: one flip flag per item")
+    out = torch.empty((B, C, H, W), dtype=torch.uint8, device=obj.device)
+    _lib.check(lib.dmh_compose_u8(_lib.ptr(scene), _lib.ptr(obj), _lib.ptr(mask), _lib.ptr(flip), B, C, H, W,
+                                  _lib.ptr(out), _lib.stream()), "compose_u8")
+    return out
+
+
+class AdvBatchComposer:
+    """`MonoDataset.set_adv_train` / `update_adv_obj` / `prep_adv_data` / `preprocess` for a collated batch on the
+    device (mono_dataset.py:146-265, 119-144).
+
+    obj_tensor / mask_tensor: the benign patch (1,3,h,w) and its mask (1,1,h,w), CUDA; cfg: {'path': calib file};
+    height, width: network input size (scale 0); dist_range as `train_dist_range`."""
+
+    def __init__(self, obj_tensor, mask_tensor, cfg, height, width, num_scales=4, dist_range=list(range(5, 10, 2)),
+                 ori_H=patch_ops.ORI_H, ori_W=patch_ops.ORI_W):
+        self.height, self.width, self.num_scales = height, width, num_scales
+        self.ori_H, self.ori_W = ori_H, ori_W
+        self.obj_mask = mask_tensor
+        self.obj_img_ben = obj_tensor
+        self.obj_img_adv = obj_tensor.clone()
+        size = (1, 3, ori_H, ori_W)
+        self.ben_trans = PhysicalTrans(self.obj_img_ben, self.obj_mask, cfg, size, dist_range=dist_range)
+        self.adv_trans = PhysicalTrans(self.obj_img_adv, self.obj_mask, cfg, size, dist_range=dist_range)
+        # mono_dataset.py:169-175, 111-116
+        self.adv_K = np.array([[0.58, 0, 0.5, 0], [0, 1.92, 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+        self.adv_K[0, :] *= ori_W
+        self.adv_K[1, :] *= ori_H
+        self.stereo_T = np.eye(4, dtype=np.float32)
+        self.stereo_T[0, 3] = -0.54
+
+    def update_adv_obj(self, obj_img_adv: torch.Tensor) -> None:
+        """mono_dataset.py:178-184 with the attack's result handed in (the attack itself is `attacks.Phy_obj_atk*`)."""
+        self.obj_img_adv = obj_img_adv
+        self.adv_trans.reset_img(self.obj_img_adv, self.obj_mask)
+
+    def _placement(self, trans: PhysicalTrans, z0, alpha, with_T):
+        ends = np.stack([patch_ops.project_corners(z, a, trans.P, self.adv_K, self.stereo_T if t else None)
+                         for z, a, t in zip(z0, alpha, with_T)])
+        _, _, h, w = trans.obj_img.size()
+        return patch_ops.make_placement(trans.pos_obj_img_start, ends, (h, w), (self.ori_H, self.ori_W)).to(
+            trans.obj_img.device)
+
+    def __call__(self, color_0: torch.Tensor, color_s: torch.Tensor, sides: Sequence[str], do_flip: Sequence[bool],
+                 z0_sample: Optional[Sequence[float]] = None, alpha_sample: Optional[Sequence[float]] = None):
+        """color_0 / color_s: (B,3,ori_H,ori_W) uint8 CUDA -- frame 0 and its stereo partner at native resolution, as
+        `get_color` returns them (already mirrored for the items with do_flip, mono_dataset.py:325-329); sides[i]:
+        'l' / 'r', the side frame 0 of item i was taken from; do_flip[i]: mirror the warped patch too (:226-228);
+        z0_sample / alpha_sample: one placement per item (drawn like `PhysicalTrans.project` if None).
+
+        Returns the dictionary entries `prep_adv_data` + `preprocess` produce, as fp32 CUDA tensors:
+        ("color_aug", 0 | "s", 0..S-1), ("color", 0 | "s", 0..S-1), ("color_ben", 0, 0), ("color_objmask", 0, 0),
+        ("objdepth", 0, 0)."""
+        color_0 = _need_u8_cuda(color_0, "color_0")
+        color_s = _need_u8_cuda(color_s, "color_s")
+        B = color_0.shape[0]
+        if tuple(color_0.shape) != (B, 3, self.ori_H, self.ori_W) or color_s.shape != color_0.shape:
+            raise RuntimeError("AdvBatchComposer: frames must be (B,3,%d,%d) uint8" % (self.ori_H, self.ori_W))
+        if len(sides) != B or len(do_flip) != B:
+            raise RuntimeError("Batch size doesn't match!")
+        if z0_sample is None:
+            z0_sample = [sample(self.ben_trans.dist_range, 1)[0] for _ in range(B)]
+        if alpha_sample is None:
+            alpha_sample = [sample(self.ben_trans.angle_range, 1)[0] for _ in range(B)]
+        right = [s != "l" for s in sides]
+        # frame 0 sees the placement of its own camera: left camera (project) for side 'l', right camera
+        # (project_w_trans with stereo_T) for side 'r'; the stereo partner sees the other one (:207-223)
+        place_0 = self._placement(self.ben_trans, z0_sample, alpha_sample, right)
+        place_s = self._placement(self.ben_trans, z0_sample, alpha_sample, [not r for r in right])
+        hw = (self.ori_H, self.ori_W)
+        mask_0 = patch_ops.perspective_batch(self.obj_mask, place_0, hw)
+        mask_s = patch_ops.perspective_batch(self.obj_mask, place_s, hw)
+        adv_0 = patch_ops.perspective_batch(self.obj_img_adv, place_0, hw)
+        ben_0 = patch_ops.perspective_batch(self.obj_img_ben, place_0, hw)
+        ben_s = patch_ops.perspective_batch(self.obj_img_ben, place_s, hw)
+        flip = torch.tensor([1 if f else 0 for f in do_flip], dtype=torch.int32, device=color_0.device)
+        with torch.no_grad():
+            aug_0 = compose_u8(color_0, adv_0, mask_0, flip)          # the adversarial current frame
+            aug_s = compose_u8(color_s, ben_s, mask_s, flip)          # its benign stereo partner
+            ben = compose_u8(color_0, ben_0, mask_0, flip)            # the benign current frame (:239-251)
+            objmask = compose_u8(None, mask_0.expand(-1, 3, -1, -1).contiguous(), None, flip)   # (:254)
+            out = {}
+            S = self.num_scales
+            for name, fid, img in (("color_aug", 0, aug_0), ("color_aug", "s", aug_s), ("color", 0, ben)):
+                for i, lvl in enumerate(pyramid_u8(img, self.height, self.width, S)):
+                    out[(name, fid, i)] = unpack_u8(lvl)
+            for i in range(S):                                        # :257: color['s'] is color_aug['s']
+                out[("color", "s", i)] = out[("color_aug", "s", i)]
+            out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
+            out[("color_objmask", 0, 0)] = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
+            out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
+                                                   device=color_0.device)
+        return out

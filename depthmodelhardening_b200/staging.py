@@ -47,3 +47,26 @@ class BatchArena:
         else:
             with torch.cuda.stream(stream):
                 self.dev[slot].copy_(self.host, non_blocking=True)
+
+
+def unpack_u8(src: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """uint8 CUDA tensor -> fp32 `src / 255` (IEEE division: torchvision `to_tensor`, the conversion every colour
+    frame of the reference goes through in its loaders, `mono_dataset.py:79,133-144`) by `dmh_unpack_u8`.
+
+    Lets a batch cross PCIe as bytes -- a quarter of the fp32 volume -- and arrive bit-identical to the fp32 tensors
+    the reference's DataLoader would have produced from the same 8-bit images.  `out`: optional preallocated fp32
+    tensor of the same shape (16-byte aligned, as torch allocations and `BatchArena` slots are)."""
+    from . import _lib
+    if src.dtype != torch.uint8:
+        raise RuntimeError("unpack_u8: expected a uint8 tensor, got %s" % src.dtype)
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    elif out.shape != src.shape or out.dtype != torch.float32:
+        raise RuntimeError("unpack_u8: `out` must be fp32 of shape %s" % (tuple(src.shape),))
+    if src.numel() == 0:
+        if not src.is_cuda:
+            raise RuntimeError("dmh_b200: tensor is on %s; the hot path is CUDA-only (no CPU fallback)" % src.device)
+        return out
+    _lib.check(lib.dmh_unpack_u8(_lib.ptr(src), src.numel(), _lib.ptr(out), _lib.stream()), "unpack_u8")
+    return out

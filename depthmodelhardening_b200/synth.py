@@ -199,6 +199,13 @@ def patch_batch(batch=4, seed=0, scene_kind="smooth") -> PatchBatch:
     return PatchBatch(batch, obj, mask, scenes, z0, alpha, upstream, ppos, pneg)
 
 
+def frames_u8(seed: int, batch: int = 1) -> torch.Tensor:
+    """Seeded native-resolution 8-bit frames (batch,3,375,1242): smooth field + noise, quantised -- the raw images
+    a KITTI loader decodes (inputs of the training-batch compositing, loader.py)."""
+    f = smooth_field((batch, 3, ORI_H, ORI_W), seed)
+    return (f * 255.0).round().clamp(0, 255).to(torch.uint8)
+
+
 def cost_volume_inputs(B=2, L=2, C=16, h=24, w=40, D=12, seed=80):
     """Seeded matching-resolution inputs: smooth non-negative features (post-ReLU), small temporal poses,
     item 1's second lookup frame missing (all-zero pose), KITTI intrinsics at (h, w), linear depth bins."""

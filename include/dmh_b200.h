@@ -323,6 +323,37 @@ int dmh_cost_volume(const float* current_feats, const float* lookup_feats, const
  * launches a small kernel and synchronises, then cached).  0: the kernels use IEEE division for that size. */
 int dmh_const_div_exact(int c);
 
+/* -- training-batch compositing on the device ------------------------------------------
+ * The byte work of MonoDataset.prep_adv_data + preprocess (DepthNetworks/monodepth2/datasets/mono_dataset.py:
+ * 186-265, 119-144), which the reference runs per item inside DataLoader workers on the CPU.
+ *
+ * dmh_compose_u8: out = (uint8) trunc(255 * (scene/255 * (1 - mask) + obj * mask)) -- to_tensor, the composite
+ * (:229-230, 246-249) and to_pilimage (`.mul(255).byte()`, :235-236, 251) in one pass; every fp32 operation
+ * rounded as torch's CPU kernels round it.  scene (B,C,H,W) u8, obj (B,C,H,W) f32 (the warped patch, from
+ * dmh_perspective_fwd), mask (B,1,H,W) f32, flip (B) int32 or NULL: items whose warped patch / mask are mirrored
+ * horizontally first (torch.flip(..., [3]), :226-228).  scene == NULL: out = trunc(255 * obj) (the `color_objmask`
+ * image, :254; mask may be NULL). */
+int dmh_compose_u8(const uint8_t* scene, const float* obj, const float* mask, const int* flip, int B, int C, int H,
+                   int W, uint8_t* out, dmh_stream_t stream);
+
+/* dmh_lanczos_u8: `transforms.Resize((h, w), interpolation=Image.ANTIALIAS)` on 8-bit PIL images (:71, 100-104,
+ * 126-131) == Pillow's fixed-point Lanczos resampling (libImaging/Resample.c), bit-exact: horizontal pass, then
+ * vertical pass, each with 22-bit integer weights, rounded and clipped to 8 bits.  in (planes, in_h, in_w) ->
+ * out (planes, out_h, out_w).  bounds_* (out, 2) int32 = (first input index, tap count), kk_* (out, ksize) int32
+ * weights: host-computed in double precision as Pillow does (depthmodelhardening_b200/loader.py
+ * lanczos_coefficients); an axis that keeps its size is skipped and needs no tables.  tmp: (planes, in_h, out_w)
+ * bytes, needed when both axes change. */
+int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h, int out_w, const int* bounds_x,
+                   const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp,
+                   uint8_t* out, dmh_stream_t stream);
+
+/* 8-bit frame transport (data format either side of the path): out[i] = (float)in[i] / 255 with IEEE division --
+ * torchvision's `to_tensor` (`pic.to(float32).div(255)`), the conversion every colour frame of the reference goes
+ * through in its loaders (DepthNetworks/monodepth2/datasets/mono_dataset.py:79, 133-144; composited frames are
+ * re-quantised by to_pilimage first, :235-236) -- done on the device, so that a batch
+ * can cross PCIe as bytes (a quarter of the fp32 volume) and still arrive bit-identical.  in/out 16-byte aligned. */
+int dmh_unpack_u8(const uint8_t* in, long long n, float* out, dmh_stream_t stream);
+
 /* out[i] = a[0] * x[i] + b[0] * y[i] with DEVICE scalars a, b (no host sync); out may alias x or y. */
 int dmh_axpby_dev(const float* a, const float* x, const float* b, const float* y, long long n, float* out,
                   dmh_stream_t stream);

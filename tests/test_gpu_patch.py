@@ -330,6 +330,34 @@ def test_batch_arena_roundtrip(dev):
         assert v.data_ptr() % 256 == 0
 
 
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 256 * 3 + 5, 2 * 3 * 37 * 53])
+def test_unpack_u8_is_to_tensor_bit_for_bit(dev, n):
+    """8-bit frame transport (staging.unpack_u8 / dmh_unpack_u8): the device conversion equals torchvision's
+    `to_tensor` arithmetic (`.to(float32).div(255)` on the CPU: IEEE division) bit for bit, for every byte value,
+    ragged sizes (tail of n % 16 elements) and through a BatchArena slot."""
+    from depthmodelhardening_b200.staging import BatchArena, unpack_u8
+    g = torch.Generator().manual_seed(5 + n)
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
+    if n >= 256:
+        src[:256] = torch.arange(256, dtype=torch.uint8)          # every value at least once
+    ref = src.to(torch.float32).div(255)
+    out = unpack_u8(src.to(dev))
+    assert out.dtype == torch.float32 and torch.equal(out.cpu(), ref)
+    if n == 2 * 3 * 37 * 53:
+        ex = {("color", 0, 0): src.view(2, 3, 37, 53), ("K",): torch.rand(2, 4, 4)}
+        arena = BatchArena(ex, dev, slots=1)
+        for k, v in arena.host_views().items():
+            v.copy_(ex[k])
+        arena.upload(0)
+        pre = torch.empty(2, 3, 37, 53, device=dev)
+        got = unpack_u8(arena.device_views(0)[("color", 0, 0)], out=pre)
+        assert got.data_ptr() == pre.data_ptr() and torch.equal(got.cpu(), ref.view(2, 3, 37, 53))
+    with pytest.raises(RuntimeError):
+        unpack_u8(torch.zeros(4, device=dev))                       # not uint8
+    with pytest.raises(RuntimeError):
+        unpack_u8(src)                                              # CPU tensor: no fallback
+
+
 @pytest.mark.parametrize("ev", [False, True])
 def test_vanila_attack_class_vs_reference_golden(dev, calib, ev):
     """Drop-in `Phy_obj_atk_vanila` (next-4: the placement-only attack of the evaluation harness) against the

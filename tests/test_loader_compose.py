@@ -1,0 +1,199 @@
+"""Training-batch compositing: `MonoDataset.prep_adv_data` + `preprocess`
+(DepthNetworks/monodepth2/datasets/mono_dataset.py:186-265, 119-144) on the device.
+
+Byte / integer work is compared BIT-EXACTLY: the Lanczos resize against the oracle restatement of Pillow's
+fixed-point resampling (itself pinned to the installed Pillow, the third-party owner of that arithmetic) and the
+composite + 8-bit quantisation on identical fp32 inputs.  End to end the only floating-point step is the
+perspective warp of the patch (<= 1e-5 relative between the CUDA kernel and torch's CPU grid_sample, tested in
+test_gpu_patch.py); a difference there can move a composited pixel across a truncation boundary, so the full
+pipeline is held to: identical outside the patch, <= 1 grey level on < 1 % of the bytes.
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from depthmodelhardening_b200 import synth
+from oracle import loader_compose as LC
+from oracle import pil_resize as R
+from oracle.refload import CALIB_P2, write_calib
+from tests.util import load_golden
+
+P34 = np.array(CALIB_P2, dtype=np.float64).reshape(3, 4)
+H, W, S = 320, 1024, 4
+# (side, do_flip, z0, alpha) -- the cases of oracle/make_golden_loader.py
+CASES = [("l", False, 7, -10), ("r", False, 5, 15), ("l", True, 9, 0), ("r", True, 7, 25)]
+SIZES = [(375, 1242, 320, 1024), (320, 1024, 160, 512), (160, 512, 80, 256), (80, 256, 40, 128),
+         (375, 1242, 192, 640), (100, 333, 37, 53), (64, 64, 64, 32), (50, 70, 25, 70), (33, 47, 90, 121),
+         (7, 5, 3, 2), (50, 70, 50, 70)]
+
+
+def crc(a):
+    return np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+
+
+def as_u8(t):
+    """fp32 k/255 tensor -> the bytes it came from (exact: to_tensor output)."""
+    u8 = (t.detach().cpu() * 255.0).round().to(torch.uint8)
+    assert torch.equal(u8.float().div(255), t.detach().cpu()), "not a to_tensor image (k/255)"
+    return u8.numpy()
+
+
+def patches():
+    pbt = synth.patch_batch(batch=1, seed=0)
+    return pbt.obj, synth.rand(pbt.obj.shape, 78), pbt.mask
+
+
+# ----------------------------------------------------------------------------- CPU: oracle pins, host logic
+@pytest.mark.parametrize("size", SIZES)
+def test_oracle_resize_equals_pillow(size):
+    """The oracle's restatement of Resample.c == the installed Pillow, bit for bit (random + saturated structure)."""
+    from PIL import Image
+    ih, iw, oh, ow = size
+    rng = np.random.default_rng(ih * 1000 + ow)
+    imgs = [rng.integers(0, 256, (3, ih, iw), dtype=np.uint8), np.zeros((3, ih, iw), np.uint8)]
+    imgs[1][:, ::7, :] = 255
+    imgs[1][:, :, ::5] = 255
+    for img in imgs:
+        pil = Image.fromarray(np.transpose(img, (1, 2, 0))).resize((ow, oh), Image.LANCZOS)
+        assert np.array_equal(R.resize_lanczos_u8(img, oh, ow), np.transpose(np.asarray(pil), (2, 0, 1)))
+
+
+@pytest.mark.parametrize("n", [(1242, 1024), (375, 320), (1024, 512), (320, 160), (333, 53), (47, 121), (5, 2)])
+def test_product_coefficients_equal_oracle(n):
+    """loader.lanczos_coefficients (host side of dmh_lanczos_u8) produces Pillow's integers."""
+    from depthmodelhardening_b200 import loader
+    b, k = loader.lanczos_coefficients(*n)
+    bo, ko = R.coefficients(*n)
+    assert b.dtype == np.int32 and k.dtype == np.int32
+    assert np.array_equal(b, bo) and np.array_equal(k, ko)
+    assert int(np.abs(k.astype(np.int64)).sum(1).max()) * 255 < 2 ** 31      # the kernels accumulate in int32
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_oracle_composer_matches_reference_golden(ci):
+    """oracle/loader_compose.prep_item == the unmodified MonoDataset.prep_adv_data + preprocess: CRC of every
+    pyramid level of every dictionary entry (tests/golden/loader_compose.npz, oracle/make_golden_loader.py)."""
+    g = load_golden("loader_compose")
+    side, flip, z0, alpha = CASES[ci]
+    ben, adv, mask = patches()
+    c0, cs = synth.frames_u8(1000 + 2 * ci)[0].numpy(), synth.frames_u8(1001 + 2 * ci)[0].numpy()
+    out = LC.prep_item(c0, cs, side, flip, z0, alpha, adv, ben, mask, P34, H, W, S)
+    n = 0
+    for k, v in out.items():
+        name = "c%d_%s_%s_%d" % ((ci,) + k)
+        if k[0] == "objdepth":
+            assert np.array_equal(v.numpy(), g["c%d_objdepth" % ci])
+            continue
+        u8 = as_u8(v)
+        assert int(u8.astype(np.int64).sum()) == int(g[name + "_sum"]), name
+        assert crc(u8) == g[name + "_crc"], name
+        n += 1
+    assert n == 4 * S + 2
+
+
+def test_composer_rejects_cpu_tensors():
+    from depthmodelhardening_b200 import loader
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        loader.resize_lanczos_u8(torch.zeros(3, 8, 8, dtype=torch.uint8), 4, 4)
+    with pytest.raises(RuntimeError):
+        loader.compose_u8(torch.zeros(1, 3, 8, 8, dtype=torch.uint8), torch.zeros(1, 3, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def dev():
+    from depthmodelhardening_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", SIZES)
+def test_cuda_resize_is_bit_exact(dev, size):
+    from depthmodelhardening_b200 import loader
+    ih, iw, oh, ow = size
+    rng = np.random.default_rng(ih + 7 * ow)
+    img = rng.integers(0, 256, (2, 3, ih, iw), dtype=np.uint8)
+    img[1, :, ::3, :] = 255
+    img[1, :, 1::3, :] = 0
+    out = loader.resize_lanczos_u8(torch.from_numpy(img).to(dev), oh, ow)
+    assert out.shape == (2, 3, oh, ow) and out.dtype == torch.uint8
+    assert np.array_equal(out.cpu().numpy(), R.resize_lanczos_u8(img, oh, ow))
+
+
+@pytest.mark.gpu
+def test_cuda_pyramid_full_batch_properties(dev):
+    """Full size (B=32 frames, the loader's four levels): every item equals the oracle on a sample of items,
+    a constant image stays constant (weights sum to 2^22 per output) and items do not leak into each other."""
+    from depthmodelhardening_b200 import loader
+    B = 32
+    frames = synth.frames_u8(77, batch=B)
+    lv = loader.pyramid_u8(frames.to(dev), H, W, S)
+    assert [tuple(l.shape) for l in lv] == [(B, 3, H >> i, W >> i) for i in range(S)]
+    for b in (0, 17, 31):
+        ref = R.pyramid_u8(frames[b].numpy(), H, W, S)
+        for i in range(S):
+            assert np.array_equal(lv[i][b].cpu().numpy(), ref[i]), (b, i)
+    const = torch.full((2, 3, 375, 1242), 201, dtype=torch.uint8, device=dev)
+    for l in loader.pyramid_u8(const, H, W, S):
+        assert int(l.min()) == 201 and int(l.max()) == 201
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flip", [False, True])
+def test_cuda_compose_is_bit_exact_on_identical_inputs(dev, flip):
+    """dmh_compose_u8 against torch's CPU arithmetic on the SAME fp32 warped patch / mask (the oracle's)."""
+    from depthmodelhardening_b200 import loader
+    ben, adv, mask = patches()
+    K = LC.adv_K()
+    z0, al = [5.0, 8.5, 9.0], [-25.0, 0.0, 30.0]
+    objw, maskw, _ = LC.OQ.project_patch(adv, mask, z0, al, P34, K=K, T=LC.STEREO_T)
+    scenes = synth.frames_u8(31, batch=3)
+    fl = [flip, not flip, flip]
+    ref = np.stack([LC.compose_u8(scenes[i].numpy(), objw[i:i + 1], maskw[i:i + 1], fl[i]) for i in range(3)])
+    out = loader.compose_u8(scenes.to(dev), objw.to(dev), maskw.to(dev),
+                            torch.tensor([int(f) for f in fl], dtype=torch.int32))
+    assert np.array_equal(out.cpu().numpy(), ref)
+    m3 = maskw.expand(-1, 3, -1, -1).contiguous()
+    refm = np.stack([LC.to_pil_u8(torch.flip(m3[i], [2]) if fl[i] else m3[i]) for i in range(3)])
+    outm = loader.compose_u8(None, m3.to(dev), None, torch.tensor([int(f) for f in fl], dtype=torch.int32))
+    assert np.array_equal(outm.cpu().numpy(), refm)
+
+
+@pytest.mark.gpu
+def test_cuda_composer_vs_oracle_and_golden(dev, tmp_path):
+    """AdvBatchComposer on the four golden cases as ONE batch (mixed sides / flips / placements)."""
+    from depthmodelhardening_b200 import loader
+    g = load_golden("loader_compose")
+    ben, adv, mask = patches()
+    calib = write_calib(str(tmp_path))
+    comp = loader.AdvBatchComposer(ben.to(dev), mask.to(dev), {"path": calib}, H, W, S)
+    comp.update_adv_obj(adv.to(dev))
+    c0 = torch.cat([synth.frames_u8(1000 + 2 * ci) for ci in range(len(CASES))])
+    cs = torch.cat([synth.frames_u8(1001 + 2 * ci) for ci in range(len(CASES))])
+    out = comp(c0.to(dev), cs.to(dev), [c[0] for c in CASES], [c[1] for c in CASES], [c[2] for c in CASES],
+               [c[3] for c in CASES])
+    assert out[("objdepth", 0, 0)].shape == (len(CASES), 1, 1)
+    assert out[("color", "s", 2)] is out[("color_aug", "s", 2)]
+    worst = 0.0
+    for ci, (side, flip, z0, alpha) in enumerate(CASES):
+        ref = LC.prep_item(c0[ci].numpy(), cs[ci].numpy(), side, flip, z0, alpha, adv, ben, mask, P34, H, W, S)
+        for k, v in ref.items():
+            if k[0] == "objdepth":
+                assert torch.equal(out[k][ci].cpu(), v)
+                continue
+            got, want = as_u8(out[k][ci]).astype(np.int32), as_u8(v).astype(np.int32)
+            assert got.shape == want.shape, k
+            d = np.abs(got - want)
+            frac = float((d > 0).mean())
+            worst = max(worst, frac)
+            assert d.max() <= 1 and frac < 0.01, (ci, k, int(d.max()), frac)
+            # bytes that cannot see the patch are exact: everything above the horizon rows of the placement
+            assert np.array_equal(got[:, : got.shape[1] // 4], want[:, : want.shape[1] // 4]), (ci, k)
+            name = "c%d_%s_%s_%d" % ((ci,) + k)
+            assert abs(int(got.sum()) - int(g[name + "_sum"])) <= d.size * 0.01, name
+    print("composer: worst fraction of bytes off by one grey level: %.2e" % worst)
+    with pytest.raises(RuntimeError, match="Batch size"):
+        comp(c0.to(dev), cs.to(dev), ["l"], [False])
