@@ -225,16 +225,17 @@ def compose_bench(dev, args, lib):
         for i in range(S):
             im = im.resize((W >> i, H >> i), Image.LANCZOS)
     cpu_ms_item = (time.perf_counter() - t0) / reps * 1e3
-    # bytes: 2 raw frames in, 3 composites out/in, 3 pyramids (u8 + fp32) out, 5 warped canvases (fp32) out + in
+    # bytes: 2 raw frames in, 3 composites + mask plane out and in again, 3 pyramids (u8 out / in, fp32 out), the
+    # horizontal-pass intermediates out / in
     px, pyr_px = 375 * 1242, sum((H >> i) * (W >> i) for i in range(S))
-    bytes_item = 3 * px * (2 + 3 * 2) + 3 * 3 * pyr_px * (1 + 4) + 2 * 4 * px * (3 * 3 + 2)
+    bytes_item = 3 * px * (2 + 3 * 2) + 2 * px + 3 * 3 * pyr_px * (2 + 4) + 2 * 3 * 3 * 375 * W
     print(json.dumps({"workload": "training-batch compositing on the device (next-2: prep_adv_data + preprocess)",
                       "B": B, "native": [375, 1242], "H": H, "W": W, "scales": S, "ms_per_batch": ms,
                       "items_per_s": B / (ms * 1e-3), "pyramids_only_ms": ms_pyr, "gpu_launches_per_batch": int(launches),
                       "approx_bytes_per_batch": bytes_item * B, "approx_gbs": bytes_item * B / (ms * 1e-3) / 1e9,
                       "cpu_pillow_pyramids_ms_per_item": cpu_ms_item, "cpu_cores": 1,
-                      "note": "GPU: 5 batched perspective launches, 4 composites, 13 Lanczos resizes (2 passes each), "
-                              "13 unpacks; CPU figure: only the three 4-level Pillow pyramids of one item on one core "
+                      "note": "GPU: 2 fused warp+composite launches (the fp32 canvases are never materialised), the three "
+                              "composites resized as one stack (2 passes + 1 unpack per level) + the mask image; CPU figure: only the three 4-level Pillow pyramids of one item on one core "
                               "(the reference additionally warps and composites on the CPU, ~1 s per item)"}))
 
 

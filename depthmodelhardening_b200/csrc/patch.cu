@@ -608,9 +608,77 @@ patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__
     }
 }
 
+// --------------------------------------------------------------------------- loader-side composite, 8-bit (next-2)
+// MonoDataset.prep_adv_data (mono_dataset.py:193-251) for one frame of every item: to_tensor(scene), the perspective
+// warp of up to two patches that share one placement and one mask (the adversarial and the benign patch on frame 0),
+// optional mirror of the warped patch / mask, scene*(1-m) + obj*m, to_pilimage (`.mul(255).byte()`).  The warped
+// canvases (B,3,375,1242 fp32 each) never exist: a pixel samples the patch itself, with exactly the arithmetic of
+// perspective_fwd_kernel.  One thread per canvas pixel; HBM-bound by bytes (3 in, 3..7 out per pixel).
+__device__ __forceinline__ uint8_t to_byte(float v) {
+    const float q = mul_rn(v, 255.0f);
+    return (uint8_t)min(max((int)q, 0), 255);             // `.byte()` truncates; images in [0,1] never saturate
+}
+
+__global__ void __launch_bounds__(256)
+compose_patch_u8_kernel(const uint8_t* __restrict__ scene, const float* __restrict__ patch_a,
+                        const float* __restrict__ patch_b, const float* __restrict__ pmask,
+                        const float* __restrict__ coeffs, const int* __restrict__ bbox, const int* __restrict__ flip,
+                        int ph, int pw, int H, int W, int l_pad, int t_pad, uint8_t* __restrict__ out_a,
+                        uint8_t* __restrict__ out_b, uint8_t* __restrict__ mask_out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const int xs = (flip && __ldg(flip + b) != 0) ? W - 1 - x : x;       // torch.flip(warped, [3])
+    bool hit = true;
+    if (bbox) hit = xs >= __ldg(bbox + b * 4) && xs <= __ldg(bbox + b * 4 + 2) && y >= __ldg(bbox + b * 4 + 1) &&
+                    y <= __ldg(bbox + b * 4 + 3);
+    float m = 0.f, oa[3] = {0.f, 0.f, 0.f}, ob[3] = {0.f, 0.f, 0.f};
+    if (hit) {
+        const Homography hm = load_homography(coeffs, b, W, H);
+        float ix, iy;
+        perspective_src(hm, xs, y, W, H, ix, iy);
+        const PatchTaps t = patch_taps(ix, iy, W, H, l_pad, t_pad, pw, ph);
+        if (t.any) {
+            const int PN = ph * pw;
+            m = sample_plane(pmask, t, pw);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                oa[c] = sample_plane(patch_a + c * PN, t, pw);
+                if (patch_b) ob[c] = sample_plane(patch_b + c * PN, t, pw);
+            }
+        }
+    }
+    const float om = sub_rn(1.0f, m);
+    const size_t N = (size_t)H * W, po = (size_t)y * W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = ((size_t)b * 3 + c) * N + po;
+        const float s = mul_rn(div_rn((float)__ldg(scene + o), 255.0f), om);
+        out_a[o] = to_byte(add_rn(s, mul_rn(oa[c], m)));
+        if (out_b) out_b[o] = to_byte(add_rn(s, mul_rn(ob[c], m)));
+    }
+    if (mask_out) mask_out[(size_t)b * N + po] = to_byte(m);
+}
+
 }  // namespace
 
 extern "C" {
+
+int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float* patch_b, const float* patch_mask,
+                         const float* coeffs, const int* bbox, const int* flip, int B, int ph, int pw, int H, int W,
+                         uint8_t* out_a, uint8_t* out_b, uint8_t* mask_out, dmh_stream_t stream) {
+    DMH_REQUIRE(scene && patch_a && patch_mask && coeffs && out_a, "dmh_compose_patch_u8: null pointer");
+    DMH_REQUIRE((patch_b != nullptr) == (out_b != nullptr), "dmh_compose_patch_u8: patch_b and out_b go together");
+    DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && H >= ph && H <= 65535 && W >= pw,
+                "dmh_compose_patch_u8: bad shape (patch %dx%d, canvas %dx%d)", ph, pw, H, W);
+    const int l_pad = (W - pw) / 2, t_pad = (H - ph) / 2;
+    dim3 grid(ceil_div(W, 256), H, B);
+    DMH_LAUNCH(compose_patch_u8_kernel, grid, 256, 0, (cudaStream_t)stream)(scene, patch_a, patch_b, patch_mask, coeffs, bbox,
+                                                                          flip, ph, pw, H, W, l_pad, t_pad, out_a, out_b,
+                                                                          mask_out);
+    DMH_CHECK_LAUNCH("dmh_compose_patch_u8");
+    return DMH_OK;
+}
 
 int dmh_perspective_fwd(const float* img, const float* coeffs, int B, int C, int ph, int pw, int oh, int ow,
                         float* out, dmh_stream_t stream) {

@@ -148,6 +148,49 @@ def compose_u8(scene: Optional[torch.Tensor], obj: torch.Tensor, mask: Optional[
     return out
 
 
+def compose_patch_u8(scene: torch.Tensor, patch_a: torch.Tensor, patch_b: Optional[torch.Tensor], patch_mask: torch.Tensor,
+                     place, flip: Optional[torch.Tensor] = None, want_mask: bool = False, out_a=None, out_b=None):
+    """`compose_u8` with the perspective warp inside (`dmh_compose_patch_u8`): scene (B,3,H,W) uint8, patches
+    (1,3,h,w) and mask (1,1,h,w) fp32, `place` a `patch_ops.Placement` (or bare (B,8) coefficients) for the canvas
+    (H,W).  Returns (out_a, out_b or None, warped mask as 8-bit (B,1,H,W) or None).  Bit-identical to
+    `compose_u8(scene, perspective_batch(patch, place), perspective_batch(mask, place), flip)` without the fp32
+    canvases."""
+    lib = _lib.load()
+    scene = _need_u8_cuda(scene, "compose_patch_u8 scene")
+    B, C, H, W = scene.shape
+    patch_a, patch_mask = _lib.f32c(patch_a), _lib.f32c(patch_mask)
+    if patch_b is not None:
+        patch_b = _lib.f32c(patch_b)
+        if patch_b.shape != patch_a.shape:
+            raise RuntimeError("compose_patch_u8: the two patches must have one shape")
+    _, pc, ph, pw = patch_a.shape
+    if C != 3 or pc != 3 or tuple(patch_mask.shape) != (1, 1, ph, pw):
+        raise RuntimeError("compose_patch_u8: expected (B,3,H,W) scenes, (1,3,h,w) patches and a (1,1,h,w) mask")
+    coeffs, bbox, _, _ = patch_ops._unpack(place)
+    if coeffs.shape[0] != B:
+        raise RuntimeError("Batch size doesn't match!")
+    if flip is not None:
+        flip = flip.to(device=scene.device, dtype=torch.int32).contiguous()
+        if flip.numel() != B:
+            raise RuntimeError("compose_patch_u8: one flip flag per item")
+    for o in (out_a, out_b):
+        if o is not None and (o.shape != scene.shape or o.dtype != torch.uint8 or not o.is_contiguous()
+                              or o.device != scene.device):
+            raise RuntimeError("compose_patch_u8: preallocated outputs must be contiguous uint8 of the scene's shape")
+    if out_a is None:
+        out_a = torch.empty_like(scene)
+    if patch_b is None:
+        out_b = None
+    elif out_b is None:
+        out_b = torch.empty_like(scene)
+    m_out = torch.empty((B, 1, H, W), dtype=torch.uint8, device=scene.device) if want_mask else None
+    _lib.check(lib.dmh_compose_patch_u8(_lib.ptr(scene), _lib.ptr(patch_a), _lib.ptr(patch_b), _lib.ptr(patch_mask),
+                                        _lib.ptr(coeffs), _lib.ptr(bbox), _lib.ptr(flip), B, ph, pw, H, W,
+                                        _lib.ptr(out_a), _lib.ptr(out_b), _lib.ptr(m_out), _lib.stream()),
+               "compose_patch_u8")
+    return out_a, out_b, m_out
+
+
 class AdvBatchComposer:
     """`MonoDataset.set_adv_train` / `update_adv_obj` / `prep_adv_data` / `preprocess` for a collated batch on the
     device (mono_dataset.py:146-265, 119-144).
@@ -171,6 +214,7 @@ class AdvBatchComposer:
         self.adv_K[1, :] *= ori_H
         self.stereo_T = np.eye(4, dtype=np.float32)
         self.stereo_T[0, 3] = -0.54
+        self._place_cache: Dict = {}
 
     def update_adv_obj(self, obj_img_adv: torch.Tensor) -> None:
         """mono_dataset.py:178-184 with the attack's result handed in (the attack itself is `attacks.Phy_obj_atk*`)."""
@@ -178,11 +222,24 @@ class AdvBatchComposer:
         self.adv_trans.reset_img(self.obj_img_adv, self.obj_mask)
 
     def _placement(self, trans: PhysicalTrans, z0, alpha, with_T):
-        ends = np.stack([patch_ops.project_corners(z, a, trans.P, self.adv_K, self.stereo_T if t else None)
-                         for z, a, t in zip(z0, alpha, with_T)])
+        """Per-item placements (mono_dataset.py:207-223): homography + conservative box, cached per
+        (distance, angle, camera) -- the reference draws them from 3 x 13 values -- and sent as one small copy."""
         _, _, h, w = trans.obj_img.size()
-        return patch_ops.make_placement(trans.pos_obj_img_start, ends, (h, w), (self.ori_H, self.ori_W)).to(
-            trans.obj_img.device)
+        keys = [(float(z), float(a), bool(t), h, w) for z, a, t in zip(z0, alpha, with_T)]
+        miss = [k for k in dict.fromkeys(keys) if k not in self._place_cache]
+        if miss:
+            ends = np.stack([patch_ops.project_corners(z, a, trans.P, self.adv_K, self.stereo_T if t else None)
+                             for (z, a, t, _, _) in miss])
+            pl = patch_ops.make_placement(trans.pos_obj_img_start, ends, (h, w), (self.ori_H, self.ori_W))
+            if len(self._place_cache) > 4096:
+                self._place_cache.clear()
+            for i, k in enumerate(miss):
+                self._place_cache[k] = (pl.coeffs[i].clone(), pl.bbox[i].clone())
+        co = torch.stack([self._place_cache[k][0] for k in keys])
+        bb = torch.stack([self._place_cache[k][1] for k in keys])
+        wh = (int((bb[:, 2] - bb[:, 0] + 1).max()), int((bb[:, 3] - bb[:, 1] + 1).max()))
+        dev = trans.obj_img.device
+        return patch_ops.Placement(co.to(dev, non_blocking=True), bb.to(dev, non_blocking=True), wh)
 
     def __call__(self, color_0: torch.Tensor, color_s: torch.Tensor, sides: Sequence[str], do_flip: Sequence[bool],
                  z0_sample: Optional[Sequence[float]] = None, alpha_sample: Optional[Sequence[float]] = None):
@@ -210,27 +267,28 @@ class AdvBatchComposer:
         # (project_w_trans with stereo_T) for side 'r'; the stereo partner sees the other one (:207-223)
         place_0 = self._placement(self.ben_trans, z0_sample, alpha_sample, right)
         place_s = self._placement(self.ben_trans, z0_sample, alpha_sample, [not r for r in right])
-        hw = (self.ori_H, self.ori_W)
-        mask_0 = patch_ops.perspective_batch(self.obj_mask, place_0, hw)
-        mask_s = patch_ops.perspective_batch(self.obj_mask, place_s, hw)
-        adv_0 = patch_ops.perspective_batch(self.obj_img_adv, place_0, hw)
-        ben_0 = patch_ops.perspective_batch(self.obj_img_ben, place_0, hw)
-        ben_s = patch_ops.perspective_batch(self.obj_img_ben, place_s, hw)
-        flip = torch.tensor([1 if f else 0 for f in do_flip], dtype=torch.int32, device=color_0.device)
+        flip = torch.tensor([1 if f else 0 for f in do_flip], dtype=torch.int32).to(color_0.device, non_blocking=True)
         with torch.no_grad():
-            aug_0 = compose_u8(color_0, adv_0, mask_0, flip)          # the adversarial current frame
-            aug_s = compose_u8(color_s, ben_s, mask_s, flip)          # its benign stereo partner
-            ben = compose_u8(color_0, ben_0, mask_0, flip)            # the benign current frame (:239-251)
-            objmask = compose_u8(None, mask_0.expand(-1, 3, -1, -1).contiguous(), None, flip)   # (:254)
+            # frame 0: the adversarial frame, the benign frame (:239-251) and the warped mask image (:254) share the
+            # scene, the placement and the mask -> one pass; the stereo partner carries the benign patch
+            comp = torch.empty((3,) + tuple(color_0.shape), dtype=torch.uint8, device=color_0.device)
+            _, _, objmask = compose_patch_u8(color_0, self.obj_img_adv, self.obj_img_ben, self.obj_mask, place_0, flip,
+                                             want_mask=True, out_a=comp[0], out_b=comp[2])
+            compose_patch_u8(color_s, self.obj_img_ben, None, self.obj_mask, place_s, flip, out_a=comp[1])
             out = {}
             S = self.num_scales
-            for name, fid, img in (("color_aug", 0, aug_0), ("color_aug", "s", aug_s), ("color", 0, ben)):
-                for i, lvl in enumerate(pyramid_u8(img, self.height, self.width, S)):
-                    out[(name, fid, i)] = unpack_u8(lvl)
+            # the three composites go through the pyramid as one stack: 2 resize passes + 1 unpack per level
+            names = (("color_aug", 0), ("color_aug", "s"), ("color", 0))
+            for i, lvl in enumerate(pyramid_u8(comp.view((3 * B,) + tuple(color_0.shape[1:])), self.height, self.width, S)):
+                f = unpack_u8(lvl)
+                for j, (name, fid) in enumerate(names):
+                    out[(name, fid, i)] = f[j * B:(j + 1) * B]
             for i in range(S):                                        # :257: color['s'] is color_aug['s']
                 out[("color", "s", i)] = out[("color_aug", "s", i)]
             out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
-            out[("color_objmask", 0, 0)] = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
+            # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
+            om = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
+            out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1).contiguous()
             out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
                                                    device=color_0.device)
         return out

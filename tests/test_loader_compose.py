@@ -163,6 +163,32 @@ def test_cuda_compose_is_bit_exact_on_identical_inputs(dev, flip):
 
 
 @pytest.mark.gpu
+def test_cuda_fused_compose_equals_warp_then_compose(dev):
+    """dmh_compose_patch_u8 (warp inside, two patches, mask image) == dmh_perspective_fwd + dmh_compose_u8, bit for
+    bit, with and without the placement boxes, mixed flips."""
+    from depthmodelhardening_b200 import loader, patch_ops
+    ben, adv, mask = patches()
+    ben, adv, mask = ben.to(dev), adv.to(dev), mask.to(dev)
+    z0, al = [5.0, 6.5, 8.0, 9.0], [-30.0, -5.0, 10.0, 30.0]
+    place = patch_ops.homographies(z0, al, P34, K=LC.adv_K(), T=LC.STEREO_T).to(dev)
+    scenes = synth.frames_u8(55, batch=4).to(dev)
+    flip = torch.tensor([0, 1, 1, 0], dtype=torch.int32)
+    hw = (synth.ORI_H, synth.ORI_W)
+    mw = patch_ops.perspective_batch(mask, place, hw)
+    ref_a = loader.compose_u8(scenes, patch_ops.perspective_batch(adv, place, hw), mw, flip)
+    ref_b = loader.compose_u8(scenes, patch_ops.perspective_batch(ben, place, hw), mw, flip)
+    ref_m = loader.compose_u8(None, mw, None, flip)
+    for pl in (place, place.coeffs):
+        a, b, m = loader.compose_patch_u8(scenes, adv, ben, mask, pl, flip, want_mask=True)
+        assert torch.equal(a, ref_a) and torch.equal(b, ref_b) and torch.equal(m, ref_m)
+    a, b, m = loader.compose_patch_u8(scenes, adv, None, mask, place, flip)
+    assert torch.equal(a, ref_a) and b is None and m is None
+    assert int((ref_a != ref_b).sum()) > 10000                 # the patches are visible
+    with pytest.raises(RuntimeError, match="Batch size"):
+        loader.compose_patch_u8(scenes[:3], adv, None, mask, place, None)
+
+
+@pytest.mark.gpu
 def test_cuda_composer_vs_oracle_and_golden(dev, tmp_path):
     """AdvBatchComposer on the four golden cases as ONE batch (mixed sides / flips / placements)."""
     from depthmodelhardening_b200 import loader
