@@ -19,6 +19,7 @@ using namespace dmh;
 namespace {
 
 #define LZ_PRECISION_BITS 22
+#define LZ_UNR 4                   // taps whose loads are in flight together
 
 __device__ __forceinline__ uint8_t clip8(int v) {
     v >>= LZ_PRECISION_BITS;                               // arithmetic shift, as Resample.c clip8
@@ -35,18 +36,31 @@ lanczos_h_kernel(const uint8_t* __restrict__ in, int rows, int in_w, int out_w, 
     const int xo = blockIdx.x * LH_TX + threadIdx.x;
     const int r0 = (blockIdx.y * LH_TY + threadIdx.y) * LH_ROWS;
     if (xo >= out_w || r0 >= rows) return;
-    const int xmin = __ldg(bounds + 2 * xo), cnt = __ldg(bounds + 2 * xo + 1);
-    const int* __restrict__ k = kk + (size_t)xo * ksize;
+    const int2 bd = __ldg(reinterpret_cast<const int2*>(bounds) + xo);
+    const int xmin = bd.x, cnt = bd.y;
+    const int* __restrict__ k = kk + xo;                  // weights are laid out (ksize, out): lanes read neighbours
     const uint8_t* p[LH_ROWS];
 #pragma unroll
     for (int i = 0; i < LH_ROWS; ++i) p[i] = in + (size_t)min(r0 + i, rows - 1) * in_w + xmin;
     int acc[LH_ROWS];
 #pragma unroll
     for (int i = 0; i < LH_ROWS; ++i) acc[i] = 1 << (LZ_PRECISION_BITS - 1);
-    for (int j = 0; j < cnt; ++j) {
-        const int kj = __ldg(k + j);
+    // taps in groups of LZ_UNR: the group's loads are issued together (the tap count is a run-time value, so the
+    // compiler cannot batch them itself); taps past the span are clamped onto its last pixel with weight 0
+    for (int j0 = 0; j0 < cnt; j0 += LZ_UNR) {
+        int kj[LZ_UNR];
+        unsigned char v[LZ_UNR][LH_ROWS];
 #pragma unroll
-        for (int i = 0; i < LH_ROWS; ++i) acc[i] += (int)__ldg(p[i] + j) * kj;
+        for (int u = 0; u < LZ_UNR; ++u) {
+            const int j = min(j0 + u, cnt - 1);
+            kj[u] = (j0 + u < cnt) ? __ldg(k + (size_t)j * out_w) : 0;
+#pragma unroll
+            for (int i = 0; i < LH_ROWS; ++i) v[u][i] = __ldg(p[i] + j);
+        }
+#pragma unroll
+        for (int u = 0; u < LZ_UNR; ++u)
+#pragma unroll
+            for (int i = 0; i < LH_ROWS; ++i) acc[i] += (int)v[u][i] * kj[u];
     }
 #pragma unroll
     for (int i = 0; i < LH_ROWS; ++i)
@@ -62,21 +76,31 @@ lanczos_v_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, con
     const int yo = blockIdx.y;
     if (x >= w) return;
     const int ymin = __ldg(bounds + 2 * yo), cnt = __ldg(bounds + 2 * yo + 1);
-    const int* __restrict__ k = kk + (size_t)yo * ksize;
+    const int* __restrict__ k = kk + yo;                  // (ksize, out) layout; warp-uniform here
     const uint8_t* p = in + ((size_t)blockIdx.z * in_h + ymin) * w + x;
     int acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 1 << (LZ_PRECISION_BITS - 1);
-    for (int j = 0; j < cnt; ++j) {
-        const int kj = __ldg(k + j);
-        if (VEC == 4) {
-            const unsigned q = __ldg(reinterpret_cast<const unsigned*>(p + (size_t)j * w));
-            acc[0] += (int)(q & 0xffu) * kj;
-            acc[1] += (int)((q >> 8) & 0xffu) * kj;
-            acc[2] += (int)((q >> 16) & 0xffu) * kj;
-            acc[3] += (int)(q >> 24) * kj;
-        } else {
-            acc[0] += (int)__ldg(p + (size_t)j * w) * kj;
+    for (int j0 = 0; j0 < cnt; j0 += LZ_UNR) {
+        int kj[LZ_UNR];
+        unsigned q[LZ_UNR];
+#pragma unroll
+        for (int u = 0; u < LZ_UNR; ++u) {
+            const int j = min(j0 + u, cnt - 1);
+            kj[u] = (j0 + u < cnt) ? __ldg(k + (size_t)j * out_h) : 0;
+            if (VEC == 4) q[u] = __ldg(reinterpret_cast<const unsigned*>(p + (size_t)j * w));
+            else q[u] = __ldg(p + (size_t)j * w);
+        }
+#pragma unroll
+        for (int u = 0; u < LZ_UNR; ++u) {
+            if (VEC == 4) {
+                acc[0] += (int)(q[u] & 0xffu) * kj[u];
+                acc[1] += (int)((q[u] >> 8) & 0xffu) * kj[u];
+                acc[2] += (int)((q[u] >> 16) & 0xffu) * kj[u];
+                acc[3] += (int)(q[u] >> 24) * kj[u];
+            } else {
+                acc[0] += (int)q[u] * kj[u];
+            }
         }
     }
     uint8_t* o = out + ((size_t)blockIdx.z * out_h + yo) * w + x;

@@ -75,7 +75,8 @@ def _device_coefficients(in_size: int, out_size: int, device):
     hit = _coeff_cache.get(key)
     if hit is None:
         b, k = lanczos_coefficients(in_size, out_size)
-        hit = (torch.from_numpy(b).to(device), torch.from_numpy(k).to(device), k.shape[1])
+        # the kernels want the weights tap-major, (ksize, out): neighbouring outputs read neighbouring integers
+        hit = (torch.from_numpy(b).to(device), torch.from_numpy(np.ascontiguousarray(k.T)).to(device), k.shape[1])
         _coeff_cache[key] = hit
     return hit
 

@@ -349,8 +349,8 @@ int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float
 /* dmh_lanczos_u8: `transforms.Resize((h, w), interpolation=Image.ANTIALIAS)` on 8-bit PIL images (:71, 100-104,
  * 126-131) == Pillow's fixed-point Lanczos resampling (libImaging/Resample.c), bit-exact: horizontal pass, then
  * vertical pass, each with 22-bit integer weights, rounded and clipped to 8 bits.  in (planes, in_h, in_w) ->
- * out (planes, out_h, out_w).  bounds_* (out, 2) int32 = (first input index, tap count), kk_* (out, ksize) int32
- * weights: host-computed in double precision as Pillow does (depthmodelhardening_b200/loader.py
+ * out (planes, out_h, out_w).  bounds_* (out, 2) int32 = (first input index, tap count), kk_* (ksize, out) int32
+ * weights (tap-major, so that neighbouring outputs read neighbouring weights): host-computed in double precision as Pillow does (depthmodelhardening_b200/loader.py
  * lanczos_coefficients); an axis that keeps its size is skipped and needs no tables.  tmp: (planes, in_h, out_w)
  * bytes, needed when both axes change. */
 int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h, int out_w, const int* bounds_x,
