@@ -67,6 +67,60 @@ lanczos_h_kernel(const uint8_t* __restrict__ in, int rows, int in_w, int out_w, 
         if (r0 + i < rows) out[(size_t)(r0 + i) * out_w + xo] = clip8(acc[i]);
 }
 
+// ---- horizontal pass, dp4a form (spans of <= 4 * NW taps: NW = 3 covers down-scales up to 4/3, NW = 4 up to 2).
+// The 22-bit weight k splits exactly into three bytes, k = k2 * 65536 + k1 * 256 + k0 (k0, k1 unsigned, k2 signed),
+// so sum_j p_j * k_j is three 8-bit dot products: 3 dp4a per 4 taps instead of 4 byte loads + 4 multiply-adds.
+// The pixels of a span come as NW + 1 aligned 32-bit words of the flat byte stream (rows are not word-aligned:
+// in_w = 1242), shifted onto tap 0 by a funnel shift.  Taps past the span carry weight 0, so the bytes the words
+// bring along (the next pixels of the row, or of the next row) do not matter; word indices are clamped to the buffer.
+// ncu on the byte-gather form: 79 lane-instructions per output at 77 % issue utilisation -- instruction-issue bound.
+#define LD_ROWS 16
+template <int NW>
+__global__ void __launch_bounds__(LH_TX * LH_TY)
+lanczos_h_dp4a_kernel(const uint8_t* __restrict__ in, int rows, int in_w, int out_w, const int* __restrict__ bounds,
+                      const int* __restrict__ kk, unsigned nwords, uint8_t* __restrict__ out) {
+    const int xo = blockIdx.x * LH_TX + threadIdx.x;
+    const int r0 = (blockIdx.y * LH_TY + threadIdx.y) * LD_ROWS;
+    if (xo >= out_w || r0 >= rows) return;
+    const int2 bd = __ldg(reinterpret_cast<const int2*>(bounds) + xo);
+    const int xmin = bd.x, cnt = bd.y;
+    unsigned w0[NW], w1[NW], w2[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        w0[w] = w1[w] = w2[w] = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = 4 * w + i;
+            const int k = (j < cnt) ? __ldg(kk + j * out_w + xo) : 0;          // (ksize, out) layout
+            w0[w] |= (unsigned)(k & 0xff) << (8 * i);
+            w1[w] |= (unsigned)((k >> 8) & 0xff) << (8 * i);
+            w2[w] |= (unsigned)((k >> 16) & 0xff) << (8 * i);                   // signed byte (arithmetic shift)
+        }
+    }
+    const unsigned in_off = (unsigned)((uintptr_t)in & 3);
+    const unsigned* __restrict__ base = reinterpret_cast<const unsigned*>(in - in_off);
+#pragma unroll 2
+    for (int i = 0; i < LD_ROWS; ++i) {
+        const int row = min(r0 + i, rows - 1);
+        const unsigned a = in_off + (unsigned)row * (unsigned)in_w + (unsigned)xmin;   // byte index of tap 0 (< 2^32)
+        const unsigned wi = a >> 2, sh = (a & 3u) * 8u;
+        unsigned q[NW + 1];
+#pragma unroll
+        for (int w = 0; w <= NW; ++w) q[w] = __ldg(base + min(wi + w, nwords - 1));
+        unsigned d0 = 0u, d1 = 0u;
+        int d2 = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const unsigned v = __funnelshift_r(q[w], q[w + 1], sh);
+            d0 = __dp4a(v, w0[w], d0);
+            d1 = __dp4a(v, w1[w], d1);
+            asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d2) : "r"(v), "r"(w2[w]), "r"(d2));
+        }
+        const unsigned acc = (1u << (LZ_PRECISION_BITS - 1)) + d0 + (d1 << 8) + ((unsigned)d2 << 16);
+        if (r0 + i < rows) out[(size_t)(r0 + i) * out_w + xo] = clip8((int)acc);
+    }
+}
+
 // ---- vertical pass: a thread owns VEC adjacent columns of one output row; the taps of a row are warp-uniform
 template <int VEC>
 __global__ void __launch_bounds__(128)
@@ -110,6 +164,72 @@ lanczos_v_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, con
         *reinterpret_cast<unsigned*>(o) = r;
     } else {
         o[0] = clip8(acc[0]);
+    }
+}
+
+// ---- vertical pass, row-group form: a thread owns 4 adjacent columns (one 32-bit load per input row) of LV_G
+// consecutive output rows, walks the union of their input spans once and feeds every output whose span holds the
+// row: each input row is fetched ~LV_G/1.2 times less often than with one output row per thread (the spans of
+// neighbouring outputs overlap by 8 of 9 taps).  Span membership and weights are warp-uniform.
+#define LV_G 8
+#define LV_TS 32                   // rows of the weight table: the union of LV_G spans must fit (checked by the launcher)
+__global__ void __launch_bounds__(128)
+lanczos_v_group_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, const int* __restrict__ bounds,
+                       const int* __restrict__ kk, uint8_t* __restrict__ out) {
+    // sk[t][g]: weight with which input row ylo + t enters output row yo0 + g (0 outside its span): the row loop
+    // needs no span test and reads the LV_G weights of a row with two 128-bit broadcast loads
+    __shared__ __align__(16) int sk[LV_TS][LV_G];
+    __shared__ int s_ylo, s_yhi;
+    const int yo0 = blockIdx.y * LV_G;
+    const int ylo = __ldg(bounds + 2 * yo0);
+    for (int e = threadIdx.x; e < LV_TS * LV_G; e += 128) {
+        const int t = e / LV_G, g = e % LV_G;
+        int v = 0;
+        if (yo0 + g < out_h) {
+            const int2 bd = __ldg(reinterpret_cast<const int2*>(bounds) + yo0 + g);
+            const int j = t - (bd.x - ylo);
+            if (j >= 0 && j < bd.y) v = __ldg(kk + j * out_h + yo0 + g);
+        }
+        sk[t][g] = v;
+    }
+    if (threadIdx.x == 0) {
+        const int last = min(yo0 + LV_G, out_h) - 1;
+        s_ylo = ylo;
+        s_yhi = __ldg(bounds + 2 * last) + __ldg(bounds + 2 * last + 1);       // spans are monotone in the output row
+    }
+    __syncthreads();
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    if (x >= w) return;
+    const int n = min(s_yhi - s_ylo, LV_TS);
+    int acc[LV_G][4];
+#pragma unroll
+    for (int g = 0; g < LV_G; ++g)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[g][c] = 1 << (LZ_PRECISION_BITS - 1);
+    const int wq = w >> 2;                                 // row pitch in 32-bit words
+    const unsigned* p = reinterpret_cast<const unsigned*>(in + ((size_t)blockIdx.z * in_h + ylo) * w + x);
+    unsigned q = __ldg(p);
+    for (int t = 0; t < n; ++t) {
+        const unsigned cur = q;
+        p += wq;
+        if (t + 1 < n) q = __ldg(p);                                            // next row in flight
+        const int b0 = cur & 0xffu, b1 = (cur >> 8) & 0xffu, b2 = (cur >> 16) & 0xffu, b3 = cur >> 24;
+        const int4 ka = *reinterpret_cast<const int4*>(&sk[t][0]);
+        const int4 kb = *reinterpret_cast<const int4*>(&sk[t][4]);
+        const int kv[LV_G] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int g = 0; g < LV_G; ++g) {
+            acc[g][0] += b0 * kv[g]; acc[g][1] += b1 * kv[g]; acc[g][2] += b2 * kv[g]; acc[g][3] += b3 * kv[g];
+        }
+    }
+    uint8_t* o = out + ((size_t)blockIdx.z * out_h + yo0) * w + x;
+#pragma unroll
+    for (int g = 0; g < LV_G; ++g) {
+        if (yo0 + g < out_h) {
+            const unsigned r = (unsigned)clip8(acc[g][0]) | ((unsigned)clip8(acc[g][1]) << 8) |
+                               ((unsigned)clip8(acc[g][2]) << 16) | ((unsigned)clip8(acc[g][3]) << 24);
+            *reinterpret_cast<unsigned*>(o + (size_t)g * w) = r;
+        }
     }
 }
 
@@ -186,14 +306,30 @@ int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h,
         uint8_t* hout = need_v ? tmp : out;
         const long long rows = (long long)planes * in_h;
         DMH_REQUIRE(rows < (1ll << 31) && ceil_div(rows, LH_TY * LH_ROWS) <= 65535, "dmh_lanczos_u8: too many rows");
-        dim3 grid(ceil_div(out_w, LH_TX), ceil_div(rows, LH_TY * LH_ROWS)), block(LH_TX, LH_TY);
-        DMH_LAUNCH(lanczos_h_kernel, grid, block, 0, st)(in, (int)rows, in_w, out_w, bounds_x, kk_x, ksize_x, hout);
+        dim3 block(LH_TX, LH_TY);
+        const long long bytes = rows * in_w + 3;                       // + the (<= 3) bytes below an unaligned base
+        if (ksize_x <= 16 && bytes < (1ll << 32)) {
+            const unsigned nwords = (unsigned)(((uintptr_t)in & 3) + rows * in_w + 3) >> 2;
+            dim3 grid(ceil_div(out_w, LH_TX), ceil_div(rows, LH_TY * LD_ROWS));
+            if (ksize_x <= 12)
+                DMH_LAUNCH(lanczos_h_dp4a_kernel<3>, grid, block, 0, st)(in, (int)rows, in_w, out_w, bounds_x, kk_x, nwords, hout);
+            else
+                DMH_LAUNCH(lanczos_h_dp4a_kernel<4>, grid, block, 0, st)(in, (int)rows, in_w, out_w, bounds_x, kk_x, nwords, hout);
+        } else {
+            dim3 grid(ceil_div(out_w, LH_TX), ceil_div(rows, LH_TY * LH_ROWS));
+            DMH_LAUNCH(lanczos_h_kernel, grid, block, 0, st)(in, (int)rows, in_w, out_w, bounds_x, kk_x, ksize_x, hout);
+        }
         DMH_CHECK_LAUNCH("dmh_lanczos_u8 (horizontal)");
         vin = hout;
     }
     if (need_v) {
         const bool vec = (out_w % 4 == 0) && (((uintptr_t)vin | (uintptr_t)out) % 4 == 0);
-        if (vec) {
+        // rows an LV_G-group of outputs can span: (LV_G - 1) centre steps + one full span (+ rounding slack)
+        const long long group_span = ((long long)(LV_G - 1) * in_h + out_h - 1) / out_h + ksize_y + 1;
+        if (vec && group_span <= LV_TS) {
+            dim3 grid(ceil_div(out_w, 128 * 4), ceil_div(out_h, LV_G), planes);
+            DMH_LAUNCH(lanczos_v_group_kernel, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, out);
+        } else if (vec) {
             dim3 grid(ceil_div(out_w, 128 * 4), out_h, planes);
             DMH_LAUNCH(lanczos_v_kernel<4>, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, ksize_y, out);
         } else {

@@ -26,7 +26,7 @@ H, W, S = 320, 1024, 4
 CASES = [("l", False, 7, -10), ("r", False, 5, 15), ("l", True, 9, 0), ("r", True, 7, 25)]
 SIZES = [(375, 1242, 320, 1024), (320, 1024, 160, 512), (160, 512, 80, 256), (80, 256, 40, 128),
          (375, 1242, 192, 640), (100, 333, 37, 53), (64, 64, 64, 32), (50, 70, 25, 70), (33, 47, 90, 121),
-         (7, 5, 3, 2), (50, 70, 50, 70)]
+         (7, 5, 3, 2), (50, 70, 50, 70), (375, 1242, 190, 640), (120, 64, 40, 32), (97, 130, 45, 100)]
 
 
 def crc(a):
