@@ -623,15 +623,18 @@ __global__ void __launch_bounds__(256)
 compose_patch_u8_kernel(const uint8_t* __restrict__ scene, const float* __restrict__ patch_a,
                         const float* __restrict__ patch_b, const float* __restrict__ pmask,
                         const float* __restrict__ coeffs, const int* __restrict__ bbox, const int* __restrict__ flip,
-                        int ph, int pw, int H, int W, int l_pad, int t_pad, uint8_t* __restrict__ out_a,
+                        const int* __restrict__ active, int ph, int pw, int H, int W, int l_pad, int t_pad,
+                        uint8_t* __restrict__ out_a,
                         uint8_t* __restrict__ out_b, uint8_t* __restrict__ mask_out) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     const int xs = (flip && __ldg(flip + b) != 0) ? W - 1 - x : x;       // torch.flip(warped, [3])
-    bool hit = true;
-    if (bbox) hit = xs >= __ldg(bbox + b * 4) && xs <= __ldg(bbox + b * 4 + 2) && y >= __ldg(bbox + b * 4 + 1) &&
-                    y <= __ldg(bbox + b * 4 + 3);
+    // items without synthesis (half_no_synthesis, mono_dataset.py:321-328) keep the raw frame: with m = 0 the
+    // composite is to_pilimage(to_tensor(scene)), which returns every byte unchanged (k/255*255 == k in fp32)
+    bool hit = !(active && __ldg(active + b) == 0);
+    if (hit && bbox) hit = xs >= __ldg(bbox + b * 4) && xs <= __ldg(bbox + b * 4 + 2) && y >= __ldg(bbox + b * 4 + 1) &&
+                           y <= __ldg(bbox + b * 4 + 3);
     float m = 0.f, oa[3] = {0.f, 0.f, 0.f}, ob[3] = {0.f, 0.f, 0.f};
     if (hit) {
         const Homography hm = load_homography(coeffs, b, W, H);
@@ -665,8 +668,8 @@ compose_patch_u8_kernel(const uint8_t* __restrict__ scene, const float* __restri
 extern "C" {
 
 int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float* patch_b, const float* patch_mask,
-                         const float* coeffs, const int* bbox, const int* flip, int B, int ph, int pw, int H, int W,
-                         uint8_t* out_a, uint8_t* out_b, uint8_t* mask_out, dmh_stream_t stream) {
+                         const float* coeffs, const int* bbox, const int* flip, const int* active, int B, int ph, int pw,
+                         int H, int W, uint8_t* out_a, uint8_t* out_b, uint8_t* mask_out, dmh_stream_t stream) {
     DMH_REQUIRE(scene && patch_a && patch_mask && coeffs && out_a, "dmh_compose_patch_u8: null pointer");
     DMH_REQUIRE((patch_b != nullptr) == (out_b != nullptr), "dmh_compose_patch_u8: patch_b and out_b go together");
     DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && H >= ph && H <= 65535 && W >= pw,
@@ -674,8 +677,8 @@ int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float
     const int l_pad = (W - pw) / 2, t_pad = (H - ph) / 2;
     dim3 grid(ceil_div(W, 256), H, B);
     DMH_LAUNCH(compose_patch_u8_kernel, grid, 256, 0, (cudaStream_t)stream)(scene, patch_a, patch_b, patch_mask, coeffs, bbox,
-                                                                          flip, ph, pw, H, W, l_pad, t_pad, out_a, out_b,
-                                                                          mask_out);
+                                                                          flip, active, ph, pw, H, W, l_pad, t_pad, out_a,
+                                                                          out_b, mask_out);
     DMH_CHECK_LAUNCH("dmh_compose_patch_u8");
     return DMH_OK;
 }

@@ -14,12 +14,12 @@ maintainer (a post-collate hook instead of `prep_adv_data`), whi
 `install()`.  There is no CPU path: tensors must be CUDA tensors.
 
 Not mirrored: the colour jitter (`color_aug`; off in the reference's adversarial configuration,
-`mono_dataset.py:301`, `adv_args['color_aug']`) and `half_no_synthesis`.
+`mono_dataset.py:297`, `adv_args['color_aug']`).
 """
 from __future__ import annotations
 
 import math
-from random import sample
+from random import random, sample
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -150,12 +150,13 @@ def compose_u8(scene: Optional[torch.Tensor], obj: torch.Tensor, mask: Optional[
 
 
 def compose_patch_u8(scene: torch.Tensor, patch_a: torch.Tensor, patch_b: Optional[torch.Tensor], patch_mask: torch.Tensor,
-                     place, flip: Optional[torch.Tensor] = None, want_mask: bool = False, out_a=None, out_b=None):
+                     place, flip: Optional[torch.Tensor] = None, want_mask: bool = False, out_a=None, out_b=None,
+                     active: Optional[torch.Tensor] = None):
     """`compose_u8` with the perspective warp inside (`dmh_compose_patch_u8`): scene (B,3,H,W) uint8, patches
     (1,3,h,w) and mask (1,1,h,w) fp32, `place` a `patch_ops.Placement` (or bare (B,8) coefficients) for the canvas
     (H,W).  Returns (out_a, out_b or None, warped mask as 8-bit (B,1,H,W) or None).  Bit-identical to
     `compose_u8(scene, perspective_batch(patch, place), perspective_batch(mask, place), flip)` without the fp32
-    canvases."""
+    canvases.  `active` (B,) int32: items with 0 get no patch (their frame passes through byte for byte)."""
     lib = _lib.load()
     scene = _need_u8_cuda(scene, "compose_patch_u8 scene")
     B, C, H, W = scene.shape
@@ -174,6 +175,10 @@ def compose_patch_u8(scene: torch.Tensor, patch_a: torch.Tensor, patch_b: Option
         flip = flip.to(device=scene.device, dtype=torch.int32).contiguous()
         if flip.numel() != B:
             raise RuntimeError("compose_patch_u8: one flip flag per item")
+    if active is not None:
+        active = active.to(device=scene.device, dtype=torch.int32).contiguous()
+        if active.numel() != B:
+            raise RuntimeError("compose_patch_u8: one synthesis flag per item")
     for o in (out_a, out_b):
         if o is not None and (o.shape != scene.shape or o.dtype != torch.uint8 or not o.is_contiguous()
                               or o.device != scene.device):
@@ -186,7 +191,7 @@ def compose_patch_u8(scene: torch.Tensor, patch_a: torch.Tensor, patch_b: Option
         out_b = torch.empty_like(scene)
     m_out = torch.empty((B, 1, H, W), dtype=torch.uint8, device=scene.device) if want_mask else None
     _lib.check(lib.dmh_compose_patch_u8(_lib.ptr(scene), _lib.ptr(patch_a), _lib.ptr(patch_b), _lib.ptr(patch_mask),
-                                        _lib.ptr(coeffs), _lib.ptr(bbox), _lib.ptr(flip), B, ph, pw, H, W,
+                                        _lib.ptr(coeffs), _lib.ptr(bbox), _lib.ptr(flip), _lib.ptr(active), B, ph, pw, H, W,
                                         _lib.ptr(out_a), _lib.ptr(out_b), _lib.ptr(m_out), _lib.stream()),
                "compose_patch_u8")
     return out_a, out_b, m_out
@@ -200,8 +205,9 @@ class AdvBatchComposer:
     height, width: network input size (scale 0); dist_range as `train_dist_range`."""
 
     def __init__(self, obj_tensor, mask_tensor, cfg, height, width, num_scales=4, dist_range=list(range(5, 10, 2)),
-                 ori_H=patch_ops.ORI_H, ori_W=patch_ops.ORI_W):
+                 ori_H=patch_ops.ORI_H, ori_W=patch_ops.ORI_W, half_no_synthesis=False):
         self.height, self.width, self.num_scales = height, width, num_scales
+        self.half_no_synthesis = half_no_synthesis            # args['half_no_synthesis'], mono_dataset.py:160
         self.ori_H, self.ori_W = ori_H, ori_W
         self.obj_mask = mask_tensor
         self.obj_img_ben = obj_tensor
@@ -243,11 +249,15 @@ class AdvBatchComposer:
         return patch_ops.Placement(co.to(dev, non_blocking=True), bb.to(dev, non_blocking=True), wh)
 
     def __call__(self, color_0: torch.Tensor, color_s: torch.Tensor, sides: Sequence[str], do_flip: Sequence[bool],
-                 z0_sample: Optional[Sequence[float]] = None, alpha_sample: Optional[Sequence[float]] = None):
+                 z0_sample: Optional[Sequence[float]] = None, alpha_sample: Optional[Sequence[float]] = None,
+                 synthesize: Optional[Sequence[bool]] = None):
         """color_0 / color_s: (B,3,ori_H,ori_W) uint8 CUDA -- frame 0 and its stereo partner at native resolution, as
         `get_color` returns them (already mirrored for the items with do_flip, mono_dataset.py:325-329); sides[i]:
         'l' / 'r', the side frame 0 of item i was taken from; do_flip[i]: mirror the warped patch too (:226-228);
-        z0_sample / alpha_sample: one placement per item (drawn like `PhysicalTrans.project` if None).
+        z0_sample / alpha_sample: one placement per item (drawn like `PhysicalTrans.project` if None);
+        synthesize[i] (only with half_no_synthesis, :321-328; drawn with `random.random() > 0.5` if None): items
+        with False keep their raw frames -- ("color_objmask", 0, 0) / ("objdepth", 0, 0) are then not produced at all,
+        as in the reference (:253-255).
 
         Returns the dictionary entries `prep_adv_data` + `preprocess` produce, as fp32 CUDA tensors:
         ("color_aug", 0 | "s", 0..S-1), ("color", 0 | "s", 0..S-1), ("color_ben", 0, 0), ("color_objmask", 0, 0),
@@ -263,6 +273,13 @@ class AdvBatchComposer:
             z0_sample = [sample(self.ben_trans.dist_range, 1)[0] for _ in range(B)]
         if alpha_sample is None:
             alpha_sample = [sample(self.ben_trans.angle_range, 1)[0] for _ in range(B)]
+        active = None
+        if self.half_no_synthesis:
+            if synthesize is None:
+                synthesize = [random() > 0.5 for _ in range(B)]
+            if len(synthesize) != B:
+                raise RuntimeError("Batch size doesn't match!")
+            active = torch.tensor([1 if a else 0 for a in synthesize], dtype=torch.int32).to(color_0.device)
         right = [s != "l" for s in sides]
         # frame 0 sees the placement of its own camera: left camera (project) for side 'l', right camera
         # (project_w_trans with stereo_T) for side 'r'; the stereo partner sees the other one (:207-223)
@@ -274,8 +291,10 @@ class AdvBatchComposer:
             # scene, the placement and the mask -> one pass; the stereo partner carries the benign patch
             comp = torch.empty((3,) + tuple(color_0.shape), dtype=torch.uint8, device=color_0.device)
             _, _, objmask = compose_patch_u8(color_0, self.obj_img_adv, self.obj_img_ben, self.obj_mask, place_0, flip,
-                                             want_mask=True, out_a=comp[0], out_b=comp[2])
-            compose_patch_u8(color_s, self.obj_img_ben, None, self.obj_mask, place_s, flip, out_a=comp[1])
+                                             want_mask=not self.half_no_synthesis, out_a=comp[0], out_b=comp[2],
+                                             active=active)
+            compose_patch_u8(color_s, self.obj_img_ben, None, self.obj_mask, place_s, flip, out_a=comp[1],
+                             active=active)
             out = {}
             S = self.num_scales
             # the three composites go through the pyramid as one stack: 2 resize passes + 1 unpack per level
@@ -287,9 +306,10 @@ class AdvBatchComposer:
             for i in range(S):                                        # :257: color['s'] is color_aug['s']
                 out[("color", "s", i)] = out[("color_aug", "s", i)]
             out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
-            # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
-            om = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
-            out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1).contiguous()
-            out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
-                                                   device=color_0.device)
+            if not self.half_no_synthesis:
+                # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
+                om = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
+                out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1).contiguous()
+                out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
+                                                       device=color_0.device)
         return out

@@ -341,10 +341,12 @@ int dmh_compose_u8(const uint8_t* scene, const float* obj, const float* mask, co
  * canvases are never materialised.  patch_a / patch_b (1,3,ph,pw): up to two patches that share the placement
  * `coeffs` (B,8) and the mask (1,1,ph,pw) -- the adversarial and the benign patch on frame 0 (mono_dataset.py:
  * 207-251); patch_b / out_b may both be NULL.  bbox (B,4) int32 or NULL: conservative placement boxes (optimisation
- * hint only).  out_a / out_b (B,3,H,W) u8; mask_out (B,1,H,W) u8 or NULL = to_pilimage of the warped mask (:254). */
+ * hint only).  active (B) int32 or NULL: items with 0 get no patch (`half_no_synthesis`, :321-328: the raw frame
+ * goes through unchanged).  out_a / out_b (B,3,H,W) u8; mask_out (B,1,H,W) u8 or NULL = to_pilimage of the warped
+ * mask (:254). */
 int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float* patch_b, const float* patch_mask,
-                         const float* coeffs, const int* bbox, const int* flip, int B, int ph, int pw, int H, int W,
-                         uint8_t* out_a, uint8_t* out_b, uint8_t* mask_out, dmh_stream_t stream);
+                         const float* coeffs, const int* bbox, const int* flip, const int* active, int B, int ph, int pw,
+                         int H, int W, uint8_t* out_a, uint8_t* out_b, uint8_t* mask_out, dmh_stream_t stream);
 
 /* dmh_lanczos_u8: `transforms.Resize((h, w), interpolation=Image.ANTIALIAS)` on 8-bit PIL images (:71, 100-104,
  * 126-131) == Pillow's fixed-point Lanczos resampling (libImaging/Resample.c), bit-exact: horizontal pass, then

@@ -41,6 +41,18 @@ def compose_u8(scene_u8: np.ndarray, obj: torch.Tensor, mask: torch.Tensor, flip
     return to_pil_u8((s * (1 - mask) + obj * mask).squeeze(0))
 
 
+def raw_item(color_0: np.ndarray, color_s: np.ndarray, height=320, width=1024, num_scales=4):
+    """An item of the `half_no_synthesis` branch that drew no synthesis (mono_dataset.py:325-328): color_aug and
+    color_ben are the raw frames; then preprocess (:119-144)."""
+    tt = lambda a: torch.from_numpy(a).to(torch.float32).div(255)
+    out = {}
+    for fid, img in ((0, color_0), ("s", color_s)):
+        for i, lvl in enumerate(R.pyramid_u8(img, height, width, num_scales)):
+            out[("color", fid, i)] = out[("color_aug", fid, i)] = tt(lvl)
+    out[("color_ben", 0, 0)] = out[("color", 0, 0)]
+    return out
+
+
 def prep_item(color_0: np.ndarray, color_s: np.ndarray, side: str, do_flip: bool, z0, alpha, obj_adv, obj_ben, mask,
               P34, height=320, width=1024, num_scales=4):
     """One item: uint8 frames [3,375,1242] -> dict of fp32 tensors keyed like the reference's `inputs`."""

@@ -223,3 +223,29 @@ def test_cuda_composer_vs_oracle_and_golden(dev, tmp_path):
     print("composer: worst fraction of bytes off by one grey level: %.2e" % worst)
     with pytest.raises(RuntimeError, match="Batch size"):
         comp(c0.to(dev), cs.to(dev), ["l"], [False])
+
+
+@pytest.mark.gpu
+def test_cuda_composer_half_no_synthesis_raw_items_are_bit_exact(dev, tmp_path):
+    """half_no_synthesis (mono_dataset.py:321-328): items that drew no synthesis keep their raw frames -- the whole
+    device pipeline (composite with m = 0, four Lanczos levels, unpack) is then pure byte work and must equal the
+    oracle bit for bit; the synthesised item of the same batch still matches its own oracle; the mask / depth
+    entries are absent as in the reference (:253-255)."""
+    from depthmodelhardening_b200 import loader
+    ben, adv, mask = patches()
+    calib = write_calib(str(tmp_path))
+    comp = loader.AdvBatchComposer(ben.to(dev), mask.to(dev), {"path": calib}, H, W, S, half_no_synthesis=True)
+    comp.update_adv_obj(adv.to(dev))
+    c0, cs = synth.frames_u8(2000, batch=3), synth.frames_u8(2001, batch=3)
+    out = comp(c0.to(dev), cs.to(dev), ["l", "r", "l"], [False, True, False], [7, 5, 9], [-10, 15, 0],
+               synthesize=[False, False, True])
+    assert ("color_objmask", 0, 0) not in out and ("objdepth", 0, 0) not in out
+    for b in (0, 1):
+        ref = LC.raw_item(c0[b].numpy(), cs[b].numpy(), H, W, S)
+        assert set(ref) <= set(out)
+        for k, v in ref.items():
+            assert torch.equal(out[k][b].cpu(), v), (b, k)
+    ref = LC.prep_item(c0[2].numpy(), cs[2].numpy(), "l", False, 9, 0, adv, ben, mask, P34, H, W, S)
+    d = np.abs(as_u8(out[("color_aug", 0, 0)][2]).astype(np.int32) - as_u8(ref[("color_aug", 0, 0)]).astype(np.int32))
+    assert d.max() <= 1 and float((d > 0).mean()) < 0.01
+    assert int((as_u8(out[("color_aug", 0, 0)][2]) != as_u8(out[("color", 0, 0)][2])).sum()) > 1000   # patch differs
