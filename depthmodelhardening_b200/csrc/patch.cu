@@ -619,6 +619,8 @@ __device__ __forceinline__ uint8_t to_byte(float v) {
     return (uint8_t)min(max((int)q, 0), 255);             // `.byte()` truncates; images in [0,1] never saturate
 }
 
+// PX pixels per thread (2 when rows are 2-byte aligned: 16-bit loads / stores halve the byte-wide memory instructions)
+template <int PX>
 __global__ void __launch_bounds__(256)
 compose_patch_u8_kernel(const uint8_t* __restrict__ scene, const float* __restrict__ patch_a,
                         const float* __restrict__ patch_b, const float* __restrict__ pmask,
@@ -626,41 +628,71 @@ compose_patch_u8_kernel(const uint8_t* __restrict__ scene, const float* __restri
                         const int* __restrict__ active, int ph, int pw, int H, int W, int l_pad, int t_pad,
                         uint8_t* __restrict__ out_a,
                         uint8_t* __restrict__ out_b, uint8_t* __restrict__ mask_out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
     const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
-    const int xs = (flip && __ldg(flip + b) != 0) ? W - 1 - x : x;       // torch.flip(warped, [3])
+    if (x0 >= W) return;
+    const bool fl = flip && __ldg(flip + b) != 0;
     // items without synthesis (half_no_synthesis, mono_dataset.py:321-328) keep the raw frame: with m = 0 the
     // composite is to_pilimage(to_tensor(scene)), which returns every byte unchanged (k/255*255 == k in fp32)
-    bool hit = !(active && __ldg(active + b) == 0);
-    if (hit && bbox) hit = xs >= __ldg(bbox + b * 4) && xs <= __ldg(bbox + b * 4 + 2) && y >= __ldg(bbox + b * 4 + 1) &&
-                           y <= __ldg(bbox + b * 4 + 3);
-    float m = 0.f, oa[3] = {0.f, 0.f, 0.f}, ob[3] = {0.f, 0.f, 0.f};
-    if (hit) {
-        const Homography hm = load_homography(coeffs, b, W, H);
-        float ix, iy;
-        perspective_src(hm, xs, y, W, H, ix, iy);
-        const PatchTaps t = patch_taps(ix, iy, W, H, l_pad, t_pad, pw, ph);
-        if (t.any) {
-            const int PN = ph * pw;
-            m = sample_plane(pmask, t, pw);
+    const bool on = !(active && __ldg(active + b) == 0);
+    int bx0 = 0, by0 = 0, bx1 = W - 1, by1 = H - 1;
+    if (on && bbox) {
+        const int4 bb = __ldg(reinterpret_cast<const int4*>(bbox) + b);
+        bx0 = bb.x; by0 = bb.y; bx1 = bb.z; by1 = bb.w;
+    }
+    float m[PX], oa[PX][3], ob[PX][3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                oa[c] = sample_plane(patch_a + c * PN, t, pw);
-                if (patch_b) ob[c] = sample_plane(patch_b + c * PN, t, pw);
+    for (int i = 0; i < PX; ++i) {
+        m[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) oa[i][c] = ob[i][c] = 0.f;
+        const int x = x0 + i;
+        const int xs = fl ? W - 1 - x : x;                // torch.flip(warped, [3])
+        if (on && x < W && xs >= bx0 && xs <= bx1 && y >= by0 && y <= by1) {
+            const Homography hm = load_homography(coeffs, b, W, H);
+            float ix, iy;
+            perspective_src(hm, xs, y, W, H, ix, iy);
+            const PatchTaps t = patch_taps(ix, iy, W, H, l_pad, t_pad, pw, ph);
+            if (t.any) {
+                const int PN = ph * pw;
+                m[i] = sample_plane(pmask, t, pw);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    oa[i][c] = sample_plane(patch_a + c * PN, t, pw);
+                    if (patch_b) ob[i][c] = sample_plane(patch_b + c * PN, t, pw);
+                }
             }
         }
     }
-    const float om = sub_rn(1.0f, m);
-    const size_t N = (size_t)H * W, po = (size_t)y * W + x;
+    const size_t N = (size_t)H * W, po = (size_t)y * W + x0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const size_t o = ((size_t)b * 3 + c) * N + po;
-        const float s = mul_rn(div_rn((float)__ldg(scene + o), 255.0f), om);
-        out_a[o] = to_byte(add_rn(s, mul_rn(oa[c], m)));
-        if (out_b) out_b[o] = to_byte(add_rn(s, mul_rn(ob[c], m)));
+        unsigned sv;
+        if (PX == 2) sv = __ldg(reinterpret_cast<const unsigned short*>(scene + o));       // (W even: x0 + 1 < W)
+        else sv = __ldg(scene + o);
+        unsigned ra = 0u, rb = 0u;
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const float s = mul_rn(div_rn((float)((sv >> (8 * i)) & 0xffu), 255.0f), sub_rn(1.0f, m[i]));
+            ra |= (unsigned)to_byte(add_rn(s, mul_rn(oa[i][c], m[i]))) << (8 * i);
+            if (out_b) rb |= (unsigned)to_byte(add_rn(s, mul_rn(ob[i][c], m[i]))) << (8 * i);
+        }
+        if (PX == 2) {
+            *reinterpret_cast<unsigned short*>(out_a + o) = (unsigned short)ra;
+            if (out_b) *reinterpret_cast<unsigned short*>(out_b + o) = (unsigned short)rb;
+        } else {
+            out_a[o] = (uint8_t)ra;
+            if (out_b) out_b[o] = (uint8_t)rb;
+        }
     }
-    if (mask_out) mask_out[(size_t)b * N + po] = to_byte(m);
+    if (mask_out) {
+        if (PX == 2)
+            *reinterpret_cast<unsigned short*>(mask_out + (size_t)b * N + po) =
+                (unsigned short)((unsigned)to_byte(m[0]) | ((unsigned)to_byte(m[PX - 1]) << 8));
+        else
+            mask_out[(size_t)b * N + po] = to_byte(m[0]);
+    }
 }
 
 }  // namespace
@@ -675,10 +707,17 @@ int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float
     DMH_REQUIRE(B > 0 && B <= 65535 && ph > 0 && pw > 0 && H >= ph && H <= 65535 && W >= pw,
                 "dmh_compose_patch_u8: bad shape (patch %dx%d, canvas %dx%d)", ph, pw, H, W);
     const int l_pad = (W - pw) / 2, t_pad = (H - ph) / 2;
-    dim3 grid(ceil_div(W, 256), H, B);
-    DMH_LAUNCH(compose_patch_u8_kernel, grid, 256, 0, (cudaStream_t)stream)(scene, patch_a, patch_b, patch_mask, coeffs, bbox,
-                                                                          flip, active, ph, pw, H, W, l_pad, t_pad, out_a,
-                                                                          out_b, mask_out);
+    DMH_REQUIRE(!bbox || ((uintptr_t)bbox & 15) == 0, "dmh_compose_patch_u8: bbox must be 16-byte aligned");
+    const uintptr_t al = (uintptr_t)scene | (uintptr_t)out_a | (uintptr_t)out_b | (uintptr_t)mask_out;
+    if (W % 2 == 0 && (al & 1) == 0) {
+        dim3 grid(ceil_div(W, 512), H, B);
+        DMH_LAUNCH(compose_patch_u8_kernel<2>, grid, 256, 0, (cudaStream_t)stream)(
+            scene, patch_a, patch_b, patch_mask, coeffs, bbox, flip, active, ph, pw, H, W, l_pad, t_pad, out_a, out_b, mask_out);
+    } else {
+        dim3 grid(ceil_div(W, 256), H, B);
+        DMH_LAUNCH(compose_patch_u8_kernel<1>, grid, 256, 0, (cudaStream_t)stream)(
+            scene, patch_a, patch_b, patch_mask, coeffs, bbox, flip, active, ph, pw, H, W, l_pad, t_pad, out_a, out_b, mask_out);
+    }
     DMH_CHECK_LAUNCH("dmh_compose_patch_u8");
     return DMH_OK;
 }

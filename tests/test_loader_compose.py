@@ -183,6 +183,12 @@ def test_cuda_fused_compose_equals_warp_then_compose(dev):
         assert torch.equal(a, ref_a) and torch.equal(b, ref_b) and torch.equal(m, ref_m)
     a, b, m = loader.compose_patch_u8(scenes, adv, None, mask, place, flip)
     assert torch.equal(a, ref_a) and b is None and m is None
+    # a scene buffer at an odd address takes the one-pixel-per-thread instantiation: same bytes
+    odd = torch.empty(scenes.numel() + 1, dtype=torch.uint8, device=dev)[1:].view(scenes.shape)
+    odd.copy_(scenes)
+    assert odd.data_ptr() % 2 == 1 and odd.is_contiguous()
+    a, b, m = loader.compose_patch_u8(odd, adv, ben, mask, place, flip, want_mask=True)
+    assert torch.equal(a, ref_a) and torch.equal(b, ref_b) and torch.equal(m, ref_m)
     assert int((ref_a != ref_b).sum()) > 10000                 # the patches are visible
     with pytest.raises(RuntimeError, match="Batch size"):
         loader.compose_patch_u8(scenes[:3], adv, None, mask, place, None)
