@@ -75,6 +75,7 @@ SIGNATURES = {
     "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_pgd_linf_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _st]),
+    "dmh_pgd_l2_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _fl, _f, _st]),
     "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),
     "dmh_l0_adam_step": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _fl, _i,
                               _st]),

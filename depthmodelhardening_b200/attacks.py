@@ -142,6 +142,58 @@ class Phy_obj_atk(Attack):
         return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
 
 
+class Phy_obj_atk_l2(Phy_obj_atk):
+    r"""Distance measure: L2 -- drop-in of the reference's `Phy_obj_atk_l2`
+    (torchattacks/attacks/phy_obj_atk_l2.py:13-136; next-4).  Same signature (the `alpha` argument is ignored there
+    too: the step is 2.5 * eps / steps, :44), return 4-tuple and RNG consumption; the update (:108-120: gradient
+    normalised by its L2 norm, projection onto the eps-ball, clamp) is one launch (`dmh_pgd_l2_step`).
+
+    The reference views the gradient of the ONE shared patch as (batch_size, -1) (:108), which is only meaningful
+    for batch_size == 1; here the norms are those of the shared patch for any batch size (identical at 1)."""
+
+    def __init__(self, model, obj_img, obj_mask, eps=1, alpha=0.2, steps=40, random_start=True,
+                 dist_range=list(range(5, 31, 2))):
+        super().__init__(model, obj_img, obj_mask, eps=eps, alpha=2.5 * eps / steps, steps=steps,
+                         random_start=random_start, dist_range=dist_range)
+        self.eps_for_division = 1e-10
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False):
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        loss = nn.MSELoss()
+        obj_img_adv = self.obj_img.clone().detach()
+        if self.random_start:                                  # phy_obj_atk_l2.py:79-87
+            delta = torch.empty_like(obj_img_adv).normal_()
+            d_flat = delta.view(obj_img_adv.size(0), -1)
+            n = d_flat.norm(p=2, dim=1).view(obj_img_adv.size(0), 1, 1, 1)
+            r = torch.zeros_like(n).uniform_(0, 1)
+            delta *= r / n * self.eps
+            obj_img_adv = torch.clamp(obj_img_adv + delta, min=0, max=1).detach()
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        tr = self.phy_trans_adv
+        for _ in range(self.steps):
+            obj_img_adv.requires_grad_()
+            z0 = sample(tr.dist_range, batch_size)             # physicalTrans.py:146-155 order
+            al = sample(tr.angle_range, batch_size)
+            adv_scenes, obj_masks_out = self._apply(tr, obj_img_adv, scene_imgs, z0, al)
+            adv_depth = self.model(adv_scenes)
+            cost = -loss(adv_depth * obj_masks_out, self.depth_target)
+            grad = torch.autograd.grad(cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
+            grad = _sync_patch_grad(grad)
+            obj_img_adv = patch_ops.pgd_l2_step(obj_img_adv.detach(), grad, self.obj_img, self.alpha, self.eps,
+                                                self.eps_for_division)
+        tr.reset_img(obj_img_adv, self.obj_mask)
+        z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+        alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+        if eval:
+            z0_sample[0] = 7
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            adv_scenes, obj_masks_out = self._apply(tr, obj_img_adv, scene_imgs, z0_sample, alpha_sample)
+            ben_scenes, _ = self._apply(self.phy_trans_ben, self.obj_img, scene_imgs, z0_sample, alpha_sample)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
+
+
 class Phy_obj_atk_vanila(Attack):
     r"""Drop-in of the reference's `Phy_obj_atk_vanila` (torchattacks/attacks/phy_obj_atk_vanila.py:18-96): no
     optimisation -- a given object image is placed on the scenes at random (or, with `eval`, fixed first) distance /

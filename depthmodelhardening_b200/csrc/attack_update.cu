@@ -4,6 +4,7 @@
 // launch each, with the L0 count kept on the device.
 //
 //   dmh_pgd_linf_step     phy_obj_atk.py:98-100 (same 3 lines: pgd_depth.py:76-78, pgd.py:73-75)
+//   dmh_pgd_l2_step       phy_obj_atk_l2.py:108-120 (gradient normalisation, step, projection onto the L2 ball)
 //   dmh_l0_compose_count  phy_obj_atk_l0.py:94-99 + cal_l0 :43-52
 //   dmh_l0_adam_step      phy_obj_atk_l0.py:130-138 (mask cost gradient + chain through the
 //                         compose clamps + torch.optim.Adam(betas=(0.5,0.9)) update)
@@ -34,6 +35,53 @@ __global__ void pgd_linf_kernel(const float* __restrict__ adv, const float* __re
     const float c = clean[i];
     const float delta = fminf(fmaxf(sub_rn(a, c), -eps), eps);
     out[i] = fminf(fmaxf(add_rn(c, delta), 0.0f), 1.0f);
+}
+
+// --------------------------------------------------------------------------- L2 PGD update (next-4)
+// phy_obj_atk_l2.py:108-120 for the one shared patch, in ONE launch of one CTA (0.94 MB of state: latency-bound):
+//   g = grad / (||grad||_2 + 1e-10);  x = adv + alpha * g;  d = x - clean;
+//   out = clamp(clean + d * min(eps / ||d||_2, 1), 0, 1)
+// Every element-wise operation is rounded as torch rounds it; the two norms are accumulated in double in a fixed
+// order (deterministic; torch.norm's fp32 tree differs from it by ~1e-7 relative).
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    if (wid == 0) v = warp_sum_d(v);
+    if (threadIdx.x == 0) red[0] = v;
+    __syncthreads();
+    v = red[0];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+pgd_l2_kernel(const float* __restrict__ adv, const float* __restrict__ grad, const float* __restrict__ clean,
+              long long n, float alpha, float eps, float eps_div, float* __restrict__ out) {
+    __shared__ double red[32];
+    double ss = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double g = (double)grad[i];
+        ss += g * g;
+    }
+    const float gnorm = add_rn((float)sqrt(block_sum_d(ss, red)), eps_div);
+    ss = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = add_rn(adv[i], mul_rn(alpha, div_rn(grad[i], gnorm)));
+        out[i] = x;                                        // (out may alias adv: element i is read before it is written)
+        const double d = (double)sub_rn(x, clean[i]);
+        ss += d * d;
+    }
+    const float dnorm = (float)sqrt(block_sum_d(ss, red));
+    const float factor = fminf(div_rn(eps, dnorm), 1.0f);  // eps / 0 = inf -> 1
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float c = clean[i];
+        const float d = mul_rn(sub_rn(out[i], c), factor);
+        out[i] = fminf(fmaxf(add_rn(c, d), 0.0f), 1.0f);
+    }
 }
 
 // --------------------------------------------------------------------------- A7
@@ -249,6 +297,15 @@ int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, l
     DMH_REQUIRE(adv && grad && clean && out && n > 0, "dmh_pgd_linf_step: null pointer or n <= 0");
     DMH_LAUNCH(pgd_linf_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(adv, grad, clean, n, alpha, eps, out);
     DMH_CHECK_LAUNCH("dmh_pgd_linf_step");
+    return DMH_OK;
+}
+
+int dmh_pgd_l2_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
+                    float eps_div, float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(adv && grad && clean && out && n > 0, "dmh_pgd_l2_step: null pointer or n <= 0");
+    DMH_REQUIRE(out != grad && out != clean, "dmh_pgd_l2_step: out may alias adv only");
+    DMH_LAUNCH(pgd_l2_kernel, 1, 1024, 0, (cudaStream_t)stream)(adv, grad, clean, n, alpha, eps, eps_div, out);
+    DMH_CHECK_LAUNCH("dmh_pgd_l2_step");
     return DMH_OK;
 }
 

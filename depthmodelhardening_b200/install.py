@@ -80,8 +80,10 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
         _attacks.object_dataset_root = dataset_root
     for mod_name, cls in (("torchattacks.attacks.phy_obj_atk", "Phy_obj_atk"),
                           ("torchattacks.attacks.phy_obj_atk_l0", "Phy_obj_atk_l0"),
-                          ("torchattacks.attacks.phy_obj_atk_vanila", "Phy_obj_atk_vanila"), ("torchattacks", "Phy_obj_atk"),
-                          ("torchattacks", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk_vanila")):
+                          ("torchattacks.attacks.phy_obj_atk_vanila", "Phy_obj_atk_vanila"),
+                          ("torchattacks.attacks.phy_obj_atk_l2", "Phy_obj_atk_l2"), ("torchattacks", "Phy_obj_atk"),
+                          ("torchattacks", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk_vanila"),
+                          ("torchattacks", "Phy_obj_atk_l2")):
         mod = sys.modules.get(mod_name)
         if mod is not None and hasattr(mod, cls):
             setattr(mod, cls, getattr(_attacks, cls))

@@ -258,6 +258,16 @@ def pgd_linf_step(adv, grad, clean, alpha, eps):
     return out
 
 
+def pgd_l2_step(adv, grad, clean, alpha, eps, eps_div=1e-10):
+    """phy_obj_atk_l2.py:108-120 in one launch: normalised-gradient ascent, projection onto the L2 ball of radius
+    eps around the clean patch, clamp to [0,1]."""
+    a, g, c = f32c(adv), f32c(grad), f32c(clean)
+    out = torch.empty_like(a)
+    check(_lib_().dmh_pgd_l2_step(ptr(a), ptr(g), ptr(c), a.numel(), float(alpha), float(eps), float(eps_div), ptr(out),
+                                  stream()), "pgd_l2_step")
+    return out
+
+
 class L0State:
     """Device-resident state of the L0 attack (patterns, Adam moments, counts)."""
 

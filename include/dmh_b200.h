@@ -261,6 +261,12 @@ int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const fl
 int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
                       float* out, dmh_stream_t stream);
 
+/* -- L2 PGD update of the shared patch (next-4; torchattacks/attacks/phy_obj_atk_l2.py:108-120):
+ * g = grad / (||grad||_2 + eps_div); x = adv + alpha*g; d = x - clean;
+ * out = clamp(clean + d * min(eps / ||d||_2, 1), 0, 1).  One launch; out may alias adv.                      */
+int dmh_pgd_l2_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
+                    float eps_div, float* out, dmh_stream_t stream);
+
 /* -- A7 L0 compose + cal_l0 (phy_obj_atk_l0.py:94-99, 43-52): adv (nullable) =
  * clamp(obj + clamp(P+) - clamp(P-)); *count = #pixels whose thresholded pattern is
  * non-zero in any channel (device uint64, overwritten).                              */

@@ -149,6 +149,21 @@ def pgd_linf_step(adv, grad, clean, alpha, eps):
     return torch.clamp(clean + delta, min=0, max=1)
 
 
+def pgd_l2_step(adv, grad, clean, alpha, eps, eps_div=1e-10):
+    """torchattacks/attacks/phy_obj_atk_l2.py:108-120 for the one shared patch (the reference's batch_size is 1
+    there: it views the (1,3,h,w) gradient as (batch_size, -1))."""
+    n = grad.shape[0]
+    grad_norms = torch.norm(grad.view(n, -1), p=2, dim=1) + eps_div
+    grad = grad / grad_norms.view(n, 1, 1, 1)
+    adv = adv + alpha * grad
+    delta = adv - clean
+    delta_norms = torch.norm(delta.view(n, -1), p=2, dim=1)
+    factor = eps / delta_norms
+    factor = torch.min(factor, torch.ones_like(delta_norms))
+    delta = delta * factor.view(-1, 1, 1, 1)
+    return torch.clamp(clean + delta, min=0, max=1)
+
+
 # ----------------------------------------------------------------------------- A7
 def l0_compose(obj, p_pos, p_neg, clip_max=1.0):
     """phy_obj_atk_l0.py:94-99 -- adv patch from the positive/negative patterns."""
@@ -214,7 +229,7 @@ def topk_l0_project(p_pos, p_neg, k):
 
 
 # ----------------------------------------------------------------------------- whole attack loops
-def linf_attack(model, obj, mask, scenes, placements, final_placement, P34, eps, alpha):
+def linf_attack(model, obj, mask, scenes, placements, final_placement, P34, eps, alpha, step=None):
     """phy_obj_atk.py:73-123 with the random placements injected:
     placements = [(z0s, alphas)] per step.  Device agnostic (runs where the tensors live)."""
     import torch.nn as nn
@@ -227,12 +242,19 @@ def linf_attack(model, obj, mask, scenes, placements, final_placement, P34, eps,
         cost = -loss(depth * m, torch.zeros_like(depth))
         grad = torch.autograd.grad(cost, adv)[0]
         with torch.no_grad():
-            adv = pgd_linf_step(adv, grad, obj, alpha, eps)
+            adv = (step or pgd_linf_step)(adv, grad, obj, alpha, eps)
     z0s, als = final_placement
     with torch.no_grad():
         adv_s, m_out = apply_patch(adv, mask, scenes, z0s, als, P34)
         ben_s, _ = apply_patch(obj, mask, scenes, z0s, als, P34)
     return adv_s, ben_s, m_out, adv
+
+
+def l2_attack(model, obj, mask, scenes, placements, final_placement, P34, eps, steps):
+    """phy_obj_atk_l2.py:73-136 (random_start off) with the random placements injected: the L-inf loop with the L2
+    update and the step 2.5 * eps / steps (:44)."""
+    return linf_attack(model, obj, mask, scenes, placements, final_placement, P34, eps, 2.5 * eps / steps,
+                       step=pgd_l2_step)
 
 
 def l0_attack(model, obj, mask, scenes, init_pos, init_neg, placements, final_placement, P34, steps, lr, mask_wt,

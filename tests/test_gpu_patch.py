@@ -244,6 +244,54 @@ def test_linf_attack_class_vs_reference_golden(dev, calib):
         atk(pbt.scenes[:2].clone(), 3)
 
 
+def test_pgd_l2_step_vs_oracle(dev):
+    """dmh_pgd_l2_step (phy_obj_atk_l2.py:108-120 in one launch): inside the ball (no projection), outside it
+    (projection + clamp) and the zero-gradient / zero-delta corner (eps / 0 -> factor 1)."""
+    from depthmodelhardening_b200 import patch_ops
+    clean = synth.rand((1, 3, 260, 300), 1)
+    grad = synth.randn(clean.shape, 3) * 1e-4
+    for adv, alpha, eps in ((clean.clone(), 0.5, 3.0), ((clean + 0.05 * synth.randn(clean.shape, 4)).clamp(0, 1), 2.5, 3.0),
+                            (clean.clone(), 0.0, 1.0)):
+        ref = OQ.pgd_l2_step(adv, grad, clean, alpha, eps)
+        ref64 = OQ.pgd_l2_step(adv.double(), grad.double(), clean.double(), alpha, eps)
+        out = patch_ops.pgd_l2_step(adv.to(dev), grad.to(dev), clean.to(dev), alpha, eps)
+        assert_close_arb(out, ref, ref64, 1e-6, "l2 step alpha=%g" % alpha)
+        assert float((out.cpu() - clean).double().norm()) <= eps * (1 + 1e-6)
+    zero = patch_ops.pgd_l2_step(clean.to(dev), torch.zeros_like(clean).to(dev), clean.to(dev), 0.5, 1.0)
+    assert torch.equal(zero.cpu(), clean)                       # 0 / (0 + 1e-10) = 0; eps / 0 = inf -> factor 1
+
+
+@pytest.mark.parametrize("ev", [False, True])
+def test_l2_attack_class_vs_reference_golden(dev, calib, ev):
+    """Drop-in `Phy_obj_atk_l2` (next-4) against the unmodified reference class at batch size 1
+    (oracle/make_golden_l2.py): same placements, patch within fp32 tolerance (no sign() in this update, so no
+    knife-edge flips), scenes / masks to fp32 tolerance."""
+    import os
+    from depthmodelhardening_b200 import attacks
+    g = load_golden("attack_l2")
+    tag = "eval" if ev else "rand"
+    attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
+    pbt = synth.patch_batch(batch=1, seed=0).to(dev)
+    random.seed(21)
+    atk = attacks.Phy_obj_atk_l2(_tiny(dev), pbt.obj.clone(), pbt.mask.clone(), eps=3.0, steps=3, random_start=False,
+                                 dist_range=list(range(5, 10, 2)))
+    assert atk.alpha == 2.5 * 3.0 / 3
+    adv_s, ben_s, m_out, obj_adv = atk(pbt.scenes.clone(), 1, eval=ev)
+    assert adv_s.shape == (1, 3, 320, 1024) and m_out.shape == (1, 1, 320, 1024) and obj_adv.shape == (1, 3, 260, 300)
+    assert_close(m_out.double().sum(), g[tag + "_mask_sum"], 1e-6)
+    assert_close(ben_s.double().sum(), g[tag + "_ben_sum"], 1e-6)
+    assert_close(obj_adv[:, :, ::2, ::2], g[tag + "_obj_adv"], 2e-4, "patch")      # cuDNN vs CPU convolution gradients
+    assert_close((obj_adv - pbt.obj).double().norm(), g[tag + "_delta_norm"], 1e-5)
+    assert_close(adv_s[:, :, 90:200:2, 380:640:2], g[tag + "_adv_crop"], 2e-4, "adv crop")
+    with pytest.raises(RuntimeError, match="Batch size"):
+        atk(pbt.scenes.repeat(2, 1, 1, 1), 3)
+    # random start (device RNG) stays inside the ball and in [0,1]
+    atk2 = attacks.Phy_obj_atk_l2(_tiny(dev), pbt.obj.clone(), pbt.mask.clone(), eps=0.5, steps=1, random_start=True,
+                                  dist_range=list(range(5, 10, 2)))
+    _, _, _, adv2 = atk2(pbt.scenes.clone(), 1)
+    assert float((adv2 - pbt.obj).norm()) <= 0.5 * (1 + 1e-5) and float(adv2.min()) >= 0 and float(adv2.max()) <= 1
+
+
 def test_l0_attack_class_vs_reference_golden(dev, calib):
     import os
     from depthmodelhardening_b200 import attacks
