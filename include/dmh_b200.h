@@ -139,7 +139,7 @@ int dmh_warp_bwd(const float* grad_warped, const float* disp, int input_is_depth
  * (nullable == zeros), Fi = avg_reprojection ? 1 : F.
  * flags: DMH_PHOTO_*.
  * Outputs:
- *   loss_partial : dmh_photo_blocks(B,H,W) floats, per-CTA sums of to_optimise
+ *   loss_partial : B * dmh_photo_tiles(H,W) floats, per-CTA sums of to_optimise
  *   grad_disp    : (B,1,H,W) = grad_scale * d(sum to_optimise)/d(up-sampled disp); push it
  *                  through dmh_upsample_bilinear_bwd / dmh_disp_grad to reach (disp_h,disp_w)
  *   grad_P_partial (nullable): (F, B, tiles, 12) per-CTA partial sums of
