@@ -79,23 +79,35 @@ template <int NW>
 __global__ void __launch_bounds__(LH_TX * LH_TY)
 lanczos_h_dp4a_kernel(const uint8_t* __restrict__ in, int rows, int in_w, int out_w, const int* __restrict__ bounds,
                       const int* __restrict__ kk, unsigned nwords, uint8_t* __restrict__ out) {
+    // packed weights of the CTA's 64 output columns, built once per CTA: row ty of the block packs word ty, ty + 4, ...
+    __shared__ unsigned sw[3 * NW][LH_TX];
     const int xo = blockIdx.x * LH_TX + threadIdx.x;
     const int r0 = (blockIdx.y * LH_TY + threadIdx.y) * LD_ROWS;
-    if (xo >= out_w || r0 >= rows) return;
-    const int2 bd = __ldg(reinterpret_cast<const int2*>(bounds) + xo);
+    const int xc = min(xo, out_w - 1);
+    const int2 bd = __ldg(reinterpret_cast<const int2*>(bounds) + xc);
     const int xmin = bd.x, cnt = bd.y;
-    unsigned w0[NW], w1[NW], w2[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        w0[w] = w1[w] = w2[w] = 0u;
+    for (int w = threadIdx.y; w < NW; w += LH_TY) {
+        unsigned p0 = 0u, p1 = 0u, p2 = 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int j = 4 * w + i;
-            const int k = (j < cnt) ? __ldg(kk + j * out_w + xo) : 0;          // (ksize, out) layout
-            w0[w] |= (unsigned)(k & 0xff) << (8 * i);
-            w1[w] |= (unsigned)((k >> 8) & 0xff) << (8 * i);
-            w2[w] |= (unsigned)((k >> 16) & 0xff) << (8 * i);                   // signed byte (arithmetic shift)
+            const int k = (j < cnt) ? __ldg(kk + j * out_w + xc) : 0;          // (ksize, out) layout
+            p0 |= (unsigned)(k & 0xff) << (8 * i);
+            p1 |= (unsigned)((k >> 8) & 0xff) << (8 * i);
+            p2 |= (unsigned)((k >> 16) & 0xff) << (8 * i);                      // signed byte (arithmetic shift)
         }
+        sw[w][threadIdx.x] = p0;
+        sw[NW + w][threadIdx.x] = p1;
+        sw[2 * NW + w][threadIdx.x] = p2;
+    }
+    __syncthreads();
+    if (xo >= out_w || r0 >= rows) return;
+    unsigned w0[NW], w1[NW], w2[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        w0[w] = sw[w][threadIdx.x];
+        w1[w] = sw[NW + w][threadIdx.x];
+        w2[w] = sw[2 * NW + w][threadIdx.x];
     }
     const unsigned in_off = (unsigned)((uintptr_t)in & 3);
     const unsigned* __restrict__ base = reinterpret_cast<const unsigned*>(in - in_off);
@@ -208,11 +220,13 @@ lanczos_v_group_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_
         for (int c = 0; c < 4; ++c) acc[g][c] = 1 << (LZ_PRECISION_BITS - 1);
     const int wq = w >> 2;                                 // row pitch in 32-bit words
     const unsigned* p = reinterpret_cast<const unsigned*>(in + ((size_t)blockIdx.z * in_h + ylo) * w + x);
-    unsigned q = __ldg(p);
+    unsigned qa = __ldg(p), qb = (n > 1) ? __ldg(p + wq) : 0u;
+    p += 2 * (size_t)wq;
     for (int t = 0; t < n; ++t) {
-        const unsigned cur = q;
+        const unsigned cur = qa;
+        qa = qb;
+        if (t + 2 < n) qb = __ldg(p);                                           // two rows in flight
         p += wq;
-        if (t + 1 < n) q = __ldg(p);                                            // next row in flight
         const int b0 = cur & 0xffu, b1 = (cur >> 8) & 0xffu, b2 = (cur >> 16) & 0xffu, b3 = cur >> 24;
         const int4 ka = *reinterpret_cast<const int4*>(&sk[t][0]);
         const int4 kb = *reinterpret_cast<const int4*>(&sk[t][4]);
