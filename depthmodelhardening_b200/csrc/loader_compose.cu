@@ -26,6 +26,12 @@ __device__ __forceinline__ uint8_t clip8(int v) {
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// to_tensor of four pixels: byte / 255 with IEEE division (mono_dataset.py:137-144), fused into the last resize pass
+__device__ __forceinline__ float4 bytes_to_float4(unsigned r) {
+    return make_float4(div_rn((float)(r & 0xffu), 255.0f), div_rn((float)((r >> 8) & 0xffu), 255.0f),
+                       div_rn((float)((r >> 16) & 0xffu), 255.0f), div_rn((float)(r >> 24), 255.0f));
+}
+
 // ---- horizontal pass: rows are independent (planes * in_h of them); a thread owns one output column of 4 rows
 #define LH_TX 64
 #define LH_TY 4
@@ -137,7 +143,7 @@ lanczos_h_dp4a_kernel(const uint8_t* __restrict__ in, int rows, int in_w, int ou
 template <int VEC>
 __global__ void __launch_bounds__(128)
 lanczos_v_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, const int* __restrict__ bounds,
-                 const int* __restrict__ kk, int ksize, uint8_t* __restrict__ out) {
+                 const int* __restrict__ kk, int ksize, uint8_t* __restrict__ out, float* __restrict__ out_f32) {
     const int x = (blockIdx.x * 128 + threadIdx.x) * VEC;
     const int yo = blockIdx.y;
     if (x >= w) return;
@@ -169,13 +175,16 @@ lanczos_v_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, con
             }
         }
     }
-    uint8_t* o = out + ((size_t)blockIdx.z * out_h + yo) * w + x;
+    const size_t oi = ((size_t)blockIdx.z * out_h + yo) * w + x;
+    uint8_t* o = out + oi;
     if (VEC == 4) {
         const unsigned r = (unsigned)clip8(acc[0]) | ((unsigned)clip8(acc[1]) << 8) | ((unsigned)clip8(acc[2]) << 16) |
                            ((unsigned)clip8(acc[3]) << 24);
         *reinterpret_cast<unsigned*>(o) = r;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = bytes_to_float4(r);
     } else {
         o[0] = clip8(acc[0]);
+        if (out_f32) out_f32[oi] = div_rn((float)o[0], 255.0f);
     }
 }
 
@@ -187,7 +196,7 @@ lanczos_v_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, con
 #define LV_TS 32                   // rows of the weight table: the union of LV_G spans must fit (checked by the launcher)
 __global__ void __launch_bounds__(128)
 lanczos_v_group_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_h, const int* __restrict__ bounds,
-                       const int* __restrict__ kk, uint8_t* __restrict__ out) {
+                       const int* __restrict__ kk, uint8_t* __restrict__ out, float* __restrict__ out_f32) {
     // sk[t][g]: weight with which input row ylo + t enters output row yo0 + g (0 outside its span): the row loop
     // needs no span test and reads the LV_G weights of a row with two 128-bit broadcast loads
     __shared__ __align__(16) int sk[LV_TS][LV_G];
@@ -236,13 +245,14 @@ lanczos_v_group_kernel(const uint8_t* __restrict__ in, int in_h, int w, int out_
             acc[g][0] += b0 * kv[g]; acc[g][1] += b1 * kv[g]; acc[g][2] += b2 * kv[g]; acc[g][3] += b3 * kv[g];
         }
     }
-    uint8_t* o = out + ((size_t)blockIdx.z * out_h + yo0) * w + x;
+    const size_t oi = ((size_t)blockIdx.z * out_h + yo0) * w + x;
 #pragma unroll
     for (int g = 0; g < LV_G; ++g) {
         if (yo0 + g < out_h) {
             const unsigned r = (unsigned)clip8(acc[g][0]) | ((unsigned)clip8(acc[g][1]) << 8) |
                                ((unsigned)clip8(acc[g][2]) << 16) | ((unsigned)clip8(acc[g][3]) << 24);
-            *reinterpret_cast<unsigned*>(o + (size_t)g * w) = r;
+            *reinterpret_cast<unsigned*>(out + oi + (size_t)g * w) = r;
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi + (size_t)g * w) = bytes_to_float4(r);   // to_tensor
         }
     }
 }
@@ -299,8 +309,9 @@ int dmh_compose_u8(const uint8_t* scene, const float* obj, const float* mask, co
 
 int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h, int out_w, const int* bounds_x,
                    const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp,
-                   uint8_t* out, dmh_stream_t stream) {
+                   uint8_t* out, float* out_f32, dmh_stream_t stream) {
     DMH_REQUIRE(in && out, "dmh_lanczos_u8: null pointer");
+    DMH_REQUIRE(!out_f32 || ((uintptr_t)out_f32 & 15) == 0, "dmh_lanczos_u8: out_f32 must be 16-byte aligned");
     DMH_REQUIRE(planes > 0 && planes <= 65535 && in_h > 0 && in_w > 0 && out_h > 0 && out_h <= 65535 && out_w > 0,
                 "dmh_lanczos_u8: bad shape");
     const bool need_h = out_w != in_w, need_v = out_h != in_h;
@@ -313,6 +324,7 @@ int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h,
             set_error("dmh_lanczos_u8: copy failed");
             return DMH_ERR_CUDA;
         }
+        if (out_f32) return dmh_unpack_u8(out, (long long)planes * in_h * in_w, out_f32, stream);
         return DMH_OK;
     }
     const uint8_t* vin = in;
@@ -342,15 +354,18 @@ int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h,
         const long long group_span = ((long long)(LV_G - 1) * in_h + out_h - 1) / out_h + ksize_y + 1;
         if (vec && group_span <= LV_TS) {
             dim3 grid(ceil_div(out_w, 128 * 4), ceil_div(out_h, LV_G), planes);
-            DMH_LAUNCH(lanczos_v_group_kernel, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, out);
+            DMH_LAUNCH(lanczos_v_group_kernel, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, out, out_f32);
         } else if (vec) {
             dim3 grid(ceil_div(out_w, 128 * 4), out_h, planes);
-            DMH_LAUNCH(lanczos_v_kernel<4>, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, ksize_y, out);
+            DMH_LAUNCH(lanczos_v_kernel<4>, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, ksize_y, out, out_f32);
         } else {
             dim3 grid(ceil_div(out_w, 128), out_h, planes);
-            DMH_LAUNCH(lanczos_v_kernel<1>, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, ksize_y, out);
+            DMH_LAUNCH(lanczos_v_kernel<1>, grid, 128, 0, st)(vin, in_h, out_w, out_h, bounds_y, kk_y, ksize_y, out, out_f32);
         }
         DMH_CHECK_LAUNCH("dmh_lanczos_u8 (vertical)");
+    } else if (out_f32) {
+        // the horizontal pass was the last one: to_tensor as its own (HBM-bound) launch
+        return dmh_unpack_u8(out, (long long)planes * out_h * out_w, out_f32, stream);
     }
     return DMH_OK;
 }

@@ -9,7 +9,7 @@ The reference builds every adversarial training item inside its DataLoader worke
 
 `AdvBatchComposer` does the same for a whole collated batch of raw 8-bit frames that is already on the device:
 one batched perspective launch per warped tensor (`physical.PhysicalTrans`), `dmh_compose_u8`, `dmh_lanczos_u8`
-(Pillow's fixed-point resampling, bit-exact) and `dmh_unpack_u8` (to_tensor).  It is a *host-code change* for a
+(Pillow's fixed-point resampling, bit-exact; `to_tensor` fused into its last pass).  It is a *host-code change* for a
 maintainer (a post-collate hook instead of `prep_adv_data`), which is why it sits outside
 `install()`.  There is no CPU path: tensors must be CUDA tensors.
 
@@ -27,7 +27,6 @@ import torch
 
 from . import _lib, patch_ops
 from .physical import PhysicalTrans
-from .staging import unpack_u8
 
 _PRECISION_BITS = 32 - 8 - 2          # Resample.c: PRECISION_BITS
 _coeff_cache: Dict = {}
@@ -89,9 +88,10 @@ def _need_u8_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def resize_lanczos_u8(img: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+def resize_lanczos_u8(img: torch.Tensor, out_h: int, out_w: int, want_f32: bool = False):
     """uint8 CUDA tensor [..., H, W] -> [..., out_h, out_w]; == `PIL.Image.resize((out_w, out_h), LANCZOS)` plane by
-    plane, bit for bit (`transforms.Resize(..., interpolation=Image.ANTIALIAS)`, mono_dataset.py:100-104)."""
+    plane, bit for bit (`transforms.Resize(..., interpolation=Image.ANTIALIAS)`, mono_dataset.py:100-104).
+    want_f32: also return `to_tensor` of the result (fp32 k/255, written by the last resize pass): (u8, f32)."""
     img = _need_u8_cuda(img, "resize_lanczos_u8 input")
     H, W = img.shape[-2:]
     planes = img.numel() // max(H * W, 1)
@@ -106,19 +106,25 @@ def resize_lanczos_u8(img: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor
     if out_h != H:
         by, ky, ny = _device_coefficients(H, out_h, img.device)
     tmp = torch.empty((planes, H, out_w), dtype=torch.uint8, device=img.device) if (nx and ny) else None
+    f32 = torch.empty(out.shape, dtype=torch.float32, device=img.device) if want_f32 else None
     _lib.check(lib.dmh_lanczos_u8(_lib.ptr(img), planes, H, W, out_h, out_w, _lib.ptr(bx), _lib.ptr(kx), nx,
-                                  _lib.ptr(by), _lib.ptr(ky), ny, _lib.ptr(tmp), _lib.ptr(out), _lib.stream()),
-               "lanczos_u8")
-    return out
+                                  _lib.ptr(by), _lib.ptr(ky), ny, _lib.ptr(tmp), _lib.ptr(out), _lib.ptr(f32),
+                                  _lib.stream()), "lanczos_u8")
+    return (out, f32) if want_f32 else out
 
 
-def pyramid_u8(img: torch.Tensor, height: int, width: int, num_scales: int = 4):
+def pyramid_u8(img: torch.Tensor, height: int, width: int, num_scales: int = 4, want_f32: bool = False):
     """MonoDataset.preprocess (mono_dataset.py:126-131): level i = Resize(height // 2^i, width // 2^i) of level i-1
-    (level -1 = the native-resolution image); 8-bit levels."""
+    (level -1 = the native-resolution image); 8-bit levels -- with want_f32 the list of their `to_tensor` images
+    (:137-144) instead, each written by the last pass of its resize."""
     out, cur = [], img
     for i in range(num_scales):
-        cur = resize_lanczos_u8(cur, height // (2 ** i), width // (2 ** i))
-        out.append(cur)
+        if want_f32:
+            cur, f = resize_lanczos_u8(cur, height // (2 ** i), width // (2 ** i), want_f32=True)
+            out.append(f)
+        else:
+            cur = resize_lanczos_u8(cur, height // (2 ** i), width // (2 ** i))
+            out.append(cur)
     return out
 
 
@@ -299,8 +305,8 @@ class AdvBatchComposer:
             S = self.num_scales
             # the three composites go through the pyramid as one stack: 2 resize passes + 1 unpack per level
             names = (("color_aug", 0), ("color_aug", "s"), ("color", 0))
-            for i, lvl in enumerate(pyramid_u8(comp.view((3 * B,) + tuple(color_0.shape[1:])), self.height, self.width, S)):
-                f = unpack_u8(lvl)
+            for i, f in enumerate(pyramid_u8(comp.view((3 * B,) + tuple(color_0.shape[1:])), self.height, self.width, S,
+                                             want_f32=True)):
                 for j, (name, fid) in enumerate(names):
                     out[(name, fid, i)] = f[j * B:(j + 1) * B]
             for i in range(S):                                        # :257: color['s'] is color_aug['s']
@@ -308,7 +314,7 @@ class AdvBatchComposer:
             out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
             if not self.half_no_synthesis:
                 # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
-                om = unpack_u8(resize_lanczos_u8(objmask, self.height, self.width))
+                _, om = resize_lanczos_u8(objmask, self.height, self.width, want_f32=True)
                 out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1).contiguous()
                 out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
                                                        device=color_0.device)

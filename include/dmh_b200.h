@@ -360,10 +360,11 @@ int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float
  * out (planes, out_h, out_w).  bounds_* (out, 2) int32 = (first input index, tap count), kk_* (ksize, out) int32
  * weights (tap-major, so that neighbouring outputs read neighbouring weights): host-computed in double precision as Pillow does (depthmodelhardening_b200/loader.py
  * lanczos_coefficients); an axis that keeps its size is skipped and needs no tables.  tmp: (planes, in_h, out_w)
- * bytes, needed when both axes change. */
+ * bytes, needed when both axes change.  out_f32 (nullable, 16-byte aligned): additionally out / 255 in fp32 --
+ * `to_tensor` of the resized image (:137-144), written by the last pass instead of a separate dmh_unpack_u8. */
 int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h, int out_w, const int* bounds_x,
                    const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp,
-                   uint8_t* out, dmh_stream_t stream);
+                   uint8_t* out, float* out_f32, dmh_stream_t stream);
 
 /* 8-bit frame transport (data format either side of the path): out[i] = (float)in[i] / 255 with IEEE division --
  * torchvision's `to_tensor` (`pic.to(float32).div(255)`), the conversion every colour frame of the reference goes

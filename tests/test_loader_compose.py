@@ -121,6 +121,11 @@ def test_cuda_resize_is_bit_exact(dev, size):
     out = loader.resize_lanczos_u8(torch.from_numpy(img).to(dev), oh, ow)
     assert out.shape == (2, 3, oh, ow) and out.dtype == torch.uint8
     assert np.array_equal(out.cpu().numpy(), R.resize_lanczos_u8(img, oh, ow))
+    # to_tensor fused into the last pass (every kernel variant: row-group / 4-column / scalar vertical pass,
+    # horizontal-only, no resize at all): the same bytes and exactly byte / 255
+    out2, f32 = loader.resize_lanczos_u8(torch.from_numpy(img).to(dev), oh, ow, want_f32=True)
+    assert torch.equal(out2, out) and f32.dtype == torch.float32
+    assert torch.equal(f32.cpu(), out.cpu().to(torch.float32).div(255))
 
 
 @pytest.mark.gpu
