@@ -225,8 +225,8 @@ def compose_bench(dev, args, lib):
         for i in range(S):
             im = im.resize((W >> i, H >> i), Image.LANCZOS)
     cpu_ms_item = (time.perf_counter() - t0) / reps * 1e3
-    # bytes: 2 raw frames in, 3 composites + mask plane out and in again, 3 pyramids (u8 out / in, fp32 out), the
-    # horizontal-pass intermediates out / in
+    # bytes: 2 raw frames in, 3 composites + mask plane out and in again, 3 pyramids (u8 out, in again as the next
+    # level's input, fp32 out), the horizontal-pass intermediates out / in
     px, pyr_px = 375 * 1242, sum((H >> i) * (W >> i) for i in range(S))
     bytes_item = 3 * px * (2 + 3 * 2) + 2 * px + 3 * 3 * pyr_px * (2 + 4) + 2 * 3 * 3 * 375 * W
     print(json.dumps({"workload": "training-batch compositing on the device (next-2: prep_adv_data + preprocess)",
@@ -235,7 +235,7 @@ def compose_bench(dev, args, lib):
                       "approx_bytes_per_batch": bytes_item * B, "approx_gbs": bytes_item * B / (ms * 1e-3) / 1e9,
                       "cpu_pillow_pyramids_ms_per_item": cpu_ms_item, "cpu_cores": 1,
                       "note": "GPU: 2 fused warp+composite launches (the fp32 canvases are never materialised), the three "
-                              "composites resized as one stack (2 passes + 1 unpack per level) + the mask image; CPU figure: only the three 4-level Pillow pyramids of one item on one core "
+                              "composites resized as one stack (2 passes per level, to_tensor fused into the second) + the mask image; CPU figure: only the three 4-level Pillow pyramids of one item on one core "
                               "(the reference additionally warps and composites on the CPU, ~1 s per item)"}))
 
 

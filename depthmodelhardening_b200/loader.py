@@ -315,7 +315,8 @@ class AdvBatchComposer:
             if not self.half_no_synthesis:
                 # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
                 _, om = resize_lanczos_u8(objmask, self.height, self.width, want_f32=True)
-                out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1).contiguous()
+                # (a stride-0 view: the trainer reads channel 0 only, M2/trainer.py:552; .contiguous() if needed)
+                out[("color_objmask", 0, 0)] = om.expand(-1, 3, -1, -1)
                 out[("objdepth", 0, 0)] = torch.tensor([[[float(z)]] for z in z0_sample], dtype=torch.float32,
                                                        device=color_0.device)
         return out
