@@ -72,7 +72,6 @@ def main():
         pil = lambda a: Image.fromarray(np.transpose(a, (1, 2, 0)))
         inputs = {("color", 0, -1): pil(c0), ("color", "s", -1): pil(cs)}
         # the placement draw of project(batch_size=1) (:207 / :216) is pinned through random.sample's two calls
-        import random
         seq = iter([[z0], [alpha]])
         orig = ref.physicalTrans.sample
         ref.physicalTrans.sample = lambda rng, n: next(seq)
