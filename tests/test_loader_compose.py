@@ -93,6 +93,28 @@ def test_oracle_composer_matches_reference_golden(ci):
     assert n == 4 * S + 2
 
 
+@pytest.mark.parametrize("n", [(1242, 1024), (1024, 512), (375, 320), (47, 121)])
+def test_dp4a_weight_split_is_exact(n):
+    """The arithmetic identity behind lanczos_h_dp4a_kernel, emulated in integer numpy: every 22-bit weight splits
+    into k2 * 65536 + k1 * 256 + k0 (k0, k1 unsigned bytes, k2 a signed byte), so a span is three 8-bit dot products
+    whose recombination (in wrapping 32-bit arithmetic, as the kernel does it) equals Pillow's 32-bit accumulator."""
+    from depthmodelhardening_b200 import loader
+    bounds, kk = loader.lanczos_coefficients(*n)
+    k = kk.astype(np.int64)
+    k0, k1, k2 = k & 0xff, (k >> 8) & 0xff, k >> 16                 # arithmetic shift: k2 is signed
+    assert np.array_equal(k2 * 65536 + k1 * 256 + k0, k)
+    assert k2.min() >= -128 and k2.max() <= 127
+    rng = np.random.default_rng(n[0])
+    for px in (rng.integers(0, 256, kk.shape), np.full(kk.shape, 255), np.zeros(kk.shape, np.int64)):
+        px = px.astype(np.int64)
+        direct = (1 << 21) + (px * k).sum(1)
+        d0, d1, d2 = (px * k0).sum(1), (px * k1).sum(1), (px * k2).sum(1)
+        wrapped = ((1 << 21) + d0 + (d1 << 8) + ((d2 << 16) & 0xffffffff)) & 0xffffffff
+        wrapped = np.where(wrapped >= 1 << 31, wrapped - (1 << 32), wrapped)     # reinterpret as int32
+        assert np.array_equal(wrapped, direct)
+        assert np.abs(direct).max() < 1 << 31
+
+
 def test_composer_rejects_cpu_tensors():
     from depthmodelhardening_b200 import loader
     with pytest.raises(RuntimeError, match="CUDA-only"):
