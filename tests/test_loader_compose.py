@@ -115,6 +115,36 @@ def test_dp4a_weight_split_is_exact(n):
         assert np.abs(direct).max() < 1 << 31
 
 
+@pytest.mark.parametrize("n", [(375, 320), (320, 160), (160, 80), (80, 40), (375, 190), (375, 192), (97, 45)])
+def test_row_group_weight_table_covers_every_span(n):
+    """Host-side restatement of lanczos_v_group_kernel's weight table: for every group of 8 output rows the union of
+    the spans starts at the first row's span, fits the launcher's bound (the formula dmh_lanczos_u8 uses to choose
+    the kernel) and the zero-padded table reproduces each output's own weighted sum."""
+    from depthmodelhardening_b200 import loader
+    G, TS = 8, 32
+    in_h, out_h = n
+    bounds, kk = loader.lanczos_coefficients(in_h, out_h)
+    ksize = kk.shape[1]
+    group_span = ((G - 1) * in_h + out_h - 1) // out_h + ksize + 1          # as in dmh_lanczos_u8
+    col = np.random.default_rng(in_h).integers(0, 256, in_h).astype(np.int64)
+    for yo0 in range(0, out_h, G):
+        last = min(yo0 + G, out_h) - 1
+        ylo, yhi = int(bounds[yo0, 0]), int(bounds[last, 0] + bounds[last, 1])
+        assert all(bounds[yo0 + g, 0] >= ylo and bounds[yo0 + g, 0] + bounds[yo0 + g, 1] <= yhi
+                   for g in range(last - yo0 + 1))
+        assert yhi - ylo <= group_span
+        if group_span > TS:
+            continue                                                         # the launcher takes the per-row kernel
+        table = np.zeros((TS, G), dtype=np.int64)
+        for g in range(last - yo0 + 1):
+            lo, cnt = bounds[yo0 + g]
+            table[lo - ylo:lo - ylo + cnt, g] = kk[yo0 + g, :cnt]
+        acc = (table[:yhi - ylo] * col[ylo:yhi, None]).sum(0)
+        for g in range(last - yo0 + 1):
+            lo, cnt = bounds[yo0 + g]
+            assert acc[g] == int((kk[yo0 + g, :cnt].astype(np.int64) * col[lo:lo + cnt]).sum())
+
+
 def test_composer_rejects_cpu_tensors():
     from depthmodelhardening_b200 import loader
     with pytest.raises(RuntimeError, match="CUDA-only"):
