@@ -1,7 +1,7 @@
 """Host -> device staging of a training batch as ONE transfer.
 
 The reference moves its batch dictionary tensor by tensor (`inputs[key] = ipt.to(self.device)`,
-`M2/trainer.py:262-263`): ~20 separate copies per step, each paying its own launch and PCIe ramp.
+`M2/trainer.py:338-339`): ~20 separate copies per step, each paying its own launch and PCIe ramp.
 `BatchArena` lays the dictionary out in one pinned host buffer and one device buffer of the same layout
 (256-byte aligned slots); `upload()` is a single `cudaMemcpyAsync`, the tensors handed to the kernels are views.
 """
