@@ -3,7 +3,7 @@
 // for a whole collated batch instead of per item inside DataLoader workers.
 //
 //   dmh_compose_u8   to_tensor(scene) * (1 - m) + obj * m  ->  to_pilimage  (`.mul(255).byte()`: truncation),
-//                    optional per-item horizontal flip of the warped patch / mask (mono_dataset.py:226-234)
+//                    optional per-item horizontal flip of the warped patch / mask (mono_dataset.py:222-228)
 //   dmh_lanczos_u8   PIL.Image.resize(size, ANTIALIAS) on 8-bit planes -- Pillow's fixed-point Lanczos
 //                    (libImaging/Resample.c: 22-bit integer weights, horizontal pass then vertical pass,
 //                    each rounded and clipped to 8 bits).  Integer arithmetic: results are bit-exact.

@@ -130,8 +130,8 @@ def pyramid_u8(img: torch.Tensor, height: int, width: int, num_scales: int = 4, 
 
 def compose_u8(scene: Optional[torch.Tensor], obj: torch.Tensor, mask: Optional[torch.Tensor],
                flip: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """to_pilimage(to_tensor(scene) * (1 - mask) + obj * mask) as 8-bit planes (mono_dataset.py:229-236); `flip`
-    (B,) int32: items whose warped patch and mask are mirrored first (:226-228).  scene None: to_pilimage(obj)."""
+    """to_pilimage(to_tensor(scene) * (1 - mask) + obj * mask) as 8-bit planes (mono_dataset.py:227-236); `flip`
+    (B,) int32: items whose warped patch and mask are mirrored first (:222-225).  scene None: to_pilimage(obj)."""
     lib = _lib.load()
     obj = _lib.f32c(obj)
     B, C, H, W = obj.shape
@@ -259,7 +259,7 @@ class AdvBatchComposer:
                  synthesize: Optional[Sequence[bool]] = None):
         """color_0 / color_s: (B,3,ori_H,ori_W) uint8 CUDA -- frame 0 and its stereo partner at native resolution, as
         `get_color` returns them (already mirrored for the items with do_flip, mono_dataset.py:325-329); sides[i]:
-        'l' / 'r', the side frame 0 of item i was taken from; do_flip[i]: mirror the warped patch too (:226-228);
+        'l' / 'r', the side frame 0 of item i was taken from; do_flip[i]: mirror the warped patch too (:222-225);
         z0_sample / alpha_sample: one placement per item (drawn like `PhysicalTrans.project` if None);
         synthesize[i] (only with half_no_synthesis, :321-328; drawn with `random.random() > 0.5` if None): items
         with False keep their raw frames -- ("color_objmask", 0, 0) / ("objdepth", 0, 0) are then not produced at all,
@@ -309,7 +309,7 @@ class AdvBatchComposer:
                                              want_f32=True)):
                 for j, (name, fid) in enumerate(names):
                     out[(name, fid, i)] = f[j * B:(j + 1) * B]
-            for i in range(S):                                        # :257: color['s'] is color_aug['s']
+            for i in range(S):                                        # :258: color['s'] is color_aug['s']
                 out[("color", "s", i)] = out[("color_aug", "s", i)]
             out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
             if not self.half_no_synthesis:

@@ -334,10 +334,10 @@ int dmh_const_div_exact(int c);
  * 186-265, 119-144), which the reference runs per item inside DataLoader workers on the CPU.
  *
  * dmh_compose_u8: out = (uint8) trunc(255 * (scene/255 * (1 - mask) + obj * mask)) -- to_tensor, the composite
- * (:229-230, 246-249) and to_pilimage (`.mul(255).byte()`, :235-236, 251) in one pass; every fp32 operation
+ * (:227-228, 246-249) and to_pilimage (`.mul(255).byte()`, :235-236, 251) in one pass; every fp32 operation
  * rounded as torch's CPU kernels round it.  scene (B,C,H,W) u8, obj (B,C,H,W) f32 (the warped patch, from
  * dmh_perspective_fwd), mask (B,1,H,W) f32, flip (B) int32 or NULL: items whose warped patch / mask are mirrored
- * horizontally first (torch.flip(..., [3]), :226-228).  scene == NULL: out = trunc(255 * obj) (the `color_objmask`
+ * horizontally first (torch.flip(..., [3]), :222-225).  scene == NULL: out = trunc(255 * obj) (the `color_objmask`
  * image, :254; mask may be NULL). */
 int dmh_compose_u8(const uint8_t* scene, const float* obj, const float* mask, const int* flip, int B, int C, int H,
                    int W, uint8_t* out, dmh_stream_t stream);

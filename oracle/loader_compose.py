@@ -34,7 +34,7 @@ def to_pil_u8(t: torch.Tensor) -> np.ndarray:
 
 
 def compose_u8(scene_u8: np.ndarray, obj: torch.Tensor, mask: torch.Tensor, flip: bool) -> np.ndarray:
-    """scene_u8 [3,H,W] uint8, obj [1,3,H,W], mask [1,1,H,W] fp32 -> uint8 [3,H,W] (mono_dataset.py:193, 226-236)."""
+    """scene_u8 [3,H,W] uint8, obj [1,3,H,W], mask [1,1,H,W] fp32 -> uint8 [3,H,W] (mono_dataset.py:193, 222-236)."""
     s = torch.from_numpy(scene_u8).to(torch.float32).div(255).unsqueeze(0)     # to_tensor
     if flip:
         obj, mask = torch.flip(obj, [3]), torch.flip(mask, [3])
