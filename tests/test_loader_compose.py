@@ -145,6 +145,34 @@ def test_row_group_weight_table_covers_every_span(n):
             assert acc[g] == int((kk[yo0 + g, :cnt].astype(np.int64) * col[lo:lo + cnt]).sum())
 
 
+def test_oracle_enhance_equals_pillow():
+    """Groundwork for the colour jitter: oracle/pil_enhance.py restates the four ColorJitter
+    steps on 8-bit PIL images (mono_dataset.py:297, 344-350 -> torchvision functional_pil -> PIL.ImageEnhance /
+    convert('HSV')) and equals the installed Pillow / torchvision bit for bit."""
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from oracle import pil_enhance as E
+    rng = np.random.default_rng(3)
+    rand_img = rng.integers(0, 256, (3, 61, 83), dtype=np.uint8)
+    rand_img[:, :4] = rand_img[0:1, :4]                                   # grey pixels (max == min)
+    # a dense sweep of the colour cube: every (r, g) pair with 17 blue levels -> 1.1 M colours
+    r, g, b = np.meshgrid(np.arange(256), np.arange(256), np.arange(0, 256, 15), indexing="ij")
+    cube = np.stack([r.reshape(1024, -1), g.reshape(1024, -1), b.reshape(1024, -1)]).astype(np.uint8)
+    for img in (rand_img, cube):
+        pil = Image.fromarray(np.ascontiguousarray(np.transpose(img, (1, 2, 0))))
+        as_np = lambda im: np.transpose(np.asarray(im), (2, 0, 1))
+        hsv = as_np(pil.convert("HSV"))
+        assert np.array_equal(E.rgb_to_hsv(img), hsv)
+        back = Image.fromarray(np.ascontiguousarray(np.transpose(hsv, (1, 2, 0))), "HSV").convert("RGB")
+        assert np.array_equal(E.hsv_to_rgb(hsv), as_np(back))
+        for f in (0.8, 0.8731, 1.0, 1.1999, 1.2, 0.0, 0.5, 1.7):
+            assert np.array_equal(E.brightness(img, f), as_np(TF.adjust_brightness(pil, f))), ("brightness", f)
+            assert np.array_equal(E.contrast(img, f), as_np(TF.adjust_contrast(pil, f))), ("contrast", f)
+            assert np.array_equal(E.saturation(img, f), as_np(TF.adjust_saturation(pil, f))), ("saturation", f)
+        for f in (-0.1, -0.0371, 0.0, 0.05, 0.1, 0.5, -0.5):
+            assert np.array_equal(E.hue(img, f), as_np(TF.adjust_hue(pil, f))), ("hue", f)
+
+
 def test_composer_rejects_cpu_tensors():
     from depthmodelhardening_b200 import loader
     with pytest.raises(RuntimeError, match="CUDA-only"):
