@@ -153,3 +153,48 @@ def test_fast_path_arithmetic_vs_reference_golden(emu, name):
                           outlier_frac=5e-3 if name == "stereo_iid" else 2e-3)
         if automask:
             assert np.mean((sel.numpy() > 0).astype(np.uint8) != g["ident_sel_%d" % s]) < 1e-3
+
+
+# ----------------------------------------------------------------------------- colour jitter (groundwork)
+@pytest.fixture(scope="module")
+def emu_jitter():
+    src = os.path.join(HERE, "host_emul_jitter.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "depthmodelhardening_b200", "csrc", "jitter_math.cuh")
+    so = os.path.join(BUILD, "libdmh_hostemu_jitter.so")
+    os.makedirs(BUILD, exist_ok=True)
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.emu_grey_sum.restype = C.c_longlong
+    return lib
+
+
+def test_colour_jitter_math_vs_oracle(emu_jitter):
+    """csrc/jitter_math.cuh (the per-pixel formulas a jitter kernel will use) compiled with g++ equals
+    oracle/pil_enhance.py -- which equals Pillow / torchvision bit for bit -- over a sweep of the colour cube, for
+    factors inside and outside [0, 1] and every hue shift class."""
+    import numpy as np
+    from oracle import pil_enhance as E
+    r, g, b = np.meshgrid(np.arange(256), np.arange(256), np.arange(0, 256, 15), indexing="ij")
+    img = np.ascontiguousarray(np.stack([r.reshape(1024, -1), g.reshape(1024, -1), b.reshape(1024, -1)]).astype(np.uint8))
+    n = img.shape[1] * img.shape[2]
+
+    def run(op, f=0.0, aux=0):
+        out = np.empty_like(img)
+        emu_jitter.emu_jitter(C.c_void_p(img.ctypes.data), C.c_longlong(n), C.c_int(op), C.c_float(f), C.c_int(aux),
+                              C.c_void_p(out.ctypes.data))
+        return out
+
+    assert emu_jitter.emu_grey_sum(C.c_void_p(img.ctypes.data), C.c_longlong(n)) == int(E.grey(img).astype(np.int64).sum())
+    mean = int(E.grey(img).astype(np.float64).mean() + 0.5)
+    for f in (0.8, 0.8731, 1.0, 1.1999, 1.2, 0.0, 0.5, 1.7):
+        assert np.array_equal(run(0, f), E.brightness(img, f)), ("brightness", f)
+        assert np.array_equal(run(1, f, mean), E.contrast(img, f)), ("contrast", f)
+        assert np.array_equal(run(2, f), E.saturation(img, f)), ("saturation", f)
+    hsv = E.rgb_to_hsv(img)
+    assert np.array_equal(run(4), hsv)
+    img_keep, img = img, hsv
+    assert np.array_equal(run(5), E.hsv_to_rgb(hsv))
+    img = img_keep
+    for f in (-0.1, -0.0371, 0.0, 0.05, 0.1, 0.5, -0.5):
+        assert np.array_equal(run(3, aux=int(f * 255) & 0xff), E.hue(img, f)), ("hue", f)
