@@ -33,6 +33,7 @@ import torch  # noqa: E402
 H, W = 320, 1024
 SCALES = (0, 1, 2, 3)
 FRAME_IDS = (0, "s")
+GLOBAL_BATCH = 32           # north_star: batch 32 sharded across the GPUs (strong-scaling sub-record)
 METRIC = "reproj_loss_fwd_bwd_mpix_per_s"
 UNIT = "Mpix/s"
 
@@ -53,7 +54,10 @@ def parse_args():
     ap.add_argument("--no-patch", action="store_true", help="skip stage 1 (debug)")
     ap.add_argument("--attack", default="l0", choices=["l0", "linf"],
                     help="stage-1 update rule: l0 = README config (--norm_type l_0), linf = sign/project step")
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="batch slice of the CPU legs (0: cpu_baseline 8; --impl reference: adaptive, see reference_arm)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (sharded batch 32) sub-record")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-on-the-same-GPU baseline")
     return ap.parse_args()
 
 
@@ -162,6 +166,7 @@ class Stage1:
         self.adv = self.g.obj.clone()
         self.world = world
         self.attack = attack
+        self.gbuf = None
         if attack == "l0":      # M2/trainer.py:216-218: adam_lr 0.5, mask_wt 0.06, l0_thresh 0.1
             self.l0 = patch_ops.L0State(self.g.obj, self.g.pattern_pos, self.g.pattern_neg, lr=0.5, betas=(0.5, 0.9))
             self.first = True
@@ -172,11 +177,17 @@ class Stage1:
         if self.attack == "l0":
             self.adv = self.l0.compose_count(first=self.first)
             self.first = False
-        adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream)
         if self.world > 1:
-            from depthmodelhardening_b200 import dist as D
-            # the ONE collective of the step: patch gradient + scalar attack loss in a single all-reduce
-            grad_patch, _ = D.allreduce_patch_grad(grad_patch, [adv_scene.new_zeros(())], average=True)
+            # the ONE collective of the step: the backward kernel writes the patch gradient straight into the
+            # all-reduce buffer (the scalar attack loss rides in its last element); all-reduce in place
+            if self.gbuf is None:
+                self.gbuf = torch.zeros(self.adv.numel() + 1, device=self.adv.device)
+            adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream,
+                                                                      grad_out=self.gbuf)
+            torch.distributed.all_reduce(self.gbuf)
+            self.gbuf.div_(self.world)
+        else:
+            adv_scene, mask_out, grad_patch = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream)
         if self.attack == "l0":
             self.l0.adam_step(grad_patch, 0.06, 0.1)
         else:
@@ -205,28 +216,95 @@ def timed_loop(fn, steps, warmup, world):
     return ms / steps
 
 
+def measure_strong(args, rank, world, device, global_batch):
+    """Strong scaling (north_star / SURVEY.md 8(e)): the batch-32 step with the batch SHARDED over the ranks.
+    Same step as the headline (stage 1 + the one all-reduce + stage 2); timed eagerly and as a CUDA-graph replay of
+    the whole step (the all-reduce included): with 4 items per GPU the eager step is launch-bound."""
+    if global_batch % world != 0:
+        return {"error": "global batch %d not divisible by %d ranks" % (global_batch, world)}
+    Bs = global_batch // world
+    pb, pt = make_host_workload(Bs, rank, True)
+    s2 = Stage2(pb, device)
+    s1 = Stage1(pt, device, world, args.attack)
+
+    def step():
+        s1.step()
+        return s2.step()
+
+    steps = max(args.steps, 20)
+    ms_eager = timed_loop(step, steps, max(args.warmup, 3), world)
+    out = {"global_batch": global_batch, "per_gpu_batch": Bs, "n_gpus": world, "ms_per_step_eager": ms_eager,
+           "value_eager": global_batch * H * W / (ms_eager * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong"}
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    cur.wait_stream(side)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    ms_graph = timed_loop(graph.replay, steps, max(args.warmup, 3), world)
+    out.update({"ms_per_step": ms_graph, "value": global_batch * H * W / (ms_graph * 1e-3) / 1e6,
+                "note": "ms_per_step / value: CUDA-graph replay of the whole step (stage 1, NCCL all-reduce of the "
+                        "patch gradient, stage 2 fwd+bwd) captured once; *_eager: the same step launched from Python. "
+                        "The L0 Adam bias-correction step index is frozen in the replay (timing only)."})
+    return out
+
+
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_reference_step(sample_batch, with_patch, threads=None, attack="l0"):
-    """The reference algorithm on the host cores: oracle restatement (the
-    reference itself is Python and does not travel to the GPU box)."""
+def reference_available():
+    """The unmodified reference: /root/reference in the build container, else the copy that build() placed under
+    oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot)."""
+    try:
+        from oracle import refload
+        return refload.available()
+    except Exception:
+        return False
+
+
+def reference_step(sample_batch, with_patch, device="cpu", attack="l0", seed=7):
+    """One step of the hot path executed by the REFERENCE'S OWN CODE (oracle/ref_step.py: Trainer.generate_images_pred
+    + compute_losses + backward; the L0 PGD iteration on the reference's PhysicalTrans) on `device`."""
+    from depthmodelhardening_b200 import synth
+    from oracle import ref_step
+    pb = synth.photo_batch(batch=sample_batch, height=H, width=W, frame_ids=FRAME_IDS, scales=SCALES, seed=seed)
+    pt = synth.patch_batch(batch=sample_batch, seed=seed) if with_patch else None
+    if device != "cpu":
+        pb = pb.to(device)
+        pt = pt.to(device) if pt is not None else None
+    s2 = ref_step.Stage2Reference(pb, device)
+    s1 = ref_step.Stage1Reference(pt, device) if pt is not None else None
+
+    def step():
+        if s1 is not None:
+            s1.step()
+        return s2.step()["loss"]
+    return step
+
+
+def cpu_port_step(sample_batch, with_patch, attack="l0"):
+    """Fallback when the reference copy is absent: the oracle restatement (kind "port")."""
     import numpy as np
     from depthmodelhardening_b200 import synth
     from oracle import patch as OQ
     from oracle import photometric as OP
-    if threads:
-        torch.set_num_threads(threads)
+    from oracle.refload import CALIB_P2
     pb = synth.photo_batch(batch=sample_batch, height=H, width=W, frame_ids=FRAME_IDS, scales=SCALES, seed=7)
     pt = synth.patch_batch(batch=sample_batch, seed=7) if with_patch else None
-    P34 = np.array(OQ_P2(), dtype=np.float64).reshape(3, 4)
+    P34 = np.array(CALIB_P2, dtype=np.float64).reshape(3, 4)
     state = {}
-    if pt is not None and attack == "l0":
+    if pt is not None:
         state["pp"] = pt.pattern_pos.clone().requires_grad_(True)
         state["pn"] = pt.pattern_neg.clone().requires_grad_(True)
         state["opt"] = torch.optim.Adam([state["pp"], state["pn"]], lr=0.5, betas=(0.5, 0.9))
 
     def step():
-        if pt is not None and attack == "l0":
-            # one iteration of phy_obj_atk_l0.py:94-138 with the network gradient supplied
+        if pt is not None:
             adv, pos, neg = OQ.l0_compose(pt.obj, state["pp"], state["pn"])
             OQ.l0_count(pos, neg)
             scene, _ = OQ.apply_patch(adv, pt.mask, pt.scenes, pt.z0, pt.alpha, P34)
@@ -234,58 +312,99 @@ def cpu_reference_step(sample_batch, with_patch, threads=None, attack="l0"):
             state["opt"].zero_grad()
             cost.backward()
             state["opt"].step()
-        elif pt is not None:
-            obj = pt.obj.clone().requires_grad_(True)
-            adv, _ = OQ.apply_patch(obj, pt.mask, pt.scenes, pt.z0, pt.alpha, P34)
-            (adv * pt.upstream).sum().backward()
-            OQ.pgd_linf_step(obj.detach(), obj.grad, pt.obj, 0.02, 0.1)
         OP.objective_from_batch(pb)
     return step
 
 
-def OQ_P2():
-    from oracle.refload import CALIB_P2
-    return CALIB_P2
+def cpu_step_factory(with_patch, attack):
+    """(make_step(batch), kind)"""
+    if reference_available():
+        return (lambda nb: reference_step(nb, with_patch, "cpu", attack)), "reference"
+    return (lambda nb: cpu_port_step(nb, with_patch, attack)), "port"
 
 
-def run_cpu_baseline(sample_batch, with_patch, reps=8, attack="l0"):
-    step = cpu_reference_step(sample_batch, with_patch, attack=attack)
+def run_cpu_baseline(sample_batch, with_patch, reps=6, attack="l0"):
+    torch.set_num_threads(os.cpu_count() or 1)
+    make, kind = cpu_step_factory(with_patch, attack)
+    step = make(sample_batch)
     step()
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
-    return {"value": sample_batch * H * W / dt / 1e6, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle (torch-CPU restatement of the reference) on a batch-%d slice of the 1024x320 workload, "
-                      "%d reps, %.2f s/step" % (sample_batch, reps, dt)}
+    what = ("the reference's own code (oracle/_ref copy: Trainer.generate_images_pred + compute_losses + backward; L0 "
+            "PGD iteration on its PhysicalTrans)" if kind == "reference" else "oracle port (torch-CPU restatement)")
+    return {"value": sample_batch * H * W / dt / 1e6, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%s on a batch-%d slice of the 1024x320 workload, %d reps after 1 warm-up, %.2f s/step"
+                      % (what, sample_batch, reps, dt)}
 
 
 def reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the step on the box's host cores, with every
+    host thread, on this arm's config / metric / unit.  --steps / --warmup are honoured; the per-step sample is the
+    largest batch (<= the per-GPU batch) for which the whole run is projected to end within ~4 minutes."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sb = args.cpu_sample_batch
     with_patch = not args.no_patch
-    step = cpu_reference_step(sb, with_patch, attack=args.attack)
-    for _ in range(min(args.warmup, 1)):
+    make, kind = cpu_step_factory(with_patch, args.attack)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_s = float(os.environ.get("DMH_REF_BUDGET_S", "240"))
+    sb = args.cpu_sample_batch if args.cpu_sample_batch > 0 else args.batch
+    while True:
+        step = make(sb)
+        t0 = time.perf_counter()
+        step()                                             # first call: lazy initialisation + a first timing
+        t1 = time.perf_counter()
         step()
-    steps = max(1, min(args.steps, 12))
+        probe = time.perf_counter() - t1
+        if sb <= 1 or probe * (steps + warmup) <= budget_s:
+            break
+        sb = max(1, sb // 2)
+    for _ in range(max(0, warmup - 2)):
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
     val = sb * H * W / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: monodepth2 1024x320 stereo [0,'s'], 4 scales, automask; "
-                                   "patch PGD step + photometric loss fwd/bwd", "sample_batch": sb,
-                       "per_gpu_batch": args.batch},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "oracle port on a batch-%d slice, %d steps (the reference is pure Python and "
-                                       "cannot travel to the GPU box)" % (sb, steps)},
+            "config": workload_config(args.attack, with_patch, args.batch, world),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": "batch-%d slice per step (largest power-of-two fraction of the per-GPU batch %d "
+                                       "that keeps %d + %d steps within %.0f s on these cores), %.2f s/step"
+                                       % (sb, args.batch, steps, warmup, budget_s, dt)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def workload_config(attack, with_patch, B, world):
+    return {"workload": "configs[1]: monodepth2 1024x320 stereo [0,'s'], 4 scales, automask, SSIM+L1, "
+                        "smoothness; step = patch PGD step (stage 1, %s update) + photometric loss fwd/bwd (stage 2)" % attack
+                        if with_patch else "configs[1] stage 2 only: photometric loss fwd/bwd",
+            "per_gpu_batch": B, "global_batch": B * world, "height": H, "width": W, "frame_ids": list(FRAME_IDS),
+            "scales": list(SCALES), "l2_policy": "inputs (2x126 MB frames + 168 MB noise) exceed the 126 MB L2"}
+
+
+def gpu_eager_baseline(B, with_patch, attack, device, steps=6):
+    """The reference's own code (stock eager PyTorch: ATen / cuDNN-free elementwise + grid_sample kernels) on the
+    SAME B200, same workload: what the graft buys over running the unmodified repository on this GPU."""
+    step = reference_step(B, with_patch, device, attack)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps, "kind": "reference",
+            "what": "the unmodified reference (oracle/_ref copy) on cuda: Trainer.generate_images_pred + compute_losses "
+                    "+ backward and one L0 PGD iteration on its PhysicalTrans, per-GPU batch %d, CUDA events" % B}
 
 
 # ----------------------------------------------------------------------------- main
@@ -360,25 +479,36 @@ def main():
 
         ms_overlap = timed_loop(step_overlapped, args.steps, 2, world)
 
-    # dominant kernel: the fused per-scale objective kernel, timed with events around its launches
+    # dominant kernel, timed live with CUDA events around its launches on the launching stream: the one-launch
+    # multi-scale objective kernel (photo_ms_kernel, csrc/photo_ms.cu) -- or, with DMH_MULTISCALE=0, the per-scale
+    # kernel (one launch per scale, alternating two streams: span of the step's group / launches in it)
     from depthmodelhardening_b200 import ops
     ops.KERNEL_EVENTS = []
     for _ in range(3):
         s2.step()
     torch.cuda.synchronize()
+    ev_ms = [(a, b) for (name, a, b) in ops.KERNEL_EVENTS if name == "photo_ms"]
     ev = [(a, b) for (name, a, b) in ops.KERNEL_EVENTS if name == "photo_scale"]
     ops.KERNEL_EVENTS = None
-    # the per-scale launches of a step alternate between two streams and overlap at their tails: the time of one
-    # launch is the span of the step's group (first start -> last end) divided by the launches in it
     S_ = len(SCALES)
-    kt = []
-    for i in range(0, len(ev) - S_ + 1, S_):
-        grp = ev[i:i + S_]
-        span = max(grp[0][0].elapsed_time(b) for (_, b) in grp) - min(grp[0][0].elapsed_time(a) for (a, _) in grp)
-        kt += [span / S_] * S_
-    kms = sum(kt) / max(len(kt), 1)
     F = len(FRAME_IDS) - 1
-    k_bytes = (12 + 12 * F + 4 + 4 * F + 4 * F + 4) * B * H * W
+    sigma_disp = sum(4.0 ** (-s) for s in range(S_))
+    if ev_ms:
+        kt = [a.elapsed_time(b) for (a, b) in ev_ms]
+        kernel_name = "photo_ms_kernel<FASTDIV, PIPE=1, 2 CTAs/SM> (dmh_photo_multiscale: all %d scales in one launch)" % S_
+        # compulsory traffic of the launch (fp32): target 12 + packed source 16 (the (B,H,W,4) layout it is handed)
+        # + identity loss 4 + per scale (tie-break noise 4 + gradient 4) + the disparity pyramid 4 * sum 4^-s
+        k_px = 12 + 16 + 4 + S_ * (4 + 4) + 4 * sigma_disp
+    else:
+        kt = []
+        for i in range(0, len(ev) - S_ + 1, S_):
+            grp = ev[i:i + S_]
+            span = max(grp[0][0].elapsed_time(b) for (_, b) in grp) - min(grp[0][0].elapsed_time(a) for (a, _) in grp)
+            kt += [span / S_] * S_
+        kernel_name = "photo_fast_kernel<TMA,FASTDIV,PACKED,UP> (dmh_photo_scale, one launch per scale)"
+        k_px = 12 + 12 * F + 4 + 4 * F + 4 * F + 4
+    kms = sum(kt) / max(len(kt), 1)
+    k_bytes = k_px * B * H * W
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -414,8 +544,9 @@ def main():
         # the batch dictionary lives in ONE pinned arena: one cudaMemcpyAsync per step instead of ~20
         from depthmodelhardening_b200.staging import BatchArena
         arena = BatchArena(host, device, slots=2)
-        for k, v in arena.host_views().items():
-            v.copy_(host[k])
+        for sl_ in range(2):
+            for k, v in arena.host_views(sl_).items():
+                v.copy_(host[k])
         slots = [arena.device_views(i) for i in range(2)]
         for sl in slots:
             for k in sl:
@@ -515,8 +646,9 @@ def main():
         host.update({("T", k): pin(v) for k, v in pb_host.T.items()})
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         arena = BatchArena(host, device, slots=2)
-        for k, v in arena.host_views().items():
-            v.copy_(host[k])
+        for sl_ in range(2):
+            for k, v in arena.host_views(sl_).items():
+                v.copy_(host[k])
         slots = [arena.device_views(i) for i in range(2)]
         for sl in slots:
             for k in sl:
@@ -607,20 +739,36 @@ def main():
         if s1 is not None:
             s1.g.scenes = scenes_f32
 
-    # DRAM traffic and instruction count of the dominant kernel per launch: from the committed `ncu --set full`
-    # capture of this same command (profiles/r01_ncu_full_x.txt; mean of the 4 per-scale launches at B=32)
-    ncu_traffic = 419.1e6 if (B == 32 and F == 1) else None
-    ncu_warp_inst = 244.4e6 if (B == 32 and F == 1) else None
+    # DRAM traffic / instruction count of the dominant kernel per launch are NOT measured by this run: they are read
+    # from the committed ncu capture of this command (profiles/r02_ncu_photo_ms.json, written by
+    # profiles/summarize_ncu.py --json) when it describes the same kernel and batch; otherwise null
+    ncu_traffic = ncu_warp_inst = None
+    ncu_src = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_photo_ms.json")))
+        if cap.get("batch") == B and bool(ev_ms) and cap.get("kernel", "").startswith("photo_ms"):
+            ncu_traffic = cap.get("dram_bytes_per_launch")
+            ncu_warp_inst = cap.get("warp_instructions_per_launch")
+            ncu_src = "profiles/r02_ncu_photo_ms.json (%s)" % cap.get("source", "ncu --set full")
+    except Exception:
+        pass
     sm_clock_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-    roofline = {"bound": "hbm", "kernel": "photo_fast_kernel<TMA,FASTDIV,PACKED,UP> (dmh_photo_scale, one launch per scale)",
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                "traffic": ncu_traffic,
+                "traffic": ncu_traffic, "traffic_source": ncu_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                 "kernel_ms": kms, "kernel_launches_timed": len(kt), "algorithmic_bytes_per_launch": k_bytes,
+                "algorithmic_bytes_per_px": k_px,
+                # continuity with round 1, whose accounting charged every scale its own copy of the target / source /
+                # identity loss (40 B per pixel and scale): the same kernel time against S x 40 B/px
+                "frac_round1_accounting": (40.0 * S_ * B * H * W / (kms * 1e-3) / 1e9 / peak) if (kms > 0 and ev_ms) else None,
                 "step_algorithmic_bytes": step_bytes_total,
                 "step_hbm_frac": step_bytes_total / (ms_step * 1e-3) / 1e9 / peak,
-                "note": "traffic == algorithmic bytes (no re-reads) but the kernel is fp32 instruction-issue bound, "
-                        "not HBM bound: see issue_frac"}
+                "note": "DRAM traffic ~ algorithmic bytes (no re-reads) but the kernel is fp32 instruction-issue "
+                        "bound, not HBM bound (see issue_frac): fusing the scales REMOVED compulsory bytes (target, "
+                        "source and identity loss are read once instead of once per scale), so `frac` of the fused "
+                        "launch is lower than round 1's per-scale figure although the launch is faster; "
+                        "step_hbm_frac (SURVEY.md 8(d) whole-step bytes / step time) is the comparable number"}
     if ncu_warp_inst and kms > 0:
         # fraction of the SM issue slots (148 SMs x 4 schedulers x 1 warp-instruction / clock) the kernel uses
         roofline["issue_frac"] = ncu_warp_inst / (kms * 1e-3) / (148 * 4 * sm_clock_hz)
@@ -651,8 +799,24 @@ def main():
         line["e2e_u8_frames"] = e2e_u8
     if e2e_composer is not None:
         line["e2e_composer"] = e2e_composer
+    if not args.no_strong and s1 is not None:
+        # north_star's scaling configuration: GLOBAL batch 32 sharded over the ranks (32/16/8/4 items per GPU)
+        try:
+            line["strong_scaling"] = measure_strong(args, rank, world, device, GLOBAL_BATCH)
+        except Exception as exc:
+            line["strong_scaling"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch, s1 is not None, attack=args.attack)
+        line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch or 8, s1 is not None, attack=args.attack)
+    if rank == 0 and world == 1 and not args.no_gpu_eager and reference_available():
+        try:
+            # free this arm's buffers first: the eager reference keeps ~10 full-size tensors per scale alive
+            del s2, s1
+            torch.cuda.empty_cache()
+            ge = gpu_eager_baseline(B, with_patch, args.attack, device)
+            ge["graft_speedup"] = ge["ms_per_step"] / ms_step
+            line["gpu_eager_baseline"] = ge
+        except Exception as exc:                            # informational: never take the bench down with it
+            line["gpu_eager_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if world > 1:
         torch.distributed.destroy_process_group()
     sys.stdout.flush()

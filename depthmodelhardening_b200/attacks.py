@@ -47,6 +47,15 @@ class Attack(object):
         self._model_training = False
         self._batchnorm_training = False
         self._dropout_training = False
+        # multi-GPU universal patch: set to a torch.distributed group (or True for the default group) to all-reduce
+        # the patch gradient and broadcast the starting point; None (default) = no collective at all
+        self.sync_group = None
+
+    def enable_patch_sync(self, group=True):
+        """Opt in to the shared-patch collectives; every rank of `group` must run the attack in
+        lock-step with the same `steps`."""
+        self.sync_group = group
+        return self
 
     def forward(self, *input):
         raise NotImplementedError
@@ -68,12 +77,29 @@ class Attack(object):
         return images
 
 
-def _sync_patch_grad(grad):
-    """The ONE collective of stage 1: mean of the shared patch's gradient over
-    ranks (equals the single-process gradient of the global-batch mean)."""
+def _sync_patch_grad(attack, grad):
+    """The ONE collective of stage 1 -- mean of the shared patch's gradient over the ranks of `attack.sync_group`
+    (equals the single-process gradient of the global-batch mean).  OPT-IN: without a sync group the attack is a
+    purely local computation, also when torch.distributed is initialised (ordinary DDP training calls the attack
+    independently on every rank, with different RNG draws and possibly different iteration counts: a collective
+    keyed on `dist.is_initialized()` would deadlock there)."""
+    group = getattr(attack, "sync_group", None)
+    if group is None:
+        return grad
     from . import dist as _dist
-    g, _ = _dist.allreduce_patch_grad(grad, (), average=True)
+    g, _ = _dist.allreduce_patch_grad(grad, (), average=True, group=_dist.resolve_group(group))
     return g
+
+
+def _sync_initial_state(attack, *tensors):
+    """With a sync group: the starting point of the shared patch (random start / L0 patterns) is rank 0's on every
+    rank, so that the identical update after each all-reduce keeps the patches bit-identical -- and with them the L0
+    counts, i.e. every rank takes the same early-break decision and leaves the loop at the same step."""
+    group = getattr(attack, "sync_group", None)
+    if group is None:
+        return
+    from . import dist as _dist
+    _dist.broadcast_patch_state(tensors, group=_dist.resolve_group(group))
 
 
 def _tile_scenes(images, batch_size):
@@ -118,6 +144,7 @@ class Phy_obj_atk(Attack):
         if self.random_start:
             obj_img_adv = obj_img_adv + torch.empty_like(obj_img_adv).uniform_(-self.eps, self.eps)
             obj_img_adv = torch.clamp(obj_img_adv, min=0, max=1).detach()
+        _sync_initial_state(self, obj_img_adv)
         self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
         tr = self.phy_trans_adv
         for _ in range(self.steps):
@@ -128,7 +155,7 @@ class Phy_obj_atk(Attack):
             adv_depth = self.model(adv_scenes)
             cost = -loss(adv_depth * obj_masks_out, self.depth_target)
             grad = torch.autograd.grad(cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
-            grad = _sync_patch_grad(grad)
+            grad = _sync_patch_grad(self, grad)
             obj_img_adv = patch_ops.pgd_linf_step(obj_img_adv.detach(), grad, self.obj_img, self.alpha, self.eps)
         tr.reset_img(obj_img_adv, self.obj_mask)
         z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
@@ -179,7 +206,7 @@ class Phy_obj_atk_l2(Phy_obj_atk):
             adv_depth = self.model(adv_scenes)
             cost = -loss(adv_depth * obj_masks_out, self.depth_target)
             grad = torch.autograd.grad(cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
-            grad = _sync_patch_grad(grad)
+            grad = _sync_patch_grad(self, grad)
             obj_img_adv = patch_ops.pgd_l2_step(obj_img_adv.detach(), grad, self.obj_img, self.alpha, self.eps,
                                                 self.eps_for_division)
         tr.reset_img(obj_img_adv, self.obj_mask)
@@ -280,6 +307,7 @@ class Phy_obj_atk_l0(Attack):
             init_pattern = np.random.random(self.obj_img.size()) * self.clip_max
             init_pattern = np.clip(init_pattern, 0.0, self.clip_max) / self.clip_max
             inits.append(torch.Tensor(init_pattern).to(self.device))
+        _sync_initial_state(self, *inits)
         st = patch_ops.L0State(self.obj_img, inits[0], inits[1], lr=self.learning_rate, betas=(0.5, 0.9),
                                clip_max=float(self.clip_max))
         self._state = st
@@ -305,7 +333,7 @@ class Phy_obj_atk_l0(Attack):
             adv_depth = self.model(adv_scenes)
             adv_cost = loss(adv_depth * adv_obj_mask, self.depth_target)
             grad = torch.autograd.grad(adv_cost, obj_img_adv, retain_graph=False, create_graph=False)[0]
-            grad = _sync_patch_grad(grad)
+            grad = _sync_patch_grad(self, grad)
             # mask cost gradient + clamp chain + Adam in one launch; mask_weight gated on the device
             st.adam_step(grad, self.mask_weight_init, self.l0_thresh)
         if self.topk is not None:

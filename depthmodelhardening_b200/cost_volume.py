@@ -20,9 +20,12 @@ def cost_volume(current_feats, lookup_feats, relative_poses, K, invK, depth_bins
     matching resolution, depth_bins (D,) -> (cost_volume (B,D,h,w), missing_mask (B,D,h,w)).  No gradient."""
     with torch.no_grad():
         cur, look, pose = f32c(current_feats), f32c(lookup_feats), f32c(relative_poses)
-        k, ik = f32c(K), f32c(invK)
-        bins = f32c(depth_bins.to(cur.device)).reshape(-1)
         B, C, h, w = cur.shape
+        from .ops import _mat_batch
+        k, ik = f32c(_mat_batch(K, B, "K")), f32c(_mat_batch(invK, B, "invK"))   # the kernel indexes K + b*16
+        bins = f32c(depth_bins.to(cur.device)).reshape(-1)
+        if pose.dim() != 4 or pose.shape[0] != B or tuple(pose.shape[2:]) != (4, 4):
+            raise RuntimeError("relative_poses must be (B, L, 4, 4), got %s" % (tuple(pose.shape),))
         if look.dim() != 5 or look.shape[0] != B or look.shape[2:] != (C, h, w):
             raise RuntimeError("lookup_feats must be (B, L, C, h, w) matching current_feats %s, got %s" %
                                (tuple(cur.shape), tuple(look.shape)))

@@ -172,9 +172,10 @@ class _ObjectiveDH(torch.autograd.Function):
         Ts = [f32c(next(it)) for _ in range(n_src)]
         disps = [f32c(next(it)) for _ in range(S)]
         noises = [f32c(next(it)) for _ in range(S)] if has_noise else [None] * S
-        k, ik = f32c(K), f32c(inv_K)
         target = colors[0]
         B, _, H, W = target.shape
+        k, ik = f32c(ops._mat_batch(K, B, "K")), f32c(ops._mat_batch(inv_K, B, "inv_K"))
+        Ts = [f32c(ops._mat_batch(t, B, "T")) for t in Ts]
         dev = target.device
         lib = _lib_()
         idn = f32c(ident) if ident is not None else None

@@ -48,21 +48,40 @@ def shard_batch(tensors: Dict, batch: int, rank: Optional[int] = None, world_siz
     return out
 
 
-def allreduce_patch_grad(grad: torch.Tensor, scalars: Sequence[torch.Tensor] = (), average: bool = True):
+def resolve_group(group):
+    """True / None -> the default process group; a ProcessGroup -> itself."""
+    return None if group is True or group is None else group
+
+
+def broadcast_patch_state(tensors: Sequence[torch.Tensor], src: int = 0, group=None) -> None:
+    """Make the shared patch's starting point (random start, L0 patterns) rank `src`'s on every rank, in place."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    for t in tensors:
+        dist.broadcast(t, src=src, group=group)
+
+
+def allreduce_patch_grad(grad: torch.Tensor, scalars: Sequence[torch.Tensor] = (), average: bool = True, group=None,
+                         out: Optional[torch.Tensor] = None):
     """Sum `grad` (the shared patch's gradient) over ranks; `scalars` (0-dim
     tensors, e.g. the attack loss) are appended to the same flat buffer so the
     step costs ONE collective.  Returns (grad, [scalars...]) -- identical on
     every rank, so the sign / Adam / threshold update that follows stays
-    bit-identical across ranks."""
-    r, w = world()
+    bit-identical across ranks.  Without scalars the all-reduce runs in place on `grad` (no staging launches)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return grad, list(scalars)
+    w = dist.get_world_size(group)
     if w == 1:
         return grad, list(scalars)
     n = grad.numel()
-    buf = torch.empty(n + len(scalars), device=grad.device, dtype=grad.dtype)
-    buf[:n].copy_(grad.reshape(-1))
-    for i, s in enumerate(scalars):
-        buf[n + i] = s.to(grad.dtype)
-    dist.all_reduce(buf)
+    if len(scalars) == 0 and grad.is_contiguous():
+        buf = grad.view(-1)                      # in place: no staging buffer, no copy
+    else:
+        buf = out if out is not None else torch.empty(n + len(scalars), device=grad.device, dtype=grad.dtype)
+        buf[:n].copy_(grad.reshape(-1))
+        for i, s in enumerate(scalars):
+            buf[n + i] = s.to(grad.dtype)
+    dist.all_reduce(buf, group=group)
     if average:
         buf.div_(w)
     return buf[:n].view_as(grad), [buf[n + i] for i in range(len(scalars))]

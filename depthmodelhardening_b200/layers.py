@@ -36,7 +36,8 @@ class BackprojectDepth(nn.Module):
         if depth.shape[2] != self.height * self.width:
             raise RuntimeError("shape '[%d, 1, %d]' is invalid for input of size %d" %
                                (self.batch_size, self.height * self.width, depth.numel()))
-        return ops._Backproject.apply(depth.view(self.batch_size, 1, self.height, self.width), inv_K,
+        return ops._Backproject.apply(depth.view(self.batch_size, 1, self.height, self.width),
+                                      ops._mat_batch(inv_K, self.batch_size, "inv_K"),
                                       self.batch_size, self.height, self.width)
 
 
@@ -54,7 +55,9 @@ class Project3D(nn.Module):
         if points.shape[0] != self.batch_size or points.shape[-1] != self.height * self.width:
             raise RuntimeError("shape '[%d, 2, %d, %d]' is invalid for input of size %d" %
                                (self.batch_size, self.height, self.width, points.shape[0] * 2 * points.shape[-1]))
-        return ops._Project3D.apply(points, K, T, self.batch_size, self.height, self.width, float(self.eps))
+        B = self.batch_size
+        return ops._Project3D.apply(points, ops._mat_batch(K, B, "K"), ops._mat_batch(T, B, "T"), B, self.height,
+                                    self.width, float(self.eps))
 
 
 class SSIM(nn.Module):

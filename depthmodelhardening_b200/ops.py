@@ -41,6 +41,23 @@ def _lib_():
     return _lib.load()
 
 
+def _mat_batch(m: torch.Tensor, B: int, name: str) -> torch.Tensor:
+    """(B,4,4) camera matrix for a kernel that indexes `m + b*16`.  The reference relies on broadcasting -- ManyDepth's
+    `match_features` hands (1,4,4) matrices to `BackprojectDepth(batch_size=96)` / `Project3D`
+    (MD/networks/resnet_encoder.py:182,194) -- so a batch-1 matrix is expanded; anything else raises (torch.matmul
+    would raise for it too) instead of reading past the end of the buffer.  The gradient of an expanded matrix is
+    summed back over the batch by autograd's expand."""
+    if m.dim() == 2:
+        m = m.unsqueeze(0)
+    if m.dim() != 3 or tuple(m.shape[1:]) != (4, 4):
+        raise RuntimeError("%s must be (B,4,4) or (1,4,4), got %s" % (name, tuple(m.shape)))
+    if m.shape[0] == B:
+        return m
+    if m.shape[0] == 1:
+        return m.expand(B, 4, 4)
+    raise RuntimeError("%s holds %d matrices but the batch is %d (only a batch of 1 broadcasts)" % (name, m.shape[0], B))
+
+
 # ----------------------------------------------------------------------------- A9
 def disp_to_depth_cuda(disp: torch.Tensor, min_depth: float, max_depth: float):
     d = f32c(disp)
@@ -318,7 +335,9 @@ def warp_reproject(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input
     """disp (B,1,H,W) [or depth] + src (B,C,H,W) -> src warped into the target view.
     One gather kernel for trainer.py:485-519 (disp_to_depth, BackprojectDepth,
     Project3D, grid_sample(border, align_corners=True))."""
-    return _WarpFused.apply(disp, src, K, inv_K, T, float(min_depth), float(max_depth), bool(input_is_depth))
+    B = src.shape[0]
+    return _WarpFused.apply(disp, src, _mat_batch(K, B, "K"), _mat_batch(inv_K, B, "inv_K"), _mat_batch(T, B, "T"),
+                            float(min_depth), float(max_depth), bool(input_is_depth))
 
 
 def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_is_depth=False, align_corners=True,
@@ -326,7 +345,9 @@ def warp_with_aux(disp, src, K, inv_K, T, min_depth=0.1, max_depth=100.0, input_
     """No-grad variant also returning the sampling grid and the depth map
     (the tensors the reference stores in `outputs` for logging).  align_corners=False: the sampling convention of
     the depth-hints warp (`F.grid_sample` default, DH/trainer.py:523-525)."""
-    d, s, k, ik, t = f32c(disp), f32c(src), f32c(K), f32c(inv_K), f32c(T)
+    B = src.shape[0]
+    d, s, k, ik, t = (f32c(disp), f32c(src), f32c(_mat_batch(K, B, "K")), f32c(_mat_batch(inv_K, B, "inv_K")),
+                      f32c(_mat_batch(T, B, "T")))
     B, Cc, H, W = s.shape
     out = torch.empty_like(s)
     grid = torch.empty(B, H, W, 2, device=s.device, dtype=torch.float32) if want_aux else None
@@ -400,8 +421,10 @@ def photo_scale_sum(disp_full, target, srcs: Sequence[torch.Tensor], Ts: Sequenc
                     input_is_depth=False, want_sel=False):
     flags = (FLAG_NO_SSIM if no_ssim else 0) | (FLAG_AVG_REPROJECTION if avg_reprojection else 0) | \
             (FLAG_INPUT_IS_DEPTH if input_is_depth else 0)
-    return _PhotoScale.apply(disp_full, target, ident, noise, K, inv_K, float(min_depth), float(max_depth), flags,
-                             bool(want_sel), len(srcs), *srcs, *Ts)
+    B = target.shape[0]
+    return _PhotoScale.apply(disp_full, target, ident, noise, _mat_batch(K, B, "K"), _mat_batch(inv_K, B, "inv_K"),
+                             float(min_depth), float(max_depth), flags, bool(want_sel), len(srcs), *srcs,
+                             *[_mat_batch(t, B, "T") for t in Ts])
 
 
 # ----------------------------------------------------------------------------- whole multi-scale objective
@@ -417,6 +440,9 @@ SPLIT_PATH = _os.environ.get("DMH_SPLIT", "0") in ("1", "2")
 # DMH_SPLIT=2: the persistent producer / consumer kernel (one launch per scale, warp of tile i+1 beside SSIM of tile i;
 # bit-identical, measured 520-550 us per scale -- 16 warps per SM issue less than the fused kernel's 24)
 PIPELINED = _os.environ.get("DMH_SPLIT", "0") == "2"
+# all scales of the single-source objective in one launch (csrc/photo_ms.cu, bit-identical to the per-scale launches);
+# DMH_MULTISCALE=0 keeps one launch per scale
+MULTISCALE = _os.environ.get("DMH_MULTISCALE", "1") != "0"
 
 
 def _side_stream(dev, which=0):
@@ -489,9 +515,26 @@ class _Objective(torch.autograd.Function):
                                            stream()), "smooth_fused")
         # the per-scale launches are independent of each other: odd scales go to a second stream so that the
         # tail of one launch (10240 CTAs = 23.06 waves of 444) overlaps the head of the next
+        multiscale = (packed and MULTISCALE and not split and S <= 4 and W % 4 == 0 and target.data_ptr() % 16 == 0
+                      and H * W < (1 << 27))
+        if multiscale:
+            # ONE launch for all scales (csrc/photo_ms.cu): the scale loop of generate_images_pred / compute_losses
+            # runs inside the kernel; same bits as the per-scale launches below
+            for s in range(S):
+                parts.append(torch.empty(B * tiles, device=dev, dtype=torch.float32))
+                G.append(torch.empty(B, 1, H, W, device=dev, dtype=torch.float32))
+                gPs.append(None)
+                sels.append(torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None)
+            dh_ = (_C.c_int * S)(*[d.shape[2] for d in disps])
+            dw_ = (_C.c_int * S)(*[d.shape[3] for d in disps])
+            with _timed("photo_ms"):
+                check(lib.dmh_photo_multiscale(ptr(target), ptr(src_pk), ptr(Ts[0]), S, ptr_array(disps), dh_, dw_, ptr(k),
+                                               ptr(ik), ptr(ident), ptr_array(noises) if has_noise else None, B, H, W,
+                                               min_depth, max_depth, inv_den, ptr_array(parts), ptr_array(G),
+                                               ptr_array(sels) if want_sel else None, stream()), "photo_multiscale")
         alt = _side_stream(dev, 1)
         alt.wait_stream(cur)
-        for s in range(S):
+        for s in range(S if not multiscale else 0):
             d = disps[s]
             h, w = d.shape[2], d.shape[3]
             part = torch.empty(B * tiles, device=dev, dtype=torch.float32)
@@ -591,5 +634,7 @@ def objective(colors0, srcs, Ts, disps, K, inv_K, noises=None, min_depth=0.1, ma
     has_noise = automask and noises is not None and all(n is not None for n in noises)
     cfg = (float(min_depth), float(max_depth), flags, tuple(smooth_weights), bool(want_sel), n_src, S, bool(automask),
            has_noise)
+    B = colors0[0].shape[0]
+    Ts = [_mat_batch(t, B, "T") for t in Ts]
     tensors = list(colors0) + list(srcs) + list(Ts) + list(disps) + (list(noises) if has_noise else [])
-    return _Objective.apply(K, inv_K, cfg, *tensors)
+    return _Objective.apply(_mat_batch(K, B, "K"), _mat_batch(inv_K, B, "inv_K"), cfg, *tensors)

@@ -229,9 +229,12 @@ def apply_patch(obj, mask, scenes, coeffs, size=(320, 1024)):
     return _PatchApply.apply(obj, mask, scenes, coeffs, int(size[0]), int(size[1]))
 
 
-def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024)):
+def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024), grad_out=None):
     """No-autograd fast path for a PGD iteration whose upstream gradient
-    d(cost)/d(adv_scene) is already known: returns (adv, mask_out, grad_patch)."""
+    d(cost)/d(adv_scene) is already known: returns (adv, mask_out, grad_patch).
+    grad_out: optional flat fp32 buffer of >= obj.numel() elements that receives the patch gradient in its head
+    (zeroed here).  Multi-GPU callers hand in the all-reduce buffer itself, with room for the scalar attack loss
+    in the tail: the one collective of the step then runs in place, without staging launches."""
     o, m, s, up = f32c(obj), f32c(mask), f32c(scenes), f32c(upstream)
     co, bb, bw, bh = _unpack(coeffs)
     _, _, ph, pw = o.shape
@@ -239,7 +242,14 @@ def apply_patch_fwd_bwd(obj, mask, scenes, coeffs, upstream, size=(320, 1024)):
     oh, ow = int(size[0]), int(size[1])
     adv = torch.empty(B, 3, oh, ow, device=o.device, dtype=torch.float32)
     mout = torch.empty(B, 1, oh, ow, device=o.device, dtype=torch.float32)
-    gp = torch.zeros(1, 3, ph, pw, device=o.device, dtype=torch.float32)
+    if grad_out is None:
+        gp = torch.zeros(1, 3, ph, pw, device=o.device, dtype=torch.float32)
+    else:
+        if (grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.dim() != 1
+                or grad_out.numel() < o.numel() or grad_out.device != o.device):
+            raise RuntimeError("grad_out must be a contiguous 1-D fp32 buffer of >= %d elements on %s" % (o.numel(), o.device))
+        grad_out.zero_()
+        gp = grad_out[:o.numel()].view(1, 3, ph, pw)
     lib = _lib_()
     check(lib.dmh_patch_apply_fwd(ptr(o), ptr(m), ptr(s), ptr(co), ptr(bb), B, ph, pw, ih, iw, oh, ow, ptr(adv),
                                   ptr(mout), stream()), "patch_apply_fwd")

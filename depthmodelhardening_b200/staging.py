@@ -2,8 +2,13 @@
 
 The reference moves its batch dictionary tensor by tensor (`inputs[key] = ipt.to(self.device)`,
 `M2/trainer.py:338-339`): ~20 separate copies per step, each paying its own launch and PCIe ramp.
-`BatchArena` lays the dictionary out in one pinned host buffer and one device buffer of the same layout
-(256-byte aligned slots); `upload()` is a single `cudaMemcpyAsync`, the tensors handed to the kernels are views.
+`BatchArena` lays the dictionary out in a pinned host buffer and a device buffer of the same layout (256-byte
+aligned entries), one pair per slot; `upload()` is a single `cudaMemcpyAsync`, the tensors handed to the kernels are
+views.
+
+Double-buffering contract: slot k's pinned buffer may be refilled only after its previous upload has finished --
+`upload(k)` records an event, `host_views(k)` waits for it (host-side) before handing the views out, so filling
+batch k+1 while batch k uploads or computes can never tear a batch.
 """
 from __future__ import annotations
 
@@ -24,8 +29,9 @@ class BatchArena:
             self.layout[k] = (off, tuple(v.shape), v.dtype, n)
             off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
         self.nbytes = off
-        self.host = torch.empty(off, dtype=torch.uint8).pin_memory()
+        self.hosts = [torch.empty(off, dtype=torch.uint8).pin_memory() for _ in range(slots)]
         self.dev = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(slots)]
+        self._uploaded = [None] * slots                    # event of the last H2D copy that read hosts[k]
 
     def _views(self, buf):
         out = {}
@@ -33,9 +39,17 @@ class BatchArena:
             out[k] = buf[off:off + n].view(dtype).view(shape)
         return out
 
-    def host_views(self) -> Dict[Hashable, torch.Tensor]:
-        """Pinned host tensors to fill (e.g. as DataLoader collate targets)."""
-        return self._views(self.host)
+    @property
+    def host(self):
+        return self.hosts[0]
+
+    def host_views(self, slot: int = 0) -> Dict[Hashable, torch.Tensor]:
+        """Pinned host tensors of `slot` to fill (e.g. as DataLoader collate targets).  Blocks until the last upload
+        from this slot's pinned buffer has completed (the DMA engine may still be reading it)."""
+        ev = self._uploaded[slot]
+        if ev is not None:
+            ev.synchronize()
+        return self._views(self.hosts[slot])
 
     def device_views(self, slot: int) -> Dict[Hashable, torch.Tensor]:
         return self._views(self.dev[slot])
@@ -43,10 +57,12 @@ class BatchArena:
     def upload(self, slot: int, stream=None) -> None:
         """One async H2D copy of the whole batch into device slot `slot` (on `stream` or the current stream)."""
         if stream is None:
-            self.dev[slot].copy_(self.host, non_blocking=True)
-        else:
-            with torch.cuda.stream(stream):
-                self.dev[slot].copy_(self.host, non_blocking=True)
+            stream = torch.cuda.current_stream(self.dev[slot].device)
+        with torch.cuda.stream(stream):
+            self.dev[slot].copy_(self.hosts[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._uploaded[slot] = ev
 
 
 def unpack_u8(src: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:

@@ -182,6 +182,27 @@ int dmh_photo_scale_split(const float* target, const float* src, const float* T,
                           float min_depth, float max_depth, int flags, float grad_scale, float* workspace,
                           float* loss_partial, float* grad_disp, uint8_t* sel, dmh_stream_t stream);
 
+/* ALL scales of the single-source objective in one launch (DepthNetworks/monodepth2/trainer.py:476-523 and
+ * :589-660 -- the `for scale in self.opt.scales` loops of generate_images_pred and compute_losses run inside the
+ * kernel: a CTA owns one 32 x 32 target tile and walks over the S <= 4 scales).  Same contract and the same bits as
+ * S calls of dmh_photo_scale with F == 1, DMH_PHOTO_SRC_PACKED, SSIM on, disparity input, no pose gradient:
+ * src_packed = the (B,H,W,4) copy written by dmh_identity_loss_pack; disp_host[s] (B,1,disp_h[s],disp_w[s]);
+ * noise_host[s] (B,1,H,W) or NULL; loss_partial_host[s] receives B*dmh_photo_tiles(H,W) floats (the first
+ * B*ceil(H/32)*ceil(W/32) are written); grad_disp_host[s] (B,1,H,W); sel_host (nullable) / sel_host[s] (B,H,W).
+ * The *_host arguments are HOST arrays of device pointers.  Returns DMH_ERR_UNSUPPORTED when the frames cannot be
+ * staged by TMA (W % 4 != 0 or unaligned bases): the caller then uses dmh_photo_scale per scale.               */
+int dmh_photo_multiscale(const float* target, const float* src_packed, const float* T, int S,
+                         const float* const* disp_host, const int* disp_h, const int* disp_w, const float* K,
+                         const float* inv_K, const float* ident, const float* const* noise_host, int B, int H, int W,
+                         float min_depth, float max_depth, float grad_scale, float* const* loss_partial_host,
+                         float* const* grad_disp_host, uint8_t* const* sel_host, dmh_stream_t stream);
+
+/* Test hook of dmh_photo_multiscale's branch-free IEEE reciprocals (the instruction sequence of the hardware fast
+ * path of 1/x and a/z, valid for operands in [2^-60, 2^60]; operands outside raise a per-tile flag and take the
+ * generic division): counts the mismatches against __frcp_rn over EVERY float of that range and against
+ * __fdiv_rn over 2^32 pseudo-random pairs.  mismatches: 2 device counters (uint64); both must read 0.           */
+int dmh_selftest_reciprocals(unsigned long long* mismatches, unsigned int seed, dmh_stream_t stream);
+
 /* Depth-hints variant of dmh_photo_scale (A18; DepthNetworks/depth-hints/trainer.py:476-525, 541-590, 629-727),
  * one scale: same fused warp + SSIM/L1 + backward, but the per-pixel decision is the depth-hints one -- min (or
  * mean) over the source frames first, ONE tie-break noise plane noise (B,1,H,W) added to the identity minimum,

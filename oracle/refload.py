@@ -2,9 +2,11 @@
 
 Imports the *unmodified* reference (`/root/reference`, present only in the
 build container, never on the GPU box) so that `oracle/make_golden.py` can
-generate the golden vectors under `tests/golden/` and so that
-`tests/test_oracle_vs_reference.py` can pin the oracle restatement against the
-reference's own code.
+generate the golden vectors under `tests/golden/` (`tests/test_oracle_golden.py`
+pins the oracle restatement to them).  On the GPU box the copy made by
+`oracle/build_ref.py` (`oracle/_ref/reference`, git-ignored) is loaded instead:
+`oracle/ref_step.py` runs the reference's own code there for the bench's
+reference arm, its eager-PyTorch-on-B200 baseline and the integration tests.
 
 The reference needs six import-level stubs; none of
 them touches arithmetic:
@@ -23,7 +25,10 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("DMH_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference where it lies (build container), else the copy `oracle/build_ref.py` shipped to the GPU box
+_SHIPPED = os.path.join(_HERE, "_ref", "reference")
+REF_ROOT = os.environ.get("DMH_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _SHIPPED)
 M2_DIR = os.path.join(REF_ROOT, "DepthNetworks", "monodepth2")
 
 # KITTI object calib 003086 values as printed in physicalTrans.py:208-213.

@@ -17,7 +17,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--multiscale", type=int, default=1, help="0: one photometric launch per scale (round-1 form)")
     a = ap.parse_args()
+    from depthmodelhardening_b200 import ops
+    ops.MULTISCALE = bool(a.multiscale)
     dev = torch.device("cuda:0")
     pb, pt = bench.make_host_workload(a.batch, 0, True)
     s2, s1 = bench.Stage2(pb, dev), bench.Stage1(pt, dev, 1)

@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the short text summary kept under profiles/.
-usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/rNN_<what>.txt"""
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/rNN_<what>.txt
+       python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep --json KERNEL_SUBSTRING BATCH > profiles/rNN_ncu_<k>.json
+         (per-launch DRAM bytes / warp instructions of the first matching launch: what bench.py's roofline.traffic
+          quotes, with its source)"""
 import csv
 import subprocess
 import sys
@@ -37,5 +40,37 @@ def main(path):
                 print("  %-82s %16s %s" % (w, r[idx[w]][:16], units[idx[w]]))
 
 
+def as_json(path, pat, batch):
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        if pat in name:
+            f = lambda k: float(r[idx[k]].replace(",", ""))
+            units = rows[1]
+            def byt(k):
+                u = units[idx[k]].lower()
+                m = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
+                return f(k) * m
+            out = {"kernel": pat, "kernel_name": name[:160], "batch": int(batch),
+                   "dram_bytes_per_launch": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
+                   "dram_bytes_read": byt("dram__bytes_read.sum"), "dram_bytes_write": byt("dram__bytes_write.sum"),
+                   "warp_instructions_per_launch": f("smsp__inst_executed.sum"),
+                   "gpu_time_us_under_ncu": f("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(
+                       units[idx["gpu__time_duration.sum"]].lower().replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns"), 1.0),
+                   "registers_per_thread": f("launch__registers_per_thread"),
+                   "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "source": "ncu --set full --clock-control none, %s" % path.split("/")[-1]}
+            print(json.dumps(out, indent=1))
+            return
+    raise SystemExit("no launch matching %r in %s" % (pat, path))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--json":
+        as_json(sys.argv[1], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1])

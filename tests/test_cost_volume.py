@@ -101,3 +101,49 @@ def test_install_patches_manydepth_encoder():
         "print('ok')\n") % root
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.reference
+def test_install_before_import_patches_manydepth_encoder():
+    """The documented order -- install() BEFORE the trainer / encoder modules are imported: `resnet_encoder` is not
+    in sys.modules yet, its `from layers import BackprojectDepth, Project3D` then binds the drop-ins, and
+    `match_features` (which hands them (1,4,4) matrices with batch_size = 96 depth bins,
+    MD/networks/resnet_encoder.py:182,194) must be patched by the import hook; uninstall() restores everything."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os, importlib; sys.path.insert(0, %r)\n"
+        "from oracle import make_golden_md as M, refload\n"
+        "for p in (refload.REF_ROOT, M.MD_DIR): sys.path.insert(0, p)\n"
+        "os.chdir(M.MD_DIR)\n"
+        "layers = importlib.import_module('layers')\n"
+        "ref_bp = layers.BackprojectDepth\n"
+        "import depthmodelhardening_b200.install as dmh\n"
+        "done = dmh.install(mode='ops')\n"
+        "assert 'networks.resnet_encoder' not in sys.modules\n"
+        "enc = importlib.import_module('networks.resnet_encoder')\n"
+        "assert enc.BackprojectDepth.__module__ == 'depthmodelhardening_b200.layers'\n"
+        "assert enc.ResnetEncoderMatching.match_features.__module__ == 'depthmodelhardening_b200.cost_volume', enc.ResnetEncoderMatching.match_features.__module__\n"
+        "dmh.uninstall()\n"
+        "assert enc.ResnetEncoderMatching.match_features.__module__.endswith('resnet_encoder')\n"
+        "assert layers.BackprojectDepth is ref_bp and not hasattr(layers, '_dmh_ref_SSIM')\n"
+        "print('ok')\n") % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_camera_matrix_batch_is_validated():
+    """ops._mat_batch: a batch-1 matrix broadcasts (ManyDepth passes (1,4,4) with batch_size = num_depth_bins), any
+    other mismatch raises instead of letting the kernel index past the buffer (`K + b*16`)."""
+    import torch
+    from depthmodelhardening_b200 import ops
+    K = torch.eye(4).unsqueeze(0)
+    assert tuple(ops._mat_batch(K, 96, "K").shape) == (96, 4, 4)
+    assert tuple(ops._mat_batch(torch.eye(4), 3, "K").shape) == (3, 4, 4)
+    assert ops._mat_batch(K.repeat(5, 1, 1), 5, "K").shape[0] == 5
+    with pytest.raises(RuntimeError):
+        ops._mat_batch(K.repeat(2, 1, 1), 96, "K")
+    with pytest.raises(RuntimeError):
+        ops._mat_batch(torch.zeros(1, 3, 4), 1, "K")

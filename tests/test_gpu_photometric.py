@@ -194,10 +194,13 @@ def test_fused_objective_vs_reference_golden(dev, name):
 
 
 @pytest.mark.parametrize("frame_ids,shape", [((0, "s"), (4, 192, 640)), ((0, -1, 1), (2, 96, 320)),
-                                             ((0, -1, 1, "s"), (1, 72, 200)), ((0, "s"), (2, 50, 70))])
+                                             ((0, -1, 1, "s"), (1, 72, 200)), ((0, "s"), (2, 50, 70)),
+                                             ((0, "s"), (2, 320, 1024))])
 def test_fused_objective_vs_oracle(dev, frame_ids, shape):
-    """Config 1 of BASELINE.json (B=4, 640x192 stereo) and ragged / multi-frame cases,
-    incl. a size that is not a multiple of the tile (and where the pyramid is ragged)."""
+    """Config 1 of BASELINE.json (B=4, 640x192 stereo), ragged / multi-frame cases incl. a size that is not a
+    multiple of the tile (and where the pyramid is ragged), and the BENCHMARKED shape (config 2: 1024x320,
+    [0,'s'], 4 scales; B=2 -- the kernel instantiation bench.py times, divisors 1023 / 319) against the fp32
+    oracle with the fp64 arbiter."""
     B, H, W = shape
     scales = (0, 1, 2, 3) if H % 8 == 0 and W % 8 == 0 else (0, 1)
     pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=frame_ids, scales=scales, seed=31)
@@ -502,3 +505,140 @@ def test_split_path_is_bit_identical_to_fused(dev, hw, dhw):
                 assert torch.allclose(a[:nfast], b_[:nfast], rtol=2e-6, atol=0.0)
             else:
                 assert torch.equal(a, b_)
+
+
+# ----------------------------------------------------------------------------- all scales in one launch (photo_ms.cu)
+def _per_scale_vs_multiscale(dev, H, W, dsizes, B=2, seed=81, disp_fn=None, T=None, noise=True, automask=True):
+    """S calls of dmh_photo_scale (packed source) against ONE dmh_photo_multiscale call on the same buffers."""
+    import ctypes as C
+    from depthmodelhardening_b200 import _lib, ops
+    from depthmodelhardening_b200._lib import check, ptr, ptr_array, stream
+    S = len(dsizes)
+    pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, "s"), scales=(0,), seed=seed).to(dev)
+    lib = _lib.load()
+    target, src = pb.color[(0, 0)].contiguous(), pb.color[("s", 0)].contiguous()
+    gen = torch.Generator().manual_seed(seed + 1)
+    disps = []
+    for (h, w) in dsizes:
+        d = 0.05 + 0.4 * torch.rand(B, 1, h, w, generator=gen)
+        if disp_fn is not None:
+            d = disp_fn(d)
+        disps.append(d.to(dev).contiguous())
+    noises = [(1e-5 * torch.randn(B, 1, H, W, generator=gen)).to(dev).contiguous() if noise else None for _ in range(S)]
+    ident = torch.empty(B, 1, H, W, device=dev) if automask else None
+    pk = torch.empty(B, H, W, 4, device=dev)
+    check(lib.dmh_identity_loss_pack(ptr(target), ptr(src), B, H, W, 0, ptr(ident), ptr(pk), stream()))
+    tiles = lib.dmh_photo_tiles(H, W)
+    K, iK = pb.K.contiguous(), pb.inv_K.contiguous()
+    Tm = (pb.T["s"] if T is None else T.to(dev)).contiguous()
+    ref = []
+    for s in range(S):
+        part = torch.zeros(B * tiles, device=dev)
+        g = torch.full((B, 1, H, W), float("nan"), device=dev)
+        sel = torch.full((B, H, W), 255, device=dev, dtype=torch.uint8)
+        h, w = dsizes[s]
+        check(lib.dmh_photo_scale(ptr(target), ptr_array([pk]), ptr_array([Tm]), 1, ptr(disps[s]), h, w, ptr(K), ptr(iK),
+                                  ptr(ident), ptr(noises[s]), B, H, W, 0.1, 100.0, ops.FLAG_SRC_PACKED, 0.25, ptr(part),
+                                  ptr(g), None, ptr(sel), None, stream()), "photo_scale")
+        ref.append((part, g, sel))
+    parts = [torch.full((B * tiles,), float("nan"), device=dev) for _ in range(S)]
+    gs = [torch.full((B, 1, H, W), float("nan"), device=dev) for _ in range(S)]
+    sels = [torch.full((B, H, W), 255, device=dev, dtype=torch.uint8) for _ in range(S)]
+    dh = (C.c_int * S)(*[h for h, _ in dsizes])
+    dw = (C.c_int * S)(*[w for _, w in dsizes])
+    check(lib.dmh_photo_multiscale(ptr(target), ptr(pk), ptr(Tm), S, ptr_array(disps), dh, dw, ptr(K), ptr(iK), ptr(ident),
+                                   ptr_array(noises) if noise else None, B, H, W, 0.1, 100.0, 0.25, ptr_array(parts),
+                                   ptr_array(gs), ptr_array(sels), stream()), "photo_multiscale")
+    torch.cuda.synchronize()
+    return ref, list(zip(parts, gs, sels))
+
+
+def _assert_same_bits(ref, got):
+    for s, (r, g) in enumerate(zip(ref, got)):
+        for name, a, b_ in zip(("loss partial sums", "disparity gradient", "argmin"), r, g):
+            same = torch.equal(a, b_) if a.dtype == torch.uint8 else torch.equal(a.view(torch.int32), b_.view(torch.int32))
+            assert same, "scale %d: %s differ (%d elements)" % (s, name, int((a != b_).sum()))
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (40, 72), (96, 160), (72, 200), (192, 640)])
+def test_multiscale_kernel_is_bit_identical_to_per_scale(dev, hw):
+    """dmh_photo_multiscale (all scales in one launch, cp.async tap pipeline, branch-free exact reciprocals) against S
+    launches of the per-scale kernel: loss partial sums, disparity gradients and argmin agree BIT FOR BIT, incl.
+    ragged tiles, every up-sampling factor of the 4-scale pyramid and a non-integer factor."""
+    H, W = hw
+    dsizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
+    ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes)
+    _assert_same_bits(ref, got)
+    assert float(got[0][1].abs().max()) > 0
+    ref, got = _per_scale_vs_multiscale(dev, H, W, [(H // 2 + 3, W // 2 + 5), (H, W)], seed=83)   # odd factor, S = 2
+    _assert_same_bits(ref, got)
+    ref, got = _per_scale_vs_multiscale(dev, H, W, [(H, W)], seed=85, noise=False)                # S = 1, no noise
+    _assert_same_bits(ref, got)
+
+
+def test_multiscale_kernel_full_size_is_bit_identical(dev):
+    """The benchmarked configuration's shape (1024 x 320, 4 scales; B = 3) -- the instantiation bench.py times."""
+    H, W = 320, 1024
+    dsizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
+    ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes, B=3, seed=91)
+    _assert_same_bits(ref, got)
+
+
+def test_multiscale_kernel_exponent_range_fallback(dev):
+    """Operands outside [2^-60, 2^60] (and exact zeros: identity pose, column 0 projects to u = 0) flag the tile, which
+    then re-runs the gather with the generic IEEE divisions: still the per-scale kernel's bits.  NaN / inf / zero /
+    negative disparities included."""
+    H, W = 64, 96
+    dsizes = [(H, W), (H // 2, W // 2)]
+    ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes, T=torch.eye(4).repeat(2, 1, 1), seed=87)
+    _assert_same_bits(ref, got)
+
+    def poison(d):
+        d = d.clone()
+        d.view(-1)[::97] = 0.0
+        d.view(-1)[5::131] = -0.001001001          # scaled disparity ~ 0 / negative: depth overflows the range
+        d.view(-1)[7::257] = float("inf")
+        d.view(-1)[11::263] = 1e30
+        return d
+    ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes, disp_fn=poison, seed=89)
+    for (rp, rg, rs), (gp, gg, gs_) in zip(ref, got):
+        # NaN payloads aside, same bits: compare with NaN == NaN
+        assert torch.equal(rs, gs_)
+        assert torch.equal(torch.isnan(rg), torch.isnan(gg))
+        assert torch.equal(torch.nan_to_num(rg, nan=0.0).view(torch.int32), torch.nan_to_num(gg, nan=0.0).view(torch.int32))
+
+
+def test_branch_free_reciprocals_equal_ieee(dev):
+    """The reciprocal / division sequences of the multi-scale kernel against __frcp_rn over EVERY float in
+    [2^-60, 2^60] and against __fdiv_rn over 2^32 pseudo-random pairs: zero mismatches."""
+    from depthmodelhardening_b200 import _lib
+    from depthmodelhardening_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(lib.dmh_selftest_reciprocals(ptr(cnt), 20261018, stream()), "selftest_reciprocals")
+    torch.cuda.synchronize()
+    assert cnt.tolist() == [0, 0], "mismatches (rcp, div) = %s" % cnt.tolist()
+
+
+def test_objective_multiscale_switch_is_bit_identical(dev):
+    """ops.objective with the one-launch kernel (default) against DMH_MULTISCALE=0 (one launch per scale): identical
+    losses and disparity gradients through the public autograd path."""
+    from depthmodelhardening_b200 import objective, ops
+    pb = synth.photo_batch(batch=2, height=96, width=160, frame_ids=(0, "s"), seed=93)
+    g = pb.to(dev)
+    res = []
+    for ms in (True, False):
+        old = ops.MULTISCALE
+        ops.MULTISCALE = ms
+        try:
+            disps = {s: g.disp[s].clone().requires_grad_(True) for s in g.scales}
+            losses, _ = objective.photometric_losses(g.color, disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height,
+                                                     g.width, noise=g.noise)
+            losses["loss"].backward()
+            res.append((losses["loss"].detach().clone(), [disps[s].grad.clone() for s in g.scales]))
+        finally:
+            ops.MULTISCALE = old
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b_ in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b_)

@@ -6,6 +6,16 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+# Measured parity numbers, one record per comparison: tests/conftest.py tags them with the running test and writes
+# them to $DMH_PARITY_REPORT at the end of the session (committed per round as profiles/rNN_parity_errors.json, so
+# that a regression INSIDE the tolerance is visible).
+REPORT = []
+CURRENT_TEST = [""]
+
+
+def _record(kind, what, **numbers):
+    REPORT.append(dict(test=CURRENT_TEST[0], kind=kind, what=what, **{k: float(v) for k, v in numbers.items()}))
+
 
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
@@ -37,6 +47,7 @@ def assert_close(a, b, rtol, what="", max_outlier_frac=0.0, outlier_rtol=None):
     (coordinate-floor discontinuities), which must still be
     within `outlier_rtol`."""
     e = rel_err(a, b)
+    _record("close", what, rel_err=e, rtol=rtol, beyond_rtol_frac=mismatch_fraction(a, b, rtol) if e > rtol else 0.0)
     if e <= rtol:
         return e
     if max_outlier_frac > 0.0:
@@ -56,9 +67,11 @@ def assert_close_arb(a, ref32, ref64, rtol, what=""):
     reference, not an error of the kernel."""
     e32 = rel_err(a, ref32)
     if e32 <= rtol:
+        _record("close_arb", what, rel_err_vs_fp32=e32, rtol=rtol)
         return e32
     e64 = rel_err(a, ref64)
     eref = rel_err(ref32, ref64)
+    _record("close_arb", what, rel_err_vs_fp32=e32, rel_err_vs_fp64=e64, oracle32_vs_fp64=eref, rtol=rtol)
     assert e64 <= max(rtol, 1.2 * eref), "%s: rel err vs fp32 oracle %.3g, vs fp64 %.3g (oracle32 vs fp64 %.3g)" % (
         what, e32, e64, eref)
     return e32
@@ -78,6 +91,7 @@ def assert_grad_close(a, ref32, ref64, rtol, what="", outlier_frac=2e-3, slack=2
     against fp64."""
     e32 = rel_err(a, ref32)
     if e32 <= rtol:
+        _record("grad", what, rel_err_vs_fp32=e32, rtol=rtol, elements=float(np.asarray(to_np(ref32)).size))
         return e32
     a_, r32, r64 = to_np(a), to_np(ref32), to_np(ref64)
     scale = max(float(np.max(np.abs(r64))), 1e-30)
@@ -89,6 +103,9 @@ def assert_grad_close(a, ref32, ref64, rtol, what="", outlier_frac=2e-3, slack=2
     # knife-edge pixels (coordinate floor(), automask near-ties): a fraction, but never fewer than 2 elements
     # (small tensors) unless outliers are disabled
     allowed = 0 if outlier_frac == 0.0 else max(2, int(np.ceil(outlier_frac * er.size)))
+    _record("grad", what, rel_err_vs_fp32=e32, rel_err_vs_fp64_max=float(ea.max()),
+            rel_err_vs_fp64_p999=float(np.quantile(ea, 0.999)), oracle32_noise=noise, threshold=thr,
+            outliers=bad, outliers_allowed=allowed, elements=er.size, rtol=rtol)
     assert bad <= allowed, "%s: %d of %d elements beyond %.3g of fp64 (allowed %d; vs fp32 oracle %.3g; oracle noise %.3g)" % (
         what, bad, er.size, thr, allowed, e32, noise)
     return e32
@@ -99,4 +116,5 @@ def assert_selection_close(sel, ref, what="argmin", frac=1e-4):
     sel, ref = np.asarray(sel), np.asarray(ref)
     bad = int(np.sum(sel != ref))
     allowed = max(2, int(np.ceil(frac * sel.size)))
+    _record("selection", what, differ=bad, allowed=allowed, elements=sel.size)
     assert bad <= allowed, "%s: %d of %d selections differ (allowed %d)" % (what, bad, sel.size, allowed)
