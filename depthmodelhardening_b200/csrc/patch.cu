@@ -347,7 +347,10 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
     constexpr int NCU = (PITCH + 31) / 32, NRU = (ROWS + 7) / 8;
     float* comp = smem;                                   // [4][ROWS][PITCH] : 3 colour planes + mask
     __shared__ int x_lo[PA_TW], y_lo[PA_TH];
-    __shared__ float x_w[PA_TW][3], y_w[PA_TH][3];
+    __shared__ float x_w[PA_TW][3];
+    // vertical weights of a thread's 4 CONSECUTIVE output rows against the (<= 8) input rows their spans cover:
+    // wy4[q][i] = weights of input row y_lo[4q] + i in output rows 4q .. 4q+3 (0 outside a row's span)
+    __shared__ float4 wy4[PA_TH / 4][8];
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
     const int ox0 = blockIdx.x * PA_TW, oy0 = blockIdx.y * PA_TH;
@@ -380,10 +383,13 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
         for (int j = 0; j < 3; ++j) x_w[tid][j] = s.w[j];
     } else if (tid < PA_TW + PA_TH) {
         const int k = tid - PA_TW;
-        const AaSpan3 s = aa_span3(min(oy0 + k, oh - 1), ih, sy);
-        y_lo[k] = s.lo;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) y_w[k][j] = s.w[j];
+        y_lo[k] = aa_span_lo(min(oy0 + k, oh - 1), sy);
+    } else if (tid < PA_TW + PA_TH + 32 * (PA_TH / 4)) {
+        const int t = tid - (PA_TW + PA_TH);
+        const int q = t >> 5, i = (t & 31) >> 2, k = t & 3;
+        const AaSpan3 s = aa_span3(min(oy0 + 4 * q + k, oh - 1), ih, sy);
+        const int d = i - (s.lo - aa_span_lo(min(oy0 + 4 * q, oh - 1), sy));
+        reinterpret_cast<float*>(&wy4[q][i])[k] = (d >= 0 && d < 3) ? s.w[d] : 0.0f;
     }
     bool tile_hits = true;
     int bx0 = 0, by0 = 0, bx1 = iw - 1, by1 = ih - 1;
@@ -454,58 +460,78 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
     const float wx1 = xshift == 0 ? xw1 : (xshift == 1 ? xw0 : 0.f);
     const float wx2 = xshift == 0 ? xw2 : (xshift == 1 ? xw1 : (xshift == 2 ? xw0 : 0.f));
     const int ON = oh * ow;
-    const int ty0 = tid / PA_TW;
-    float* aout = adv + (size_t)b * 3 * ON + (oy0 + ty0) * ow + ox;
-    float* mout = mask_out ? mask_out + (size_t)b * ON + (oy0 + ty0) * ow + ox : nullptr;
+    // A thread owns 4 consecutive output rows of its column: the horizontal 3-tap sum of an input row is formed once
+    // and feeds every output row whose span holds it (7 input rows instead of 12 at 375 -> 320: 70 shared-memory
+    // loads per thread instead of 120 -- the kernel was shared-memory bound).  Same products, same order of the
+    // non-zero terms, i.e. the same bits as one output at a time.
+    const int q = tid / PA_TW;
+    const int yb = y_lo[4 * q] - cy0;                                       // first input row (tile coordinates)
+    const int last = min(4 * q + 3, last_y);
+    const int nrows = min(y_lo[last] - cy0 - yb + 3, 8);                    // warp-uniform (a warp shares q)
+    float* aout = adv + (size_t)b * 3 * ON + (oy0 + 4 * q) * ow + ox;
+    float* mout = mask_out ? mask_out + (size_t)b * ON + (oy0 + 4 * q) * ow + ox : nullptr;
     const float* cbase = comp + xl;
-    constexpr int KSTEP = PA_THREADS / PA_TW;
     if (tile_hits) {
+        float acc[4][4];
 #pragma unroll
-        for (int k = 0; k < PA_TH / KSTEP; ++k) {
-            const int ty = ty0 + k * KSTEP;
-            if (oy0 + ty >= oh) break;
-            const int yl = y_lo[ty] - cy0;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float wy = y_w[ty][j];              // 0 beyond the span
-                const float* row = cbase + min(yl + j, ch - 1) * PITCH;
+            for (int p = 0; p < 4; ++p) acc[k][p] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nrows) {
+                const float4 w = wy4[q][i];
+                const float* row = cbase + min(yb + i, ch - 1) * PITCH;
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     float h = row[p * PLANE] * wx0;
                     h = fmaf(row[p * PLANE + 1], wx1, h);
                     h = fmaf(row[p * PLANE + 2], wx2, h);
-                    acc[p] = fmaf(h, wy, acc[p]);
+                    acc[0][p] = fmaf(h, w.x, acc[0][p]);
+                    acc[1][p] = fmaf(h, w.y, acc[1][p]);
+                    acc[2][p] = fmaf(h, w.z, acc[2][p]);
+                    acc[3][p] = fmaf(h, w.w, acc[3][p]);
                 }
             }
-            aout[k * KSTEP * ow] = acc[0];
-            aout[ON + k * KSTEP * ow] = acc[1];
-            aout[2 * ON + k * KSTEP * ow] = acc[2];
-            if (mout) mout[k * KSTEP * ow] = acc[3];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (oy0 + 4 * q + k >= oh) break;
+            aout[k * ow] = acc[k][0];
+            aout[ON + k * ow] = acc[k][1];
+            aout[2 * ON + k * ow] = acc[k][2];
+            if (mout) mout[k * ow] = acc[k][3];
         }
     } else {
+        float acc[4][3];
 #pragma unroll
-        for (int k = 0; k < PA_TH / KSTEP; ++k) {
-            const int ty = ty0 + k * KSTEP;
-            if (oy0 + ty >= oh) break;
-            const int yl = y_lo[ty] - cy0;
-            float acc[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float wy = y_w[ty][j];
-                const float* row = cbase + min(yl + j, ch - 1) * PITCH;
+            for (int p = 0; p < 3; ++p) acc[k][p] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nrows) {
+                const float4 w = wy4[q][i];
+                const float* row = cbase + min(yb + i, ch - 1) * PITCH;
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     float h = row[p * PLANE] * wx0;
                     h = fmaf(row[p * PLANE + 1], wx1, h);
                     h = fmaf(row[p * PLANE + 2], wx2, h);
-                    acc[p] = fmaf(h, wy, acc[p]);
+                    acc[0][p] = fmaf(h, w.x, acc[0][p]);
+                    acc[1][p] = fmaf(h, w.y, acc[1][p]);
+                    acc[2][p] = fmaf(h, w.z, acc[2][p]);
+                    acc[3][p] = fmaf(h, w.w, acc[3][p]);
                 }
             }
-            aout[k * KSTEP * ow] = acc[0];
-            aout[ON + k * KSTEP * ow] = acc[1];
-            aout[2 * ON + k * KSTEP * ow] = acc[2];
-            if (mout) mout[k * KSTEP * ow] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (oy0 + 4 * q + k >= oh) break;
+            aout[k * ow] = acc[k][0];
+            aout[ON + k * ow] = acc[k][1];
+            aout[2 * ON + k * ow] = acc[k][2];
+            if (mout) mout[k * ow] = 0.f;
         }
     }
 }
