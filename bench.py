@@ -249,6 +249,23 @@ def measure_strong(args, rank, world, device, global_batch):
     with torch.cuda.graph(graph):
         step()
     ms_graph = timed_loop(graph.replay, steps, max(args.warmup, 3), world)
+    # informational: the two stages of a step read different inputs (stage 1 of step i+1 does not depend on stage 2
+    # of step i: a trainer can pipeline them), so a second capture runs stage 1 -- with its all-reduce -- on a side
+    # stream beside stage 2; at 4 items per GPU both are latency-bound chains and overlap almost completely
+    try:
+        graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph2):
+            cs = torch.cuda.current_stream()
+            side.wait_stream(cs)
+            with torch.cuda.stream(side):
+                s1.step()
+            s2.step()
+            cs.wait_stream(side)
+        ms_graph2 = timed_loop(graph2.replay, steps, max(args.warmup, 3), world)
+        out.update({"ms_per_step_two_stream": ms_graph2,
+                    "value_two_stream": global_batch * H * W / (ms_graph2 * 1e-3) / 1e6})
+    except Exception as exc:
+        out["two_stream_error"] = "%s: %s" % (type(exc).__name__, exc)
     out.update({"ms_per_step": ms_graph, "value": global_batch * H * W / (ms_graph * 1e-3) / 1e6,
                 "note": "ms_per_step / value: CUDA-graph replay of the whole step (stage 1, NCCL all-reduce of the "
                         "patch gradient, stage 2 fwd+bwd) captured once; *_eager: the same step launched from Python. "

@@ -50,6 +50,7 @@ SIGNATURES = {
     "dmh_warp_bwd": (_i, [_f, _f, _i, _fl, _fl, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_identity_loss": (_i, [_f, C.POINTER(C.c_void_p), _i, _i, _i, _i, _i, _f, _st]),
     "dmh_identity_loss_pack": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
+    "dmh_identity_loss_pack_bf16": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_photo_tiles": (_i, [_i, _i]),
     "dmh_photo_scale": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _i, _i, _i,
                              _fl, _fl, _i, _fl, _f, _f, _f, _f, C.POINTER(C.c_void_p), _st]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "dmh_compose_u8": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _f, _st]),
     "dmh_compose_patch_u8": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_lanczos_u8": (_i, [_f, _i, _i, _i, _i, _i, _f, _f, _i, _f, _f, _i, _f, _f, _f, _st]),
+    "dmh_color_jitter_u8": (_i, [_f, _i, _i, _i, _f, _f, _f, _f, _f, _f, _st]),
     "dmh_unpack_u8": (_i, [_f, _ll, _f, _st]),
     "dmh_axpby_dev": (_i, [_f, _f, _f, _f, _ll, _f, _st]),
     "dmh_perspective_fwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _st]),
@@ -79,6 +81,8 @@ SIGNATURES = {
     "dmh_patch_apply_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_pgd_linf_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _st]),
+    "dmh_apgd_linf_step": (_i, [_f, _f, _f, _f, _ll, _fl, _fl, _fl, _f, _st]),
+    "dmh_depth_errors": (_i, [_f, _f, _f, _ll, _fl, _fl, _fl, _fl, _fl, _f, _st]),
     "dmh_pgd_l2_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _fl, _f, _st]),
     "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),
     "dmh_l0_adam_step": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _fl, _i,
@@ -132,7 +136,7 @@ def ptr(t):
         raise RuntimeError("dmh_b200: tensor is on %s; the hot path is CUDA-only (no CPU fallback)" % t.device)
     if not t.is_contiguous():
         raise RuntimeError("dmh_b200: tensor must be contiguous")
-    if t.dtype not in (torch.float32, torch.uint8, torch.int32, torch.int64):
+    if t.dtype not in (torch.float32, torch.float64, torch.uint8, torch.int32, torch.int64, torch.bfloat16):
         raise RuntimeError("dmh_b200: unsupported dtype %s" % t.dtype)
     return C.c_void_p(t.data_ptr())
 

@@ -4,6 +4,7 @@
 // launch each, with the L0 count kept on the device.
 //
 //   dmh_pgd_linf_step     phy_obj_atk.py:98-100 (same 3 lines: pgd_depth.py:76-78, pgd.py:73-75)
+//   dmh_apgd_linf_step    phy_obj_atk_apgd.py:214-222 (APGD step with momentum and double projection)
 //   dmh_pgd_l2_step       phy_obj_atk_l2.py:108-120 (gradient normalisation, step, projection onto the L2 ball)
 //   dmh_l0_compose_count  phy_obj_atk_l0.py:94-99 + cal_l0 :43-52
 //   dmh_l0_adam_step      phy_obj_atk_l0.py:130-138 (mask cost gradient + chain through the
@@ -37,6 +38,26 @@ __global__ void pgd_linf_kernel(const float* __restrict__ adv, const float* __re
     out[i] = fminf(fmaxf(add_rn(c, delta), 0.0f), 1.0f);
 }
 
+// --------------------------------------------------------------------------- APGD L-inf step with momentum (next-4)
+// phy_obj_atk_apgd.py:214-222 in one launch, every operation rounded as the torch expression rounds it:
+//   grad2 = x_adv - x_adv_old
+//   z     = clamp(min(max(x_adv + step * sign(grad), x - eps), x + eps), 0, 1)
+//   x_new = clamp(min(max(x_adv + (z - x_adv) * a + grad2 * (1 - a), x - eps), x + eps), 0, 1)
+// (a = 0.75 after the first iteration, 1 at the first: python floats, exact in fp32.)
+__global__ void apgd_linf_kernel(const float* __restrict__ x_adv, const float* __restrict__ x_adv_old,
+                                 const float* __restrict__ grad, const float* __restrict__ x0, long long n, float step,
+                                 float a, float eps, float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float xa = x_adv[i], c = x0[i];
+    const float lo = sub_rn(c, eps), hi = add_rn(c, eps);
+    const float grad2 = sub_rn(xa, x_adv_old[i]);
+    float z = add_rn(xa, mul_rn(step, sgnf(grad[i])));
+    z = fminf(fmaxf(fminf(fmaxf(z, lo), hi), 0.0f), 1.0f);
+    float y = add_rn(add_rn(xa, mul_rn(sub_rn(z, xa), a)), mul_rn(grad2, sub_rn(1.0f, a)));
+    out[i] = fminf(fmaxf(fminf(fmaxf(y, lo), hi), 0.0f), 1.0f);
+}
+
 // --------------------------------------------------------------------------- L2 PGD update (next-4)
 // phy_obj_atk_l2.py:108-120 for the one shared patch, in ONE launch of one CTA (0.94 MB of state: latency-bound):
 //   g = grad / (||grad||_2 + 1e-10);  x = adv + alpha * g;  d = x - clean;
@@ -56,6 +77,46 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     v = red[0];
     __syncthreads();
     return v;
+}
+
+// --------------------------------------------------------------------------- evaluation metrics (next-4)
+// evaluate_depth.py:193-196 + compute_errors (:57-99) for one batch, one launch: both disparity maps go through
+// disp_to_depth(|disp|, 0.1, 100)[1] * 5.4 clamped to [1e-3, 80] (fp32, rounded as torch rounds it), then the eight
+// (masked) error sums of compute_errors.  The nine sums -- mask total first -- are accumulated in double per thread,
+// reduced per block and added to out[9] with double atomics (evaluation statistics, not on the training path;
+// order-dependent in the last bits of a double, far below the fp32 the harness prints).
+__global__ void __launch_bounds__(256)
+depth_errors_kernel(const float* __restrict__ disp_gt, const float* __restrict__ disp_pred,
+                    const float* __restrict__ mask, long long n, DepthScale ds, float scale_factor, float min_depth,
+                    float max_depth, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    const float t1 = 1.25f, t2 = 1.25f * 1.25f, t3 = 1.25f * 1.25f * 1.25f;   // python 1.25**k, exact in fp32 (k <= 3)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float m = mask ? mask[i] : 1.0f;
+        const float gt = fminf(fmaxf(mul_rn(disp_to_depth(fabsf(disp_gt[i]), ds), scale_factor), min_depth), max_depth);
+        const float pr = fminf(fmaxf(mul_rn(disp_to_depth(fabsf(disp_pred[i]), ds), scale_factor), min_depth), max_depth);
+        const float thr = fmaxf(div_rn(gt, pr), div_rn(pr, gt));
+        const float d = sub_rn(gt, pr);
+        const float d2 = mul_rn(d, d);
+        const float dl = sub_rn(logf(gt), logf(pr));
+        acc[0] += (double)m;
+        acc[1] += (double)mul_rn(fabsf(d), m);                      // abs_err
+        acc[2] += (double)mul_rn(div_rn(fabsf(d), gt), m);          // abs_rel
+        acc[3] += (double)mul_rn(div_rn(d2, gt), m);                // sq_rel
+        acc[4] += (double)mul_rn(d2, m);                            // rmse^2
+        acc[5] += (double)mul_rn(mul_rn(dl, dl), m);                // rmse_log^2
+        acc[6] += (double)((thr < t1 ? 1.0f : 0.0f) * m);
+        acc[7] += (double)((thr < t2 ? 1.0f : 0.0f) * m);
+        acc[8] += (double)((thr < t3 ? 1.0f : 0.0f) * m);
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const double v = block_sum_d(acc[q], red);
+        if (threadIdx.x == 0 && v != 0.0) atomicAdd(out + q, v);
+    }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -297,6 +358,32 @@ int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, l
     DMH_REQUIRE(adv && grad && clean && out && n > 0, "dmh_pgd_linf_step: null pointer or n <= 0");
     DMH_LAUNCH(pgd_linf_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(adv, grad, clean, n, alpha, eps, out);
     DMH_CHECK_LAUNCH("dmh_pgd_linf_step");
+    return DMH_OK;
+}
+
+int dmh_apgd_linf_step(const float* x_adv, const float* x_adv_old, const float* grad, const float* x0, long long n,
+                       float step, float a, float eps, float* out, dmh_stream_t stream) {
+    DMH_REQUIRE(x_adv && x_adv_old && grad && x0 && out && n > 0, "dmh_apgd_linf_step: null pointer or n <= 0");
+    DMH_REQUIRE(out != x_adv_old && out != grad && out != x0, "dmh_apgd_linf_step: out may alias x_adv only");
+    DMH_LAUNCH(apgd_linf_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(x_adv, x_adv_old, grad, x0, n, step, a,
+                                                                               eps, out);
+    DMH_CHECK_LAUNCH("dmh_apgd_linf_step");
+    return DMH_OK;
+}
+
+int dmh_depth_errors(const float* disp_gt, const float* disp_pred, const float* mask, long long n, float min_disp_depth,
+                     float max_disp_depth, float scale_factor, float min_depth, float max_depth, double* out,
+                     dmh_stream_t stream) {
+    DMH_REQUIRE(disp_gt && disp_pred && out && n > 0, "dmh_depth_errors: null pointer or n <= 0");
+    DepthScale ds;
+    ds.min_disp = (float)(1.0 / (double)max_disp_depth);
+    ds.range = (float)(1.0 / (double)min_disp_depth - 1.0 / (double)max_disp_depth);
+    cudaError_t e = cudaMemsetAsync(out, 0, 9 * sizeof(double), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dmh_depth_errors: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+    const int blocks = (int)(n / 1024 < 1 ? 1 : (n / 1024 > 1184 ? 1184 : n / 1024));
+    DMH_LAUNCH(depth_errors_kernel, blocks, 256, 0, (cudaStream_t)stream)(disp_gt, disp_pred, mask, n, ds, scale_factor,
+                                                                         min_depth, max_depth, out);
+    DMH_CHECK_LAUNCH("dmh_depth_errors");
     return DMH_OK;
 }
 

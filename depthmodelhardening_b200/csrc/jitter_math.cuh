@@ -1,5 +1,5 @@
-// Per-pixel arithmetic of the colour jitter on 8-bit frames (GROUNDWORK for the loader row, DESIGN.md section 9;
-// not part of libdmh_b200.so yet: no kernel includes it).  `transforms.ColorJitter` on PIL images
+// Per-pixel arithmetic of the colour jitter on 8-bit frames (dmh_color_jitter_u8, loader_compose.cu).
+// `transforms.ColorJitter` on PIL images
 // (DepthNetworks/monodepth2/datasets/mono_dataset.py:297, 344-350 -> torchvision functional_pil ->
 // PIL.ImageEnhance / convert('HSV')) restated from Pillow's libImaging (Blend.c, Convert.c) as DMH_HD functions so
 // that tests/host_emul_jitter.cpp can run the SAME code with g++ against the oracle (oracle/pil_enhance.py, itself

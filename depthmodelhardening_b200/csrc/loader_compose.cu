@@ -13,6 +13,7 @@
 // critical path (the CPU reference spends ~20 ms per frame on it).
 #include "../../include/dmh_b200.h"
 #include "dmh_common.cuh"
+#include "jitter_math.cuh"
 
 using namespace dmh;
 
@@ -292,7 +293,90 @@ compose_u8_kernel(const uint8_t* __restrict__ scene, const float* __restrict__ o
     }
 }
 
+// --------------------------------------------------------------------------- colour jitter on 8-bit frames (next-2)
+// transforms.ColorJitter on the PIL frames of an item (mono_dataset.py:297, 344-350, applied per pyramid level in
+// preprocess :140-144): the four steps of torchvision's ColorJitter.forward in the item's drawn order fn_idx --
+// 0 brightness, 1 contrast, 2 saturation, 3 hue -- each on 8-bit pixels with Pillow's arithmetic (jitter_math.cuh,
+// bit-exact against the oracle / Pillow).  Contrast blends against the rounded MEAN GREY LEVEL of the image as it is
+// when the step runs, so the work is two passes: pass 1 applies the steps that precede the contrast step and sums the
+// grey levels per image (exact: integer atomics), pass 2 applies all steps.  A step with factor 1 (hue shift 0) is an
+// identity in Pillow's arithmetic as well; order entries < 0 are skipped (that step is switched off).
+struct JitterItem { int order[4]; float f[3]; int hue_shift; };
+
+__device__ __forceinline__ Rgb8 jitter_steps(Rgb8 p, const JitterItem& it, int upto, uint8_t mean_grey) {
+    // applies order[0 .. upto-1]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= upto) break;
+        const int op = it.order[k];
+        if (op == 0) p = jit_brightness(p, it.f[0]);
+        else if (op == 1) p = jit_contrast(p, it.f[1], mean_grey);
+        else if (op == 2) p = jit_saturation(p, it.f[2]);
+        else if (op == 3) p = jit_hue(p, (uint8_t)it.hue_shift);
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+jitter_grey_sum_kernel(const uint8_t* __restrict__ in, int npix, const int* __restrict__ order,
+                       const float* __restrict__ factors, const int* __restrict__ hue_shift,
+                       unsigned long long* __restrict__ sums) {
+    __shared__ unsigned int red[8];
+    const int b = blockIdx.y;
+    JitterItem it;
+    int cpos = 4;                                           // position of the contrast step (4: none)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { it.order[k] = order[b * 4 + k]; if (it.order[k] == 1 && cpos == 4) cpos = k; }
+    it.f[0] = factors[b * 3]; it.f[1] = factors[b * 3 + 1]; it.f[2] = factors[b * 3 + 2];
+    it.hue_shift = hue_shift[b];
+    if (cpos == 4) return;                                  // no contrast step: the mean is never read
+    const uint8_t* base = in + (size_t)b * 3 * npix;
+    unsigned int acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        Rgb8 p = {base[i], base[npix + i], base[2 * npix + i]};
+        p = jitter_steps(p, it, cpos, 0);
+        acc += jit_grey(p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(sums + b, (unsigned long long)t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+jitter_apply_kernel(const uint8_t* __restrict__ in, int npix, const int* __restrict__ order,
+                    const float* __restrict__ factors, const int* __restrict__ hue_shift,
+                    const unsigned long long* __restrict__ sums, uint8_t* __restrict__ out_u8,
+                    float* __restrict__ out_f32) {
+    const int b = blockIdx.y;
+    JitterItem it;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) it.order[k] = order[b * 4 + k];
+    it.f[0] = factors[b * 3]; it.f[1] = factors[b * 3 + 1]; it.f[2] = factors[b * 3 + 2];
+    it.hue_shift = hue_shift[b];
+    // ImageStat.Stat(img.convert("L")).mean[0] is sum / count in double; ImageEnhance.Contrast takes int(mean + 0.5)
+    const uint8_t mean_grey = (uint8_t)(int)((double)sums[b] / (double)npix + 0.5);
+    const size_t off = (size_t)b * 3 * npix;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        Rgb8 p = {in[off + i], in[off + npix + i], in[off + 2 * npix + i]};
+        p = jitter_steps(p, it, 4, mean_grey);
+        if (out_u8) { out_u8[off + i] = p.r; out_u8[off + npix + i] = p.g; out_u8[off + 2 * npix + i] = p.b; }
+        if (out_f32) {                                      // to_tensor: byte / 255 with IEEE division
+            out_f32[off + i] = div_rn((float)p.r, 255.0f);
+            out_f32[off + npix + i] = div_rn((float)p.g, 255.0f);
+            out_f32[off + 2 * npix + i] = div_rn((float)p.b, 255.0f);
+        }
+    }
+}
+
 }  // namespace
+
 
 extern "C" {
 
@@ -367,6 +451,24 @@ int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h,
         // the horizontal pass was the last one: to_tensor as its own (HBM-bound) launch
         return dmh_unpack_u8(out, (long long)planes * out_h * out_w, out_f32, stream);
     }
+    return DMH_OK;
+}
+
+int dmh_color_jitter_u8(const uint8_t* in, int B, int H, int W, const int* order, const float* factors,
+                        const int* hue_shift, unsigned long long* sums, uint8_t* out_u8, float* out_f32,
+                        dmh_stream_t stream) {
+    DMH_REQUIRE(in && order && factors && hue_shift && sums && (out_u8 || out_f32), "dmh_color_jitter_u8: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "dmh_color_jitter_u8: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * (size_t)B, st);
+    if (e != cudaSuccess) { set_error("dmh_color_jitter_u8: memset failed: %s", cudaGetErrorString(e)); return DMH_ERR_CUDA; }
+    const int npix = H * W;
+    const int bx = ceil_div(npix, 256 * 4) < 1 ? 1 : (ceil_div(npix, 256 * 4) > 592 ? 592 : ceil_div(npix, 256 * 4));
+    dim3 grid(bx, B);
+    DMH_LAUNCH(jitter_grey_sum_kernel, grid, 256, 0, st)(in, npix, order, factors, hue_shift, sums);
+    DMH_CHECK_LAUNCH("dmh_color_jitter_u8 (grey sums)");
+    DMH_LAUNCH(jitter_apply_kernel, grid, 256, 0, st)(in, npix, order, factors, hue_shift, sums, out_u8, out_f32);
+    DMH_CHECK_LAUNCH("dmh_color_jitter_u8 (apply)");
     return DMH_OK;
 }
 

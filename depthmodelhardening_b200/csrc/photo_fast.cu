@@ -578,6 +578,81 @@ struct IdentParams {
 #define ID_PL (ID_R * ID_P)      // plane stride
 struct IdentMaps { CUtensorMap tgt; CUtensorMap src[DMH_PHOTO_MAX_FRAMES]; };
 
+// Shared tail of the identity-loss kernels: packed copy of the source tile (+ optional fp32 copy of the target tile,
+// bf16 inputs) and the identity reprojection loss of the tile from the two staged 34 x 34 x 3 tiles.
+__device__ __forceinline__ void ident_tile_tail(const IdentParams& p, const float* xs, const float* ys, int tid, int b,
+                                                int f, int x0, int y0, float* tgt_f32) {
+    const int H = p.H, W = p.W;
+    const size_t N = (size_t)H * W;
+    __syncthreads();
+    const int c = tid & 31, strip = tid >> 5;           // 8 strips of 4 rows
+    const int px = x0 + c;
+    if (p.packed && px < W) {     // pixel-packed copy of the source tile: a warp writes 512 contiguous bytes per row
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = 4 * strip + k, py = y0 + r;
+            if (py < H) {
+                const int i = (r + 1) * ID_P + c + 1 + ID_O;
+                p.packed[(size_t)b * N + (size_t)py * W + px] = make_float4(xs[i], xs[ID_PL + i], xs[2 * ID_PL + i], 0.0f);
+            }
+        }
+    }
+    if (tgt_f32 && x0 + c < W) {   // bf16 inputs: the fp32 target the photometric kernels stage by TMA
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = 4 * strip + k, py = y0 + r;
+            if (py < H) {
+                const int i = (r + 1) * ID_P + c + 1 + ID_O;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) tgt_f32[((size_t)b * 3 + ch) * N + (size_t)py * W + x0 + c] = ys[ch * ID_PL + i];
+            }
+        }
+    }
+    if (!p.out) return;
+    // same lane-typed SSIM arithmetic as the fused kernels (channels 0,1 packed, channel 2 scalar): the
+    // identity loss and the reprojection loss must come out of identical arithmetic (automask ties)
+    Row5T<float2> histP[2];
+    Row5T<float> histS[2];
+    float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;
+    float cenxS = 0.f, cenyS = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+        const int r2 = 4 * strip + rr;                   // halo-tile row
+        const float* x0p = xs + r2 * ID_P + c + ID_O;
+        const float* y0p = ys + r2 * ID_P + c + ID_O;
+        const float2 xa = make_float2(x0p[0], x0p[ID_PL]), xb = make_float2(x0p[1], x0p[ID_PL + 1]),
+                     xc = make_float2(x0p[2], x0p[ID_PL + 2]);
+        const float2 ya = make_float2(y0p[0], y0p[ID_PL]), yb = make_float2(y0p[1], y0p[ID_PL + 1]),
+                     yc = make_float2(y0p[2], y0p[ID_PL + 2]);
+        const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
+        const float* x2p = x0p + 2 * ID_PL;
+        const float* y2p = y0p + 2 * ID_PL;
+        const Row5T<float> curS = row5(x2p[0], x2p[1], x2p[2], y2p[0], y2p[1], y2p[2]);
+        if (rr >= 2) {
+            const int py = y0 + 4 * strip + rr - 2;
+            if (py < H && px < W) {
+                float l1 = fabsf(cenyP.x - cenxP.x);
+                l1 += fabsf(cenyP.y - cenxP.y);
+                l1 += fabsf(cenyS - cenxS);
+                float ss = 0.f;
+                if (!p.no_ssim) {
+                    float2 passP, rP, nrP;
+                    const float2 vP = ssim_value_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, rP, nrP);
+                    float passS, rS, nrS;
+                    const float vS = ssim_value_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, rS, nrS);
+                    ss = (vP.x + vP.y) + vS;
+                }
+                l1 *= (1.0f / 3.0f);
+                const float rp = p.no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
+                p.out[((size_t)b * p.F + f) * N + (size_t)py * W + px] = rp;
+            }
+        }
+        histP[0] = histP[1]; histP[1] = curP;
+        histS[0] = histS[1]; histS[1] = curS;
+        cenxP = xb; cenyP = yb; cenxS = x2p[1]; cenyS = y2p[1];
+    }
+}
+
 template <bool TMA>
 __global__ void __launch_bounds__(256, 4)
 ident_fast_kernel(const IdentParams p, const __grid_constant__ IdentMaps maps) {
@@ -638,62 +713,57 @@ ident_fast_kernel(const IdentParams p, const __grid_constant__ IdentMaps maps) {
             }
         }
     }
+    ident_tile_tail(p, xs, ys, tid, b, f, x0, y0, nullptr);
+}
+
+// bf16 frames (north_star: "bf16x8 coalesced loads"): the tiles are filled by 128-bit loads of 8 bf16 each -- aligned
+// chunks [x0-8, x0+40) of every tile row, zero outside the image like a TMA box, then the same reflection patch --
+// and widened to fp32 in shared memory; everything downstream is the fp32 code.  Needs W % 8 == 0 and 16-byte
+// aligned frames.  tgt_f32 (B,3,H,W) receives the widened target (what the per-scale kernels read).
+__global__ void __launch_bounds__(256, 4)
+ident_bf16_kernel(const IdentParams p, const uint16_t* __restrict__ tgt16, const uint16_t* __restrict__ src16,
+                  float* __restrict__ tgt_f32) {
+    __shared__ __align__(128) float xs[3 * ID_PL];
+    __shared__ __align__(128) float ys[3 * ID_PL];
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * FT_T, y0 = blockIdx.y * FT_T;
+    // items: (frame, channel, tile row, chunk of 8 columns); tile column j holds image column x0 - 4 + j
+    for (int it = tid; it < 2 * 3 * ID_R * 6; it += 256) {
+        const int ck = it % 6, r = (it / 6) % ID_R, ch = (it / (6 * ID_R)) % 3, fr = it / (6 * ID_R * 3);
+        const int y = y0 - 1 + r, xc = x0 - 8 + 8 * ck;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < H && xc >= 0 && xc < W) {
+            const uint16_t* base = (fr ? tgt16 : src16) + (((size_t)b * 3 + ch) * H + y) * W + xc;
+            v = __ldg(reinterpret_cast<const uint4*>(base));
+        }
+        float* dst = (fr ? ys : xs) + ch * ID_PL + r * ID_P;
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = 8 * ck - 4 + e;                 // tile column
+            if (j >= 0 && j < ID_P) dst[j] = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+        }
+    }
     __syncthreads();
-    const int c = tid & 31, strip = tid >> 5;           // 8 strips of 4 rows
-    const int px = x0 + c;
-    if (p.packed && px < W) {     // pixel-packed copy of the source tile: a warp writes 512 contiguous bytes per row
+    if (x0 < 1 || y0 < 1 || x0 + FT_T + 1 > W || y0 + FT_T + 1 > H) {
+        for (int i = tid; i < ID_N; i += 256) {
+            const int r = i / ID_R, c = i - r * ID_R;
+            const int ey = y0 - 1 + r, ex = x0 - 1 + c;
+            if (ey < 0 || ey >= H || ex < 0 || ex >= W) {
+                const int sr = ext_to_img(ey, H) - (y0 - 1), sc = ext_to_img(ex, W) - (x0 - 1);
+                if (sr >= 0 && sr < ID_R && sc >= 0 && sc < ID_R) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = 4 * strip + k, py = y0 + r;
-            if (py < H) {
-                const int i = (r + 1) * ID_P + c + 1 + ID_O;
-                p.packed[(size_t)b * N + (size_t)py * W + px] = make_float4(xs[i], xs[ID_PL + i], xs[2 * ID_PL + i], 0.0f);
-            }
-        }
-    }
-    if (!p.out) return;
-    // same lane-typed SSIM arithmetic as the fused kernels (channels 0,1 packed, channel 2 scalar): the
-    // identity loss and the reprojection loss must come out of identical arithmetic (automask ties)
-    Row5T<float2> histP[2];
-    Row5T<float> histS[2];
-    float2 cenxP = make_float2(0.f, 0.f), cenyP = cenxP;
-    float cenxS = 0.f, cenyS = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < 6; ++rr) {
-        const int r2 = 4 * strip + rr;                   // halo-tile row
-        const float* x0p = xs + r2 * ID_P + c + ID_O;
-        const float* y0p = ys + r2 * ID_P + c + ID_O;
-        const float2 xa = make_float2(x0p[0], x0p[ID_PL]), xb = make_float2(x0p[1], x0p[ID_PL + 1]),
-                     xc = make_float2(x0p[2], x0p[ID_PL + 2]);
-        const float2 ya = make_float2(y0p[0], y0p[ID_PL]), yb = make_float2(y0p[1], y0p[ID_PL + 1]),
-                     yc = make_float2(y0p[2], y0p[ID_PL + 2]);
-        const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
-        const float* x2p = x0p + 2 * ID_PL;
-        const float* y2p = y0p + 2 * ID_PL;
-        const Row5T<float> curS = row5(x2p[0], x2p[1], x2p[2], y2p[0], y2p[1], y2p[2]);
-        if (rr >= 2) {
-            const int py = y0 + 4 * strip + rr - 2;
-            if (py < H && px < W) {
-                float l1 = fabsf(cenyP.x - cenxP.x);
-                l1 += fabsf(cenyP.y - cenxP.y);
-                l1 += fabsf(cenyS - cenxS);
-                float ss = 0.f;
-                if (!p.no_ssim) {
-                    float2 passP, rP, nrP;
-                    const float2 vP = ssim_value_t(ssim_stats_rows_t(histP[0], histP[1], curP), passP, rP, nrP);
-                    float passS, rS, nrS;
-                    const float vS = ssim_value_t(ssim_stats_rows_t(histS[0], histS[1], curS), passS, rS, nrS);
-                    ss = (vP.x + vP.y) + vS;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        xs[ch * ID_PL + r * ID_P + c + ID_O] = xs[ch * ID_PL + sr * ID_P + sc + ID_O];
+                        ys[ch * ID_PL + r * ID_P + c + ID_O] = ys[ch * ID_PL + sr * ID_P + sc + ID_O];
+                    }
                 }
-                l1 *= (1.0f / 3.0f);
-                const float rp = p.no_ssim ? l1 : fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
-                p.out[((size_t)b * p.F + f) * N + (size_t)py * W + px] = rp;
             }
         }
-        histP[0] = histP[1]; histP[1] = curP;
-        histS[0] = histS[1]; histS[1] = curS;
-        cenxP = xb; cenyP = yb; cenxS = x2p[1]; cenyS = y2p[1];
     }
+    ident_tile_tail(p, xs, ys, tid, b, 0, x0, y0, tgt_f32);
 }
 
 size_t fast_smem_bytes() { return sizeof(float) * (3 * FT_NT + 3 * FT_N2 + 9 * FT_N1 + 24 + 32) + FT_N1; }
@@ -918,6 +988,19 @@ int launch_ident_fast(const float* target, const float* const* src_host, int F, 
     }
     if (use_tma) DMH_LAUNCH(ident_fast_kernel<true>, grid, 256, 0, st)(p, maps);
     else DMH_LAUNCH(ident_fast_kernel<false>, grid, 256, 0, st)(p, maps);
+    return DMH_OK;
+}
+
+// bf16 frames: identity loss + packed fp32 source + fp32 target in one pass over the bf16 inputs
+int launch_ident_bf16(const uint16_t* target, const uint16_t* src, int B, int H, int W, int no_ssim, float* out,
+                      float* packed, float* tgt_f32, cudaStream_t st) {
+    IdentParams p;
+    p.target = nullptr;
+    p.packed = reinterpret_cast<float4*>(packed);
+    for (int f = 0; f < DMH_PHOTO_MAX_FRAMES; ++f) p.src[f] = nullptr;
+    p.out = out; p.B = B; p.F = 1; p.H = H; p.W = W; p.no_ssim = no_ssim;
+    dim3 grid(ceil_div(W, FT_T), ceil_div(H, FT_T), B);
+    DMH_LAUNCH(ident_bf16_kernel, grid, 256, 0, st)(p, target, src, tgt_f32);
     return DMH_OK;
 }
 

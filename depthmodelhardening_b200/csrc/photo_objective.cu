@@ -482,6 +482,8 @@ int launch_photo_fast(const float* target, const float* src, const float* T, con
                       float max_depth, int flags, float grad_scale, float* loss_partial, float* grad_disp,
                       uint8_t* sel, float* warped, float* split_ws, const FastDhArgs* dh, cudaStream_t st);
 long long photo_split_workspace_floats(int B, int H, int W);
+int launch_ident_bf16(const uint16_t* target, const uint16_t* src, int B, int H, int W, int no_ssim, float* out,
+                      float* packed, float* tgt_f32, cudaStream_t st);
 int launch_ident_fast(const float* target, const float* const* src_host, int F, int B, int H, int W, int no_ssim,
                       float* out, float* packed, cudaStream_t st);
 }  // namespace dmh
@@ -509,6 +511,20 @@ int dmh_identity_loss_pack(const float* target, const float* src, int B, int H, 
     const int rc = launch_ident_fast(target, srcs, 1, B, H, W, no_ssim, ident, src_packed, (cudaStream_t)stream);
     if (rc != DMH_OK) return rc;
     DMH_CHECK_LAUNCH("dmh_identity_loss_pack");
+    return DMH_OK;
+}
+
+int dmh_identity_loss_pack_bf16(const uint16_t* target_bf16, const uint16_t* src_bf16, int B, int H, int W, int no_ssim,
+                                float* ident, float* src_packed, float* target_f32, dmh_stream_t stream) {
+    DMH_REQUIRE(target_bf16 && src_bf16 && src_packed && target_f32, "dmh_identity_loss_pack_bf16: null pointer");
+    DMH_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "dmh_identity_loss_pack_bf16: bad shape");
+    DMH_REQUIRE(W % 8 == 0 && (uintptr_t)target_bf16 % 16 == 0 && (uintptr_t)src_bf16 % 16 == 0,
+                "dmh_identity_loss_pack_bf16: needs W %% 8 == 0 and 16-byte aligned frames (128-bit loads of 8 bf16)");
+    DMH_REQUIRE((uintptr_t)src_packed % 16 == 0, "dmh_identity_loss_pack_bf16: src_packed must be 16-byte aligned");
+    const int rc = launch_ident_bf16(target_bf16, src_bf16, B, H, W, no_ssim, ident, src_packed, target_f32,
+                                     (cudaStream_t)stream);
+    if (rc != DMH_OK) return rc;
+    DMH_CHECK_LAUNCH("dmh_identity_loss_pack_bf16");
     return DMH_OK;
 }
 

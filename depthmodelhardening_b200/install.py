@@ -96,7 +96,11 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
     for mod_name, cls in (("torchattacks.attacks.phy_obj_atk", "Phy_obj_atk"),
                           ("torchattacks.attacks.phy_obj_atk_l0", "Phy_obj_atk_l0"),
                           ("torchattacks.attacks.phy_obj_atk_vanila", "Phy_obj_atk_vanila"),
-                          ("torchattacks.attacks.phy_obj_atk_l2", "Phy_obj_atk_l2"), ("torchattacks", "Phy_obj_atk"),
+                          ("torchattacks.attacks.phy_obj_atk_l2", "Phy_obj_atk_l2"),
+                          ("torchattacks.attacks.phy_obj_atk_apgd", "Phy_obj_atk_APGD"),
+                          ("torchattacks.attacks.phy_obj_atk_guassian", "Phy_obj_atk_guassian"),
+                          ("torchattacks", "Phy_obj_atk_guassian"),
+                          ("torchattacks", "Phy_obj_atk_APGD"), ("torchattacks", "Phy_obj_atk"),
                           ("torchattacks", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk_vanila"),
                           ("torchattacks", "Phy_obj_atk_l2")):
         mod = sys.modules.get(mod_name)

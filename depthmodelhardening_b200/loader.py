@@ -27,6 +27,7 @@ import torch
 
 from . import _lib, patch_ops
 from .physical import PhysicalTrans
+from .staging import unpack_u8
 
 _PRECISION_BITS = 32 - 8 - 2          # Resample.c: PRECISION_BITS
 _coeff_cache: Dict = {}
@@ -203,6 +204,47 @@ def compose_patch_u8(scene: torch.Tensor, patch_a: torch.Tensor, patch_b: Option
     return out_a, out_b, m_out
 
 
+def color_jitter_u8(img: torch.Tensor, params: Sequence, want_u8: bool = True, want_f32: bool = False):
+    """`transforms.ColorJitter` with drawn parameters on a batch of 8-bit frames (`dmh_color_jitter_u8`).
+
+    img (B,3,H,W) uint8 CUDA; params: one entry per item -- the tuple `ColorJitter.get_params(...)` returns,
+    (fn_idx, brightness_factor, contrast_factor, saturation_factor, hue_factor) with factors possibly None, or None
+    for an item without augmentation (`color_aug = lambda x: x`, mono_dataset.py:347-348).  The same parameters
+    apply to every pyramid level of an item (:120-125): call once per level.  Returns (uint8 or None, fp32 or None),
+    fp32 = byte / 255 (`to_tensor`).  Bit-exact against Pillow / torchvision (oracle/pil_enhance.py)."""
+    lib = _lib.load()
+    img = _need_u8_cuda(img, "color_jitter_u8")
+    B, C, H, W = img.shape
+    if C != 3 or len(params) != B:
+        raise RuntimeError("color_jitter_u8: expected (B,3,H,W) frames and one parameter tuple per item")
+    order = np.full((B, 4), -1, dtype=np.int32)
+    fac = np.ones((B, 3), dtype=np.float32)
+    shift = np.zeros((B,), dtype=np.int32)
+    for i, p in enumerate(params):
+        if p is None:
+            continue
+        fn_idx, bf, cf, sf, hf = p
+        for k, fn in enumerate([int(v) for v in fn_idx]):
+            val = (bf, cf, sf, hf)[fn]
+            order[i, k] = fn if val is not None else -1
+        for k, val in enumerate((bf, cf, sf)):
+            if val is not None:
+                fac[i, k] = np.float32(float(val))
+        if hf is not None:
+            shift[i] = int(float(hf) * 255) & 0xff           # np.uint8(hue_factor * 255), functional_pil.adjust_hue
+    dev = img.device
+    order_d = torch.from_numpy(order).to(dev)
+    fac_d = torch.from_numpy(fac).to(dev)
+    shift_d = torch.from_numpy(shift).to(dev)
+    sums = torch.empty(B, dtype=torch.int64, device=dev)
+    out_u8 = torch.empty_like(img) if want_u8 else None
+    out_f32 = torch.empty(img.shape, dtype=torch.float32, device=dev) if want_f32 else None
+    _lib.check(lib.dmh_color_jitter_u8(_lib.ptr(img), B, H, W, _lib.ptr(order_d), _lib.ptr(fac_d), _lib.ptr(shift_d),
+                                       _lib.ptr(sums), _lib.ptr(out_u8), _lib.ptr(out_f32), _lib.stream()),
+               "color_jitter_u8")
+    return out_u8, out_f32
+
+
 class AdvBatchComposer:
     """`MonoDataset.set_adv_train` / `update_adv_obj` / `prep_adv_data` / `preprocess` for a collated batch on the
     device (mono_dataset.py:146-265, 119-144).
@@ -256,7 +298,7 @@ class AdvBatchComposer:
 
     def __call__(self, color_0: torch.Tensor, color_s: torch.Tensor, sides: Sequence[str], do_flip: Sequence[bool],
                  z0_sample: Optional[Sequence[float]] = None, alpha_sample: Optional[Sequence[float]] = None,
-                 synthesize: Optional[Sequence[bool]] = None):
+                 synthesize: Optional[Sequence[bool]] = None, color_aug: Optional[Sequence] = None):
         """color_0 / color_s: (B,3,ori_H,ori_W) uint8 CUDA -- frame 0 and its stereo partner at native resolution, as
         `get_color` returns them (already mirrored for the items with do_flip, mono_dataset.py:325-329); sides[i]:
         'l' / 'r', the side frame 0 of item i was taken from; do_flip[i]: mirror the warped patch too (:222-225);
@@ -264,6 +306,9 @@ class AdvBatchComposer:
         synthesize[i] (only with half_no_synthesis, :321-328; drawn with `random.random() > 0.5` if None): items
         with False keep their raw frames -- ("color_objmask", 0, 0) / ("objdepth", 0, 0) are then not produced at all,
         as in the reference (:253-255).
+        color_aug: per item, the tuple `transforms.ColorJitter.get_params(...)` drew for it (`do_color_aug`, :344-348)
+        or None (identity); None for the whole batch = no colour augmentation (the adversarial configuration).  With
+        it the "color_aug" entries and ("color_ben", 0, 0) carry the jittered levels (:132-133, 143-144).
 
         Returns the dictionary entries `prep_adv_data` + `preprocess` produce, as fp32 CUDA tensors:
         ("color_aug", 0 | "s", 0..S-1), ("color", 0 | "s", 0..S-1), ("color_ben", 0, 0), ("color_objmask", 0, 0),
@@ -305,13 +350,26 @@ class AdvBatchComposer:
             S = self.num_scales
             # the three composites go through the pyramid as one stack: 2 resize passes + 1 unpack per level
             names = (("color_aug", 0), ("color_aug", "s"), ("color", 0))
-            for i, f in enumerate(pyramid_u8(comp.view((3 * B,) + tuple(color_0.shape[1:])), self.height, self.width, S,
-                                             want_f32=True)):
-                for j, (name, fid) in enumerate(names):
-                    out[(name, fid, i)] = f[j * B:(j + 1) * B]
-            for i in range(S):                                        # :258: color['s'] is color_aug['s']
-                out[("color", "s", i)] = out[("color_aug", "s", i)]
-            out[("color_ben", 0, 0)] = out[("color", 0, 0)]           # :132-133 with the identity colour jitter
+            stack = comp.view((3 * B,) + tuple(color_0.shape[1:]))
+            if color_aug is None:
+                for i, f in enumerate(pyramid_u8(stack, self.height, self.width, S, want_f32=True)):
+                    for j, (name, fid) in enumerate(names):
+                        out[(name, fid, i)] = f[j * B:(j + 1) * B]
+                for i in range(S):                                    # :258: color['s'] is color_aug['s']
+                    out[("color", "s", i)] = out[("color_aug", "s", i)]
+                out[("color_ben", 0, 0)] = out[("color", 0, 0)]       # :132-133 with the identity colour jitter
+            else:
+                if len(color_aug) != B:
+                    raise RuntimeError("Batch size doesn't match!")
+                pa = list(color_aug)
+                for i, u in enumerate(pyramid_u8(stack, self.height, self.width, S, want_f32=False)):
+                    # "color" entries: to_tensor of the level; "color_aug": to_tensor(color_aug(level)) (:140-144)
+                    plain = unpack_u8(u[B:])                          # [stereo partner, benign frame 0]
+                    out[("color", "s", i)], out[("color", 0, i)] = plain[:B], plain[B:]
+                    _, jit = color_jitter_u8(u[:2 * B], pa + pa, want_u8=False, want_f32=True)
+                    out[("color_aug", 0, i)], out[("color_aug", "s", i)] = jit[:B], jit[B:]
+                    if i == 0:                                        # :132-133
+                        _, out[("color_ben", 0, 0)] = color_jitter_u8(u[2 * B:], pa, want_u8=False, want_f32=True)
             if not self.half_no_synthesis:
                 # mask.expand(-1, 3, -1, -1): three identical planes -> resize one, replicate
                 _, om = resize_lanczos_u8(objmask, self.height, self.width, want_f32=True)

@@ -465,8 +465,18 @@ class _Objective(torch.autograd.Function):
     def forward(ctx, K, inv_K, cfg, *tensors):
         (min_depth, max_depth, flags, smooth_w, want_sel, n_src, S, automask, has_noise) = cfg
         it = iter(tensors)
-        colors = [f32c(next(it)) for _ in range(S)]          # color(0, s)
-        srcs = [f32c(next(it)) for _ in range(n_src)]
+        colors_in = [next(it) for _ in range(S)]             # color(0, s)
+        srcs_in = [next(it) for _ in range(n_src)]
+        # bf16 frames (2e-3 tolerance class): the full-resolution target / source are read AS bf16 by the identity
+        # kernel (128-bit loads of 8 elements), which also writes the widened target -- no up-cast pass over them
+        bf16_frames = (n_src == 1 and colors_in[0].dtype == torch.bfloat16 and srcs_in[0].dtype == torch.bfloat16
+                       and colors_in[0].is_cuda and colors_in[0].shape[3] % 8 == 0 and not (flags & FLAG_NO_SSIM))
+        if bf16_frames:
+            colors = [colors_in[0].contiguous()] + [f32c(c) for c in colors_in[1:]]
+            srcs = [srcs_in[0].contiguous()]
+        else:
+            colors = [f32c(c) for c in colors_in]
+            srcs = [f32c(t) for t in srcs_in]
         Ts = [f32c(next(it)) for _ in range(n_src)]
         disps = [f32c(next(it)) for _ in range(S)]
         noises = [f32c(next(it)) for _ in range(S)] if has_noise else [None] * S
@@ -482,12 +492,22 @@ class _Objective(torch.autograd.Function):
         # single source, no pose gradient: the per-scale kernel gathers from a pixel-packed (B,H,W,4) copy of the
         # source (one 128-bit load per bilinear tap), written once by the identity-loss kernel
         packed = n_src == 1 and not need_T and not no_ssim and H * W < (1 << 28)
+        if bf16_frames and not (packed and target.data_ptr() % 16 == 0 and srcs[0].data_ptr() % 16 == 0):
+            bf16_frames = False                             # general kernels: widen first
+            target = colors[0] = f32c(target)
+            srcs = [f32c(srcs[0])]
         ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32) if automask else None
-        src_arr = ptr_array(srcs)
+        src_arr = ptr_array(srcs) if not bf16_frames else None
         if packed:
             src_pk = torch.empty(B, H, W, 4, device=dev, dtype=torch.float32)
-            check(lib.dmh_identity_loss_pack(ptr(target), ptr(srcs[0]), B, H, W, no_ssim, ptr(ident), ptr(src_pk),
-                                             stream()), "identity_loss_pack")
+            if bf16_frames:
+                tgt32 = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+                check(lib.dmh_identity_loss_pack_bf16(ptr(target), ptr(srcs[0]), B, H, W, no_ssim, ptr(ident),
+                                                      ptr(src_pk), ptr(tgt32), stream()), "identity_loss_pack_bf16")
+                target = colors[0] = tgt32
+            else:
+                check(lib.dmh_identity_loss_pack(ptr(target), ptr(srcs[0]), B, H, W, no_ssim, ptr(ident), ptr(src_pk),
+                                                 stream()), "identity_loss_pack")
             src_arr = ptr_array([src_pk])
             flags |= FLAG_SRC_PACKED
         elif automask:

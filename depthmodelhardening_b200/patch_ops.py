@@ -268,6 +268,16 @@ def pgd_linf_step(adv, grad, clean, alpha, eps):
     return out
 
 
+def apgd_linf_step(x_adv, x_adv_old, grad, x0, step, a, eps):
+    """phy_obj_atk_apgd.py:214-222 (L-inf branch) in one launch: momentum step with the double eps-ball / [0,1]
+    projection; returns the new iterate."""
+    xa, xo, g, c = f32c(x_adv), f32c(x_adv_old), f32c(grad), f32c(x0)
+    out = torch.empty_like(xa)
+    check(_lib_().dmh_apgd_linf_step(ptr(xa), ptr(xo), ptr(g), ptr(c), xa.numel(), float(step), float(a), float(eps),
+                                     ptr(out), stream()), "apgd_linf_step")
+    return out
+
+
 def pgd_l2_step(adv, grad, clean, alpha, eps, eps_div=1e-10):
     """phy_obj_atk_l2.py:108-120 in one launch: normalised-gradient ascent, projection onto the L2 ball of radius
     eps around the clean patch, clamp to [0,1]."""

@@ -156,6 +156,13 @@ int dmh_identity_loss(const float* target, const float* const* src_host, int F, 
  * every scale, the re-layout is done once).  ident nullable: re-layout only (automasking disabled).            */
 int dmh_identity_loss_pack(const float* target, const float* src, int B, int H, int W, int no_ssim, float* ident,
                            float* src_packed, dmh_stream_t stream);
+/* bf16 frames (BASELINE north_star: bf16 inputs at 2e-3, "bf16x8 coalesced loads"): the same pass reading the two
+ * frames as bf16 (B,3,H,W) with 128-bit loads of 8 elements and ALSO writing target_f32 (B,3,H,W), the widened
+ * target every later kernel of the step stages by TMA -- no separate up-cast pass over the frames.  The identity
+ * loss is computed on the widened values, i.e. equals dmh_identity_loss_pack on target.float(), src.float() bit for
+ * bit.  Needs W % 8 == 0 and 16-byte aligned frames.                                                          */
+int dmh_identity_loss_pack_bf16(const uint16_t* target_bf16, const uint16_t* src_bf16, int B, int H, int W, int no_ssim,
+                                float* ident, float* src_packed, float* target_f32, dmh_stream_t stream);
 #define DMH_PHOTO_NO_SSIM 1
 #define DMH_PHOTO_AVG_REPROJECTION 2
 #define DMH_PHOTO_INPUT_IS_DEPTH 4
@@ -282,6 +289,21 @@ int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const fl
 int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, long long n, float alpha, float eps,
                       float* out, dmh_stream_t stream);
 
+/* -- APGD L-inf step with momentum (next-4; torchattacks/attacks/phy_obj_atk_apgd.py:214-222), one launch:
+ * z = clamp(proj_eps(x_adv + step*sign(grad)), 0, 1); out = clamp(proj_eps(x_adv + (z - x_adv)*a +
+ * (x_adv - x_adv_old)*(1-a)), 0, 1), proj_eps = min(max(., x0-eps), x0+eps).  out may alias x_adv.            */
+int dmh_apgd_linf_step(const float* x_adv, const float* x_adv_old, const float* grad, const float* x0, long long n,
+                       float step, float a, float eps, float* out, dmh_stream_t stream);
+
+/* -- evaluation metrics of the attack harness (next-4; DepthNetworks/monodepth2/evaluate_depth.py:193-196 and
+ * compute_errors :57-99), one launch per batch: depth = clamp(disp_to_depth(|disp|, min_disp_depth, max_disp_depth)[1]
+ * * scale_factor, min_depth, max_depth) for both maps, then out[9] (double, zeroed here) = [sum mask, sum |d|*m,
+ * sum |d|/gt*m, sum d^2/gt*m, sum d^2*m, sum (log gt - log pred)^2*m, sum [thr<1.25]*m, [thr<1.25^2], [thr<1.25^3]],
+ * thr = max(gt/pred, pred/gt); mask NULL = all ones.  The caller divides by out[0] and takes the two roots.    */
+int dmh_depth_errors(const float* disp_gt, const float* disp_pred, const float* mask, long long n, float min_disp_depth,
+                     float max_disp_depth, float scale_factor, float min_depth, float max_depth, double* out,
+                     dmh_stream_t stream);
+
 /* -- L2 PGD update of the shared patch (next-4; torchattacks/attacks/phy_obj_atk_l2.py:108-120):
  * g = grad / (||grad||_2 + eps_div); x = adv + alpha*g; d = x - clean;
  * out = clamp(clean + d * min(eps / ||d||_2, 1), 0, 1).  One launch; out may alias adv.                      */
@@ -386,6 +408,17 @@ int dmh_compose_patch_u8(const uint8_t* scene, const float* patch_a, const float
 int dmh_lanczos_u8(const uint8_t* in, int planes, int in_h, int in_w, int out_h, int out_w, const int* bounds_x,
                    const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp,
                    uint8_t* out, float* out_f32, dmh_stream_t stream);
+
+/* Colour jitter on 8-bit frames (next-2; DepthNetworks/monodepth2/datasets/mono_dataset.py:297, 344-350, applied to
+ * every pyramid level in preprocess :140-144; torchvision ColorJitter.forward -> functional_pil -> PIL.ImageEnhance /
+ * convert("HSV")): in (B,3,H,W) uint8; per item order (B,4) int32 = the drawn fn_idx (0 brightness, 1 contrast,
+ * 2 saturation, 3 hue; < 0: step off), factors (B,3) = brightness / contrast / saturation factors, hue_shift (B)
+ * int32 = uint8(hue_factor * 255) -- all DEVICE arrays; sums (B) uint64 workspace (per-image grey-level sums of the
+ * contrast step).  out_u8 (B,3,H,W) and / or out_f32 = byte / 255 (to_tensor).  Pillow's integer / single-precision
+ * arithmetic, bit-exact.  Two launches.                                                                        */
+int dmh_color_jitter_u8(const uint8_t* in, int B, int H, int W, const int* order, const float* factors,
+                        const int* hue_shift, unsigned long long* sums, uint8_t* out_u8, float* out_f32,
+                        dmh_stream_t stream);
 
 /* 8-bit frame transport (data format either side of the path): out[i] = (float)in[i] / 255 with IEEE division --
  * torchvision's `to_tensor` (`pic.to(float32).div(255)`), the conversion every colour frame of the reference goes

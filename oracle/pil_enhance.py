@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.  GROUNDWORK for the colour jitter of the
-loader row: no CUDA kernel consumes it yet.
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.  Oracle of the colour jitter of the loader
+row: `dmh_color_jitter_u8` (csrc/loader_compose.cu, csrc/jitter_math.cuh) is checked against it.
 
 CPU restatement (numpy) of the brightness / contrast / saturation steps that `transforms.ColorJitter` applies to the
 8-bit PIL frames when the reference trains with contrastive learning (`mono_dataset.py:297, 344-350`; torchvision
@@ -105,3 +105,19 @@ def hue(img: np.ndarray, f: float) -> np.ndarray:
     hsv = rgb_to_hsv(img)
     hsv[0] = (hsv[0].astype(np.int32) + int(np.uint8(int(f * 255) & 0xff))).astype(np.uint8)   # uint8 wrap
     return hsv_to_rgb(hsv)
+
+
+def jitter(img: np.ndarray, fn_idx, brightness_factor, contrast_factor, saturation_factor, hue_factor) -> np.ndarray:
+    """torchvision `ColorJitter.forward` on an 8-bit RGB image [3,H,W] with the parameters `ColorJitter.get_params`
+    drew (the reference draws them once per item and applies them to every pyramid level, mono_dataset.py:344-350,
+    140-144): the four steps in the order `fn_idx`; a factor of None switches its step off."""
+    for fn_id in [int(i) for i in fn_idx]:
+        if fn_id == 0 and brightness_factor is not None:
+            img = brightness(img, float(brightness_factor))
+        elif fn_id == 1 and contrast_factor is not None:
+            img = contrast(img, float(contrast_factor))
+        elif fn_id == 2 and saturation_factor is not None:
+            img = saturation(img, float(saturation_factor))
+        elif fn_id == 3 and hue_factor is not None:
+            img = hue(img, float(hue_factor))
+    return img

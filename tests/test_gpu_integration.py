@@ -240,3 +240,151 @@ def test_reference_attack_iteration_vs_fused_apply(dev):
     # Adam's first step moves every element by lr * sign(g) wherever |g| >> eps: compare the updated patterns
     assert_close(l0.ppos, s1.pp.detach(), 1e-4, "pattern_pos after the Adam step", max_outlier_frac=2e-3, outlier_rtol=2.0)
     assert_close(l0.pneg, s1.pn.detach(), 1e-4, "pattern_neg after the Adam step", max_outlier_frac=2e-3, outlier_rtol=2.0)
+
+
+def test_apgd_dropin_vs_reference_class_same_device(dev):
+    """next-4: `Phy_obj_atk_apgd` (Auto-PGD with momentum and the step-size schedule) -- the drop-in against the
+    reference's OWN class (oracle/_ref copy) on the same GPU, same stand-in network, same torch / numpy / random seeds.
+    Both consume the RNGs identically, so placements and the random start agree; what differs is kernels vs torch ops
+    (sign flips of the step where |grad| ~ 0 are bounded as in the other attack-loop tests)."""
+    import importlib
+    import os
+    import random
+    from depthmodelhardening_b200 import attacks
+    from tests.test_gpu_patch import _tiny
+    ref = _reference_or_skip()
+    ref_apgd = importlib.import_module("torchattacks.attacks.phy_obj_atk_apgd")
+    attacks.object_dataset_root = ref.calib_root
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    dist = list(range(5, 10, 2))
+    outs = []
+    for cls in (ref_apgd.Phy_obj_atk_APGD, attacks.Phy_obj_atk_APGD):
+        torch.manual_seed(123)
+        torch.cuda.manual_seed_all(123)
+        random.seed(11)
+        np.random.seed(12)
+        atk = cls(model, pbt.obj.clone(), pbt.mask.clone(), norm="Linf", eps=0.1, steps=8, seed=17, dist_range=dist)
+        outs.append(atk(pbt.scenes.clone(), 3))
+    (adv_r, ben_r, m_r, x_r), (adv_o, ben_o, m_o, x_o) = outs
+    assert x_o.shape == x_r.shape == pbt.obj.shape
+    assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    # the adversarial patch: identical except where a ~0 gradient flipped the sign of a step
+    frac = float(((x_o - x_r).abs() > 1e-6).float().mean())
+    assert frac < 2e-2, frac
+    assert float((x_o - pbt.obj).abs().max()) <= 0.1 + 1e-6 and float(x_o.min()) >= 0.0 and float(x_o.max()) <= 1.0
+    assert_close(adv_o.double().sum(), adv_r.double().sum(), 1e-3, "adv scenes (sum)")
+
+
+def test_apgd_step_kernel_is_the_torch_expression_bit_for_bit(dev):
+    """dmh_apgd_linf_step against phy_obj_atk_apgd.py:214-222 evaluated by torch, element for element."""
+    from depthmodelhardening_b200 import patch_ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 3, 260, 300, generator=gen).to(dev)
+    x_adv = (x + 0.1 * (2 * torch.rand(x.shape, generator=gen).to(dev) - 1)).clamp(0, 1)
+    x_old = (x + 0.1 * (2 * torch.rand(x.shape, generator=gen).to(dev) - 1)).clamp(0, 1)
+    grad = torch.randn(x.shape, generator=gen).to(dev)
+    grad.view(-1)[::7] = 0.0                                   # sign(0) = 0
+    eps = 0.1
+    for a, step in ((1.0, 0.2), (0.75, 0.05), (0.75, 0.0125)):
+        step_size = step * torch.ones([1, 1, 1, 1], device=dev)
+        grad2 = x_adv - x_old
+        z = x_adv + step_size * torch.sign(grad)
+        z = torch.clamp(torch.min(torch.max(z, x - eps), x + eps), 0.0, 1.0)
+        want = torch.clamp(torch.min(torch.max(x_adv + (z - x_adv) * a + grad2 * (1 - a), x - eps), x + eps), 0.0, 1.0)
+        got = patch_ops.apgd_linf_step(x_adv, x_old, grad, x, step, a, eps)
+        assert torch.equal(got, want), int((got != want).sum())
+
+
+def _numpy_compute_errors(gt, pred, mask):
+    """evaluate_depth.py:57-99 verbatim semantics in numpy (float32 in, as the harness feeds it)."""
+    if mask is None:
+        mask = np.ones_like(gt)
+    total = mask.sum()
+    thresh = np.maximum(gt / pred, pred / gt)
+    a = [((thresh < 1.25 ** k) * mask).sum() / total for k in (1, 2, 3)]
+    abs_err = (np.abs(gt - pred) * mask).sum() / total
+    rmse = np.sqrt((((gt - pred) ** 2) * mask).sum() / total)
+    rmse_log = np.sqrt((((np.log(gt) - np.log(pred)) ** 2) * mask).sum() / total)
+    abs_rel = np.sum(np.abs(gt - pred) / gt * mask) / total
+    sq_rel = np.sum(((gt - pred) ** 2) / gt * mask) / total
+    return abs_err, abs_rel, sq_rel, rmse, rmse_log, a[0], a[1], a[2]
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_depth_error_metrics_vs_numpy(dev, masked):
+    """evaluation.compute_errors (one launch: disparity -> clamped metric depth -> eight masked reductions) against the
+    harness' own sequence -- torch disp_to_depth / clamp on the device, numpy reductions on the host
+    (evaluate_depth.py:193-196, 57-99)."""
+    from depthmodelhardening_b200 import evaluation, layers
+    gen = torch.Generator().manual_seed(8)
+    B, H, W = 3, 320, 1024
+    disp_gt = (torch.rand(B, 1, H, W, generator=gen) * 0.6 + 0.01).to(dev)
+    disp_atk = (disp_gt.cpu() * (0.5 + torch.rand(B, 1, H, W, generator=gen))).to(dev)
+    disp_atk.view(-1)[::1001] *= -1.0                      # the harness takes |disp|
+    mask = None
+    if masked:
+        mask = torch.zeros(B, 1, H, W)
+        mask[:, :, 100:220, 300:700] = torch.rand(B, 1, 120, 400, generator=gen)   # resized masks are fractional
+        mask = mask.to(dev)
+    got = evaluation.compute_errors(disp_gt, disp_atk, mask)
+    gt_depth = torch.clamp(layers.disp_to_depth(torch.abs(disp_gt), 0.1, 100)[1] * 5.4, max=80, min=1e-3)
+    atk_depth = torch.clamp(layers.disp_to_depth(torch.abs(disp_atk), 0.1, 100)[1] * 5.4, max=80, min=1e-3)
+    want = _numpy_compute_errors(gt_depth.cpu().numpy().astype(np.float64), atk_depth.cpu().numpy().astype(np.float64),
+                                 None if mask is None else mask.cpu().numpy().astype(np.float64))
+    for name, g, w in zip(evaluation.ERROR_NAMES, got, want):
+        assert abs(g - w) <= 1e-5 * max(abs(w), 1e-12), (name, g, w)
+
+
+def test_evaluate_attacks_harness_runs_on_the_dropins(dev):
+    """evaluation.evaluate_attacks (evaluate_depth.py:113-214 on the drop-in attack classes): two scene batches, L-inf
+    and vanila, finite statistics; the attacked depth error on the object is larger than the vanila one."""
+    import os
+    from depthmodelhardening_b200 import attacks, evaluation
+    from oracle import refload
+    from tests.test_gpu_patch import _tiny
+    import tempfile
+    root = tempfile.mkdtemp(prefix="dmh_eval_")
+    refload.write_calib(root)
+    attacks.object_dataset_root = root
+    pbt = synth.patch_batch(batch=2, seed=6).to(dev)
+    model = _tiny(dev).eval()
+    scenes = [pbt.scenes, pbt.scenes.flip(0)]
+    base = dict(batch_size=2, epsilon=0.1, alpha=0.02, step=3)
+    torch.manual_seed(0)
+    mean_v, max_v = evaluation.evaluate_attacks(model, dict(base, norm_type="vanila"), scenes, pbt.obj, pbt.mask,
+                                                eval_count=2, verbose=False)
+    mean_a, max_a = evaluation.evaluate_attacks(model, dict(base, norm_type="l_inf"), scenes, pbt.obj, pbt.mask,
+                                                eval_count=2, verbose=False)
+    assert mean_v.shape == (8,) and np.isfinite(mean_v).all() and np.isfinite(max_a).all()
+    assert mean_v[0] < 1e-6                                  # vanila: adversarial == benign object
+    assert mean_a[0] > mean_v[0]
+    with pytest.raises(NotImplementedError):
+        evaluation.build_attack(model, dict(base, norm_type="Square"), pbt.obj, pbt.mask)
+
+
+
+def test_gaussian_blur_attack_dropin_vs_reference_class_same_device(dev):
+    """next-4: `Phy_obj_atk_guassian` -- the drop-in against the reference's own class on the same GPU, same network
+    and seeds: same candidates (scipy blur), same placements, so the chosen patch is the same candidate and the
+    returned scenes agree to the patch-apply tolerance."""
+    import importlib
+    import random
+    from depthmodelhardening_b200 import attacks
+    from tests.test_gpu_patch import _tiny
+    ref = _reference_or_skip()
+    ref_g = importlib.import_module("torchattacks.attacks.phy_obj_atk_guassian")
+    attacks.object_dataset_root = ref.calib_root
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    outs = []
+    for cls in (ref_g.Phy_obj_atk_guassian, attacks.Phy_obj_atk_guassian):
+        random.seed(21)
+        atk = cls(model, pbt.obj.clone(), pbt.mask.clone(), steps=5, dist_range=list(range(5, 10, 2)))
+        outs.append(atk(pbt.scenes.clone(), 3))
+    (adv_r, ben_r, m_r, x_r), (adv_o, ben_o, m_o, x_o) = outs
+    assert torch.equal(x_o, x_r)                           # the same blurred candidate won
+    assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)

@@ -334,14 +334,35 @@ def _placements(seed, steps, ranges, batch):
     return out[:-1], out[-1]
 
 
-def test_attack_classes_vs_oracle_loop_same_device(dev, calib):
+def _resnet18_monodepth2(dev):
+    """north_star's network: random-init ResNet-18 monodepth2 encoder + depth decoder, the reference's own classes
+    (`networks.ResnetEncoder(18, False)`, `DepthDecoder`, `depth_model.DepthModelWrapper`; depth_model.py:10-20) from
+    the copy oracle/build_ref.py ships; deterministic fp32 cuDNN as for the stand-in network."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference copy not present")
+    ref = refload.load()
+    _tiny(dev)                                              # sets the cuDNN determinism flags
+    torch.manual_seed(0)
+    enc = ref.networks.ResnetEncoder(18, False)
+    dec = ref.networks.DepthDecoder(num_ch_enc=enc.num_ch_enc, scales=range(4))
+    return ref.depth_model.DepthModelWrapper(enc, dec).to(dev)
+
+
+@pytest.mark.parametrize("net", ["tiny", "resnet18"])
+def test_attack_classes_vs_oracle_loop_same_device(dev, calib, net):
     """Our attack classes against the oracle's restatement of the reference loops, BOTH driven on the GPU with
-    the same network, so the only difference is kernels vs torch ops."""
+    the same network, so the only difference is kernels vs torch ops.  `resnet18`: the random-init ResNet-18
+    monodepth2 encoder / decoder BASELINE.json names (the reference's own network classes)."""
     import os
     from depthmodelhardening_b200 import attacks
     attacks.object_dataset_root = os.path.dirname(os.path.dirname(os.path.dirname(calib)))
     pbt = synth.patch_batch(batch=3, seed=4).to(dev)
-    model = _tiny(dev).eval()
+    model = (_tiny(dev) if net == "tiny" else _resnet18_monodepth2(dev)).eval()
+    # fraction of elements allowed to differ: sign(grad) flips where |grad| ~ 0.  The random-init ResNet-18 has far
+    # more near-zero patch gradients than the 2-conv stand-in (measured 0.8 % over 3 L-inf steps against 0.1 %)
+    flips = 5e-3 if net == "tiny" else 2e-2
+    l0_atol = 1e-4
     dist, ang = list(range(5, 10, 2)), list(range(-30, 31, 5))
     # ---- L-inf, 3 steps
     pl, fin = _placements(9, 3, (dist, ang), 3)
@@ -350,9 +371,28 @@ def test_attack_classes_vs_oracle_loop_same_device(dev, calib):
     atk = attacks.Phy_obj_atk(model, pbt.obj.clone(), pbt.mask.clone(), eps=0.1, alpha=0.02, steps=3,
                               random_start=False, dist_range=dist)
     out = atk(pbt.scenes.clone(), 3)
-    assert float(((out[3] - ref[3]).abs() > 1e-6).float().mean()) < 5e-3      # sign flips at |grad| ~ 0
+    assert float(((out[3] - ref[3]).abs() > 1e-6).float().mean()) < flips      # sign flips at |grad| ~ 0
     assert_close(out[1], ref[1], TOL, "benign scenes")
     assert_close(out[2], ref[2], TOL, "masks")
+    if net == "resnet18":
+        # L0 through this network is not a kernel test: |d cost / d patch| is ~1e-9 for most elements, below Adam's
+        # eps = 1e-8, so the update lr * m / (sqrt(v) + eps) is LINEAR in grad / 1e-8 and iterating it amplifies the
+        # 1e-5-level difference between the fused and the composed backward into O(0.1) pattern differences within 4
+        # steps (measured: 16 % of the elements beyond 5e-3) -- in both directions, also between two torch runs with
+        # different cuDNN algorithms.  What IS checked with the real network: one gradient of the attack cost w.r.t.
+        # the patch through fused apply -> ResNet-18 -> MSE against the composed torch ops, same placements.
+        from depthmodelhardening_b200 import patch_ops
+        z0, al = pl[0]
+        obj_a = pbt.obj.clone().requires_grad_(True)
+        coeffs = patch_ops.homographies(z0, al, P34, obj_hw=(synth.PATCH_H, synth.PATCH_W)).to(dev)
+        adv_a, m_a = patch_ops.apply_patch(obj_a, pbt.mask, pbt.scenes, coeffs)
+        torch.nn.functional.mse_loss(model(adv_a) * m_a, torch.zeros_like(m_a)).backward()
+        obj_b = pbt.obj.clone().requires_grad_(True)
+        adv_b, m_b = OQ.apply_patch(obj_b, pbt.mask, pbt.scenes, z0, al, P34)
+        torch.nn.functional.mse_loss(model(adv_b) * m_b, torch.zeros_like(m_b)).backward()
+        assert_close(adv_a, adv_b, TOL, "adv scenes (ResNet-18 run)", max_outlier_frac=1e-4, outlier_rtol=1.0)
+        assert_close(obj_a.grad, obj_b.grad, 5e-3, "d cost / d patch through ResNet-18")
+        return
     # ---- L0, steps=2 (4 iterations)
     np.random.seed(3)
     init = [torch.Tensor(np.clip(np.random.random(pbt.obj.size()), 0.0, 1.0)).to(dev) for _ in range(2)]
@@ -364,10 +404,10 @@ def test_attack_classes_vs_oracle_loop_same_device(dev, calib):
     atk0 = attacks.Phy_obj_atk_l0(model, pbt.obj.clone(), pbt.mask.clone(), adam_lr=0.5, steps=2, mask_wt=0.06,
                                   l0_thresh=0.1, dist_range=dist)
     out0 = atk0(pbt.scenes.clone(), 3)
-    assert float(((atk0.pattern_pos_tensor - ref0[3]).abs() > 1e-4).float().mean()) < 5e-3
-    assert float(((atk0.pattern_neg_tensor - ref0[4]).abs() > 1e-4).float().mean()) < 5e-3
+    assert float(((atk0.pattern_pos_tensor - ref0[3]).abs() > l0_atol).float().mean()) < flips
+    assert float(((atk0.pattern_neg_tensor - ref0[4]).abs() > l0_atol).float().mean()) < flips
     surv, surv_ref = (atk0.pattern.abs().sum(1) != 0), (ref0[5].abs().sum(1) != 0)
-    assert float((surv != surv_ref).float().mean()) < 5e-3
+    assert float((surv != surv_ref).float().mean()) < flips
 
 
 def test_batch_arena_roundtrip(dev):

@@ -328,16 +328,60 @@ def test_bf16_frames(dev):
     rounded.color = {k: v.to(torch.bfloat16).float() for k, v in pb.color.items()}
     total_r, losses_r, grads_r = OP.objective_from_batch(rounded)
     _, _, grads64 = OP.objective_from_batch(rounded, dtype=torch.float64)
+    from depthmodelhardening_b200 import ops
     g = pb.to(dev)
     colors = {k: v.to(torch.bfloat16) for k, v in g.color.items()}
     disps = {s: g.disp[s].clone().requires_grad_(True) for s in g.scales}
-    losses, _ = objective.photometric_losses(colors, disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height,
-                                             g.width, noise=g.noise)
+    # the full-resolution frames must be read AS bf16 by the kernel (dmh_identity_loss_pack_bf16), not widened by an
+    # ATen pass: any f32c() of a full-resolution bf16 tensor fails the test
+    real_f32c = ops.f32c
+
+    def guarded(t):
+        assert not (t.dtype == torch.bfloat16 and tuple(t.shape[-2:]) == (g.height, g.width)), "ATen up-cast of a frame"
+        return real_f32c(t)
+    ops.f32c = guarded
+    try:
+        losses, _ = objective.photometric_losses(colors, disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height,
+                                                 g.width, noise=g.noise)
+    finally:
+        ops.f32c = real_f32c
     losses["loss"].backward()
     assert_close(losses["loss"], total_r, TOL, "loss vs oracle on bf16-rounded frames")
     for s in pb.scales:
         assert_grad_close(disps[s].grad, grads_r[s], grads64[s], TOL, "grad_disp_%d" % s)
     assert rel_err(losses["loss"], total32) < 2e-3
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (40, 72), (33, 40), (320, 1024)])
+def test_bf16_identity_pack_equals_fp32_on_widened_frames(dev, hw):
+    """dmh_identity_loss_pack_bf16 (128-bit loads of 8 bf16, widened in shared memory) against
+    dmh_identity_loss_pack on `.float()` of the same frames: identity loss, packed source and the widened target
+    agree BIT FOR BIT (ragged heights / border tiles included; W % 8 == 0)."""
+    from depthmodelhardening_b200 import _lib
+    from depthmodelhardening_b200._lib import check, ptr, stream
+    H, W = hw
+    B = 2
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(17)
+    t16 = torch.rand(B, 3, H, W, generator=gen).to(torch.bfloat16).to(dev)
+    s16 = torch.rand(B, 3, H, W, generator=gen).to(torch.bfloat16).to(dev)
+    t32, s32 = t16.float().contiguous(), s16.float().contiguous()
+    ident_a = torch.full((B, 1, H, W), float("nan"), device=dev)
+    pk_a = torch.full((B, H, W, 4), float("nan"), device=dev)
+    check(lib.dmh_identity_loss_pack(ptr(t32), ptr(s32), B, H, W, 0, ptr(ident_a), ptr(pk_a), stream()))
+    ident_b = torch.full((B, 1, H, W), float("nan"), device=dev)
+    pk_b = torch.full((B, H, W, 4), float("nan"), device=dev)
+    tgt = torch.full((B, 3, H, W), float("nan"), device=dev)
+    check(lib.dmh_identity_loss_pack_bf16(ptr(t16), ptr(s16), B, H, W, 0, ptr(ident_b), ptr(pk_b), ptr(tgt), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(tgt, t32)
+    assert torch.equal(pk_b[..., :3], pk_a[..., :3]) and torch.equal(pk_b[..., :3], s32.permute(0, 2, 3, 1))
+    assert torch.equal(ident_a, ident_b)
+    # unsupported shapes are refused, not mis-read
+    bad = torch.zeros(1, 3, 8, 12, dtype=torch.bfloat16, device=dev)
+    rc = lib.dmh_identity_loss_pack_bf16(ptr(bad), ptr(bad), 1, 8, 12, 0, None, ptr(torch.empty(1, 8, 12, 4, device=dev)),
+                                         ptr(torch.empty(1, 3, 8, 12, device=dev)), stream())
+    assert rc != 0
 
 
 @pytest.mark.parametrize("hw", [(320, 1024), (640, 2048)])

@@ -173,6 +173,45 @@ def test_oracle_enhance_equals_pillow():
             assert np.array_equal(E.hue(img, f), as_np(TF.adjust_hue(pil, f))), ("hue", f)
 
 
+def _jitter_cases():
+    """(fn_idx, b, c, s, h) tuples: every position of the contrast step, factors inside / outside [0, 1], None factors."""
+    import itertools
+    rng = np.random.default_rng(9)
+    cases = []
+    for perm in list(itertools.permutations(range(4)))[::3]:
+        cases.append((list(perm), float(rng.uniform(0.8, 1.2)), float(rng.uniform(0.8, 1.2)), float(rng.uniform(0.8, 1.2)),
+                      float(rng.uniform(-0.1, 0.1))))
+    cases.append(([1, 0, 3, 2], 1.7, 0.3, 0.0, -0.5))
+    cases.append(([3, 2, 1, 0], None, 1.1, None, 0.07))
+    cases.append(([0, 1, 2, 3], 0.9, None, 1.15, None))
+    return cases
+
+
+def test_oracle_jitter_equals_torchvision_colorjitter():
+    """oracle/pil_enhance.jitter (the composition `ColorJitter.forward` applies, in the drawn order) against
+    torchvision's own functional chain on the PIL image, bit for bit -- incl. the contrast step's mean grey level
+    of the PARTIALLY jittered image."""
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from oracle import pil_enhance as E
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (3, 47, 65), dtype=np.uint8)
+    pil0 = Image.fromarray(np.ascontiguousarray(np.transpose(img, (1, 2, 0))))
+    for (fn_idx, bf, cf, sf, hf) in _jitter_cases():
+        pil = pil0
+        for fn_id in fn_idx:                                   # torchvision ColorJitter.forward
+            if fn_id == 0 and bf is not None:
+                pil = TF.adjust_brightness(pil, bf)
+            elif fn_id == 1 and cf is not None:
+                pil = TF.adjust_contrast(pil, cf)
+            elif fn_id == 2 and sf is not None:
+                pil = TF.adjust_saturation(pil, sf)
+            elif fn_id == 3 and hf is not None:
+                pil = TF.adjust_hue(pil, hf)
+        want = np.transpose(np.asarray(pil), (2, 0, 1))
+        assert np.array_equal(E.jitter(img, fn_idx, bf, cf, sf, hf), want), (fn_idx, bf, cf, sf, hf)
+
+
 def test_composer_rejects_cpu_tensors():
     from depthmodelhardening_b200 import loader
     with pytest.raises(RuntimeError, match="CUDA-only"):
@@ -340,3 +379,63 @@ def test_cuda_composer_half_no_synthesis_raw_items_are_bit_exact(dev, tmp_path):
     d = np.abs(as_u8(out[("color_aug", 0, 0)][2]).astype(np.int32) - as_u8(ref[("color_aug", 0, 0)]).astype(np.int32))
     assert d.max() <= 1 and float((d > 0).mean()) < 0.01
     assert int((as_u8(out[("color_aug", 0, 0)][2]) != as_u8(out[("color", 0, 0)][2])).sum()) > 1000   # patch differs
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [(40, 128), (33, 37), (320, 1024)])
+def test_cuda_colour_jitter_equals_oracle(dev, hw):
+    """dmh_color_jitter_u8 (two launches: grey-level sums of the contrast step, then all four steps in the item's drawn
+    order) against the oracle, which equals Pillow / torchvision: 8-bit output and its to_tensor image BIT-EXACT,
+    every item of the batch with its own parameters, one item without augmentation."""
+    from depthmodelhardening_b200 import loader
+    from oracle import pil_enhance as E
+    H, W = hw
+    cases = _jitter_cases() + [None]
+    if H * W > 100000:
+        cases = cases[:3] + [None]
+    B = len(cases)
+    rng = np.random.default_rng(21)
+    img = rng.integers(0, 256, (B, 3, H, W), dtype=np.uint8)
+    img[:, :, :2] = img[:, :1, :2]                              # grey pixels
+    out_u8, out_f32 = loader.color_jitter_u8(torch.from_numpy(img).to(dev), cases, want_u8=True, want_f32=True)
+    torch.cuda.synchronize()
+    for i, p in enumerate(cases):
+        want = img[i] if p is None else E.jitter(img[i], *p)
+        got = out_u8[i].cpu().numpy()
+        assert np.array_equal(got, want), (i, p, int((got != want).sum()))
+        assert torch.equal(out_f32[i].cpu(), torch.from_numpy(want).float() / 255.0)
+
+
+@pytest.mark.gpu
+def test_composer_with_colour_jitter_vs_oracle(dev):
+    """AdvBatchComposer(..., color_aug=...) (mono_dataset.py:132-133, 140-144, 344-350): the "color_aug" entries and
+    ("color_ben", 0, 0) are the jittered pyramid levels, the "color" entries the plain ones -- each equal to the
+    oracle jitter of the composer's own 8-bit level (the levels themselves are pinned by the tests above)."""
+    from depthmodelhardening_b200 import loader, synth
+    from oracle import pil_enhance as E
+    from oracle.refload import write_calib
+    import tempfile
+    calib = write_calib(tempfile.mkdtemp(prefix="dmh_calib_"))
+    B = 2
+    pt = synth.patch_batch(batch=B, seed=3)
+    comp = loader.AdvBatchComposer(pt.obj.to(dev), pt.mask.to(dev), {"path": calib}, 320, 1024, 4)
+    raw0 = synth.frames_u8(41, batch=B).to(dev)
+    raws = synth.frames_u8(42, batch=B).to(dev)
+    params = [([2, 0, 3, 1], 0.91, 1.13, 0.85, 0.04), None]
+    kw = dict(sides=["l", "r"], do_flip=[False, True], z0_sample=[5, 7], alpha_sample=[-10, 15])
+    plain = comp(raw0, raws, **kw)
+    jit = comp(raw0, raws, color_aug=params, **kw)
+    torch.cuda.synchronize()
+    to_u8 = lambda t: (t * 255.0).round().to(torch.uint8).cpu().numpy()
+    for i in range(4):
+        for fid in (0, "s"):
+            base = to_u8(plain[("color_aug", fid, i)])             # the un-jittered level of the same composite
+            for b in range(B):
+                want = base[b] if params[b] is None else E.jitter(base[b], *params[b])
+                assert np.array_equal(to_u8(jit[("color_aug", fid, i)])[b], want), (i, fid, b)
+            assert torch.equal(jit[("color", fid, i)], plain[("color", fid, i)])
+    base = to_u8(plain[("color", 0, 0)])
+    for b in range(B):
+        want = base[b] if params[b] is None else E.jitter(base[b], *params[b])
+        assert np.array_equal(to_u8(jit[("color_ben", 0, 0)])[b], want)
