@@ -20,7 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 
-// ---- exhaustive check of the 3-instruction division by a launch constant (dmh_math.cuh div_const)
+// ---- exhaustive check of the 3-instruction division by a launch constant (dmh_math.cuh div_const): all 2^24
+// significands of the binades [1,2) and [2,4), both signs.  For a NORMAL quotient without intermediate underflow the
+// result depends only on the significand of a, so this covers every a with 2^-100 <= |a| <= FLT_MAX (inf / NaN pass
+// through in div_const); below that a * rc may lose bits to underflow and the quotient can differ from IEEE division
+// by one subnormal ulp (~1e-45) -- far below anything floor() of a pixel coordinate can see.
 __device__ unsigned g_const_div_bad;
 __global__ void const_div_check_kernel(float c, float rc) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;          // 2^24 significands: binades [1,2) and [2,4)
@@ -34,6 +38,7 @@ __global__ void const_div_check_kernel(float c, float rc) {
 bool const_div_exact(int c, float* rc_out) {
     static std::mutex mu;
     static std::map<std::pair<int, int>, bool> cache;               // (device, c) -> verified
+    static std::map<int, cudaStream_t> check_stream;                // one private non-blocking stream per device
     const float rc = (float)(1.0 / (double)c);
     *rc_out = rc;
     if (c < 1) return false;
@@ -42,17 +47,30 @@ bool const_div_exact(int c, float* rc_out) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find({dev, c});
     if (it != cache.end()) return it->second;
-    // first use of this constant on this device: one small launch + one synchronous 4-byte read-back
+    // First use of this constant on this device: one small launch + a 4-byte read-back, on a PRIVATE non-blocking
+    // stream with asynchronous copies (never the legacy stream: no device-wide synchronisation, nothing joins a
+    // stream capture that may be in progress on the caller's stream).  If the check cannot run -- e.g. this thread
+    // is inside a capture whose mode forbids the synchronisation -- the constant is reported as NOT verified and
+    // NOT cached: the caller then takes the generic IEEE division (same bits), and a later call verifies it.
+    cudaStream_t& cs = check_stream[dev];
+    bool ran = true;
+    if (!cs) ran = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess;
     unsigned bad = 0;
-    bool ok = cudaMemcpyToSymbol(g_const_div_bad, &bad, sizeof(bad)) == cudaSuccess;
-    if (ok) {
-        const_div_check_kernel<<<(1u << 24) / 256, 256>>>((float)c, rc);
+    unsigned* dbad = nullptr;
+    ran = ran && cudaGetSymbolAddress((void**)&dbad, g_const_div_bad) == cudaSuccess;
+    ran = ran && cudaMemsetAsync(dbad, 0, sizeof(unsigned), cs) == cudaSuccess;
+    if (ran) {
+        const_div_check_kernel<<<(1u << 24) / 256, 256, 0, cs>>>((float)c, rc);
         bad = 1;
-        ok = cudaMemcpyFromSymbol(&bad, g_const_div_bad, sizeof(bad)) == cudaSuccess && bad == 0;
+        ran = cudaMemcpyAsync(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost, cs) == cudaSuccess &&
+              cudaStreamSynchronize(cs) == cudaSuccess;
     }
-    cudaGetLastError();
-    cache[{dev, c}] = ok;
-    return ok;
+    if (!ran) {
+        cudaGetLastError();
+        return false;
+    }
+    cache[{dev, c}] = (bad == 0);
+    return bad == 0;
 }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -163,8 +163,9 @@ DMH_HD Bilinear bilinear_setup(float ix, float iy) {
 
 // a / c for a launch constant c (W-1, H-1) in three instructions: q0 = a*rc, r = a - q0*c (exact, FMA),
 // q = q0 + r*rc.  Correctly rounded -- i.e. bit-identical to IEEE division -- for the constants the library has
-// verified EXHAUSTIVELY on the device (all 2^24 significands of two binades; the result depends only on the
-// significand of a), see dmh::const_div_exact() in core.cu; other constants take div_rn.  +-inf / NaN pass through.
+// verified EXHAUSTIVELY on the device (all 2^24 significands of two binades; for normal quotients the result depends
+// only on the significand of a: valid for 2^-100 <= |a| <= FLT_MAX), see dmh::const_div_exact() in core.cu; other
+// constants take div_rn.  +-inf / NaN pass through.
 DMH_HD float div_const(float a, float c, float rc) {
     const float q0 = mul_rn(a, rc);
     const float r = fmaf(-q0, c, a);

@@ -73,3 +73,51 @@ def test_single_process_is_identity():
     out, sc = D.allreduce_patch_grad(g, [torch.tensor(2.0)])
     assert out is g and float(sc[0]) == 2.0
     assert D.shard_range(8) == (0, 8)
+
+
+def _sync_worker(rank, world, port, ret):
+    """The attack classes' shared-patch collectives are OPT-IN (attacks._sync_patch_grad / _sync_initial_state):
+    exercised on CPU tensors through the same helpers the attack loops call (the loops themselves need the kernels)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+        from depthmodelhardening_b200 import attacks
+        gen = torch.Generator().manual_seed(100 + rank)               # every rank draws a DIFFERENT start and gradient
+        # --- no sync group (default): purely local, no collective is issued although torch.distributed is up
+        local = SimpleNamespace(sync_group=None)
+        start = torch.rand(1, 3, 6, 8, generator=gen)
+        keep = start.clone()
+        attacks._sync_initial_state(local, start)
+        g = torch.rand(1, 3, 6, 8, generator=gen)
+        assert attacks._sync_patch_grad(local, g) is g and torch.equal(start, keep)
+        # --- opted in: rank 0's start everywhere, mean gradient everywhere -> identical sign step on every rank
+        synced = SimpleNamespace(sync_group=True)
+        pos, neg = torch.rand(1, 3, 6, 8, generator=gen), torch.rand(1, 3, 6, 8, generator=gen)
+        attacks._sync_initial_state(synced, pos, neg)
+        patch = pos.clone()
+        for _ in range(3):                                            # a lock-step "attack": 3 sign steps
+            grad = torch.rand(1, 3, 6, 8, generator=gen) - 0.5
+            grad = attacks._sync_patch_grad(synced, grad)
+            patch = (patch + 0.02 * torch.sign(grad)).clamp(0, 1)
+        gathered = [torch.zeros_like(patch) for _ in range(world)]
+        dist.all_gather(gathered, patch)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "patches diverged across ranks"
+        gathered = [torch.zeros_like(neg) for _ in range(world)]
+        dist.all_gather(gathered, neg)
+        assert all(torch.equal(gathered[0], t) for t in gathered)
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_patch_sync_is_opt_in_and_keeps_ranks_identical():
+    """without `enable_patch_sync` an attack issues no collective (ordinary DDP training calls the attack
+    independently per rank); with it the start is rank 0's and every rank applies the same mean gradient, so the
+    shared patch stays bit-identical and both ranks exit cleanly."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sync_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) == "ok" and ret.get(1) == "ok"
