@@ -381,6 +381,56 @@ class Phy_obj_atk_APGD(Attack):
 Phy_obj_atk_apgd = Phy_obj_atk_APGD          # module-style alias
 
 
+class Phy_obj_atk_arbi(Attack):
+    r""""Arbitrary pattern" baseline -- drop-in of the reference's `Phy_obj_atk_arbi`
+    (torchattacks/attacks/phy_obj_atk_arbi.py:14-109; next-4): no optimisation, the window [90:170, 100:200] of the
+    patch is overwritten by uniform noise or by one random colour (the instance's `np.random.RandomState(17)` stream,
+    kept across calls as in the reference), the object is placed at `np.linspace(5, 30, batch_size)` metres with yaw
+    drawn from `RandomState(17).choice(range(-30, 31, 2))`.  One fused patch-apply launch per branch."""
+
+    def __init__(self, model, obj_img, obj_mask, dist_range=list(range(5, 31, 2))):
+        super().__init__("PGD", model)
+        self.obj_img = obj_img
+        self.obj_mask = obj_mask
+        self._supported_mode = ["default", "targeted"]
+        self._targeted = True
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        self.eps_for_division = 1e-10
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.rs = np.random.RandomState(17)
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False):
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        obj_img_adv = self.obj_img.clone().detach()
+        window = torch.zeros_like(self.obj_mask).to(self.device)
+        window[:, :, 90:170, 100:200] = 1
+        b, c, h, w = obj_img_adv.shape
+        if self.rs.rand() > 0.5:
+            pattern = torch.from_numpy(self.rs.rand(b, c, h, w)).float().to(self.device)
+        else:
+            pattern = torch.ones_like(obj_img_adv).float().to(self.device)
+            for c_ind in range(c):
+                pattern[:, c_ind, :, :] *= self.rs.rand()
+        obj_img_adv = window * pattern + obj_img_adv * (1 - window)
+        self.phy_trans_adv.reset_img(obj_img_adv, self.obj_mask)
+        z0_sample = np.linspace(5, 30, num=batch_size)
+        alpha_sample = np.random.RandomState(17).choice(list(range(-30, 31, 2)), batch_size, replace=True)
+        if eval:
+            z0_sample[0] = 7
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            co = self.phy_trans_adv._coeffs(z0_sample, alpha_sample)
+            adv_scenes, obj_masks_out = patch_ops.apply_patch(obj_img_adv, self.obj_mask, scene_imgs, co, self.scene_size)
+            ben_scenes, _ = patch_ops.apply_patch(self.obj_img, self.obj_mask, scene_imgs, co, self.scene_size)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
+
+
 class Phy_obj_atk_guassian(Attack):
     r"""Black-box blur search -- drop-in of the reference's `Phy_obj_atk_guassian`
     (torchattacks/attacks/phy_obj_atk_guassian.py:14-143; next-4; the spelling is the reference's).  `steps`

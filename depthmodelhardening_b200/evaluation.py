@@ -68,11 +68,13 @@ def build_attack(model2atk, args: Dict, obj_tensor: torch.Tensor, mask_tensor: t
                                       steps=args["step"])
     if nt == "APGD":
         return attacks.Phy_obj_atk_APGD(model2atk, obj_tensor, mask_tensor, eps=args["epsilon"], steps=args["step"])
+    if nt == "arbi":
+        return attacks.Phy_obj_atk_arbi(model2atk, obj_tensor, mask_tensor)
     if nt == "guassian":
         return attacks.Phy_obj_atk_guassian(model2atk, obj_tensor, mask_tensor, steps=args["step"])
     if nt == "vanila":
         return attacks.Phy_obj_atk_vanila(model2atk, obj_tensor, mask_tensor)
-    raise NotImplementedError("norm_type %r: the black-box searches Square / light / arbi and the whole-image PGD are "
+    raise NotImplementedError("norm_type %r: the black-box searches Square / light and the whole-image PGD are "
                               "not mirrored; after install() the reference's own classes run on the grafted "
                               "PhysicalTrans" % (nt,))
 

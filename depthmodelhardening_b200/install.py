@@ -99,6 +99,8 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
                           ("torchattacks.attacks.phy_obj_atk_l2", "Phy_obj_atk_l2"),
                           ("torchattacks.attacks.phy_obj_atk_apgd", "Phy_obj_atk_APGD"),
                           ("torchattacks.attacks.phy_obj_atk_guassian", "Phy_obj_atk_guassian"),
+                          ("torchattacks.attacks.phy_obj_atk_arbi", "Phy_obj_atk_arbi"),
+                          ("torchattacks", "Phy_obj_atk_arbi"),
                           ("torchattacks", "Phy_obj_atk_guassian"),
                           ("torchattacks", "Phy_obj_atk_APGD"), ("torchattacks", "Phy_obj_atk"),
                           ("torchattacks", "Phy_obj_atk_l0"), ("torchattacks", "Phy_obj_atk_vanila"),

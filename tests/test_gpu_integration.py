@@ -388,3 +388,26 @@ def test_gaussian_blur_attack_dropin_vs_reference_class_same_device(dev):
     assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
     assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
     assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)
+
+
+
+def test_arbitrary_pattern_attack_dropin_vs_reference_class_same_device(dev):
+    """next-4: `Phy_obj_atk_arbi` against the reference's own class: same RandomState(17) stream (two calls: the
+    stream carries over), same placements; patches equal bit for bit, scenes to the patch-apply tolerance."""
+    import importlib
+    from depthmodelhardening_b200 import attacks
+    from tests.test_gpu_patch import _tiny
+    ref = _reference_or_skip()
+    ref_a = importlib.import_module("torchattacks.attacks.phy_obj_atk_arbi")
+    attacks.object_dataset_root = ref.calib_root
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    a_ref = ref_a.Phy_obj_atk_arbi(model, pbt.obj.clone(), pbt.mask.clone())
+    a_our = attacks.Phy_obj_atk_arbi(model, pbt.obj.clone(), pbt.mask.clone())
+    for call in range(2):
+        adv_r, ben_r, m_r, x_r = a_ref(pbt.scenes.clone(), 3, eval=bool(call))
+        adv_o, ben_o, m_o, x_o = a_our(pbt.scenes.clone(), 3, eval=bool(call))
+        assert torch.equal(x_o, x_r)
+        assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+        assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+        assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)

@@ -618,6 +618,8 @@ def test_multiscale_kernel_is_bit_identical_to_per_scale(dev, hw):
     _assert_same_bits(ref, got)
     ref, got = _per_scale_vs_multiscale(dev, H, W, [(H, W)], seed=85, noise=False)                # S = 1, no noise
     _assert_same_bits(ref, got)
+    ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes[:3], seed=86, noise=False, automask=False)   # S = 3, automask off
+    _assert_same_bits(ref, got)
 
 
 def test_multiscale_kernel_full_size_is_bit_identical(dev):
