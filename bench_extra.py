@@ -106,11 +106,17 @@ def main():
                           "note": "fused: one dmh_photo_scale_dh launch per scale (single-source fast kernel with the depth-hints decision, packed source)"}))
 
     if "md_f2" in want:
-        from depthmodelhardening_b200 import objective
-        for (B, H, W) in ((16, 320, 1024), (4, 640, 2048)):
-            pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, -1, 1), seed=6).to(dev)
+        from depthmodelhardening_b200 import objective, ops
+        # BASELINE config 5 (two temporal sources, pose gradients, resolution sweep) and the "true mono+stereo" variant of
+        # config 2 (F = 3, [0,-1,1,'s']), each through the multi-source tile kernel (photo_mf.cu, one
+        # launch for all sources and scales) and through the general per-scale kernel it replaces (photo_objective.cu)
+        for (B, H, W, fids, bpp, label) in ((16, 320, 1024, (0, -1, 1), 208.0, "config 5"),
+                                            (8, 480, 1536, (0, -1, 1), 208.0, "config 5"),
+                                            (4, 640, 2048, (0, -1, 1), 208.0, "config 5"),
+                                            (32, 320, 1024, (0, -1, 1, "s"), 264.0, "config 2, mono+stereo")):
+            pb = synth.photo_batch(batch=B, height=H, width=W, frame_ids=fids, seed=6).to(dev)
             disps = {s: pb.disp[s].clone().requires_grad_(True) for s in pb.scales}
-            Ts = {k: v.clone().requires_grad_(True) for k, v in pb.T.items()}
+            Ts = {k: v.clone().requires_grad_(k != "s") for k, v in pb.T.items()}
 
             def step():
                 for d in disps.values():
@@ -120,13 +126,19 @@ def main():
                 losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, Ts, pb.frame_ids, pb.scales,
                                                          H, W, noise=pb.noise)
                 losses["loss"].backward()
-            ms = timed(step, args.steps, args.warmup)
-            bpp = 208.0          # F=2
-            print(json.dumps({"workload": "photometric objective fwd+bwd, two temporal sources + pose gradients "
-                                          "(config 5)", "B": B, "H": H, "W": W, "ms_per_step": ms,
-                              "mpix_per_s": B * H * W / ms / 1e3, "algorithmic_bytes_per_px": bpp,
-                              "hbm_frac": bpp * B * H * W / (ms * 1e-3) / 1e9 / peak,
-                              "note": "photo_scale_kernel<2> (general multi-source kernel)"}))
+            for mf in (True, False):
+                old = ops.MULTISOURCE
+                ops.MULTISOURCE = mf
+                try:
+                    ms = timed(step, args.steps, args.warmup)
+                finally:
+                    ops.MULTISOURCE = old
+                print(json.dumps({"workload": "photometric objective fwd+bwd, %d sources %s + pose gradients (%s)"
+                                              % (len(fids) - 1, list(fids[1:]), label), "B": B, "H": H, "W": W,
+                                  "ms_per_step": ms, "mpix_per_s": B * H * W / ms / 1e3, "algorithmic_bytes_per_px": bpp,
+                                  "hbm_frac": bpp * B * H * W / (ms * 1e-3) / 1e9 / peak,
+                                  "note": "photo_mf_kernel: all sources and scales in one launch (multi-source tile kernel)"
+                                          if mf else "photo_scale_kernel<F> per scale (general multi-source kernel)"}))
             del pb, disps, Ts
 
     if "costvol" in want:

@@ -60,6 +60,11 @@ SIGNATURES = {
     "dmh_photo_multiscale": (_i, [_f, _f, _f, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), _f, _f, _f,
                                   C.POINTER(C.c_void_p), _i, _i, _i, _fl, _fl, _fl, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _st]),
+    "dmh_photo_multisource_workspace_floats": (_ll, [_i]),
+    "dmh_photo_multisource": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _i, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), _f, _f, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), _i, _i, _i, _fl, _fl, _fl, _f, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _st]),
     "dmh_selftest_reciprocals": (_i, [_f, C.c_uint, _st]),
     "dmh_photo_scale_dh": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _f, _f,
                                 _f, _i, _i, _i, _fl, _fl, _i, _f, _f, _f, _f, _f, _st]),

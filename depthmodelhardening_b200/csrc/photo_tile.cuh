@@ -328,56 +328,6 @@ __device__ __forceinline__ float phase_b(const P& p, const TileSmem& sm, int tid
     return loss_local;
 }
 
-// Forward-only twin of phase B (multi-source cascade, photo_ms2.cu): the reprojection loss rp of this thread's 5 ring
-// pixels from the same sliding windows, the same operations in the same order as phase_b -- bit-identical values --
-// without the decision, the coefficients or any store.
-__device__ __forceinline__ void phase_b_values(const TileSmem& sm, int tid, float (&rp_out)[FT_ROWS]) {
-    const int bc = tid % FT_R1, bstrip = tid / FT_R1;
-    const float* tgt = sm.tgt;
-    const float* pred = sm.pred;
-#pragma unroll
-    for (int k = 0; k < FT_ROWS; ++k) rp_out[k] = 0.0f;
-    if (tid < FT_R1 * FT_STRIPS) {
-        const int r0 = bstrip * FT_ROWS;
-        Row5T<float2> histP[2];
-        Row5T<float> histS[2];
-        float2 cenxP, cenyP;
-        float cenxS, cenyS;
-#pragma unroll
-        for (int rr = 0; rr < FT_ROWS + 2; ++rr) {
-            const int r2 = min(r0 + rr, FT_R2 - 1);
-            const float* xs = pred + r2 * FT_R2 + bc;
-            const float* ys = tgt + r2 * FT_TP + bc + FT_TO;
-            const float2 xa = make_float2(xs[0], xs[FT_N2]), xb = make_float2(xs[1], xs[FT_N2 + 1]),
-                         xc = make_float2(xs[2], xs[FT_N2 + 2]);
-            const float2 ya = make_float2(ys[0], ys[FT_NT]), yb = make_float2(ys[1], ys[FT_NT + 1]),
-                         yc = make_float2(ys[2], ys[FT_NT + 2]);
-            const Row5T<float2> curP = row5(xa, xb, xc, ya, yb, yc);
-            const float* x2 = xs + 2 * FT_N2;
-            const float* y2 = ys + 2 * FT_NT;
-            const float x2m = x2[1], y2m = y2[1];
-            const Row5T<float> curS = row5(x2[0], x2m, x2[2], y2[0], y2m, y2[2]);
-            if (rr >= 2) {
-                float l1 = fabsf(cenyP.x - cenxP.x);
-                l1 += fabsf(cenyP.y - cenxP.y);
-                l1 += fabsf(cenyS - cenxS);
-                const SsimStatsT<float2> stP = ssim_stats_rows_t(histP[0], histP[1], curP);
-                const SsimStatsT<float> stS = ssim_stats_rows_t(histS[0], histS[1], curS);
-                float2 passP, rP, nrP;
-                const float2 vP = ssim_value_t(stP, passP, rP, nrP);
-                float passS, rS, nrS;
-                const float vS = ssim_value_t(stS, passS, rS, nrS);
-                const float ss = (vP.x + vP.y) + vS;
-                l1 *= (1.0f / 3.0f);
-                rp_out[rr - 2] = fmaf(0.85f, ss * (1.0f / 3.0f), 0.15f * l1);
-            }
-            histP[0] = histP[1]; histP[1] = curP;
-            histS[0] = histS[1]; histS[1] = curS;
-            cenxP = xb; cenyP = yb; cenxS = x2m; cenyS = y2m;
-        }
-    }
-}
-
 // ---- phase C of the tile kernels: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp).
 // `tid` < 256 owns column tid%32, rows 4*(tid/32)+k of the tile; D = d(pred_ch)/d(disp) of those 4 pixels.
 // DH: the proxy loss of the depth hints, log(|hint - depth| + 1) * valid where the hint won (bit 1 of the gate byte),
@@ -385,7 +335,7 @@ __device__ __forceinline__ void phase_b_values(const TileSmem& sm, int tid, floa
 template <bool DH, bool UP, class P>
 __device__ __forceinline__ void phase_c(const P& p, const TileSmem& sm, int tid, int b, int x0, int y0,
                                         const float (&D)[4][3], float (&acc)[4], float (*gp_out)[3] = nullptr,
-                                        float* g_acc = nullptr) {
+                                        float* g_acc = nullptr, const float (*xv_in)[3] = nullptr) {
     const int H = p.H, W = p.W, N = H * W;
     const float w_l1 = 0.15f / 3.0f;
     const int oc = tid & 31, os = tid >> 5;
@@ -453,8 +403,10 @@ __device__ __forceinline__ void phase_c(const P& p, const TileSmem& sm, int tid,
                 const float2 scP = vfma(wu2, hprev[0][2], vfma(wd2, hc[2], hprev[1][2]));
                 const float2 sab2 = vfma(wu2, hprev[0][3], vfma(wd2, hc[3], hprev[1][3]));
                 const float scS = fmaf(wu, hprevC[0], fmaf(wd, hcC, hprevC[1]));
-                const float2 xvP = make_float2(pred[i2], pred[FT_N2 + i2]), yvP = make_float2(tgt[it], tgt[FT_NT + it]);
-                const float xvS = pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
+                // (multi-source kernel: the warped values of an earlier source come back from its scratch, xv_in)
+                const float2 xvP = xv_in ? make_float2(xv_in[k][0], xv_in[k][1]) : make_float2(pred[i2], pred[FT_N2 + i2]);
+                const float2 yvP = make_float2(tgt[it], tgt[FT_NT + it]);
+                const float xvS = xv_in ? xv_in[k][2] : pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
                 const float2 dP = vsub(xvP, yvP);
                 const float dS = xvS - yvS;
                 const float2 sgP = make_float2(dP.x > 0.f ? gl1 : (dP.x < 0.f ? -gl1 : 0.f),
@@ -465,8 +417,9 @@ __device__ __forceinline__ void phase_c(const P& p, const TileSmem& sm, int tid,
                 float g = gpP.x * D[k][0];
                 g = fmaf(gpP.y, D[k][1], g);
                 g = fmaf(gpS, D[k][2], g);
-                // multi-source cascade: d(loss)/d(pred) of this source for the pose-gradient epilogue (gp_out), and the
-                // disparity gradient accumulated over the sources in registers (g_acc) instead of stored per source
+                // multi-source kernel (photo_mf.cu): d(loss)/d(pred) of this source for the pose-gradient epilogue
+                // (gp_out), and the disparity gradient accumulated over the sources in registers (g_acc) instead of
+                // stored per source
                 if (gp_out) { gp_out[k][0] = gpP.x; gp_out[k][1] = gpP.y; gp_out[k][2] = gpS; }
                 if (g_acc) g_acc[k] += g;
                 else if (py < H && px < W) gout[py * W] = g;

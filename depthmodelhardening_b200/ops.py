@@ -443,6 +443,9 @@ PIPELINED = _os.environ.get("DMH_SPLIT", "0") == "2"
 # all scales of the single-source objective in one launch (csrc/photo_ms.cu, bit-identical to the per-scale launches);
 # DMH_MULTISCALE=0 keeps one launch per scale
 MULTISCALE = _os.environ.get("DMH_MULTISCALE", "1") != "0"
+# several source frames and / or pose gradients: all sources and all scales in one launch of the tile kernel
+# (csrc/photo_mf.cu); DMH_MULTISOURCE=0 keeps the general per-scale kernel (csrc/photo_objective.cu)
+MULTISOURCE = _os.environ.get("DMH_MULTISOURCE", "1") != "0"
 
 
 def _side_stream(dev, which=0):
@@ -496,9 +499,19 @@ class _Objective(torch.autograd.Function):
             bf16_frames = False                             # general kernels: widen first
             target = colors[0] = f32c(target)
             srcs = [f32c(srcs[0])]
-        ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32) if automask else None
+        # mono / mono+stereo / multi-frame (or one source with pose gradients): every source is packed and the
+        # tile kernel walks sources and scales in one launch
+        multisrc = (MULTISOURCE and not packed and not no_ssim and not (flags & (FLAG_AVG_REPROJECTION | FLAG_INPUT_IS_DEPTH))
+                    and 1 <= n_src <= 4 and S <= 4 and W % 4 == 0 and H * W < (1 << 27) and target.data_ptr() % 16 == 0)
+        ident = torch.empty(B, n_src, H, W, device=dev, dtype=torch.float32) if (automask and not multisrc) else None
         src_arr = ptr_array(srcs) if not bf16_frames else None
-        if packed:
+        if multisrc:
+            src_pks = [torch.empty(B, H, W, 4, device=dev, dtype=torch.float32) for _ in range(n_src)]
+            idents = [torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if automask else None for _ in range(n_src)]
+            for f in range(n_src):
+                check(lib.dmh_identity_loss_pack(ptr(target), ptr(srcs[f]), B, H, W, 0, ptr(idents[f]), ptr(src_pks[f]),
+                                                 stream()), "identity_loss_pack")
+        elif packed:
             src_pk = torch.empty(B, H, W, 4, device=dev, dtype=torch.float32)
             if bf16_frames:
                 tgt32 = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
@@ -537,6 +550,23 @@ class _Objective(torch.autograd.Function):
         # tail of one launch (10240 CTAs = 23.06 waves of 444) overlaps the head of the next
         multiscale = (packed and MULTISCALE and not split and S <= 4 and W % 4 == 0 and target.data_ptr() % 16 == 0
                       and H * W < (1 << 27))
+        if multisrc:
+            tiles32 = ((H + 31) // 32) * ((W + 31) // 32)
+            for s in range(S):
+                parts.append(torch.empty(B * tiles, device=dev, dtype=torch.float32))
+                G.append(torch.empty(B, 1, H, W, device=dev, dtype=torch.float32))
+                gPs.append(torch.empty(n_src, B, tiles32, 12, device=dev, dtype=torch.float32) if need_T else None)
+                sels.append(torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None)
+            mf_ws = torch.empty(lib.dmh_photo_multisource_workspace_floats(n_src), device=dev, dtype=torch.float32)
+            dh_ = (_C.c_int * S)(*[d.shape[2] for d in disps])
+            dw_ = (_C.c_int * S)(*[d.shape[3] for d in disps])
+            with _timed("photo_mf"):
+                check(lib.dmh_photo_multisource(ptr(target), ptr_array(src_pks), ptr_array(Ts), n_src, S, ptr_array(disps),
+                                                dh_, dw_, ptr(k), ptr(ik), ptr_array(idents) if automask else None,
+                                                ptr_array(noises) if has_noise else None, B, H, W, min_depth, max_depth,
+                                                inv_den, ptr(mf_ws), ptr_array(parts), ptr_array(G),
+                                                ptr_array(gPs) if need_T else None,
+                                                ptr_array(sels) if want_sel else None, stream()), "photo_multisource")
         if multiscale:
             # ONE launch for all scales (csrc/photo_ms.cu): the scale loop of generate_images_pred / compute_losses
             # runs inside the kernel; same bits as the per-scale launches below
@@ -554,7 +584,7 @@ class _Objective(torch.autograd.Function):
                                                ptr_array(sels) if want_sel else None, stream()), "photo_multiscale")
         alt = _side_stream(dev, 1)
         alt.wait_stream(cur)
-        for s in range(S if not multiscale else 0):
+        for s in range(S if not (multiscale or multisrc) else 0):
             d = disps[s]
             h, w = d.shape[2], d.shape[3]
             part = torch.empty(B * tiles, device=dev, dtype=torch.float32)

@@ -204,6 +204,28 @@ int dmh_photo_multiscale(const float* target, const float* src_packed, const flo
                          float min_depth, float max_depth, float grad_scale, float* const* loss_partial_host,
                          float* const* grad_disp_host, uint8_t* const* sel_host, dmh_stream_t stream);
 
+/* The objective with SEVERAL source frames and / or pose gradients, ALL scales, in one launch
+ * (DepthNetworks/monodepth2/trainer.py:476-523 -- every frame id of every scale is warped -- and :589-660 --
+ * torch.cat([identity losses + noise, reprojection losses]) -> torch.min, the first minimum in cat order wins --;
+ * pose branch: Project3D's T, layers.py:182-198).  The tile kernel of dmh_photo_multiscale for F <= 4 sources:
+ * min-reprojection, SSIM on, disparity input (avg_reprojection / no_ssim / depth input / depth hints stay with
+ * dmh_photo_scale).  src_packed_host[f] = (B,H,W,4) copy of source f and ident_host[f] = its (B,1,H,W) identity loss,
+ * both from dmh_identity_loss_pack (ident_host NULL or all NULL: automask off); noise_host[s] (B,F,H,W), the
+ * reference's layout, or NULL; workspace: dmh_photo_multisource_workspace_floats(F) floats, 16-byte aligned, contents
+ * irrelevant before and after (per-CTA scratch that lives in L2).  Outputs per scale: loss_partial_host[s]
+ * (B*dmh_photo_tiles floats; the first B*ceil(H/32)*ceil(W/32) are written, the rest zeroed), grad_disp_host[s]
+ * (B,1,H,W) = grad_scale * d(sum loss)/d(up-sampled disparity), grad_P_partial_host (nullable) /
+ * grad_P_partial_host[s] (F, B, ceil(H/32)*ceil(W/32), 12) = grad_scale * per-tile d(sum loss)/d((K@T)[:3,:]),
+ * sel_host (nullable) / sel_host[s] (B,H,W) argmin in cat order.  With F == 1 and no pose gradient the results are
+ * bit-identical to dmh_photo_multiscale.  Returns DMH_ERR_UNSUPPORTED when the frames cannot be staged by TMA.    */
+long long dmh_photo_multisource_workspace_floats(int F);
+int dmh_photo_multisource(const float* target, const float* const* src_packed_host, const float* const* T_host, int F,
+                          int S, const float* const* disp_host, const int* disp_h, const int* disp_w, const float* K,
+                          const float* inv_K, const float* const* ident_host, const float* const* noise_host, int B,
+                          int H, int W, float min_depth, float max_depth, float grad_scale, float* workspace,
+                          float* const* loss_partial_host, float* const* grad_disp_host,
+                          float* const* grad_P_partial_host, uint8_t* const* sel_host, dmh_stream_t stream);
+
 /* Test hook of dmh_photo_multiscale's branch-free IEEE reciprocals (the instruction sequence of the hardware fast
  * path of 1/x and a/z, valid for operands in [2^-60, 2^60]; operands outside raise a per-tile flag and take the
  * generic division): counts the mismatches against __frcp_rn over EVERY float of that range and against

@@ -84,7 +84,7 @@ def test_trainer_dropins_executed_vs_reference_golden(dev, name, materialise):
     for s in pb.scales:
         assert_close(losses["loss/%d" % s], g["loss_%d" % s], TOL, "loss/%d" % s)
         assert_grad_close(disps[s].grad, g["grad_disp_%d" % s], g64[s], TOL, "grad_disp_%d" % s,
-                          outlier_frac=5e-3 if name == "stereo_iid" else 2e-3)
+                          outlier_frac=5e-3 if name == "stereo_iid" else (4e-3 if name == "mono_small" else 2e-3))
     assert_close(outputs[("depth", 0, 0)], g["depth_0"], TOL, "depth_0")
     if materialise:
         for f in pb.frame_ids[1:]:
