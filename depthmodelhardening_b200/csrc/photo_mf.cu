@@ -326,10 +326,34 @@ __device__ __forceinline__ void pose_epilogue(const MfParams& p, const float* ca
             acc[a * 4 + 3] += dp[a];
         }
     }
+    // warp reduction of the 12 sums as a reduce-scatter: every step halves the number of values a lane carries
+    // (12 -> 6 -> 3 -> 2 -> 1: 13 shuffles instead of 60); lane L ends with the warp total of value vi(L)
+    {
+        const int lane = tid & 31;
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+        float v6[6], v3[3], v2[2];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        const float w = warp_sum(acc[i]);
-        if ((tid & 31) == 0) red2[(tid >> 5) * 12 + i] = w;
+        for (int i = 0; i < 6; ++i) {
+            const float keep = b4 ? acc[6 + i] : acc[i], send = b4 ? acc[i] : acc[6 + i];
+            v6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float keep = b3 ? v6[3 + i] : v6[i], send = b3 ? v6[i] : v6[3 + i];
+            v3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {   // 3 values padded to 4: (v3[0], v3[1]) | (v3[2], 0)
+            const float k0 = b2 ? v3[2] : v3[0], s0 = b2 ? v3[0] : v3[2];
+            const float k1 = b2 ? 0.0f : v3[1], s1 = b2 ? v3[1] : 0.0f;
+            v2[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+            v2[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+        }
+        const float k = b1 ? v2[1] : v2[0], sd = b1 ? v2[0] : v2[1];
+        float v1 = k + __shfl_xor_sync(0xffffffffu, sd, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        // index of the value this lane holds: 6*b4 + 3*b3 + (b2 ? 2 : b1); the slot (b2 && b1) is the zero padding
+        const int vi = (b4 ? 6 : 0) + (b3 ? 3 : 0) + (b2 ? 2 : (b1 ? 1 : 0));
+        if (!(lane & 1) && !(b2 && b1)) red2[(tid >> 5) * 12 + vi] = v1;
     }
     __syncthreads();
     if (tid < 12) {
@@ -543,15 +567,49 @@ photo_mf_kernel(const MfParams p, const __grid_constant__ CUtensorMap tgt_map) {
         // ---- pass 2: the last source from shared memory / registers, the earlier ones from the scratch
         float g_acc[4] = {0.f, 0.f, 0.f, 0.f};
         float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            const int f = F - 1;
+            unsigned gm = 0u;
+#pragma unroll
+            for (int k = 0; k < FT_ROWS; ++k)
+                gm |= (((winbits >> k) & 1u) && ((idx_r >> (2 * k)) & 3u) == (unsigned)f) ? (1u << k) : 0u;
+            // barrier: the planes of the last source are complete
+            const int any = __syncthreads_or(gm != 0u);
+            int tidC = threadIdx.x, bC = geo[0], x0C = geo[1], y0C = geo[2];
+            asm volatile("" : "+r"(tidC), "+r"(bC), "+r"(x0C), "+r"(y0C));
+            float* gp_dst = nullptr;
+            if (POSE && p.sc[s].grad_P) {
+                const int blk = (y0C / FT_T) * p.gx + x0C / FT_T;
+                gp_dst = p.sc[s].grad_P + (((size_t)f * p.B + bC) * per_img + blk) * 12;
+            }
+            if (any) {
+                float gp[4][3];
+                phase_c<false, false>(v, sm, tidC, bC, x0C, y0C, D, acc4, POSE ? gp : nullptr, g_acc);
+                if (POSE && gp_dst)
+                    pose_epilogue(p, cams + f * 24, scr_of(scr_cta, f, tidC).aux, gp, tidC, bC, x0C, y0C, red2, gp_dst);
+            } else if (gp_dst && tidC < 12) gp_dst[tidC] = 0.f;     // wins nowhere in the tile: no gradient through it
+        }
 #pragma unroll 1
-        for (int f = F - 1; f >= 0; --f) {
-            const bool last = f == F - 1;
+        for (int f = F - 2; f >= 0; --f) {
             const Scr scr = scr_of(scr_cta, f, threadIdx.x);
             unsigned gm = 0u;
 #pragma unroll
             for (int k = 0; k < FT_ROWS; ++k)
                 gm |= (((winbits >> k) & 1u) && ((idx_r >> (2 * k)) & 3u) == (unsigned)f) ? (1u << k) : 0u;
-            // barrier: the planes of the last source are complete / phase C of the previous source is done with them
+            // the parked coefficients / factors are requested BEFORE the barrier (they are this thread's own data) and
+            // consumed after it
+            float4 qa[FT_ROWS], qc[FT_ROWS], a0[4], a1[4];
+            float qe[FT_ROWS];
+#pragma unroll
+            for (int k = 0; k < FT_ROWS; ++k) {
+                qa[k] = ld4(scr.q, k * FT_THREADS); qc[k] = ld4(scr.q, (FT_ROWS + k) * FT_THREADS);
+                qe[k] = scr.q3[k * FT_THREADS];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a0[k] = ld4(scr.aux, (k * 4 + 0) * FT_THREADS); a1[k] = ld4(scr.aux, (k * 4 + 1) * FT_THREADS);
+            }
+            // barrier: phase C of the previous source is done with the planes
             const int any = __syncthreads_or(gm != 0u);
             int tidC = threadIdx.x, bC = geo[0], x0C = geo[1], y0C = geo[2];
             asm volatile("" : "+r"(tidC), "+r"(bC), "+r"(x0C), "+r"(y0C));
@@ -564,38 +622,31 @@ photo_mf_kernel(const MfParams p, const __grid_constant__ CUtensorMap tgt_map) {
                 if (gp_dst && tidC < 12) gp_dst[tidC] = 0.f;
                 continue;
             }
-            float gp[4][3];
-            if (last) {
-                phase_c<false, false>(v, sm, tidC, bC, x0C, y0C, D, acc4, POSE ? gp : nullptr, g_acc);
-            } else {
-                const int bc = tidC % FT_R1, bstrip = tidC / FT_R1;
-                if (tidC < FT_R1 * FT_STRIPS) {
+            const int bc = tidC % FT_R1, bstrip = tidC / FT_R1;
+            if (tidC < FT_R1 * FT_STRIPS) {
 #pragma unroll
-                    for (int k = 0; k < FT_ROWS; ++k) {
-                        const int qr = bstrip * FT_ROWS + k;
-                        if (qr < FT_R1) {
-                            const bool w = (gm >> k) & 1u;
-                            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float4 a = ld4(scr.q, k * FT_THREADS), c = ld4(scr.q, (FT_ROWS + k) * FT_THREADS);
-                            const float e = scr.q3[k * FT_THREADS];
-                            const int qi = qr * FT_R1 + bc;
-                            coefQ1[qi] = w ? a : z4;
-                            coefQ2[qi] = w ? c : z4;
-                            coefQ3[qi] = w ? e : 0.f;
-                            gate[qi] = (uint8_t)(w ? 1 : 0);
-                        }
+                for (int k = 0; k < FT_ROWS; ++k) {
+                    const int qr = bstrip * FT_ROWS + k;
+                    if (qr < FT_R1) {
+                        const bool w = (gm >> k) & 1u;
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int qi = qr * FT_R1 + bc;
+                        coefQ1[qi] = w ? qa[k] : z4;
+                        coefQ2[qi] = w ? qc[k] : z4;
+                        coefQ3[qi] = w ? qe[k] : 0.f;
+                        gate[qi] = (uint8_t)(w ? 1 : 0);
                     }
                 }
-                float Dl[4][3], xv[4][3];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 a = ld4(scr.aux, (k * 4 + 0) * FT_THREADS), c = ld4(scr.aux, (k * 4 + 1) * FT_THREADS);
-                    Dl[k][0] = a.x; Dl[k][1] = a.y; Dl[k][2] = a.z;
-                    xv[k][0] = c.x; xv[k][1] = c.y; xv[k][2] = c.z;
-                }
-                __syncthreads();
-                phase_c<false, false>(v, sm, tidC, bC, x0C, y0C, Dl, acc4, POSE ? gp : nullptr, g_acc, xv);
             }
+            float Dl[4][3], xv[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Dl[k][0] = a0[k].x; Dl[k][1] = a0[k].y; Dl[k][2] = a0[k].z;
+                xv[k][0] = a1[k].x; xv[k][1] = a1[k].y; xv[k][2] = a1[k].z;
+            }
+            __syncthreads();
+            float gp[4][3];
+            phase_c<false, false>(v, sm, tidC, bC, x0C, y0C, Dl, acc4, POSE ? gp : nullptr, g_acc, xv);
             if (POSE && gp_dst) pose_epilogue(p, cams + f * 24, scr.aux, gp, tidC, bC, x0C, y0C, red2, gp_dst);
         }
 

@@ -552,10 +552,12 @@ class _Objective(torch.autograd.Function):
                       and H * W < (1 << 27))
         if multisrc:
             tiles32 = ((H + 31) // 32) * ((W + 31) // 32)
+            # one buffer for the pose-gradient partials of every scale: the backward reduces it with one einsum
+            gP_all = torch.empty(S, n_src, B, tiles32, 12, device=dev, dtype=torch.float32) if need_T else None
             for s in range(S):
                 parts.append(torch.empty(B * tiles, device=dev, dtype=torch.float32))
                 G.append(torch.empty(B, 1, H, W, device=dev, dtype=torch.float32))
-                gPs.append(torch.empty(n_src, B, tiles32, 12, device=dev, dtype=torch.float32) if need_T else None)
+                gPs.append(gP_all[s] if need_T else None)
                 sels.append(torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_sel else None)
             mf_ws = torch.empty(lib.dmh_photo_multisource_workspace_floats(n_src), device=dev, dtype=torch.float32)
             dh_ = (_C.c_int * S)(*[d.shape[2] for d in disps])
@@ -622,6 +624,9 @@ class _Objective(torch.autograd.Function):
                                        ptr(fin_ws), ptr(img_scalars), ptr(losses), stream()), "objective_finish")
         ctx.cfg = (S, n_src, B, H, W, tuple(float(x) for x in smooth_w), need_T, [tuple(d.shape) for d in disps],
                    has_noise)
+        if multisrc and need_T:
+            gPs = [gP_all]                                   # (S, F, B, tiles, 12) as ONE saved tensor
+        ctx.gp_stacked = bool(multisrc and need_T)
         ctx.save_for_backward(img_scalars, k, *G, *gN, *[t for t in Ts], *[g for g in gPs if g is not None])
         out_sels = tuple(sels) if want_sel else ()
         for t in out_sels:
@@ -661,7 +666,17 @@ class _Objective(torch.autograd.Function):
             grads_disp.append(gd.view(dshapes[s]))
         cur.wait_stream(alt)
         g_T = [None] * n_src
-        if need_T:
+        if need_T and ctx.gp_stacked:
+            # multi-source kernel: sum over tiles and weighted sum over scales in one contraction, then the 4x4
+            # algebra of all sources in one batched matmul
+            u = (gt[0] / S if gt is not None else torch.zeros((), device=dev)) + \
+                (gs if gs is not None else torch.zeros(S, device=dev))
+            acc = torch.einsum("s,sfbtk->fbk", u.expand(S).to(torch.float32), gPs[0]).view(n_src, B, 3, 4)
+            gT_all = torch.matmul(k[:, :3, :].transpose(1, 2).unsqueeze(0), acc)        # (F,B,4,4)
+            for f in range(n_src):
+                if ctx.needs_input_grad[base + f]:
+                    g_T[f] = gT_all[f]
+        elif need_T:
             u = [(gt[0] / S if gt is not None else 0.0) + (gs[s] if gs is not None else 0.0) for s in range(S)]
             for f in range(n_src):
                 if ctx.needs_input_grad[base + f]:
