@@ -167,6 +167,13 @@ class Stage1:
         self.world = world
         self.attack = attack
         self.gbuf = None
+        # the step's one collective: one kernel over NVLink peer memory (dist.PeerReducer, csrc/peer_reduce.cu) when
+        # symmetric memory is available; DMH_PEER_REDUCE=0 (or no peer access) keeps the NCCL all-reduce + scaling
+        self.peer = None
+        if world > 1 and os.environ.get("DMH_PEER_REDUCE", "1") != "0":
+            from depthmodelhardening_b200 import dist as D
+            if D.PeerReducer.available():
+                self.peer = D.PeerReducer(self.adv.numel() + 1, device)
         if attack == "l0":      # M2/trainer.py:216-218: adam_lr 0.5, mask_wt 0.06, l0_thresh 0.1
             self.l0 = patch_ops.L0State(self.g.obj, self.g.pattern_pos, self.g.pattern_neg, lr=0.5, betas=(0.5, 0.9))
             self.first = True
@@ -177,7 +184,18 @@ class Stage1:
         if self.attack == "l0":
             self.adv = self.l0.compose_count(first=self.first)
             self.first = False
-        if self.world > 1:
+        if self.peer is not None:
+            # the ONE collective of the step, without NCCL: the backward kernel accumulates into the rank's symmetric
+            # buffer, one kernel sums all ranks' buffers over NVLink in rank order, averages, and (L-inf) updates
+            adv_scene, mask_out, _ = ops.apply_patch_fwd_bwd(self.adv, g.mask, g.scenes, self.coeffs, g.upstream,
+                                                             grad_out=self.peer.buffer)
+            if self.attack != "l0":
+                new_adv = torch.empty_like(self.adv)
+                self.peer.allreduce(average=True, linf=(self.adv, g.obj, 0.02, 0.1, new_adv))
+                self.adv = new_adv
+                return adv_scene
+            grad_patch = self.peer.allreduce(average=True)[:self.adv.numel()].view_as(self.adv)
+        elif self.world > 1:
             # the ONE collective of the step: the backward kernel writes the patch gradient straight into the
             # all-reduce buffer (the scalar attack loss rides in its last element); all-reduce in place
             if self.gbuf is None:
@@ -267,9 +285,23 @@ def measure_strong(args, rank, world, device, global_batch):
     except Exception as exc:
         out["two_stream_error"] = "%s: %s" % (type(exc).__name__, exc)
     out.update({"ms_per_step": ms_graph, "value": global_batch * H * W / (ms_graph * 1e-3) / 1e6,
-                "note": "ms_per_step / value: CUDA-graph replay of the whole step (stage 1, NCCL all-reduce of the "
+                "collective": "dmh_peer_allreduce (one kernel over NVLink peer memory)" if s1.peer is not None
+                              else ("nccl all_reduce + div_" if world > 1 else "none"),
+                "note": "ms_per_step / value: CUDA-graph replay of the whole step (stage 1, the all-reduce of the "
                         "patch gradient, stage 2 fwd+bwd) captured once; *_eager: the same step launched from Python. "
                         "The L0 Adam bias-correction step index is frozen in the replay (timing only)."})
+    if world > 1:
+        # the collective alone, both forms, back to back on this box (device time, max over ranks)
+        n = s1.adv.numel() + 1
+        buf = torch.zeros(n, device=device)
+
+        def nccl():
+            torch.distributed.all_reduce(buf)
+            buf.div_(world)
+        us = {"nccl_all_reduce_plus_div": 1e3 * timed_loop(nccl, 200, 20, world)}
+        if s1.peer is not None:
+            us["peer_memory_kernel"] = 1e3 * timed_loop(lambda: s1.peer.allreduce(average=True), 200, 20, world)
+        out["allreduce_us"] = us
     return out
 
 

@@ -66,6 +66,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_void_p), _i, _i, _i, _fl, _fl, _fl, _f, C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _st]),
     "dmh_selftest_reciprocals": (_i, [_f, C.c_uint, _st]),
+    "dmh_peer_allreduce": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _i, _ll, _fl, _f, _f, _f, _f, _ll, _fl, _fl,
+                                _f, _st]),
     "dmh_photo_scale_dh": (_i, [_f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _f, _i, _i, _f, _f, _f, _f, _f, _f,
                                 _f, _i, _i, _i, _fl, _fl, _i, _f, _f, _f, _f, _f, _st]),
     "dmh_smooth_fused_workspace_floats": (_ll, [_i, _i, _i]),

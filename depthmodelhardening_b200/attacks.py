@@ -55,6 +55,7 @@ class Attack(object):
         """Opt in to the shared-patch collectives; every rank of `group` must run the attack in
         lock-step with the same `steps`."""
         self.sync_group = group
+        self._peer = None            # dist.PeerReducer, built at the first synchronised gradient (its size is known then)
         return self
 
     def forward(self, *input):
@@ -86,8 +87,18 @@ def _sync_patch_grad(attack, grad):
     group = getattr(attack, "sync_group", None)
     if group is None:
         return grad
+    import os
     from . import dist as _dist
-    g, _ = _dist.allreduce_patch_grad(grad, (), average=True, group=_dist.resolve_group(group))
+    grp = _dist.resolve_group(group)
+    # on NVLink-connected GPUs: one kernel over peer memory (csrc/peer_reduce.cu) instead of NCCL + a scaling launch;
+    # same value on every rank (rank-order sum), so the patches stay bit-identical.  DMH_PEER_REDUCE=0: NCCL.
+    if grad.is_cuda and os.environ.get("DMH_PEER_REDUCE", "1") != "0" and _dist.PeerReducer.available(grp):
+        peer = getattr(attack, "_peer", None)
+        if peer is None or peer.n != grad.numel():
+            peer = attack._peer = _dist.PeerReducer(grad.numel(), grad.device, grp)
+        peer.buffer.copy_(grad.reshape(-1))
+        return peer.allreduce(average=True).view_as(grad).clone()
+    g, _ = _dist.allreduce_patch_grad(grad, (), average=True, group=grp)
     return g
 
 

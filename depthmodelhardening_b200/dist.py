@@ -93,3 +93,69 @@ def allreduce_loss_sums(sums: torch.Tensor) -> torch.Tensor:
     if w > 1:
         dist.all_reduce(sums)
     return sums
+
+
+class PeerReducer:
+    """The all-reduce of the shared patch gradient as ONE kernel over NVLink peer memory (csrc/peer_reduce.cu,
+    dmh_peer_allreduce) instead of an NCCL call + a scaling launch: every rank's backward kernel accumulates into
+    `self.buffer` -- a symmetric allocation mapped into every process (torch.distributed._symmetric_memory is the
+    plumbing: CUDA VMM handles exchanged once at construction) --, `allreduce()` sums the ranks' buffers in rank order
+    (the same bits on every rank: the update that follows keeps the universal patch bit-identical), scales by 1/world
+    and, for the L-inf attack, applies the PGD update in the same launch.  CUDA-graph capturable (the step counter
+    lives on the device).  Construct it on every rank of `group` (collective: rendezvous + barrier).
+
+    `PeerReducer.available()` is False without CUDA peer access / symmetric memory (gloo, a single GPU, other
+    backends): callers then keep `allreduce_patch_grad` (NCCL)."""
+
+    FLAG_WORDS = 64          # 2 * world <= 32 used; one 256-byte block behind the gradient
+
+    @staticmethod
+    def available(group=None) -> bool:
+        if not (dist.is_available() and dist.is_initialized() and torch.cuda.is_available()):
+            return False
+        if dist.get_backend(group) != "nccl" or dist.get_world_size(group) < 2 or dist.get_world_size(group) > 16:
+            return False
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+        except Exception:
+            return False
+        return True
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = int(numel)
+        self.n_pad = (self.n + 3) // 4 * 4
+        self._alloc = symm.empty(self.n_pad + self.FLAG_WORDS, dtype=torch.float32, device=device)
+        self._hdl = symm.rendezvous(self._alloc, self.group)
+        self._alloc.zero_()
+        self.buffer = self._alloc[:self.n]                       # what the backward kernel accumulates into
+        self.out = torch.zeros(self.n_pad, device=device, dtype=torch.float32)
+        self.state = torch.zeros(2, device=device, dtype=torch.int32)
+        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self._bufs = (C.c_void_p * self.world)(*ptrs)
+        self._flags = (C.c_void_p * self.world)(*[p + 4 * self.n_pad for p in ptrs])
+        self._lib = _lib.load()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)                           # every rank's flags are zero before the first step
+
+    def allreduce(self, average: bool = True, linf=None):
+        """Enqueue the kernel on the current stream.  Returns the reduced gradient (flat, n floats; identical on
+        every rank).  linf = (adv, clean, alpha, eps, adv_out): also apply the L-inf update to the first
+        adv.numel() elements."""
+        from ._lib import check, ptr, stream
+        scale = 1.0 / self.world if average else 1.0
+        if linf is not None:
+            adv, clean, alpha, eps, adv_out = linf
+            check(self._lib.dmh_peer_allreduce(self._bufs, self._flags, self.rank, self.world, self.n, scale, ptr(self.out),
+                                               ptr(self.state), ptr(adv), ptr(clean), adv.numel(), float(alpha), float(eps),
+                                               ptr(adv_out), stream()), "peer_allreduce")
+        else:
+            check(self._lib.dmh_peer_allreduce(self._bufs, self._flags, self.rank, self.world, self.n, scale, ptr(self.out),
+                                               ptr(self.state), None, None, 0, 0.0, 0.0, None, stream()), "peer_allreduce")
+        return self.out[:self.n]

@@ -460,6 +460,24 @@ int dmh_reduce_sum(const float* in, long long n, float scale, int accumulate, fl
  * of the depth-hints objective, DH/trainer.py:699-713) */
 int dmh_reduce_rows(const float* in, int rows, long long n, float scale, float* out, dmh_stream_t stream);
 
+/* -- the ONE collective of stage 1, as one kernel over NVLink peer memory -----------------------
+ * all-reduce(sum) of the shared patch gradient (the scalar attack loss rides in its tail), scaled by `scale`
+ * (1 / world: dist.allreduce_patch_grad's average), optionally fused with the L-inf PGD update that consumes it
+ * (TA/attacks/phy_obj_atk.py:98-100) -- replaces torch.distributed.all_reduce (NCCL) + div_ [+ dmh_pgd_linf_step].
+ * peer_bufs_host[r]  = rank r's n-float gradient buffer AS MAPPED IN THIS PROCESS (a symmetric allocation: CUDA VMM
+ *                      handles exchanged by the host, e.g. torch.distributed._symmetric_memory), 16-byte aligned;
+ * peer_flags_host[r] = rank r's flag block, 2 * world uint32 (zeroed once before the first call), same mapping rule;
+ * state              = 2 uint32 of LOCAL device memory (zeroed once): step counter, CTA arrival counter;
+ * out                = n LOCAL floats: sum over ranks in rank order (the same bits on every rank) * scale;
+ * adv / clean / adv_out (all NULL: no update; else n_update <= n floats each): adv_out = clamp(clean +
+ *                      clamp(adv + alpha * sign(out) - clean, +-eps), 0, 1).
+ * Every rank of the group must enqueue the call for the same step (like a collective).  The kernel synchronises the
+ * ranks through the flag blocks (system-scope release / acquire) at its start and at its end: when it retires, the
+ * rank's buffer may be overwritten by the next step.  The step counter lives on the device: CUDA-graph capturable. */
+int dmh_peer_allreduce(const float* const* peer_bufs_host, unsigned* const* peer_flags_host, int rank, int world,
+                       long long n, float scale, float* out, unsigned* state, const float* adv, const float* clean,
+                       long long n_update, float alpha, float eps, float* adv_out, dmh_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
