@@ -305,6 +305,45 @@ def measure_strong(args, rank, world, device, global_batch):
     return out
 
 
+def measure_multisource(args, device, batch):
+    """Informational (N = 1): the objective of configs[1] read as TRUE mono+stereo (F = 3,
+    frame_ids [0,-1,1,'s'], pose gradients for the temporal frames) and BASELINE configs[4] (two temporal sources,
+    batch 16), each through the multi-source tile kernel (csrc/photo_mf.cu, one launch for all sources and scales)
+    and through the general per-scale kernel it replaces."""
+    from depthmodelhardening_b200 import objective, ops, synth
+    out = {}
+    for key, B_, fids in (("mono_stereo_f3", batch, (0, -1, 1, "s")), ("multi_frame_f2_b16", 16, (0, -1, 1))):
+        pb = synth.photo_batch(batch=B_, height=H, width=W, frame_ids=fids, scales=SCALES, seed=6).to(device)
+        disps = {s_: pb.disp[s_].clone().requires_grad_(True) for s_ in pb.scales}
+        Ts = {k: v.clone().requires_grad_(k != "s") for k, v in pb.T.items()}
+
+        def step():
+            for d in disps.values():
+                d.grad = None
+            for t in Ts.values():
+                t.grad = None
+            losses, _ = objective.photometric_losses(pb.color, disps, pb.K, pb.inv_K, Ts, pb.frame_ids, pb.scales, H, W,
+                                                     noise=pb.noise)
+            losses["loss"].backward()
+        rec = {"per_gpu_batch": B_, "frame_ids": [str(f) for f in fids], "unit": UNIT}
+        for name, flag in (("tile_kernel", True), ("general_kernel", False)):
+            old = ops.MULTISOURCE
+            ops.MULTISOURCE = flag
+            try:
+                ms = timed_loop(step, max(5, args.steps // 2), 3, 1)
+            finally:
+                ops.MULTISOURCE = old
+            rec["ms_per_step_" + name] = ms
+            rec["value_" + name] = B_ * H * W / (ms * 1e-3) / 1e6
+        out[key] = rec
+        del pb, disps, Ts
+        torch.cuda.empty_cache()
+    out["note"] = ("stage 2 only (objective fwd+bwd incl. pose gradients); tile_kernel = dmh_photo_multisource "
+                   "(photo_mf_kernel: all sources and scales in one launch), general_kernel = dmh_photo_scale per scale "
+                   "(photo_scale_kernel<F>, the round-1 path)")
+    return out
+
+
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
 def reference_available():
     """The unmodified reference: /root/reference in the build container, else the copy that build() placed under
@@ -854,6 +893,11 @@ def main():
             line["strong_scaling"] = measure_strong(args, rank, world, device, GLOBAL_BATCH)
         except Exception as exc:
             line["strong_scaling"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if world == 1 and not args.no_strong and s1 is not None:
+        try:
+            line["multisource"] = measure_multisource(args, device, B)
+        except Exception as exc:                            # informational: never take the bench down with it
+            line["multisource"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample_batch or 8, s1 is not None, attack=args.attack)
     if rank == 0 and world == 1 and not args.no_gpu_eager and reference_available():

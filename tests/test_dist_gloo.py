@@ -54,6 +54,9 @@ def _worker(rank, world, port, ret):
         assert abs(float(total) - float(full)) <= 1e-6 * abs(float(full))
         with pytest.raises(ValueError):
             D.shard_range(5)
+        # the peer-memory form of collective 1 needs NCCL ranks on NVLink-connected GPUs: under gloo the callers keep
+        # the all-reduce above (attacks._sync_patch_grad, bench.Stage1 test `PeerReducer.available()` first)
+        assert not D.PeerReducer.available()
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
