@@ -198,3 +198,34 @@ def test_colour_jitter_math_vs_oracle(emu_jitter):
     img = img_keep
     for f in (-0.1, -0.0371, 0.0, 0.05, 0.1, 0.5, -0.5):
         assert np.array_equal(run(3, aux=int(f * 255) & 0xff), E.hue(img, f)), ("hue", f)
+
+
+def test_pose_sum_reduce_scatter_network_host_emulation():
+    """csrc/photo_mf.cu pose_epilogue: 12 per-lane sums are reduced over a warp by a reduce-scatter (12 -> 6 -> 3 -> 2 -> 1
+    values per lane, 13 shuffles) instead of 12 butterflies (60).  The same network emulated on 32 numpy lanes: every
+    one of the 12 totals ends in exactly the lane / index the kernel writes from, and equals the plain sum."""
+    rng = np.random.RandomState(5)
+    acc = rng.randn(32, 12)                     # acc[lane][i]
+    lanes = np.arange(32)
+    xor = lambda v, m: v[lanes ^ m]             # __shfl_xor_sync
+    b4, b3, b2, b1 = [(lanes & m) != 0 for m in (16, 8, 4, 2)]
+    v6 = np.zeros((32, 6))
+    for i in range(6):
+        keep = np.where(b4, acc[:, 6 + i], acc[:, i]); send = np.where(b4, acc[:, i], acc[:, 6 + i])
+        v6[:, i] = keep + xor(send, 16)
+    v3 = np.zeros((32, 3))
+    for i in range(3):
+        keep = np.where(b3, v6[:, 3 + i], v6[:, i]); send = np.where(b3, v6[:, i], v6[:, 3 + i])
+        v3[:, i] = keep + xor(send, 8)
+    k0 = np.where(b2, v3[:, 2], v3[:, 0]); s0 = np.where(b2, v3[:, 0], v3[:, 2])
+    k1 = np.where(b2, 0.0, v3[:, 1]); s1 = np.where(b2, v3[:, 1], 0.0)
+    v2 = np.stack([k0 + xor(s0, 4), k1 + xor(s1, 4)], 1)
+    k = np.where(b1, v2[:, 1], v2[:, 0]); sd = np.where(b1, v2[:, 0], v2[:, 1])
+    v1 = k + xor(sd, 2)
+    v1 = v1 + xor(v1, 1)
+    vi = np.where(b4, 6, 0) + np.where(b3, 3, 0) + np.where(b2, 2, np.where(b1, 1, 0))
+    writers = ((lanes & 1) == 0) & ~(b2 & b1)
+    assert sorted(vi[writers].tolist()) == list(range(12))
+    want = acc.sum(0)
+    for lane in lanes[writers]:
+        assert abs(v1[lane] - want[vi[lane]]) < 1e-12
