@@ -446,6 +446,9 @@ MULTISCALE = _os.environ.get("DMH_MULTISCALE", "1") != "0"
 # several source frames and / or pose gradients: all sources and all scales in one launch of the tile kernel
 # (csrc/photo_mf.cu); DMH_MULTISOURCE=0 keeps the general per-scale kernel (csrc/photo_objective.cu)
 MULTISOURCE = _os.environ.get("DMH_MULTISOURCE", "1") != "0"
+# development switch: the single-source objective through the multi-source kernel's persistent (tile, scale) item loop
+# (same bits as dmh_photo_multiscale; measured slower / faster: DESIGN.md section 7)
+SINGLE_VIA_MF = _os.environ.get("DMH_SINGLE_VIA_MF", "0") == "1"
 
 
 def _side_stream(dev, which=0):
@@ -494,7 +497,7 @@ class _Objective(torch.autograd.Function):
         need_T = any(ctx.needs_input_grad[base + i] for i in range(n_src))
         # single source, no pose gradient: the per-scale kernel gathers from a pixel-packed (B,H,W,4) copy of the
         # source (one 128-bit load per bilinear tap), written once by the identity-loss kernel
-        packed = n_src == 1 and not need_T and not no_ssim and H * W < (1 << 28)
+        packed = n_src == 1 and not need_T and not no_ssim and H * W < (1 << 28) and not (SINGLE_VIA_MF and not bf16_frames)
         if bf16_frames and not (packed and target.data_ptr() % 16 == 0 and srcs[0].data_ptr() % 16 == 0):
             bf16_frames = False                             # general kernels: widen first
             target = colors[0] = f32c(target)
