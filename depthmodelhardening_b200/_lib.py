@@ -19,6 +19,7 @@ _f = C.c_void_p          # device float*
 _i = C.c_int
 _ll = C.c_longlong
 _fl = C.c_float
+_d = C.c_double
 _st = C.c_void_p         # cudaStream_t
 
 # name -> (restype, argtypes); mirrors include/dmh_b200.h one to one
@@ -89,6 +90,9 @@ SIGNATURES = {
     "dmh_patch_apply_bwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _st]),
     "dmh_pgd_linf_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _st]),
     "dmh_apgd_linf_step": (_i, [_f, _f, _f, _f, _ll, _fl, _fl, _fl, _f, _st]),
+    "dmh_tube_light_patch": (_i, [_f, _i, _i, _d, _d, _d, _d, _i, _i, _d, _d, _d, _f, _f, _st]),
+    "dmh_square_linf_candidate": (_i, [_f, _f, _i, _i, _i, _i, _i, _fl, _fl, _fl, _fl, _f, _st]),
+    "dmh_keep_best": (_i, [_f, _f, _f, _f, _f, _ll, _st]),
     "dmh_depth_errors": (_i, [_f, _f, _f, _ll, _fl, _fl, _fl, _fl, _fl, _f, _st]),
     "dmh_pgd_l2_step": (_i, [_f, _f, _f, _ll, _fl, _fl, _fl, _f, _st]),
     "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),

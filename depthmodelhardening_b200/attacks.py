@@ -512,6 +512,248 @@ class Phy_obj_atk_guassian(Attack):
         return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
 
 
+# ----------------------------------------------------------------------------- black-box searches (next-4)
+_LIGHT_Q = np.asarray([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [1, 1, 0, 0], [1, 0, 1, 0],
+                       [1, 0, 0, 1], [0, 1, 1, 0], [0, 1, 0, 1], [0, 0, 1, 1]])          # phy_obj_atk_light.py:75-86
+_LIGHT_LO, _LIGHT_HI = [380, 0, 0, 10], [750, 180, 400, 1600]                            # :111
+
+
+def wavelength_to_rgb(wavelength, gamma=0.8):
+    """Colour of a visible wavelength (light_simulation.py:40-86; three python floats per candidate, host side): a
+    band table with the reference's expressions, evaluated in its order."""
+    wl = float(wavelength)
+    bands = (
+        (380, 440, lambda a: (((-(wl - 440) / (440 - 380)) * a) ** gamma, 0.0, (1.0 * a) ** gamma),
+         lambda: 0.3 + 0.7 * (wl - 380) / (440 - 380)),
+        (440, 490, lambda a: (0.0, ((wl - 440) / (490 - 440)) ** gamma, 1.0), None),
+        (490, 510, lambda a: (0.0, 1.0, (-(wl - 510) / (510 - 490)) ** gamma), None),
+        (510, 580, lambda a: (((wl - 510) / (580 - 510)) ** gamma, 1.0, 0.0), None),
+        (580, 645, lambda a: (1.0, (-(wl - 645) / (645 - 580)) ** gamma, 0.0), None),
+        (645, 750, lambda a: ((1.0 * a) ** gamma, 0.0, 0.0), lambda: 0.3 + 0.7 * (750 - wl) / (750 - 645)),
+    )
+    for lo, hi, colour, attenuation in bands:              # first matching band wins (shared end points)
+        if lo <= wl <= hi:
+            return colour(attenuation() if attenuation else None)
+    return (0.0, 0.0, 0.0)
+
+
+class Phy_obj_atk_light(Attack):
+    r"""Drop-in of the reference's tube-light search (torchattacks/attacks/phy_obj_atk_light.py:18-190, candidates by
+    light_simulation.py:132-170): 200 random beams (wavelength, angle, intercept, attenuation), 20 random +-steps each,
+    the candidate with the lowest masked-disparity MSE wins.  Same signature, return 4-tuple and consumption order of
+    `numpy.random` (beam walk) and `random` (placements) as the reference.
+
+    Per candidate the reference fills the 300 x 260 x 3 light field in a Python double loop (~0.1 s), adds it with
+    OpenCV, goes through PIL, uploads the patch, runs 2*Ba perspective warps + composite + two Resizes and reads the
+    cost back to compare it on the host.  Here: ONE launch builds the candidate patch on the device
+    (`dmh_tube_light_patch`, the reference's float64 / 8-bit arithmetic bit for bit), one fused patch-apply launch
+    places it, and the candidate is accepted on the device (`dmh_keep_best`) -- the 8000-candidate loop never waits
+    for the host.  `n_init` / `n_search` (keyword-only EXTENSION) default to the reference's hard-coded 200 / 20."""
+
+    def __init__(self, model, obj_img, obj_mask, eps=1, alpha=0.2, steps=40, random_start=True,
+                 dist_range=list(range(5, 31, 2)), *, n_init=200, n_search=20):
+        super().__init__("PGD", model)
+        self.obj_img = obj_img
+        self.obj_mask = obj_mask
+        self.eps = eps
+        self.steps = steps
+        self.random_start = random_start
+        self._supported_mode = ["default", "targeted"]
+        self._targeted = True
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        self.eps_for_division = 1e-10
+        self.n_init, self.n_search = int(n_init), int(n_search)
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False):
+        import math
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        loss = nn.MSELoss()
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        obj_img_adv = self.obj_img.clone().detach()
+        # ToPILImage on a float tensor (:95): mul(255).byte() -- kept on the device, planar
+        base_u8 = obj_img_adv.squeeze(0).mul(255).byte().contiguous()
+        keeper = patch_ops.BestKeeper(obj_img_adv, init_cost=1e10)
+        cand = torch.empty_like(obj_img_adv, dtype=torch.float32)
+        tr = self.phy_trans_adv
+        params_list = []
+        for _ in range(self.n_init):                                                     # :96-99
+            params_list.append([np.random.randint(380, 750), np.random.randint(0, 180), np.random.randint(0, 400),
+                                np.random.randint(10, 1600)])
+        n_cand = 0
+        with torch.no_grad():
+            for init_v in params_list:
+                for _ in range(self.n_search):
+                    q = _LIGHT_Q[np.random.randint(len(_LIGHT_Q))]
+                    q = q * np.random.randint(1, 20)
+                    for a in (-1, 1):
+                        temp_q = np.clip(init_v + a * q, _LIGHT_LO, _LIGHT_HI)
+                        k = round(math.tan(math.radians(temp_q[1])), 2)
+                        patch_ops.tube_light_patch(base_u8, k, temp_q[2], temp_q[3], wavelength_to_rgb(temp_q[0]),
+                                                   alpha=1.0, out=cand)
+                        z0 = sample(tr.dist_range, batch_size)                           # physicalTrans.py:146-155 order
+                        al = sample(tr.angle_range, batch_size)
+                        adv_scenes, masks = patch_ops.apply_patch(cand, self.obj_mask, scene_imgs, tr._coeffs(z0, al),
+                                                                  self.scene_size)
+                        cost = loss(self.model(adv_scenes) * masks, self.depth_target)
+                        keeper.offer(cost, cand)                                         # if cost < best_cost (:148-150)
+                        n_cand += 1
+            if n_cand == 0 or not bool(keeper.best_cost < 1e10):
+                # the reference ends with best_adv_obj = None here and fails in reset_img
+                raise AttributeError("'NoneType' object has no attribute 'size'")
+            obj_img_adv = keeper.best
+            tr.reset_img(obj_img_adv, self.obj_mask)
+            z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+            alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+            if eval:
+                z0_sample[0] = 7
+                alpha_sample[0] = 0
+            co = tr._coeffs(z0_sample, alpha_sample)
+            adv_scenes, obj_masks_out = patch_ops.apply_patch(obj_img_adv, self.obj_mask, scene_imgs, co, self.scene_size)
+            ben_scenes, _ = patch_ops.apply_patch(self.obj_img, self.obj_mask, scene_imgs, co, self.scene_size)
+        return adv_scenes, ben_scenes, obj_masks_out, obj_img_adv
+
+
+class Phy_obj_atk_Square(Attack):
+    r"""Drop-in of the reference's patch version of the Square attack (torchattacks/attacks/
+    phy_obj_atk_square.py:25-511), L-inf random search.  Mirrored AS THE REFERENCE BEHAVES, including two quirks of
+    its code: every query evaluates the cost of the CURRENT BEST patch, not of the new candidate (`depth_loss(x_best,
+    ...)`, :277), on placements drawn from a fresh `RandomState(seed)` (:118) -- so the cost of a query equals the
+    stored minimum whenever the network is deterministic, the strict `<` of :281 never accepts, and the result is
+    the striped initialisation `clamp(x + eps * sign, 0, 1)` (:242-243); and `margin` is the constant 1 (:123), so no
+    query ever counts as a success.  The L2 branch of the reference reads an undefined name (:327) and raises
+    NameError; so does this class.
+
+    Same constructor, call signature, return 4-tuple, and the same draws from the torch CPU generator (stripes,
+    window position, per-channel signs) and from `random` (final placements).  Per query the reference runs five
+    full-size elementwise launches for the candidate, 2*Ba perspective warps, composite, two Resizes and three host
+    syncs (`nonzero`, the window indices, the verbose test); here: one candidate launch, one fused patch-apply launch
+    and the acceptance on the device (`dmh_keep_best`) -- no sync inside the loop."""
+
+    def __init__(self, model, obj_img, obj_mask, norm="Linf", eps=0.1, n_queries=5000, n_restarts=1, p_init=.8,
+                 loss="margin", resc_schedule=True, seed=0, verbose=False, dist_range=list(range(5, 31, 2))):
+        super().__init__("Square", model)
+        self.obj_img = obj_img
+        self.obj_mask = obj_mask
+        self.norm = norm
+        self.n_queries = n_queries
+        self.eps = eps
+        self.p_init = p_init
+        self.n_restarts = n_restarts
+        self.seed = seed
+        self.verbose = verbose
+        self.loss = loss
+        self.rescale_schedule = resc_schedule
+        self._supported_mode = ["default", "targeted"]
+        self._targeted = True
+        self.depth_target = torch.zeros(1).float().to(self.device)
+        self.scene_size = [320, 1024]
+        self.eps_for_division = 1e-10
+        conf = {"path": _default_calib()}
+        self.phy_trans_adv = PhysicalTrans(self.obj_img.clone(), self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+        self.phy_trans_ben = PhysicalTrans(self.obj_img, self.obj_mask, conf, (1, 3, ori_H, ori_W),
+                                           dist_range=dist_range)
+
+    # -- helpers of the reference, same draws from the torch CPU generator (:161-167)
+    def random_choice(self, shape):
+        return torch.sign(2 * torch.rand(shape) - 1)
+
+    def random_int(self, low=0, high=1, shape=[1]):
+        return (low + (high - low) * torch.rand(shape)).long()
+
+    def p_selection(self, it):
+        """Schedule of the window size (:210-240)."""
+        if self.rescale_schedule:
+            it = int(it / self.n_queries * 10000)
+        for bound, div in ((8000, 512), (6000, 256), (4000, 128), (2000, 64), (1000, 32), (500, 16), (200, 8), (50, 4),
+                           (10, 2)):
+            if it > bound:
+                return self.p_init / div
+        return self.p_init
+
+    def _fixed_placement(self, batch_size):
+        # project(batch_size, rs=np.random.RandomState(self.seed)) (:118): the same placements at every query
+        tr = self.phy_trans_adv
+        rs = np.random.RandomState(self.seed)
+        z0 = rs.choice(tr.dist_range, batch_size, replace=False)
+        al = rs.choice(tr.angle_range, batch_size, replace=False)
+        return tr._coeffs([z0[i] for i in range(batch_size)], [al[i] for i in range(batch_size)])
+
+    def depth_loss(self, x_adv, scene_imgs, coeffs=None):
+        """(:115-126) -> (margin, loss): margin is the reference's constant 1, loss a 1-element tensor."""
+        co = coeffs if coeffs is not None else self._fixed_placement(self.batch_size)
+        adv_scenes, masks = patch_ops.apply_patch(x_adv, self.obj_mask, scene_imgs, co, self.scene_size)
+        loss_indiv = nn.MSELoss()(self.model(adv_scenes) * masks, self.depth_target).unsqueeze(0)
+        return torch.ones(x_adv.shape[0]).to(loss_indiv.device), loss_indiv
+
+    def attack_single_run(self, x, scene_imgs):
+        import math
+        if self.norm != "Linf":
+            # the reference's L2 branch: `margin_and_loss(x_best, y)` with no `y` in scope (:327)
+            raise NameError("name 'y' is not defined")
+        with torch.no_grad():
+            c, h, w = x.shape[1:]
+            n_features = c * h * w
+            x_best = torch.clamp(x + (self.eps * self.random_choice([x.shape[0], c, 1, w])).to(self.device), 0., 1.)
+            co = self._fixed_placement(self.batch_size)
+            _, loss_min = self.depth_loss(x_best, scene_imgs, co)
+            keeper = patch_ops.BestKeeper(x_best, init=x_best)
+            keeper.set_cost(loss_min)
+            x_new = torch.empty_like(x_best)
+            n_queries = torch.ones(x.shape[0]).to(self.device)
+            for i_iter in range(self.n_queries):
+                p = self.p_selection(i_iter)
+                s = max(int(round(math.sqrt(p * n_features / c))), 1)
+                vh = int(self.random_int(0, h - s))
+                vw = int(self.random_int(0, w - s))
+                delta = (2. * self.eps * self.random_choice([c, 1, 1])).reshape(c)
+                patch_ops.square_linf_candidate(keeper.best, x, vh, vw, s, delta.tolist(), self.eps, out=x_new)
+                _, loss = self.depth_loss(keeper.best, scene_imgs, co)         # (sic, :277: the best, not x_new)
+                keeper.offer(loss, x_new)                                      # loss < loss_min ? (:281-297)
+                n_queries += 1.
+            return n_queries, keeper.best
+
+    def perturb(self, scene_imgs):
+        """(:440-511) with its one always-run restart pattern: restart r re-runs the search from the clean patch
+        while `acc` is non-zero -- after the first run it is zero."""
+        assert self.norm in ["Linf", "L2"]
+        assert self.eps is not None
+        assert self.loss in ["ce", "margin"]
+        adv = self.obj_img.clone()
+        for counter in range(self.n_restarts):
+            if counter > 0:
+                break
+            _, adv_curr = self.attack_single_run(self.obj_img[[0]].clone(), scene_imgs)
+            adv[[0]] = adv_curr[[0]].clone()
+        return adv
+
+    def forward(self, images, batch_size, cfg_path=None, eval=False):
+        images = images.detach().to(self.device)
+        scene_imgs = _tile_scenes(images, batch_size)
+        self.batch_size = batch_size
+        self.depth_target = torch.zeros((batch_size, 1, self.scene_size[0], self.scene_size[1])).float().to(self.device)
+        adv_images = self.perturb(scene_imgs)
+        tr = self.phy_trans_adv
+        tr.reset_img(adv_images, self.obj_mask)
+        z0_sample = sample(self.phy_trans_ben.dist_range, batch_size)
+        alpha_sample = sample(self.phy_trans_ben.angle_range, batch_size)
+        if eval:
+            z0_sample[0] = 7
+            alpha_sample[0] = 0
+        with torch.no_grad():
+            co = tr._coeffs(z0_sample, alpha_sample)
+            adv_scenes, obj_masks_out = patch_ops.apply_patch(adv_images, self.obj_mask, scene_imgs, co, self.scene_size)
+            ben_scenes, _ = patch_ops.apply_patch(self.obj_img, self.obj_mask, scene_imgs, co, self.scene_size)
+        return adv_scenes, ben_scenes, obj_masks_out, adv_images
+
+
 class Phy_obj_atk_vanila(Attack):
     r"""Drop-in of the reference's `Phy_obj_atk_vanila` (torchattacks/attacks/phy_obj_atk_vanila.py:18-96): no
     optimisation -- a given object image is placed on the scenes at random (or, with `eval`, fixed first) distance /

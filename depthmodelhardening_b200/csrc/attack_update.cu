@@ -10,10 +10,14 @@
 //   dmh_l0_adam_step      phy_obj_atk_l0.py:130-138 (mask cost gradient + chain through the
 //                         compose clamps + torch.optim.Adam(betas=(0.5,0.9)) update)
 //   dmh_l0_finalize       phy_obj_atk_l0.py:143-150
+//   dmh_tube_light_patch  light_simulation.py:132-170 + phy_obj_atk_light.py:118-122 (one black-box candidate)
+//   dmh_square_linf_candidate  phy_obj_atk_square.py:263-274 (one Square-attack candidate)
+//   dmh_keep_best         phy_obj_atk_light.py:148-150 / phy_obj_atk_square.py:281-297 (accept on the device)
 //   dmh_topk_select       EXTENSION: exact k-th largest by 4-pass radix
 //                         select with warp-aggregated shared-memory histograms
 #include "../../include/dmh_b200.h"
 #include "dmh_common.cuh"
+#include "light_math.cuh"
 
 using namespace dmh;
 
@@ -349,6 +353,59 @@ topk_select_kernel(float* __restrict__ ppos, float* __restrict__ pneg, int C, in
     }
 }
 
+
+// --------------------------------------------------------------------------- black-box candidates (next-4)
+// One candidate of the tube-light search (phy_obj_atk_light.py:109-122): the reference fills the (h, w, 3) light
+// field in a Python double loop (~0.1 s for the 300 x 260 object), adds it to the 8-bit object image with OpenCV and
+// converts back with ToTensor; here one thread per pixel does the same float64 / float32 operations (light_math.cuh)
+// and writes the candidate patch as fp32 (k / 255, IEEE division == ToTensor).  base: planar (3, h, w) bytes.
+__global__ void __launch_bounds__(256)
+tube_light_kernel(const uint8_t* __restrict__ base, int h, int w, TubeLight t, float* __restrict__ patch,
+                  uint8_t* __restrict__ lit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = h * w;
+    if (i >= n) return;
+    const int y = i / w, x = i - y * w;
+    double att = 0.0;
+    const int zone = tube_light_zone(t, x, y, &att);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint8_t v = lit_u8(base[c * n + i], t.ca[c], zone, att);
+        patch[c * n + i] = div_rn((float)v, 255.0f);
+        if (lit) lit[c * n + i] = v;
+    }
+}
+
+// One candidate of the Square attack's L-inf random search (phy_obj_atk_square.py:263-274): the square
+// [vh, vh+s) x [vw, vw+s) of the best patch so far moves by delta[c] = 2 * eps * (+-1) per channel, then the eps-ball
+// around the clean patch and [0, 1] are enforced -- three full-size temporaries and five launches in the reference.
+__global__ void __launch_bounds__(256)
+square_candidate_kernel(const float* __restrict__ x_best, const float* __restrict__ x, int H, int W, int vh, int vw,
+                        int s, float d0, float d1, float d2, float eps, float* __restrict__ x_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = H * W;
+    if (i >= n) return;
+    const int py = i / W, px = i - py * W;
+    const bool in = py >= vh && py < vh + s && px >= vw && px < vw + s;
+    const float d[3] = {d0, d1, d2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        x_new[c * n + i] = square_linf_candidate(x_best[c * n + i], x[c * n + i], in ? d[c] : 0.0f, eps);
+}
+
+// Accepting a candidate without a host round trip: `if cost < best_cost: best_cost, best = cost, candidate`
+// (phy_obj_atk_light.py:148-150; phy_obj_atk_square.py:281-297 with its 0/1 blend) -- every thread reads the
+// previous best cost from `best_in`, thread 0 writes the new one to `best_out` (the caller ping-pongs the two).
+__global__ void __launch_bounds__(256)
+keep_best_kernel(const float* __restrict__ cost, const float* __restrict__ best_in, float* __restrict__ best_out,
+                 const float* __restrict__ cand, float* __restrict__ best, long long n) {
+    const float c = cost[0], b = best_in[0];
+    const bool better = c < b;                          // false for NaN, as in Python
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) best_out[0] = better ? c : b;
+    if (better && i < n) best[i] = cand[i];
+}
+
 }  // namespace
 
 extern "C" {
@@ -368,6 +425,42 @@ int dmh_apgd_linf_step(const float* x_adv, const float* x_adv_old, const float* 
     DMH_LAUNCH(apgd_linf_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(x_adv, x_adv_old, grad, x0, n, step, a,
                                                                                eps, out);
     DMH_CHECK_LAUNCH("dmh_apgd_linf_step");
+    return DMH_OK;
+}
+
+int dmh_tube_light_patch(const uint8_t* base_u8, int h, int w, double k, double b, double norm, double beta,
+                         int full_end, int light_end, double ca0, double ca1, double ca2, float* patch, uint8_t* lit_u8,
+                         dmh_stream_t stream) {
+    DMH_REQUIRE(base_u8 && patch, "dmh_tube_light_patch: null pointer");
+    DMH_REQUIRE(h > 0 && w > 0 && (long long)h * w < (1ll << 30), "dmh_tube_light_patch: bad shape %d x %d", h, w);
+    DMH_REQUIRE(norm >= 1.0 && full_end >= 0 && light_end >= full_end, "dmh_tube_light_patch: bad beam scalars");
+    TubeLight t;
+    t.k = k; t.b = b; t.norm = norm; t.beta = beta; t.full_end = (double)full_end; t.light_end = (double)light_end;
+    t.ca[0] = ca0; t.ca[1] = ca1; t.ca[2] = ca2;
+    DMH_LAUNCH(tube_light_kernel, ceil_div((long long)h * w, 256), 256, 0, (cudaStream_t)stream)(base_u8, h, w, t, patch,
+                                                                                                lit_u8);
+    DMH_CHECK_LAUNCH("dmh_tube_light_patch");
+    return DMH_OK;
+}
+
+int dmh_square_linf_candidate(const float* x_best, const float* x, int H, int W, int vh, int vw, int s, float d0,
+                              float d1, float d2, float eps, float* x_new, dmh_stream_t stream) {
+    DMH_REQUIRE(x_best && x && x_new, "dmh_square_linf_candidate: null pointer");
+    DMH_REQUIRE(H > 0 && W > 0 && s >= 0 && vh >= 0 && vw >= 0, "dmh_square_linf_candidate: bad shape / window");
+    DMH_REQUIRE(x_new != x, "dmh_square_linf_candidate: x_new may alias x_best only");
+    DMH_LAUNCH(square_candidate_kernel, ceil_div((long long)H * W, 256), 256, 0, (cudaStream_t)stream)(
+        x_best, x, H, W, vh, vw, s, d0, d1, d2, eps, x_new);
+    DMH_CHECK_LAUNCH("dmh_square_linf_candidate");
+    return DMH_OK;
+}
+
+int dmh_keep_best(const float* cost, const float* best_cost_in, float* best_cost_out, const float* cand, float* best,
+                  long long n, dmh_stream_t stream) {
+    DMH_REQUIRE(cost && best_cost_in && best_cost_out && cand && best && n > 0, "dmh_keep_best: null pointer or n <= 0");
+    DMH_REQUIRE(best_cost_in != best_cost_out && cand != best, "dmh_keep_best: in / out buffers must differ");
+    DMH_LAUNCH(keep_best_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream)(cost, best_cost_in, best_cost_out, cand,
+                                                                              best, n);
+    DMH_CHECK_LAUNCH("dmh_keep_best");
     return DMH_OK;
 }
 

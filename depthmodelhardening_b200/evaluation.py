@@ -74,9 +74,13 @@ def build_attack(model2atk, args: Dict, obj_tensor: torch.Tensor, mask_tensor: t
         return attacks.Phy_obj_atk_guassian(model2atk, obj_tensor, mask_tensor, steps=args["step"])
     if nt == "vanila":
         return attacks.Phy_obj_atk_vanila(model2atk, obj_tensor, mask_tensor)
-    raise NotImplementedError("norm_type %r: the black-box searches Square / light and the whole-image PGD are "
-                              "not mirrored; after install() the reference's own classes run on the grafted "
-                              "PhysicalTrans" % (nt,))
+    if nt == "Square":
+        return attacks.Phy_obj_atk_Square(model2atk, obj_tensor, mask_tensor, eps=args["epsilon"],
+                                          n_queries=args["n_queries"])
+    if nt == "light":
+        return attacks.Phy_obj_atk_light(model2atk, obj_tensor, mask_tensor, **args.get("light_kwargs", {}))
+    raise NotImplementedError("norm_type %r: the whole-image PGD (`PGD_depth`, no patch, no PhysicalTrans) is not on "
+                              "the grafted path" % (nt,))
 
 
 def evaluate_attacks(model2atk, args: Dict, scenes: Iterable[torch.Tensor], obj_tensor: torch.Tensor,
@@ -103,8 +107,12 @@ def evaluate_attacks(model2atk, args: Dict, scenes: Iterable[torch.Tensor], obj_
         scene_img = scene_img.to(dev)
         if args["norm_type"] == "vanila":
             adv_images, ben_images, obj_masks_out, _ = vanila(scene_img, obj_tensor, args["batch_size"], eval=True)
+        elif args["norm_type"] == "light" and i != start_idx:
+            # evaluate_depth.py:178-182: the light search runs on the first batch only, its patch is then placed
+            adv_images, ben_images, obj_masks_out, obj_img_adv = vanila(scene_img, obj_img_adv, args["batch_size"],
+                                                                        eval=True)
         else:
-            adv_images, ben_images, obj_masks_out, _ = atk(scene_img, args["batch_size"], eval=True)
+            adv_images, ben_images, obj_masks_out, obj_img_adv = atk(scene_img, args["batch_size"], eval=True)
         with torch.no_grad():
             disp_gt = model2atk(ben_images)
             disp_atk = model2atk(adv_images)

@@ -100,6 +100,9 @@ def install(mode: str = "fused", dataset_root: str = None) -> dict:
                           ("torchattacks.attacks.phy_obj_atk_apgd", "Phy_obj_atk_APGD"),
                           ("torchattacks.attacks.phy_obj_atk_guassian", "Phy_obj_atk_guassian"),
                           ("torchattacks.attacks.phy_obj_atk_arbi", "Phy_obj_atk_arbi"),
+                          ("torchattacks.attacks.phy_obj_atk_square", "Phy_obj_atk_Square"),
+                          ("torchattacks.attacks.phy_obj_atk_light", "Phy_obj_atk_light"),
+                          ("torchattacks", "Phy_obj_atk_Square"), ("torchattacks", "Phy_obj_atk_light"),
                           ("torchattacks", "Phy_obj_atk_arbi"),
                           ("torchattacks", "Phy_obj_atk_guassian"),
                           ("torchattacks", "Phy_obj_atk_APGD"), ("torchattacks", "Phy_obj_atk"),

@@ -288,6 +288,64 @@ def pgd_l2_step(adv, grad, clean, alpha, eps, eps_div=1e-10):
     return out
 
 
+def tube_light_patch(base_u8, k, b, beta, rgb, alpha=1.0, out=None):
+    """One candidate of the tube-light search (light_simulation.py:132-170 + phy_obj_atk_light.py:118-122) in one
+    launch: base_u8 = planar (3,h,w) uint8 object image on the device, (k, b) the beam axis y = k*x + b, `beta` the
+    attenuation, `rgb` = wavelength_to_rgb(wavelength) (python floats) -> (1,3,h,w) fp32 candidate patch.  The beam
+    scalars are formed here exactly as the reference forms them (python floats)."""
+    import math
+    if base_u8.dtype != torch.uint8 or not base_u8.is_cuda or base_u8.dim() != 3 or base_u8.shape[0] != 3:
+        raise RuntimeError("base_u8 must be a (3,h,w) uint8 CUDA tensor")
+    bu = base_u8.contiguous()
+    _, h, w = bu.shape
+    if out is None:
+        out = torch.empty(1, 3, h, w, device=bu.device, dtype=torch.float32)
+    k, b, beta = float(k), float(b), float(beta)
+    check(_lib_().dmh_tube_light_patch(ptr(bu), h, w, k, b, math.sqrt(1 + k * k), beta, int(math.sqrt(beta) + 0.5),
+                                       int(math.sqrt(beta * 20) + 0.5), float(rgb[0] * alpha), float(rgb[1] * alpha),
+                                       float(rgb[2] * alpha), ptr(out), None, stream()), "tube_light_patch")
+    return out
+
+
+def square_linf_candidate(x_best, x, vh, vw, s, delta3, eps, out=None):
+    """phy_obj_atk_square.py:263-274 in one launch: x_best / x (1,3,H,W), window [vh,vh+s) x [vw,vw+s), delta3 = the
+    three per-channel moves (fp32 values of 2 * eps * sign)."""
+    xb, xc = f32c(x_best), f32c(x)
+    _, _, H, W = xb.shape
+    if out is None:
+        out = torch.empty_like(xb)
+    check(_lib_().dmh_square_linf_candidate(ptr(xb), ptr(xc), H, W, int(vh), int(vw), int(s), float(delta3[0]),
+                                            float(delta3[1]), float(delta3[2]), float(eps), ptr(out), stream()),
+          "square_linf_candidate")
+    return out
+
+
+class BestKeeper:
+    """`if cost < best_cost: best_cost, best = cost, candidate` on the device (dmh_keep_best): the search loops of the
+    black-box attacks never wait for the host.  `best` starts as `init` (or zeros), `best_cost` as `init_cost`."""
+
+    def __init__(self, like, init_cost=1e10, init=None):
+        self.best = f32c(init).clone() if init is not None else torch.zeros_like(f32c(like))
+        self._cost = [torch.full((1,), float(init_cost), device=self.best.device, dtype=torch.float32),
+                      torch.empty(1, device=self.best.device, dtype=torch.float32)]
+        self._cur = 0
+
+    @property
+    def best_cost(self):
+        return self._cost[self._cur]
+
+    def set_cost(self, cost):
+        self._cost[self._cur].copy_(cost.detach().reshape(1))
+
+    def offer(self, cost, cand):
+        c, x = f32c(cost.detach()).reshape(1), f32c(cand)
+        if x.numel() != self.best.numel():
+            raise RuntimeError("candidate / best size mismatch")
+        check(_lib_().dmh_keep_best(ptr(c), ptr(self._cost[self._cur]), ptr(self._cost[1 - self._cur]), ptr(x),
+                                    ptr(self.best), x.numel(), stream()), "keep_best")
+        self._cur = 1 - self._cur
+
+
 class L0State:
     """Device-resident state of the L0 attack (patterns, Adam moments, counts)."""
 

@@ -317,6 +317,26 @@ int dmh_pgd_linf_step(const float* adv, const float* grad, const float* clean, l
 int dmh_apgd_linf_step(const float* x_adv, const float* x_adv_old, const float* grad, const float* x0, long long n,
                        float step, float a, float eps, float* out, dmh_stream_t stream);
 
+/* -- black-box patch searches (next-4): candidates and acceptance on the device ---------------------------------
+ * Tube-light candidate (torchattacks/attacks/light_simulation.py:132-170 tube_light_generation_by_func, then
+ * phy_obj_atk_light.py:118-122 / light_simulation.py:23-28): per pixel d = |k*x - y + b| / norm in float64;
+ * light = ca[c] for d <= full_end, ca[c] * beta / d^2 for d <= light_end, else 0; lit = uint8(clip(base +
+ * float32(light * 255), 0, 255)); patch = float(lit) / 255 (ToTensor).  base_u8 / lit_u8 (optional): planar (3,h,w)
+ * bytes; patch: (3,h,w) floats.  The scalars are formed on the host as the reference forms them: k = round(tan, 2),
+ * norm = sqrt(1 + k*k), full_end = int(sqrt(beta) + .5), light_end = int(sqrt(20 beta) + .5), ca = rgb * alpha.   */
+int dmh_tube_light_patch(const uint8_t* base_u8, int h, int w, double k, double b, double norm, double beta,
+                         int full_end, int light_end, double ca0, double ca1, double ca2, float* patch, uint8_t* lit_u8,
+                         dmh_stream_t stream);
+/* Square-attack L-inf candidate (torchattacks/attacks/phy_obj_atk_square.py:263-274): x_new = clamp(min(max(x_best +
+ * delta, x - eps), x + eps), 0, 1), delta = d[c] inside the window [vh,vh+s) x [vw,vw+s), 0 outside; (3,H,W).   */
+int dmh_square_linf_candidate(const float* x_best, const float* x, int H, int W, int vh, int vw, int s, float d0,
+                              float d1, float d2, float eps, float* x_new, dmh_stream_t stream);
+/* `if cost < best_cost: best_cost, best = cost, cand` without a host round trip (phy_obj_atk_light.py:148-150,
+ * phy_obj_atk_square.py:281-297): best_cost_out[0] = min-select of cost[0] / best_cost_in[0] (strict <, NaN never
+ * accepted), best[0..n) = cand where accepted.  best_cost_in != best_cost_out (the caller ping-pongs them).     */
+int dmh_keep_best(const float* cost, const float* best_cost_in, float* best_cost_out, const float* cand, float* best,
+                  long long n, dmh_stream_t stream);
+
 /* -- evaluation metrics of the attack harness (next-4; DepthNetworks/monodepth2/evaluate_depth.py:193-196 and
  * compute_errors :57-99), one launch per batch: depth = clamp(disp_to_depth(|disp|, min_disp_depth, max_disp_depth)[1]
  * * scale_factor, min_depth, max_depth) for both maps, then out[9] (double, zeroed here) = [sum mask, sum |d|*m,

@@ -361,7 +361,16 @@ def test_evaluate_attacks_harness_runs_on_the_dropins(dev):
     assert mean_v[0] < 1e-6                                  # vanila: adversarial == benign object
     assert mean_a[0] > mean_v[0]
     with pytest.raises(NotImplementedError):
-        evaluation.build_attack(model, dict(base, norm_type="Square"), pbt.obj, pbt.mask)
+        evaluation.build_attack(model, dict(base, norm_type="image"), pbt.obj, pbt.mask)
+    # the black-box searches through the same harness: Square (reference constructor arguments) and light (search on
+    # the first batch, its patch placed on the following ones, evaluate_depth.py:178-182)
+    mean_s, _ = evaluation.evaluate_attacks(model, dict(base, norm_type="Square", n_queries=3), scenes, pbt.obj,
+                                            pbt.mask, eval_count=2, verbose=False)
+    np.random.seed(3)
+    mean_l, _ = evaluation.evaluate_attacks(model, dict(base, norm_type="light", light_kwargs=dict(n_init=2, n_search=2)),
+                                            scenes, pbt.obj, pbt.mask, eval_count=2, verbose=False)
+    assert np.isfinite(mean_s).all() and np.isfinite(mean_l).all()
+    assert mean_s[0] > mean_v[0] and mean_l[0] >= mean_v[0]
 
 
 
@@ -411,3 +420,120 @@ def test_arbitrary_pattern_attack_dropin_vs_reference_class_same_device(dev):
         assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
         assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
         assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)
+
+
+
+def test_tube_light_kernel_vs_oracle(dev):
+    """`dmh_tube_light_patch` against oracle/light.py (pinned bit for bit to the reference's
+    tube_light_generation_by_func + simple_add, tests/golden/light.npz): candidate patches of a seeded beam walk at
+    the attack's patch size, compared bit for bit."""
+    from depthmodelhardening_b200 import attacks, patch_ops
+    from oracle import light as OL
+    obj = synth.patch_batch(batch=1, seed=2).obj
+    base_hwc = OL.to_u8_hwc(obj[0].numpy())
+    base_dev = obj[0].to(dev).mul(255).byte().contiguous()
+    assert np.array_equal(base_dev.cpu().numpy(), np.transpose(base_hwc, (2, 0, 1)))
+    np.random.seed(7)
+    cases = [tuple(int(v) for v in q) for q in OL.candidate_params(n_init=3, n_search=2)]
+    cases += [(380, 0, 0, 10), (470, 90, 30, 1600), (500, 91, 399, 333), (750, 180, 400, 9)]
+    n_lit = 0
+    for wl, ang, icpt, beta in cases:
+        want = OL.candidate_patch(base_hwc, (wl, ang, icpt, beta))
+        got = patch_ops.tube_light_patch(base_dev, OL.slope_of(ang), icpt, beta, attacks.wavelength_to_rgb(wl))
+        assert got.shape == (1, 3, synth.PATCH_H, synth.PATCH_W)
+        assert np.array_equal(got[0].cpu().numpy(), want), (wl, ang, icpt, beta)
+        n_lit += int((want != np.transpose(base_hwc, (2, 0, 1)).astype(np.float32) / np.float32(255)).any())
+    assert n_lit >= 6
+
+
+def test_keep_best_and_square_candidate_kernels_bit_exact(dev):
+    """`dmh_square_linf_candidate` against the torch expression of phy_obj_atk_square.py:263-274 and `dmh_keep_best`
+    against the host-side `if cost < best_cost` (strict, NaN never accepted), bit for bit."""
+    from depthmodelhardening_b200 import patch_ops
+    g = torch.Generator().manual_seed(3)
+    H, W, eps = synth.PATCH_H, synth.PATCH_W, 0.1
+    x = torch.rand(1, 3, H, W, generator=g).to(dev)
+    x_best = torch.clamp(x + eps * torch.sign(2 * torch.rand(1, 3, 1, W, generator=g) - 1).to(dev), 0., 1.)
+    for vh, vw, s in ((0, 0, 250), (5, 7, 99), (259, 299, 1), (3, 4, 0)):
+        sign = torch.sign(2 * torch.rand(3, 1, 1, generator=g) - 1)
+        new_deltas = torch.zeros(3, H, W, device=dev)
+        new_deltas[:, vh:vh + s, vw:vw + s] = (2. * eps * sign).to(dev)
+        want = torch.clamp(torch.min(torch.max(x_best + new_deltas, x - eps), x + eps), 0., 1.)
+        got = patch_ops.square_linf_candidate(x_best, x, vh, vw, s, (2. * eps * sign).reshape(3).tolist(), eps)
+        assert torch.equal(got, want), (vh, vw, s)
+    keeper = patch_ops.BestKeeper(x, init_cost=1e10)
+    best_cost, best = 1e10, None
+    cands = [torch.rand(1, 3, H, W, generator=g).to(dev) for _ in range(6)]
+    for cost, cand in zip((0.5, 0.7, 0.5, float("nan"), 0.25, 0.25), cands):
+        keeper.offer(torch.tensor(cost, device=dev), cand)
+        if cost < best_cost:
+            best_cost, best = cost, cand
+        assert torch.equal(keeper.best, best) and float(keeper.best_cost) == np.float32(best_cost)
+
+
+def test_square_attack_dropin_vs_reference_class_same_device(dev):
+    """next-4: `Phy_obj_atk_Square` -- the drop-in against the reference's own class on the same GPU, same network
+    and seeds.  Both draw the stripes, windows and signs from the torch CPU generator and the final placements from
+    `random` in the same order; the returned patch must be the SAME tensor (the reference's search evaluates the
+    current best at every query and therefore keeps its striped start, see the class docstring)."""
+    import importlib
+    import random
+    from depthmodelhardening_b200 import attacks
+    from tests.test_gpu_patch import _tiny
+    ref = _reference_or_skip()
+    ref_s = importlib.import_module("torchattacks.attacks.phy_obj_atk_square")
+    attacks.object_dataset_root = ref.calib_root
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    outs, rng_after = [], []
+    for cls in (ref_s.Phy_obj_atk_Square, attacks.Phy_obj_atk_Square):
+        torch.manual_seed(31)
+        random.seed(32)
+        atk = cls(model, pbt.obj.clone(), pbt.mask.clone(), eps=0.1, n_queries=6, seed=5, dist_range=list(range(5, 10, 2)))
+        outs.append(atk(pbt.scenes.clone(), 3, eval=True))
+        rng_after.append((float(torch.rand(1)), random.random()))
+    (adv_r, ben_r, m_r, x_r), (adv_o, ben_o, m_o, x_o) = outs
+    assert rng_after[0] == rng_after[1]                    # the same number of draws from both generators
+    assert torch.equal(x_o, x_r)
+    assert float((x_o - pbt.obj).abs().max()) > 0.05       # (the stripes)
+    assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    with pytest.raises(NameError):
+        attacks.Phy_obj_atk_Square(model, pbt.obj.clone(), pbt.mask.clone(), norm="L2", n_queries=2)(pbt.scenes.clone(), 3)
+
+
+def test_light_attack_dropin_vs_reference_class_same_device(dev, monkeypatch):
+    """next-4: `Phy_obj_atk_light` -- the drop-in against the reference's own class on the same GPU, same network and
+    seeds, on a shortened search (the reference hard-codes 200 x 20 x 2 candidates at ~0.1 s of Python loops each:
+    its module-level `range` is shadowed so that both loops run twice -- 8 candidates -- and the drop-in gets
+    n_init = n_search = 2).  Same beam walk (numpy RNG) and placements (`random`): the same candidate must win, and
+    its patch -- built by `dmh_tube_light_patch` -- must equal the reference's PIL / OpenCV result bit for bit."""
+    import builtins
+    import importlib
+    import random
+    from depthmodelhardening_b200 import attacks
+    from tests.test_gpu_patch import _tiny
+    ref = _reference_or_skip()
+    try:
+        ref_l = importlib.import_module("torchattacks.attacks.phy_obj_atk_light")
+    except ImportError as e:                               # cv2 / scipy.ndimage.filters of the reference's imports
+        pytest.skip("reference light attack not importable here: %s" % e)
+    monkeypatch.setattr(ref_l, "range", lambda n: builtins.range(min(n, 2)), raising=False)
+    attacks.object_dataset_root = ref.calib_root
+    pbt = synth.patch_batch(batch=3, seed=4).to(dev)
+    model = _tiny(dev).eval()
+    outs, rng_after = [], []
+    for cls, kw in ((ref_l.Phy_obj_atk_light, {}), (attacks.Phy_obj_atk_light, dict(n_init=2, n_search=2))):
+        np.random.seed(41)
+        random.seed(42)
+        atk = cls(model, pbt.obj.clone(), pbt.mask.clone(), dist_range=list(range(5, 10, 2)), **kw)
+        outs.append(atk(pbt.scenes.clone(), 3, eval=True))
+        rng_after.append((np.random.randint(1 << 30), random.random()))
+    (adv_r, ben_r, m_r, x_r), (adv_o, ben_o, m_o, x_o) = outs
+    assert rng_after[0] == rng_after[1]
+    assert torch.equal(x_o, x_r)                           # the same candidate won, the same bytes / 255
+    assert float((x_o - pbt.obj).abs().max()) > 0.0
+    assert_close(adv_o, adv_r, TOL, "adv scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(ben_o, ben_r, TOL, "benign scenes", max_outlier_frac=1e-4, outlier_rtol=1.0)
+    assert_close(m_o, m_r, TOL, "masks", max_outlier_frac=1e-4, outlier_rtol=1.0)

@@ -229,3 +229,64 @@ def test_pose_sum_reduce_scatter_network_host_emulation():
     want = acc.sum(0)
     for lane in lanes[writers]:
         assert abs(v1[lane] - want[vi[lane]]) < 1e-12
+
+
+# ----------------------------------------------------------------------------- black-box candidates (next-4)
+@pytest.fixture(scope="module")
+def emu_light():
+    src = os.path.join(HERE, "host_emul_light.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "depthmodelhardening_b200", "csrc", "light_math.cuh")
+    so = os.path.join(BUILD, "libdmh_hostemu_light.so")
+    os.makedirs(BUILD, exist_ok=True)
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-o", so, src])
+    return C.CDLL(so)
+
+
+def test_tube_light_math_vs_oracle(emu_light):
+    """csrc/light_math.cuh (the per-pixel body of dmh_tube_light_patch) compiled with g++ equals oracle/light.py --
+    which equals the reference's tube_light_generation_by_func + simple_add bit for bit (tests/golden/light.npz) --
+    over the golden cases and a seeded walk of the search, lit bytes and fp32 patch."""
+    import math
+    from oracle import light as OL
+    rs = np.random.RandomState(9)
+    np.random.seed(5)
+    cases = [(380, 0, 0, 10), (470, 89, 30, 1600), (500, 91, 399, 333), (600, 179, 5, 1234), (750, 160, 350, 9)]
+    cases += [tuple(int(v) for v in q) for q in OL.candidate_params(n_init=3, n_search=3)]
+    h, w = 52, 60
+    for wl, ang, icpt, beta in cases:
+        base = rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        want = OL.candidate_patch(base, (wl, ang, icpt, beta))
+        k = OL.slope_of(ang)
+        full_end, light_end = OL.light_ends(beta)
+        ca = [c * 1.0 for c in OL.wavelength_to_rgb(wl)]
+        planar = np.ascontiguousarray(np.transpose(base, (2, 0, 1)))
+        patch = np.empty((3, h, w), np.float32)
+        lit = np.empty((3, h, w), np.uint8)
+        emu_light.emu_tube_light(C.c_void_p(planar.ctypes.data), C.c_int(h), C.c_int(w), C.c_double(k),
+                                 C.c_double(float(icpt)), C.c_double(math.sqrt(1 + k * k)), C.c_double(float(beta)),
+                                 C.c_int(full_end), C.c_int(light_end), C.c_double(ca[0]), C.c_double(ca[1]),
+                                 C.c_double(ca[2]), C.c_void_p(patch.ctypes.data), C.c_void_p(lit.ctypes.data))
+        assert np.array_equal(patch, want), (wl, ang, icpt, beta)
+        assert np.array_equal(lit, (want * np.float32(255) + np.float32(0.5)).astype(np.uint8))
+
+
+def test_square_candidate_math_vs_torch(emu_light):
+    """The body of dmh_square_linf_candidate against the torch expression of phy_obj_atk_square.py:263-274."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    H, W, eps = 26, 30, 0.1
+    x = torch.rand(1, 3, H, W, generator=g)
+    x_best = torch.clamp(x + eps * torch.sign(2 * torch.rand(1, 3, 1, W, generator=g) - 1), 0., 1.)
+    for vh, vw, s in ((0, 0, 23), (5, 7, 9), (25, 29, 1), (3, 4, 0)):
+        sign = torch.sign(2 * torch.rand(3, 1, 1, generator=g) - 1)
+        new_deltas = torch.zeros(3, H, W)
+        new_deltas[:, vh:vh + s, vw:vw + s] = 2. * eps * sign
+        want = torch.clamp(torch.min(torch.max(x_best + new_deltas, x - eps), x + eps), 0., 1.)
+        d = (2. * eps * sign).reshape(3).tolist()
+        xb, xc = x_best.numpy().copy(), x.numpy().copy()
+        out = np.empty((1, 3, H, W), np.float32)
+        emu_light.emu_square_candidate(C.c_void_p(xb.ctypes.data), C.c_void_p(xc.ctypes.data), C.c_int(H), C.c_int(W),
+                                       C.c_int(vh), C.c_int(vw), C.c_int(s), C.c_float(d[0]), C.c_float(d[1]),
+                                       C.c_float(d[2]), C.c_float(eps), C.c_void_p(out.ctypes.data))
+        assert np.array_equal(out, want.numpy()), (vh, vw, s)
