@@ -58,6 +58,8 @@ def parse_args():
                     help="batch slice of the CPU legs (0: cpu_baseline 8; --impl reference: adaptive, see reference_arm)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (sharded batch 32) sub-record")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-on-the-same-GPU baseline")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="headline = the step launched from Python on one stream (default: CUDA-graph replay, two streams)")
     return ap.parse_args()
 
 
@@ -234,6 +236,34 @@ def timed_loop(fn, steps, warmup, world):
     return ms / steps
 
 
+def capture_step(s1, s2, device, lib, two_stream=True):
+    """One step (stage 1 incl. its collective, stage 2 fwd+bwd) captured into a CUDA graph; returns (graph, number of
+    this library's kernel launches inside one replay).  two_stream: stage 1 runs on a side stream beside stage 2."""
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):                          # warm-up off the capturing stream (allocator, lazy inits)
+        for _ in range(3):
+            s1.step()
+            s2.step()
+    cur.wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    n0 = lib.dmh_launch_count()
+    with torch.cuda.graph(graph):
+        if two_stream:
+            cs = torch.cuda.current_stream()
+            side.wait_stream(cs)
+            with torch.cuda.stream(side):
+                s1.step()
+            s2.step()
+            cs.wait_stream(side)
+        else:
+            s1.step()
+            s2.step()
+    return graph, int(lib.dmh_launch_count() - n0)
+
+
 def measure_strong(args, rank, world, device, global_batch):
     """Strong scaling (north_star / SURVEY.md 8(e)): the batch-32 step with the batch SHARDED over the ranks.
     Same step as the headline (stage 1 + the one all-reduce + stage 2); timed eagerly and as a CUDA-graph replay of
@@ -289,7 +319,7 @@ def measure_strong(args, rank, world, device, global_batch):
                               else ("nccl all_reduce + div_" if world > 1 else "none"),
                 "note": "ms_per_step / value: CUDA-graph replay of the whole step (stage 1, the all-reduce of the "
                         "patch gradient, stage 2 fwd+bwd) captured once; *_eager: the same step launched from Python. "
-                        "The L0 Adam bias-correction step index is frozen in the replay (timing only)."})
+                        "The L0 Adam step index lives on the device (dmh_l0_adam_step_dev): replays are exact."})
     if world > 1:
         # the collective alone, both forms, back to back on this box (device time, max over ranks)
         n = s1.adv.numel() + 1
@@ -534,13 +564,36 @@ def main():
         return s2.step()
 
     # inputs > L2 (126 MB): colour frames alone are 2 x 126 MB at B=32, so no explicit flush is needed
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # (1) the step launched from Python, one stream (the round-1 / early round-2 headline; kept as `ms_per_step_eager`)
     n0 = lib.dmh_launch_count()
-    ms_step = timed_loop(step, args.steps, args.warmup, world)
+    ms_eager = timed_loop(step, args.steps, args.warmup, world)
     n1 = lib.dmh_launch_count()
-    clocks = sampler.stop()
     launches = int((n1 - n0) * args.steps / (args.steps + args.warmup))
+    # (2) the product schedule and the headline: the SAME step captured once into a CUDA graph -- stage 1 (with the
+    # step's one collective) on a side stream beside stage 2, the two stages read different inputs -- and replayed.
+    # Nothing is frozen into the capture that a real run would change: the L0 Adam step index lives on the device
+    # (dmh_l0_adam_step_dev), the all-reduce's step counter too (dmh_peer_allreduce).  --no-graph, a failed capture
+    # or stage 2 alone: the eager step is the headline.
+    schedule = "eager, one stream"
+    ms_step, graph = ms_eager, None
+    sampler = ClockSampler(local_rank)
+    if s1 is not None and not args.no_graph:
+        try:
+            graph, launches_graph = capture_step(s1, s2, device, lib, two_stream=True)
+            if world > 1:
+                torch.distributed.barrier()
+            sampler.start()
+            ms_step = timed_loop(graph.replay, args.steps, args.warmup, world)
+            launches = launches_graph * args.steps
+            schedule = "CUDA-graph replay, stage 1 on a side stream beside stage 2"
+        except Exception as exc:
+            schedule = "eager, one stream (graph capture failed: %s: %s)" % (type(exc).__name__, str(exc)[:120])
+            graph = None
+            torch.cuda.synchronize()
+    if graph is None:
+        sampler.start()
+        ms_step = timed_loop(step, args.steps, args.warmup, world)
+    clocks = sampler.stop()
 
     # per-stage split (same loop, one stage at a time)
     ms_s2 = timed_loop(s2.step, args.steps, 2, world)
@@ -873,6 +926,8 @@ def main():
                    "per_gpu_batch": B, "global_batch": B * world, "height": H, "width": W, "frame_ids": list(FRAME_IDS),
                    "scales": list(SCALES), "l2_policy": "inputs (2x126 MB frames + 168 MB noise) exceed the 126 MB L2"},
         "gpu_launches": launches,
+        "schedule": schedule, "ms_per_step_eager": ms_eager,
+        "value_eager": world * B * H * W / (ms_eager * 1e-3) / 1e6,
         "clocks": clocks,
         "stages": {"photometric_ms": ms_s2, "patch_pgd_ms": ms_s1, "two_stream_step_ms": ms_overlap,
                    "pgd_steps_per_s": (1e3 / ms_s1) if ms_s1 else None,

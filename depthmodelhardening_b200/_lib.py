@@ -98,6 +98,9 @@ SIGNATURES = {
     "dmh_l0_compose_count": (_i, [_f, _f, _f, _i, _i, _i, _fl, _fl, _f, _f, _st]),
     "dmh_l0_adam_step": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _fl, _i,
                               _st]),
+    "dmh_l0_adam_bias_table": (_i, [_fl, _fl, _fl, _i, C.POINTER(C.c_float)]),
+    "dmh_l0_adam_step_dev": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _f, _fl, _fl, _fl, _fl, _fl, _f, _i, _f,
+                                  _st]),
     "dmh_l0_finalize": (_i, [_f, _f, _f, _ll, _fl, _fl, _f, _f, _st]),
     "dmh_topk_select": (_i, [_f, _f, _i, _i, _i, _i, _f, _f, _st]),
     "dmh_hint_select_blocks": (_i, [_i, _i, _i]),

@@ -183,8 +183,26 @@ __global__ void l0_adam_kernel(const float* __restrict__ obj, const float* __res
                                float* __restrict__ v_pos, float* __restrict__ m_neg, float* __restrict__ v_neg,
                                int C, int npix, float clip_max, const unsigned long long* __restrict__ counts,
                                float l0_thresh, float mask_weight_init, float step_size, float beta1, float beta2,
-                               float adam_eps, float bc2_sqrt) {
+                               float adam_eps, float bc2_sqrt, const float* __restrict__ bias_table, int table_len,
+                               unsigned* step_state) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bias_table) {
+        // step index on the device (dmh_l0_adam_step_dev): every CTA reads the number of finished steps before any
+        // CTA can advance it -- the advance is done by the LAST CTA to arrive at the end of the kernel
+        const unsigned done = *reinterpret_cast<volatile unsigned*>(step_state);
+        const int idx = min((int)done, table_len - 1);
+        step_size = bias_table[2 * idx];
+        bc2_sqrt = bias_table[2 * idx + 1];
+        __syncthreads();                                 // the whole CTA has read `done`
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(step_state + 1, 1u) == gridDim.x - 1) {
+                step_state[1] = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned*>(step_state) = done + 1u;
+            }
+        }
+    }
     if (p >= npix) return;
     // mask_weight = 0 once l0/l0_init <= thresh (fp32 division as torch does on the int64 tensors)
     float mask_w = mask_weight_init;
@@ -514,8 +532,36 @@ int dmh_l0_adam_step(const float* obj, const float* grad_adv, float* pattern_pos
     const int npix = H * W;
     DMH_LAUNCH(l0_adam_kernel, ceil_div(npix, 256), 256, 0, (cudaStream_t)stream)(
         obj, grad_adv, pattern_pos, pattern_neg, m_pos, v_pos, m_neg, v_neg, C, npix, clip_max, counts, l0_thresh,
-        mask_weight, (float)((double)lr / bc1), beta1, beta2, adam_eps, (float)sqrt(bc2));
+        mask_weight, (float)((double)lr / bc1), beta1, beta2, adam_eps, (float)sqrt(bc2), nullptr, 0, nullptr);
     DMH_CHECK_LAUNCH("dmh_l0_adam_step");
+    return DMH_OK;
+}
+
+int dmh_l0_adam_bias_table(float lr, float beta1, float beta2, int table_len, float* table_host) {
+    DMH_REQUIRE(table_host && table_len >= 1, "dmh_l0_adam_bias_table: null pointer or empty table");
+    for (int t = 1; t <= table_len; ++t) {
+        // the two scalars dmh_l0_adam_step forms from its host-side step index, same double arithmetic
+        const double bc1 = 1.0 - pow((double)beta1, (double)t);
+        const double bc2 = 1.0 - pow((double)beta2, (double)t);
+        table_host[2 * (t - 1)] = (float)((double)lr / bc1);
+        table_host[2 * (t - 1) + 1] = (float)sqrt(bc2);
+    }
+    return DMH_OK;
+}
+
+int dmh_l0_adam_step_dev(const float* obj, const float* grad_adv, float* pattern_pos, float* pattern_neg, float* m_pos,
+                         float* v_pos, float* m_neg, float* v_neg, int C, int H, int W, float clip_max,
+                         const unsigned long long* counts, float l0_thresh, float mask_weight, float beta1, float beta2,
+                         float adam_eps, const float* bias_table, int table_len, unsigned* step_state,
+                         dmh_stream_t stream) {
+    DMH_REQUIRE(obj && pattern_pos && pattern_neg && m_pos && v_pos && m_neg && v_neg && bias_table && step_state,
+                "dmh_l0_adam_step_dev: null pointer");
+    DMH_REQUIRE(C > 0 && H > 0 && W > 0 && table_len >= 1, "dmh_l0_adam_step_dev: bad shape or empty table");
+    const int npix = H * W;
+    DMH_LAUNCH(l0_adam_kernel, ceil_div(npix, 256), 256, 0, (cudaStream_t)stream)(
+        obj, grad_adv, pattern_pos, pattern_neg, m_pos, v_pos, m_neg, v_neg, C, npix, clip_max, counts, l0_thresh,
+        mask_weight, 0.0f, beta1, beta2, adam_eps, 1.0f, bias_table, table_len, step_state);
+    DMH_CHECK_LAUNCH("dmh_l0_adam_step_dev");
     return DMH_OK;
 }
 

@@ -349,7 +349,13 @@ class BestKeeper:
 class L0State:
     """Device-resident state of the L0 attack (patterns, Adam moments, counts)."""
 
-    def __init__(self, obj, pattern_pos, pattern_neg, lr=0.5, betas=(0.5, 0.9), eps=1e-8, clip_max=1.0):
+    BIAS_TABLE_LEN = 4096
+
+    def __init__(self, obj, pattern_pos, pattern_neg, lr=0.5, betas=(0.5, 0.9), eps=1e-8, clip_max=1.0,
+                 device_step=True):
+        """device_step (default): Adam's step index lives on the device (dmh_l0_adam_step_dev) -- an attack iteration
+        can be captured into a CUDA graph and replayed with the correct bias correction at every replay; False: the
+        host-side index of dmh_l0_adam_step (frozen by a capture).  Both give the same bits."""
         self.obj = f32c(obj)
         self.ppos = f32c(pattern_pos).clone()
         self.pneg = f32c(pattern_neg).clone()
@@ -360,6 +366,14 @@ class L0State:
         self.step = 0
         self.thr = self.clip_max / 255.0
         _, self.C, self.H, self.W = self.obj.shape
+        self.step_state = self.bias_table = None
+        if device_step:
+            import ctypes as C
+            n = self.BIAS_TABLE_LEN
+            host = (C.c_float * (2 * n))()
+            check(_lib_().dmh_l0_adam_bias_table(self.lr, float(betas[0]), float(betas[1]), n, host), "l0_adam_bias_table")
+            self.bias_table = torch.tensor(list(host), dtype=torch.float32).to(self.obj.device)
+            self.step_state = torch.zeros(2, device=self.obj.device, dtype=torch.int32)   # [steps done, ticket]
 
     def compose_count(self, first=False):
         """phy_obj_atk_l0.py:94-111: adv patch + l0 count (stays on the device)."""
@@ -374,6 +388,13 @@ class L0State:
     def adam_step(self, grad_adv, mask_weight, l0_thresh):
         self.step += 1
         g = f32c(grad_adv) if grad_adv is not None else None
+        if self.step_state is not None:
+            check(_lib_().dmh_l0_adam_step_dev(ptr(self.obj), ptr(g), ptr(self.ppos), ptr(self.pneg), ptr(self.m_pos),
+                                               ptr(self.v_pos), ptr(self.m_neg), ptr(self.v_neg), self.C, self.H, self.W,
+                                               self.clip_max, ptr(self.counts), float(l0_thresh), float(mask_weight),
+                                               self.betas[0], self.betas[1], self.eps, ptr(self.bias_table),
+                                               self.BIAS_TABLE_LEN, ptr(self.step_state), stream()), "l0_adam_step_dev")
+            return
         check(_lib_().dmh_l0_adam_step(ptr(self.obj), ptr(g), ptr(self.ppos), ptr(self.pneg), ptr(self.m_pos),
                                        ptr(self.v_pos), ptr(self.m_neg), ptr(self.v_neg), self.C, self.H, self.W,
                                        self.clip_max, ptr(self.counts), float(l0_thresh), float(mask_weight), self.lr,

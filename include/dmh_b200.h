@@ -368,6 +368,21 @@ int dmh_l0_adam_step(const float* obj, const float* grad_adv, float* pattern_pos
                      const unsigned long long* counts, float l0_thresh, float mask_weight, float lr, float beta1,
                      float beta2, float adam_eps, int step, dmh_stream_t stream);
 
+/* The same step with the step index kept ON THE DEVICE, so that a whole attack iteration (compose, patch apply,
+ * network, this update) can be captured once into a CUDA graph and replayed: a host-side `step` argument would be
+ * frozen into the capture.  bias_table: table_len x 2 device floats, entry t-1 = {lr / (1 - beta1^t),
+ * sqrt(1 - beta2^t)} -- the two scalars dmh_l0_adam_step forms from `step`, filled on the host by
+ * dmh_l0_adam_bias_table with the same double arithmetic (bit-identical updates); steps past the table read its last
+ * entry (both factors have converged in fp32 long before: t > 25 / 160 for torch's betas (0.5, 0.9)).
+ * step_state: 2 uint32 of device memory, zeroed before the first step: {steps done, CTA arrival ticket}; the last
+ * CTA of a launch advances the step, after every CTA has read it.                                            */
+int dmh_l0_adam_bias_table(float lr, float beta1, float beta2, int table_len, float* table_host);
+int dmh_l0_adam_step_dev(const float* obj, const float* grad_adv, float* pattern_pos, float* pattern_neg, float* m_pos,
+                         float* v_pos, float* m_neg, float* v_neg, int C, int H, int W, float clip_max,
+                         const unsigned long long* counts, float l0_thresh, float mask_weight, float beta1, float beta2,
+                         float adam_eps, const float* bias_table, int table_len, unsigned* step_state,
+                         dmh_stream_t stream);
+
 /* -- phy_obj_atk_l0.py:143-150: hard threshold at `threshold`, compose; pattern nullable */
 int dmh_l0_finalize(const float* obj, const float* pattern_pos, const float* pattern_neg, long long n, float clip_max,
                     float threshold, float* adv, float* pattern, dmh_stream_t stream);

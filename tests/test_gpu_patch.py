@@ -202,6 +202,63 @@ def test_l0_adam_step_vs_torch_autograd(dev):
         assert_close(st.pneg, pn, 2e-6, "P- after step %d" % i)
 
 
+def test_l0_attack_iteration_graph_replay_equals_eager(dev):
+    """Adam's step index lives on the device (dmh_l0_adam_step_dev): (a) the device-step update equals the host-step
+    one (dmh_l0_adam_step) bit for bit over several steps, through the point where the mask weight switches off;
+    (b) ONE captured attack iteration (compose + count -> fused patch apply -> update with a fixed gradient), replayed n times,
+    leaves the same patterns, moments and counts as n eager iterations -- a host-side step index would be frozen
+    into the capture and mis-scale every replay after the first."""
+    from depthmodelhardening_b200 import patch_ops
+    from oracle.refload import CALIB_P2
+    pt_cpu = synth.patch_batch(batch=2, seed=9)
+    pt = pt_cpu.to(dev)
+    P34 = np.array(CALIB_P2, dtype=np.float64).reshape(3, 4)
+    coeffs = patch_ops.homographies(pt_cpu.z0, pt_cpu.alpha, P34, obj_hw=(synth.PATCH_H, synth.PATCH_W)).to(dev)
+
+    def make(device_step):
+        return patch_ops.L0State(pt.obj, pt.pattern_pos, pt.pattern_neg, lr=0.5, betas=(0.5, 0.9), device_step=device_step)
+
+    # the patch gradient of the iteration: computed ONCE (the backward scatters with fp32 atomics -- its last bits
+    # differ from launch to launch) and fed to every instance
+    adv0 = make(False).compose_count(first=True)
+    _, _, grad0 = patch_ops.apply_patch_fwd_bwd(adv0, pt.mask, pt.scenes, coeffs, pt.upstream)
+    grad0 = grad0.clone()
+
+    def iteration(st, first=False):
+        adv = st.compose_count(first=first)
+        patch_ops.apply_patch(adv, pt.mask, pt.scenes, coeffs)       # (the forward placement: deterministic)
+        st.adam_step(grad0, 0.06, 0.1)
+
+    def state(st):
+        return [t.clone() for t in (st.ppos, st.pneg, st.m_pos, st.v_pos, st.m_neg, st.v_neg, st.counts)]
+
+    n = 6
+    host, devs = make(False), make(True)
+    for i in range(n):
+        iteration(host, first=(i == 0))
+        iteration(devs, first=(i == 0))
+        for a, b in zip(state(host), state(devs)):
+            assert torch.equal(a, b), "device-step vs host-step after iteration %d" % i
+    assert int(devs.step_state[0]) == n and int(devs.step_state[1]) == 0
+    # (b) graph replay
+    g = make(True)
+    iteration(g, first=True)                               # the init count is taken outside the capture
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph):
+            iteration(g)
+    torch.cuda.current_stream().wait_stream(side)
+    # (capturing does not execute: the state is still the one after the first eager iteration)
+    for _ in range(n - 1):
+        graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(state(host), state(g)):
+        assert torch.equal(a, b), "graph replay vs eager"
+    assert int(g.step_state[0]) == n
+
+
 @pytest.mark.parametrize("k", [0, 1, 777, 40000, 78000, 90000])
 def test_topk_radix_select_bit_exact(dev, k):
     from depthmodelhardening_b200 import patch_ops
