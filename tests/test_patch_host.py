@@ -100,3 +100,37 @@ def test_placement_bbox_is_conservative():
         # ... and is not vacuous: within a few pixels of the true extent
         assert int(xs.min()) - x0 <= 8 and x1 - int(xs.max()) <= 8
         assert place.bbox_wh[0] >= x1 - x0 + 1 and place.bbox_wh[1] >= y1 - y0 + 1
+
+
+def test_install_rebinds_every_patch_attack_class():
+    """next-4: every `Phy_obj_atk*` class of the reference (nine modules) is rebound to its drop-in by install() and
+    restored by uninstall()."""
+    import importlib
+    import os
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not present")
+    ref = refload.load()
+    import depthmodelhardening_b200.install as dmh
+    names = {"phy_obj_atk": "Phy_obj_atk", "phy_obj_atk_l0": "Phy_obj_atk_l0", "phy_obj_atk_l2": "Phy_obj_atk_l2",
+             "phy_obj_atk_vanila": "Phy_obj_atk_vanila", "phy_obj_atk_apgd": "Phy_obj_atk_APGD",
+             "phy_obj_atk_guassian": "Phy_obj_atk_guassian", "phy_obj_atk_arbi": "Phy_obj_atk_arbi",
+             "phy_obj_atk_square": "Phy_obj_atk_Square", "phy_obj_atk_light": "Phy_obj_atk_light"}
+    old = os.getcwd()
+    os.chdir(refload.M2_DIR)
+    try:
+        mods = {m: importlib.import_module("torchattacks.attacks." + m) for m in names}
+    finally:
+        os.chdir(old)
+    originals = {m: getattr(mods[m], c) for m, c in names.items()}
+    for m, c in names.items():
+        assert originals[m].__module__ == "torchattacks.attacks." + m, (m, originals[m].__module__)
+    done = dmh.install(mode="ops", dataset_root=ref.calib_root)
+    try:
+        for m, c in names.items():
+            assert done.get("torchattacks.attacks.%s.%s" % (m, c)), (m, sorted(done))
+            assert getattr(mods[m], c).__module__ == "depthmodelhardening_b200.attacks", m
+    finally:
+        dmh.uninstall()
+    for m, c in names.items():
+        assert getattr(mods[m], c) is originals[m], m
