@@ -78,6 +78,11 @@ SIGNATURES = {
                                   _f, _st]),
     "dmh_objective_finish_workspace_bytes": (_ll, [_i, _i]),
     "dmh_disp_grad": (_i, [_f, _f, _f, _fl, _f, _f, _f, _fl, _i, _i, _i, _i, _i, _f, _st]),
+    "dmh_smooth_fused_multi": (_i, [_i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _st]),
+    "dmh_disp_grad_multi": (_i, [_i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_float), _f, C.POINTER(C.c_void_p), _f, _fl, _i, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), _i, _i, C.POINTER(C.c_void_p), _st]),
     "dmh_compose_u8": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _f, _st]),
     "dmh_compose_patch_u8": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f, _f, _f, _st]),
     "dmh_lanczos_u8": (_i, [_f, _i, _i, _i, _i, _i, _f, _f, _i, _f, _f, _i, _f, _f, _f, _st]),
@@ -111,6 +116,8 @@ SIGNATURES = {
     "dmh_reduce_sum": (_i, [_f, _ll, _fl, _i, _f, _st]),
     "dmh_reduce_rows": (_i, [_f, _i, _ll, _fl, _f, _st]),
 }
+
+ERR_UNSUPPORTED = 3      # DMH_ERR_UNSUPPORTED: nothing was launched, the caller takes the general entry point
 
 _lib = None
 

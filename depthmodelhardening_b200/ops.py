@@ -449,6 +449,9 @@ MULTISOURCE = _os.environ.get("DMH_MULTISOURCE", "1") != "0"
 # development switch: the single-source objective through the multi-source kernel's persistent (tile, scale) item loop
 # (same bits as dmh_photo_multiscale; measured slower / faster: DESIGN.md section 7)
 SINGLE_VIA_MF = _os.environ.get("DMH_SINGLE_VIA_MF", "0") == "1"
+# glue steps of all scales in one launch each (csrc/objective_fused.cu: dmh_smooth_fused_multi = 2 launches instead of
+# 2 S, dmh_disp_grad_multi = 1 instead of S; identical outputs); DMH_GLUE_MULTI=0 keeps the per-scale launches
+GLUE_MULTI = _os.environ.get("DMH_GLUE_MULTI", "1") != "0"
 
 
 def _side_stream(dev, which=0):
@@ -545,10 +548,16 @@ class _Objective(torch.autograd.Function):
             gN.append(torch.empty(B, 1, h, w, device=dev, dtype=torch.float32))
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for s in range(S):
-                d = disps[s]
-                check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]), ptr(gN[s]),
-                                           stream()), "smooth_fused")
+            if GLUE_MULTI and S <= 8 and all(c.shape[1] == 3 for c in colors[:S]):
+                check(lib.dmh_smooth_fused_multi(S, ptr_array(disps), ptr_array(colors[:S]), B,
+                                                 (_C.c_int * S)(*[d.shape[2] for d in disps]),
+                                                 (_C.c_int * S)(*[d.shape[3] for d in disps]), ptr_array(wss),
+                                                 ptr_array(gN), stream()), "smooth_fused_multi")
+            else:
+                for s in range(S):
+                    d = disps[s]
+                    check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]),
+                                               ptr(gN[s]), stream()), "smooth_fused")
         # the per-scale launches are independent of each other: odd scales go to a second stream so that the
         # tail of one launch (10240 CTAs = 23.06 waves of 444) overlaps the head of the next
         multiscale = (packed and MULTISCALE and not split and S <= 4 and W % 4 == 0 and target.data_ptr() % 16 == 0
@@ -655,19 +664,33 @@ class _Objective(torch.autograd.Function):
         # four independent, short launches: alternate two streams so that their tails overlap
         dev = G[0].device
         cur, alt = torch.cuda.current_stream(dev), _side_stream(dev, 1)
-        alt.wait_stream(cur)
-        for s in range(S):
-            if not ctx.needs_input_grad[base + n_src + s]:
-                grads_disp.append(None)
-                continue
-            _, _, h, w = dshapes[s]
-            gd = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
-            with torch.cuda.stream(alt if (s & 1) else cur):
-                check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
-                                        ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
-                                        ptr(gd), stream()), "disp_grad")
-            grads_disp.append(gd.view(dshapes[s]))
-        cur.wait_stream(alt)
+        want = [bool(ctx.needs_input_grad[base + n_src + s]) for s in range(S)]
+        if GLUE_MULTI and all(want) and S <= 8:
+            # one launch for all scales; falls through to the per-scale launches when a scale needs the generic kernel
+            gds = [torch.empty(B, 1, dshapes[s][2], dshapes[s][3], device=dev, dtype=torch.float32) for s in range(S)]
+            rc = lib.dmh_disp_grad_multi(S, ptr_array(list(G)), ptr_array(list(gN)),
+                                         ptr_array([img_scalars[s] for s in range(S)]), (_C.c_float * S)(*smooth_w),
+                                         ptr(gt), ptr_array([gs[s:s + 1] for s in range(S)]) if gs is not None else None,
+                                         None, 1.0 / S, B, (_C.c_int * S)(*[sh_[2] for sh_ in dshapes]),
+                                         (_C.c_int * S)(*[sh_[3] for sh_ in dshapes]), H, W, ptr_array(gds), stream())
+            if rc == 0:
+                grads_disp = [gds[s].view(dshapes[s]) for s in range(S)]
+            elif rc != _lib.ERR_UNSUPPORTED:
+                check(rc, "disp_grad_multi")
+        if not grads_disp:
+            alt.wait_stream(cur)
+            for s in range(S):
+                if not want[s]:
+                    grads_disp.append(None)
+                    continue
+                _, _, h, w = dshapes[s]
+                gd = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
+                with torch.cuda.stream(alt if (s & 1) else cur):
+                    check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
+                                            ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
+                                            ptr(gd), stream()), "disp_grad")
+                grads_disp.append(gd.view(dshapes[s]))
+            cur.wait_stream(alt)
         g_T = [None] * n_src
         if need_T and ctx.gp_stacked:
             # multi-source kernel: sum over tiles and weighted sum over scales in one contraction, then the 4x4

@@ -276,6 +276,18 @@ int dmh_objective_finish(int S, int B, const float* const* smooth_ws_host, const
 int dmh_disp_grad(const float* G_full, const float* gN, const float* img_scalars, float smooth_weight,
                   const float* g_total, const float* g_scale, const float* g_smooth, float inv_S, int B, int h, int w,
                   int H, int W, float* grad_disp, dmh_stream_t stream);
+/* All-scales forms of the two glue steps (the `for scale in self.opt.scales` loop of M2/trainer.py:589-674 inside the
+ * launch): dmh_smooth_fused_multi = dmh_smooth_fused of S scales in two launches (3-channel images);
+ * dmh_disp_grad_multi = dmh_disp_grad of S scales in one launch (u_s = *g_total * inv_S + *g_scale_host[s]).
+ * *_host arrays are host arrays of length S.  Outputs identical to the per-scale entry points.
+ * dmh_disp_grad_multi returns DMH_ERR_UNSUPPORTED, with nothing launched, when a scale needs dmh_disp_grad's generic
+ * kernel (non-integer factor, factor outside {1,2,4,8}, unaligned rows).                                            */
+int dmh_smooth_fused_multi(int S, const float* const* disp_host, const float* const* img_host, int B, const int* h_host,
+                           const int* w_host, float* const* ws_host, float* const* gN_host, dmh_stream_t stream);
+int dmh_disp_grad_multi(int S, const float* const* G_full_host, const float* const* gN_host,
+                        const float* const* img_scalars_host, const float* smooth_weight_host, const float* g_total,
+                        const float* const* g_scale_host, const float* g_smooth, float inv_S, int B, const int* h_host,
+                        const int* w_host, int H, int W, float* const* grad_disp_host, dmh_stream_t stream);
 
 /* ======================= stage 1: physical patch attack ======================= */
 
