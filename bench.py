@@ -58,6 +58,9 @@ def parse_args():
                     help="batch slice of the CPU legs (0: cpu_baseline 8; --impl reference: adaptive, see reference_arm)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (sharded batch 32) sub-record")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-on-the-same-GPU baseline")
+    ap.add_argument("--strong-shard", type=int, default=0,
+                    help="N = 1 only: also time the step at the shard size of a K-GPU strong-scaling run (batch 32 / K "
+                         "items, no collective) -- sub-record strong_shard_emulation")
     ap.add_argument("--no-graph", action="store_true",
                     help="headline = the step launched from Python on one stream (default: CUDA-graph replay, two streams)")
     return ap.parse_args()
@@ -236,11 +239,18 @@ def timed_loop(fn, steps, warmup, world):
     return ms / steps
 
 
+def stage1_stream(device):
+    """The side stream stage 1 runs on beside stage 2.  High priority (DMH_S1_PRIORITY, default -1): stage 1 is a chain
+    of short kernels; at equal priority each of them queues behind every CTA of the photometric kernel that is not yet
+    resident (it fills all SMs for its whole run) and the chain ends long after stage 2 -- measured at 4 items per GPU."""
+    return torch.cuda.Stream(device=device, priority=int(os.environ.get("DMH_S1_PRIORITY", "-1")))
+
+
 def capture_step(s1, s2, device, lib, two_stream=True):
     """One step (stage 1 incl. its collective, stage 2 fwd+bwd) captured into a CUDA graph; returns (graph, number of
     this library's kernel launches inside one replay).  two_stream: stage 1 runs on a side stream beside stage 2."""
     cur = torch.cuda.current_stream()
-    side = torch.cuda.Stream(device=device)
+    side = stage1_stream(device)
     side.wait_stream(cur)
     with torch.cuda.stream(side):                          # warm-up off the capturing stream (allocator, lazy inits)
         for _ in range(3):
@@ -264,13 +274,14 @@ def capture_step(s1, s2, device, lib, two_stream=True):
     return graph, int(lib.dmh_launch_count() - n0)
 
 
-def measure_strong(args, rank, world, device, global_batch):
+def measure_strong(args, rank, world, device, global_batch, shard=1):
     """Strong scaling (north_star / SURVEY.md 8(e)): the batch-32 step with the batch SHARDED over the ranks.
     Same step as the headline (stage 1 + the one all-reduce + stage 2); timed eagerly and as a CUDA-graph replay of
-    the whole step (the all-reduce included): with 4 items per GPU the eager step is launch-bound."""
-    if global_batch % world != 0:
-        return {"error": "global batch %d not divisible by %d ranks" % (global_batch, world)}
-    Bs = global_batch // world
+    the whole step (the all-reduce included): with 4 items per GPU the eager step is launch-bound.
+    shard > 1 (world == 1): emulate the shard of a `shard`-GPU run on this GPU (no collective)."""
+    if global_batch % (world * shard) != 0:
+        return {"error": "global batch %d not divisible by %d ranks" % (global_batch, world * shard)}
+    Bs = global_batch // (world * shard)
     pb, pt = make_host_workload(Bs, rank, True)
     s2 = Stage2(pb, device)
     s1 = Stage1(pt, device, world, args.attack)
@@ -284,7 +295,7 @@ def measure_strong(args, rank, world, device, global_batch):
     out = {"global_batch": global_batch, "per_gpu_batch": Bs, "n_gpus": world, "ms_per_step_eager": ms_eager,
            "value_eager": global_batch * H * W / (ms_eager * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong"}
     cur = torch.cuda.current_stream()
-    side = torch.cuda.Stream(device=device)
+    side = stage1_stream(device)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         for _ in range(3):
@@ -948,6 +959,16 @@ def main():
             line["strong_scaling"] = measure_strong(args, rank, world, device, GLOBAL_BATCH)
         except Exception as exc:
             line["strong_scaling"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if world == 1 and args.strong_shard > 1 and s1 is not None:
+        try:
+            em = measure_strong(args, rank, 1, device, GLOBAL_BATCH, shard=args.strong_shard)
+            em["note"] = ("EMULATION on one GPU of the shard a %d-GPU strong-scaling run gives each rank (%d items), "
+                          "without the collective; the N-GPU numbers are the strong_scaling records of the N-GPU runs"
+                          % (args.strong_shard, GLOBAL_BATCH // args.strong_shard))
+            em["value"] = em["value_eager"] = em["value_two_stream"] = None
+            line["strong_shard_emulation"] = em
+        except Exception as exc:
+            line["strong_shard_emulation"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if world == 1 and not args.no_strong and s1 is not None:
         try:
             line["multisource"] = measure_multisource(args, device, B)

@@ -8,6 +8,8 @@ contain isolated pixels where the sampling coordinate sits within 1 ulp of an
 integer (floor() picks the other tap pair): those are
 bounded by `max_outlier_frac`.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -620,6 +622,40 @@ def test_multiscale_kernel_is_bit_identical_to_per_scale(dev, hw):
     _assert_same_bits(ref, got)
     ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes[:3], seed=86, noise=False, automask=False)   # S = 3, automask off
     _assert_same_bits(ref, got)
+
+
+def _pair_check():
+    """Body of test_multiscale_pair_variant_matches_per_scale (own process: DMH_MS_PAIR is read once per process)."""
+    dev = torch.device("cuda:0")
+    cases = [((64, 96), None, 2, 81), ((40, 72), None, 2, 82), ((96, 160), None, 2, 83), ((72, 200), None, 1, 84),
+             ((320, 1024), None, 2, 91)]
+    for (H, W), dsizes, B, seed in cases:
+        dsizes = dsizes or [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
+        for kw in ({}, {"noise": False, "automask": False}):
+            ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes, B=B, seed=seed, **kw)
+            nfast = B * ((H + 31) // 32) * ((W + 31) // 32)
+            for s_, ((rp, rg, rs), (gp, gg, gs_)) in enumerate(zip(ref, got)):
+                assert torch.equal(rs, gs_), "scale %d: argmin differs" % s_
+                # same values (a coefficient that is gated off may be -0 instead of +0: equal as floats)
+                assert torch.equal(rg, gg), "scale %d: %d gradient values differ" % (s_, int((rg != gg).sum()))
+                assert float(gg.abs().max()) > 0
+                # tile loss sums: same per-pixel values added in a different order; the tail reads as zero
+                assert torch.allclose(rp[:nfast], gp[:nfast], rtol=2e-6, atol=0.0)
+                assert not gp[nfast:].any()
+    print("PAIR_OK")
+
+
+@pytest.mark.parametrize("rows", [3, 4, 5])
+def test_multiscale_pair_variant_matches_per_scale(dev, rows):
+    """photo_ms_kernel<..., PAIR = rows> (phase B over column pairs, channel 2 packed across the pair, interleaved tiles;
+    DMH_MS_PAIR) against the per-scale kernel: identical argmin, equal gradients, tile loss sums to 2e-6."""
+    import subprocess
+    import sys
+    env = dict(os.environ, DMH_MS_PAIR=str(rows))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import tests.test_gpu_photometric as t; t._pair_check()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PAIR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_multiscale_kernel_full_size_is_bit_identical(dev):
