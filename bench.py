@@ -240,10 +240,11 @@ def timed_loop(fn, steps, warmup, world):
 
 
 def stage1_stream(device):
-    """The side stream stage 1 runs on beside stage 2.  High priority (DMH_S1_PRIORITY, default -1): stage 1 is a chain
-    of short kernels; at equal priority each of them queues behind every CTA of the photometric kernel that is not yet
-    resident (it fills all SMs for its whole run) and the chain ends long after stage 2 -- measured at 4 items per GPU."""
-    return torch.cuda.Stream(device=device, priority=int(os.environ.get("DMH_S1_PRIORITY", "-1")))
+    """The side stream stage 1 runs on beside stage 2 (DMH_S1_PRIORITY, default 0 = the priority of stage 2's stream).
+    Measured on one box (profiles/r02_kernel_ab.txt, block r3a): a high-priority stage-1 stream is SLOWER -- 1.877 vs
+    1.866 ms at 32 items, 0.2845 vs 0.2753 ms at 4 items per GPU: stage 1's short kernels then displace CTAs of the
+    photometric kernel, which is the critical path, instead of filling its tail."""
+    return torch.cuda.Stream(device=device, priority=int(os.environ.get("DMH_S1_PRIORITY", "0")))
 
 
 def capture_step(s1, s2, device, lib, two_stream=True):

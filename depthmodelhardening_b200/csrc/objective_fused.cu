@@ -570,7 +570,7 @@ struct DgScale {
     const float* g_scale;
     float* grad;
     float smooth_weight, sh, sw;
-    int h, w, R, gx, gy;         // R == 1: gx = blocks of 256 float4 per image, gy unused
+    int h, w, R, gx, gy;         // R == 1: gx = blocks of 1024 float4 per image, gy unused
     int blk0;
 };
 struct DgMultiParams {
@@ -592,10 +592,14 @@ disp_grad_multi_kernel(const __grid_constant__ DgMultiParams p) {
     const int r = blk - c.blk0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (c.R == 1) {
+        // four 128-bit chunks per thread (the all-scales kernel is register-capped by its up-sampling branches: fewer
+        // resident threads than the per-scale streaming kernel, so each keeps more loads in flight)
         const int b = r / c.gx, bx = r - b * c.gx;
-        disp_grad_same_body(reinterpret_cast<const float4*>(c.G), reinterpret_cast<const float4*>(c.gN), c.img_scalars,
-                            c.smooth_weight, p.g_total, c.g_scale, p.g_smooth, p.inv_S, (c.h * c.w) >> 2,
-                            reinterpret_cast<float4*>(c.grad), bx * 256 + (int)threadIdx.x, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            disp_grad_same_body(reinterpret_cast<const float4*>(c.G), reinterpret_cast<const float4*>(c.gN), c.img_scalars,
+                                c.smooth_weight, p.g_total, c.g_scale, p.g_smooth, p.inv_S, (c.h * c.w) >> 2,
+                                reinterpret_cast<float4*>(c.grad), bx * 1024 + j * 256 + (int)threadIdx.x, b);
         return;
     }
     const int per = c.gx * c.gy;
@@ -893,7 +897,7 @@ int dmh_disp_grad_multi(int S, const float* const* G_full_host, const float* con
         c.g_scale = g_scale_host ? g_scale_host[s] : nullptr; c.grad = grad_disp_host[s];
         c.smooth_weight = smooth_weight_host[s]; c.sh = (float)h / (float)H; c.sw = (float)w / (float)W;
         c.h = h; c.w = w; c.R = R;
-        if (R == 1) { c.gx = ceil_div((int)(((size_t)h * w) / 4), 256); c.gy = 1; }
+        if (R == 1) { c.gx = ceil_div((int)(((size_t)h * w) / 4), 1024); c.gy = 1; }
         else { c.gx = ceil_div(w, 32); c.gy = ceil_div(h, 64 / R); }
         c.blk0 = (int)blocks;
         blocks += (long long)c.gx * c.gy * B;

@@ -328,183 +328,11 @@ __device__ __forceinline__ float phase_b(const P& p, const TileSmem& sm, int tid
     return loss_local;
 }
 
-// ---- phase B over COLUMN PAIRS (photo_ms_kernel<..., PAIR>): a thread owns two adjacent ring columns and 3 ring rows.
-// Three packed streams -- (ch0, ch1) of the left column, (ch0, ch1) of the right column, (ch2 left, ch2 right) -- so
-// channel 2, scalar in phase_b (as many instructions as the packed pair beside it), rides in a packed register too:
-// 3 packed streams per two windows instead of 2 packed + 2 scalar.  The two windows share 2 of their 3 columns: the
-// warped tile AND the target tile are read from an INTERLEAVED layout (first two planes = [rows][pitch] float2 of channels
-// 0 / 1, third plane = channel 2; the target is re-laid once per tile after its TMA load) with two 128-bit + two 64-bit
-// loads per row and tile (9 scalar loads each in phase_b): every packed operand arrives as an aligned register pair, no
-// register shuffles.  Every value is produced
-// by the same rounded operation sequence as in phase_b (the lane type of the dmh_math.cuh templates is float2 for all
-// three streams): coefficient planes, argmin and therefore the gradients are bit-identical; the tile's loss sum adds the
-// same per-pixel values in a different order.
-// NR = ring rows per thread (template parameter): 3 -> 12 strips, 204 threads; 4 -> 9 strips, 153 threads; 5 -> 7, 119
-#define FT_PB_PAIRS (FT_R1 / 2)                              // 17 column pairs
-#define FT_PB_STRIPS(NR) ((FT_R1 + (NR) - 1) / (NR))
-#define FT_PB_THREADS(NR) (FT_PB_PAIRS * FT_PB_STRIPS(NR))
-
-// identity loss / tie-break noise of this thread's 3 x 2 ring pixels, raw (added at the end of the gather phase):
-// index 2 * k + j = ring row strip * 3 + k, ring column 2 * pair + j.  +inf where the pixel exists but automasking is
-// off, NaN outside the image / the ring.
-template <int NR, class P>
-__device__ __forceinline__ void ident_loads_pair(const P& p, int tid, int b, int x0, int y0, float (&ia)[2 * NR],
-                                                 float (&na)[2 * NR]) {
-    const int H = p.H, W = p.W, N = H * W;
-    const int cp = tid % FT_PB_PAIRS, strip = tid / FT_PB_PAIRS;
-    const bool has_ident = p.ident != nullptr;
-    const float* idp = p.ident + (size_t)b * N;
-    const float* nzp = p.noise + (size_t)b * N;
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-        const int qr = strip * NR + k, qy = y0 - 1 + qr;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int qx = x0 - 1 + 2 * cp + j;
-            const bool ok = tid < FT_PB_THREADS(NR) && qr < FT_R1 && qy >= 0 && qy < H && qx >= 0 && qx < W;
-            ia[2 * k + j] = ok ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);
-            na[2 * k + j] = 0.0f;
-            if (ok && has_ident) {
-                ia[2 * k + j] = __ldg(idp + qy * W + qx);
-                if (p.noise) na[2 * k + j] = __ldg(nzp + qy * W + qx);
-            }
-        }
-    }
-}
-
-// two consecutive shared-memory floats at an ODD offset (no 64-bit load) straight into a register pair.  Taking the
-// halves out of the neighbouring 64-bit loads instead costs two register moves per USE: the packed-fp32 wrappers of
-// dmh_math.cuh pack their float2 operands per use, which is free only when the halves already sit in an aligned pair.
-__device__ __forceinline__ float2 lds_pair(const float* p) {
-    float2 r;
-    const uint32_t a = smem_u32(p);
-    asm volatile("ld.volatile.shared.f32 %0, [%2];\n\tld.volatile.shared.f32 %1, [%2+4];" : "=f"(r.x), "=f"(r.y) : "r"(a));
-    return r;
-}
-
-template <int NR, class P>
-__device__ __forceinline__ float phase_b_pair(const P& p, const TileSmem& sm, int tid, int b, int x0, int y0,
-                                              const float (&idv_pre)[2 * NR]) {
-    const int W = p.W, N = p.H * p.W;
-    const float w_ssim = 0.85f / 3.0f;
-    const int cp = tid % FT_PB_PAIRS, strip = tid / FT_PB_PAIRS;
-    const bool has_ident = p.ident != nullptr;
-    const float* tgt = sm.tgt;
-    const float2* tgtP = reinterpret_cast<const float2*>(sm.tgt);       // [36][40] (ch0, ch1); plane 2 = ch2 in place
-    const float2* predP = reinterpret_cast<const float2*>(sm.pred);
-    const float* pred2 = sm.pred + 2 * FT_N2;
-    float4* coefQ1 = sm.q1;
-    float4* coefQ2 = sm.q2;
-    float* coefQ3 = sm.q3;
-    uint8_t* gate = sm.gate;
-    float loss_local = 0.0f;
-    if (tid < FT_PB_THREADS(NR)) {
-        const int r0 = strip * NR;              // first ring row of this strip == first R2 row of its window
-        const int c0 = 2 * cp;                          // left ring column == first R2 column of its window
-        Row5T<float2> hA[2], hB[2], hC[2];              // [older, newer] row sums: left (ch0,ch1), right (ch0,ch1), ch2 (l,r)
-        float2 cxA, cyA, cxB, cyB, cxC, cyC;            // centre values of the previous row
-#pragma unroll
-        for (int rr = 0; rr < NR + 2; ++rr) {
-            const int r2 = min(r0 + rr, FT_R2 - 1);     // R2 row being added
-            const float4 xp01 = *reinterpret_cast<const float4*>(predP + r2 * FT_R2 + c0);
-            const float4 xp23 = *reinterpret_cast<const float4*>(predP + r2 * FT_R2 + c0 + 2);
-            const float2 xs01 = *reinterpret_cast<const float2*>(pred2 + r2 * FT_R2 + c0);
-            const float2 xs23 = *reinterpret_cast<const float2*>(pred2 + r2 * FT_R2 + c0 + 2);
-            const int yi = r2 * FT_TP + c0 + FT_TO;
-            const float4 yp01 = *reinterpret_cast<const float4*>(tgtP + yi);
-            const float4 yp23 = *reinterpret_cast<const float4*>(tgtP + yi + 2);
-            const float2 ys01 = *reinterpret_cast<const float2*>(tgt + 2 * FT_NT + yi);
-            const float2 ys23 = *reinterpret_cast<const float2*>(tgt + 2 * FT_NT + yi + 2);
-            const float2 y0v = make_float2(yp01.x, yp01.y), y1v = make_float2(yp01.z, yp01.w),
-                         y2v = make_float2(yp23.x, yp23.y), y3v = make_float2(yp23.z, yp23.w);
-            const float2 x0v = make_float2(xp01.x, xp01.y), x1v = make_float2(xp01.z, xp01.w),
-                         x2v = make_float2(xp23.x, xp23.y), x3v = make_float2(xp23.z, xp23.w);
-            const float2 xmC = lds_pair(pred2 + r2 * FT_R2 + c0 + 1), ymC = lds_pair(tgt + 2 * FT_NT + yi + 1);
-            const Row5T<float2> curA = row5(x0v, x1v, x2v, y0v, y1v, y2v);
-            const Row5T<float2> curB = row5(x1v, x2v, x3v, y1v, y2v, y3v);
-            const Row5T<float2> curC = row5(xs01, xmC, xs23, ys01, ymC, ys23);
-            if (rr >= 2) {
-                const int qr = r0 + rr - 2;             // ring row of the window centres
-                // Per stream: statistics -> value -> coefficients, gated by the clamp only (g = w_ssim * pass, the value g
-                // takes wherever the reprojection wins), so that the statistics die before the decision; the decision then
-                // multiplies the coefficients by 1 or 0 (exact: the same values as gating g itself, up to the sign of a
-                // zero coefficient).
-                const float2 wss = make_float2(w_ssim, w_ssim);
-                float2 vA, kaA, kbA, kcA, vB, kaB, kbB, kcB, vC, kaC, kbC, kcC;
-                {
-                    const SsimStatsT<float2> st = ssim_stats_rows_t(hA[0], hA[1], curA);
-                    float2 pass, r, nr;
-                    vA = ssim_value_t(st, pass, r, nr);
-                    ssim_coef_gated_t(st, r, nr, vmul(wss, pass), kaA, kbA, kcA);
-                }
-                {
-                    const SsimStatsT<float2> st = ssim_stats_rows_t(hB[0], hB[1], curB);
-                    float2 pass, r, nr;
-                    vB = ssim_value_t(st, pass, r, nr);
-                    ssim_coef_gated_t(st, r, nr, vmul(wss, pass), kaB, kbB, kcB);
-                }
-                {
-                    const SsimStatsT<float2> st = ssim_stats_rows_t(hC[0], hC[1], curC);
-                    float2 pass, r, nr;
-                    vC = ssim_value_t(st, pass, r, nr);
-                    ssim_coef_gated_t(st, r, nr, vmul(wss, pass), kaC, kbC, kcC);
-                }
-                float l1a = fabsf(cyA.x - cxA.x);
-                l1a += fabsf(cyA.y - cxA.y);
-                l1a += fabsf(cyC.x - cxC.x);
-                float l1b = fabsf(cyB.x - cxB.x);
-                l1b += fabsf(cyB.y - cxB.y);
-                l1b += fabsf(cyC.y - cxC.y);
-                const float ssa = (vA.x + vA.y) + vC.x, ssb = (vB.x + vB.y) + vC.y;
-                l1a *= (1.0f / 3.0f);
-                l1b *= (1.0f / 3.0f);
-                const float rpa = fmaf(0.85f, ssa * (1.0f / 3.0f), 0.15f * l1a);
-                const float rpb = fmaf(0.85f, ssb * (1.0f / 3.0f), 0.15f * l1b);
-                const float idva = idv_pre[2 * (rr - 2)], idvb = idv_pre[2 * (rr - 2) + 1];
-                const bool wina = rpa < idva, winb = rpb < idvb;     // torch.min: first minimum wins, identity is first
-                const bool ina = idva == idva, inb = idvb == idvb;   // (NaN marks ring pixels outside the image)
-                const float ma = wina ? 1.0f : 0.0f, mb = winb ? 1.0f : 0.0f;
-                const float2 mA = make_float2(ma, ma), mB = make_float2(mb, mb), mC = make_float2(ma, mb);
-                kaA = vmul(kaA, mA); kbA = vmul(kbA, mA); kcA = vmul(kcA, mA);
-                kaB = vmul(kaB, mB); kbB = vmul(kbB, mB); kcB = vmul(kcB, mB);
-                kaC = vmul(kaC, mC); kbC = vmul(kbC, mC); kcC = vmul(kcC, mC);
-                if (qr < FT_R1) {
-                    const int qi = qr * FT_R1 + c0;
-                    coefQ1[qi] = make_float4(kaA.x, kaA.y, kbA.x, kbA.y);
-                    coefQ1[qi + 1] = make_float4(kaB.x, kaB.y, kbB.x, kbB.y);
-                    coefQ2[qi] = make_float4(kcA.x, kcA.y, kaC.x, kbC.x);
-                    coefQ2[qi + 1] = make_float4(kcB.x, kcB.y, kaC.y, kbC.y);
-                    *reinterpret_cast<float2*>(coefQ3 + qi) = kcC;
-                    *reinterpret_cast<uchar2*>(gate + qi) = make_uchar2(wina ? 1 : 0, winb ? 1 : 0);
-                }
-                if (qr >= 1 && qr <= FT_T) {
-                    const int qo = (y0 - 1 + qr) * W + x0 - 1 + c0;
-                    if (cp >= 1 && ina) {                       // left column: ring columns 2 .. 32
-                        loss_local += wina ? rpa : idva;
-                        if (p.sel) p.sel[(size_t)b * N + qo] = (uint8_t)((wina && has_ident) ? 1 : 0);
-                    }
-                    if (cp < FT_PB_PAIRS - 1 && inb) {          // right column: ring columns 1 .. 31
-                        loss_local += winb ? rpb : idvb;
-                        if (p.sel) p.sel[(size_t)b * N + qo + 1] = (uint8_t)((winb && has_ident) ? 1 : 0);
-                    }
-                }
-            }
-            hA[0] = hA[1]; hA[1] = curA;
-            hB[0] = hB[1]; hB[1] = curB;
-            hC[0] = hC[1]; hC[1] = curC;
-            cxA = x1v; cyA = y1v; cxB = x2v; cyB = y2v; cxC = xmC; cyC = ymC;
-        }
-    }
-    return loss_local;
-}
-
 // ---- phase C of the tile kernels: separable weighted box sums of the coefficient planes -> d/d(pred) -> d/d(disp).
 // `tid` < 256 owns column tid%32, rows 4*(tid/32)+k of the tile; D = d(pred_ch)/d(disp) of those 4 pixels.
 // DH: the proxy loss of the depth hints, log(|hint - depth| + 1) * valid where the hint won (bit 1 of the gate byte),
 // its masked sums (acc[2], acc[3]) and its gradient map, for the same 4 pixels.
-// IL: channels 0 and 1 of the warped tile and of the target tile are interleaved (float2 over the first two planes, see
-// phase_b_pair)
-template <bool DH, bool UP, bool IL = false, class P>
+template <bool DH, bool UP, class P>
 __device__ __forceinline__ void phase_c(const P& p, const TileSmem& sm, int tid, int b, int x0, int y0,
                                         const float (&D)[4][3], float (&acc)[4], float (*gp_out)[3] = nullptr,
                                         float* g_acc = nullptr, const float (*xv_in)[3] = nullptr) {
@@ -576,9 +404,8 @@ __device__ __forceinline__ void phase_c(const P& p, const TileSmem& sm, int tid,
                 const float2 sab2 = vfma(wu2, hprev[0][3], vfma(wd2, hc[3], hprev[1][3]));
                 const float scS = fmaf(wu, hprevC[0], fmaf(wd, hcC, hprevC[1]));
                 // (multi-source kernel: the warped values of an earlier source come back from its scratch, xv_in)
-                const float2 xvP = xv_in ? make_float2(xv_in[k][0], xv_in[k][1])
-                                         : (IL ? reinterpret_cast<const float2*>(pred)[i2] : make_float2(pred[i2], pred[FT_N2 + i2]));
-                const float2 yvP = IL ? reinterpret_cast<const float2*>(tgt)[it] : make_float2(tgt[it], tgt[FT_NT + it]);
+                const float2 xvP = xv_in ? make_float2(xv_in[k][0], xv_in[k][1]) : make_float2(pred[i2], pred[FT_N2 + i2]);
+                const float2 yvP = make_float2(tgt[it], tgt[FT_NT + it]);
                 const float xvS = xv_in ? xv_in[k][2] : pred[2 * FT_N2 + i2], yvS = tgt[2 * FT_NT + it];
                 const float2 dP = vsub(xvP, yvP);
                 const float dS = xvS - yvS;

@@ -449,9 +449,14 @@ MULTISOURCE = _os.environ.get("DMH_MULTISOURCE", "1") != "0"
 # development switch: the single-source objective through the multi-source kernel's persistent (tile, scale) item loop
 # (same bits as dmh_photo_multiscale; measured slower / faster: DESIGN.md section 7)
 SINGLE_VIA_MF = _os.environ.get("DMH_SINGLE_VIA_MF", "0") == "1"
-# glue steps of all scales in one launch each (csrc/objective_fused.cu: dmh_smooth_fused_multi = 2 launches instead of
-# 2 S, dmh_disp_grad_multi = 1 instead of S; identical outputs); DMH_GLUE_MULTI=0 keeps the per-scale launches
-GLUE_MULTI = _os.environ.get("DMH_GLUE_MULTI", "1") != "0"
+# glue steps of all scales in one launch (csrc/objective_fused.cu; identical outputs):
+#   DMH_SMOOTH_MULTI   dmh_smooth_fused_multi: 2 launches instead of 2 S
+#   DMH_DGRAD_MULTI    dmh_disp_grad_multi: 1 launch instead of S (two streams)
+SMOOTH_MULTI = _os.environ.get("DMH_SMOOTH_MULTI", "1") != "0"
+DGRAD_MULTI = _os.environ.get("DMH_DGRAD_MULTI", "0") != "0"
+
+
+_SMOOTH_PRIORITY = int(_os.environ.get("DMH_SMOOTH_PRIORITY", "-1"))    # development switch
 
 
 def _side_stream(dev, which=0):
@@ -460,7 +465,7 @@ def _side_stream(dev, which=0):
     key = (idx, which)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx, priority=-1 if which == 0 else 0)
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx, priority=_SMOOTH_PRIORITY if which == 0 else 0)
     return st
 
 
@@ -548,7 +553,7 @@ class _Objective(torch.autograd.Function):
             gN.append(torch.empty(B, 1, h, w, device=dev, dtype=torch.float32))
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            if GLUE_MULTI and S <= 8 and all(c.shape[1] == 3 for c in colors[:S]):
+            if SMOOTH_MULTI and S <= 8 and all(c.shape[1] == 3 for c in colors[:S]):
                 check(lib.dmh_smooth_fused_multi(S, ptr_array(disps), ptr_array(colors[:S]), B,
                                                  (_C.c_int * S)(*[d.shape[2] for d in disps]),
                                                  (_C.c_int * S)(*[d.shape[3] for d in disps]), ptr_array(wss),
@@ -665,7 +670,7 @@ class _Objective(torch.autograd.Function):
         dev = G[0].device
         cur, alt = torch.cuda.current_stream(dev), _side_stream(dev, 1)
         want = [bool(ctx.needs_input_grad[base + n_src + s]) for s in range(S)]
-        if GLUE_MULTI and all(want) and S <= 8:
+        if DGRAD_MULTI and all(want) and S <= 8:
             # one launch for all scales; falls through to the per-scale launches when a scale needs the generic kernel
             gds = [torch.empty(B, 1, dshapes[s][2], dshapes[s][3], device=dev, dtype=torch.float32) for s in range(S)]
             rc = lib.dmh_disp_grad_multi(S, ptr_array(list(G)), ptr_array(list(gN)),

@@ -624,40 +624,6 @@ def test_multiscale_kernel_is_bit_identical_to_per_scale(dev, hw):
     _assert_same_bits(ref, got)
 
 
-def _pair_check():
-    """Body of test_multiscale_pair_variant_matches_per_scale (own process: DMH_MS_PAIR is read once per process)."""
-    dev = torch.device("cuda:0")
-    cases = [((64, 96), None, 2, 81), ((40, 72), None, 2, 82), ((96, 160), None, 2, 83), ((72, 200), None, 1, 84),
-             ((320, 1024), None, 2, 91)]
-    for (H, W), dsizes, B, seed in cases:
-        dsizes = dsizes or [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
-        for kw in ({}, {"noise": False, "automask": False}):
-            ref, got = _per_scale_vs_multiscale(dev, H, W, dsizes, B=B, seed=seed, **kw)
-            nfast = B * ((H + 31) // 32) * ((W + 31) // 32)
-            for s_, ((rp, rg, rs), (gp, gg, gs_)) in enumerate(zip(ref, got)):
-                assert torch.equal(rs, gs_), "scale %d: argmin differs" % s_
-                # same values (a coefficient that is gated off may be -0 instead of +0: equal as floats)
-                assert torch.equal(rg, gg), "scale %d: %d gradient values differ" % (s_, int((rg != gg).sum()))
-                assert float(gg.abs().max()) > 0
-                # tile loss sums: same per-pixel values added in a different order; the tail reads as zero
-                assert torch.allclose(rp[:nfast], gp[:nfast], rtol=2e-6, atol=0.0)
-                assert not gp[nfast:].any()
-    print("PAIR_OK")
-
-
-@pytest.mark.parametrize("rows", [3, 4, 5])
-def test_multiscale_pair_variant_matches_per_scale(dev, rows):
-    """photo_ms_kernel<..., PAIR = rows> (phase B over column pairs, channel 2 packed across the pair, interleaved tiles;
-    DMH_MS_PAIR) against the per-scale kernel: identical argmin, equal gradients, tile loss sums to 2e-6."""
-    import subprocess
-    import sys
-    env = dict(os.environ, DMH_MS_PAIR=str(rows))
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", "import tests.test_gpu_photometric as t; t._pair_check()"], cwd=root, env=env,
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "PAIR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
-
-
 def test_multiscale_kernel_full_size_is_bit_identical(dev):
     """The benchmarked configuration's shape (1024 x 320, 4 scales; B = 3) -- the instantiation bench.py times."""
     H, W = 320, 1024
@@ -797,16 +763,17 @@ def test_glue_multi_launches_are_bit_identical_to_per_scale(dev, hw, B):
 
 @pytest.mark.parametrize("shape", [(2, 96, 160), (2, 320, 1024), (2, 50, 70)])
 def test_objective_glue_switch_is_bit_identical(dev, shape):
-    """ops.objective with the all-scales glue launches (default) against DMH_GLUE_MULTI=0: identical losses and disparity
-    gradients through the public autograd path (the 50 x 70 case falls back to per-scale backward launches)."""
+    """ops.objective with the all-scales glue launches (DMH_SMOOTH_MULTI / DMH_DGRAD_MULTI) against the per-scale
+    launches: identical losses and disparity gradients through the public autograd path (the 50 x 70 case falls back
+    to per-scale backward launches)."""
     from depthmodelhardening_b200 import objective, ops
     B, H, W = shape
     scales = (0, 1, 2, 3) if H % 8 == 0 and W % 8 == 0 else (0, 1)
     g = synth.photo_batch(batch=B, height=H, width=W, frame_ids=(0, "s"), scales=scales, seed=95).to(dev)
     res = []
     for multi in (True, False):
-        old = ops.GLUE_MULTI
-        ops.GLUE_MULTI = multi
+        old = (ops.SMOOTH_MULTI, ops.DGRAD_MULTI)
+        ops.SMOOTH_MULTI = ops.DGRAD_MULTI = multi
         try:
             disps = {s: g.disp[s].clone().requires_grad_(True) for s in g.scales}
             losses, _ = objective.photometric_losses(g.color, disps, g.K, g.inv_K, g.T, g.frame_ids, g.scales, g.height,
@@ -814,7 +781,7 @@ def test_objective_glue_switch_is_bit_identical(dev, shape):
             losses["loss"].backward()
             res.append((losses["loss"].detach().clone(), [disps[s].grad.clone() for s in g.scales]))
         finally:
-            ops.GLUE_MULTI = old
+            ops.SMOOTH_MULTI, ops.DGRAD_MULTI = old
     torch.cuda.synchronize()
     assert torch.equal(res[0][0], res[1][0])
     for a, b_ in zip(res[0][1], res[1][1]):
