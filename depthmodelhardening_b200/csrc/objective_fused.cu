@@ -120,6 +120,8 @@ __device__ __forceinline__ void load_px4(const float* __restrict__ row, int x, i
     }
 }
 
+// (Every product-sum below is written with an explicit rounding sequence -- mul_rn / fmaf -- so that the per-scale and
+// the all-scales instantiation of this body cannot differ by the compiler's FMA contraction choices: measured, they did.)
 // A16 forward + gradient w.r.t. the normalised disparity.  A lane owns 4 consecutive pixels of a row and
 // walks down SF_RPW rows keeping the previous row in registers, so every disparity / colour value is loaded
 // once per warp (128-bit loads) plus one row of overlap above and below; the edge weight exp(-mean_c|dI|)
@@ -183,10 +185,10 @@ __device__ __forceinline__ void sf_main_body(const float* __restrict__ disp, con
 #pragma unroll
             for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - in_[c][j]);
             const float e = edge_weight(sabs, nicl);
-            const float diff = dc[j] * inv_m - dn_[j] * inv_m;
+            const float diff = sub_rn(mul_rn(dc[j], inv_m), mul_rn(dn_[j], inv_m));
             const bool ok = row_ok && below_ok && x + j < w;
             gy[j] = ok ? sgn(diff) * e : 0.f;
-            if (r >= 0 && ok) sum_y += fabsf(diff) * e;
+            if (r >= 0 && ok) sum_y = fmaf(fabsf(diff), e, sum_y);
         }
         if (r >= 0) {
             // right neighbour of pixel 3: lane+1's pixel 0, or (lane 31) the first pixel of the next tile
@@ -206,10 +208,10 @@ __device__ __forceinline__ void sf_main_body(const float* __restrict__ disp, con
 #pragma unroll
                 for (int c = 0; c < C; ++c) sabs += fabsf(ic[c][j] - (j < 3 ? ic[c][j + 1] : ir[c]));
                 const float e = edge_weight(sabs, nicl);
-                const float diff = dc[j] * inv_m - (j < 3 ? dc[j + 1] : dr) * inv_m;
+                const float diff = sub_rn(mul_rn(dc[j], inv_m), mul_rn(j < 3 ? dc[j + 1] : dr, inv_m));
                 const bool ok = row_ok && x + j < w - 1;
                 gx[j] = ok ? sgn(diff) * e : 0.f;
-                if (ok) sum_x += fabsf(diff) * e;
+                if (ok) sum_x = fmaf(fabsf(diff), e, sum_x);
             }
             // x-edge owned by the pixel left of pixel 0: lane-1's gx[3], or (lane 0) recomputed across the tile border
             float gl = __shfl_up_sync(0xffffffffu, gx[3], 1);
@@ -219,7 +221,7 @@ __device__ __forceinline__ void sf_main_body(const float* __restrict__ disp, con
                     float sabs = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; ++c) sabs += fabsf(__ldg(im + (size_t)c * hw + (size_t)y * w + xl) - ic[c][0]);
-                    const float diff = __ldg(d + (size_t)y * w + xl) * inv_m - dc[0] * inv_m;
+                    const float diff = sub_rn(mul_rn(__ldg(d + (size_t)y * w + xl), inv_m), mul_rn(dc[0], inv_m));
                     gl = sgn(diff) * edge_weight(sabs, nicl);
                 }
             }
@@ -227,8 +229,8 @@ __device__ __forceinline__ void sf_main_body(const float* __restrict__ disp, con
                 float g[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    g[j] = (gx[j] - (j > 0 ? gx[j - 1] : gl)) * inv_nx + (gy[j] - gy_up[j]) * inv_ny;
-                    if (x + j < w) sum_g += g[j] * dc[j];
+                    g[j] = fmaf(gx[j] - (j > 0 ? gx[j - 1] : gl), inv_nx, mul_rn(gy[j] - gy_up[j], inv_ny));
+                    if (x + j < w) sum_g = fmaf(g[j], dc[j], sum_g);
                 }
                 float* go = gN + (size_t)b * hw + (size_t)y * w + x;
                 if (vok && x + 3 < w) {
@@ -500,7 +502,7 @@ __device__ __forceinline__ void disp_grad_up_body(const float* __restrict__ G_fu
     }
     __syncthreads();
     if (x >= w) return;
-    const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
+    const float up = add_rn(g_total ? mul_rn(g_total[0], inv_S) : 0.0f, g_scale ? g_scale[0] : 0.0f);
     float inv_m = 0.f, corr = 0.f;
     if (gN) { inv_m = img_scalars[b * 2]; corr = img_scalars[b * 2 + 1]; }
 #pragma unroll
@@ -511,8 +513,8 @@ __device__ __forceinline__ void disp_grad_up_body(const float* __restrict__ G_fu
 #pragma unroll
         for (int j = 0; j < RW; ++j) acc = fmaf(s_wy[ly][j], s_h[R * ly + j][lane], acc);
         const size_t o = (size_t)b * h * w + (size_t)y * w + x;
-        const float sm = gN ? smooth_weight * (gN[o] * inv_m - corr) : 0.0f;
-        grad[o] = g_smooth ? fmaf(g_smooth[0], sm, up * acc) : up * (acc + sm);
+        const float sm = gN ? mul_rn(smooth_weight, fmaf(gN[o], inv_m, -corr)) : 0.0f;
+        grad[o] = g_smooth ? fmaf(g_smooth[0], sm, mul_rn(up, acc)) : mul_rn(up, add_rn(acc, sm));
     }
 }
 
@@ -534,7 +536,7 @@ __device__ __forceinline__ void disp_grad_same_body(const float4* __restrict__ G
                                                     const float* __restrict__ g_smooth, float inv_S, int n4,
                                                     float4* __restrict__ grad4, int i, int b) {
     if (i >= n4) return;
-    const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
+    const float up = add_rn(g_total ? mul_rn(g_total[0], inv_S) : 0.0f, g_scale ? g_scale[0] : 0.0f);
     const size_t o = (size_t)b * n4 + i;
     const float4 a = __ldg(G4 + o);
     float acc[4] = {a.x, a.y, a.z, a.w}, sm[4] = {0.f, 0.f, 0.f, 0.f}, out[4];
@@ -543,11 +545,11 @@ __device__ __forceinline__ void disp_grad_same_body(const float4* __restrict__ G
         const float4 n = __ldg(gN4 + o);
         const float nv[4] = {n.x, n.y, n.z, n.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sm[j] = smooth_weight * (nv[j] * inv_m - corr);
+        for (int j = 0; j < 4; ++j) sm[j] = mul_rn(smooth_weight, fmaf(nv[j], inv_m, -corr));
     }
     const float gsm = g_smooth ? g_smooth[0] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = g_smooth ? fmaf(gsm, sm[j], up * acc[j]) : up * (acc[j] + sm[j]);
+    for (int j = 0; j < 4; ++j) out[j] = g_smooth ? fmaf(gsm, sm[j], mul_rn(up, acc[j])) : mul_rn(up, add_rn(acc[j], sm[j]));
     grad4[o] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
@@ -625,7 +627,7 @@ disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
     const bool in = x < w && y < h;
     if (R <= 1 && !in) return;                            // (R > 1: every thread works on the tile)
     const int b = blockIdx.z;
-    const float up = (g_total ? g_total[0] * inv_S : 0.0f) + (g_scale ? g_scale[0] : 0.0f);
+    const float up = add_rn(g_total ? mul_rn(g_total[0], inv_S) : 0.0f, g_scale ? g_scale[0] : 0.0f);
     const float* g = G_full + (size_t)b * H * W;
     float acc;
     if (R == 1) {
@@ -727,11 +729,11 @@ disp_grad_kernel(const float* __restrict__ G_full, const float* __restrict__ gN,
     float sm = 0.0f;
     if (gN) {
         const float inv_m = img_scalars[b * 2], corr = img_scalars[b * 2 + 1];
-        sm = smooth_weight * (gN[(size_t)b * h * w + (size_t)y * w + x] * inv_m - corr);
+        sm = mul_rn(smooth_weight, fmaf(gN[(size_t)b * h * w + (size_t)y * w + x], inv_m, -corr));
     }
     // g_smooth: separate upstream weight of the smoothness term (depth-hints objective: the photometric
     // gradients arrive already weighted by their masked-mean denominators)
-    grad[(size_t)b * h * w + (size_t)y * w + x] = g_smooth ? fmaf(g_smooth[0], sm, up * acc) : up * (acc + sm);
+    grad[(size_t)b * h * w + (size_t)y * w + x] = g_smooth ? fmaf(g_smooth[0], sm, mul_rn(up, acc)) : mul_rn(up, add_rn(acc, sm));
 }
 
 }  // namespace
