@@ -458,20 +458,17 @@ SINGLE_VIA_MF = _os.environ.get("DMH_SINGLE_VIA_MF", "0") == "1"
 # 1.835 ms at 32 items, 0.276 vs 0.267 ms at 4 items per GPU; the merged backward is 30 us slower at 32 items.
 SMOOTH_MULTI = _os.environ.get("DMH_SMOOTH_MULTI", "0") != "0"
 DGRAD_MULTI = _os.environ.get("DMH_DGRAD_MULTI", "0") != "0"
-# per-scale glue launches as independent branches: DMH_GLUE_STREAMS = number of side streams the S smoothness chains
-# (mean -> main) and the S backward launches are spread over (1: one high-priority stream for the smoothness, the
-# backward alternating two streams -- the round-2 schedule)
-GLUE_STREAMS = max(1, int(_os.environ.get("DMH_GLUE_STREAMS", "1")))
+# (spreading the per-scale glue launches over 2 / 4 side streams instead of 1 + 2 was measured too: no change at 32
+# items, within the +-1.5 % run-to-run noise at 4 items per GPU -- not kept)
 
 
 _SMOOTH_PRIORITY = int(_os.environ.get("DMH_SMOOTH_PRIORITY", "-1"))    # development switch
 
 
-def _side_stream(dev, which=0, n=0):
-    """Side streams of a device, created once: which 0 = high priority (smoothness launches), 1 = normal priority;
-    n = index within the kind (DMH_GLUE_STREAMS > 1)."""
+def _side_stream(dev, which=0):
+    """Side streams of a device, created once: 0 = high priority (smoothness launches), 1 = normal priority."""
     idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    key = (idx, which, n)
+    key = (idx, which)
     st = _SIDE_STREAMS.get(key)
     if st is None:
         st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx, priority=_SMOOTH_PRIORITY if which == 0 else 0)
@@ -568,17 +565,10 @@ class _Objective(torch.autograd.Function):
                                                  (_C.c_int * S)(*[d.shape[3] for d in disps]), ptr_array(wss),
                                                  ptr_array(gN), stream()), "smooth_fused_multi")
             else:
-                # (GLUE_STREAMS > 1: scale s on side stream s % GLUE_STREAMS, forked from and joined into `side`)
                 for s in range(S):
                     d = disps[s]
-                    st_s = _side_stream(dev, 0, s % GLUE_STREAMS)
-                    if st_s is not side:
-                        st_s.wait_stream(side)
-                    with torch.cuda.stream(st_s):
-                        check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]),
-                                                   ptr(gN[s]), stream()), "smooth_fused")
-                for n in range(1, min(GLUE_STREAMS, S)):
-                    side.wait_stream(_side_stream(dev, 0, n))
+                    check(lib.dmh_smooth_fused(ptr(d), ptr(colors[s]), B, 3, d.shape[2], d.shape[3], ptr(wss[s]),
+                                               ptr(gN[s]), stream()), "smooth_fused")
         # the per-scale launches are independent of each other: odd scales go to a second stream so that the
         # tail of one launch (10240 CTAs = 23.06 waves of 444) overlaps the head of the next
         multiscale = (packed and MULTISCALE and not split and S <= 4 and W % 4 == 0 and target.data_ptr() % 16 == 0
@@ -699,24 +689,19 @@ class _Objective(torch.autograd.Function):
             elif rc != _lib.ERR_UNSUPPORTED:
                 check(rc, "disp_grad_multi")
         if not grads_disp:
-            nst = max(2, GLUE_STREAMS)
-            alts = [cur] + [_side_stream(dev, 1, n) for n in range(nst - 1)]
-            for a_ in alts[1:]:
-                a_.wait_stream(cur)
+            alt.wait_stream(cur)
             for s in range(S):
                 if not want[s]:
                     grads_disp.append(None)
                     continue
                 _, _, h, w = dshapes[s]
                 gd = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
-                st_s = alts[s % nst]
-                with torch.cuda.stream(st_s):
+                with torch.cuda.stream(alt if (s & 1) else cur):
                     check(lib.dmh_disp_grad(ptr(G[s]), ptr(gN[s]), ptr(img_scalars[s]), smooth_w[s], ptr(gt),
                                             ptr(gs[s:s + 1]) if gs is not None else None, None, 1.0 / S, B, h, w, H, W,
                                             ptr(gd), stream()), "disp_grad")
                 grads_disp.append(gd.view(dshapes[s]))
-            for a_ in alts[1:]:
-                cur.wait_stream(a_)
+            cur.wait_stream(alt)
         g_T = [None] * n_src
         if need_T and ctx.gp_stacked:
             # multi-source kernel: sum over tiles and weighted sum over scales in one contraction, then the 4x4
