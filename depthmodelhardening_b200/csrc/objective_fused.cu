@@ -879,7 +879,8 @@ int dmh_disp_grad_multi(int S, const float* const* G_full_host, const float* con
     long long blocks = 0;
     for (int s = 0; s < S; ++s) {
         const int h = h_host[s], w = w_host[s];
-        DMH_REQUIRE(G_full_host[s] && grad_disp_host[s] && h >= 1 && w >= 1 && H >= h && W >= w,
+        DMH_REQUIRE(G_full_host[s] && grad_disp_host[s] && h >= 1 && w >= 1 && H >= h && W >= w &&
+                        (long long)H * W < (1ll << 31),
                     "dmh_disp_grad_multi: scale %d: null buffer or bad shape", s);
         const float* gn = gN_host ? gN_host[s] : nullptr;
         DMH_REQUIRE(!gn || (img_scalars_host && img_scalars_host[s]), "dmh_disp_grad_multi: gN given without img_scalars");
