@@ -20,6 +20,11 @@
 //   sample: grid_sample(bilinear, zeros, align_corners=False) (:545-561)
 //   resize: F.interpolate(bilinear, antialias=True, align_corners=False)
 //           (ATen UpSample.cuh upsample_antialias::_compute_weights*)
+#include <stdlib.h>
+
+#include <mutex>
+#include <vector>
+
 #include "../../include/dmh_b200.h"
 #include "dmh_common.cuh"
 
@@ -336,15 +341,30 @@ __device__ __forceinline__ AaSpan3 aa_span3(int i, int in_size, float scale) {
     return s;
 }
 
-template <int PITCH, int ROWS>
+// The anti-aliasing spans of every output column and row, evaluated ONCE per (sizes, device) instead of by every CTA:
+// tab[ox] (ox < ow) and tab[ow + oy] = (span start as an int bit pattern, w0, w1, w2) = aa_span3 of that index.
+__global__ void aa_table_kernel(int ih, int iw, int oh, int ow, float sy, float sx, float4* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ow + oh) return;
+    const AaSpan3 s = i < ow ? aa_span3(i, iw, sx) : aa_span3(i - ow, ih, sy);
+    tab[i] = make_float4(__int_as_float(s.lo), s.w[0], s.w[1], s.w[2]);
+}
+
+// TAB: the weight tables of the tile are read from `aa_tab` (aa_table_kernel) instead of computed -- the same values
+// CPL = 2: a lane stages two adjacent scene columns with 64-bit loads / stores; the tile then starts on an EVEN canvas
+// column (one column further left when the span start is odd), which needs iw and ih * iw even, 8-byte aligned scenes
+// and a tile pitch that holds one more column (checked by the launcher)
+template <int PITCH, int ROWS, bool TAB = false, int CPL = 1>
 __global__ void __launch_bounds__(PA_THREADS)
 patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
                         const float* __restrict__ scenes, const float* __restrict__ coeffs,
                         const int* __restrict__ bbox, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
-                        int t_pad, float sy, float sx, float* __restrict__ adv, float* __restrict__ mask_out) {
+                        int t_pad, float sy, float sx, float* __restrict__ adv, float* __restrict__ mask_out,
+                        const float4* __restrict__ aa_tab) {
     extern __shared__ float smem[];
     constexpr int PLANE = PITCH * ROWS;
-    constexpr int NCU = (PITCH + 31) / 32, NRU = (ROWS + 7) / 8;
+    constexpr int NCU = (PITCH + 32 * CPL - 1) / (32 * CPL), NRU = (ROWS + 7) / 8;
+    static_assert(CPL == 1 || (CPL == 2 && PITCH % 2 == 0), "CPL: 1 or 2 (even pitch)");
     float* comp = smem;                                   // [4][ROWS][PITCH] : 3 colour planes + mask
     __shared__ int x_lo[PA_TW], y_lo[PA_TH];
     __shared__ float x_w[PA_TW][3];
@@ -357,26 +377,52 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
     // tile geometry from the span starts alone (every thread, no shared memory): the scene loads are issued
     // BEFORE the weights are tabulated, so their latency overlaps that phase
     const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
-    const int cx0 = aa_span_lo(ox0, sx), cy0 = aa_span_lo(oy0, sy);
+    const int cx0 = CPL == 2 ? (aa_span_lo(ox0, sx) & ~1) : aa_span_lo(ox0, sx), cy0 = aa_span_lo(oy0, sy);
     const int cw = min(min(aa_span_lo(ox0 + last_x, sx) + 3, iw) - cx0, PITCH);
     const int ch = min(min(aa_span_lo(oy0 + last_y, sy) + 3, ih) - cy0, ROWS);
     const int IN = ih * iw;
     const float* sc = scenes + (size_t)b * 3 * IN + cx0;
     // a warp takes tile rows wid, wid+8, ..., its lanes the columns lane, lane+32, ...: all loads in flight at once
     const int lane = tid & 31, wid = tid >> 5;
-    float sv[NRU][NCU][3];
+    float sv[NRU][NCU][3][CPL];
 #pragma unroll
     for (int ru = 0; ru < NRU; ++ru) {
         const int r = wid + 8 * ru;
         const float* srow = sc + (cy0 + min(r, ch - 1)) * iw;
 #pragma unroll
         for (int u = 0; u < NCU; ++u) {
-            const int c = 32 * u + lane;
+            const int c = CPL * (32 * u + lane);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sv[ru][u][k] = (r < ch && c < cw) ? __ldg(srow + k * IN + c) : 0.f;
+            for (int k = 0; k < 3; ++k) {
+                if (CPL == 2) {
+                    // (cx0 + c even and < iw, iw even: the pair lies inside the row)
+                    float2 v = make_float2(0.f, 0.f);
+                    if (r < ch && c < cw) v = __ldg(reinterpret_cast<const float2*>(srow + k * IN + c));
+                    sv[ru][u][k][0] = v.x;
+                    sv[ru][u][k][CPL - 1] = (c + 1 < cw) ? v.y : 0.f;
+                } else {
+                    sv[ru][u][k][0] = (r < ch && c < cw) ? __ldg(srow + k * IN + c) : 0.f;
+                }
+            }
         }
     }
-    if (tid < PA_TW) {
+    if (TAB) {
+        if (tid < PA_TW) {
+            const float4 t = __ldg(aa_tab + min(ox0 + tid, ow - 1));
+            x_lo[tid] = __float_as_int(t.x);
+            x_w[tid][0] = t.y; x_w[tid][1] = t.z; x_w[tid][2] = t.w;
+        } else if (tid < PA_TW + PA_TH) {
+            const int k = tid - PA_TW;
+            y_lo[k] = __float_as_int(__ldg(aa_tab + ow + min(oy0 + k, oh - 1)).x);
+        } else if (tid < PA_TW + PA_TH + 32 * (PA_TH / 4)) {
+            const int t = tid - (PA_TW + PA_TH);
+            const int q = t >> 5, i = (t & 31) >> 2, k = t & 3;
+            const float4 e = __ldg(aa_tab + ow + min(oy0 + 4 * q + k, oh - 1));
+            const int lo0 = __float_as_int(__ldg(aa_tab + ow + min(oy0 + 4 * q, oh - 1)).x);
+            const int d = i - (__float_as_int(e.x) - lo0);
+            reinterpret_cast<float*>(&wy4[q][i])[k] = d == 0 ? e.y : (d == 1 ? e.z : (d == 2 ? e.w : 0.0f));
+        }
+    } else if (tid < PA_TW) {
         const AaSpan3 s = aa_span3(min(ox0 + tid, ow - 1), iw, sx);
         x_lo[tid] = s.lo;
 #pragma unroll
@@ -408,10 +454,15 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
             float* crow = comp + r * PITCH;
 #pragma unroll
             for (int u = 0; u < NCU; ++u) {
-                const int c = 32 * u + lane;
+                const int c = CPL * (32 * u + lane);
                 if (c < cwz) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) crow[k * PLANE + c] = sv[ru][u][k];
+                    for (int k = 0; k < 3; ++k) {
+                        if (CPL == 2)
+                            *reinterpret_cast<float2*>(crow + k * PLANE + c) = make_float2(sv[ru][u][k][0], sv[ru][u][k][CPL - 1]);
+                        else
+                            crow[k * PLANE + c] = sv[ru][u][k][0];
+                    }
                 }
             }
         }
@@ -425,8 +476,9 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
             const int cy = cy0 + r;
             float* crow = comp + r * PITCH;
 #pragma unroll
-            for (int u = 0; u < NCU; ++u) {
-                const int c = 32 * u + lane;
+            for (int ue = 0; ue < NCU * CPL; ++ue) {
+                const int u = ue / CPL, e = ue % CPL;
+                const int c = CPL * (32 * u + lane) + e;
                 if (c >= cwz) continue;
                 const int cx = cx0 + c;
                 float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
@@ -442,9 +494,9 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
                     }
                 }
                 const float om = sub_rn(1.0f, m);
-                crow[c] = add_rn(mul_rn(sv[ru][u][0], om), mul_rn(o0, m));
-                crow[PLANE + c] = add_rn(mul_rn(sv[ru][u][1], om), mul_rn(o1, m));
-                crow[2 * PLANE + c] = add_rn(mul_rn(sv[ru][u][2], om), mul_rn(o2, m));
+                crow[c] = add_rn(mul_rn(sv[ru][u][0][e], om), mul_rn(o0, m));
+                crow[PLANE + c] = add_rn(mul_rn(sv[ru][u][1][e], om), mul_rn(o1, m));
+                crow[2 * PLANE + c] = add_rn(mul_rn(sv[ru][u][2][e], om), mul_rn(o2, m));
                 crow[3 * PLANE + c] = m;
             }
         }
@@ -777,6 +829,52 @@ static int aa_tile_extent(int tile, float scale) {
     return (int)(scale * tile + 2.0f * support + 3.0f);
 }
 
+}  // extern "C"
+
+namespace {
+// Weight tables of the 3-tap forward kernel, one per (device, sizes), built on first use: a 20 KB allocation and one
+// small launch on a private stream, waited for once.  Never built while the caller's stream is being captured (an
+// allocation would invalidate the capture): the kernel then computes its weights itself, as it does when the table
+// cannot be built -- same values either way.  DMH_AA_TABLE=0 disables the table.
+struct AaTabEntry { int dev, ih, iw, oh, ow; float4* tab; };
+std::mutex g_aa_mu;
+std::vector<AaTabEntry> g_aa_tabs;
+
+const float4* aa_table_get(int ih, int iw, int oh, int ow, float sy, float sx, cudaStream_t st) {
+    static const bool enabled = [] { const char* e = getenv("DMH_AA_TABLE"); return !(e && atoi(e) == 0); }();
+    if (!enabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_aa_mu);
+    for (const AaTabEntry& e : g_aa_tabs)
+        if (e.dev == dev && e.ih == ih && e.iw == iw && e.oh == oh && e.ow == ow) return e.tab;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    float4* tab = nullptr;
+    cudaStream_t priv = nullptr;
+    bool ok = cudaMalloc(&tab, sizeof(float4) * (size_t)(ow + oh)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&priv, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) {
+        count_launches(1);
+        aa_table_kernel<<<ceil_div(ow + oh, 256), 256, 0, priv>>>(ih, iw, oh, ow, sy, sx, tab);
+        ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(priv) == cudaSuccess;
+    }
+    if (priv) cudaStreamDestroy(priv);
+    if (!ok) {
+        if (tab) cudaFree(tab);
+        cudaGetLastError();
+        return nullptr;
+    }
+    g_aa_tabs.push_back(AaTabEntry{dev, ih, iw, oh, ow, tab});
+    return tab;
+}
+}  // namespace
+
+extern "C" {
+
 int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs,
                         const int* bbox, int B, int ph, int pw, int ih, int iw, int oh, int ow, float* adv,
                         float* mask_out, dmh_stream_t stream) {
@@ -814,12 +912,24 @@ int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float
             }
             configured[dev & 63] = true;
         }
-        if (small)
+        const float4* tab = small ? aa_table_get(ih, iw, oh, ow, sy, sx, (cudaStream_t)stream) : nullptr;
+        // 64-bit staging (DMH_PATCH_VEC=0 disables): even row length / plane size, aligned scenes, room for one more column
+        static const bool vec_on = [] { const char* e = getenv("DMH_PATCH_VEC"); return !(e && atoi(e) == 0); }();
+        const bool vec = vec_on && iw % 2 == 0 && ((long long)ih * iw) % 2 == 0 && (uintptr_t)scenes % 8 == 0 && cw_max + 1 <= 84;
+        if (small && tab && vec)
+            DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24, true, 2>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out, tab);
+        else if (small && tab)
+            DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24, true>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out, tab);
+        else if (small)
             DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
-                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out);
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out,
+                nullptr);
         else
             DMH_LAUNCH((patch_apply_fwd3_kernel<104, 30>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
-                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out);
+                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out,
+                nullptr);
     } else if (sy < 1.5f && sx < 1.5f)
         DMH_LAUNCH(patch_apply_fwd_kernel<3>, grid, PA_THREADS, smem, (cudaStream_t)stream)(
             patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, cw_max, ch_max, adv,
