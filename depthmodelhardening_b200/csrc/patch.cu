@@ -355,7 +355,7 @@ __global__ void aa_table_kernel(int ih, int iw, int oh, int ow, float sy, float 
 // column (one column further left when the span start is odd), which needs iw and ih * iw even, 8-byte aligned scenes
 // and a tile pitch that holds one more column (checked by the launcher)
 template <int PITCH, int ROWS, bool TAB = false, int CPL = 1>
-__global__ void __launch_bounds__(PA_THREADS)
+__global__ void __launch_bounds__(PA_THREADS, (PITCH <= 84 ? 4 : 3))
 patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
                         const float* __restrict__ scenes, const float* __restrict__ coeffs,
                         const int* __restrict__ bbox, int ph, int pw, int ih, int iw, int oh, int ow, int l_pad,
