@@ -351,10 +351,9 @@ __global__ void aa_table_kernel(int ih, int iw, int oh, int ow, float sy, float 
 }
 
 // TAB: the weight tables of the tile are read from `aa_tab` (aa_table_kernel) instead of computed -- the same values
-// CPL = 2: a lane stages two adjacent scene columns with 64-bit loads / stores; the tile then starts on an EVEN canvas
-// column (one column further left when the span start is odd), which needs iw and ih * iw even, 8-byte aligned scenes
-// and a tile pitch that holds one more column (checked by the launcher)
-template <int PITCH, int ROWS, bool TAB = false, int CPL = 1>
+// (Staging two adjacent scene columns per lane with 64-bit loads / stores from an even tile start was built and measured
+// too: 112 us against 99 us -- the wider accesses leave a third of the lanes idle in the second column group; removed.)
+template <int PITCH, int ROWS, bool TAB = false>
 __global__ void __launch_bounds__(PA_THREADS, (PITCH <= 84 ? 4 : 3))
 patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict__ pmask,
                         const float* __restrict__ scenes, const float* __restrict__ coeffs,
@@ -363,8 +362,7 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
                         const float4* __restrict__ aa_tab) {
     extern __shared__ float smem[];
     constexpr int PLANE = PITCH * ROWS;
-    constexpr int NCU = (PITCH + 32 * CPL - 1) / (32 * CPL), NRU = (ROWS + 7) / 8;
-    static_assert(CPL == 1 || (CPL == 2 && PITCH % 2 == 0), "CPL: 1 or 2 (even pitch)");
+    constexpr int NCU = (PITCH + 31) / 32, NRU = (ROWS + 7) / 8;
     float* comp = smem;                                   // [4][ROWS][PITCH] : 3 colour planes + mask
     __shared__ int x_lo[PA_TW], y_lo[PA_TH];
     __shared__ float x_w[PA_TW][3];
@@ -377,33 +375,23 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
     // tile geometry from the span starts alone (every thread, no shared memory): the scene loads are issued
     // BEFORE the weights are tabulated, so their latency overlaps that phase
     const int last_x = min(PA_TW, ow - ox0) - 1, last_y = min(PA_TH, oh - oy0) - 1;
-    const int cx0 = CPL == 2 ? (aa_span_lo(ox0, sx) & ~1) : aa_span_lo(ox0, sx), cy0 = aa_span_lo(oy0, sy);
+    const int cx0 = aa_span_lo(ox0, sx), cy0 = aa_span_lo(oy0, sy);
     const int cw = min(min(aa_span_lo(ox0 + last_x, sx) + 3, iw) - cx0, PITCH);
     const int ch = min(min(aa_span_lo(oy0 + last_y, sy) + 3, ih) - cy0, ROWS);
     const int IN = ih * iw;
     const float* sc = scenes + (size_t)b * 3 * IN + cx0;
     // a warp takes tile rows wid, wid+8, ..., its lanes the columns lane, lane+32, ...: all loads in flight at once
     const int lane = tid & 31, wid = tid >> 5;
-    float sv[NRU][NCU][3][CPL];
+    float sv[NRU][NCU][3];
 #pragma unroll
     for (int ru = 0; ru < NRU; ++ru) {
         const int r = wid + 8 * ru;
         const float* srow = sc + (cy0 + min(r, ch - 1)) * iw;
 #pragma unroll
         for (int u = 0; u < NCU; ++u) {
-            const int c = CPL * (32 * u + lane);
+            const int c = 32 * u + lane;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (CPL == 2) {
-                    // (cx0 + c even and < iw, iw even: the pair lies inside the row)
-                    float2 v = make_float2(0.f, 0.f);
-                    if (r < ch && c < cw) v = __ldg(reinterpret_cast<const float2*>(srow + k * IN + c));
-                    sv[ru][u][k][0] = v.x;
-                    sv[ru][u][k][CPL - 1] = (c + 1 < cw) ? v.y : 0.f;
-                } else {
-                    sv[ru][u][k][0] = (r < ch && c < cw) ? __ldg(srow + k * IN + c) : 0.f;
-                }
-            }
+            for (int k = 0; k < 3; ++k) sv[ru][u][k] = (r < ch && c < cw) ? __ldg(srow + k * IN + c) : 0.f;
         }
     }
     if (TAB) {
@@ -454,15 +442,10 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
             float* crow = comp + r * PITCH;
 #pragma unroll
             for (int u = 0; u < NCU; ++u) {
-                const int c = CPL * (32 * u + lane);
+                const int c = 32 * u + lane;
                 if (c < cwz) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        if (CPL == 2)
-                            *reinterpret_cast<float2*>(crow + k * PLANE + c) = make_float2(sv[ru][u][k][0], sv[ru][u][k][CPL - 1]);
-                        else
-                            crow[k * PLANE + c] = sv[ru][u][k][0];
-                    }
+                    for (int k = 0; k < 3; ++k) crow[k * PLANE + c] = sv[ru][u][k];
                 }
             }
         }
@@ -476,9 +459,8 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
             const int cy = cy0 + r;
             float* crow = comp + r * PITCH;
 #pragma unroll
-            for (int ue = 0; ue < NCU * CPL; ++ue) {
-                const int u = ue / CPL, e = ue % CPL;
-                const int c = CPL * (32 * u + lane) + e;
+            for (int u = 0; u < NCU; ++u) {
+                const int c = 32 * u + lane;
                 if (c >= cwz) continue;
                 const int cx = cx0 + c;
                 float m = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f;
@@ -494,9 +476,9 @@ patch_apply_fwd3_kernel(const float* __restrict__ patch, const float* __restrict
                     }
                 }
                 const float om = sub_rn(1.0f, m);
-                crow[c] = add_rn(mul_rn(sv[ru][u][0][e], om), mul_rn(o0, m));
-                crow[PLANE + c] = add_rn(mul_rn(sv[ru][u][1][e], om), mul_rn(o1, m));
-                crow[2 * PLANE + c] = add_rn(mul_rn(sv[ru][u][2][e], om), mul_rn(o2, m));
+                crow[c] = add_rn(mul_rn(sv[ru][u][0], om), mul_rn(o0, m));
+                crow[PLANE + c] = add_rn(mul_rn(sv[ru][u][1], om), mul_rn(o1, m));
+                crow[2 * PLANE + c] = add_rn(mul_rn(sv[ru][u][2], om), mul_rn(o2, m));
                 crow[3 * PLANE + c] = m;
             }
         }
@@ -913,13 +895,7 @@ int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float
             configured[dev & 63] = true;
         }
         const float4* tab = small ? aa_table_get(ih, iw, oh, ow, sy, sx, (cudaStream_t)stream) : nullptr;
-        // 64-bit staging (DMH_PATCH_VEC=0 disables): even row length / plane size, aligned scenes, room for one more column
-        static const bool vec_on = [] { const char* e = getenv("DMH_PATCH_VEC"); return !(e && atoi(e) == 0); }();
-        const bool vec = vec_on && iw % 2 == 0 && ((long long)ih * iw) % 2 == 0 && (uintptr_t)scenes % 8 == 0 && cw_max + 1 <= 84;
-        if (small && tab && vec)
-            DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24, true, 2>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
-                patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out, tab);
-        else if (small && tab)
+        if (small && tab)
             DMH_LAUNCH((patch_apply_fwd3_kernel<84, 24, true>), grid, PA_THREADS, smem3, (cudaStream_t)stream)(
                 patch, patch_mask, scenes, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, adv, mask_out, tab);
         else if (small)
