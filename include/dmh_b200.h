@@ -310,7 +310,10 @@ int dmh_perspective_bwd(const float* grad_out, const float* coeffs, int B, int C
  * bwd: grad_adv (B,3,oh,ow) -> grad_patch (3,ph,pw) accumulated (sum over the batch).
  * bbox (nullable): (B,4) int32 device array {x0,y0,x1,y1} (inclusive canvas pixels) outside of which item b
  * cannot sample the patch (host-computed from the projected corners; an optimisation hint that must be
- * conservative); bwd launches only max-bbox-sized grids (bbox_max_w/h = largest extent over the batch).  */
+ * conservative); bwd launches only max-bbox-sized grids (bbox_max_w/h = largest extent over the batch).
+ * State: the first forward call for a new (device, ih, iw, oh, ow) outside a stream capture builds a small table of
+ * resize weights (one 16 (oh+ow)-byte allocation kept for the life of the process, one launch on a private stream that
+ * is waited for); inside a capture, or if that fails, the kernel computes the same weights itself.               */
 int dmh_patch_apply_fwd(const float* patch, const float* patch_mask, const float* scenes, const float* coeffs,
                         const int* bbox, int B, int ph, int pw, int ih, int iw, int oh, int ow, float* adv,
                         float* mask_out, dmh_stream_t stream);
