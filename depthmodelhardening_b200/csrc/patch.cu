@@ -593,10 +593,22 @@ __device__ __forceinline__ float aa_weight_of(int o, int in_size, float scale, i
     return total != 0.f ? mine / total : mine;
 }
 
+// weight with which output index o reads input index ci, from the span table (aa_table_kernel: 3-tap spans, both
+// scale factors < 1.5): the value aa_weight_of computes, bit for bit
+__device__ __forceinline__ float aa_weight_tab(const float4* __restrict__ tab, int o, int ci) {
+    const float4 e = __ldg(tab + o);
+    const int d = ci - __float_as_int(e.x);
+    return d == 0 ? e.y : (d == 1 ? e.z : (d == 2 ? e.w : 0.f));
+}
+
+// TAB: resize weights from the span table (aa_tab: columns, then rows) instead of ~12 evaluations of aa_weight_of per
+// pixel -- three quarters of this kernel's instructions
+template <bool TAB>
 __global__ void __launch_bounds__(256)
 patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__ pmask,
                        const float* __restrict__ coeffs, const int* __restrict__ bbox, int ph, int pw, int ih, int iw,
-                       int oh, int ow, int l_pad, int t_pad, float sy, float sx, float* __restrict__ gpatch) {
+                       int oh, int ow, int l_pad, int t_pad, float sy, float sx, float* __restrict__ gpatch,
+                       const float4* __restrict__ aa_tab) {
     const int b = blockIdx.z;
     int cx = blockIdx.x * blockDim.x + threadIdx.x;
     int cy = blockIdx.y * blockDim.y + threadIdx.y;
@@ -627,9 +639,10 @@ patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__
     constexpr int MAXO = 8;
     float wxv[MAXO];
 #pragma unroll
-    for (int i = 0; i < MAXO; ++i) wxv[i] = (ox_a + i <= ox_b) ? aa_weight_of(ox_a + i, iw, sx, cx) : 0.f;
+    for (int i = 0; i < MAXO; ++i)
+        wxv[i] = (ox_a + i <= ox_b) ? (TAB ? aa_weight_tab(aa_tab, ox_a + i, cx) : aa_weight_of(ox_a + i, iw, sx, cx)) : 0.f;
     for (int oy = oy_a; oy <= oy_b; ++oy) {
-        const float wy = aa_weight_of(oy, ih, sy, cy);
+        const float wy = TAB ? aa_weight_tab(aa_tab + ow, oy, cy) : aa_weight_of(oy, ih, sy, cy);
         if (wy == 0.f) continue;
         const float* grow = g + (size_t)oy * ow + ox_a;
 #pragma unroll
@@ -643,10 +656,10 @@ patch_apply_bwd_kernel(const float* __restrict__ gadv, const float* __restrict__
     }
     // windows wider than MAXO (up-scaling by more than ~1.3x): the remaining columns, weight by weight
     for (int ox = ox_a + MAXO; ox <= ox_b; ++ox) {
-        const float wx = aa_weight_of(ox, iw, sx, cx);
+        const float wx = TAB ? aa_weight_tab(aa_tab, ox, cx) : aa_weight_of(ox, iw, sx, cx);
         if (wx == 0.f) continue;
         for (int oy = oy_a; oy <= oy_b; ++oy) {
-            const float w = aa_weight_of(oy, ih, sy, cy) * wx;
+            const float w = (TAB ? aa_weight_tab(aa_tab + ow, oy, cy) : aa_weight_of(oy, ih, sy, cy)) * wx;
             if (w == 0.f) continue;
             const size_t oo = (size_t)oy * ow + ox;
             gc[0] = fmaf(w, __ldg(g + oo), gc[0]);
@@ -930,8 +943,14 @@ int dmh_patch_apply_bwd(const float* grad_adv, const float* patch_mask, const fl
     DMH_REQUIRE(!bbox || (bbox_max_w > 0 && bbox_max_h > 0), "dmh_patch_apply_bwd: bbox given without its max extent");
     const int gw = bbox ? (bbox_max_w < iw ? bbox_max_w : iw) : iw, gh = bbox ? (bbox_max_h < ih ? bbox_max_h : ih) : ih;
     dim3 block(32, 8), grid(ceil_div(gw, 32), ceil_div(gh, 8), B);
-    DMH_LAUNCH(patch_apply_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(grad_adv, patch_mask, coeffs, bbox, ph, pw, ih, iw,
-                                                                          oh, ow, l_pad, t_pad, sy, sx, grad_patch);
+    // the span table of the 3-tap forward kernel serves the backward too (same cache; nullptr: weights computed in place)
+    const float4* tab = (sy < 1.5f && sx < 1.5f) ? aa_table_get(ih, iw, oh, ow, sy, sx, (cudaStream_t)stream) : nullptr;
+    if (tab)
+        DMH_LAUNCH(patch_apply_bwd_kernel<true>, grid, block, 0, (cudaStream_t)stream)(
+            grad_adv, patch_mask, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, grad_patch, tab);
+    else
+        DMH_LAUNCH(patch_apply_bwd_kernel<false>, grid, block, 0, (cudaStream_t)stream)(
+            grad_adv, patch_mask, coeffs, bbox, ph, pw, ih, iw, oh, ow, l_pad, t_pad, sy, sx, grad_patch, nullptr);
     DMH_CHECK_LAUNCH("dmh_patch_apply_bwd");
     return DMH_OK;
 }
